@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (amcolex/ofdm-sync-math).
+
+TEST INFRASTRUCTURE ONLY.  Runs in the build container (where /root/reference is mounted);
+the produced fixtures are committed so that the GPU box (which has no /root/reference) can
+pin both the oracle (oracle/) and the CUDA path against real reference outputs.
+
+How values are captured: the reference modules are imported unmodified behind a matplotlib
+stub (oracle/refshim) and each script's own `run_simulation()` is executed; a `sys.setprofile`
+hook grabs the local variables of `run_simulation` at return, so every array stored here was
+computed by reference code (sc.py:159-368, minn.py:300-653, park.py:123-348,
+combined_sc_min.py:272-580, zc.py:57-283, zc_v2.py:522-787, zc_freq.py:102-290,
+minn_rtl.py:849-1100).  sync_aa / minn_rtl function-level cases call the reference functions
+directly on inputs built with the reference's own builders.
+
+Usage:  python oracle/gen_golden.py [--ref /root/reference] [--out tests/golden]
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+
+
+def _setup(ref: str) -> None:
+    sys.path.insert(0, str(HERE / "refshim"))
+    sys.path.insert(0, ref)
+    sys.path.insert(0, str(Path(ref) / "ref"))
+    os.chdir(tempfile.mkdtemp(prefix="ofs_golden_"))  # scripts mkdir plots/ under cwd
+
+
+def _run_capture(module, fn_name: str, args: tuple) -> dict:
+    """Run module.fn_name(*args) and return a copy of its locals at return."""
+    captured: dict = {}
+    target_code = getattr(module, fn_name).__code__
+
+    def prof(frame, event, _arg):
+        if event == "return" and frame.f_code is target_code:
+            captured.update(frame.f_locals)
+
+    sys.setprofile(prof)
+    try:
+        getattr(module, fn_name)(*args)
+    finally:
+        sys.setprofile(None)
+    return captured
+
+
+def _segments(mask: np.ndarray) -> np.ndarray:
+    m = np.asarray(mask, dtype=bool)
+    d = np.diff(np.concatenate(([0], m.astype(np.int8), [0])))
+    return np.stack([np.flatnonzero(d == 1), np.flatnonzero(d == -1)], axis=1).astype(np.int64)
+
+
+SCEN = [("cir1", "measured_channel"), (None, "flat_awgn")]
+
+
+def gen_sc(out: Path) -> None:
+    import sc
+    for ch, sub in SCEN:
+        loc = _run_capture(sc, "run_simulation", (ch, sub))
+        tag = ch or "awgn"
+        np.savez_compressed(
+            out / f"sc_{tag}.npz",
+            rx=loc["rx_samples"], M=loc["M"], P=loc["P_sum"], R=loc["R_sum"],
+            plateau_end=np.int64(loc["plateau_end"]), coarse_start=np.int64(loc["coarse_start"]),
+            cp_len=np.int64(sc.CYCLIC_PREFIX), lookahead=np.int64(sc.CYCLIC_PREFIX // 4),
+            smooth_win=np.int64(sc.SMOOTH_WIN), sc_delta=np.int64(sc.SC_DELTA),
+            cfo_est_hz=np.float64(loc.get("cfo_est_hz", np.nan)),
+        )
+        print("sc", tag, int(loc["plateau_end"]), int(loc["coarse_start"]))
+
+
+def gen_minn(out: Path) -> None:
+    import minn
+    for ch, sub in SCEN:
+        loc = _run_capture(minn, "run_simulation", (ch, sub))
+        tag = ch or "awgn"
+        np.savez_compressed(
+            out / f"minn_{tag}.npz",
+            rx=loc["rx_samples"], M=loc["M"], P=loc["P_sum"], R=loc["R_sum"],
+            peak=np.int64(loc["peak_position"]), gate=_segments(loc["minn_gate_mask"]),
+            Ms=loc["M_smooth"], smooth_win=np.int64(minn.SMOOTH_WIN),
+            gate_threshold=np.float64(minn.MINN_GATE_THRESHOLD),
+        )
+        print("minn", tag, int(loc["peak_position"]), _segments(loc["minn_gate_mask"]).tolist())
+    # parameterised symbol length on a short random input (minn.py:697-751)
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((2, 1500)) + 1j * rng.standard_normal((2, 1500))
+    d = {"rx": x}
+    for n in (64, 100, 256, 1024):
+        M, P, R = minn.minn_streaming_metric_parameterized(x, n)
+        d[f"M_{n}"], d[f"P_{n}"], d[f"R_{n}"] = M, P, R
+    np.savez_compressed(out / "minn_param.npz", **d)
+
+
+def gen_park(out: Path) -> None:
+    import park
+    for ch, sub in SCEN:
+        loc = _run_capture(park, "run_simulation", (ch, sub))
+        tag = ch or "awgn"
+        np.savez_compressed(
+            out / f"park_{tag}.npz",
+            rx=loc["rx_samples"], ds=loc["ds"], M=loc["M"], P=loc["P_sum"], E=loc["E_sum"],
+            det_center=np.int64(loc["det_center"]), det_symbol_start=np.int64(loc["det_symbol_start"]),
+        )
+        print("park", tag, int(loc["det_center"]), int(loc["det_symbol_start"]))
+
+
+def gen_combined(out: Path) -> None:
+    import combined_sc_min as c
+    for ch, sub in SCEN:
+        loc = _run_capture(c, "run_simulation", (ch, sub))
+        tag = ch or "awgn"
+        np.savez_compressed(
+            out / f"combined_{tag}.npz",
+            rx=loc["rx_samples"], M=loc["M"], P=loc["P_sum"], R=loc["R_sum"],
+            M_sc=loc["M_sc"], P_sc=loc["P_sc"], R_sc=loc["R_sc"],
+            sc_gate=_segments(loc["sc_gate_mask"]), sc_gate_span=np.asarray(loc["sc_gate_span"], dtype=np.int64),
+            peak=np.int64(loc["peak_position"]), smooth_win=np.int64(c.SMOOTH_WIN),
+            sc_gate_threshold=np.float64(c.SC_GATE_THRESHOLD),
+        )
+        print("combined", tag, int(loc["peak_position"]), loc["sc_gate_span"])
+
+
+def gen_zc(out: Path) -> None:
+    import zc
+    for ch, sub in SCEN:
+        loc = _run_capture(zc, "run_simulation", (ch, sub))
+        tag = ch or "awgn"
+        np.savez_compressed(
+            out / f"zc_{tag}.npz",
+            rx=loc["rx_samples"], ref=loc["pss_reference"], corr=loc["combined_corr"],
+            peak=np.int64(loc["peak_index"]), start=np.int64(loc["detected_start"]),
+        )
+        print("zc", tag, int(loc["peak_index"]), int(loc["detected_start"]))
+
+
+def gen_zc_v2(out: Path) -> None:
+    import zc_v2
+    for ch, sub in SCEN:
+        loc = _run_capture(zc_v2, "run_simulation", (ch, sub))
+        tag = ch or "awgn"
+        res = loc["result"]
+        st = res.state
+        ev = np.array(
+            [[e.peak_index, e.gate_start, e.gate_end, e.detected_start] for e in res.events], dtype=np.int64
+        ).reshape(-1, 4)
+        evv = np.array([e.peak_value for e in res.events], dtype=np.float64)
+        np.savez_compressed(
+            out / f"zc_v2_{tag}.npz",
+            rx=loc["rx_samples"], ref=zc_v2.build_pss_symbol(include_cp=False),
+            corr_mag=st.corr_mag, local_sum=st.local_sum, above=st.above_threshold,
+            valid=st.metric_valid, gate=_segments(res.gate_mask), events=ev, event_values=evv,
+            window_size=np.int64(zc_v2.CORR_WINDOW_SIZE), thresh_value=np.int64(zc_v2.THRESH_VALUE),
+            thresh_frac_bits=np.int64(zc_v2.THRESH_FRAC_BITS), min_corr_mag=np.float64(zc_v2.MIN_CORR_MAG),
+            hysteresis=np.int64(zc_v2.HYSTERESIS),
+        )
+        print("zc_v2", tag, ev.tolist(), evv.tolist())
+
+
+def gen_zc_freq(out: Path) -> None:
+    import zc_freq
+    for ch, sub in SCEN:
+        loc = _run_capture(zc_freq, "run_simulation", (ch, sub))
+        tag = ch or "awgn"
+        np.savez_compressed(
+            out / f"zc_freq_{tag}.npz",
+            rx=loc["rx_samples"], metric=loc["metric"], peak=np.int64(loc["peak_index"]),
+            bin_indices=loc["bin_positions"], template=loc["template_bins"],
+            template_energy=np.float64(loc["template_energy"]),
+        )
+        print("zc_freq", tag, int(loc["peak_index"]))
+
+
+def _rtl_state_dict(st, det) -> dict:
+    ev = np.array(
+        [[e.peak_index, e.detected_index, e.gate_segment[0], e.gate_segment[1]] for e in det.events],
+        dtype=np.int64,
+    ).reshape(-1, 4)
+    return dict(
+        corr_total=st.corr_total, corr_positive=st.corr_positive, smooth_metric=st.smooth_metric,
+        energy_total=st.energy_total, corr_scaled=st.corr_scaled, energy_scaled=st.energy_scaled,
+        metric_valid=st.metric_valid, above=st.above_threshold, events=ev,
+        gate_segments=np.asarray(det.gate_segments, dtype=np.int64).reshape(-1, 2),
+    )
+
+
+def gen_minn_rtl(out: Path) -> None:
+    import minn_rtl as mr
+    for ch, sub in SCEN:
+        loc = _run_capture(mr, "run_simulation", (ch, sub))
+        tag = ch or "awgn"
+        d = _rtl_state_dict(loc["metric_state"], loc["detection"])
+        np.savez_compressed(
+            out / f"minn_rtl_{tag}.npz", rx=loc["rx_samples"],
+            smooth_shift=np.int64(mr.SMOOTH_SHIFT), threshold_value=np.int64(mr.THRESH_VALUE),
+            threshold_frac_bits=np.int64(mr.THRESH_FRAC_BITS), quarter_len=np.int64(mr.PREAMBLE_Q),
+            hysteresis=np.int64(mr.HYSTERESIS), timing_offset=np.int64(mr.TIMING_OFFSET), **d,
+        )
+        print("minn_rtl", tag, d["events"].tolist())
+
+    # int12-valued, 2-antenna stimulus following the cocotb recipe
+    # (ref/test_minn_preamble_detector.py:27-38,150-161,193-208) with a SEEDED data symbol
+    # (the testbench leaves it unseeded, ref/ofdm.py:115-116).
+    import ofdm
+    params = ofdm.OFDMParameters(n_fft=2048, cp_len=512)
+    preamble, _ = ofdm.generate_preamble(params=params)
+    data_symbol, _ = ofdm.generate_qpsk_symbol(params=params, rng=np.random.default_rng(0))
+    full = np.concatenate((np.zeros(256, complex), preamble, data_symbol, np.zeros(2048 + 512, complex)))
+    rng = np.random.default_rng(0)
+
+    def awgn(sig):
+        p = np.mean(np.abs(sig) ** 2)
+        npow = p / (10 ** (10.0 / 10))
+        return sig + np.sqrt(npow / 2) * (rng.standard_normal(sig.shape) + 1j * rng.standard_normal(sig.shape))
+
+    def quant(s, width=12):
+        lo, hi = -(1 << (width - 1)), (1 << (width - 1)) - 1
+        scale = (hi - 1) / np.max(np.abs(s))
+        sc_ = s * scale
+        return (np.clip(np.round(sc_.real), lo, hi).astype(np.int16),
+                np.clip(np.round(sc_.imag), lo, hi).astype(np.int16))
+
+    iq = np.zeros((2, full.size, 2), dtype=np.int16)
+    for a in range(2):
+        re, im = quant(awgn(full))
+        iq[a, :, 0], iq[a, :, 1] = re, im
+    rx = iq[..., 0].astype(np.float64) + 1j * iq[..., 1].astype(np.float64)
+    kw = dict(smooth_shift=3, threshold_value=int(0.1 * (1 << 15)), threshold_frac_bits=15, quarter_len=512)
+    st = mr.minn_rtl_streaming_metric(rx, **kw)
+    det = mr.detect_minn_rtl(st, hysteresis=2, timing_offset=0)
+    np.savez_compressed(
+        out / "minn_rtl_int12.npz", iq=iq, hysteresis=np.int64(2), timing_offset=np.int64(0),
+        **{k: np.int64(v) for k, v in kw.items()}, **_rtl_state_dict(st, det),
+    )
+    print("minn_rtl int12", _rtl_state_dict(st, det)["events"].tolist())
+
+
+def _aa_pack(res) -> dict:
+    ev_i = np.array(
+        [[e.peak_index, e.gate_start, e.gate_end, e.frame_start] for e in res.events], dtype=np.int64
+    ).reshape(-1, 4)
+    ev_f = np.array(
+        [[e.P_at_peak.real, e.P_at_peak.imag, e.M_at_peak, e.cfo_hz] for e in res.events], dtype=np.float64
+    ).reshape(-1, 4)
+    return dict(P=res.state.P, R=res.state.R, M=res.state.M, valid=res.state.valid, ev_i=ev_i, ev_f=ev_f)
+
+
+def gen_sync_aa(out: Path, ref: str) -> None:
+    import sync_aa as aa
+    # (a) the docs scenario: [500 zeros][preamble][500 zeros], 1 antenna, no noise, L=512
+    pre, _, _ = aa.build_aa_preamble(1024)
+    tx = np.concatenate([np.zeros(500, complex), pre, np.zeros(500, complex)])
+    docs = {}
+    for name, cfo in (("clean", 0.0), ("cfo", 500.0)):
+        rx = aa.apply_cfo(tx, cfo, aa.SAMPLE_RATE_HZ) if cfo else tx
+        res = aa.aa_detect_streaming(rx, L=512)
+        for k, v in _aa_pack(res).items():
+            docs[f"{name}_{k}"] = v
+        docs[f"{name}_rx"] = rx
+        print("sync_aa docs", name, docs[f"{name}_ev_i"].tolist(), docs[f"{name}_ev_f"].tolist())
+    # the reference's own golden vectors (docs/*.csv, docs/*.hex) stored as arrays
+    d = Path(ref) / "docs"
+    docs["csv_clean"] = np.genfromtxt(d / "detector_test_vector.csv", delimiter=",", comments="#", skip_header=4)
+    docs["csv_cfo"] = np.genfromtxt(d / "detector_cfo_test_vector.csv", delimiter=",", comments="#", skip_header=3)
+    docs["csv_preamble"] = np.genfromtxt(d / "preamble_test_vector.csv", delimiter=",", skip_header=1)
+    hexw = [int(l.split()[0], 16) for l in (d / "preamble_test_vector.hex").read_text().splitlines()
+            if l.strip() and not l.startswith("//")]
+    docs["hex_preamble"] = np.asarray(hexw, dtype=np.int64)
+    docs["preamble"] = pre
+    docs["preamble_q12"] = aa.quantize_adc(pre, full_scale=2.0)
+    np.savez_compressed(out / "sync_aa_docs.npz", **docs)
+
+    # (b) grid cases through the real run_single_test (capture the detector's in/out)
+    orig = aa.aa_detect_streaming
+    cases = [(10.0, None, 2.0, 1024), (0.0, "cir1", 2.0, 1024), (10.0, "cir2", 1.0, 512),
+             (5.0, None, 1.5, 256), (-5.0, "cir1", 2.0, 1024)]
+    for i, (snr, ch, fs, plen) in enumerate(cases):
+        box = {}
+
+        def spy(rx, L=aa.PREAMBLE_HALF_LEN, **kw):
+            r = orig(rx, L=L, **kw)
+            box.update(rx=np.array(rx), L=np.int64(L), **_aa_pack(r))
+            return r
+
+        aa.aa_detect_streaming = spy
+        try:
+            tr = aa.run_single_test(snr, ch, fs, preamble_length=plen)
+        finally:
+            aa.aa_detect_streaming = orig
+        np.savez_compressed(
+            out / f"sync_aa_grid{i}.npz", snr=np.float64(snr), fs_ratio=np.float64(fs),
+            timing_error=np.int64(tr.timing_error), detected=np.bool_(tr.detected),
+            cfo_est=np.float64(tr.cfo_estimated_hz), **box,
+        )
+        print("sync_aa grid", i, snr, ch, fs, plen, tr.detected, tr.timing_error, tr.cfo_estimated_hz)
+
+
+def gen_detector_cases(out: Path) -> None:
+    """Function-level detector KATs on synthetic metrics (edge rules of SURVEY.md §8a)."""
+    import sc, minn, combined_sc_min as c
+    rng = np.random.default_rng(11)
+    d = {}
+    # plateau finder: three shapes exercising the three return paths (sc.py:106-114,117-133,136-146)
+    n = 3000
+    base = 0.02 * rng.random(n)
+    m1 = base.copy(); m1[1000:1500] += 0.8 + 0.05 * rng.random(500); m1[1500:1600] += np.linspace(0.8, 0, 100)
+    m2 = base.copy(); m2[500:2900] += 0.5 + 0.001 * rng.random(2400)          # no early drop inside cp
+    m3 = np.zeros(n); m3[100] = 1.0                                             # isolated spike
+    for k, m in (("p1", m1), ("p2", m2), ("p3", m3)):
+        d[f"{k}_M"] = m
+        d[f"{k}_end"] = np.int64(sc.find_plateau_end_from_metric(m, 512, lookahead=128, smooth_win=16))
+        d[f"{k}_end_default"] = np.int64(sc.find_plateau_end_from_metric(m, 512))
+    # minn peak finder incl. ties on run length and search bounds (minn.py:131-205)
+    g1 = base.copy(); g1[400:420] += 1.0; g1[900:920] += 1.0; g1[1500:1510] += 2.0
+    for k, (m, kw) in {
+        "g1": (g1, dict(smooth_win=16, gate_threshold=0.5)),
+        "g2": (g1, dict(smooth_win=1, gate_threshold=0.3, search_bounds=(800, 1200))),
+        "g3": (g1, dict(smooth_win=8, gate_threshold=0.5, search_bounds=(2000, 100))),
+        "g4": (g1, dict(smooth_win=4, gate_threshold=0.99)),
+    }.items():
+        pk, mask, ms = minn.find_minn_peak(m, **kw)
+        d[f"{k}_M"], d[f"{k}_peak"], d[f"{k}_gate"], d[f"{k}_Ms"] = m, np.int64(pk), _segments(mask), ms
+    # gated first-segment peak (combined_sc_min.py:183-259)
+    gate = np.zeros(n, bool); gate[395:430] = True; gate[890:1000] = True
+    d["c1_M"], d["c1_gate"] = g1, gate
+    d["c1_peak"] = np.int64(c.find_minn_peak(g1, smooth_win=16, gate_mask=gate))
+    d["c2_peak"] = np.int64(c.find_minn_peak(g1, smooth_win=16, gate_mask=gate, search_bounds=(850, 2000)))
+    np.savez_compressed(out / "detector_cases.npz", **d)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref", default="/root/reference")
+    ap.add_argument("--out", default=str(HERE.parent / "tests" / "golden"))
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    out = Path(a.out).resolve()
+    out.mkdir(parents=True, exist_ok=True)
+    _setup(a.ref)
+    gens = dict(sc=gen_sc, minn=gen_minn, park=gen_park, combined=gen_combined, zc=gen_zc, zc_v2=gen_zc_v2,
+                zc_freq=gen_zc_freq, minn_rtl=gen_minn_rtl, detector_cases=gen_detector_cases)
+    for name, fn in gens.items():
+        if a.only and name not in a.only.split(","):
+            continue
+        fn(out)
+    if not a.only or "sync_aa" in a.only.split(","):
+        gen_sync_aa(out, a.ref)
+    total = sum(p.stat().st_size for p in out.glob("*.npz"))
+    print(f"wrote {len(list(out.glob('*.npz')))} fixtures, {total / 1e6:.1f} MB -> {out}")
+
+
+if __name__ == "__main__":
+    main()

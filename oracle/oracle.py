@@ -1,0 +1,324 @@
+"""Python face of the CPU oracle (oracle/ofs_oracle.c) -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+import this module.  It mirrors the reference's function signatures (amcolex/ofdm-sync-math)
+so that parity tests read like calls to the reference; every function cites the reference
+file:line it restates.  Parity status: pinned by tests/test_oracle_golden.py against
+tests/golden/*.npz (outputs of the unmodified reference, made by oracle/gen_golden.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from dataclasses import dataclass
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB_PATH = _HERE / "libofs_oracle.so"
+_lib = None
+
+i64 = C.c_int64
+_dp = C.POINTER(C.c_double)
+
+
+def build(force: bool = False) -> Path:
+    """Compile oracle/ofs_oracle.c with gcc (make)."""
+    src = _HERE / "ofs_oracle.c"
+    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["make", "-C", str(_HERE), "-s", "-B"], check=True)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(str(_LIB_PATH))
+        for name in ("orc_sc_metric", "orc_scb_metric", "orc_minn_metric", "orc_park_metric",
+                     "orc_find_plateau_end", "orc_find_minn_peak", "orc_find_minn_peak_gated",
+                     "orc_detect_zc_peaks", "orc_zc_freq_metric", "orc_aa_events", "orc_detect_minn_rtl",
+                     "orc_detect_minn_rtl_int", "orc_metric_prefix_c64"):
+            getattr(_lib, name).restype = i64
+    return _lib
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _c128_2d(rx) -> np.ndarray:
+    x = np.asarray(rx)
+    if x.ndim == 1:
+        x = x[np.newaxis, :]
+    return np.ascontiguousarray(x, dtype=np.complex128)
+
+
+def _cplx(a: np.ndarray) -> np.ndarray:
+    return a.view(np.complex128).reshape(-1)
+
+
+# ----------------------------------------------------------------------------- metrics
+def _metric3(fn, rx, N):
+    x = _c128_2d(rx)
+    nb, L = x.shape
+    n = max(L - N + 1, 0)
+    M = np.zeros(n); P = np.zeros(2 * n); R = np.zeros(n)
+    if n > 0:
+        got = fn(_p(x), i64(nb), i64(L), i64(N), _p(M), _p(P), _p(R))
+        if got == 0:
+            return np.zeros(0), np.zeros(0, dtype=complex), np.zeros(0)
+    return M, _cplx(P), R
+
+
+def sc_streaming_metric(rx, n_fft: int = 2048):
+    """sc.py:42-78."""
+    return _metric3(lib().orc_sc_metric, rx, n_fft)
+
+
+def schmidl_cox_streaming_metric(rx, symbol_len: int = 2048):
+    """combined_sc_min.py:116-164 (R over both halves)."""
+    return _metric3(lib().orc_scb_metric, rx, symbol_len)
+
+
+def minn_streaming_metric(rx, symbol_len: int = 2048):
+    """minn.py:59-112 / minn.py:697-751 / combined_sc_min.py:60-113."""
+    return _metric3(lib().orc_minn_metric, rx, symbol_len)
+
+
+minn_streaming_metric_parameterized = minn_streaming_metric
+
+
+def park_streaming_metric(rx, n_fft: int = 2048):
+    """park.py:64-114."""
+    x = _c128_2d(rx)
+    nb, L = x.shape
+    n = max(L - 2 * (n_fft // 2), 0)
+    ds = np.zeros(n, dtype=np.int64); M = np.zeros(n); P = np.zeros(2 * n); E = np.zeros(n)
+    got = lib().orc_park_metric(_p(x), i64(nb), i64(L), i64(n_fft), _p(ds), _p(M), _p(P), _p(E)) if n else 0
+    if got == 0:
+        return np.zeros(0, dtype=int), np.zeros(0), np.zeros(0, dtype=complex), np.zeros(0)
+    return ds, M, _cplx(P), E
+
+
+# ----------------------------------------------------------------------------- detectors
+def trailing_average(x, win: int) -> np.ndarray:
+    """minn.py:115-128."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    lib().orc_trailing_average(_p(x), i64(x.size), i64(win), _p(y))
+    return y
+
+
+def find_plateau_end_from_metric(M, cp_len: int, lookahead: int | None = None, smooth_win: int = 8) -> int:
+    """sc.py:81-146."""
+    M = np.ascontiguousarray(M, dtype=np.float64)
+    if M.size == 0:
+        return 0
+    return int(lib().orc_find_plateau_end(_p(M), i64(M.size), i64(cp_len),
+                                          i64(-1 if lookahead is None else int(max(1, lookahead))),
+                                          i64(smooth_win), None))
+
+
+def find_minn_peak(M, smooth_win: int = 8, gate_threshold: float = 0.5, search_bounds=None):
+    """minn.py:131-205."""
+    M = np.ascontiguousarray(M, dtype=np.float64)
+    if M.size == 0:
+        raise ValueError("Minn metric is empty")
+    gate = np.zeros(M.size, dtype=np.uint8); Ms = np.zeros(M.size)
+    hb = search_bounds is not None
+    lo, hi = (search_bounds if hb else (0, 0))
+    pk = lib().orc_find_minn_peak(_p(M), i64(M.size), i64(smooth_win), C.c_double(gate_threshold),
+                                  C.c_int(int(hb)), i64(int(lo)), i64(int(hi)), _p(gate), _p(Ms))
+    if pk == -2:
+        raise ValueError("Minn metric did not produce a positive peak")
+    return int(pk), gate.astype(bool), Ms
+
+
+def find_minn_peak_gated(M, smooth_win: int = 8, gate_mask=None, search_bounds=None) -> int:
+    """combined_sc_min.py:212-259."""
+    M = np.ascontiguousarray(M, dtype=np.float64)
+    if M.size == 0:
+        return 0
+    if gate_mask is None:
+        raise ValueError("Minn peak detection requires S&C gate mask")
+    g = np.ascontiguousarray(gate_mask, dtype=np.uint8)
+    if g.shape[0] != M.shape[0]:
+        raise ValueError("gate_mask must match metric length")
+    Ms = np.zeros(M.size)
+    hb = search_bounds is not None
+    lo, hi = (search_bounds if hb else (0, 0))
+    pk = lib().orc_find_minn_peak_gated(_p(M), i64(M.size), i64(smooth_win), _p(g),
+                                        C.c_int(int(hb)), i64(int(lo)), i64(int(hi)), _p(Ms))
+    if pk == -3:
+        raise ValueError("Minn peak detector received empty gate region")
+    return int(pk)
+
+
+def sc_gate(M_sc, threshold: float = 0.6) -> np.ndarray:
+    """combined_sc_min.py:337-351."""
+    M_sc = np.ascontiguousarray(M_sc, dtype=np.float64)
+    g = np.zeros(M_sc.size, dtype=np.uint8)
+    lib().orc_sc_gate(_p(M_sc), i64(M_sc.size), C.c_double(threshold), _p(g))
+    return g.astype(bool)
+
+
+# ----------------------------------------------------------------------------- ZC
+def matched_filter_correlation(rx, ref):
+    """zc_v2.py:244-254 (also zc.py:116-117): returns (corr, sliding energy)."""
+    x = np.ascontiguousarray(rx, dtype=np.complex128).reshape(-1)
+    r = np.ascontiguousarray(ref, dtype=np.complex128).reshape(-1)
+    n = x.size + r.size - 1
+    corr = np.zeros(2 * n); en = np.zeros(n)
+    lib().orc_zc_matched_filter(_p(x), i64(x.size), _p(r), i64(r.size), _p(corr), _p(en))
+    return _cplx(corr), en
+
+
+def zc_correlation(rx, ref):
+    """zc.py:105-130: branch-summed numerator / energy, normalised AFTER the sum."""
+    x = _c128_2d(rx)
+    num = None; pw = None
+    for b in x:
+        c, e = matched_filter_correlation(b, ref)
+        num = c if num is None else num + c
+        pw = e if pw is None else pw + e
+    ref_norm = np.sqrt(np.sum(np.abs(ref) ** 2))
+    corr = num / (ref_norm * np.sqrt(np.maximum(pw, 0.0) + 1e-12))
+    mag = np.abs(corr)
+    peak = int(np.argmax(mag))
+    return corr, peak, max(peak - len(ref) + 1, 0)
+
+
+def zc_v2_corr_mag(rx, ref, normalize: bool = True):
+    """zc_v2.py:486-498: per-branch normalise, then sum, then magnitude."""
+    x = _c128_2d(rx)
+    tot = None
+    ref_norm = np.sqrt(np.sum(np.abs(ref) ** 2))
+    for b in x:
+        c, e = matched_filter_correlation(b, ref)
+        if normalize:
+            c = c / (ref_norm * np.sqrt(np.maximum(e, 1e-12)))
+        tot = c if tot is None else tot + c
+    return np.abs(tot)
+
+
+@dataclass
+class ZCState:
+    corr_mag: np.ndarray
+    local_sum: np.ndarray
+    corr_scaled: np.ndarray
+    thresh_scaled: np.ndarray
+    above_threshold: np.ndarray
+    metric_valid: np.ndarray
+
+
+def zc_streaming_detection(corr_mag, window_size=2048, thresh_value=64, thresh_frac_bits=15, min_corr_mag=0.3):
+    """zc_v2.py:288-336."""
+    m = np.ascontiguousarray(corr_mag, dtype=np.float64)
+    n = m.size
+    ls = np.zeros(n); v = np.zeros(n, np.uint8); a = np.zeros(n, np.uint8)
+    lib().orc_zc_streaming_detection(_p(m), i64(n), i64(window_size), i64(thresh_value), i64(thresh_frac_bits),
+                                     C.c_double(min_corr_mag), _p(ls), _p(v), _p(a))
+    return ZCState(m, ls, m * float(1 << thresh_frac_bits), ls * float(thresh_value), a.astype(bool), v.astype(bool))
+
+
+def detect_zc_peaks(state: ZCState, reference_length: int, hysteresis: int = 256, max_ev: int = 256):
+    """zc_v2.py:360-450 -> (events int64[n,4]=(peak,gate_start,gate_end,detected_start), values, gate_mask)."""
+    n = state.corr_mag.size
+    gm = np.zeros(n, np.uint8); ev = np.zeros((max_ev, 4), np.int64); vals = np.zeros(max_ev)
+    v = np.ascontiguousarray(state.metric_valid, dtype=np.uint8)
+    a = np.ascontiguousarray(state.above_threshold, dtype=np.uint8)
+    nev = lib().orc_detect_zc_peaks(_p(state.corr_mag), _p(v), _p(a), i64(n), i64(reference_length),
+                                    i64(hysteresis), _p(gm), _p(ev), _p(vals), i64(max_ev))
+    return ev[:nev].copy(), vals[:nev].copy(), gm.astype(bool)
+
+
+def compute_frequency_metric(rx, bin_indices, template_bins, template_energy, n_fft=2048, cp=512):
+    """zc_freq.py:62-99."""
+    x = _c128_2d(rx)
+    nb, L = x.shape
+    nofs = L - (n_fft + cp) + 1
+    if nofs <= 0:
+        raise ValueError("Received stream is shorter than a single OFDM symbol.")
+    bi = np.ascontiguousarray(bin_indices, dtype=np.int64)
+    t = np.ascontiguousarray(template_bins, dtype=np.complex128)
+    out = np.zeros(nofs)
+    lib().orc_zc_freq_metric(_p(x), i64(nb), i64(L), i64(n_fft), i64(cp), _p(bi), _p(t), i64(bi.size),
+                             C.c_double(template_energy), _p(out))
+    return out
+
+
+# ----------------------------------------------------------------------------- sync_aa
+def aa_detect_streaming(rx, L=512, threshold=0.15, hysteresis=128, sample_rate=15_360_000.0, max_ev=64):
+    """sync_aa.py:421-571 -> dict(P,R,M,valid, ev_i[n,4]=(peak,gate_start,gate_end,frame_start),
+    ev_f[n,4]=(P_re,P_im,M_at_peak,cfo_hz))."""
+    x = _c128_2d(rx)
+    na, n = x.shape
+    P = np.zeros(2 * n); R = np.zeros(n); M = np.zeros(n); v = np.zeros(n, np.uint8)
+    lib().orc_aa_metric(_p(x), i64(na), i64(n), i64(L), _p(P), _p(R), _p(M), _p(v))
+    ev_i = np.zeros((max_ev, 4), np.int64); ev_f = np.zeros((max_ev, 4))
+    nev = lib().orc_aa_events(_p(P), _p(M), _p(v), i64(n), i64(L), C.c_double(threshold), i64(hysteresis),
+                              C.c_double(sample_rate), _p(ev_i), _p(ev_f), i64(max_ev))
+    return dict(P=_cplx(P), R=R, M=M, valid=v.astype(bool), ev_i=ev_i[:nev].copy(), ev_f=ev_f[:nev].copy())
+
+
+# ----------------------------------------------------------------------------- minn_rtl
+def minn_rtl_streaming_metric(rx, *, smooth_shift, threshold_value, threshold_frac_bits, quarter_len=512):
+    """minn_rtl.py:667-733 -> dict of the 8 state arrays."""
+    x = _c128_2d(rx)
+    nb, n = x.shape
+    f = lambda: np.zeros(n)
+    d = dict(corr_total=f(), corr_positive=f(), smooth_metric=f(), energy_total=f(), corr_scaled=f(),
+             energy_scaled=f(), metric_valid=np.zeros(n, np.uint8), above=np.zeros(n, np.uint8))
+    lib().orc_minn_rtl_metric(_p(x), i64(nb), i64(n), i64(quarter_len), i64(smooth_shift), i64(threshold_value),
+                              i64(threshold_frac_bits), *[_p(d[k]) for k in d])
+    d["metric_valid"] = d["metric_valid"].astype(bool); d["above"] = d["above"].astype(bool)
+    return d
+
+
+def detect_minn_rtl(state: dict, *, hysteresis: int, timing_offset: int, max_ev: int = 256):
+    """minn_rtl.py:750-825 -> (events int64[n,4]=(peak,detected,seg_lo,seg_hi), gate_segments int64[m,2])."""
+    n = state["corr_positive"].size
+    ev = np.zeros((max_ev, 4), np.int64); sg = np.zeros((max_ev, 2), np.int64); nseg = i64(0)
+    a = np.ascontiguousarray(state["above"], dtype=np.uint8)
+    v = np.ascontiguousarray(state["metric_valid"], dtype=np.uint8)
+    cp = state["corr_positive"]
+    if cp.dtype == np.int64:
+        nev = lib().orc_detect_minn_rtl_int(_p(cp), _p(a), _p(v), i64(n), i64(hysteresis), i64(timing_offset),
+                                            _p(ev), _p(sg), i64(max_ev), C.byref(nseg))
+    else:
+        cp = np.ascontiguousarray(cp, dtype=np.float64)
+        nev = lib().orc_detect_minn_rtl(_p(cp), _p(a), _p(v), i64(n), i64(hysteresis), i64(timing_offset),
+                                        _p(ev), _p(sg), i64(max_ev), C.byref(nseg))
+    return ev[:nev].copy(), sg[:nseg.value].copy()
+
+
+def minn_rtl_int(iq, *, smooth_shift, threshold_value, threshold_frac_bits, quarter_len=512, lag_extra=0):
+    """Integer model of ref/minn_antenna_path.sv + ref/minn_preamble_detector.sv:247-325.
+    iq: int16 (antennas, n, 2)."""
+    q = np.ascontiguousarray(iq, dtype=np.int16)
+    if q.ndim == 2:
+        q = q[np.newaxis]
+    nb, n, _ = q.shape
+    f = lambda: np.zeros(n, np.int64)
+    d = dict(corr_total=f(), corr_positive=f(), smooth_metric=f(), energy_total=f(),
+             metric_valid=np.zeros(n, np.uint8), above=np.zeros(n, np.uint8))
+    lib().orc_minn_rtl_int(_p(q), i64(nb), i64(n), i64(quarter_len), i64(smooth_shift), i64(threshold_value),
+                           i64(threshold_frac_bits), i64(lag_extra), *[_p(d[k]) for k in d])
+    d["metric_valid"] = d["metric_valid"].astype(bool); d["above"] = d["above"].astype(bool)
+    return d
+
+
+# ----------------------------------------------------------------------------- scale path
+def metric_prefix_c64(x_c64: np.ndarray, n_fft: int, kind: int, want_pr: bool = False):
+    """Closed forms of SURVEY.md Appendix B in float64 on a complex64 row (kind 0 S&C, 1 S&C both
+    halves, 2 Minn).  Used for BASELINE-size checks and as bench.py's cpu_baseline 'port'."""
+    x = np.ascontiguousarray(x_c64, dtype=np.complex64).reshape(-1)
+    n = max(x.size - n_fft + 1, 0)
+    M = np.zeros(n)
+    P = np.zeros(2 * n) if want_pr else None
+    R = np.zeros(n) if want_pr else None
+    lib().orc_metric_prefix_c64(_p(x), i64(x.size), i64(n_fft), C.c_int(kind), _p(M),
+                                _p(P) if want_pr else None, _p(R) if want_pr else None)
+    return (M, _cplx(P), R) if want_pr else M

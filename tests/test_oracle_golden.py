@@ -1,0 +1,231 @@
+"""Pins the CPU oracle (oracle/) against outputs of the UNMODIFIED reference (tests/golden/*.npz,
+made by oracle/gen_golden.py) and against the reference's own docs/*_test_vector files.
+Float tolerance: 1e-11 relative to the array scale (numpy's internal summation order differs
+from the oracle's sequential sums); indices, masks and event lists must be equal."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from conftest import segments
+
+RTOL = 1e-11
+
+
+def close(a, b, rtol=RTOL):
+    a = np.asarray(a); b = np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    scale = max(float(np.max(np.abs(b))) if b.size else 0.0, 1e-300)
+    err = float(np.max(np.abs(a - b))) if b.size else 0.0
+    assert err <= rtol * scale, f"max err {err:.3e} vs scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("tag", ["cir1", "awgn"])
+def test_sc(golden, tag):
+    g = golden(f"sc_{tag}")
+    M, P, R = orc.sc_streaming_metric(g["rx"])
+    close(M, g["M"]); close(P, g["P"]); close(R, g["R"])
+    for Min in (M, g["M"]):
+        end = orc.find_plateau_end_from_metric(Min, int(g["cp_len"]), lookahead=int(g["lookahead"]),
+                                               smooth_win=int(g["smooth_win"]))
+        assert end == int(g["plateau_end"])
+        assert max(end - int(g["sc_delta"]), 0) == int(g["coarse_start"])
+
+
+@pytest.mark.parametrize("tag", ["cir1", "awgn"])
+def test_minn(golden, tag):
+    g = golden(f"minn_{tag}")
+    M, P, R = orc.minn_streaming_metric(g["rx"])
+    close(M, g["M"]); close(P, g["P"]); close(R, g["R"])
+    pk, gate, Ms = orc.find_minn_peak(g["M"], smooth_win=int(g["smooth_win"]), gate_threshold=float(g["gate_threshold"]))
+    assert pk == int(g["peak"]); assert np.array_equal(segments(gate), g["gate"]); close(Ms, g["Ms"], 1e-13)
+    pk2, gate2, _ = orc.find_minn_peak(M, smooth_win=int(g["smooth_win"]), gate_threshold=float(g["gate_threshold"]))
+    assert pk2 == int(g["peak"]); assert np.array_equal(segments(gate2), g["gate"])
+
+
+def test_minn_param(golden):
+    g = golden("minn_param")
+    for n in (64, 100, 256, 1024):
+        M, P, R = orc.minn_streaming_metric_parameterized(g["rx"], n)
+        close(M, g[f"M_{n}"]); close(P, g[f"P_{n}"]); close(R, g[f"R_{n}"])
+    M, P, R = orc.minn_streaming_metric_parameterized(g["rx"], 4096)   # L < N -> empty (minn.py:723-724)
+    assert M.size == 0 and P.size == 0 and R.size == 0 and P.dtype == complex
+
+
+@pytest.mark.parametrize("tag", ["cir1", "awgn"])
+def test_park(golden, tag):
+    g = golden(f"park_{tag}")
+    ds, M, P, E = orc.park_streaming_metric(g["rx"])
+    assert np.array_equal(ds, g["ds"]); close(M, g["M"]); close(P, g["P"]); close(E, g["E"])
+    c = int(ds[int(np.argmax(M))])
+    assert c == int(g["det_center"]) and max(c - 1024, 0) == int(g["det_symbol_start"])
+
+
+@pytest.mark.parametrize("tag", ["cir1", "awgn"])
+def test_combined(golden, tag):
+    g = golden(f"combined_{tag}")
+    M, P, R = orc.minn_streaming_metric(g["rx"])
+    Msc, Psc, Rsc = orc.schmidl_cox_streaming_metric(g["rx"])
+    close(M, g["M"]); close(Msc, g["M_sc"]); close(Psc, g["P_sc"]); close(Rsc, g["R_sc"])
+    gate = orc.sc_gate(Msc, float(g["sc_gate_threshold"]))
+    assert np.array_equal(segments(gate), g["sc_gate"])
+    idx = np.flatnonzero(gate)
+    assert (idx[0], idx[-1] + 1) == tuple(g["sc_gate_span"])
+    assert orc.find_minn_peak_gated(M, smooth_win=int(g["smooth_win"]), gate_mask=gate) == int(g["peak"])
+
+
+@pytest.mark.parametrize("tag", ["cir1", "awgn"])
+def test_zc(golden, tag):
+    g = golden(f"zc_{tag}")
+    corr, peak, start = orc.zc_correlation(g["rx"], g["ref"])
+    close(corr, g["corr"]); assert peak == int(g["peak"]) and start == int(g["start"])
+
+
+@pytest.mark.parametrize("tag", ["cir1", "awgn"])
+def test_zc_v2(golden, tag):
+    g = golden(f"zc_v2_{tag}")
+    mag = orc.zc_v2_corr_mag(g["rx"], g["ref"])
+    close(mag, g["corr_mag"])
+    for m in (mag, g["corr_mag"]):
+        st = orc.zc_streaming_detection(m, int(g["window_size"]), int(g["thresh_value"]),
+                                        int(g["thresh_frac_bits"]), float(g["min_corr_mag"]))
+        close(st.local_sum, g["local_sum"], 1e-10)
+        assert np.array_equal(st.metric_valid, g["valid"]); assert np.array_equal(st.above_threshold, g["above"])
+        ev, vals, gm = orc.detect_zc_peaks(st, g["ref"].size, int(g["hysteresis"]))
+        assert np.array_equal(ev, g["events"]); close(vals, g["event_values"]); assert np.array_equal(segments(gm), g["gate"])
+
+
+@pytest.mark.parametrize("tag", ["cir1", "awgn"])
+def test_zc_freq(golden, tag):
+    g = golden(f"zc_freq_{tag}")
+    n = 600   # the direct-DFT restatement is O(62*2048) per offset: check a window around the peak + the start
+    pk = int(g["peak"])
+    lo = max(pk - n // 2, 0)
+    rx = g["rx"][:, lo: lo + n + 2559]
+    m = orc.compute_frequency_metric(rx, g["bin_indices"], g["template"], float(g["template_energy"]))
+    close(m, g["metric"][lo: lo + m.size], 1e-10)
+    assert lo + int(np.argmax(m)) == pk
+    with pytest.raises(ValueError):
+        orc.compute_frequency_metric(g["rx"][:, :2559], g["bin_indices"], g["template"], float(g["template_energy"]))
+
+
+@pytest.mark.parametrize("tag", ["cir1", "awgn", "int12"])
+def test_minn_rtl(golden, tag):
+    g = golden(f"minn_rtl_{tag}")
+    if tag == "int12":
+        rx = g["iq"][..., 0].astype(np.float64) + 1j * g["iq"][..., 1].astype(np.float64)
+    else:
+        rx = g["rx"]
+    kw = dict(smooth_shift=int(g["smooth_shift"]), threshold_value=int(g["threshold_value"]),
+              threshold_frac_bits=int(g["threshold_frac_bits"]), quarter_len=int(g["quarter_len"]))
+    st = orc.minn_rtl_streaming_metric(rx, **kw)
+    exact = tag == "int12"       # integer-valued input: every float64 op is exact -> bit-equal
+    for k in ("corr_total", "corr_positive", "smooth_metric", "energy_total", "corr_scaled", "energy_scaled"):
+        if exact:
+            assert np.array_equal(st[k], g[k]), k
+        else:
+            close(st[k], g[k], 1e-12)
+    assert np.array_equal(st["metric_valid"], g["metric_valid"]); assert np.array_equal(st["above"], g["above"])
+    ev, segs = orc.detect_minn_rtl(st, hysteresis=int(g["hysteresis"]), timing_offset=int(g["timing_offset"]))
+    assert np.array_equal(ev, g["events"]); assert np.array_equal(segs, g["gate_segments"])
+
+
+def test_minn_rtl_int_model_vs_float_mirror(golden):
+    """Integer SV model == minn_rtl.py on int12 input for corr/energy/valid (exact); the floor-shift
+    smoother differs from the float smoother by design: bounded, flags compared."""
+    g = golden("minn_rtl_int12")
+    kw = dict(smooth_shift=3, threshold_value=3276, threshold_frac_bits=15, quarter_len=512)
+    d = orc.minn_rtl_int(g["iq"], **kw)
+    assert np.array_equal(d["corr_total"], g["corr_total"].astype(np.int64))
+    assert np.array_equal(d["energy_total"], g["energy_total"].astype(np.int64))
+    assert np.array_equal(d["corr_positive"], g["corr_positive"].astype(np.int64))
+    assert np.array_equal(d["metric_valid"], g["metric_valid"])
+    assert np.max(np.abs(d["smooth_metric"] - g["smooth_metric"])) < 8.0   # < 2^shift LSB
+    ev, segs = orc.detect_minn_rtl(d, hysteresis=2, timing_offset=0)
+    assert abs(int(ev[0, 0]) - int(g["events"][0, 0])) <= 16              # the testbench's own criterion
+
+
+def test_sync_aa_docs_vectors(golden):
+    """docs/detector_test_vector.csv + docs/detector_cfo_test_vector.csv + docs/preamble_test_vector.{csv,hex}
+    (these pin sync_aa.aa_detect_streaming)."""
+    g = golden("sync_aa_docs")
+    for name, csv in (("clean", g["csv_clean"]), ("cfo", g["csv_cfo"])):
+        r = orc.aa_detect_streaming(g[f"{name}_rx"], L=512)
+        # P: bit-exact against the reference run (pure scalar recurrence).  R, M: numpy's |z|^2 goes
+        # through its own hypot and is not bit-reproducible (see ofs_oracle.c sq_abs) -> few ulp.
+        assert np.array_equal(r["P"], g[f"{name}_P"]); close(r["R"], g[f"{name}_R"], 4e-15)
+        assert np.max(np.abs(r["M"] - g[f"{name}_M"])) <= 4e-15; assert np.array_equal(r["valid"], g[f"{name}_valid"])
+        assert np.array_equal(r["ev_i"], g[f"{name}_ev_i"]); close(r["ev_f"], g[f"{name}_ev_f"], 4e-15)
+        assert r["ev_i"].tolist() == [[1523, 1210, 2024, 500]]
+        # the CSV rows (samples 1000..1599), to their printed precision
+        s = csv[:, 0].astype(int)
+        assert np.max(np.abs(r["M"][s] - csv[:, 1])) <= 5.1e-9
+        assert np.max(np.abs(r["P"][s].real - csv[:, 2])) <= 5.1e-3
+        assert np.max(np.abs(r["P"][s].imag - csv[:, 3])) <= 5.1e-3
+        assert np.max(np.abs(np.abs(r["P"][s]) ** 2 - csv[:, 4])) <= 5.1e-3 + 1e-9 * np.max(csv[:, 4])
+        if name == "clean":
+            assert np.max(np.abs(r["R"][s] - csv[:, 5])) <= 5.1e-3
+        else:
+            assert np.max(np.abs(np.angle(r["P"][s]) - csv[:, 5])) <= 5.1e-9
+    assert abs(g["cfo_ev_f"][0, 3] - 500.0) < 1e-9
+    # preamble vectors: float columns, int12 columns == quantize_adc(x, 2.0) * 1024, hex packing
+    pc = g["csv_preamble"]
+    assert np.max(np.abs(g["preamble"].real - pc[:, 1])) < 6e-11 and np.max(np.abs(g["preamble"].imag - pc[:, 2])) < 6e-11
+    q = np.round(g["preamble_q12"] * 1024.0)
+    assert np.array_equal(q.real.astype(int), pc[:, 3].astype(int)); assert np.array_equal(q.imag.astype(int), pc[:, 4].astype(int))
+    words = ((pc[:, 3].astype(np.int64) & 0xFFF) << 12) | (pc[:, 4].astype(np.int64) & 0xFFF)
+    assert np.array_equal(words, g["hex_preamble"])
+
+
+@pytest.mark.parametrize("i", range(5))
+def test_sync_aa_grid(golden, i):
+    g = golden(f"sync_aa_grid{i}")
+    r = orc.aa_detect_streaming(g["rx"], L=int(g["L"]))
+    for k in ("P", "valid", "ev_i"):
+        assert np.array_equal(r[k], g[k]), k
+    for k in ("R", "M", "ev_f"):
+        close(r[k], g[k], 4e-15)
+    assert bool(g["detected"]) == (r["ev_i"].shape[0] > 0)
+
+
+def test_detector_cases(golden):
+    g = golden("detector_cases")
+    for k in ("p1", "p2", "p3"):
+        assert orc.find_plateau_end_from_metric(g[f"{k}_M"], 512, lookahead=128, smooth_win=16) == int(g[f"{k}_end"])
+        assert orc.find_plateau_end_from_metric(g[f"{k}_M"], 512) == int(g[f"{k}_end_default"])
+    kws = dict(g1=dict(smooth_win=16, gate_threshold=0.5), g2=dict(smooth_win=1, gate_threshold=0.3, search_bounds=(800, 1200)),
+               g3=dict(smooth_win=8, gate_threshold=0.5, search_bounds=(2000, 100)), g4=dict(smooth_win=4, gate_threshold=0.99))
+    for k, kw in kws.items():
+        pk, gate, Ms = orc.find_minn_peak(g[f"{k}_M"], **kw)
+        assert pk == int(g[f"{k}_peak"]), k
+        assert np.array_equal(segments(gate), g[f"{k}_gate"]); close(Ms, g[f"{k}_Ms"], 1e-13)
+    assert orc.find_minn_peak_gated(g["c1_M"], smooth_win=16, gate_mask=g["c1_gate"]) == int(g["c1_peak"])
+    assert orc.find_minn_peak_gated(g["c1_M"], smooth_win=16, gate_mask=g["c1_gate"], search_bounds=(850, 2000)) == int(g["c2_peak"])
+
+
+def test_edge_cases():
+    z = np.zeros(100, complex)
+    for f in (orc.sc_streaming_metric, orc.minn_streaming_metric, orc.schmidl_cox_streaming_metric):
+        M, P, R = f(z)
+        assert M.size == 0 and P.size == 0 and R.size == 0
+    ds, M, P, E = orc.park_streaming_metric(np.zeros(2048, complex))
+    assert ds.size == 0 and M.size == 0
+    assert orc.find_plateau_end_from_metric(np.zeros(0), 512) == 0
+    with pytest.raises(ValueError):
+        orc.find_minn_peak(np.zeros(0))
+    with pytest.raises(ValueError):
+        orc.find_minn_peak(np.zeros(10))
+    assert orc.find_minn_peak_gated(np.zeros(0)) == 0
+    with pytest.raises(ValueError):
+        orc.find_minn_peak_gated(np.ones(10))
+    with pytest.raises(ValueError):
+        orc.find_minn_peak_gated(np.ones(10), gate_mask=np.zeros(10, bool))
+
+
+def test_prefix_scale_path_matches_literal():
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal(6000) + 1j * rng.standard_normal(6000)).astype(np.complex64)
+    for kind, fn in ((0, orc.sc_streaming_metric), (1, orc.schmidl_cox_streaming_metric), (2, orc.minn_streaming_metric)):
+        M, P, R = orc.metric_prefix_c64(x, 2048, kind, want_pr=True)
+        M0, P0, R0 = fn(x.astype(np.complex128))
+        close(P, P0, 1e-12 * 50); close(R, R0, 1e-12)
+        assert np.max(np.abs(M - M0) / np.maximum(M0, 1e-6)) < 1e-9

@@ -1,0 +1,236 @@
+/*
+ * ofdmsync.h -- C ABI of the B200-native OFDM synchronisation engine (libofdmsync.so).
+ *
+ * The reference (amcolex/ofdm-sync-math) has no FFI/plugin boundary: its hot path sits behind
+ * plain module-level Python functions.  This header is the boundary a maintainer
+ * would bind from those functions (ctypes stubs in INTEGRATION.md); every entry point names the
+ * reference function it replaces (file:line under /root/reference).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no torch / CUDA types (a stream is passed as void*,
+ *    it is a cudaStream_t; NULL = the legacy default stream).
+ *  - All *device* entry points take DEVICE pointers, are asynchronous on `stream`, allocate
+ *    nothing persistent and never synchronise.  The caller owns every buffer.
+ *  - *_host entry points take HOST pointers (pinned memory makes the copies asynchronous),
+ *    stage through an ofs_ctx workspace, and return after the results are in host memory.
+ *  - Return value: OFS_OK (0); < 0 invalid argument (ofs_last_error_string() says which);
+ *    > 0 a cudaError_t.  Nothing throws across the ABI.  Re-entrant; error strings are
+ *    thread-local.
+ *  - Complex arrays are interleaved (re, im).  "frames" is the leading batch axis added for
+ *    the B200 engine; branches (antennas) are summed before the non-linear metric exactly as
+ *    in the reference (sc.py:73-74, minn.py:106-107, sync_aa.py:478-479, ...).
+ */
+#ifndef OFDMSYNC_H
+#define OFDMSYNC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFS_ABI_VERSION 1
+
+#define OFS_OK 0
+#define OFS_EINVAL (-1)      /* bad descriptor / null pointer / unsupported size */
+#define OFS_EUNSUPPORTED (-2) /* valid request that this build cannot serve (e.g. span too large) */
+
+/* input sample formats */
+#define OFS_C64 0   /* float  (re, im)   8 B / sample */
+#define OFS_C128 1  /* double (re, im)  16 B / sample */
+#define OFS_IQ16 2  /* int16  (i, q)     4 B / sample */
+
+/* autocorrelation metric kinds */
+#define OFS_SC 0       /* sc.sc_streaming_metric                     sc.py:42-78   (R: 2nd half)   */
+#define OFS_SC_BOTH 1  /* combined_sc_min.schmidl_cox_streaming_metric  :116-164   (R: both halves) */
+#define OFS_MINN 2     /* minn.minn_streaming_metric(_parameterized) minn.py:59-112, :697-751       */
+#define OFS_AA 3       /* sync_aa.aa_detect_streaming loop 1         sync_aa.py:458-493 (causal)    */
+
+/* kernel family selection */
+#define OFS_PATH_AUTO 0
+#define OFS_PATH_STRIPE 1 /* fast: fp32 products, fp64 carries, TMA-fed persistent stripes (c64 / iq16 in, f32 out) */
+#define OFS_PATH_TILE 2   /* precise: float64 prefix sums, any lag / branch count / dtype */
+
+typedef struct ofs_metric_desc {
+    int32_t kind;        /* OFS_SC ... OFS_AA */
+    int32_t in_dtype;    /* OFS_C64 / OFS_C128 / OFS_IQ16 */
+    int32_t out_f64;     /* 0: M,R float32 + P complex64; 1: M,R float64 + P complex128 */
+    int32_t path;        /* OFS_PATH_* */
+    int32_t symbol_len;  /* N (SC, SC_BOTH, MINN: Q = N/4, half = N/2); L = half-preamble length for AA */
+    int32_t n_branches;  /* antennas summed before the metric */
+    int64_t n_frames;
+    int64_t n_samples;        /* samples per frame and branch */
+    int64_t x_frame_stride;   /* in samples */
+    int64_t x_branch_stride;  /* in samples */
+    int64_t out_stride;       /* elements between frames in M / P / R / chunk_max (>= out_len) */
+    int32_t store_mode;       /* stripe path only: 0 direct vector stores, 1 TMA bulk stores (default) */
+    int32_t reserved;
+} ofs_metric_desc;
+
+/* Library / error -------------------------------------------------------------------------- */
+int ofs_version(void);
+const char *ofs_last_error_string(void);
+/* number of outputs per frame for a descriptor: L-N+1 (SC, SC_BOTH, MINN; 0 if L<N), L (AA) */
+int64_t ofs_metric_out_len(const ofs_metric_desc *d);
+/* 1 if the stripe (fast) path can serve this descriptor and these pointers (alignment rules in DESIGN.md) */
+int ofs_metric_stripe_ok(const ofs_metric_desc *d, const void *x, const void *M);
+/* outputs covered by one chunk_max entry (stripe path), 256 */
+int32_t ofs_chunk_len(void);
+
+/* Timing metric M (and optionally P, R) for a batch of frames ---------------------------------
+ * Replaces sc.py:42-78, combined_sc_min.py:116-164, minn.py:59-112 / :697-751, sync_aa.py:458-493.
+ * M, P, R: out_len elements per frame (out_stride apart); P and R may be NULL.
+ * chunk_max (may be NULL; stripe path only): float[n_frames][ceil(n_samples/256)] at stride
+ * cm_stride, max of M over each aligned block of 256 causal sample times -- used by the
+ * detectors to prune their second pass. */
+int ofs_metric(const ofs_metric_desc *d, const void *x, void *M, void *P, void *R,
+               float *chunk_max, int64_t cm_stride, void *stream);
+
+/* Park metric -- park.py:64-114.  n = L - 2*(N/2) outputs per frame (0 if L < N+1): M, P, E
+ * (ds = h + arange(n) is implicit).  in/out dtypes as in ofs_metric_desc (kind ignored). */
+int ofs_park_metric(const ofs_metric_desc *d, const void *x, void *M, void *P, void *E, void *stream);
+
+/* Detectors on metric arrays (one row per frame; float32 or float64 rows) ----------------------- */
+typedef struct ofs_rows {
+    const void *data;   /* row-major metric array */
+    int32_t f64;        /* 0 float32, 1 float64 */
+    int32_t reserved;
+    int64_t n_rows, n, stride;
+} ofs_rows;
+
+/* sc.find_plateau_end_from_metric -- sc.py:81-146.  lookahead < 0 == None.  out: int64[n_rows]. */
+int ofs_find_plateau_end(const ofs_rows *M, int32_t cp_len, int32_t lookahead, int32_t smooth_win,
+                         int64_t *plateau_end, void *stream);
+
+/* minn.find_minn_peak -- minn.py:131-205 (incl. _trailing_average :115-128).
+ * peak: int64[n_rows] (-1 empty metric, -2 non-positive peak -> the shim raises ValueError);
+ * gate_span: int64[n_rows][2] = the selected gate [start, end) AFTER bounds (fallback, minn.py:195-200:
+ * the single-sample gate [peak, peak+1)); Ms (optional): smoothed metric, same dtype/stride as M. */
+int ofs_find_minn_peak(const ofs_rows *M, int32_t smooth_win, double gate_threshold, int32_t has_bounds,
+                       int64_t bound_lo, int64_t bound_hi, int64_t *peak, int64_t *gate_span, void *Ms,
+                       void *stream);
+
+/* combined_sc_min: S&C gate construction :337-351 (gate = M_sc/max >= thr, seeded with argmax) */
+int ofs_sc_gate(const ofs_rows *Msc, double threshold, uint8_t *gate, int64_t gate_stride, void *stream);
+/* combined_sc_min.find_minn_peak :212-259 + _streaming_peak_detector :183-209.
+ * peak: -1 empty M (reference returns 0), -3 empty gate region (ValueError). */
+int ofs_find_minn_peak_gated(const ofs_rows *M, int32_t smooth_win, const uint8_t *gate, int64_t gate_stride,
+                             int32_t has_bounds, int64_t bound_lo, int64_t bound_hi, int64_t *peak, void *stream);
+
+/* argmax with numpy semantics (first maximum): park.py:161, zc.py:128, zc_freq.py:147 */
+int ofs_argmax(const ofs_rows *M, int64_t *index, void *stream);
+
+/* Gate / hysteresis state machines ------------------------------------------------------------- */
+#define OFS_MAX_EVENTS 64
+typedef struct ofs_event {
+    int64_t peak_index;
+    int64_t gate_start;
+    int64_t gate_end;   /* close index (n if the gate never closed) */
+    int64_t aux;        /* aa: frame_start = peak-2L+1; zc_v2: detected_start; minn_rtl: detected_index */
+    double value;       /* aa: M[peak]; zc_v2: corr_mag[peak]; minn_rtl: corr_positive[peak] */
+    double p_re, p_im;  /* aa: P at peak */
+    double cfo;         /* aa: angle(P)*fs/(2*pi*L) in Hz */
+    int32_t closed;     /* 0: gate still open at end of input */
+    int32_t reserved;
+} ofs_event;
+
+/* sync_aa.aa_detect_streaming loop 2 -- sync_aa.py:495-568.  M, P: rows of length n (P complex,
+ * same precision as M).  events: ofs_event[n_rows][OFS_MAX_EVENTS]; n_events: int32[n_rows]. */
+int ofs_aa_events(const ofs_rows *M, const void *P, int32_t L, double threshold, int32_t hysteresis,
+                  double sample_rate, ofs_event *events, int32_t *n_events, void *stream);
+
+/* Reference-ORDER [A][A] metric (sync_aa.py:321-386, 458-493): the reference's running-sum recurrences
+ * `sum + sample - oldest` in its exact operation order, one thread per frame, float64 outputs
+ * [n_frames][n].  P is bit-equal to the reference; needed where a detection depends on the rounding
+ * of the running sums (docs/detector_test_vector.csv: the 1523/1524 tie).
+ * x: (n_frames, n_antennas, n), n_antennas <= 64. */
+int ofs_aa_metric_reference(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_antennas, int64_t n,
+                            int32_t L, void *P_c128, double *R, double *M, uint8_t *valid, void *stream);
+
+/* zc_v2.zc_streaming_detection -- zc_v2.py:288-336: local_sum (same dtype as corr_mag), valid, above. */
+int ofs_zc_streaming_detection(const ofs_rows *corr_mag, int32_t window, int32_t thresh_value,
+                               int32_t frac_bits, double min_corr_mag, void *local_sum, uint8_t *valid,
+                               uint8_t *above, int64_t mask_stride, void *stream);
+/* zc_v2.detect_zc_peaks -- zc_v2.py:360-450.  gate_mask optional. */
+int ofs_zc_events(const ofs_rows *corr_mag, const uint8_t *valid, const uint8_t *above, int64_t mask_stride,
+                  int32_t reference_length, int32_t hysteresis, ofs_event *events, int32_t *n_events,
+                  uint8_t *gate_mask, void *stream);
+
+/* minn_rtl.detect_minn_rtl -- minn_rtl.py:750-825 (== ref/minn_preamble_detector.sv:337-384).
+ * corr_positive rows: float64, or int64 when is_int != 0 (integer RTL mode).  An unclosed tail gate
+ * is returned as an event with closed == 0 (the reference reports it as a segment, not an event). */
+int ofs_minn_rtl_events(const void *corr_positive, int32_t is_int, const uint8_t *valid, const uint8_t *above,
+                        int64_t n_rows, int64_t n, int64_t stride, int32_t hysteresis, int32_t timing_offset,
+                        ofs_event *events, int32_t *n_events, void *stream);
+
+/* minn_rtl metric ------------------------------------------------------------------------------
+ * Float mirror -- minn_rtl.minn_rtl_streaming_metric, minn_rtl.py:583-733.
+ * x: (n_frames, n_branches, n) complex128 or complex64.  All outputs float64[n_frames][n] (stride n)
+ * except the two uint8 masks.  Bit-equal to the reference on integer-valued input. */
+int ofs_minn_rtl_metric(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_branches, int64_t n,
+                        int32_t quarter_len, int32_t smooth_shift, int32_t threshold_value, int32_t frac_bits,
+                        double *corr_total, double *corr_positive, double *smooth_metric, double *energy_total,
+                        double *corr_scaled, double *energy_scaled, uint8_t *metric_valid, uint8_t *above,
+                        void *stream);
+/* Integer RTL datapath -- ref/minn_antenna_path.sv:63-194, ref/minn_preamble_detector.sv:247-325.
+ * iq: int16 (n_frames, n_branches, n, 2).  lag_extra: 0 (minn_rtl.py lag Q) or 1 (registered delay-line
+ * read of the SV).  Outputs int64[n_frames][n] + masks. */
+int ofs_minn_rtl_int(const int16_t *iq, int64_t n_frames, int32_t n_branches, int64_t n, int32_t quarter_len,
+                     int32_t smooth_shift, int32_t threshold_value, int32_t frac_bits, int32_t lag_extra,
+                     int64_t *corr_total, int64_t *corr_positive, int64_t *smooth_metric, int64_t *energy_total,
+                     uint8_t *metric_valid, uint8_t *above, void *stream);
+
+/* Zadoff-Chu ---------------------------------------------------------------------------------------
+ * Matched filter by FFT overlap-save: corr = x (*) conj(ref[::-1]) and energy = |x|^2 (*) ones(nr),
+ * full length n + nr - 1 -- zc.py:115-117, zc_v2.py:244-254,268.  x: (n_frames, n_branches, n).
+ * mode 0 (zc.py:118-126): sum branches, then corr / (||ref|| * sqrt(max(pow,0) + 1e-12)) -> corr_out.
+ * mode 1 (zc_v2.py:488-495): normalise each branch by ||ref||*sqrt(max(E,1e-12)), then sum.
+ * mode 2: raw branch-summed numerator (normalize=False).
+ * corr_out: complex (c64 or c128 per out_f64) [n_frames][n+nr-1]; mag_out (optional): |corr|. */
+int ofs_zc_matched_filter(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_branches, int64_t n,
+                          const void *ref_c128, int32_t nr, int32_t mode, int32_t out_f64, void *corr_out,
+                          void *mag_out, int64_t out_stride, void *stream);
+/* zc_freq.compute_frequency_metric -- zc_freq.py:62-99, as a sliding DFT of the used bins.
+ * bins: DFT bin numbers k_j in [0, n_fft); templ: complex128[nbins].  metric: [n_frames][n-(n_fft+cp)+1]. */
+int ofs_zc_freq_metric(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_branches, int64_t n,
+                       int32_t n_fft, int32_t cp, const int32_t *bins, const void *templ_c128, int32_t nbins,
+                       double templ_energy, int32_t out_f64, void *metric, int64_t out_stride, void *stream);
+/* End-to-end sync over HOST buffers --------------------------------------------------------------- */
+typedef struct ofs_ctx ofs_ctx;
+int ofs_ctx_create(ofs_ctx **ctx, int device);
+void ofs_ctx_destroy(ofs_ctx *ctx);
+void *ofs_host_alloc(size_t bytes);  /* pinned */
+void ofs_host_free(void *p);
+
+typedef struct ofs_sync_record {
+    int64_t timing;      /* SC: plateau_end; MINN: peak */
+    int64_t coarse;      /* SC: max(plateau_end - delta, 0); MINN: peak */
+    float metric;        /* M at the timing index */
+    float p_re, p_im;    /* P at the coarse/timing index (float64 recompute, stored as float) */
+    float cfo;           /* -angle(P)/(2*pi*lag) cycles/sample (lag = N/2 for SC, N/4 for MINN) */
+} ofs_sync_record;
+
+/* One call = "sync metric + CFO" for a batch of frames (the BASELINE.json headline):
+ *   metric (ofs_metric, stripe path) -> detector (SC: plateau, MINN: find_minn_peak) -> P at the
+ *   detected index -> CFO.  Device version: x, M, records are device pointers. */
+int ofs_sync(const ofs_metric_desc *d, const void *x, float *M, float *chunk_max, int64_t cm_stride,
+             int32_t cp_len, int32_t smooth_win, int32_t sc_delta, double gate_threshold,
+             ofs_sync_record *records, int64_t *scratch /* int64[3*n_frames] */, void *stream);
+/* Second half of ofs_sync alone (detector + P/CFO records on an already computed metric). */
+int ofs_sync_detect(const ofs_metric_desc *d, const void *x, const float *M, int32_t cp_len, int32_t smooth_win,
+                    int32_t sc_delta, double gate_threshold, ofs_sync_record *records, int64_t *scratch,
+                    void *stream);
+/* Host version: x_host (n_frames x n_samples, dtype per d->in_dtype), M_host optional (float32
+ * [n_frames][out_stride]); records_host[n_frames].  Frames are pipelined through the ctx workspace
+ * in batches (H2D, kernels, D2H overlapped on three streams). */
+int ofs_sync_host(ofs_ctx *ctx, const ofs_metric_desc *d, const void *x_host, float *M_host,
+                  int32_t cp_len, int32_t smooth_win, int32_t sc_delta, double gate_threshold,
+                  ofs_sync_record *records_host);
+/* kernels launched by this library on the calling thread since load (for bench.py's gpu_launches) */
+int64_t ofs_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFDMSYNC_H */

@@ -1,0 +1,302 @@
+// C-ABI entry points of libofdmsync: library/error plumbing, ofs_metric dispatch and the
+// end-to-end "sync metric + CFO" pipeline (device and host-buffer versions).
+#include "common.cuh"
+#include <string.h>
+#include <new>
+
+namespace ofs {
+
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int64_t &launch_counter() { return g_launches; }
+
+int sm_count()
+{
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            cached = 148;
+    }
+    return cached;
+}
+
+int launch_metric_tile(const ofs_metric_desc *d, const void *x, void *M, void *P, void *R, cudaStream_t stream);
+int launch_metric_stripe(const ofs_metric_desc *d, const void *x, float *M, float *chunk_max, int64_t cm_stride,
+                         cudaStream_t stream);
+bool stripe_supported(const ofs_metric_desc *d);
+
+static int check_desc(const ofs_metric_desc *d, const char *who)
+{
+    OFS_REQUIRE(d, "%s: null descriptor", who);
+    OFS_REQUIRE(d->kind >= OFS_SC && d->kind <= OFS_AA, "%s: unknown metric kind %d", who, d->kind);
+    OFS_REQUIRE(d->in_dtype >= OFS_C64 && d->in_dtype <= OFS_IQ16, "%s: unknown input dtype %d", who, d->in_dtype);
+    OFS_REQUIRE(d->symbol_len > 0, "%s: symbol_len must be positive", who);
+    OFS_REQUIRE(d->kind == OFS_AA || d->kind == OFS_MINN || d->symbol_len % 2 == 0,
+                "%s: symbol_len must be even for Schmidl-Cox", who);
+    OFS_REQUIRE(d->n_branches >= 1 && d->n_frames >= 0 && d->n_samples >= 0, "%s: bad batch geometry", who);
+    OFS_REQUIRE(d->x_branch_stride >= d->n_samples || d->n_branches == 1, "%s: branch stride < n_samples", who);
+    OFS_REQUIRE(d->x_frame_stride >= d->n_samples, "%s: frame stride < n_samples", who);
+    return OFS_OK;
+}
+
+// ---- P at one index per frame, in float64, + record (one warp per frame) -------------------------
+__global__ void sync_record_kernel(const void *x, int dtype, int64_t L, int64_t xfs, int kind, int N,
+                                   const float *M, int64_t out_stride, int64_t out_len, const int64_t *timing,
+                                   int sc_delta, ofs_sync_record *rec, int64_t n_frames)
+{
+    const int64_t frame = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (frame >= n_frames) return;
+    int64_t t = timing[frame];
+    int64_t coarse = t;
+    if (kind != OFS_MINN) coarse = t - sc_delta > 0 ? t - sc_delta : 0;     // sc.py:211
+    if (coarse > out_len - 1) coarse = out_len - 1;
+    if (coarse < 0) coarse = 0;
+    const size_t esz = dtype == OFS_C64 ? 8 : (dtype == OFS_C128 ? 16 : 4);
+    const void *xr = reinterpret_cast<const unsigned char *>(x) + (size_t)frame * xfs * esz;
+    double pr = 0.0, pi = 0.0;
+    const int lag = kind == OFS_MINN ? N / 4 : N / 2;
+    const int nwin = kind == OFS_MINN ? 2 : 1;
+    for (int wdw = 0; wdw < nwin; ++wdw) {
+        const int64_t base = coarse + (int64_t)wdw * 2 * lag;
+        for (int m = lane; m < lag; m += 32) {
+            const double2 a = load_sample_f64(xr, dtype, base + m);
+            const double2 b = load_sample_f64(xr, dtype, base + lag + m);
+            pr += a.x * b.x + a.y * b.y;
+            pi += a.y * b.x - a.x * b.y;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { pr += shfl_xor_f64(pr, o); pi += shfl_xor_f64(pi, o); }
+    if (lane == 0) {
+        ofs_sync_record r;
+        r.timing = t; r.coarse = coarse;
+        r.metric = M ? M[frame * out_stride + coarse] : 0.f;
+        r.p_re = (float)pr; r.p_im = (float)pi;
+        r.cfo = (float)(-atan2(pi, pr) / (2.0 * 3.14159265358979323846 * (double)lag));
+        rec[frame] = r;
+    }
+}
+
+}  // namespace ofs
+
+using namespace ofs;
+
+OFS_API int ofs_version(void) { return OFS_ABI_VERSION; }
+OFS_API const char *ofs_last_error_string(void) { return g_err; }
+OFS_API int64_t ofs_launch_count(void) { return g_launches; }
+OFS_API int32_t ofs_chunk_len(void) { return 256; }
+
+OFS_API int64_t ofs_metric_out_len(const ofs_metric_desc *d)
+{
+    if (!d) return 0;
+    if (d->kind == OFS_AA) return d->n_samples;
+    const int64_t n = d->n_samples - d->symbol_len + 1;
+    return n > 0 ? n : 0;
+}
+
+OFS_API int ofs_metric_stripe_ok(const ofs_metric_desc *d, const void *x, const void *M)
+{
+    (void)x; (void)M;
+    return d && check_desc(d, "ofs_metric_stripe_ok") == OFS_OK && stripe_supported(d) ? 1 : 0;
+}
+
+OFS_API int ofs_metric(const ofs_metric_desc *d, const void *x, void *M, void *P, void *R, float *chunk_max,
+                       int64_t cm_stride, void *stream)
+{
+    if (int rc = check_desc(d, "ofs_metric")) return rc;
+    const int64_t out_len = ofs_metric_out_len(d);
+    if (out_len == 0 || d->n_frames == 0) return OFS_OK;
+    OFS_REQUIRE(x, "ofs_metric: null input");
+    OFS_REQUIRE(M || P || R || chunk_max, "ofs_metric: no output requested");
+    OFS_REQUIRE(d->out_stride >= out_len, "ofs_metric: out_stride %lld < out_len %lld", (long long)d->out_stride,
+                (long long)out_len);
+    int path = d->path;
+    if (path == OFS_PATH_AUTO) path = (stripe_supported(d) && !P && !R) ? OFS_PATH_STRIPE : OFS_PATH_TILE;
+    if (path == OFS_PATH_STRIPE) {
+        OFS_REQUIRE(!P && !R, "ofs_metric: the stripe path writes M only (P, R must be NULL)");
+        OFS_REQUIRE(!chunk_max || cm_stride >= (d->n_samples + 255) / 256, "ofs_metric: cm_stride too small");
+        return launch_metric_stripe(d, x, (float *)M, chunk_max, cm_stride, (cudaStream_t)stream);
+    }
+    OFS_REQUIRE(path == OFS_PATH_TILE, "ofs_metric: unknown path %d", path);
+    OFS_REQUIRE(!chunk_max, "ofs_metric: chunk_max is produced by the stripe path only");
+    return launch_metric_tile(d, x, M, P, R, (cudaStream_t)stream);
+}
+
+OFS_API int ofs_sync_detect(const ofs_metric_desc *d, const void *x, const float *M, int32_t cp_len, int32_t smooth_win,
+                            int32_t sc_delta, double gate_threshold, ofs_sync_record *records, int64_t *scratch,
+                            void *stream)
+{
+    if (int rc = check_desc(d, "ofs_sync_detect")) return rc;
+    OFS_REQUIRE(d->kind == OFS_SC || d->kind == OFS_SC_BOTH || d->kind == OFS_MINN, "ofs_sync: kind must be SC or MINN");
+    OFS_REQUIRE(x && M && records && scratch, "ofs_sync: null argument");
+    OFS_REQUIRE(d->n_branches == 1, "ofs_sync: one branch per frame");
+    const int64_t out_len = ofs_metric_out_len(d);
+    OFS_REQUIRE(out_len > 0, "ofs_sync: frames shorter than one symbol");
+    if (d->n_frames == 0) return OFS_OK;
+    ofs_rows rows{M, 0, 0, d->n_frames, out_len, d->out_stride};
+    int64_t *timing = scratch;
+    if (d->kind == OFS_MINN) {
+        if (int rc = ofs_find_minn_peak(&rows, smooth_win, gate_threshold, 0, 0, 0, timing, scratch + d->n_frames, nullptr, stream))
+            return rc;
+    } else {
+        if (int rc = ofs_find_plateau_end(&rows, cp_len, cp_len / 4, smooth_win, timing, stream)) return rc;
+    }
+    const int wpb = 4;
+    sync_record_kernel<<<(unsigned)((d->n_frames + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        x, d->in_dtype, d->n_samples, d->x_frame_stride, d->kind, d->symbol_len, M, d->out_stride, out_len, timing,
+        sc_delta, records, d->n_frames);
+    return check_launch("sync_record_kernel");
+}
+
+OFS_API int ofs_sync(const ofs_metric_desc *d, const void *x, float *M, float *chunk_max, int64_t cm_stride,
+                     int32_t cp_len, int32_t smooth_win, int32_t sc_delta, double gate_threshold,
+                     ofs_sync_record *records, int64_t *scratch, void *stream)
+{
+    if (int rc = check_desc(d, "ofs_sync")) return rc;
+    OFS_REQUIRE(x && M && records && scratch, "ofs_sync: null argument");
+    OFS_REQUIRE(d->out_f64 == 0, "ofs_sync: float32 metric only");
+    if (d->n_frames == 0) return OFS_OK;
+    if (int rc = ofs_metric(d, x, M, nullptr, nullptr, chunk_max, cm_stride, stream)) return rc;
+    return ofs_sync_detect(d, x, M, cp_len, smooth_win, sc_delta, gate_threshold, records, scratch, stream);
+}
+
+// ---- host-buffer pipeline -------------------------------------------------------------------------
+struct ofs_ctx {
+    int device;
+    cudaStream_t s_h2d, s_comp, s_d2h;
+    cudaEvent_t ev_h2d[2], ev_comp[2], ev_d2h[2];
+    void *x_dev[2];
+    float *m_dev[2];
+    float *cm_dev[2];
+    ofs_sync_record *rec_dev[2];
+    int64_t *scratch[2];
+    size_t x_cap, m_cap, cm_cap, rec_cap;
+};
+
+OFS_API int ofs_ctx_create(ofs_ctx **out, int device)
+{
+    OFS_REQUIRE(out, "ofs_ctx_create: null output");
+    OFS_CUDA(cudaSetDevice(device));
+    ofs_ctx *c = new (std::nothrow) ofs_ctx();
+    OFS_REQUIRE(c, "ofs_ctx_create: out of host memory");
+    memset(c, 0, sizeof(*c));
+    c->device = device;
+    OFS_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    OFS_CUDA(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+    OFS_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        OFS_CUDA(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+        OFS_CUDA(cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming));
+        OFS_CUDA(cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming));
+    }
+    *out = c;
+    return OFS_OK;
+}
+
+static void ctx_free_buffers(ofs_ctx *c)
+{
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->x_dev[i]); cudaFree(c->m_dev[i]); cudaFree(c->cm_dev[i]); cudaFree(c->rec_dev[i]); cudaFree(c->scratch[i]);
+        c->x_dev[i] = nullptr; c->m_dev[i] = nullptr; c->cm_dev[i] = nullptr; c->rec_dev[i] = nullptr; c->scratch[i] = nullptr;
+    }
+    c->x_cap = c->m_cap = c->cm_cap = c->rec_cap = 0;
+}
+
+OFS_API void ofs_ctx_destroy(ofs_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    ctx_free_buffers(c);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->ev_h2d[i]); cudaEventDestroy(c->ev_comp[i]); cudaEventDestroy(c->ev_d2h[i]); }
+    cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_comp); cudaStreamDestroy(c->s_d2h);
+    delete c;
+}
+
+OFS_API void *ofs_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { set_error("ofs_host_alloc(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+OFS_API void ofs_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+OFS_API int ofs_sync_host(ofs_ctx *c, const ofs_metric_desc *d, const void *x_host, float *M_host, int32_t cp_len,
+                          int32_t smooth_win, int32_t sc_delta, double gate_threshold, ofs_sync_record *records_host)
+{
+    OFS_REQUIRE(c, "ofs_sync_host: null context");
+    if (int rc = check_desc(d, "ofs_sync_host")) return rc;
+    OFS_REQUIRE(x_host && records_host, "ofs_sync_host: null argument");
+    OFS_REQUIRE(d->n_branches == 1, "ofs_sync_host: one branch per frame");
+    const int64_t out_len = ofs_metric_out_len(d);
+    OFS_REQUIRE(out_len > 0, "ofs_sync_host: frames shorter than one symbol");
+    if (d->n_frames == 0) return OFS_OK;
+    OFS_CUDA(cudaSetDevice(c->device));
+    const size_t esz = dtype_bytes(d->in_dtype);
+    const int64_t L = d->n_samples;
+    const int toff = d->symbol_len - 1;
+    const int64_t xpitch = (L + 3) / 4 * 4;                 // samples; keeps every frame 16-byte aligned
+    const int64_t mpitch = (L + 3) / 4 * 4;                 // floats, causal-time rows (d = t - toff)
+    const int64_t cmpitch = (L + 255) / 256;
+    int64_t FB = (int64_t)(256ull << 20) / (int64_t)(xpitch * esz);   // ~256 MB of samples per batch
+    if (FB < 1) FB = 1;
+    if (FB > d->n_frames) FB = d->n_frames;
+    const size_t x_need = (size_t)FB * xpitch * esz, m_need = (size_t)FB * mpitch * sizeof(float) + 64;
+    const size_t cm_need = (size_t)FB * cmpitch * sizeof(float), rec_need = (size_t)FB;
+    if (x_need > c->x_cap || m_need > c->m_cap || cm_need > c->cm_cap || rec_need > c->rec_cap) {
+        cudaDeviceSynchronize();
+        ctx_free_buffers(c);
+        for (int i = 0; i < 2; ++i) {
+            OFS_CUDA(cudaMalloc(&c->x_dev[i], x_need));
+            OFS_CUDA(cudaMalloc((void **)&c->m_dev[i], m_need));
+            OFS_CUDA(cudaMalloc((void **)&c->cm_dev[i], cm_need));
+            OFS_CUDA(cudaMalloc((void **)&c->rec_dev[i], rec_need * sizeof(ofs_sync_record)));
+            OFS_CUDA(cudaMalloc((void **)&c->scratch[i], rec_need * 3 * sizeof(int64_t)));
+        }
+        c->x_cap = x_need; c->m_cap = m_need; c->cm_cap = cm_need; c->rec_cap = rec_need;
+    }
+    const int64_t nbatch = (d->n_frames + FB - 1) / FB;
+    for (int64_t b = 0; b < nbatch; ++b) {
+        const int s = (int)(b & 1);
+        const int64_t f0 = b * FB, nf = (f0 + FB <= d->n_frames) ? FB : d->n_frames - f0;
+        // slot reuse: x_dev[s] was read by the kernels of batch b-2, m_dev[s] by its D2H copies
+        if (b >= 2) { OFS_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_comp[s], 0)); }
+        OFS_CUDA(cudaMemcpy2DAsync(c->x_dev[s], (size_t)xpitch * esz,
+                                   (const unsigned char *)x_host + (size_t)f0 * d->x_frame_stride * esz,
+                                   (size_t)d->x_frame_stride * esz, (size_t)L * esz, (size_t)nf, cudaMemcpyHostToDevice, c->s_h2d));
+        OFS_CUDA(cudaEventRecord(c->ev_h2d[s], c->s_h2d));
+        OFS_CUDA(cudaStreamWaitEvent(c->s_comp, c->ev_h2d[s], 0));
+        if (b >= 2) { OFS_CUDA(cudaStreamWaitEvent(c->s_comp, c->ev_d2h[s], 0)); }
+        ofs_metric_desc dd = *d;
+        dd.n_frames = nf; dd.x_frame_stride = xpitch; dd.out_stride = mpitch; dd.path = OFS_PATH_AUTO;
+        float *Md0 = c->m_dev[s] + toff;      // element d = 0 of frame 0; (Md0 - toff) is 256-byte aligned
+        if (int rc = ofs_sync(&dd, c->x_dev[s], Md0, c->cm_dev[s], cmpitch, cp_len, smooth_win, sc_delta, gate_threshold,
+                              c->rec_dev[s], c->scratch[s], c->s_comp))
+            return rc;
+        OFS_CUDA(cudaEventRecord(c->ev_comp[s], c->s_comp));
+        OFS_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[s], 0));
+        if (M_host)
+            OFS_CUDA(cudaMemcpy2DAsync(M_host + (size_t)f0 * d->out_stride, (size_t)d->out_stride * sizeof(float), Md0,
+                                       (size_t)mpitch * sizeof(float), (size_t)out_len * sizeof(float), (size_t)nf,
+                                       cudaMemcpyDeviceToHost, c->s_d2h));
+        OFS_CUDA(cudaMemcpyAsync(records_host + f0, c->rec_dev[s], (size_t)nf * sizeof(ofs_sync_record), cudaMemcpyDeviceToHost,
+                                 c->s_d2h));
+        OFS_CUDA(cudaEventRecord(c->ev_d2h[s], c->s_d2h));
+    }
+    OFS_CUDA(cudaStreamSynchronize(c->s_d2h));
+    OFS_CUDA(cudaStreamSynchronize(c->s_comp));
+    return OFS_OK;
+}

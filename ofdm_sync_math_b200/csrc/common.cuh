@@ -1,0 +1,171 @@
+// Shared helpers for libofdmsync (sm_100a).  Product code: nothing here touches oracle/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/ofdmsync.h"
+
+#define OFS_API extern "C" __attribute__((visibility("default")))
+
+namespace ofs {
+
+// ---- error reporting (thread-local string, int codes across the ABI) -------------------------
+void set_error(const char *fmt, ...);
+int64_t &launch_counter();
+inline void count_launch(int n = 1) { launch_counter() += n; }
+
+#define OFS_REQUIRE(cond, ...)                      \
+    do {                                            \
+        if (!(cond)) {                              \
+            ofs::set_error(__VA_ARGS__);            \
+            return OFS_EINVAL;                      \
+        }                                           \
+    } while (0)
+
+#define OFS_CUDA(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            ofs::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return (int)_e;                                                                 \
+        }                                                                                   \
+    } while (0)
+
+inline int check_launch(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    count_launch();
+    return OFS_OK;
+}
+
+int sm_count();  // cached multiprocessor count of the current device
+
+// ---- device helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// mbarrier + 1-D bulk TMA (cp.async.bulk) -- SASS: SYNCS.* / UBLKCP
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t a = smem_u32(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(a),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void *gmem_dst, const void *smem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+                 "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ double shfl_up_f64(double v, int delta)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_up_sync(0xffffffffu, lo, delta);
+    hi = __shfl_up_sync(0xffffffffu, hi, delta);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_f64(double v, int src)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_sync(0xffffffffu, lo, src);
+    hi = __shfl_sync(0xffffffffu, hi, src);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_xor_f64(double v, int m)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_xor_sync(0xffffffffu, lo, m);
+    hi = __shfl_xor_sync(0xffffffffu, hi, m);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ long long shfl_xor_i64(long long v, int m)
+{
+    int lo = (int)(v & 0xffffffffll), hi = (int)(v >> 32);
+    lo = __shfl_xor_sync(0xffffffffu, lo, m);
+    hi = __shfl_xor_sync(0xffffffffu, hi, m);
+    return ((long long)hi << 32) | (unsigned int)lo;
+}
+
+// sample loads as double2 from any input format
+template <int DT>
+struct InT;
+template <>
+struct InT<OFS_C64> {
+    using type = float2;
+    static constexpr int bytes = 8;
+};
+template <>
+struct InT<OFS_C128> {
+    using type = double2;
+    static constexpr int bytes = 16;
+};
+template <>
+struct InT<OFS_IQ16> {
+    using type = short2;
+    static constexpr int bytes = 4;
+};
+
+__device__ __forceinline__ double2 load_sample_f64(const void *base, int dtype, int64_t idx)
+{
+    if (dtype == OFS_C64) {
+        float2 v = __ldg(reinterpret_cast<const float2 *>(base) + idx);
+        return make_double2((double)v.x, (double)v.y);
+    } else if (dtype == OFS_C128) {
+        return __ldg(reinterpret_cast<const double2 *>(base) + idx);
+    } else {
+        short2 v = __ldg(reinterpret_cast<const short2 *>(base) + idx);
+        return make_double2((double)v.x, (double)v.y);
+    }
+}
+
+inline size_t dtype_bytes(int dt) { return dt == OFS_C64 ? 8 : (dt == OFS_C128 ? 16 : 4); }
+
+}  // namespace ofs

@@ -1,0 +1,695 @@
+// Detector kernels (K2): one CTA per metric row.  Parallel restatements of the reference's
+// sequential Python detectors; every tie / edge rule of SURVEY.md 8a is kept:
+//   sc.find_plateau_end_from_metric           sc.py:81-146
+//   minn._trailing_average / find_minn_peak   minn.py:115-205
+//   combined_sc_min gate + gated peak         combined_sc_min.py:183-259, 337-351
+//   sync_aa gate FSM                          sync_aa.py:495-568
+//   zc_v2 threshold + gate FSM                zc_v2.py:288-336, 360-450
+//   minn_rtl gate FSM                         minn_rtl.py:750-825 (ref/minn_preamble_detector.sv:337-384)
+// All comparisons are done in float64 on the stored metric values.
+//
+// The gate FSMs are evaluated as interval logic on a shared-memory bitmask of the "above
+// threshold" flags: a gate is a maximal cluster of above-samples whose gaps are shorter than the
+// hysteresis; it closes at (last above) + H; the peak is a block-parallel arg-max over
+// [open, close] with the reference's tie rule (first max for `>`, last max for `>=`).
+#include "common.cuh"
+
+namespace ofs {
+
+constexpr int DNT = 256;                    // threads per row-CTA
+constexpr int64_t MASK_MAX_N = 1600000;     // row length limit of the bitmask kernels (200 KB of smem)
+
+struct RowView {
+    const void *data;
+    int f64;
+    int64_t n, stride;
+    __device__ __forceinline__ double at(int64_t row, int64_t i) const
+    {
+        return f64 ? reinterpret_cast<const double *>(data)[row * stride + i]
+                   : (double)reinterpret_cast<const float *>(data)[row * stride + i];
+    }
+};
+
+// ---- block reductions ----------------------------------------------------------------------
+struct ArgVal {
+    double v;
+    long long i;
+};
+template <bool LAST>
+__device__ __forceinline__ ArgVal better(ArgVal a, ArgVal b)
+{
+    if (b.i < 0) return a;
+    if (a.i < 0) return b;
+    if (b.v > a.v) return b;
+    if (b.v < a.v) return a;
+    if (LAST) return (b.i > a.i) ? b : a;
+    return (b.i < a.i) ? b : a;
+}
+template <bool LAST>
+__device__ ArgVal block_argmax(ArgVal x, ArgVal *sh /* DNT/32 */)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ArgVal y;
+        y.v = shfl_xor_f64(x.v, o);
+        y.i = shfl_xor_i64(x.i, o);
+        x = better<LAST>(x, y);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[warp] = x;
+    __syncthreads();
+    ArgVal r = sh[0];
+    for (int w = 1; w < DNT / 32; ++w) r = better<LAST>(r, sh[w]);
+    return r;
+}
+__device__ long long block_min_i64(long long x, long long *sh)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        long long y = shfl_xor_i64(x, o);
+        x = y < x ? y : x;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[warp] = x;
+    __syncthreads();
+    long long r = sh[0];
+    for (int w = 1; w < DNT / 32; ++w) r = sh[w] < r ? sh[w] : r;
+    return r;
+}
+
+// ---- S&C plateau end -------------------------------------------------------------------------------
+struct SmoothSame {   // np.convolve(M, ones(w)/w, "same")[i], sc.py:100
+    RowView r;
+    int64_t row, ms;
+    int w, off;
+    double h;
+    __device__ __forceinline__ double operator()(int64_t i) const
+    {
+        const int64_t k = i + off;
+        int64_t jlo = k - w + 1;
+        if (jlo < 0) jlo = 0;
+        const int64_t jhi = k < r.n - 1 ? k : r.n - 1;
+        double s = 0.0;
+        for (int64_t j = jlo; j <= jhi; ++j) s = fma(r.at(row, j), h, s);
+        return s;
+    }
+};
+
+__global__ void __launch_bounds__(DNT) plateau_kernel(RowView r, int cp_len, int lookahead, int smooth_win,
+                                                      int64_t *out)
+{
+    __shared__ ArgVal sh_av[DNT / 32];
+    __shared__ long long sh_i[DNT / 32];
+    const int64_t row = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (r.n == 0) { if (tid == 0) out[row] = 0; return; }
+    const int Lk = lookahead < 0 ? cp_len / 4 : (lookahead > 1 ? lookahead : 1);
+    const int w = smooth_win > 1 ? smooth_win : 1;
+    SmoothSame Ms;
+    Ms.r = r; Ms.row = row; Ms.w = w; Ms.h = 1.0 / (double)w;
+    Ms.ms = r.n > w ? r.n : w;
+    Ms.off = (int)(((r.n > w ? (int64_t)w : r.n) - 1) / 2);
+    const int64_t ms = Ms.ms;
+
+    // pass A: center = first argmax of the smoothed metric (sc.py:106)
+    ArgVal best{0.0, -1};
+    for (int64_t i = tid; i < ms; i += DNT) {
+        const double v = Ms(i);
+        if (best.i < 0 || v > best.v) { best.v = v; best.i = i; }
+    }
+    best = block_argmax<false>(best, sh_av);
+    const int64_t center = best.i;
+    const double peak = best.v;
+
+    // pass B: first index in [center, center+cp) at or below 95 % of the maximum (sc.py:107-114)
+    const int64_t post_hi = ms < center + cp_len ? ms : center + cp_len;
+    if (post_hi > center + 1) {
+        const double thr = 0.95 * peak;
+        long long first = LLONG_MAX;
+        for (int64_t i = center + tid; i < post_hi; i += DNT)
+            if (Ms(i) <= thr) { first = i; break; }
+        first = block_min_i64(first, sh_i);
+        if (first != LLONG_MAX) { if (tid == 0) out[row] = first; return; }
+    }
+
+    // pass C: right edge of the earliest run >= 60 % of the peak with length >= max(8, cp/2) (sc.py:117-133)
+    if (peak > 0.0) {
+        const double thr = 0.6 * peak;
+        const int64_t min_run = cp_len / 2 > 8 ? cp_len / 2 : 8;
+        __shared__ long long sh_res;
+        if (tid < 32) {                      // warp 0 walks the row, 32 flags per step
+            long long res = -1, run_start = -1;
+            for (int64_t base = 0; base < ms && res < 0; base += 32) {
+                const int64_t i = base + tid;
+                const bool f = i < ms && Ms(i) >= thr;
+                const unsigned m = __ballot_sync(0xffffffffu, f);
+                const int nbits = (int)(ms - base < 32 ? ms - base : 32);
+                if (m == 0u) {
+                    if (run_start >= 0 && base - run_start >= min_run) res = base - 1;
+                    run_start = -1;
+                } else if (nbits == 32 && m == 0xffffffffu) {
+                    if (run_start < 0) run_start = base;
+                } else {
+                    for (int b = 0; b < nbits && res < 0; ++b) {
+                        if ((m >> b) & 1u) { if (run_start < 0) run_start = base + b; }
+                        else {
+                            if (run_start >= 0 && base + b - run_start >= min_run) res = base + b - 1;
+                            run_start = -1;
+                        }
+                    }
+                }
+            }
+            if (res < 0 && run_start >= 0 && ms - run_start >= min_run) res = ms - 1;
+            if (tid == 0) sh_res = res;
+        }
+        __syncthreads();
+        if (sh_res >= 0) { if (tid == 0) out[row] = sh_res; return; }
+    }
+
+    // pass D: largest drop over the lookahead around the strongest plateau (sc.py:136-146)
+    {
+        const int64_t lo = center - cp_len > 0 ? center - cp_len : 0;
+        const int64_t hi = ms - Lk - 1 < center + cp_len ? ms - Lk - 1 : center + cp_len;
+        int64_t hi_eff = hi;                       // python slice semantics for a negative stop
+        if (hi_eff < 0) hi_eff += ms;
+        if (hi_eff < 0) hi_eff = 0;
+        if (hi_eff > ms) hi_eff = ms;
+        int64_t hi2 = hi + Lk, lo2 = lo + Lk;
+        if (hi2 < 0) hi2 += ms;
+        if (hi2 < 0) hi2 = 0;
+        if (hi2 > ms) hi2 = ms;
+        if (lo2 > ms) lo2 = ms;
+        const int64_t wl = hi_eff - lo, al = hi2 - lo2;
+        if (wl <= 0 || al <= 0 || wl != al) { if (tid == 0) out[row] = center; return; }
+        ArgVal bd{0.0, -1};
+        for (int64_t i = tid; i < wl; i += DNT) {
+            const double dv = Ms(lo + i) - Ms(lo2 + i);
+            if (bd.i < 0 || dv > bd.v) { bd.v = dv; bd.i = i; }
+        }
+        bd = block_argmax<false>(bd, sh_av);
+        if (tid == 0) out[row] = lo + bd.i + Lk / 2;
+    }
+}
+
+// ---- trailing average (minn.py:115-128) as a pure function of the index ---------------------------
+struct Trailing {
+    RowView r;
+    int64_t row;
+    int w;
+    __device__ __forceinline__ double operator()(int64_t i) const
+    {
+        if (w <= 1) { const double v = r.at(row, i); return v > 0.0 ? v : 0.0; }
+        int64_t jlo = i - w + 1;
+        if (jlo < 0) jlo = 0;
+        double s = 0.0;
+        for (int64_t j = jlo; j <= i; ++j) { const double v = r.at(row, j); s += v > 0.0 ? v : 0.0; }
+        return s / (double)(i >= w - 1 ? w : i + 1);
+    }
+};
+
+// scan a bitmask for the longest run of ones (earliest on ties); single thread, word-at-a-time
+__device__ void longest_run(const unsigned *mask, int64_t n, long long &bs, long long &be)
+{
+    long long best_len = 0, start = -1;
+    bs = 0; be = 0;
+    const int64_t nw = (n + 31) / 32;
+    for (int64_t wi = 0; wi < nw; ++wi) {
+        const unsigned m = mask[wi];
+        const int64_t base = wi * 32;
+        const int nbits = (int)(n - base < 32 ? n - base : 32);
+        if (m == 0u) {
+            if (start >= 0) { if (base - start > best_len) { best_len = base - start; bs = start; be = base; } start = -1; }
+        } else if (nbits == 32 && m == 0xffffffffu) {
+            if (start < 0) start = base;
+        } else {
+            for (int b = 0; b < nbits; ++b) {
+                if ((m >> b) & 1u) { if (start < 0) start = base + b; }
+                else if (start >= 0) {
+                    if (base + b - start > best_len) { best_len = base + b - start; bs = start; be = base + b; }
+                    start = -1;
+                }
+            }
+        }
+    }
+    if (start >= 0 && n - start > best_len) { bs = start; be = n; }
+}
+
+__global__ void __launch_bounds__(DNT) minn_peak_kernel(RowView r, int smooth_win, double gate_threshold,
+                                                        int has_bounds, int64_t b_lo, int64_t b_hi, int64_t *peak,
+                                                        int64_t *gate_span, void *Ms_out)
+{
+    extern __shared__ unsigned mask[];
+    __shared__ ArgVal sh_av[DNT / 32];
+    __shared__ long long sh_span[2];
+    const int64_t row = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t n = r.n;
+    if (n == 0) { if (tid == 0) { peak[row] = -1; gate_span[2 * row] = gate_span[2 * row + 1] = 0; } return; }
+    Trailing Ms{r, row, smooth_win > 1 ? smooth_win : 1};
+
+    // pass 1: global first-argmax of Ms (also the fallback answer), optional Ms output
+    ArgVal best{0.0, -1};
+    for (int64_t i = tid; i < n; i += DNT) {
+        const double v = Ms(i);
+        if (Ms_out) {
+            if (r.f64) reinterpret_cast<double *>(Ms_out)[row * r.stride + i] = v;
+            else reinterpret_cast<float *>(Ms_out)[row * r.stride + i] = (float)v;
+        }
+        if (best.i < 0 || v > best.v) { best.v = v; best.i = i; }
+    }
+    best = block_argmax<false>(best, sh_av);
+    if (!(best.v > 0.0)) { if (tid == 0) { peak[row] = -2; gate_span[2 * row] = gate_span[2 * row + 1] = 0; } return; }
+
+    // pass 2: gate flags -> bitmask -> longest run (minn.py:155-182)
+    const double level = gate_threshold * best.v;
+    const int64_t nround = ((n + 31) / 32) * 32;
+    for (int64_t i = tid; i < nround; i += DNT) {
+        const bool f = i < n && Ms(i) >= level;
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) mask[i / 32] = m;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        long long bs, be;
+        longest_run(mask, n, bs, be);
+        if (has_bounds) {                                   // minn.py:186-193
+            long long s = b_lo > 0 ? b_lo : 0, e = b_hi < n ? b_hi : n;
+            if (s >= e) { s = 0; e = n; }
+            bs = bs > s ? bs : s;
+            be = be < e ? be : e;
+        }
+        sh_span[0] = bs; sh_span[1] = be;
+    }
+    __syncthreads();
+    const long long gs = sh_span[0], ge = sh_span[1];
+    if (gs >= ge) {                                          // empty gate -> global argmax (minn.py:195-200)
+        if (tid == 0) { peak[row] = best.i; gate_span[2 * row] = best.i; gate_span[2 * row + 1] = best.i + 1; }
+        return;
+    }
+    ArgVal pk{0.0, -1};
+    for (int64_t i = gs + tid; i < ge; i += DNT) {
+        const double v = Ms(i);
+        if (pk.i < 0 || v > pk.v) { pk.v = v; pk.i = i; }
+    }
+    pk = block_argmax<false>(pk, sh_av);
+    if (tid == 0) { peak[row] = pk.i; gate_span[2 * row] = gs; gate_span[2 * row + 1] = ge; }
+}
+
+// ---- combined_sc_min: S&C gate (:337-351) and gated first-segment peak (:183-259) -----------------
+__global__ void __launch_bounds__(DNT) sc_gate_kernel(RowView r, double thr, uint8_t *gate, int64_t gstride)
+{
+    __shared__ ArgVal sh_av[DNT / 32];
+    __shared__ long long sh_i[DNT / 32];
+    const int64_t row = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (r.n == 0) return;
+    ArgVal best{0.0, -1};
+    for (int64_t i = tid; i < r.n; i += DNT) {
+        const double v = r.at(row, i);
+        if (best.i < 0 || v > best.v) { best.v = v; best.i = i; }
+    }
+    best = block_argmax<false>(best, sh_av);
+    long long any = LLONG_MAX;
+    for (int64_t i = tid; i < r.n; i += DNT) {
+        const double v = r.at(row, i);
+        const bool g = best.v > 0.0 ? (v / best.v >= thr) : (v >= thr);
+        gate[row * gstride + i] = g;
+        if (g && any == LLONG_MAX) any = i;
+    }
+    any = block_min_i64(any, sh_i);
+    if (any == LLONG_MAX && tid == 0) gate[row * gstride + best.i] = 1;   // seed with the strongest sample
+}
+
+__global__ void __launch_bounds__(DNT) gated_peak_kernel(RowView r, int smooth_win, const uint8_t *gate,
+                                                         int64_t gstride, int has_bounds, int64_t b_lo,
+                                                         int64_t b_hi, int64_t *peak)
+{
+    __shared__ ArgVal sh_av[DNT / 32];
+    __shared__ long long sh_i[DNT / 32];
+    const int64_t row = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int64_t n = r.n;
+    if (n == 0) { if (tid == 0) peak[row] = -1; return; }
+    int64_t s = 0, e = n;
+    if (has_bounds) {
+        s = b_lo > 0 ? b_lo : 0; e = b_hi < n ? b_hi : n;
+        if (s >= e) { s = 0; e = n; }
+    }
+    const uint8_t *g = gate + row * gstride;
+    long long first = LLONG_MAX;
+    for (int64_t i = s + tid; i < e; i += DNT)
+        if (g[i]) { first = i; break; }
+    first = block_min_i64(first, sh_i);
+    if (first == LLONG_MAX) { if (tid == 0) peak[row] = -3; return; }
+    long long stop = LLONG_MAX;                      // the gate drops -> the streaming detector returns
+    for (int64_t i = first + 1 + tid; i < e; i += DNT)
+        if (!g[i]) { stop = i; break; }
+    stop = block_min_i64(stop, sh_i);
+    if (stop == LLONG_MAX) stop = e;
+    Trailing Ms{r, row, smooth_win > 1 ? smooth_win : 1};
+    ArgVal pk{0.0, -1};
+    for (int64_t i = first + tid; i < stop; i += DNT) {
+        const double v = Ms(i);
+        if (pk.i < 0 || v > pk.v) { pk.v = v; pk.i = i; }
+    }
+    pk = block_argmax<false>(pk, sh_av);
+    if (tid == 0) peak[row] = pk.i;
+}
+
+__global__ void __launch_bounds__(DNT) argmax_kernel(RowView r, int64_t *out)
+{
+    __shared__ ArgVal sh_av[DNT / 32];
+    const int64_t row = blockIdx.x;
+    ArgVal best{0.0, -1};
+    for (int64_t i = threadIdx.x; i < r.n; i += DNT) {
+        const double v = r.at(row, i);
+        if (best.i < 0 || v > best.v) { best.v = v; best.i = i; }
+    }
+    best = block_argmax<false>(best, sh_av);
+    if (threadIdx.x == 0) out[row] = best.i < 0 ? 0 : best.i;
+}
+
+// ---- zc_v2 running-sum threshold (zc_v2.py:288-336) ------------------------------------------------
+// local_sum[i] = sum_{j=max(0,i-W+1)}^{i} mag[j]; valid[i] = i >= W.  (The reference's recurrence
+// `acc + sample - oldest` drifts by ~1e-16 relative; this is the drift-free windowed sum.)
+// One CTA per (row, tile of ZT outputs): float64 inclusive prefix of tile + W-sample halo in smem.
+constexpr int ZT = 2048;
+__global__ void __launch_bounds__(DNT) zc_stream_kernel(RowView r, int W, double thresh_value, double scale,
+                                                        double min_mag, void *local_sum, uint8_t *valid,
+                                                        uint8_t *above, int64_t mstride)
+{
+    extern __shared__ double zs[];              // zs[k] = sum of mag[j0 .. j0+k-1]
+    __shared__ double wtot[DNT / 32];
+    const int64_t row = blockIdx.y;
+    const int64_t i0 = (int64_t)blockIdx.x * ZT;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int64_t j0 = i0 - W + 1;
+    if (j0 < 0) j0 = 0;
+    const int64_t iend = i0 + ZT < r.n ? i0 + ZT : r.n;
+    const int cnt = (int)(iend - j0);           // samples covered
+    for (int k = tid; k < cnt; k += DNT) zs[k + 1] = r.at(row, j0 + k);
+    if (tid == 0) zs[0] = 0.0;
+    __syncthreads();
+    int ipt = (cnt + DNT - 1) / DNT;
+    ipt |= 1;
+    const int s0 = 1 + tid * ipt, s1 = min(s0 + ipt, cnt + 1);
+    double acc = 0.0;
+    for (int s = s0; s < s1; ++s) { acc += zs[s]; zs[s] = acc; }
+    double t = acc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double y = shfl_up_f64(t, o); if (lane >= o) t += y; }
+    if (lane == 31) wtot[warp] = t;
+    __syncthreads();
+    double off = t - acc;
+    for (int w = 0; w < warp; ++w) off += wtot[w];
+    for (int s = s0; s < s1; ++s) zs[s] += off;
+    __syncthreads();
+    for (int64_t i = i0 + tid; i < iend; i += DNT) {
+        int64_t lo = i - W + 1;
+        if (lo < 0) lo = 0;
+        const double sum = zs[i + 1 - j0] - zs[lo - j0];
+        const double m = r.at(row, i);
+        const bool v = i >= W;
+        if (r.f64) reinterpret_cast<double *>(local_sum)[row * r.stride + i] = sum;
+        else reinterpret_cast<float *>(local_sum)[row * r.stride + i] = (float)sum;
+        valid[row * mstride + i] = v;
+        above[row * mstride + i] = v && (m * scale >= sum * thresh_value) && (m >= min_mag);
+    }
+}
+
+// ---- gate / hysteresis FSMs ------------------------------------------------------------------------
+enum { FSM_AA = 0, FSM_ZC = 1, FSM_RTL = 2 };
+
+struct FsmParams {
+    RowView val;              // AA: M rows; ZC: corr_mag rows; RTL: corr_positive rows (f64, or int64 if is_int)
+    const void *P;            // AA: complex rows (same precision as val)
+    const uint8_t *valid, *above;   // ZC / RTL
+    int64_t mstride;
+    int is_int;
+    int L;                    // AA: half length; ZC: reference length; RTL: timing offset
+    int heff;                 // max(hysteresis, 1)
+    double thr, fs;
+    ofs_event *events;
+    int32_t *n_events;
+    uint8_t *gate_mask;       // ZC optional
+};
+
+template <int KIND>
+__device__ __forceinline__ double fsm_track_value(const FsmParams &p, int64_t row, int64_t i)
+{
+    if (KIND == FSM_AA) {
+        if (p.val.f64) {
+            const double2 z = reinterpret_cast<const double2 *>(p.P)[row * p.val.stride + i];
+            return z.x * z.x + z.y * z.y;
+        }
+        const float2 z = reinterpret_cast<const float2 *>(p.P)[row * p.val.stride + i];
+        return (double)z.x * z.x + (double)z.y * z.y;
+    }
+    if (KIND == FSM_RTL && p.is_int)
+        return (double)reinterpret_cast<const long long *>(p.val.data)[row * p.val.stride + i];   // < 2^53
+    return p.val.at(row, i);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(DNT) fsm_kernel(FsmParams p)
+{
+    extern __shared__ unsigned mask[];
+    __shared__ ArgVal sh_av[DNT / 32];
+    __shared__ long long g_start[OFS_MAX_EVENTS], g_close[OFS_MAX_EVENTS];
+    __shared__ int g_closed[OFS_MAX_EVENTS];
+    __shared__ int g_count;
+    const int64_t row = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t n = p.val.n;
+
+    // 1. above-threshold flags of the valid samples -> bitmask
+    const int64_t nround = ((n + 31) / 32) * 32;
+    for (int64_t i = tid; i < nround; i += DNT) {
+        bool f = false;
+        if (i < n) {
+            if (KIND == FSM_AA) f = i >= p.L && p.val.at(row, i) >= p.thr;
+            else f = p.valid[row * p.mstride + i] && p.above[row * p.mstride + i];
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) mask[i / 32] = m;
+    }
+    __syncthreads();
+
+    // 2. gates = clusters of above-runs separated by fewer than heff below-samples
+    if (tid == 0) {
+        int cnt = 0; bool open = false; long long gs = 0, last = 0;
+        const int64_t nw = (n + 31) / 32;
+        long long run_start = -1;
+        auto run_begin = [&](long long a) {
+            if (open && a - last - 1 >= p.heff) {
+                if (cnt < OFS_MAX_EVENTS) { g_start[cnt] = gs; g_close[cnt] = last + p.heff; g_closed[cnt] = 1; }
+                ++cnt; open = false;
+            }
+            if (!open) { open = true; gs = a; }
+        };
+        for (int64_t wi = 0; wi < nw; ++wi) {
+            const unsigned m = mask[wi];
+            const long long base = wi * 32;
+            if (m == 0u) { if (run_start >= 0) { last = base - 1; run_start = -1; } continue; }
+            if (m == 0xffffffffu) { if (run_start < 0) { run_start = base; run_begin(base); } continue; }
+            for (int b = 0; b < 32; ++b) {
+                if ((m >> b) & 1u) { if (run_start < 0) { run_start = base + b; run_begin(base + b); } }
+                else if (run_start >= 0) { last = base + b - 1; run_start = -1; }
+            }
+        }
+        if (run_start >= 0) { last = n - 1; }
+        if (open) {
+            const bool closes = (n - 1 - last) >= p.heff;
+            if (cnt < OFS_MAX_EVENTS) { g_start[cnt] = gs; g_close[cnt] = closes ? last + p.heff : n - 1; g_closed[cnt] = closes; }
+            ++cnt;
+        }
+        g_count = cnt;
+    }
+    __syncthreads();
+    const int cnt = g_count < OFS_MAX_EVENTS ? g_count : OFS_MAX_EVENTS;
+
+    // 3. peak of each gate over [open, close] with the reference's tie rule
+    for (int e = 0; e < cnt; ++e) {
+        const long long gs = g_start[e], gc = g_close[e];
+        ArgVal pk{0.0, -1};
+        for (int64_t i = gs + tid; i <= gc; i += DNT) {
+            const double v = fsm_track_value<KIND>(p, row, i);
+            if (KIND == FSM_RTL) { if (pk.i < 0 || v >= pk.v) { pk.v = v; pk.i = i; } }
+            else { if (pk.i < 0 || v > pk.v) { pk.v = v; pk.i = i; } }
+        }
+        pk = block_argmax<KIND == FSM_RTL>(pk, sh_av);
+        if (KIND == FSM_ZC && p.gate_mask) {   // zc_v2.py:409,444: (open, close] when closed, [open, n) otherwise
+            const int64_t a = g_closed[e] ? gs + 1 : gs;
+            for (int64_t i = a + tid; i <= gc; i += DNT) p.gate_mask[row * p.mstride + i] = 1;
+        }
+        if (tid == 0) {
+            ofs_event ev{};
+            ev.peak_index = pk.i; ev.gate_start = gs; ev.closed = g_closed[e];
+            if (KIND == FSM_AA) {
+                ev.gate_end = g_closed[e] ? gc : n;
+                ev.aux = pk.i - 2LL * p.L + 1;
+                ev.value = p.val.at(row, pk.i);
+                if (p.val.f64) { const double2 z = reinterpret_cast<const double2 *>(p.P)[row * p.val.stride + pk.i]; ev.p_re = z.x; ev.p_im = z.y; }
+                else { const float2 z = reinterpret_cast<const float2 *>(p.P)[row * p.val.stride + pk.i]; ev.p_re = z.x; ev.p_im = z.y; }
+                ev.cfo = atan2(ev.p_im, ev.p_re) * p.fs / (2.0 * 3.14159265358979323846 * (double)p.L);
+            } else if (KIND == FSM_ZC) {
+                ev.gate_end = g_closed[e] ? gc : n;
+                const long long ds = pk.i - p.L + 1;
+                ev.aux = ds > 0 ? ds : 0;
+                ev.value = pk.v;
+            } else {
+                ev.gate_end = g_closed[e] ? gc + 1 : n;     // segment end (exclusive), minn_rtl.py:799
+                ev.aux = pk.i + p.L;
+                ev.value = pk.v;
+            }
+            p.events[row * OFS_MAX_EVENTS + e] = ev;
+        }
+    }
+    if (tid == 0) p.n_events[row] = g_count;
+}
+
+// ---- host launchers ----------------------------------------------------------------------------------
+static int rows_ok(const ofs_rows *M, const char *who)
+{
+    OFS_REQUIRE(M && (M->data || M->n_rows == 0 || M->n == 0), "%s: null metric rows", who);
+    OFS_REQUIRE(M->n_rows >= 0 && M->n >= 0 && M->stride >= M->n, "%s: bad row geometry", who);
+    OFS_REQUIRE(M->n_rows < (1LL << 31), "%s: too many rows", who);
+    return OFS_OK;
+}
+static RowView view(const ofs_rows *M) { return RowView{M->data, M->f64, M->n, M->stride}; }
+
+template <typename K>
+static int set_mask_smem(K kern, size_t bytes)
+{
+    OFS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return OFS_OK;
+}
+static size_t mask_bytes(int64_t n) { return (size_t)((n + 31) / 32) * 4 + 16; }
+
+}  // namespace ofs
+
+using namespace ofs;
+
+OFS_API int ofs_find_plateau_end(const ofs_rows *M, int32_t cp_len, int32_t lookahead, int32_t smooth_win,
+                                 int64_t *plateau_end, void *stream)
+{
+    if (int rc = rows_ok(M, "ofs_find_plateau_end")) return rc;
+    OFS_REQUIRE(plateau_end, "ofs_find_plateau_end: null output");
+    if (M->n_rows == 0) return OFS_OK;
+    plateau_kernel<<<(unsigned)M->n_rows, DNT, 0, (cudaStream_t)stream>>>(view(M), cp_len, lookahead, smooth_win, plateau_end);
+    return check_launch("plateau_kernel");
+}
+
+OFS_API int ofs_find_minn_peak(const ofs_rows *M, int32_t smooth_win, double gate_threshold, int32_t has_bounds,
+                               int64_t bound_lo, int64_t bound_hi, int64_t *peak, int64_t *gate_span, void *Ms,
+                               void *stream)
+{
+    if (int rc = rows_ok(M, "ofs_find_minn_peak")) return rc;
+    OFS_REQUIRE(peak && gate_span, "ofs_find_minn_peak: null output");
+    OFS_REQUIRE(M->n <= MASK_MAX_N, "ofs_find_minn_peak: rows longer than %lld unsupported", (long long)MASK_MAX_N);
+    if (M->n_rows == 0) return OFS_OK;
+    const size_t sm = mask_bytes(M->n);
+    if (int rc = set_mask_smem(minn_peak_kernel, sm)) return rc;
+    minn_peak_kernel<<<(unsigned)M->n_rows, DNT, sm, (cudaStream_t)stream>>>(view(M), smooth_win, gate_threshold, has_bounds,
+                                                                            bound_lo, bound_hi, peak, gate_span, Ms);
+    return check_launch("minn_peak_kernel");
+}
+
+OFS_API int ofs_sc_gate(const ofs_rows *Msc, double threshold, uint8_t *gate, int64_t gate_stride, void *stream)
+{
+    if (int rc = rows_ok(Msc, "ofs_sc_gate")) return rc;
+    OFS_REQUIRE(gate && gate_stride >= Msc->n, "ofs_sc_gate: bad gate buffer");
+    if (Msc->n_rows == 0 || Msc->n == 0) return OFS_OK;
+    sc_gate_kernel<<<(unsigned)Msc->n_rows, DNT, 0, (cudaStream_t)stream>>>(view(Msc), threshold, gate, gate_stride);
+    return check_launch("sc_gate_kernel");
+}
+
+OFS_API int ofs_find_minn_peak_gated(const ofs_rows *M, int32_t smooth_win, const uint8_t *gate, int64_t gate_stride,
+                                     int32_t has_bounds, int64_t bound_lo, int64_t bound_hi, int64_t *peak, void *stream)
+{
+    if (int rc = rows_ok(M, "ofs_find_minn_peak_gated")) return rc;
+    OFS_REQUIRE(peak && (gate || M->n == 0) && gate_stride >= M->n, "ofs_find_minn_peak_gated: bad arguments");
+    if (M->n_rows == 0) return OFS_OK;
+    gated_peak_kernel<<<(unsigned)M->n_rows, DNT, 0, (cudaStream_t)stream>>>(view(M), smooth_win, gate, gate_stride, has_bounds,
+                                                                            bound_lo, bound_hi, peak);
+    return check_launch("gated_peak_kernel");
+}
+
+OFS_API int ofs_argmax(const ofs_rows *M, int64_t *index, void *stream)
+{
+    if (int rc = rows_ok(M, "ofs_argmax")) return rc;
+    OFS_REQUIRE(index, "ofs_argmax: null output");
+    if (M->n_rows == 0) return OFS_OK;
+    argmax_kernel<<<(unsigned)M->n_rows, DNT, 0, (cudaStream_t)stream>>>(view(M), index);
+    return check_launch("argmax_kernel");
+}
+
+OFS_API int ofs_zc_streaming_detection(const ofs_rows *corr_mag, int32_t window, int32_t thresh_value, int32_t frac_bits,
+                                       double min_corr_mag, void *local_sum, uint8_t *valid, uint8_t *above,
+                                       int64_t mask_stride, void *stream)
+{
+    if (int rc = rows_ok(corr_mag, "ofs_zc_streaming_detection")) return rc;
+    OFS_REQUIRE(local_sum && valid && above && mask_stride >= corr_mag->n, "ofs_zc_streaming_detection: bad outputs");
+    OFS_REQUIRE(frac_bits >= 0 && frac_bits < 62, "ofs_zc_streaming_detection: bad frac_bits");
+    if (corr_mag->n_rows == 0 || corr_mag->n == 0) return OFS_OK;
+    const int W = window > 1 ? window : 1;
+    OFS_REQUIRE(W <= 16384, "ofs_zc_streaming_detection: window > 16384 unsupported");
+    dim3 grid((unsigned)((corr_mag->n + ZT - 1) / ZT), (unsigned)corr_mag->n_rows);
+    OFS_REQUIRE(corr_mag->n_rows < 65536, "ofs_zc_streaming_detection: too many rows");
+    const size_t zsm = (size_t)(ZT + W + 2) * sizeof(double);
+    OFS_CUDA(cudaFuncSetAttribute(zc_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsm));
+    zc_stream_kernel<<<grid, DNT, zsm, (cudaStream_t)stream>>>(view(corr_mag), W, (double)thresh_value,
+                                                            (double)(1LL << frac_bits), min_corr_mag, local_sum, valid, above,
+                                                            mask_stride);
+    return check_launch("zc_stream_kernel");
+}
+
+template <int KIND>
+static int launch_fsm(FsmParams &p, int64_t n_rows, cudaStream_t stream)
+{
+    OFS_REQUIRE(p.val.n <= MASK_MAX_N, "gate FSM: rows longer than %lld unsupported", (long long)MASK_MAX_N);
+    if (n_rows == 0) return OFS_OK;
+    const size_t sm = mask_bytes(p.val.n);
+    if (int rc = set_mask_smem(fsm_kernel<KIND>, sm)) return rc;
+    fsm_kernel<KIND><<<(unsigned)n_rows, DNT, sm, stream>>>(p);
+    return check_launch("fsm_kernel");
+}
+
+OFS_API int ofs_aa_events(const ofs_rows *M, const void *P, int32_t L, double threshold, int32_t hysteresis,
+                          double sample_rate, ofs_event *events, int32_t *n_events, void *stream)
+{
+    if (int rc = rows_ok(M, "ofs_aa_events")) return rc;
+    OFS_REQUIRE(P && events && n_events && L > 0, "ofs_aa_events: bad arguments");
+    FsmParams p{};
+    p.val = view(M); p.P = P; p.L = L; p.heff = hysteresis > 1 ? hysteresis : 1; p.thr = threshold; p.fs = sample_rate;
+    p.events = events; p.n_events = n_events;
+    return launch_fsm<FSM_AA>(p, M->n_rows, (cudaStream_t)stream);
+}
+
+OFS_API int ofs_zc_events(const ofs_rows *corr_mag, const uint8_t *valid, const uint8_t *above, int64_t mask_stride,
+                          int32_t reference_length, int32_t hysteresis, ofs_event *events, int32_t *n_events,
+                          uint8_t *gate_mask, void *stream)
+{
+    if (int rc = rows_ok(corr_mag, "ofs_zc_events")) return rc;
+    OFS_REQUIRE(valid && above && events && n_events && mask_stride >= corr_mag->n, "ofs_zc_events: bad arguments");
+    if (gate_mask && corr_mag->n_rows > 0)
+        OFS_CUDA(cudaMemsetAsync(gate_mask, 0, (size_t)corr_mag->n_rows * mask_stride, (cudaStream_t)stream));
+    FsmParams p{};
+    p.val = view(corr_mag); p.valid = valid; p.above = above; p.mstride = mask_stride; p.L = reference_length;
+    p.heff = hysteresis > 1 ? hysteresis : 1; p.events = events; p.n_events = n_events; p.gate_mask = gate_mask;
+    return launch_fsm<FSM_ZC>(p, corr_mag->n_rows, (cudaStream_t)stream);
+}
+
+OFS_API int ofs_minn_rtl_events(const void *corr_positive, int32_t is_int, const uint8_t *valid, const uint8_t *above,
+                                int64_t n_rows, int64_t n, int64_t stride, int32_t hysteresis, int32_t timing_offset,
+                                ofs_event *events, int32_t *n_events, void *stream)
+{
+    OFS_REQUIRE(corr_positive && valid && above && events && n_events, "ofs_minn_rtl_events: null argument");
+    OFS_REQUIRE(n_rows >= 0 && n >= 0 && stride >= n && n_rows < (1LL << 31), "ofs_minn_rtl_events: bad geometry");
+    FsmParams p{};
+    p.val = RowView{corr_positive, 1, n, stride}; p.is_int = is_int; p.valid = valid; p.above = above; p.mstride = stride;
+    p.L = timing_offset; p.heff = hysteresis > 1 ? hysteresis : 1; p.events = events; p.n_events = n_events;
+    return launch_fsm<FSM_RTL>(p, n_rows, (cudaStream_t)stream);
+}

@@ -1,0 +1,275 @@
+// Reference-order streaming kernels: the reference's scalar recurrences evaluated in exactly the
+// reference's operation order (no FMA contraction: __dmul_rn / __dadd_rn / __dsub_rn), one
+// thread per independent stream.  These exist because some answers of the reference depend on the
+// rounding of its running sums (the docs/detector_test_vector.csv tie 1523/1524,
+// the float smoother of minn_rtl.py:709-715, the integer floor-shift smoother of
+// ref/minn_preamble_detector.sv:294-296).  Throughput comes from the number of concurrent
+// streams, not from parallelism inside one.
+//
+//   aa_reference_kernel      sync_aa.py:321-386 + 458-493   (RunningSum / RunningSumReal / DelayLine)
+//   rtl_window_kernel<T>     minn_rtl.py:512-652            (_DelayLine / _RunningSum / _antenna_path)
+//                            ref/minn_antenna_path.sv:63-194, ref/minn_running_sum.sv:77-82
+//   rtl_combine_*            minn_rtl.py:695-733            ref/minn_preamble_detector.sv:247-325
+#include "common.cuh"
+#include <type_traits>
+
+namespace ofs {
+
+// ------------------------------------------------------------------------------------------ sync_aa
+__global__ void aa_reference_kernel(const void *x, int dtype, int64_t n_frames, int na, int64_t n, int L,
+                                    double2 *P, double *R, double *M, uint8_t *valid)
+{
+    const int64_t frame = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (frame >= n_frames) return;
+    const size_t esz = dtype == OFS_C64 ? 8 : (dtype == OFS_C128 ? 16 : 4);
+    const unsigned char *xf = reinterpret_cast<const unsigned char *>(x) + (size_t)frame * na * n * esz;
+    // per-antenna running sums live in the output rows while streaming: P/R rows of this frame are
+    // written once per sample with the antenna TOTAL, so the per-antenna state is kept in registers
+    // for na <= 8 and re-derived from memory otherwise (loop below keeps it simple: na <= 64, state
+    // in local memory).
+    double psr[64], psi[64], rs[64];
+    for (int a = 0; a < na; ++a) { psr[a] = 0.0; psi[a] = 0.0; rs[a] = 0.0; }
+    const double floor_ = 1e-6 * (double)L;
+    for (int64_t t = 0; t < n; ++t) {
+        double Pr = 0.0, Pi = 0.0, Rs = 0.0;
+        for (int a = 0; a < na; ++a) {
+            const void *xa = xf + (size_t)a * n * esz;
+            const double2 xn = load_sample_f64(xa, dtype, t);
+            // product = x[n] * conj(x[n-L]) once the delay line is full (sync_aa.py:470)
+            double qr = 0.0, qi = 0.0;
+            if (t >= L) {
+                const double2 xd = load_sample_f64(xa, dtype, t - L);
+                qr = __dadd_rn(__dmul_rn(xn.x, xd.x), __dmul_rn(xn.y, xd.y));
+                qi = __dsub_rn(__dmul_rn(xn.y, xd.x), __dmul_rn(xn.x, xd.y));
+            }
+            // oldest product in the L-deep window: the one pushed at t-L (zero before the window filled)
+            double or_ = 0.0, oi = 0.0;
+            if (t >= 2 * (int64_t)L) {
+                const double2 a1 = load_sample_f64(xa, dtype, t - L);
+                const double2 a2 = load_sample_f64(xa, dtype, t - 2 * (int64_t)L);
+                or_ = __dadd_rn(__dmul_rn(a1.x, a2.x), __dmul_rn(a1.y, a2.y));
+                oi = __dsub_rn(__dmul_rn(a1.y, a2.x), __dmul_rn(a1.x, a2.y));
+            }
+            psr[a] = __dsub_rn(__dadd_rn(psr[a], qr), or_);       // sum + sample - oldest (sync_aa.py:337)
+            psi[a] = __dsub_rn(__dadd_rn(psi[a], qi), oi);
+            const double pw = __dadd_rn(__dmul_rn(xn.x, xn.x), __dmul_rn(xn.y, xn.y));
+            double po = 0.0;
+            if (t >= L) {
+                const double2 xd = load_sample_f64(xa, dtype, t - L);
+                po = __dadd_rn(__dmul_rn(xd.x, xd.x), __dmul_rn(xd.y, xd.y));
+            }
+            rs[a] = __dsub_rn(__dadd_rn(rs[a], pw), po);
+            Pr = __dadd_rn(Pr, psr[a]); Pi = __dadd_rn(Pi, psi[a]); Rs = __dadd_rn(Rs, rs[a]);
+        }
+        const bool v = t >= L;
+        const int64_t o = frame * n + t;
+        P[o] = make_double2(Pr, Pi); R[o] = Rs; valid[o] = v;
+        double m = 0.0;
+        if (v && Rs > floor_) {
+            m = __ddiv_rn(__dadd_rn(__dmul_rn(Pr, Pr), __dmul_rn(Pi, Pi)), __dmul_rn(Rs, Rs));
+            m = m < 1.0 ? m : 1.0;
+        }
+        M[o] = m;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ minn_rtl
+// Per (frame, antenna): running Q-window sums of the lag product and of the power.
+//   C[n] = sum_{k=n-Q+1..n} prod[k],  prod[k] = re*re_d + im*im_d with the delayed sample x[k-D]
+//   E[n] = sum_{k=n-Q+1..n} |x[k]|^2
+// T = double: float mirror (operation order of minn_rtl._RunningSum.step); T = long long: integer RTL.
+template <typename T, int DT>
+__global__ void rtl_window_kernel(const void *x, int64_t n_streams, int64_t n, int Q, int D, T *C, T *E)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    using In = typename InT<DT>::type;
+    const In *xs = reinterpret_cast<const In *>(x) + s * n;
+    T *Cs = C + s * n, *Es = E + s * n;
+    T c = 0, e = 0;
+    auto prod_at = [&](int64_t k) -> T {
+        if (k < D) return (T)0;
+        const In a = xs[k], b = xs[k - D];
+        if constexpr (sizeof(T) == 8 && !std::is_floating_point<T>::value)
+            return (T)a.x * (T)b.x + (T)a.y * (T)b.y;
+        else
+            return (T)__dadd_rn(__dmul_rn((double)b.x, (double)a.x), __dmul_rn((double)b.y, (double)a.y));
+    };
+    auto pow_at = [&](int64_t k) -> T {
+        const In a = xs[k];
+        if constexpr (sizeof(T) == 8 && !std::is_floating_point<T>::value)
+            return (T)a.x * (T)a.x + (T)a.y * (T)a.y;
+        else
+            return (T)__dadd_rn(__dmul_rn((double)a.x, (double)a.x), __dmul_rn((double)a.y, (double)a.y));
+    };
+    for (int64_t i = 0; i < n; ++i) {
+        const T p = prod_at(i), w = pow_at(i);
+        const T po = i >= Q ? prod_at(i - Q) : (T)0;
+        const T wo = i >= Q ? pow_at(i - Q) : (T)0;
+        if constexpr (std::is_floating_point<T>::value) {
+            c = (T)__dsub_rn(__dadd_rn((double)c, (double)p), (double)po);     // sum_reg + val - oldest
+            e = (T)__dsub_rn(__dadd_rn((double)e, (double)w), (double)wo);
+        } else {
+            c = c + p - po;
+            e = e + w - wo;
+        }
+        Cs[i] = c; Es[i] = e;
+    }
+}
+
+// Combine antennas with the hold-register gating (minn_rtl.py:632-650 / minn_antenna_path.sv:168-194):
+//   corr_recent = C[n] (n >= Q-1), corr_previous = C[n-Q] (n >= 2Q-1),
+//   energy_recent = E[n] (n >= Q-1), energy_previous = E[n-Q] (n >= 2Q-1), energy_previous2 = E[n-2Q] (n >= 3Q-1)
+template <typename T>
+__global__ void rtl_combine_kernel(const T *C, const T *E, int64_t n_frames, int nb, int64_t n, int Q,
+                                   T *corr_total, T *corr_positive, T *energy_total, uint8_t *valid)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_frames * n) return;
+    const int64_t frame = idx / n, i = idx % n;
+    T ct = 0, et = 0;
+    for (int b = 0; b < nb; ++b) {
+        const T *Cs = C + (frame * nb + b) * n, *Es = E + (frame * nb + b) * n;
+        const T cr = i >= Q - 1 ? Cs[i] : (T)0;
+        const T cp = i >= 2 * (int64_t)Q - 1 ? Cs[i - Q] : (T)0;
+        const T er = i >= Q - 1 ? Es[i] : (T)0;
+        const T ep = i >= 2 * (int64_t)Q - 1 ? Es[i - Q] : (T)0;
+        const T e2 = i >= 3 * (int64_t)Q - 1 ? Es[i - 2 * (int64_t)Q] : (T)0;
+        if constexpr (std::is_floating_point<T>::value) {
+            ct = __dadd_rn(ct, __dadd_rn(cr, cp));                              // minn_rtl.py:696
+            et = __dadd_rn(et, __dadd_rn(__dadd_rn(er, ep), e2));              // :697-701
+        } else {
+            ct += cr + cp; et += er + ep + e2;
+        }
+    }
+    corr_total[idx] = ct;
+    corr_positive[idx] = ct > (T)0 ? ct : (T)0;
+    energy_total[idx] = et;
+    valid[idx] = i >= 3 * (int64_t)Q - 1;
+}
+
+// Smoother + threshold, sequential per frame (minn_rtl.py:707-722 / minn_preamble_detector.sv:277-325).
+__global__ void rtl_smooth_f64_kernel(const double *corr_positive, const double *energy_total, const uint8_t *valid,
+                                      int64_t n_frames, int64_t n, int shift, double thr_value, double cscale,
+                                      double *smooth, double *corr_scaled, double *energy_scaled, uint8_t *above)
+{
+    const int64_t frame = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (frame >= n_frames) return;
+    const double denom = (double)(1LL << (shift > 0 ? shift : 0));
+    double s = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t o = frame * n + i;
+        const double c = corr_positive[o];
+        if (valid[o]) {
+            if (shift == 0) s = c;
+            else s = __dadd_rn(s, __ddiv_rn(__dsub_rn(c, s), denom));
+        }
+        smooth[o] = s;
+        const double cs = __dmul_rn(s, cscale);
+        const double es = thr_value == 0.0 ? 0.0 : __dmul_rn(energy_total[o], thr_value);
+        corr_scaled[o] = cs; energy_scaled[o] = es;
+        above[o] = valid[o] && cs >= es;
+    }
+}
+__global__ void rtl_smooth_i64_kernel(const long long *corr_positive, const long long *energy_total,
+                                      const uint8_t *valid, int64_t n_frames, int64_t n, int shift, long long thr_value,
+                                      int frac_bits, long long *smooth, uint8_t *above)
+{
+    const int64_t frame = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (frame >= n_frames) return;
+    long long s = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t o = frame * n + i;
+        const long long c = corr_positive[o];
+        if (valid[o]) s = shift == 0 ? c : s + ((c - s) >> shift);            // arithmetic shift = floor
+        smooth[o] = s;
+        above[o] = valid[o] && ((s << frac_bits) >= energy_total[o] * thr_value);
+    }
+}
+
+}  // namespace ofs
+
+using namespace ofs;
+
+// Reference-order [A][A] metric (float64 outputs).  Declared here, used by the sync_aa shim.
+OFS_API int ofs_aa_metric_reference(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_antennas, int64_t n,
+                                    int32_t L, void *P_c128, double *R, double *M, uint8_t *valid, void *stream)
+{
+    OFS_REQUIRE(x && P_c128 && R && M && valid, "ofs_aa_metric_reference: null argument");
+    OFS_REQUIRE(n_antennas >= 1 && n_antennas <= 64, "ofs_aa_metric_reference: 1..64 antennas");
+    OFS_REQUIRE(L > 0 && n >= 0 && n_frames >= 0, "ofs_aa_metric_reference: bad geometry");
+    if (n_frames == 0 || n == 0) return OFS_OK;
+    const int bs = 32;
+    aa_reference_kernel<<<(unsigned)((n_frames + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(
+        x, in_dtype, n_frames, n_antennas, n, L, (double2 *)P_c128, R, M, valid);
+    return check_launch("aa_reference_kernel");
+}
+
+OFS_API int ofs_minn_rtl_metric(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_branches, int64_t n,
+                                int32_t quarter_len, int32_t smooth_shift, int32_t threshold_value, int32_t frac_bits,
+                                double *corr_total, double *corr_positive, double *smooth_metric, double *energy_total,
+                                double *corr_scaled, double *energy_scaled, uint8_t *metric_valid, uint8_t *above,
+                                void *stream_)
+{
+    OFS_REQUIRE(x && corr_total && corr_positive && smooth_metric && energy_total && corr_scaled && energy_scaled &&
+                    metric_valid && above, "ofs_minn_rtl_metric: null argument");
+    OFS_REQUIRE(in_dtype == OFS_C64 || in_dtype == OFS_C128, "ofs_minn_rtl_metric: complex64/complex128 input");
+    OFS_REQUIRE(quarter_len > 0, "quarter_len must be positive.");
+    OFS_REQUIRE(n_branches >= 1 && n >= 0 && n_frames >= 0 && frac_bits >= 0 && frac_bits < 62, "ofs_minn_rtl_metric: bad geometry");
+    if (n_frames == 0 || n == 0) return OFS_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t ns = n_frames * n_branches;
+    double *C = nullptr, *E = nullptr;
+    OFS_CUDA(cudaMallocAsync((void **)&C, (size_t)ns * n * sizeof(double), stream));
+    OFS_CUDA(cudaMallocAsync((void **)&E, (size_t)ns * n * sizeof(double), stream));
+    const int bs = 32;
+    if (in_dtype == OFS_C64)
+        rtl_window_kernel<double, OFS_C64><<<(unsigned)((ns + bs - 1) / bs), bs, 0, stream>>>(x, ns, n, quarter_len, quarter_len, C, E);
+    else
+        rtl_window_kernel<double, OFS_C128><<<(unsigned)((ns + bs - 1) / bs), bs, 0, stream>>>(x, ns, n, quarter_len, quarter_len, C, E);
+    if (int rc = check_launch("rtl_window_kernel")) return rc;
+    const int64_t tot = n_frames * n;
+    rtl_combine_kernel<double><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(C, E, n_frames, n_branches, n, quarter_len,
+                                                                               corr_total, corr_positive, energy_total, metric_valid);
+    if (int rc = check_launch("rtl_combine_kernel")) return rc;
+    rtl_smooth_f64_kernel<<<(unsigned)((n_frames + bs - 1) / bs), bs, 0, stream>>>(
+        corr_positive, energy_total, metric_valid, n_frames, n, smooth_shift, (double)threshold_value,
+        (double)(1LL << frac_bits), smooth_metric, corr_scaled, energy_scaled, above);
+    if (int rc = check_launch("rtl_smooth_f64_kernel")) return rc;
+    OFS_CUDA(cudaFreeAsync(C, stream));
+    OFS_CUDA(cudaFreeAsync(E, stream));
+    return OFS_OK;
+}
+
+OFS_API int ofs_minn_rtl_int(const int16_t *iq, int64_t n_frames, int32_t n_branches, int64_t n, int32_t quarter_len,
+                             int32_t smooth_shift, int32_t threshold_value, int32_t frac_bits, int32_t lag_extra,
+                             int64_t *corr_total, int64_t *corr_positive, int64_t *smooth_metric, int64_t *energy_total,
+                             uint8_t *metric_valid, uint8_t *above, void *stream_)
+{
+    OFS_REQUIRE(iq && corr_total && corr_positive && smooth_metric && energy_total && metric_valid && above,
+                "ofs_minn_rtl_int: null argument");
+    OFS_REQUIRE(quarter_len > 0 && (lag_extra == 0 || lag_extra == 1), "ofs_minn_rtl_int: bad quarter_len / lag_extra");
+    OFS_REQUIRE(n_branches >= 1 && n >= 0 && n_frames >= 0 && frac_bits >= 0 && frac_bits < 24, "ofs_minn_rtl_int: bad geometry");
+    if (n_frames == 0 || n == 0) return OFS_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t ns = n_frames * n_branches;
+    long long *C = nullptr, *E = nullptr;
+    OFS_CUDA(cudaMallocAsync((void **)&C, (size_t)ns * n * sizeof(long long), stream));
+    OFS_CUDA(cudaMallocAsync((void **)&E, (size_t)ns * n * sizeof(long long), stream));
+    const int bs = 32;
+    rtl_window_kernel<long long, OFS_IQ16><<<(unsigned)((ns + bs - 1) / bs), bs, 0, stream>>>(iq, ns, n, quarter_len,
+                                                                                           quarter_len + lag_extra, C, E);
+    if (int rc = check_launch("rtl_window_kernel")) return rc;
+    const int64_t tot = n_frames * n;
+    rtl_combine_kernel<long long><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(
+        C, E, n_frames, n_branches, n, quarter_len, (long long *)corr_total, (long long *)corr_positive,
+        (long long *)energy_total, metric_valid);
+    if (int rc = check_launch("rtl_combine_kernel")) return rc;
+    rtl_smooth_i64_kernel<<<(unsigned)((n_frames + bs - 1) / bs), bs, 0, stream>>>(
+        (const long long *)corr_positive, (const long long *)energy_total, metric_valid, n_frames, n, smooth_shift,
+        (long long)threshold_value, frac_bits, (long long *)smooth_metric, above);
+    if (int rc = check_launch("rtl_smooth_i64_kernel")) return rc;
+    OFS_CUDA(cudaFreeAsync(C, stream));
+    OFS_CUDA(cudaFreeAsync(E, stream));
+    return OFS_OK;
+}

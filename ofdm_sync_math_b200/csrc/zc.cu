@@ -1,0 +1,379 @@
+// Zadoff-Chu kernels.
+//
+// K4  zc_mf_kernel      matched filter by FFT overlap-save, hand-written shared-memory radix-2 FFT
+//                       (DIF forward -> pointwise multiply in bit-reversed order -> DIT inverse, so no
+//                       bit-reversal pass), fused with the sliding-energy normalisation.
+//                       Replaces np.convolve(x, conj(ref[::-1])) and np.convolve(|x|^2, ones) of
+//                       zc.py:115-126 and zc_v2.py:244-271, 486-495.
+// K5  zc_freq_kernel    zc_freq.compute_frequency_metric (zc_freq.py:62-99) as a sliding DFT of the used
+//                       bins: bins_j(o) = conj(w_j^s) (T_j[s+N]-T_j[s]), T_j = prefix sum of x[m] w_j^m,
+//                       instead of one 2048-point FFT per candidate offset.
+#include "common.cuh"
+
+namespace ofs {
+
+constexpr int ZF = 4096, ZLOG = 12, ZNT = 256;
+
+template <typename T> struct C2T;
+template <> struct C2T<float> { using type = float2; };
+template <> struct C2T<double> { using type = double2; };
+
+template <typename C2> __device__ __forceinline__ C2 cadd(C2 a, C2 b) { C2 r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+template <typename C2> __device__ __forceinline__ C2 csub(C2 a, C2 b) { C2 r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+template <typename C2> __device__ __forceinline__ C2 cmul(C2 a, C2 b) { C2 r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r; }
+template <typename C2> __device__ __forceinline__ C2 cmulc(C2 a, C2 b) { C2 r; r.x = a.x * b.x + a.y * b.y; r.y = a.y * b.x - a.x * b.y; return r; }  // a * conj(b)
+
+template <typename C2>
+__device__ __forceinline__ C2 ld_tw(const double2 *tw, int i)
+{
+    const double2 w = __ldg(tw + i);
+    C2 r; r.x = w.x; r.y = w.y;
+    return r;
+}
+
+// natural order in -> bit-reversed order out
+template <typename C2>
+__device__ void fft_dif(C2 *a, const double2 *tw)
+{
+    for (int s = 0; s < ZLOG; ++s) {
+        const int span = ZF >> (s + 1);
+        for (int t = threadIdx.x; t < ZF / 2; t += ZNT) {
+            const int j = t & (span - 1), i0 = ((t - j) << 1) + j, i1 = i0 + span;
+            const C2 u = a[i0], v = a[i1];
+            a[i0] = cadd(u, v);
+            a[i1] = cmul(csub(u, v), ld_tw<C2>(tw, j << s));
+        }
+        __syncthreads();
+    }
+}
+// bit-reversed order in -> natural order out, unscaled (multiply by 1/ZF afterwards)
+template <typename C2>
+__device__ void ifft_dit(C2 *a, const double2 *tw)
+{
+    for (int s = ZLOG - 1; s >= 0; --s) {
+        const int span = ZF >> (s + 1);
+        for (int t = threadIdx.x; t < ZF / 2; t += ZNT) {
+            const int j = t & (span - 1), i0 = ((t - j) << 1) + j, i1 = i0 + span;
+            const C2 u = a[i0], v = cmulc(a[i1], ld_tw<C2>(tw, j << s));
+            a[i0] = cadd(u, v);
+            a[i1] = csub(u, v);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void zc_twiddle_kernel(double2 *tw)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ZF / 2) {
+        double s, c;
+        sincospi(-2.0 * (double)i / (double)ZF, &s, &c);
+        tw[i] = make_double2(c, s);
+    }
+}
+
+// G = DIF-FFT of g[m] = conj(ref[nr-1-m]) zero-padded to ZF (bit-reversed order), plus ||ref||.
+__global__ void __launch_bounds__(ZNT) zc_spectrum_kernel(const double2 *ref, int nr, const double2 *tw, double2 *G,
+                                                          double *ref_norm)
+{
+    extern __shared__ __align__(16) unsigned char zsm[];
+    double2 *a = reinterpret_cast<double2 *>(zsm);
+    __shared__ double red[ZNT / 32];
+    double e = 0.0;
+    for (int m = threadIdx.x; m < ZF; m += ZNT) {
+        double2 v = make_double2(0.0, 0.0);
+        if (m < nr) { const double2 r = ref[nr - 1 - m]; v = make_double2(r.x, -r.y); e += r.x * r.x + r.y * r.y; }
+        a[m] = v;
+    }
+    for (int o = 16; o > 0; o >>= 1) e += shfl_xor_f64(e, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
+    __syncthreads();
+    fft_dif<double2>(a, tw);
+    for (int m = threadIdx.x; m < ZF; m += ZNT) G[m] = a[m];
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < ZNT / 32; ++w) t += red[w];
+        *ref_norm = sqrt(t);
+    }
+}
+
+template <typename T, int DT>
+__global__ void __launch_bounds__(ZNT) zc_mf_kernel(const void *x, int nb, int64_t n, int nr, const double2 *tw,
+                                                    const double2 *G, const double *ref_norm_p, int mode, int out_f64,
+                                                    void *corr_out, void *mag_out, int64_t out_stride, int blocks_per_frame)
+{
+    using C2 = typename C2T<T>::type;
+    using In = typename InT<DT>::type;
+    extern __shared__ __align__(16) unsigned char zsm[];
+    C2 *a = reinterpret_cast<C2 *>(zsm);                                          // ZF
+    double *se = reinterpret_cast<double *>(zsm + (size_t)ZF * sizeof(C2));       // ZF + 1 (+1 pad)
+    double *pw = se + ZF + 2;                                                     // V <= ZF
+    double2 *acc = reinterpret_cast<double2 *>(pw + ZF);                          // V, 16-byte aligned
+    __shared__ double wtot[ZNT / 32];
+
+    const int V = ZF - nr + 1;                        // valid outputs per block
+    const int64_t frame = blockIdx.x / blocks_per_frame;
+    const int blk = blockIdx.x % blocks_per_frame;
+    const int64_t k0 = (int64_t)blk * V;              // first full-convolution output of this block
+    const int64_t jb = k0 - (nr - 1);                 // first input sample of this block
+    const int64_t out_len = n + nr - 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double ref_norm = *ref_norm_p;
+
+    for (int i = tid; i < V; i += ZNT) { pw[i] = 0.0; acc[i] = make_double2(0.0, 0.0); }
+
+    for (int b = 0; b < nb; ++b) {
+        const In *xb = reinterpret_cast<const In *>(x) + (frame * nb + b) * n;
+        __syncthreads();
+        for (int m = tid; m < ZF; m += ZNT) {
+            const int64_t j = jb + m;
+            C2 v; v.x = 0; v.y = 0;
+            if (j >= 0 && j < n) { const In s = xb[j]; v.x = (T)s.x; v.y = (T)s.y; }
+            a[m] = v;
+        }
+        if (tid == 0) se[0] = 0.0;
+        __syncthreads();
+        // energy prefix se[i+1] = sum_{m<=i} |a[m]|^2 (float64): thread-serial + warp scan + CTA carry
+        {
+            constexpr int IPT = ZF / ZNT;          // 16
+            const int s0 = tid * IPT;
+            double run = 0.0;
+            for (int m = 0; m < IPT; ++m) {
+                const C2 v = a[s0 + m];
+                run += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+                se[s0 + m + 1] = run;
+            }
+            double t = run;
+            for (int o = 1; o < 32; o <<= 1) { const double y = shfl_up_f64(t, o); if (lane >= o) t += y; }
+            if (lane == 31) wtot[warp] = t;
+            __syncthreads();
+            double off = t - run;
+            for (int w = 0; w < warp; ++w) off += wtot[w];
+            for (int m = 0; m < IPT; ++m) se[s0 + m + 1] += off;
+        }
+        __syncthreads();
+        fft_dif<C2>(a, tw);
+        for (int m = tid; m < ZF; m += ZNT) {
+            const double2 g = __ldg(G + m);
+            C2 gg; gg.x = (T)g.x; gg.y = (T)g.y;
+            a[m] = cmul(a[m], gg);
+        }
+        __syncthreads();
+        ifft_dit<C2>(a, tw);
+        for (int i = tid; i < V; i += ZNT) {
+            // output k0+i is the window of local samples [i, i+nr-1]
+            const double e = se[i + nr] - se[i];
+            const C2 y = a[nr - 1 + i];
+            double yr = (double)y.x / (double)ZF, yi = (double)y.y / (double)ZF;
+            if (mode == 1) {                                   // zc_v2.py:257-271: per-branch normalisation
+                const double d = ref_norm * sqrt(e > 1e-12 ? e : 1e-12);
+                yr /= d; yi /= d;
+            }
+            acc[i].x += yr; acc[i].y += yi;
+            pw[i] += e;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < V; i += ZNT) {
+        const int64_t k = k0 + i;
+        if (k >= out_len) break;
+        double yr = acc[i].x, yi = acc[i].y;
+        if (mode == 0) {                                       // zc.py:125-126: normalise after the branch sum
+            const double p = pw[i] > 0.0 ? pw[i] : 0.0;
+            const double d = ref_norm * sqrt(p + 1e-12);
+            yr /= d; yi /= d;
+        }
+        const int64_t o = frame * out_stride + k;
+        if (out_f64) {
+            if (corr_out) reinterpret_cast<double2 *>(corr_out)[o] = make_double2(yr, yi);
+            if (mag_out) reinterpret_cast<double *>(mag_out)[o] = hypot(yr, yi);
+        } else {
+            if (corr_out) reinterpret_cast<float2 *>(corr_out)[o] = make_float2((float)yr, (float)yi);
+            if (mag_out) reinterpret_cast<float *>(mag_out)[o] = (float)hypot(yr, yi);
+        }
+    }
+}
+
+// ---- zc_freq: sliding DFT of the used bins --------------------------------------------------------
+constexpr int QNT = 256;
+
+template <int DT>
+__global__ void __launch_bounds__(QNT) zc_freq_kernel(const void *x, int nb, int64_t n, int N, int cp, const int *bins,
+                                                      const double2 *templ, int nbins, double templ_energy, int TO,
+                                                      int64_t n_off, int out_f64, void *metric, int64_t out_stride,
+                                                      int tiles_per_frame)
+{
+    using In = typename InT<DT>::type;
+    extern __shared__ __align__(16) unsigned char qsm[];
+    const int span = TO + N - 1;                                   // samples of the tile
+    double2 *xs = reinterpret_cast<double2 *>(qsm);               // span
+    double2 *S = xs + span;                                        // span + 1 (prefix of the modulated samples)
+    double2 *tw = S + span + 1;                                    // N: exp(-2 pi i m / N)
+    __shared__ double wtot[2][QNT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t frame = blockIdx.x / tiles_per_frame;
+    const int tile = blockIdx.x % tiles_per_frame;
+    const int64_t o0 = (int64_t)tile * TO;
+    const int64_t jb = o0 + cp;                                    // first sample of the tile
+    for (int m = tid; m < N; m += QNT) {
+        double s, c;
+        sincospi(-2.0 * (double)m / (double)N, &s, &c);
+        tw[m] = make_double2(c, s);
+    }
+    const int ipt = ((span + QNT - 1) / QNT) | 1;
+    const int s0 = tid * ipt, s1 = min(s0 + ipt, span);
+    constexpr int OPT = 8;                                         // offsets per thread (TO <= QNT * OPT)
+    double cr[OPT], ci[OPT], en[OPT];
+#pragma unroll
+    for (int q = 0; q < OPT; ++q) cr[q] = ci[q] = en[q] = 0.0;
+
+    for (int b = 0; b < nb; ++b) {
+        const In *xb = reinterpret_cast<const In *>(x) + (frame * nb + b) * n;
+        __syncthreads();
+        for (int m = tid; m < span; m += QNT) {
+            const int64_t j = jb + m;
+            double2 v = make_double2(0.0, 0.0);
+            if (j < n) { const In s = xb[j]; v = make_double2((double)s.x, (double)s.y); }
+            xs[m] = v;
+        }
+        if (tid == 0) S[0] = make_double2(0.0, 0.0);
+        __syncthreads();
+        for (int jbin = 0; jbin < nbins; ++jbin) {
+            const int k = bins[jbin];
+            // modulated inclusive prefix over the tile: S[m+1] = sum_{m'<=m} x[jb+m'] * w^(k (jb+m'))
+            double rr = 0.0, ri = 0.0;
+            int ph = (int)((jb + s0) % N);
+            for (int m = s0; m < s1; ++m) {
+                const double2 w = tw[(int)(((long long)k * ph) % N)];
+                const double2 v = xs[m];
+                rr += v.x * w.x - v.y * w.y;
+                ri += v.x * w.y + v.y * w.x;
+                S[m + 1] = make_double2(rr, ri);
+                ph = ph + 1 == N ? 0 : ph + 1;
+            }
+            double tr = rr, ti = ri;
+            for (int o = 1; o < 32; o <<= 1) {
+                const double yr = shfl_up_f64(tr, o), yi = shfl_up_f64(ti, o);
+                if (lane >= o) { tr += yr; ti += yi; }
+            }
+            if (lane == 31) { wtot[0][warp] = tr; wtot[1][warp] = ti; }
+            __syncthreads();
+            double offr = tr - rr, offi = ti - ri;
+            for (int w = 0; w < warp; ++w) { offr += wtot[0][w]; offi += wtot[1][w]; }
+            for (int m = s0; m < s1; ++m) { S[m + 1].x += offr; S[m + 1].y += offi; }
+            __syncthreads();
+            const double2 tj = templ[jbin];
+#pragma unroll
+            for (int q = 0; q < OPT; ++q) {
+                const int i = tid + q * QNT;                        // offset o0 + i  <->  s = jb + i
+                if (i < TO && o0 + i < n_off) {
+                    const double2 hi = S[i + N], lo = S[i];
+                    const double dr = hi.x - lo.x, di = hi.y - lo.y;
+                    const double2 w = tw[(int)(((long long)k * ((jb + i) % N)) % N)];
+                    // bin = conj(w) * d
+                    const double br = dr * w.x + di * w.y, bi = di * w.x - dr * w.y;
+                    cr[q] += tj.x * br + tj.y * bi;                 // conj(template) * bin (np.vdot)
+                    ci[q] += tj.x * bi - tj.y * br;
+                    en[q] += br * br + bi * bi;
+                }
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < OPT; ++q) {
+        const int i = tid + q * QNT;
+        if (i < TO && o0 + i < n_off) {
+            double den = templ_energy * en[q];
+            if (den < 1e-12) den = 1e-12;
+            const double m = (cr[q] * cr[q] + ci[q] * ci[q]) / den;
+            const int64_t o = frame * out_stride + o0 + i;
+            if (out_f64) reinterpret_cast<double *>(metric)[o] = m;
+            else reinterpret_cast<float *>(metric)[o] = (float)m;
+        }
+    }
+}
+
+}  // namespace ofs
+
+using namespace ofs;
+
+OFS_API int ofs_zc_matched_filter(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_branches, int64_t n,
+                                  const void *ref_c128, int32_t nr, int32_t mode, int32_t out_f64, void *corr_out,
+                                  void *mag_out, int64_t out_stride, void *stream_)
+{
+    OFS_REQUIRE(x && ref_c128 && (corr_out || mag_out), "ofs_zc_matched_filter: null argument");
+    OFS_REQUIRE(nr >= 1 && nr <= 2048, "ofs_zc_matched_filter: reference length must be 1..2048");
+    OFS_REQUIRE(mode >= 0 && mode <= 2, "ofs_zc_matched_filter: mode must be 0, 1 or 2");
+    OFS_REQUIRE(n_branches >= 1 && n >= 1 && n_frames >= 0, "ofs_zc_matched_filter: bad geometry");
+    OFS_REQUIRE(out_stride >= n + nr - 1, "ofs_zc_matched_filter: out_stride too small");
+    if (n_frames == 0) return OFS_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    double2 *tw = nullptr, *G = nullptr;
+    double *rn = nullptr;
+    OFS_CUDA(cudaMallocAsync((void **)&tw, (ZF / 2) * sizeof(double2), stream));
+    OFS_CUDA(cudaMallocAsync((void **)&G, ZF * sizeof(double2), stream));
+    OFS_CUDA(cudaMallocAsync((void **)&rn, sizeof(double), stream));
+    zc_twiddle_kernel<<<(ZF / 2 + 255) / 256, 256, 0, stream>>>(tw);
+    if (int rc = check_launch("zc_twiddle_kernel")) return rc;
+    OFS_CUDA(cudaFuncSetAttribute(zc_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ZF * sizeof(double2))));
+    zc_spectrum_kernel<<<1, ZNT, ZF * sizeof(double2), stream>>>((const double2 *)ref_c128, nr, tw, G, rn);
+    if (int rc = check_launch("zc_spectrum_kernel")) return rc;
+    const int V = ZF - nr + 1;
+    const int bpf = (int)((n + nr - 1 + V - 1) / V);
+    const int64_t grid = (int64_t)bpf * n_frames;
+    OFS_REQUIRE(grid < (1LL << 31), "ofs_zc_matched_filter: grid too large");
+    const bool dbl = in_dtype == OFS_C128 || out_f64;
+    const size_t smem = (size_t)ZF * (dbl ? 16 : 8) + (size_t)(ZF + 2 + ZF) * 8 + (size_t)ZF * 16;
+#define OFS_MF_LAUNCH(T, DT)                                                                                       \
+    do {                                                                                                           \
+        auto kern = zc_mf_kernel<T, DT>;                                                                           \
+        OFS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+        kern<<<(unsigned)grid, ZNT, smem, stream>>>(x, n_branches, n, nr, tw, G, rn, mode, out_f64, corr_out, mag_out, \
+                                                    out_stride, bpf);                                              \
+    } while (0)
+    if (in_dtype == OFS_C128) OFS_MF_LAUNCH(double, OFS_C128);
+    else if (in_dtype == OFS_C64 && dbl) OFS_MF_LAUNCH(double, OFS_C64);
+    else if (in_dtype == OFS_C64) OFS_MF_LAUNCH(float, OFS_C64);
+    else if (in_dtype == OFS_IQ16) OFS_MF_LAUNCH(float, OFS_IQ16);
+    else { set_error("ofs_zc_matched_filter: unknown dtype"); return OFS_EINVAL; }
+#undef OFS_MF_LAUNCH
+    if (int rc = check_launch("zc_mf_kernel")) return rc;
+    OFS_CUDA(cudaFreeAsync(tw, stream));
+    OFS_CUDA(cudaFreeAsync(G, stream));
+    OFS_CUDA(cudaFreeAsync(rn, stream));
+    return OFS_OK;
+}
+
+OFS_API int ofs_zc_freq_metric(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_branches, int64_t n,
+                               int32_t n_fft, int32_t cp, const int32_t *bins, const void *templ_c128, int32_t nbins,
+                               double templ_energy, int32_t out_f64, void *metric, int64_t out_stride, void *stream_)
+{
+    OFS_REQUIRE(x && bins && templ_c128 && metric, "ofs_zc_freq_metric: null argument");
+    OFS_REQUIRE(n_fft >= 2 && n_fft <= 2048 && cp >= 0 && nbins >= 1, "ofs_zc_freq_metric: n_fft must be 2..2048");
+    const int64_t n_off = n - ((int64_t)n_fft + cp) + 1;
+    OFS_REQUIRE(n_off > 0, "Received stream is shorter than a single OFDM symbol.");   /* zc_freq.py:76-78 */
+    OFS_REQUIRE(out_stride >= n_off && n_branches >= 1 && n_frames >= 0, "ofs_zc_freq_metric: bad geometry");
+    if (n_frames == 0) return OFS_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int TO = 2048;
+    if (n_off < TO) TO = (int)((n_off + 255) / 256 * 256);
+    const int tiles = (int)((n_off + TO - 1) / TO);
+    const int span = TO + n_fft - 1;
+    const size_t smem = (size_t)(span + span + 1 + n_fft) * sizeof(double2);
+    const int64_t grid = (int64_t)tiles * n_frames;
+    OFS_REQUIRE(grid < (1LL << 31), "ofs_zc_freq_metric: grid too large");
+#define OFS_ZQ_LAUNCH(DT)                                                                                          \
+    do {                                                                                                           \
+        auto kern = zc_freq_kernel<DT>;                                                                            \
+        OFS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+        kern<<<(unsigned)grid, QNT, smem, stream>>>(x, n_branches, n, n_fft, cp, bins, (const double2 *)templ_c128, nbins, \
+                                                    templ_energy, TO, n_off, out_f64, metric, out_stride, tiles);  \
+    } while (0)
+    if (in_dtype == OFS_C128) OFS_ZQ_LAUNCH(OFS_C128);
+    else if (in_dtype == OFS_C64) OFS_ZQ_LAUNCH(OFS_C64);
+    else if (in_dtype == OFS_IQ16) OFS_ZQ_LAUNCH(OFS_IQ16);
+    else { set_error("ofs_zc_freq_metric: unknown dtype"); return OFS_EINVAL; }
+#undef OFS_ZQ_LAUNCH
+    return check_launch("zc_freq_kernel");
+}

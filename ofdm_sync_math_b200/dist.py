@@ -1,0 +1,49 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), captures sharded over ranks, NO collective on the
+sample path; the only exchange is an all-gather of the fixed-size detection records.
+Works with backend "nccl" (GPU tensors over NVLink) and "gloo" (CPU tensors; used by the CPU tests)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int | None = None, world: int | None = None) -> tuple[int, int]:
+    """Contiguous block [lo, hi) of the batch axis owned by `rank` (sizes differ by at most one)."""
+    world = dist.get_world_size() if world is None else world
+    rank = dist.get_rank() if rank is None else rank
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_sizes(n_items: int, world: int) -> list[int]:
+    return [shard_range(n_items, r, world)[1] - shard_range(n_items, r, world)[0] for r in range(world)]
+
+
+class RecordGatherer:
+    """All-gather of a per-rank records tensor [frames_local, record_bytes] (uint8) into [world, frames_max, record_bytes].
+    Buffers are allocated once; ranks with fewer frames are zero-padded (counts travel with the records)."""
+
+    def __init__(self, rec: torch.Tensor, frames_max: int | None = None):
+        self.world = dist.get_world_size()
+        self.rec = rec
+        self.frames_max = int(frames_max if frames_max is not None else rec.shape[0])
+        self.padded = rec if rec.shape[0] == self.frames_max else torch.zeros((self.frames_max, rec.shape[1]), dtype=rec.dtype, device=rec.device)
+        self.out = [torch.zeros_like(self.padded) for _ in range(self.world)]
+
+    def run(self) -> list[torch.Tensor]:
+        if self.padded is not self.rec:
+            self.padded[: self.rec.shape[0]].copy_(self.rec)
+        dist.all_gather(self.out, self.padded)
+        return self.out
+
+
+def gather_records(rec: torch.Tensor, n_total: int) -> np.ndarray | None:
+    """Gather every rank's records (sharded with shard_range over n_total frames) and return them in global
+    frame order as a uint8 array [n_total, record_bytes] (on every rank)."""
+    world = dist.get_world_size()
+    sizes = shard_sizes(n_total, world)
+    g = RecordGatherer(rec, max(sizes))
+    parts = g.run()
+    return np.concatenate([parts[r][: sizes[r]].cpu().numpy() for r in range(world)], axis=0)

@@ -1,0 +1,465 @@
+"""Batched device API over libofdmsync (torch tensors in, torch tensors out).
+
+torch is plumbing only: device memory, streams, (in dist.py) process groups.  Every array
+operation on the hot path is a hand-written sm_100a kernel behind the C ABI of include/ofdmsync.h.
+Inputs: numpy or torch; shapes (L,), (branches, L) or (frames, branches, L); complex64 / complex128,
+or int16 IQ with a trailing axis of 2.  Branches are summed before the metric, frames are independent.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+KINDS = {"sc": L.OFS_SC, "sc_both": L.OFS_SC_BOTH, "minn": L.OFS_MINN, "aa": L.OFS_AA}
+PATHS = {"auto": L.OFS_PATH_AUTO, "stripe": L.OFS_PATH_STRIPE, "tile": L.OFS_PATH_TILE}
+
+
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise L.OfsError("ofdm_sync_math_b200 needs a CUDA device (no CPU fallback exists)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: torch.Tensor | None) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def to_device(rx) -> tuple[torch.Tensor, int, bool]:
+    """-> (tensor [F, B, L(,2)] contiguous on the GPU, ofs dtype code, input_was_numpy)."""
+    was_numpy = not isinstance(rx, torch.Tensor)
+    t = torch.as_tensor(np.ascontiguousarray(rx)) if was_numpy else rx
+    if t.dtype == torch.int16:
+        if t.shape[-1] != 2:
+            raise ValueError("int16 input must have a trailing I/Q axis of length 2")
+        code, nd = L.OFS_IQ16, t.dim() - 1
+    elif t.dtype == torch.complex64:
+        code, nd = L.OFS_C64, t.dim()
+    elif t.dtype == torch.complex128:
+        code, nd = L.OFS_C128, t.dim()
+    elif t.dtype in (torch.float32, torch.float64, torch.int32, torch.int64):
+        t = t.to(torch.complex128)
+        code, nd = L.OFS_C128, t.dim()
+    else:
+        raise TypeError(f"unsupported sample dtype {t.dtype}")
+    if nd == 1:
+        t = t[None, None]
+    elif nd == 2:
+        t = t[None]
+    elif nd != 3:
+        raise ValueError("samples must be 1-D, 2-D (branches, L) or 3-D (frames, branches, L)")
+    t = t.to(_device(), non_blocking=True).contiguous()
+    return t, code, was_numpy
+
+
+@dataclass
+class MetricOut:
+    M: torch.Tensor          # [F, out_len]
+    P: torch.Tensor | None   # [F, out_len] complex
+    R: torch.Tensor | None
+    chunk_max: torch.Tensor | None = None
+    path: str = "tile"
+
+
+def metric_out_len(kind: str, symbol_len: int, n: int) -> int:
+    return n if kind == "aa" else max(n - symbol_len + 1, 0)
+
+
+def metric(rx, kind: str, symbol_len: int, *, want_pr: bool = True, out_f64: bool | None = None,
+           path: str = "auto", store_mode: int = 1, want_chunk_max: bool = False) -> MetricOut:
+    """Timing metric M (+P, R) of sc.py:42-78 / combined_sc_min.py:116-164 / minn.py:59-112,697-751 /
+    sync_aa.py:458-493 for a batch of frames."""
+    x, code, _ = to_device(rx)
+    F, B, n = x.shape[0], x.shape[1], x.shape[2]
+    dev = x.device
+    if out_f64 is None:
+        out_f64 = code == L.OFS_C128
+    out_len = metric_out_len(kind, symbol_len, n)
+    rdt = torch.float64 if out_f64 else torch.float32
+    cdt = torch.complex128 if out_f64 else torch.complex64
+    if out_len == 0 or F == 0:
+        e = torch.zeros((F, 0), dtype=rdt, device=dev)
+        return MetricOut(e, torch.zeros((F, 0), dtype=cdt, device=dev) if want_pr else None, e.clone() if want_pr else None)
+    d = L.MetricDesc(kind=KINDS[kind], in_dtype=code, out_f64=int(out_f64), path=PATHS[path], symbol_len=int(symbol_len),
+                     n_branches=B, n_frames=F, n_samples=n, x_frame_stride=B * n, x_branch_stride=n,
+                     out_stride=0, store_mode=store_mode, reserved=0)
+    lib = L.lib()
+    use_stripe = path != "tile" and not want_pr and not out_f64 and bool(lib.ofs_metric_stripe_ok(C.byref(d), _ptr(x), None))
+    if path == "stripe" and not use_stripe:
+        raise L.OfsError("stripe path cannot serve this request (needs c64/iq16, 1 branch, lag in {256,512,1024}, M only)")
+    if use_stripe:
+        # causal-time rows: element d of a frame lives at column toff + d, so the kernel's 16-byte
+        # vector / bulk stores (which work in t = d + toff) are aligned.
+        toff = 0 if kind == "aa" else symbol_len - 1
+        pitch = (n + 3) // 4 * 4
+        buf = torch.empty((F, pitch), dtype=torch.float32, device=dev)
+        M = buf[:, toff:toff + out_len]
+        cm = None
+        cm_stride = 0
+        if want_chunk_max:
+            cm_stride = (n + 255) // 256
+            cm = torch.zeros((F, cm_stride), dtype=torch.float32, device=dev)
+        d.out_stride = pitch
+        d.path = L.OFS_PATH_STRIPE
+        L.check(lib.ofs_metric(C.byref(d), _ptr(x), C.c_void_p(M.data_ptr()), None, None, _ptr(cm), C.c_int64(cm_stride),
+                               _stream()), "ofs_metric(stripe)")
+        return MetricOut(M, None, None, cm, "stripe")
+    M = torch.empty((F, out_len), dtype=rdt, device=dev)
+    P = torch.empty((F, out_len), dtype=cdt, device=dev) if want_pr else None
+    R = torch.empty((F, out_len), dtype=rdt, device=dev) if want_pr else None
+    d.out_stride = out_len
+    d.path = L.OFS_PATH_TILE
+    L.check(lib.ofs_metric(C.byref(d), _ptr(x), _ptr(M), _ptr(P), _ptr(R), None, C.c_int64(0), _stream()), "ofs_metric(tile)")
+    return MetricOut(M, P, R, None, "tile")
+
+
+# ------------------------------------------------------------------------------------------- detectors
+def _rows(M: torch.Tensor) -> tuple[L.Rows, torch.Tensor]:
+    if M.dim() == 1:
+        M = M[None]
+    if M.dtype not in (torch.float32, torch.float64):
+        M = M.to(torch.float64)
+    if M.stride(-1) != 1:
+        M = M.contiguous()
+    if not M.is_cuda:
+        M = M.to(_device())
+    return L.Rows(C.c_void_p(M.data_ptr()), int(M.dtype == torch.float64), 0, M.shape[0], M.shape[1], M.stride(0) if M.shape[0] > 1 else max(M.shape[1], M.stride(0))), M
+
+
+def find_plateau_end(M: torch.Tensor, cp_len: int, lookahead: int | None = None, smooth_win: int = 8) -> torch.Tensor:
+    """sc.py:81-146 for every row -> int64[rows]."""
+    rows, M = _rows(M)
+    out = torch.zeros(M.shape[0], dtype=torch.int64, device=M.device)
+    L.check(L.lib().ofs_find_plateau_end(C.byref(rows), int(cp_len), -1 if lookahead is None else int(max(1, lookahead)),
+                                         int(smooth_win), _ptr(out), _stream()), "ofs_find_plateau_end")
+    return out
+
+
+def find_minn_peak(M: torch.Tensor, smooth_win: int = 8, gate_threshold: float = 0.5, search_bounds=None,
+                   want_ms: bool = False):
+    """minn.py:131-205 for every row -> (peak int64[rows], gate_span int64[rows,2], Ms or None)."""
+    rows, M = _rows(M)
+    if want_ms and not M.is_contiguous():
+        rows, M = _rows(M.contiguous())
+    peak = torch.zeros(M.shape[0], dtype=torch.int64, device=M.device)
+    span = torch.zeros((M.shape[0], 2), dtype=torch.int64, device=M.device)
+    Ms = torch.empty(M.shape, dtype=M.dtype, device=M.device) if want_ms else None
+    hb = search_bounds is not None
+    lo, hi = (int(search_bounds[0]), int(search_bounds[1])) if hb else (0, 0)
+    L.check(L.lib().ofs_find_minn_peak(C.byref(rows), int(smooth_win), C.c_double(gate_threshold), int(hb), C.c_int64(lo),
+                                       C.c_int64(hi), _ptr(peak), _ptr(span), _ptr(Ms), _stream()), "ofs_find_minn_peak")
+    return peak, span, Ms
+
+
+def sc_gate(M_sc: torch.Tensor, threshold: float = 0.6) -> torch.Tensor:
+    """combined_sc_min.py:337-351 -> uint8 gate [rows, n]."""
+    rows, M_sc = _rows(M_sc)
+    gate = torch.zeros(M_sc.shape, dtype=torch.uint8, device=M_sc.device)
+    L.check(L.lib().ofs_sc_gate(C.byref(rows), C.c_double(threshold), _ptr(gate), C.c_int64(gate.stride(0) if gate.shape[0] > 1 else gate.shape[1]),
+                                _stream()), "ofs_sc_gate")
+    return gate
+
+
+def find_minn_peak_gated(M: torch.Tensor, smooth_win: int, gate: torch.Tensor, search_bounds=None) -> torch.Tensor:
+    """combined_sc_min.py:183-259 -> int64[rows] (-1 empty metric, -3 empty gate)."""
+    rows, M = _rows(M)
+    g = gate if isinstance(gate, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(gate))
+    if g.dim() == 1:
+        g = g[None]
+    g = g.to(device=M.device, dtype=torch.uint8).contiguous()
+    peak = torch.zeros(M.shape[0], dtype=torch.int64, device=M.device)
+    hb = search_bounds is not None
+    lo, hi = (int(search_bounds[0]), int(search_bounds[1])) if hb else (0, 0)
+    L.check(L.lib().ofs_find_minn_peak_gated(C.byref(rows), int(smooth_win), _ptr(g), C.c_int64(g.shape[1]), int(hb),
+                                             C.c_int64(lo), C.c_int64(hi), _ptr(peak), _stream()), "ofs_find_minn_peak_gated")
+    return peak
+
+
+def argmax(M: torch.Tensor) -> torch.Tensor:
+    rows, M = _rows(M)
+    out = torch.zeros(M.shape[0], dtype=torch.int64, device=M.device)
+    L.check(L.lib().ofs_argmax(C.byref(rows), _ptr(out), _stream()), "ofs_argmax")
+    return out
+
+
+_EVENT_NP = np.dtype([("peak_index", "<i8"), ("gate_start", "<i8"), ("gate_end", "<i8"), ("aux", "<i8"), ("value", "<f8"),
+                      ("p_re", "<f8"), ("p_im", "<f8"), ("cfo", "<f8"), ("closed", "<i4"), ("reserved", "<i4")])
+assert _EVENT_NP.itemsize == C.sizeof(L.Event)
+
+
+def _events_to_numpy(ev: torch.Tensor, cnt: torch.Tensor) -> list[np.ndarray]:
+    raw = ev.cpu().numpy().view(_EVENT_NP).reshape(ev.shape[0], L.OFS_MAX_EVENTS)
+    c = cnt.cpu().numpy()
+    return [raw[i, : min(int(c[i]), L.OFS_MAX_EVENTS)].copy() for i in range(raw.shape[0])]
+
+
+def _event_buffers(n_rows: int, dev):
+    ev = torch.zeros((n_rows, L.OFS_MAX_EVENTS * C.sizeof(L.Event)), dtype=torch.uint8, device=dev)
+    cnt = torch.zeros(n_rows, dtype=torch.int32, device=dev)
+    return ev, cnt
+
+
+def aa_events(M: torch.Tensor, P: torch.Tensor, half_len: int, threshold: float, hysteresis: int, sample_rate: float):
+    """sync_aa.py:495-568 -> list (per row) of structured event arrays."""
+    rows, M = _rows(M)
+    if P.dim() == 1:
+        P = P[None]
+    P = P.to(torch.complex128 if M.dtype == torch.float64 else torch.complex64).contiguous()
+    ev, cnt = _event_buffers(M.shape[0], M.device)
+    L.check(L.lib().ofs_aa_events(C.byref(rows), _ptr(P), int(half_len), C.c_double(threshold), int(hysteresis),
+                                  C.c_double(sample_rate), _ptr(ev), _ptr(cnt), _stream()), "ofs_aa_events")
+    return _events_to_numpy(ev, cnt)
+
+
+def zc_streaming_detection(corr_mag: torch.Tensor, window: int, thresh_value: int, frac_bits: int, min_corr_mag: float):
+    """zc_v2.py:288-336 -> (local_sum, valid uint8, above uint8)."""
+    rows, m = _rows(corr_mag)
+    m = m.contiguous()
+    rows, m = _rows(m)
+    ls = torch.empty_like(m)
+    valid = torch.zeros(m.shape, dtype=torch.uint8, device=m.device)
+    above = torch.zeros(m.shape, dtype=torch.uint8, device=m.device)
+    L.check(L.lib().ofs_zc_streaming_detection(C.byref(rows), int(window), int(thresh_value), int(frac_bits),
+                                               C.c_double(min_corr_mag), _ptr(ls), _ptr(valid), _ptr(above),
+                                               C.c_int64(m.shape[1]), _stream()), "ofs_zc_streaming_detection")
+    return ls, valid, above
+
+
+def zc_events(corr_mag: torch.Tensor, valid: torch.Tensor, above: torch.Tensor, reference_length: int, hysteresis: int,
+              want_gate_mask: bool = True):
+    """zc_v2.py:360-450 -> (events per row, gate_mask uint8 or None)."""
+    rows, m = _rows(corr_mag)
+    m = m.contiguous()
+    rows, m = _rows(m)
+    v = valid.to(device=m.device, dtype=torch.uint8).reshape(m.shape).contiguous()
+    a = above.to(device=m.device, dtype=torch.uint8).reshape(m.shape).contiguous()
+    gm = torch.zeros(m.shape, dtype=torch.uint8, device=m.device) if want_gate_mask else None
+    ev, cnt = _event_buffers(m.shape[0], m.device)
+    L.check(L.lib().ofs_zc_events(C.byref(rows), _ptr(v), _ptr(a), C.c_int64(m.shape[1]), int(reference_length), int(hysteresis),
+                                  _ptr(ev), _ptr(cnt), _ptr(gm), _stream()), "ofs_zc_events")
+    return _events_to_numpy(ev, cnt), gm
+
+
+def minn_rtl_events(corr_positive: torch.Tensor, valid: torch.Tensor, above: torch.Tensor, hysteresis: int, timing_offset: int):
+    """minn_rtl.py:750-825 -> events per row (closed == 0 marks an unclosed tail segment)."""
+    cp = corr_positive if corr_positive.dim() == 2 else corr_positive[None]
+    is_int = cp.dtype == torch.int64
+    if not is_int:
+        cp = cp.to(torch.float64)
+    cp = cp.to(_device()).contiguous()
+    v = valid.to(device=cp.device, dtype=torch.uint8).reshape(cp.shape).contiguous()
+    a = above.to(device=cp.device, dtype=torch.uint8).reshape(cp.shape).contiguous()
+    ev, cnt = _event_buffers(cp.shape[0], cp.device)
+    L.check(L.lib().ofs_minn_rtl_events(_ptr(cp), int(is_int), _ptr(v), _ptr(a), C.c_int64(cp.shape[0]), C.c_int64(cp.shape[1]),
+                                        C.c_int64(cp.shape[1]), int(hysteresis), int(timing_offset), _ptr(ev), _ptr(cnt),
+                                        _stream()), "ofs_minn_rtl_events")
+    return _events_to_numpy(ev, cnt)
+
+
+# ------------------------------------------------------------------------------------------- sync pipeline
+_REC_NP = np.dtype([("timing", "<i8"), ("coarse", "<i8"), ("metric", "<f4"), ("p_re", "<f4"), ("p_im", "<f4"), ("cfo", "<f4")])
+assert _REC_NP.itemsize == C.sizeof(L.SyncRecord)
+
+
+@dataclass
+class SyncOut:
+    M: torch.Tensor            # [F, out_len] float32 view
+    records: torch.Tensor      # [F, 32] uint8 (ofs_sync_record); use records_numpy()
+    chunk_max: torch.Tensor
+
+    def records_numpy(self) -> np.ndarray:
+        return self.records.cpu().numpy().view(_REC_NP).reshape(-1)
+
+
+class SyncPlan:
+    """Pre-allocated buffers for repeated ofs_sync calls on device-resident frames [F, L] complex64/int16-IQ."""
+
+    def __init__(self, n_frames: int, n_samples: int, kind: str = "sc", symbol_len: int = 2048, in_dtype: str = "c64",
+                 cp_len: int = 512, smooth_win: int = 16, sc_delta: int = 16, gate_threshold: float = 0.5, store_mode: int = 1):
+        dev = _device()
+        self.F, self.n, self.kind, self.N = n_frames, n_samples, kind, symbol_len
+        self.code = {"c64": L.OFS_C64, "iq16": L.OFS_IQ16}[in_dtype]
+        self.cp_len, self.smooth_win, self.sc_delta, self.gate_threshold = cp_len, smooth_win, sc_delta, gate_threshold
+        self.toff = symbol_len - 1
+        self.pitch = (n_samples + 3) // 4 * 4
+        self.out_len = max(n_samples - symbol_len + 1, 0)
+        self.buf = torch.empty((n_frames, self.pitch), dtype=torch.float32, device=dev)
+        self.M = self.buf[:, self.toff:self.toff + self.out_len]
+        self.cm_stride = (n_samples + 255) // 256
+        self.cm = torch.zeros((n_frames, self.cm_stride), dtype=torch.float32, device=dev)
+        self.rec = torch.zeros((n_frames, C.sizeof(L.SyncRecord)), dtype=torch.uint8, device=dev)
+        self.scratch = torch.zeros(3 * n_frames, dtype=torch.int64, device=dev)
+        self.desc = L.MetricDesc(kind=KINDS[kind], in_dtype=self.code, out_f64=0, path=L.OFS_PATH_AUTO, symbol_len=symbol_len,
+                                 n_branches=1, n_frames=n_frames, n_samples=n_samples, x_frame_stride=n_samples,
+                                 x_branch_stride=n_samples, out_stride=self.pitch, store_mode=store_mode, reserved=0)
+
+    def run(self, x: torch.Tensor) -> SyncOut:
+        assert x.is_cuda and x.is_contiguous() and x.shape[0] == self.F
+        L.check(L.lib().ofs_sync(C.byref(self.desc), _ptr(x), C.c_void_p(self.M.data_ptr()), _ptr(self.cm), C.c_int64(self.cm_stride),
+                                 int(self.cp_len), int(self.smooth_win), int(self.sc_delta), C.c_double(self.gate_threshold),
+                                 _ptr(self.rec), _ptr(self.scratch), _stream()), "ofs_sync")
+        return SyncOut(self.M, self.rec, self.cm)
+
+    def records_numpy(self) -> np.ndarray:
+        return self.rec.cpu().numpy().view(_REC_NP).reshape(-1)
+
+    def run_detect_only(self, x: torch.Tensor) -> None:
+        L.check(L.lib().ofs_sync_detect(C.byref(self.desc), _ptr(x), C.c_void_p(self.M.data_ptr()), int(self.cp_len),
+                                        int(self.smooth_win), int(self.sc_delta), C.c_double(self.gate_threshold), _ptr(self.rec),
+                                        _ptr(self.scratch), _stream()), "ofs_sync_detect")
+
+    def run_metric_only(self, x: torch.Tensor) -> None:
+        L.check(L.lib().ofs_metric(C.byref(self.desc), _ptr(x), C.c_void_p(self.M.data_ptr()), None, None, _ptr(self.cm),
+                                   C.c_int64(self.cm_stride), _stream()), "ofs_metric")
+
+
+class HostSync:
+    """ofs_sync_host: frames in (pinned) host memory -> M + records in host memory, copies pipelined inside the library."""
+
+    def __init__(self, device: int | None = None):
+        self.ctx = C.c_void_p()
+        dev = torch.cuda.current_device() if device is None else device
+        L.check(L.lib().ofs_ctx_create(C.byref(self.ctx), int(dev)), "ofs_ctx_create")
+
+    def close(self):
+        if self.ctx:
+            L.lib().ofs_ctx_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, x_host: torch.Tensor, M_host: torch.Tensor | None, records_host: torch.Tensor, *, kind="sc", symbol_len=2048,
+            cp_len=512, smooth_win=16, sc_delta=16, gate_threshold=0.5):
+        F, n = x_host.shape[0], x_host.shape[1]
+        code = L.OFS_IQ16 if x_host.dtype == torch.int16 else L.OFS_C64
+        out_stride = M_host.stride(0) if M_host is not None else max(n - symbol_len + 1, 0)
+        d = L.MetricDesc(kind=KINDS[kind], in_dtype=code, out_f64=0, path=L.OFS_PATH_AUTO, symbol_len=symbol_len, n_branches=1,
+                         n_frames=F, n_samples=n, x_frame_stride=x_host.stride(0), x_branch_stride=n, out_stride=out_stride,
+                         store_mode=1, reserved=0)
+        L.check(L.lib().ofs_sync_host(self.ctx, C.byref(d), _ptr(x_host), _ptr(M_host), int(cp_len), int(smooth_win), int(sc_delta),
+                                      C.c_double(gate_threshold), _ptr(records_host)), "ofs_sync_host")
+        return records_host.numpy().view(_REC_NP).reshape(-1)
+
+
+# ------------------------------------------------------------------------------------------- park
+def park_metric(rx, symbol_len: int = 2048, out_f64: bool | None = None):
+    """park.py:64-114 -> (M, P, E) tensors [F, n], n = L - 2*(N/2)."""
+    x, code, _ = to_device(rx)
+    F, B, n = x.shape[0], x.shape[1], x.shape[2]
+    if out_f64 is None:
+        out_f64 = code == L.OFS_C128
+    h = symbol_len // 2
+    n_out = max(n - 2 * h, 0) if h > 0 else 0
+    rdt = torch.float64 if out_f64 else torch.float32
+    cdt = torch.complex128 if out_f64 else torch.complex64
+    M = torch.empty((F, n_out), dtype=rdt, device=x.device)
+    P = torch.empty((F, n_out), dtype=cdt, device=x.device)
+    E = torch.empty((F, n_out), dtype=rdt, device=x.device)
+    if n_out > 0 and F > 0:
+        d = L.MetricDesc(kind=0, in_dtype=code, out_f64=int(out_f64), path=0, symbol_len=int(symbol_len), n_branches=B,
+                         n_frames=F, n_samples=n, x_frame_stride=B * n, x_branch_stride=n, out_stride=n_out, store_mode=0,
+                         reserved=0)
+        L.check(L.lib().ofs_park_metric(C.byref(d), _ptr(x), _ptr(M), _ptr(P), _ptr(E), _stream()), "ofs_park_metric")
+    return M, P, E
+
+
+# ------------------------------------------------------------------------------------------- sync_aa
+def aa_metric_reference(rx, half_len: int):
+    """Reference-order [A][A] running sums (sync_aa.py:321-386, 458-493) -> P c128, R, M f64, valid u8, each [F, n]."""
+    x, code, _ = to_device(rx)
+    F, A, n = x.shape[0], x.shape[1], x.shape[2]
+    dev = x.device
+    P = torch.empty((F, n), dtype=torch.complex128, device=dev)
+    R = torch.empty((F, n), dtype=torch.float64, device=dev)
+    M = torch.empty((F, n), dtype=torch.float64, device=dev)
+    valid = torch.empty((F, n), dtype=torch.uint8, device=dev)
+    L.check(L.lib().ofs_aa_metric_reference(_ptr(x), code, C.c_int64(F), int(A), C.c_int64(n), int(half_len), _ptr(P), _ptr(R),
+                                            _ptr(M), _ptr(valid), _stream()), "ofs_aa_metric_reference")
+    return P, R, M, valid
+
+
+# ------------------------------------------------------------------------------------------- minn_rtl
+def minn_rtl_metric(rx, quarter_len: int, smooth_shift: int, threshold_value: int, frac_bits: int) -> dict:
+    """minn_rtl.py:583-733 (float mirror) -> dict of 8 tensors [F, n]."""
+    x, code, _ = to_device(rx)
+    if code == L.OFS_IQ16:
+        raise TypeError("minn_rtl_metric takes complex input; use minn_rtl_int for int16 IQ")
+    F, B, n = x.shape[0], x.shape[1], x.shape[2]
+    dev = x.device
+    f = lambda: torch.empty((F, n), dtype=torch.float64, device=dev)
+    u = lambda: torch.empty((F, n), dtype=torch.uint8, device=dev)
+    d = dict(corr_total=f(), corr_positive=f(), smooth_metric=f(), energy_total=f(), corr_scaled=f(), energy_scaled=f(),
+             metric_valid=u(), above_threshold=u())
+    rc = L.lib().ofs_minn_rtl_metric(_ptr(x), code, C.c_int64(F), int(B), C.c_int64(n), int(quarter_len), int(smooth_shift),
+                                     int(threshold_value), int(frac_bits), *[_ptr(d[k]) for k in d], _stream())
+    L.check(rc, "ofs_minn_rtl_metric")
+    return d
+
+
+def minn_rtl_int(iq, quarter_len: int, smooth_shift: int, threshold_value: int, frac_bits: int, lag_extra: int = 0) -> dict:
+    """Integer RTL datapath (ref/minn_antenna_path.sv, ref/minn_preamble_detector.sv:247-325) -> int64 tensors [F, n]."""
+    x, code, _ = to_device(iq)
+    if code != L.OFS_IQ16:
+        raise TypeError("minn_rtl_int takes int16 IQ input with a trailing axis of 2")
+    F, B, n = x.shape[0], x.shape[1], x.shape[2]
+    dev = x.device
+    f = lambda: torch.empty((F, n), dtype=torch.int64, device=dev)
+    u = lambda: torch.empty((F, n), dtype=torch.uint8, device=dev)
+    d = dict(corr_total=f(), corr_positive=f(), smooth_metric=f(), energy_total=f(), metric_valid=u(), above_threshold=u())
+    rc = L.lib().ofs_minn_rtl_int(_ptr(x), C.c_int64(F), int(B), C.c_int64(n), int(quarter_len), int(smooth_shift),
+                                  int(threshold_value), int(frac_bits), int(lag_extra), *[_ptr(d[k]) for k in d], _stream())
+    L.check(rc, "ofs_minn_rtl_int")
+    return d
+
+
+# ------------------------------------------------------------------------------------------- Zadoff-Chu
+def zc_matched_filter(rx, ref, mode: int = 0, out_f64: bool | None = None):
+    """FFT overlap-save matched filter (zc.py:115-126 mode 0, zc_v2.py:486-495 mode 1, raw sum mode 2)
+    -> (corr complex [F, n+nr-1], |corr|)."""
+    x, code, _ = to_device(rx)
+    F, B, n = x.shape[0], x.shape[1], x.shape[2]
+    if out_f64 is None:
+        out_f64 = code == L.OFS_C128
+    r = torch.as_tensor(np.ascontiguousarray(np.asarray(ref, dtype=np.complex128))).to(x.device)
+    nr = r.numel()
+    n_out = n + nr - 1
+    cdt = torch.complex128 if out_f64 else torch.complex64
+    rdt = torch.float64 if out_f64 else torch.float32
+    corr = torch.empty((F, n_out), dtype=cdt, device=x.device)
+    mag = torch.empty((F, n_out), dtype=rdt, device=x.device)
+    L.check(L.lib().ofs_zc_matched_filter(_ptr(x), code, C.c_int64(F), int(B), C.c_int64(n), _ptr(r), int(nr), int(mode),
+                                          int(out_f64), _ptr(corr), _ptr(mag), C.c_int64(n_out), _stream()), "ofs_zc_matched_filter")
+    return corr, mag
+
+
+def zc_freq_metric(rx, bin_indices, template_bins, template_energy: float, n_fft: int = 2048, cp: int = 512,
+                   out_f64: bool | None = None) -> torch.Tensor:
+    """zc_freq.py:62-99 -> metric [F, n - (n_fft+cp) + 1]."""
+    x, code, _ = to_device(rx)
+    F, B, n = x.shape[0], x.shape[1], x.shape[2]
+    if out_f64 is None:
+        out_f64 = code == L.OFS_C128
+    n_off = n - (n_fft + cp) + 1
+    if n_off <= 0:
+        raise ValueError("Received stream is shorter than a single OFDM symbol.")     # zc_freq.py:76-78
+    # positions = (N/2 + idx) % N index the fftshifted spectrum == plain DFT bin idx mod N
+    k = np.mod(np.asarray(bin_indices, dtype=np.int64), n_fft).astype(np.int32)
+    bins = torch.as_tensor(k).to(x.device)
+    t = torch.as_tensor(np.ascontiguousarray(np.asarray(template_bins, dtype=np.complex128))).to(x.device)
+    out = torch.empty((F, n_off), dtype=torch.float64 if out_f64 else torch.float32, device=x.device)
+    L.check(L.lib().ofs_zc_freq_metric(_ptr(x), code, C.c_int64(F), int(B), C.c_int64(n), int(n_fft), int(cp), _ptr(bins), _ptr(t),
+                                       int(k.size), C.c_double(float(template_energy)), int(out_f64), _ptr(out), C.c_int64(n_off),
+                                       _stream()), "ofs_zc_freq_metric")
+    return out

@@ -1,0 +1,123 @@
+"""Synthetic frames for tests and bench.py (NOT on the hot path): preamble + pilot + data through a
+measured CIR, AWGN and CFO -- the recipe of the reference's scripts (sc.py:181-202, minn.py:337-361,
+channel.py:51-98, core.py:123-138), restated so that inputs can be generated on the GPU box where
+/root/reference does not exist.  Host builders are numpy; `make_batch_device` fills a device batch
+with torch (cuFFT convolution + Philox noise) -- input generation only, never timed.
+"""
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+
+N_FFT, NUM_ACTIVE, CP, PRE_PAD, FS = 2048, 1200, 512, 1337, 30_720_000.0
+_CIR_FIXTURE = Path(__file__).resolve().parent.parent / "tests" / "golden" / "cir.npz"
+
+
+def centered_idx(width: int) -> np.ndarray:
+    h = width // 2
+    return np.concatenate((np.arange(-h, 0), np.arange(1, h + 1)))
+
+
+def _to_time(idx: np.ndarray, vals: np.ndarray, n_fft: int = N_FFT) -> np.ndarray:
+    spec = np.zeros(n_fft, dtype=complex)
+    spec[(n_fft // 2 + idx) % n_fft] = vals
+    td = np.fft.ifft(np.fft.ifftshift(spec))
+    p = np.mean(np.abs(td) ** 2)
+    return td / np.sqrt(p) if p > 0 else td
+
+
+def _with_cp(sym: np.ndarray, cp: int = CP) -> np.ndarray:
+    return np.concatenate((sym[-cp:], sym)) if cp > 0 else sym
+
+
+def sc_preamble(rng: np.random.Generator) -> np.ndarray:
+    """BPSK on the even active subcarriers -> two identical halves (sc.py:31-39)."""
+    idx = centered_idx(NUM_ACTIVE)
+    even = idx[idx % 2 == 0]
+    return _with_cp(_to_time(even, rng.choice([-1.0, 1.0], size=even.size)))
+
+
+def minn_preamble(rng: np.random.Generator) -> np.ndarray:
+    """[A A -A -A] from a quarter-length BPSK symbol (structure of minn.py:30-56)."""
+    q = N_FFT // 4
+    idx = centered_idx(NUM_ACTIVE // 4)
+    a = _to_time(idx, rng.choice([-1.0, 1.0], size=idx.size), q)
+    sym = np.concatenate((a, a, -a, -a))
+    return _with_cp(sym / np.sqrt(np.mean(np.abs(sym) ** 2)))
+
+
+def qpsk_symbol(rng: np.random.Generator) -> np.ndarray:
+    idx = centered_idx(NUM_ACTIVE)
+    m = rng.integers(0, 4, size=idx.size)
+    vals = (((m & 1) * 2 - 1) + 1j * (((m >> 1) & 1) * 2 - 1)) / np.sqrt(2.0)
+    return _with_cp(_to_time(idx, vals))
+
+
+def frame(rng: np.random.Generator, kind: str = "sc") -> np.ndarray:
+    pre = sc_preamble(rng) if kind == "sc" else minn_preamble(rng)
+    return np.concatenate((np.zeros(PRE_PAD, complex), pre, qpsk_symbol(rng), qpsk_symbol(rng)))
+
+
+def load_cirs() -> dict:
+    """cir1 / cir2 (2 RX channels x 1100 taps) from the committed fixture (made from channel_models/*.csv)."""
+    d = np.load(_CIR_FIXTURE)
+    return {"cir1": d["cir1"], "cir2": d["cir2"]}
+
+
+def apply_channel_host(tx: np.ndarray, snr_db: float, rng: np.random.Generator, cir: np.ndarray | None, cfo_hz: float,
+                       fs: float = FS) -> np.ndarray:
+    """channel.apply_channel (one branch) + core.apply_cfo, numpy."""
+    faded = tx if cir is None else np.convolve(tx, cir, mode="full")
+    p = np.mean(np.abs(faded) ** 2)
+    std = np.sqrt(p / (10 ** (snr_db / 10)) / 2)
+    rx = faded + std * (rng.standard_normal(faded.shape) + 1j * rng.standard_normal(faded.shape))
+    n = np.arange(rx.size, dtype=float)
+    return rx * np.exp(1j * 2 * np.pi * cfo_hz * n / fs)
+
+
+def tiled_stream_host(n_samples: int, seed: int, kind: str = "sc", cir: np.ndarray | None = None, snr_db: float = 10.0,
+                      cfo_hz: float = 1000.0) -> np.ndarray:
+    """One capture of n_samples complex64: frames tiled back to back, channel, AWGN, CFO (BASELINE cfg 2/3)."""
+    rng = np.random.default_rng(seed)
+    taps = 0 if cir is None else cir.size - 1
+    fr = frame(rng, kind)
+    reps = (n_samples - taps + fr.size - 1) // fr.size
+    tx = np.tile(fr, reps)[: n_samples - taps]
+    return apply_channel_host(tx, snr_db, rng, cir, cfo_hz).astype(np.complex64)
+
+
+def make_batch_device(n_frames: int, n_samples: int, kind: str = "sc", seed: int = 0, device=None, n_base: int = 32,
+                      chunk: int = 64):
+    """[n_frames, n_samples] complex64 on the device: base frames tiled, cir1-ch1 (even) / cir2-ch1 (odd) by FFT
+    convolution, SNR cycling {0,5,10,15,20} dB, CFO = linspace(-10 kHz, +10 kHz) (SURVEY.md 8d cfg 2)."""
+    import torch
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    cirs = load_cirs()
+    taps = cirs["cir1"].shape[1]
+    n_tx = n_samples - (taps - 1)
+    rng = np.random.default_rng(seed)
+    base = np.stack([np.tile(frame(rng, kind), (n_tx + 9016) // 9017)[:n_tx] for _ in range(n_base)]).astype(np.complex64)
+    base_d = torch.as_tensor(base).to(device)
+    nfft = 1 << int(np.ceil(np.log2(n_samples)))
+    H = [torch.fft.fft(torch.as_tensor(cirs[k][1].astype(np.complex64)).to(device), n=nfft) for k in ("cir1", "cir2")]
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    out = torch.empty((n_frames, n_samples), dtype=torch.complex64, device=device)
+    snrs = torch.tensor([0.0, 5.0, 10.0, 15.0, 20.0], device=device)
+    cfos = torch.linspace(-10e3, 10e3, max(n_frames, 2), device=device)[:n_frames]
+    t = torch.arange(n_samples, device=device, dtype=torch.float32)
+    for f0 in range(0, n_frames, chunk):
+        f1 = min(f0 + chunk, n_frames)
+        fidx = torch.arange(f0, f1, device=device)
+        tx = base_d[fidx % n_base]
+        X = torch.fft.fft(tx, n=nfft)
+        Hsel = torch.stack([H[int(i) & 1] for i in range(f0, f1)])
+        faded = torch.fft.ifft(X * Hsel)[:, :n_samples]
+        p = faded.abs().square().mean(dim=1, keepdim=True)
+        std = torch.sqrt(p / torch.pow(10.0, snrs[fidx % 5][:, None] / 10.0) / 2.0)
+        noise = torch.randn((f1 - f0, n_samples, 2), generator=gen, device=device, dtype=torch.float32)
+        rx = faded + std * torch.view_as_complex(noise)
+        ph = (2.0 * np.pi / FS) * cfos[fidx][:, None] * t[None, :]
+        out[f0:f1] = rx * torch.polar(torch.ones_like(ph), ph)
+    return out

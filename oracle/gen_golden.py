@@ -336,6 +336,32 @@ def gen_detector_cases(out: Path) -> None:
     np.savez_compressed(out / "detector_cases.npz", **d)
 
 
+def gen_cir_and_scale(out: Path) -> None:
+    """CIR taps (channel_models/cir{1,2}.csv through channel.load_measured_cir) and a small BASELINE-cfg-2 style
+    parity set made with the REAL channel.py / core.apply_cfo: tiled sc.py frames, cir1/cir2 ch1, AWGN, CFO,
+    cast to complex64; expected outputs from the unmodified sc.py functions on the cast input."""
+    import channel, core, sc
+    np.savez_compressed(out / "cir.npz", cir1=channel.load_measured_cir("cir1"), cir2=channel.load_measured_cir("cir2"))
+    n_samples, n_frames = 24576, 4
+    xs, Ms, ends = [], [], []
+    for f in range(n_frames):
+        rng = np.random.default_rng(f)
+        pre = sc.build_sc_preamble(rng, include_cp=True)
+        pilot, _ = core.build_random_qpsk_symbol(rng, include_cp=True)
+        data, _ = core.build_random_qpsk_symbol(rng, include_cp=True)
+        fr = np.concatenate((np.zeros(core.TX_PRE_PAD_SAMPLES, complex), pre, pilot, data))
+        cir = channel.load_measured_cir("cir1" if f % 2 == 0 else "cir2")[1:2]
+        n_tx = n_samples - (cir.shape[1] - 1)
+        tx = np.tile(fr, (n_tx + fr.size - 1) // fr.size)[:n_tx]
+        rx = channel.apply_channel(tx, [0.0, 5.0, 10.0, 15.0][f], rng, channel_impulse_response=cir)
+        rx = core.apply_cfo(rx, [-10e3, -3e3, 3e3, 10e3][f], core.SAMPLE_RATE_HZ)[0].astype(np.complex64)
+        M, P, R = sc.sc_streaming_metric(rx.astype(np.complex128))
+        xs.append(rx); Ms.append(M)
+        ends.append(sc.find_plateau_end_from_metric(M, 512, lookahead=128, smooth_win=16))
+    np.savez_compressed(out / "scale_sc.npz", x=np.stack(xs), M=np.stack(Ms).astype(np.float64), plateau_end=np.asarray(ends, np.int64))
+    print("scale_sc", ends)
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -346,7 +372,8 @@ def main() -> None:
     out.mkdir(parents=True, exist_ok=True)
     _setup(a.ref)
     gens = dict(sc=gen_sc, minn=gen_minn, park=gen_park, combined=gen_combined, zc=gen_zc, zc_v2=gen_zc_v2,
-                zc_freq=gen_zc_freq, minn_rtl=gen_minn_rtl, detector_cases=gen_detector_cases)
+                zc_freq=gen_zc_freq, minn_rtl=gen_minn_rtl, detector_cases=gen_detector_cases,
+                cir_scale=gen_cir_and_scale)
     for name, fn in gens.items():
         if a.only and name not in a.only.split(","):
             continue

@@ -1,0 +1,59 @@
+"""N > 1 host logic on CPU: world_size-2 gloo process group, contiguous frame sharding, record all-gather."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, n_total, q):
+    sys.path.insert(0, str(ROOT))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ofdm_sync_math_b200 import dist as odist
+    lo, hi = odist.shard_range(n_total)
+    rec = torch.zeros((hi - lo, 32), dtype=torch.uint8)
+    for i in range(hi - lo):                      # record = global frame index, byte-wise
+        rec[i] = torch.tensor(np.frombuffer(np.int64(lo + i).tobytes() * 4, dtype=np.uint8))
+    allrec = odist.gather_records(rec, n_total)
+    ok = allrec.shape == (n_total, 32) and np.array_equal(allrec.view(np.int64)[:, 0], np.arange(n_total))
+    q.put((rank, lo, hi, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_shard_range_partition():
+    from ofdm_sync_math_b200 import dist as odist
+    for n in (0, 1, 7, 8, 4096, 4097):
+        for w in (1, 2, 3, 8):
+            r = [odist.shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[k][1] == r[k + 1][0] for k in range(w - 1))
+            assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+            assert odist.shard_sizes(n, w) == [b - a for a, b in r]
+
+
+@pytest.mark.parametrize("n_total", [8, 11])
+def test_gloo_world2_gather_records(n_total):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == 0 and res[0][2] == res[1][1] and res[1][2] == n_total
+    assert all(r[3] for r in res)

@@ -23,6 +23,11 @@ def _captures(n_frames, n, kind="sc", seed=0):
     return np.stack(out)
 
 
+def _dev(x):
+    """[frames, L] host array -> [frames, 1 branch, L] device tensor (2-D input would mean (branches, L))."""
+    return torch.as_tensor(x).cuda()[:, None]
+
+
 def _oracle_metric(x, kind, N):
     if kind == "aa":
         return np.stack([orc.aa_detect_streaming(r.astype(np.complex128), L=N)["M"] for r in x])
@@ -45,7 +50,7 @@ def test_stripe_metric_vs_oracle(kind, N, store_mode):
     from ofdm_sync_math_b200 import engine
     n = 40960 + 2 * 4096            # several stripes worth of blocks
     x = _captures(3, n, "minn" if kind == "minn" else "sc", seed=1)
-    r = engine.metric(torch.as_tensor(x).cuda(), kind, N, want_pr=False, path="stripe", store_mode=store_mode, want_chunk_max=True)
+    r = engine.metric(_dev(x), kind, N, want_pr=False, path="stripe", store_mode=store_mode, want_chunk_max=True)
     assert r.path == "stripe"
     M = r.M.cpu().numpy()
     M_ref = _oracle_metric(x, kind, N)
@@ -63,7 +68,7 @@ def test_stripe_ragged_lengths_and_alignment(n):
     """Odd / short lengths: tail blocks, frames whose rows are not 16-byte aligned (plain-load path), single stripe."""
     from ofdm_sync_math_b200 import engine
     x = _captures(2, n, "sc", seed=2)
-    r = engine.metric(torch.as_tensor(x).cuda(), "sc", 2048, want_pr=False, path="stripe")
+    r = engine.metric(_dev(x), "sc", 2048, want_pr=False, path="stripe")
     _check_metric(r.M.cpu().numpy(), _oracle_metric(x, "sc", 2048))
 
 
@@ -72,7 +77,7 @@ def test_stripe_long_frame_many_stripes():
     n = 1 << 20
     x = _captures(1, n, "minn", seed=3)
     for kind in ("minn", "sc"):
-        r = engine.metric(torch.as_tensor(x).cuda(), kind, 2048, want_pr=False, path="stripe")
+        r = engine.metric(_dev(x), kind, 2048, want_pr=False, path="stripe")
         _check_metric(r.M.cpu().numpy(), _oracle_metric(x, kind, 2048))
 
 
@@ -92,7 +97,7 @@ def test_tile_matches_stripe_and_oracle_c64():
     from ofdm_sync_math_b200 import engine
     x = _captures(4, 30000, "sc", seed=5)
     for kind, N in (("sc", 2048), ("sc_both", 1000), ("minn", 2048), ("minn", 900)):
-        r = engine.metric(torch.as_tensor(x).cuda(), kind, N, want_pr=True, path="tile")
+        r = engine.metric(_dev(x), kind, N, want_pr=True, path="tile")
         ref = [getattr(orc, {"sc": "sc_streaming_metric", "sc_both": "schmidl_cox_streaming_metric", "minn": "minn_streaming_metric"}[kind])(
             row.astype(np.complex128), N) for row in x]
         _check_metric(r.M.cpu().numpy(), np.stack([t[0] for t in ref]))
@@ -100,7 +105,7 @@ def test_tile_matches_stripe_and_oracle_c64():
         assert np.max(np.abs(r.P.cpu().numpy() - Pref)) <= 2e-6 * np.max(np.abs(Pref))
     # two branches summed before the metric (sc.py:73-74): frames (2, 2, L)
     xb = x.reshape(2, 2, -1)
-    r = engine.metric(torch.as_tensor(xb).cuda(), "sc", 2048, want_pr=True, path="tile")
+    r = engine.metric(torch.as_tensor(xb).cuda(), "sc", 2048, want_pr=True, path="tile")  # (frames, branches, L)
     for f in range(2):
         M0, P0, R0 = orc.sc_streaming_metric(xb[f].astype(np.complex128))
         _check_metric(r.M[f:f + 1].cpu().numpy(), M0[None])
@@ -109,14 +114,14 @@ def test_tile_matches_stripe_and_oracle_c64():
 def test_batched_detectors_vs_oracle():
     from ofdm_sync_math_b200 import engine
     x = _captures(6, 30000, "sc", seed=6)
-    M = engine.metric(torch.as_tensor(x).cuda(), "sc", 2048, want_pr=False, path="stripe").M
+    M = engine.metric(_dev(x), "sc", 2048, want_pr=False, path="stripe").M
     Mh = M.cpu().numpy().astype(np.float64)
     ends = engine.find_plateau_end(M, 512, 128, 16).cpu().numpy()
     assert ends.tolist() == [orc.find_plateau_end_from_metric(r, 512, 128, 16) for r in Mh]
     am = engine.argmax(M).cpu().numpy()
     assert am.tolist() == [int(np.argmax(r)) for r in Mh]
     xm = _captures(5, 30000, "minn", seed=7)
-    Mm = engine.metric(torch.as_tensor(xm).cuda(), "minn", 2048, want_pr=False, path="stripe").M
+    Mm = engine.metric(_dev(xm), "minn", 2048, want_pr=False, path="stripe").M
     Mmh = Mm.cpu().numpy().astype(np.float64)
     pk, span, _ = engine.find_minn_peak(Mm, 16, 0.5)
     ref = [orc.find_minn_peak(r, 16, 0.5) for r in Mmh]
@@ -125,7 +130,7 @@ def test_batched_detectors_vs_oracle():
         idx = np.flatnonzero(t[1])
         assert span[f].cpu().numpy().tolist() == [idx[0], idx[-1] + 1]
     # S&C-gated Minn peak (combined_sc_min.py:337-365)
-    Msc = engine.metric(torch.as_tensor(xm).cuda(), "sc_both", 2048, want_pr=False, path="stripe").M
+    Msc = engine.metric(_dev(xm), "sc_both", 2048, want_pr=False, path="stripe").M
     gate = engine.sc_gate(Msc, 0.6)
     gh = gate.cpu().numpy().astype(bool)
     Msch = Msc.cpu().numpy().astype(np.float64)

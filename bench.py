@@ -143,7 +143,7 @@ def main() -> None:
     ap.add_argument("--frames", type=int, default=4096, help="frames per GPU")
     ap.add_argument("--samples", type=int, default=262144)
     ap.add_argument("--e2e-frames", type=int, default=1024, help="frames per GPU pushed through ofs_sync_host per e2e step")
-    ap.add_argument("--store-mode", type=int, default=1)
+    ap.add_argument("--store-mode", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

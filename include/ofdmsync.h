@@ -64,7 +64,7 @@ typedef struct ofs_metric_desc {
     int64_t x_frame_stride;   /* in samples */
     int64_t x_branch_stride;  /* in samples */
     int64_t out_stride;       /* elements between frames in M / P / R / chunk_max (>= out_len) */
-    int32_t store_mode;       /* stripe path only: 0 direct vector stores, 1 TMA bulk stores (default) */
+    int32_t store_mode;       /* stripe path only: 0 direct 16-byte vector stores (default, faster), 1 TMA bulk stores */
     int32_t reserved;
 } ofs_metric_desc;
 
@@ -110,6 +110,15 @@ int ofs_find_plateau_end(const ofs_rows *M, int32_t cp_len, int32_t lookahead, i
 int ofs_find_minn_peak(const ofs_rows *M, int32_t smooth_win, double gate_threshold, int32_t has_bounds,
                        int64_t bound_lo, int64_t bound_hi, int64_t *peak, int64_t *gate_span, void *Ms,
                        void *stream);
+
+/* Same detectors, pruned with the stripe kernel's per-chunk maxima (chunk_max rows of ofs_metric, chunk c = the 256
+ * causal sample times [256c, 256c+256), output index d = t - toff): chunks whose maximum cannot reach the
+ * running best are not re-read from HBM.  Results are identical to the unpruned calls. */
+int ofs_find_plateau_end_pruned(const ofs_rows *M, const float *chunk_max, int64_t cm_stride, int32_t toff,
+                                int32_t cp_len, int32_t lookahead, int32_t smooth_win, int64_t *plateau_end, void *stream);
+int ofs_find_minn_peak_pruned(const ofs_rows *M, const float *chunk_max, int64_t cm_stride, int32_t toff,
+                              int32_t smooth_win, double gate_threshold, int32_t has_bounds, int64_t bound_lo,
+                              int64_t bound_hi, int64_t *peak, int64_t *gate_span, void *Ms, void *stream);
 
 /* combined_sc_min: S&C gate construction :337-351 (gate = M_sc/max >= thr, seeded with argmax) */
 int ofs_sc_gate(const ofs_rows *Msc, double threshold, uint8_t *gate, int64_t gate_stride, void *stream);
@@ -218,9 +227,9 @@ int ofs_sync(const ofs_metric_desc *d, const void *x, float *M, float *chunk_max
              int32_t cp_len, int32_t smooth_win, int32_t sc_delta, double gate_threshold,
              ofs_sync_record *records, int64_t *scratch /* int64[3*n_frames] */, void *stream);
 /* Second half of ofs_sync alone (detector + P/CFO records on an already computed metric). */
-int ofs_sync_detect(const ofs_metric_desc *d, const void *x, const float *M, int32_t cp_len, int32_t smooth_win,
-                    int32_t sc_delta, double gate_threshold, ofs_sync_record *records, int64_t *scratch,
-                    void *stream);
+int ofs_sync_detect(const ofs_metric_desc *d, const void *x, const float *M, const float *chunk_max, int64_t cm_stride,
+                    int32_t cp_len, int32_t smooth_win, int32_t sc_delta, double gate_threshold,
+                    ofs_sync_record *records, int64_t *scratch, void *stream);
 /* Host version: x_host (n_frames x n_samples, dtype per d->in_dtype), M_host optional (float32
  * [n_frames][out_stride]); records_host[n_frames].  Frames are pipelined through the ctx workspace
  * in batches (H2D, kernels, D2H overlapped on three streams). */

@@ -135,9 +135,9 @@ OFS_API int ofs_metric(const ofs_metric_desc *d, const void *x, void *M, void *P
     return launch_metric_tile(d, x, M, P, R, (cudaStream_t)stream);
 }
 
-OFS_API int ofs_sync_detect(const ofs_metric_desc *d, const void *x, const float *M, int32_t cp_len, int32_t smooth_win,
-                            int32_t sc_delta, double gate_threshold, ofs_sync_record *records, int64_t *scratch,
-                            void *stream)
+OFS_API int ofs_sync_detect(const ofs_metric_desc *d, const void *x, const float *M, const float *chunk_max,
+                            int64_t cm_stride, int32_t cp_len, int32_t smooth_win, int32_t sc_delta, double gate_threshold,
+                            ofs_sync_record *records, int64_t *scratch, void *stream)
 {
     if (int rc = check_desc(d, "ofs_sync_detect")) return rc;
     OFS_REQUIRE(d->kind == OFS_SC || d->kind == OFS_SC_BOTH || d->kind == OFS_MINN, "ofs_sync: kind must be SC or MINN");
@@ -148,11 +148,14 @@ OFS_API int ofs_sync_detect(const ofs_metric_desc *d, const void *x, const float
     if (d->n_frames == 0) return OFS_OK;
     ofs_rows rows{M, 0, 0, d->n_frames, out_len, d->out_stride};
     int64_t *timing = scratch;
+    const int toff = d->symbol_len - 1;
     if (d->kind == OFS_MINN) {
-        if (int rc = ofs_find_minn_peak(&rows, smooth_win, gate_threshold, 0, 0, 0, timing, scratch + d->n_frames, nullptr, stream))
+        if (int rc = ofs_find_minn_peak_pruned(&rows, chunk_max, cm_stride, toff, smooth_win, gate_threshold, 0, 0, 0, timing,
+                                               scratch + d->n_frames, nullptr, stream))
             return rc;
     } else {
-        if (int rc = ofs_find_plateau_end(&rows, cp_len, cp_len / 4, smooth_win, timing, stream)) return rc;
+        if (int rc = ofs_find_plateau_end_pruned(&rows, chunk_max, cm_stride, toff, cp_len, cp_len / 4, smooth_win, timing, stream))
+            return rc;
     }
     const int wpb = 4;
     sync_record_kernel<<<(unsigned)((d->n_frames + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
@@ -170,7 +173,7 @@ OFS_API int ofs_sync(const ofs_metric_desc *d, const void *x, float *M, float *c
     OFS_REQUIRE(d->out_f64 == 0, "ofs_sync: float32 metric only");
     if (d->n_frames == 0) return OFS_OK;
     if (int rc = ofs_metric(d, x, M, nullptr, nullptr, chunk_max, cm_stride, stream)) return rc;
-    return ofs_sync_detect(d, x, M, cp_len, smooth_win, sc_delta, gate_threshold, records, scratch, stream);
+    return ofs_sync_detect(d, x, M, chunk_max, cm_stride, cp_len, smooth_win, sc_delta, gate_threshold, records, scratch, stream);
 }
 
 // ---- host-buffer pipeline -------------------------------------------------------------------------

@@ -112,6 +112,24 @@ __device__ __forceinline__ double shfl_up_f64(double v, int delta)
     hi = __shfl_up_sync(0xffffffffu, hi, delta);
     return __hiloint2double(hi, lo);
 }
+// one Kogge-Stone step of a warp inclusive scan: v += (value of lane - delta), predicated by the
+// shuffle's own "source lane in range" output (no ISETP / FSEL)
+__device__ __forceinline__ void scan_step_f64(double &v, int delta)
+{
+    asm volatile(
+        "{\n"
+        ".reg .b32 lo, hi, ylo, yhi;\n"
+        ".reg .pred p;\n"
+        ".reg .f64 y;\n"
+        "mov.b64 {lo, hi}, %0;\n"
+        "shfl.sync.up.b32 ylo|p, lo, %1, 0x0, 0xffffffff;\n"
+        "shfl.sync.up.b32 yhi, hi, %1, 0x0, 0xffffffff;\n"
+        "mov.b64 y, {ylo, yhi};\n"
+        "@p add.f64 %0, %0, y;\n"
+        "}\n"
+        : "+d"(v)
+        : "r"(delta));
+}
 __device__ __forceinline__ double shfl_f64(double v, int src)
 {
     int lo = __double2loint(v), hi = __double2hiint(v);

@@ -79,6 +79,70 @@ __device__ long long block_min_i64(long long x, long long *sh)
     return r;
 }
 
+// ---- arg-max of a windowed function of the metric, pruned by the stripe kernel's chunk maxima ---------
+// chunk c of a row covers the outputs d in [256c - toff, 256c - toff + 256) (256 causal sample times);
+// cm[c] = max(0, max of M over the chunk).  A window function F(i) whose window spans the chunks
+// [c(i) - rad_lo, c(i) + rad_hi] and is an average of (zero-padded, non-negative-clamped) metric values obeys
+// F(i) <= max(cm[c(i)-rad_lo .. c(i)+rad_hi]).  Chunks whose bound is below a value already attained are
+// skipped: the result (first maximum) is exactly the one of the full scan.
+struct Prune {
+    const float *cm;      // nullptr: no pruning
+    int64_t ncm;          // entries in this row of cm
+    int toff, rad_lo, rad_hi;
+    __device__ __forceinline__ float bound(int64_t c) const
+    {
+        float b = 0.f;
+        int64_t lo = c - rad_lo, hi = c + rad_hi;
+        if (lo < 0) lo = 0;
+        if (hi > ncm - 1) hi = ncm - 1;
+        for (int64_t k = lo; k <= hi; ++k) b = fmaxf(b, __ldg(cm + k));
+        return b;
+    }
+};
+
+template <typename F>
+__device__ ArgVal pruned_argmax(const F &fn, int64_t n_out, const Prune &pr, ArgVal *sh_av)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    ArgVal best{0.0, -1};
+    if (pr.cm == nullptr) {
+        for (int64_t i = tid; i < n_out; i += DNT) {
+            const double v = fn(i);
+            if (best.i < 0 || v > best.v) { best.v = v; best.i = i; }
+        }
+        return block_argmax<false>(best, sh_av);
+    }
+    const int64_t nch = (n_out + pr.toff + 255) / 256;
+    // phase 0: the chunk with the largest raw maximum
+    ArgVal bc{0.0, -1};
+    for (int64_t c = tid; c < nch && c < pr.ncm; c += DNT) {
+        const double v = (double)__ldg(pr.cm + c);
+        if (bc.i < 0 || v > bc.v) { bc.v = v; bc.i = c; }
+    }
+    bc = block_argmax<false>(bc, sh_av);
+    // phase 1: exact values over that chunk -> a value v* that the maximum is known to reach
+    ArgVal vs{0.0, -1};
+    {
+        const int64_t i = bc.i * 256 - pr.toff + tid;
+        if (bc.i >= 0 && i >= 0 && i < n_out) { vs.v = fn(i); vs.i = i; }
+    }
+    vs = block_argmax<false>(vs, sh_av);
+    const bool have = vs.i >= 0;
+    // phase 2: every chunk that could still hold the maximum
+    for (int64_t c = warp; c < nch; c += DNT / 32) {
+        if (have && (double)pr.bound(c) < vs.v) continue;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int64_t i = c * 256 - pr.toff + 32 * k + lane;
+            if (i >= 0 && i < n_out) {
+                const double v = fn(i);
+                if (best.i < 0 || v > best.v) { best.v = v; best.i = i; }
+            }
+        }
+    }
+    return block_argmax<false>(best, sh_av);
+}
+
 // ---- S&C plateau end -------------------------------------------------------------------------------
 struct SmoothSame {   // np.convolve(M, ones(w)/w, "same")[i], sc.py:100
     RowView r;
@@ -98,7 +162,7 @@ struct SmoothSame {   // np.convolve(M, ones(w)/w, "same")[i], sc.py:100
 };
 
 __global__ void __launch_bounds__(DNT) plateau_kernel(RowView r, int cp_len, int lookahead, int smooth_win,
-                                                      int64_t *out)
+                                                      int64_t *out, const float *cm, int64_t cm_stride, int toff)
 {
     __shared__ ArgVal sh_av[DNT / 32];
     __shared__ long long sh_i[DNT / 32];
@@ -113,13 +177,9 @@ __global__ void __launch_bounds__(DNT) plateau_kernel(RowView r, int cp_len, int
     Ms.off = (int)(((r.n > w ? (int64_t)w : r.n) - 1) / 2);
     const int64_t ms = Ms.ms;
 
-    // pass A: center = first argmax of the smoothed metric (sc.py:106)
-    ArgVal best{0.0, -1};
-    for (int64_t i = tid; i < ms; i += DNT) {
-        const double v = Ms(i);
-        if (best.i < 0 || v > best.v) { best.v = v; best.i = i; }
-    }
-    best = block_argmax<false>(best, sh_av);
+    // pass A: center = first argmax of the smoothed metric (sc.py:106), pruned by the chunk maxima
+    Prune pr{(cm && r.n > w) ? cm + row * cm_stride : nullptr, cm_stride, toff, (w - 1 - Ms.off + 255) / 256, (Ms.off + 255) / 256};
+    ArgVal best = pruned_argmax(Ms, ms, pr, sh_av);
     const int64_t center = best.i;
     const double peak = best.v;
 
@@ -238,7 +298,8 @@ __device__ void longest_run(const unsigned *mask, int64_t n, long long &bs, long
 
 __global__ void __launch_bounds__(DNT) minn_peak_kernel(RowView r, int smooth_win, double gate_threshold,
                                                         int has_bounds, int64_t b_lo, int64_t b_hi, int64_t *peak,
-                                                        int64_t *gate_span, void *Ms_out)
+                                                        int64_t *gate_span, void *Ms_out, const float *cm,
+                                                        int64_t cm_stride, int toff)
 {
     extern __shared__ unsigned mask[];
     __shared__ ArgVal sh_av[DNT / 32];
@@ -250,30 +311,42 @@ __global__ void __launch_bounds__(DNT) minn_peak_kernel(RowView r, int smooth_wi
     Trailing Ms{r, row, smooth_win > 1 ? smooth_win : 1};
 
     // pass 1: global first-argmax of Ms (also the fallback answer), optional Ms output
-    ArgVal best{0.0, -1};
-    for (int64_t i = tid; i < n; i += DNT) {
-        const double v = Ms(i);
-        if (Ms_out) {
+    const int wv = smooth_win > 1 ? smooth_win : 1;
+    Prune pr{cm ? cm + row * cm_stride : nullptr, cm_stride, toff, (wv - 1 + 255) / 256, 0};
+    if (Ms_out) {
+        for (int64_t i = tid; i < n; i += DNT) {
+            const double v = Ms(i);
             if (r.f64) reinterpret_cast<double *>(Ms_out)[row * r.stride + i] = v;
             else reinterpret_cast<float *>(Ms_out)[row * r.stride + i] = (float)v;
         }
-        if (best.i < 0 || v > best.v) { best.v = v; best.i = i; }
     }
-    best = block_argmax<false>(best, sh_av);
+    ArgVal best = pruned_argmax(Ms, n, pr, sh_av);
     if (!(best.v > 0.0)) { if (tid == 0) { peak[row] = -2; gate_span[2 * row] = gate_span[2 * row + 1] = 0; } return; }
 
-    // pass 2: gate flags -> bitmask -> longest run (minn.py:155-182)
+    // pass 2: gate flags -> bitmask (bit index = causal time t = d + toff, so words align with the chunks)
+    //         -> longest run (minn.py:155-182)
     const double level = gate_threshold * best.v;
-    const int64_t nround = ((n + 31) / 32) * 32;
-    for (int64_t i = tid; i < nround; i += DNT) {
-        const bool f = i < n && Ms(i) >= level;
-        const unsigned m = __ballot_sync(0xffffffffu, f);
-        if (lane == 0) mask[i / 32] = m;
+    const int64_t nch = (n + toff + 255) / 256;
+    for (int64_t c = tid >> 5; c < nch; c += DNT / 32) {
+        if (pr.cm && (double)pr.bound(c) < level) {
+            if (lane < 8) mask[c * 8 + lane] = 0u;
+            continue;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int64_t i = c * 256 - toff + 32 * k + lane;
+            const bool f = i >= 0 && i < n && Ms(i) >= level;
+            const unsigned m = __ballot_sync(0xffffffffu, f);
+            if (lane == 0) mask[c * 8 + k] = m;
+        }
     }
     __syncthreads();
     if (tid == 0) {
         long long bs, be;
-        longest_run(mask, n, bs, be);
+        longest_run(mask, nch * 256, bs, be);
+        bs -= toff; be -= toff;
+        if (bs < 0) bs = 0;
+        if (be < 0) be = 0;
         if (has_bounds) {                                   // minn.py:186-193
             long long s = b_lo > 0 ? b_lo : 0, e = b_hi < n ? b_hi : n;
             if (s >= e) { s = 0; e = n; }
@@ -572,29 +645,50 @@ static size_t mask_bytes(int64_t n) { return (size_t)((n + 31) / 32) * 4 + 16; }
 
 using namespace ofs;
 
-OFS_API int ofs_find_plateau_end(const ofs_rows *M, int32_t cp_len, int32_t lookahead, int32_t smooth_win,
-                                 int64_t *plateau_end, void *stream)
+OFS_API int ofs_find_plateau_end_pruned(const ofs_rows *M, const float *chunk_max, int64_t cm_stride, int32_t toff,
+                                        int32_t cp_len, int32_t lookahead, int32_t smooth_win, int64_t *plateau_end,
+                                        void *stream)
 {
     if (int rc = rows_ok(M, "ofs_find_plateau_end")) return rc;
     OFS_REQUIRE(plateau_end, "ofs_find_plateau_end: null output");
+    OFS_REQUIRE(!chunk_max || (toff >= 0 && cm_stride >= (M->n + toff + 255) / 256), "ofs_find_plateau_end: bad chunk_max geometry");
     if (M->n_rows == 0) return OFS_OK;
-    plateau_kernel<<<(unsigned)M->n_rows, DNT, 0, (cudaStream_t)stream>>>(view(M), cp_len, lookahead, smooth_win, plateau_end);
+    plateau_kernel<<<(unsigned)M->n_rows, DNT, 0, (cudaStream_t)stream>>>(view(M), cp_len, lookahead, smooth_win, plateau_end,
+                                                                         chunk_max, cm_stride, chunk_max ? toff : 0);
     return check_launch("plateau_kernel");
+}
+
+OFS_API int ofs_find_plateau_end(const ofs_rows *M, int32_t cp_len, int32_t lookahead, int32_t smooth_win,
+                                 int64_t *plateau_end, void *stream)
+{
+    return ofs_find_plateau_end_pruned(M, nullptr, 0, 0, cp_len, lookahead, smooth_win, plateau_end, stream);
+}
+
+OFS_API int ofs_find_minn_peak_pruned(const ofs_rows *M, const float *chunk_max, int64_t cm_stride, int32_t toff,
+                                      int32_t smooth_win, double gate_threshold, int32_t has_bounds, int64_t bound_lo,
+                                      int64_t bound_hi, int64_t *peak, int64_t *gate_span, void *Ms, void *stream)
+{
+    if (int rc = rows_ok(M, "ofs_find_minn_peak")) return rc;
+    OFS_REQUIRE(peak && gate_span, "ofs_find_minn_peak: null output");
+    if (!chunk_max) toff = 0;
+    OFS_REQUIRE(toff >= 0 && M->n + toff <= MASK_MAX_N, "ofs_find_minn_peak: rows longer than %lld unsupported",
+                (long long)MASK_MAX_N);
+    OFS_REQUIRE(!chunk_max || cm_stride >= (M->n + toff + 255) / 256, "ofs_find_minn_peak: bad chunk_max geometry");
+    if (M->n_rows == 0) return OFS_OK;
+    const size_t sm = mask_bytes(((M->n + toff + 255) / 256) * 256);
+    if (int rc = set_mask_smem(minn_peak_kernel, sm)) return rc;
+    minn_peak_kernel<<<(unsigned)M->n_rows, DNT, sm, (cudaStream_t)stream>>>(view(M), smooth_win, gate_threshold, has_bounds,
+                                                                            bound_lo, bound_hi, peak, gate_span, Ms, chunk_max,
+                                                                            cm_stride, toff);
+    return check_launch("minn_peak_kernel");
 }
 
 OFS_API int ofs_find_minn_peak(const ofs_rows *M, int32_t smooth_win, double gate_threshold, int32_t has_bounds,
                                int64_t bound_lo, int64_t bound_hi, int64_t *peak, int64_t *gate_span, void *Ms,
                                void *stream)
 {
-    if (int rc = rows_ok(M, "ofs_find_minn_peak")) return rc;
-    OFS_REQUIRE(peak && gate_span, "ofs_find_minn_peak: null output");
-    OFS_REQUIRE(M->n <= MASK_MAX_N, "ofs_find_minn_peak: rows longer than %lld unsupported", (long long)MASK_MAX_N);
-    if (M->n_rows == 0) return OFS_OK;
-    const size_t sm = mask_bytes(M->n);
-    if (int rc = set_mask_smem(minn_peak_kernel, sm)) return rc;
-    minn_peak_kernel<<<(unsigned)M->n_rows, DNT, sm, (cudaStream_t)stream>>>(view(M), smooth_win, gate_threshold, has_bounds,
-                                                                            bound_lo, bound_hi, peak, gate_span, Ms);
-    return check_launch("minn_peak_kernel");
+    return ofs_find_minn_peak_pruned(M, nullptr, 0, 0, smooth_win, gate_threshold, has_bounds, bound_lo, bound_hi, peak,
+                                     gate_span, Ms, stream);
 }
 
 OFS_API int ofs_sc_gate(const ofs_rows *Msc, double threshold, uint8_t *gate, int64_t gate_stride, void *stream)

@@ -23,6 +23,7 @@
 // Outputs live in causal time t (newest sample of the window): output index d = t - toff, so the
 // caller passes M pointing at d = 0 and vector stores need (M - toff) to be 16-byte aligned.
 #include "common.cuh"
+#include <type_traits>
 
 namespace ofs {
 
@@ -98,9 +99,24 @@ __device__ __forceinline__ float2 load1_smem<OFS_IQ16>(const unsigned char *stag
     return make_float2((float)s.x, (float)s.y);
 }
 
+// Per-block state of one thread; two copies ping-pong (cur / prev) so that no history is ever copied.
+struct BlkState {
+    float2 x[SK];                     // the thread's 8 samples
+    float sqr[SK], sqi[SK], se[SK];   // thread-local inclusive prefixes of the lag product / energy
+    double Er, Ei;                    // warp-exclusive offsets of the product prefixes (fp64)
+    float Ee;                         // warp-exclusive offset of the energy prefix (fp32: positive sums, no cancellation)
+};
+
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // KIND: OFS_SC / OFS_SC_BOTH / OFS_MINN / OFS_AA.   WARPS: D = WARPS*256.
 template <int WARPS, int KIND, int DT>
-__global__ void __launch_bounds__(WARPS * 32, ((KIND == OFS_MINN ? 384 : 512) / (WARPS * 32)))
+__global__ void __launch_bounds__(WARPS * 32, (((KIND == OFS_MINN || KIND == OFS_SC_BOTH) ? 384 : 512) / (WARPS * 32)))
 metric_stripe_kernel(StripeParams p)
 {
     constexpr int BK = WARPS * SCH;
@@ -110,7 +126,7 @@ metric_stripe_kernel(StripeParams p)
     constexpr bool H1 = (KIND == OFS_SC_BOTH || KIND == OFS_MINN);               // window history depth >= 1
     constexpr bool H2 = (KIND == OFS_MINN);
 
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *stages = smem;                                              // SSTAGES * STAGE_BYTES
     float *ost = reinterpret_cast<float *>(smem + SSTAGES * STAGE_BYTES);      // WARPS * 2 * SCH floats
     double *tot = reinterpret_cast<double *>(ost + WARPS * 2 * SCH);           // 3 * WARPS * 4 doubles
@@ -123,6 +139,12 @@ metric_stripe_kernel(StripeParams p)
         mbar_fence_init();
     }
     __syncthreads();
+
+    // Kogge-Stone masks: 1.0 where the lane takes its neighbour's partial sum (lane >= 1,2,4,8,16)
+    double mk[5];
+    float mkf[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) { mk[q] = lane >= (1 << q) ? 1.0 : 0.0; mkf[q] = lane >= (1 << q) ? 1.f : 0.f; }
 
     const int64_t total_work = p.n_frames * (int64_t)p.stripes_per_frame;
     uint32_t git = 0;                      // global block counter of this CTA (stage slot, tot slot)
@@ -141,29 +163,35 @@ metric_stripe_kernel(StripeParams p)
         const unsigned char *xrow = reinterpret_cast<const unsigned char *>(p.x) + (size_t)frame * p.xfs * ESZ;
         float *Mrow_t = p.M ? p.M + frame * p.out_stride - p.toff : nullptr;    // indexed by causal t
         const bool m_vec_ok = p.M && ((reinterpret_cast<uintptr_t>(Mrow_t) & 15) == 0);
+        // first causal time whose output exists and is fully valid (AA: the window must be full, t >= L)
+        const int64_t tlo = max(t0, (int64_t)(KIND == OFS_AA ? p.aa_L : p.toff));
+        // blocks [i_fast0, i_fast1) are "steady state": fully inside [tlo, t1), loaded by one full bulk copy,
+        // stored with aligned vector / bulk stores -> branch-free fast path
+        int i_fast0 = (int)((tlo - tb + BK - 1) / BK), i_fast1 = (int)((t1 - tb) / BK);
+        if (!p.use_tma || (p.M && !m_vec_ok)) i_fast1 = 0;
+        float *cm_row = p.chunk_max ? p.chunk_max + frame * p.cm_stride : nullptr;
 
         // ---- reset per-stripe state (history = zeros: x[t<0] = 0) -----------------------------
         if (tid < 3 * WARPS * 4) tot[tid] = 0.0;
         __syncthreads();
 
-        float2 xh[SK];
-        float sqr_h[SK], sqi_h[SK], se_h[SK];      // previous block: thread-local prefixes
-        double Er_h = 0.0, Ei_h = 0.0, Ee_h = 0.0;  // previous block: warp-exclusive offsets
+        BlkState sA, sB;
         float wqr1[SK], wqi1[SK], we1[SK], wqr2[SK], wqi2[SK], we2[SK];   // window history t-D, t-2D
 #pragma unroll
         for (int j = 0; j < SK; ++j) {
-            xh[j] = make_float2(0.f, 0.f);
-            sqr_h[j] = sqi_h[j] = se_h[j] = 0.f;
+            sA.x[j] = sB.x[j] = make_float2(0.f, 0.f);
+            sA.sqr[j] = sA.sqi[j] = sA.se[j] = sB.sqr[j] = sB.sqi[j] = sB.se[j] = 0.f;
             wqr1[j] = wqi1[j] = we1[j] = wqr2[j] = wqi2[j] = we2[j] = 0.f;
         }
+        sA.Er = sA.Ei = sB.Er = sB.Ei = 0.0;
+        sA.Ee = sB.Ee = 0.f;
 
-        auto valid_samples = [&](int i) -> int {      // samples of block i that exist in the frame
-            const int64_t rem = p.L - (tb + (int64_t)i * BK);
-            return (int)(rem < BK ? rem : BK);
-        };
+        const int rem0 = (int)min(p.L - tb, (int64_t)0x7fffffff);      // samples from tb to the end of the frame
         auto tma_samples = [&](int i) -> int {        // prefix of block i brought by the bulk copy
             if (!p.use_tma) return 0;
-            return (int)((((size_t)valid_samples(i) * ESZ) & ~(size_t)15) / ESZ);
+            const int rem = rem0 - i * BK;
+            const int valid = rem < BK ? rem : BK;
+            return (int)((((unsigned)valid * ESZ) & ~15u) / ESZ);
         };
         auto issue = [&](int i) {
             const int ns = tma_samples(i);
@@ -179,59 +207,66 @@ metric_stripe_kernel(StripeParams p)
             for (int i = 0; i < SSTAGES && i < nblk; ++i) issue(i);
         }
 
-        for (int i = 0; i < nblk; ++i) {
+        // One block: `cur` is filled, `prev` is the same thread's state one block (= D samples) earlier.
+        // FAST (compile-time) = steady-state block: no edge handling anywhere.
+        auto block = [&](auto fast_tag, int i, BlkState &cur, const BlkState &prev) {
+            constexpr bool FAST = decltype(fast_tag)::value;
             const uint32_t g = git + (uint32_t)i;
             const int st = g % SSTAGES;
             const unsigned char *stage = stages + (size_t)st * STAGE_BYTES;
             const int64_t blkpos = tb + (int64_t)i * BK;
-            const int ns_tma = tma_samples(i);
-            if (ns_tma > 0) {
+            // ---- wait for the bulk copy, load this thread's 8 samples --------------------------
+            if (FAST) {
                 mbar_wait(&bars[st], (phase_bits >> st) & 1u);
                 phase_bits ^= 1u << st;
-            }
-
-            // ---- load this thread's 8 samples -------------------------------------------------
-            float2 xc[SK];
-            if (myoff + SK <= ns_tma) {
-                load8_smem<DT>(stage, myoff, xc);
+                load8_smem<DT>(stage, myoff, cur.x);
             } else {
+                const int ns_tma = tma_samples(i);
+                if (ns_tma > 0) {
+                    mbar_wait(&bars[st], (phase_bits >> st) & 1u);
+                    phase_bits ^= 1u << st;
+                }
+                if (myoff + SK <= ns_tma) {
+                    load8_smem<DT>(stage, myoff, cur.x);
+                } else {
 #pragma unroll
-                for (int j = 0; j < SK; ++j) {
-                    const int idx = myoff + j;
-                    if (idx < ns_tma) xc[j] = load1_smem<DT>(stage, idx);
-                    else if (blkpos + idx < p.L) xc[j] = load1_gmem<DT>(xrow, blkpos + idx);
-                    else xc[j] = make_float2(0.f, 0.f);
+                    for (int j = 0; j < SK; ++j) {
+                        const int idx = myoff + j;
+                        if (idx < ns_tma) cur.x[j] = load1_smem<DT>(stage, idx);
+                        else if (blkpos + idx < p.L) cur.x[j] = load1_gmem<DT>(xrow, blkpos + idx);
+                        else cur.x[j] = make_float2(0.f, 0.f);
+                    }
                 }
             }
-
-            // ---- lag products, energies, thread-local inclusive prefixes (fp32) -----------------
-            float sqr[SK], sqi[SK], se[SK];
+            // ---- lag products q = x[t-D] conj(x[t]), energies, thread-local inclusive prefixes (fp32) ----
 #pragma unroll
             for (int j = 0; j < SK; ++j) {
-                // q = x[t-D] * conj(x[t])
-                sqr[j] = fmaf(xh[j].x, xc[j].x, xh[j].y * xc[j].y);
-                sqi[j] = fmaf(xh[j].y, xc[j].x, -(xh[j].x * xc[j].y));
-                se[j] = fmaf(xc[j].x, xc[j].x, xc[j].y * xc[j].y);
+                cur.sqr[j] = fmaf(prev.x[j].x, cur.x[j].x, prev.x[j].y * cur.x[j].y);
+                cur.sqi[j] = fmaf(prev.x[j].y, cur.x[j].x, -(prev.x[j].x * cur.x[j].y));
+                cur.se[j] = fmaf(cur.x[j].x, cur.x[j].x, cur.x[j].y * cur.x[j].y);
             }
 #pragma unroll
             for (int j = 1; j < SK; ++j) {
-                sqr[j] += sqr[j - 1];
-                sqi[j] += sqi[j - 1];
-                se[j] += se[j - 1];
+                cur.sqr[j] += cur.sqr[j - 1];
+                cur.sqi[j] += cur.sqi[j - 1];
+                cur.se[j] += cur.se[j - 1];
             }
-            // ---- warp inclusive scan of the thread totals, fp64 ---------------------------------
-            const double ownr = (double)sqr[SK - 1], owni = (double)sqi[SK - 1], owne = (double)se[SK - 1];
-            double tr = ownr, ti = owni, te = owne;
+            // ---- warp inclusive scan of the thread totals: products in fp64, energy in fp32 -----------
+            const double ownr = (double)cur.sqr[SK - 1], owni = (double)cur.sqi[SK - 1];
+            double tr = ownr, ti = owni;
+            float te = cur.se[SK - 1];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const double yr = shfl_up_f64(tr, o), yi = shfl_up_f64(ti, o), ye = shfl_up_f64(te, o);
-                if (lane >= o) { tr += yr; ti += yi; te += ye; }
+            for (int q = 0; q < 5; ++q) {
+                tr = fma(shfl_up_f64(tr, 1 << q), mk[q], tr);
+                ti = fma(shfl_up_f64(ti, 1 << q), mk[q], ti);
+                te = fmaf(__shfl_up_sync(0xffffffffu, te, 1 << q), mkf[q], te);
             }
-            const double Er = tr - ownr, Ei = ti - owni, Ee = te - owne;   // exclusive lane offsets
+            cur.Er = tr - ownr; cur.Ei = ti - owni; cur.Ee = te - cur.se[SK - 1];   // exclusive lane offsets
             const int tb_cur = (int)(g % 3u), tb_prev = (int)((g + 2u) % 3u);
             if (lane == 31) {
                 double *t = tot + (tb_cur * WARPS + warp) * 4;
-                t[0] = tr; t[1] = ti; t[2] = te;
+                *reinterpret_cast<double2 *>(t) = make_double2(tr, ti);
+                t[2] = (double)te;
             }
             __syncthreads();
             // stage `st` has been read by every warp: refill it with block i + SSTAGES
@@ -242,87 +277,102 @@ metric_stripe_kernel(StripeParams p)
 #pragma unroll
             for (int w = 0; w < WARPS; ++w) {
                 const double *t = tot + (((w < warp) ? tb_cur : tb_prev) * WARPS + w) * 4;
-                Gr += t[0]; Gi += t[1]; Ge += t[2];
+                const double2 ri = *reinterpret_cast<const double2 *>(t);
+                Gr += ri.x; Gi += ri.y; Ge += t[2];
             }
-            const float br = (float)(Gr + (Er - Er_h));
-            const float bi = (float)(Gi + (Ei - Ei_h));
-            const float be = (float)(Ge + (Ee - Ee_h));
+            const float br = (float)(Gr + (cur.Er - prev.Er));
+            const float bi = (float)(Gi + (cur.Ei - prev.Ei));
+            const float be = (float)Ge + (cur.Ee - prev.Ee);
 
             // ---- windows, metric --------------------------------------------------------------
-            const bool emit = blkpos >= t0;       // warm-up blocks produce no output
             float Mv[SK];
-            float cmax = 0.f;
-            const int64_t tpos = blkpos + myoff;
 #pragma unroll
             for (int j = 0; j < SK; ++j) {
-                const float wqr = br + (sqr[j] - sqr_h[j]);
-                const float wqi = bi + (sqi[j] - sqi_h[j]);
-                const float we = be + (se[j] - se_h[j]);
+                const float wqr = br + (cur.sqr[j] - prev.sqr[j]);
+                const float wqi = bi + (cur.sqi[j] - prev.sqi[j]);
+                const float we = be + (cur.se[j] - prev.se[j]);
                 float Pr, Pi, Rv;
                 if (KIND == OFS_MINN) { Pr = wqr + wqr2[j]; Pi = wqi + wqi2[j]; Rv = we + we1[j] + we2[j]; }
                 else if (KIND == OFS_SC_BOTH) { Pr = wqr; Pi = wqi; Rv = we + we1[j]; }
                 else { Pr = wqr; Pi = wqi; Rv = we; }
-                float m;
                 if (KIND == OFS_AA) {
-                    m = 0.f;
-                    if (tpos + j >= p.aa_L && Rv > p.aa_floor) {
-                        m = fmaf(Pr, Pr, Pi * Pi) / (Rv * Rv);
-                        m = fminf(m, 1.f);
-                    }
+                    const float r = rcp_approx(Rv);
+                    const float q = fmaf(Pr, Pr, Pi * Pi) * (r * r);
+                    Mv[j] = Rv > p.aa_floor ? fminf(q, 1.f) : 0.f;
                 } else {
-                    const float rr = fmaxf(Rv, 1e-12f);
-                    const float num = (KIND == OFS_MINN) ? fmaxf(Pr, 0.f) * fmaxf(Pr, 0.f) : fmaf(Pr, Pr, Pi * Pi);
-                    m = num / (rr * rr);
+                    const float r = rcp_approx(fmaxf(Rv, 1e-12f));
+                    const float pp = fmaxf(Pr, 0.f);
+                    const float num = (KIND == OFS_MINN) ? pp * pp : fmaf(Pr, Pr, Pi * Pi);
+                    Mv[j] = num * (r * r);
                 }
-                const int64_t t = tpos + j;
-                const bool ok = emit && t >= p.toff && t < p.L;
-                Mv[j] = ok ? m : 0.f;
-                cmax = fmaxf(cmax, Mv[j]);
                 if (H2) { wqr2[j] = wqr1[j]; wqi2[j] = wqi1[j]; we2[j] = we1[j]; }
                 if (H1) { wqr1[j] = wqr; wqi1[j] = wqi; we1[j] = we; }
-                sqr_h[j] = sqr[j]; sqi_h[j] = sqi[j]; se_h[j] = se[j];
-                xh[j] = xc[j];
             }
-            Er_h = Er; Ei_h = Ei; Ee_h = Ee;
-
-            if (emit) {
-                // ---- per-chunk maximum for the detectors ------------------------------------------
-                if (p.chunk_max && blkpos + warp * SCH < p.L) {
+            const int64_t wpos = blkpos + warp * SCH;        // this warp's chunk
+            if (!FAST) {
+                if (blkpos < t0) return;                     // warm-up blocks produce no output
+                // edge block: mask outputs that do not exist (t < toff, t >= L) or are not yet valid (AA: t < L)
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
-                    if (lane == 0) p.chunk_max[frame * p.cm_stride + (blkpos + warp * SCH) / SCH] = cmax;
+                for (int j = 0; j < SK; ++j) {
+                    const int64_t t = blkpos + myoff + j;
+                    const bool ok = t >= p.toff && t < p.L && (KIND != OFS_AA || t >= p.aa_L);
+                    Mv[j] = ok ? Mv[j] : 0.f;
                 }
-                // ---- store M ----------------------------------------------------------------------
-                if (p.M) {
-                    const int64_t wpos = blkpos + warp * SCH;
-                    const bool full = m_vec_ok && wpos >= p.toff && wpos + SCH <= t1;
-                    if (full && p.store_mode == 1) {
-                        float *buf = my_ost + (i & 1) * SCH;
-                        if (lane == 0) tma_store_wait_read<1>();   // the store that used this buffer is done
-                        __syncwarp();
-                        float4 *b4 = reinterpret_cast<float4 *>(buf + lane * SK);
-                        b4[0] = make_float4(Mv[0], Mv[1], Mv[2], Mv[3]);
-                        b4[1] = make_float4(Mv[4], Mv[5], Mv[6], Mv[7]);
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) {
-                            tma_store_1d(Mrow_t + wpos, buf, SCH * sizeof(float));
-                            tma_store_commit();
-                        }
-                    } else if (full) {
-                        float4 *g4 = reinterpret_cast<float4 *>(Mrow_t + tpos);
-                        g4[0] = make_float4(Mv[0], Mv[1], Mv[2], Mv[3]);
-                        g4[1] = make_float4(Mv[4], Mv[5], Mv[6], Mv[7]);
-                    } else {
+            }
+            // ---- per-chunk maximum for the detectors ------------------------------------------------
+            if (cm_row && (FAST || wpos < p.L)) {
+                float cmax = fmaxf(fmaxf(fmaxf(Mv[0], Mv[1]), fmaxf(Mv[2], Mv[3])), fmaxf(fmaxf(Mv[4], Mv[5]), fmaxf(Mv[6], Mv[7])));
+                cmax = fmaxf(cmax, 0.f);
+                // non-negative floats order like their bit patterns: one REDUX instead of a 5-step shuffle tree
+                const unsigned cbits = __reduce_max_sync(0xffffffffu, __float_as_uint(cmax));
+                if (lane == 0) cm_row[wpos >> 8] = __uint_as_float(cbits);
+            }
+            // ---- store M ------------------------------------------------------------------------------
+            if (p.M) {
+                const bool full = FAST || (m_vec_ok && wpos >= p.toff && wpos + SCH <= t1);
+                if (full && p.store_mode == 1) {
+                    float *buf = my_ost + (i & 1) * SCH;
+                    if (lane == 0) tma_store_wait_read<1>();   // the store that used this buffer is done
+                    __syncwarp();
+                    float4 *b4 = reinterpret_cast<float4 *>(buf + lane * SK);
+                    b4[0] = make_float4(Mv[0], Mv[1], Mv[2], Mv[3]);
+                    b4[1] = make_float4(Mv[4], Mv[5], Mv[6], Mv[7]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_1d(Mrow_t + wpos, buf, SCH * sizeof(float));
+                        tma_store_commit();
+                    }
+                } else if (full) {
+                    float4 *g4 = reinterpret_cast<float4 *>(Mrow_t + wpos + lane * SK);
+                    g4[0] = make_float4(Mv[0], Mv[1], Mv[2], Mv[3]);
+                    g4[1] = make_float4(Mv[4], Mv[5], Mv[6], Mv[7]);
+                } else {
 #pragma unroll
-                        for (int j = 0; j < SK; ++j) {
-                            const int64_t t = tpos + j;
-                            if (t >= p.toff && t < t1) Mrow_t[t] = Mv[j];
-                        }
+                    for (int j = 0; j < SK; ++j) {
+                        const int64_t t = blkpos + myoff + j;
+                        if (t >= p.toff && t < t1) Mrow_t[t] = Mv[j];
                     }
                 }
             }
+        };
+
+        using FastT = std::true_type;
+        using SlowT = std::false_type;
+        int i = 0;
+        // head (warm-up / partial) blocks, one at a time, alternating the two states
+        bool flip = false;
+        auto step_slow = [&](int ii) { if (!flip) block(SlowT{}, ii, sA, sB); else block(SlowT{}, ii, sB, sA); flip = !flip; };
+        for (; i < nblk && i < i_fast0; ++i) step_slow(i);
+        if (i_fast1 > i) {
+            if (flip) { block(FastT{}, i, sB, sA); flip = false; ++i; }      // realign so that the pair loop starts with sA
+            for (; i + 1 < i_fast1; i += 2) {
+                block(FastT{}, i, sA, sB);
+                block(FastT{}, i + 1, sB, sA);
+            }
+            if (i < i_fast1) { block(FastT{}, i, sA, sB); flip = true; ++i; }
         }
+        for (; i < nblk; ++i) step_slow(i);
         git += (uint32_t)nblk;
         // all bulk stores must have read their staging buffers before the next stripe reuses them
         if (lane == 0) tma_store_wait_read<0>();

@@ -74,7 +74,7 @@ def metric_out_len(kind: str, symbol_len: int, n: int) -> int:
 
 
 def metric(rx, kind: str, symbol_len: int, *, want_pr: bool = True, out_f64: bool | None = None,
-           path: str = "auto", store_mode: int = 1, want_chunk_max: bool = False) -> MetricOut:
+           path: str = "auto", store_mode: int = 0, want_chunk_max: bool = False) -> MetricOut:
     """Timing metric M (+P, R) of sc.py:42-78 / combined_sc_min.py:116-164 / minn.py:59-112,697-751 /
     sync_aa.py:458-493 for a batch of frames."""
     x, code, _ = to_device(rx)
@@ -134,17 +134,19 @@ def _rows(M: torch.Tensor) -> tuple[L.Rows, torch.Tensor]:
     return L.Rows(C.c_void_p(M.data_ptr()), int(M.dtype == torch.float64), 0, M.shape[0], M.shape[1], M.stride(0) if M.shape[0] > 1 else max(M.shape[1], M.stride(0))), M
 
 
-def find_plateau_end(M: torch.Tensor, cp_len: int, lookahead: int | None = None, smooth_win: int = 8) -> torch.Tensor:
-    """sc.py:81-146 for every row -> int64[rows]."""
+def find_plateau_end(M: torch.Tensor, cp_len: int, lookahead: int | None = None, smooth_win: int = 8,
+                     chunk_max: torch.Tensor | None = None, toff: int = 0) -> torch.Tensor:
+    """sc.py:81-146 for every row -> int64[rows].  chunk_max/toff (from the stripe metric) prune the argmax pass."""
     rows, M = _rows(M)
     out = torch.zeros(M.shape[0], dtype=torch.int64, device=M.device)
-    L.check(L.lib().ofs_find_plateau_end(C.byref(rows), int(cp_len), -1 if lookahead is None else int(max(1, lookahead)),
-                                         int(smooth_win), _ptr(out), _stream()), "ofs_find_plateau_end")
+    L.check(L.lib().ofs_find_plateau_end_pruned(C.byref(rows), _ptr(chunk_max), C.c_int64(0 if chunk_max is None else chunk_max.stride(0)),
+                                                int(toff), int(cp_len), -1 if lookahead is None else int(max(1, lookahead)),
+                                                int(smooth_win), _ptr(out), _stream()), "ofs_find_plateau_end")
     return out
 
 
 def find_minn_peak(M: torch.Tensor, smooth_win: int = 8, gate_threshold: float = 0.5, search_bounds=None,
-                   want_ms: bool = False):
+                   want_ms: bool = False, chunk_max: torch.Tensor | None = None, toff: int = 0):
     """minn.py:131-205 for every row -> (peak int64[rows], gate_span int64[rows,2], Ms or None)."""
     rows, M = _rows(M)
     if want_ms and not M.is_contiguous():
@@ -154,8 +156,9 @@ def find_minn_peak(M: torch.Tensor, smooth_win: int = 8, gate_threshold: float =
     Ms = torch.empty(M.shape, dtype=M.dtype, device=M.device) if want_ms else None
     hb = search_bounds is not None
     lo, hi = (int(search_bounds[0]), int(search_bounds[1])) if hb else (0, 0)
-    L.check(L.lib().ofs_find_minn_peak(C.byref(rows), int(smooth_win), C.c_double(gate_threshold), int(hb), C.c_int64(lo),
-                                       C.c_int64(hi), _ptr(peak), _ptr(span), _ptr(Ms), _stream()), "ofs_find_minn_peak")
+    L.check(L.lib().ofs_find_minn_peak_pruned(C.byref(rows), _ptr(chunk_max), C.c_int64(0 if chunk_max is None else chunk_max.stride(0)),
+                                              int(toff), int(smooth_win), C.c_double(gate_threshold), int(hb), C.c_int64(lo),
+                                              C.c_int64(hi), _ptr(peak), _ptr(span), _ptr(Ms), _stream()), "ofs_find_minn_peak")
     return peak, span, Ms
 
 
@@ -283,7 +286,7 @@ class SyncPlan:
     """Pre-allocated buffers for repeated ofs_sync calls on device-resident frames [F, L] complex64/int16-IQ."""
 
     def __init__(self, n_frames: int, n_samples: int, kind: str = "sc", symbol_len: int = 2048, in_dtype: str = "c64",
-                 cp_len: int = 512, smooth_win: int = 16, sc_delta: int = 16, gate_threshold: float = 0.5, store_mode: int = 1):
+                 cp_len: int = 512, smooth_win: int = 16, sc_delta: int = 16, gate_threshold: float = 0.5, store_mode: int = 0):
         dev = _device()
         self.F, self.n, self.kind, self.N = n_frames, n_samples, kind, symbol_len
         self.code = {"c64": L.OFS_C64, "iq16": L.OFS_IQ16}[in_dtype]
@@ -312,7 +315,8 @@ class SyncPlan:
         return self.rec.cpu().numpy().view(_REC_NP).reshape(-1)
 
     def run_detect_only(self, x: torch.Tensor) -> None:
-        L.check(L.lib().ofs_sync_detect(C.byref(self.desc), _ptr(x), C.c_void_p(self.M.data_ptr()), int(self.cp_len),
+        L.check(L.lib().ofs_sync_detect(C.byref(self.desc), _ptr(x), C.c_void_p(self.M.data_ptr()), _ptr(self.cm),
+                                        C.c_int64(self.cm_stride), int(self.cp_len),
                                         int(self.smooth_win), int(self.sc_delta), C.c_double(self.gate_threshold), _ptr(self.rec),
                                         _ptr(self.scratch), _stream()), "ofs_sync_detect")
 

@@ -140,6 +140,27 @@ def test_batched_detectors_vs_oracle():
     assert pg.tolist() == [orc.find_minn_peak_gated(Mmh[f], 16, gh[f]) for f in range(xm.shape[0])]
 
 
+def test_pruned_detectors_equal_unpruned():
+    """chunk-max pruning must not change any answer (plateau end, Minn peak / gate span)."""
+    from ofdm_sync_math_b200 import engine
+    x = _captures(6, 70000, "sc", seed=11)
+    r = engine.metric(_dev(x), "sc", 2048, want_pr=False, path="stripe", want_chunk_max=True)
+    a = engine.find_plateau_end(r.M, 512, 128, 16)
+    b = engine.find_plateau_end(r.M, 512, 128, 16, chunk_max=r.chunk_max, toff=2047)
+    assert a.tolist() == b.tolist()
+    Mh = r.M.cpu().numpy().astype(np.float64)
+    assert a.tolist() == [orc.find_plateau_end_from_metric(m, 512, 128, 16) for m in Mh]
+    xm = _captures(6, 70000, "minn", seed=12)
+    rm = engine.metric(_dev(xm), "minn", 2048, want_pr=False, path="stripe", want_chunk_max=True)
+    for thr in (0.5, 0.05, 0.9):
+        p0, s0, _ = engine.find_minn_peak(rm.M, 16, thr)
+        p1, s1, _ = engine.find_minn_peak(rm.M, 16, thr, chunk_max=rm.chunk_max, toff=2047)
+        assert p0.tolist() == p1.tolist() and s0.tolist() == s1.tolist()
+    Mmh = rm.M.cpu().numpy().astype(np.float64)
+    p1, s1, _ = engine.find_minn_peak(rm.M, 16, 0.5, chunk_max=rm.chunk_max, toff=2047)
+    assert p1.tolist() == [orc.find_minn_peak(m, 16, 0.5)[0] for m in Mmh]
+
+
 def test_fsm_random_flags_vs_oracle():
     """Gate / hysteresis FSMs on adversarial random flag patterns (dense runs, gaps around the hysteresis)."""
     from ofdm_sync_math_b200 import engine

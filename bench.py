@@ -144,6 +144,7 @@ def main() -> None:
     ap.add_argument("--samples", type=int, default=262144)
     ap.add_argument("--e2e-frames", type=int, default=1024, help="frames per GPU pushed through ofs_sync_host per e2e step")
     ap.add_argument("--store-mode", type=int, default=0)
+    ap.add_argument("--tma-mode", type=int, default=2, help="2: tiled tensor-map copies with 128B swizzle, 1: 1-D bulk copies")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -166,7 +167,7 @@ def main() -> None:
 
     F, n = args.frames, args.samples
     x = synth.make_batch_device(F, n, "sc", seed=1234 + rank, device=dev)
-    plan = engine.SyncPlan(F, n, "sc", N_FFT, "c64", cp_len=CP_LEN, smooth_win=SMOOTH, sc_delta=SC_DELTA, store_mode=args.store_mode)
+    plan = engine.SyncPlan(F, n, "sc", N_FFT, "c64", cp_len=CP_LEN, smooth_win=SMOOTH, sc_delta=SC_DELTA, store_mode=args.store_mode, tma_mode=args.tma_mode)
     gather = odist.RecordGatherer(plan.rec) if world > 1 else None
 
     def step():
@@ -283,7 +284,7 @@ def main() -> None:
             "data": "synthetic",
             "config": {"workload": workload_name(args), "frames_per_gpu": F, "samples_per_frame": n, "n_fft": N_FFT,
                        "l2": f"inputs larger than L2 ({F * n * 8 / 1e9:.2f} GB of samples per GPU, no flush needed)",
-                       "store_mode": args.store_mode, "parallelism": f"frames sharded over {world} GPU(s), no sample-path collective"},
+                       "store_mode": args.store_mode, "tma_mode": args.tma_mode, "parallelism": f"frames sharded over {world} GPU(s), no sample-path collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }))
     if world > 1:

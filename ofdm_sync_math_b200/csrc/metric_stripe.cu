@@ -24,11 +24,16 @@
 // caller passes M pointing at d = 0 and vector stores need (M - toff) to be 16-byte aligned.
 #include "common.cuh"
 #include <type_traits>
+#include <cuda.h>
+#include <string.h>   // CUtensorMap + cuTensorMapEncodeTiled prototype (resolved at run time, no -lcuda)
 
 namespace ofs {
 
 constexpr int SK = 8;            // samples per thread per block
 constexpr int SCH = 32 * SK;     // samples per warp per block (chunk)
+#ifndef OFS_STRIPE_THREADS
+#define OFS_STRIPE_THREADS 512
+#endif
 constexpr int SSTAGES = 4;
 
 struct StripeParams {
@@ -40,9 +45,10 @@ struct StripeParams {
     int64_t n_frames;
     int stripes_per_frame;
     int toff;                 // output index = t - toff
-    int use_tma, store_mode;
+    int use_tma, store_mode;  // use_tma: 0 plain loads, 1 1-D bulk copies, 2 tiled tensor-map copies (128B swizzle)
     int aa_L;
     float aa_floor;
+    int tma_mode_wanted;      // 1: 1-D bulk copies only; 2: prefer tiled tensor-map copies
 };
 
 template <int DT>
@@ -70,6 +76,49 @@ __device__ __forceinline__ void load8_smem<OFS_IQ16>(const unsigned char *stage,
         for (int k = 0; k < 4; ++k)
             v[4 * i + k] = make_float2((float)(short)(w[k] & 0xffff), (float)(short)(w[k] >> 16));
     }
+}
+
+// 128-byte-swizzled stage (tensor-map TMA, CU_TENSOR_MAP_SWIZZLE_128B): the 16-byte chunk c of 128-byte row r
+// lives at chunk (c ^ (r & 7)).  A thread's 64 contiguous bytes (c64) are 4 chunks of one row: the four
+// LDS.128 of a quarter-warp then hit 8 distinct chunk columns x 4 row groups -> conflict-free.
+template <int DT>
+__device__ __forceinline__ void load8_smem_swz(const unsigned char *stage, int idx0, float2 (&v)[SK]);
+template <>
+__device__ __forceinline__ void load8_smem_swz<OFS_C64>(const unsigned char *stage, int idx0, float2 (&v)[SK])
+{
+    const unsigned o = (unsigned)idx0 * 8u;
+    const unsigned row = o >> 7, c0 = (o >> 4) & 7u, sw = row & 7u;
+    const unsigned char *rb = stage + (row << 7);
+#pragma unroll
+    for (int i = 0; i < SK / 2; ++i) {
+        const float4 a = *reinterpret_cast<const float4 *>(rb + (((c0 + i) ^ sw) << 4));
+        v[2 * i] = make_float2(a.x, a.y);
+        v[2 * i + 1] = make_float2(a.z, a.w);
+    }
+}
+template <>
+__device__ __forceinline__ void load8_smem_swz<OFS_IQ16>(const unsigned char *stage, int idx0, float2 (&v)[SK])
+{
+    const unsigned o = (unsigned)idx0 * 4u;
+    const unsigned row = o >> 7, c0 = (o >> 4) & 7u, sw = row & 7u;
+    const unsigned char *rb = stage + (row << 7);
+#pragma unroll
+    for (int i = 0; i < SK / 4; ++i) {
+        const int4 a = *reinterpret_cast<const int4 *>(rb + (((c0 + i) ^ sw) << 4));
+        const int w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            v[4 * i + k] = make_float2((float)(short)(w[k] & 0xffff), (float)(short)(w[k] >> 16));
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
 }
 
 template <int DT>
@@ -116,8 +165,8 @@ __device__ __forceinline__ float rcp_approx(float x)
 
 // KIND: OFS_SC / OFS_SC_BOTH / OFS_MINN / OFS_AA.   WARPS: D = WARPS*256.
 template <int WARPS, int KIND, int DT>
-__global__ void __launch_bounds__(WARPS * 32, (((KIND == OFS_MINN || KIND == OFS_SC_BOTH) ? 384 : 512) / (WARPS * 32)))
-metric_stripe_kernel(StripeParams p)
+__global__ void __launch_bounds__(WARPS * 32, (((KIND == OFS_MINN || KIND == OFS_SC_BOTH) ? 384 : OFS_STRIPE_THREADS) / (WARPS * 32)))
+metric_stripe_kernel(const StripeParams p, const __grid_constant__ CUtensorMap tmap)
 {
     constexpr int BK = WARPS * SCH;
     constexpr int ESZ = InT<DT>::bytes;
@@ -187,8 +236,10 @@ metric_stripe_kernel(StripeParams p)
         sA.Ee = sB.Ee = 0.f;
 
         const int rem0 = (int)min(p.L - tb, (int64_t)0x7fffffff);      // samples from tb to the end of the frame
+        const int64_t row0 = ((int64_t)frame * p.xfs + tb) * ESZ / 128;     // tensor-map row of block 0 (use_tma == 2)
         auto tma_samples = [&](int i) -> int {        // prefix of block i brought by the bulk copy
             if (!p.use_tma) return 0;
+            if (p.use_tma == 2) return BK;           // tiled copies always bring the whole box (zero-filled past the tensor)
             const int rem = rem0 - i * BK;
             const int valid = rem < BK ? rem : BK;
             return (int)((((unsigned)valid * ESZ) & ~15u) / ESZ);
@@ -199,8 +250,11 @@ metric_stripe_kernel(StripeParams p)
                 const uint32_t g = git + (uint32_t)i;
                 uint64_t *bar = &bars[g % SSTAGES];
                 mbar_expect_tx(bar, (uint32_t)(ns * ESZ));
-                tma_load_1d(stages + (size_t)(g % SSTAGES) * STAGE_BYTES,
-                            xrow + (size_t)(tb + (int64_t)i * BK) * ESZ, (uint32_t)(ns * ESZ), bar);
+                if (p.use_tma == 2)
+                    tma_load_2d(stages + (size_t)(g % SSTAGES) * STAGE_BYTES, &tmap, 0, (int)(row0 + (int64_t)i * (STAGE_BYTES / 128)), bar);
+                else
+                    tma_load_1d(stages + (size_t)(g % SSTAGES) * STAGE_BYTES,
+                                xrow + (size_t)(tb + (int64_t)i * BK) * ESZ, (uint32_t)(ns * ESZ), bar);
             }
         };
         if (tid == 0) {
@@ -219,7 +273,15 @@ metric_stripe_kernel(StripeParams p)
             if (FAST) {
                 mbar_wait(&bars[st], (phase_bits >> st) & 1u);
                 phase_bits ^= 1u << st;
-                load8_smem<DT>(stage, myoff, cur.x);
+                if (p.use_tma == 2) load8_smem_swz<DT>(stage, myoff, cur.x);
+                else load8_smem<DT>(stage, myoff, cur.x);
+            } else if (p.use_tma == 2) {
+                mbar_wait(&bars[st], (phase_bits >> st) & 1u);
+                phase_bits ^= 1u << st;
+                load8_smem_swz<DT>(stage, myoff, cur.x);
+#pragma unroll
+                for (int j = 0; j < SK; ++j)                    // samples past the frame end belong to the next frame: zero them
+                    if (blkpos + myoff + j >= p.L) cur.x[j] = make_float2(0.f, 0.f);
             } else {
                 const int ns_tma = tma_samples(i);
                 if (ns_tma > 0) {
@@ -380,8 +442,43 @@ metric_stripe_kernel(StripeParams p)
     }
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+// The whole input batch as a 2-D tensor of 128-byte rows; one box = one stage (STAGE_BYTES / 128 rows), 128B swizzle.
+static bool make_input_map(CUtensorMap *map, const void *x, size_t total_bytes, int stage_bytes)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t gdim[2] = {32, (cuuint64_t)(total_bytes / 128)};
+    const cuuint64_t gstride[1] = {128};
+    const cuuint32_t box[2] = {32, (cuuint32_t)(stage_bytes / 128)};
+    const cuuint32_t estr[2] = {1, 1};
+    if (gdim[1] == 0 || gdim[1] > 0xffffffffull || box[1] > 256) return false;
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(x), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int WARPS, int KIND, int DT>
-static int launch_one(const StripeParams &p, int64_t total_work, cudaStream_t stream)
+static int launch_one(StripeParams p, int64_t total_work, cudaStream_t stream)
 {
     constexpr int BK = WARPS * SCH;
     constexpr int ESZ = InT<DT>::bytes;
@@ -396,9 +493,15 @@ static int launch_one(const StripeParams &p, int64_t total_work, cudaStream_t st
         if (occ < 1) occ = 1;
         attr_set = true;
     }
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    // tiled (swizzled) copies need 128-byte rows: frame pitch a multiple of 128 bytes; the batch is one tensor
+    if (p.use_tma == 1 && p.tma_mode_wanted == 2 && ((size_t)p.xfs * ESZ) % 128 == 0 &&
+        make_input_map(&tmap, p.x, (size_t)p.n_frames * p.xfs * ESZ, BK * ESZ))
+        p.use_tma = 2;
     int64_t grid = (int64_t)sm_count() * occ;
     if (grid > total_work) grid = total_work;
-    kern<<<(unsigned)grid, WARPS * 32, smem, stream>>>(p);
+    kern<<<(unsigned)grid, WARPS * 32, smem, stream>>>(p, tmap);
     return check_launch("metric_stripe_kernel");
 }
 
@@ -460,6 +563,7 @@ int launch_metric_stripe(const ofs_metric_desc *d, const void *x, float *M, floa
     p.aa_L = d->symbol_len; p.aa_floor = 1e-6f * (float)d->symbol_len;
     // bulk copies need 16-byte aligned sources: base pointer and frame pitch
     p.use_tma = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (((size_t)d->x_frame_stride * esz) % 16 == 0);
+    p.tma_mode_wanted = (d->reserved == 1) ? 1 : 2;      // desc.reserved = 1 forces the 1-D bulk-copy path (A/B testing)
     // stripe length: a multiple of D, >= 8 warm-up-amortising blocks, aiming at >= ~6 work units per CTA slot
     const int64_t nblk_frame = (d->n_samples + D - 1) / D;
     const int64_t slots = (int64_t)sm_count() * 4;

@@ -74,7 +74,7 @@ def metric_out_len(kind: str, symbol_len: int, n: int) -> int:
 
 
 def metric(rx, kind: str, symbol_len: int, *, want_pr: bool = True, out_f64: bool | None = None,
-           path: str = "auto", store_mode: int = 0, want_chunk_max: bool = False) -> MetricOut:
+           path: str = "auto", store_mode: int = 0, want_chunk_max: bool = False, tma_mode: int = 2) -> MetricOut:
     """Timing metric M (+P, R) of sc.py:42-78 / combined_sc_min.py:116-164 / minn.py:59-112,697-751 /
     sync_aa.py:458-493 for a batch of frames."""
     x, code, _ = to_device(rx)
@@ -90,7 +90,7 @@ def metric(rx, kind: str, symbol_len: int, *, want_pr: bool = True, out_f64: boo
         return MetricOut(e, torch.zeros((F, 0), dtype=cdt, device=dev) if want_pr else None, e.clone() if want_pr else None)
     d = L.MetricDesc(kind=KINDS[kind], in_dtype=code, out_f64=int(out_f64), path=PATHS[path], symbol_len=int(symbol_len),
                      n_branches=B, n_frames=F, n_samples=n, x_frame_stride=B * n, x_branch_stride=n,
-                     out_stride=0, store_mode=store_mode, reserved=0)
+                     out_stride=0, store_mode=store_mode, reserved=1 if tma_mode == 1 else 0)
     lib = L.lib()
     use_stripe = path != "tile" and not want_pr and not out_f64 and bool(lib.ofs_metric_stripe_ok(C.byref(d), _ptr(x), None))
     if path == "stripe" and not use_stripe:
@@ -286,7 +286,8 @@ class SyncPlan:
     """Pre-allocated buffers for repeated ofs_sync calls on device-resident frames [F, L] complex64/int16-IQ."""
 
     def __init__(self, n_frames: int, n_samples: int, kind: str = "sc", symbol_len: int = 2048, in_dtype: str = "c64",
-                 cp_len: int = 512, smooth_win: int = 16, sc_delta: int = 16, gate_threshold: float = 0.5, store_mode: int = 0):
+                 cp_len: int = 512, smooth_win: int = 16, sc_delta: int = 16, gate_threshold: float = 0.5, store_mode: int = 0,
+                 tma_mode: int = 2):
         dev = _device()
         self.F, self.n, self.kind, self.N = n_frames, n_samples, kind, symbol_len
         self.code = {"c64": L.OFS_C64, "iq16": L.OFS_IQ16}[in_dtype]
@@ -302,7 +303,8 @@ class SyncPlan:
         self.scratch = torch.zeros(3 * n_frames, dtype=torch.int64, device=dev)
         self.desc = L.MetricDesc(kind=KINDS[kind], in_dtype=self.code, out_f64=0, path=L.OFS_PATH_AUTO, symbol_len=symbol_len,
                                  n_branches=1, n_frames=n_frames, n_samples=n_samples, x_frame_stride=n_samples,
-                                 x_branch_stride=n_samples, out_stride=self.pitch, store_mode=store_mode, reserved=0)
+                                 x_branch_stride=n_samples, out_stride=self.pitch, store_mode=store_mode,
+                                 reserved=1 if tma_mode == 1 else 0)
 
     def run(self, x: torch.Tensor) -> SyncOut:
         assert x.is_cuda and x.is_contiguous() and x.shape[0] == self.F
@@ -351,7 +353,7 @@ class HostSync:
         out_stride = M_host.stride(0) if M_host is not None else max(n - symbol_len + 1, 0)
         d = L.MetricDesc(kind=KINDS[kind], in_dtype=code, out_f64=0, path=L.OFS_PATH_AUTO, symbol_len=symbol_len, n_branches=1,
                          n_frames=F, n_samples=n, x_frame_stride=x_host.stride(0), x_branch_stride=n, out_stride=out_stride,
-                         store_mode=1, reserved=0)
+                         store_mode=0, reserved=0)
         L.check(L.lib().ofs_sync_host(self.ctx, C.byref(d), _ptr(x_host), _ptr(M_host), int(cp_len), int(smooth_win), int(sc_delta),
                                       C.c_double(gate_threshold), _ptr(records_host)), "ofs_sync_host")
         return records_host.numpy().view(_REC_NP).reshape(-1)

@@ -45,12 +45,12 @@ def _check_metric(M_gpu, M_ref):
 
 @pytest.mark.parametrize("kind,N", [("sc", 2048), ("sc", 1024), ("sc", 512), ("sc_both", 2048), ("minn", 2048),
                                     ("minn", 4096), ("minn", 1024), ("aa", 512), ("aa", 256), ("aa", 1024)])
-@pytest.mark.parametrize("store_mode", [0, 1])
-def test_stripe_metric_vs_oracle(kind, N, store_mode):
+@pytest.mark.parametrize("store_mode,tma_mode", [(0, 2), (1, 2), (0, 1)])
+def test_stripe_metric_vs_oracle(kind, N, store_mode, tma_mode):
     from ofdm_sync_math_b200 import engine
     n = 40960 + 2 * 4096            # several stripes worth of blocks
     x = _captures(3, n, "minn" if kind == "minn" else "sc", seed=1)
-    r = engine.metric(_dev(x), kind, N, want_pr=False, path="stripe", store_mode=store_mode, want_chunk_max=True)
+    r = engine.metric(_dev(x), kind, N, want_pr=False, path="stripe", store_mode=store_mode, want_chunk_max=True, tma_mode=tma_mode)
     assert r.path == "stripe"
     M = r.M.cpu().numpy()
     M_ref = _oracle_metric(x, kind, N)

@@ -1,0 +1,154 @@
+#!/usr/bin/env python
+"""Secondary measurements: the other BASELINE.json configs (bench.py stays the headline / driver contract).
+
+One JSON line per case: throughput in Msamples/s (input samples, all branches), the algorithmic bytes or flops of
+SURVEY.md 8d, the achieved GB/s or TFLOP/s from CUDA events, and the fraction of the measured peak.
+    python bench_configs.py [--scale 1.0] [--cases minn,combined,park,zc,zcfreq,aa64,rtl,tile]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"])
+    return 6650.0
+
+
+def timeit(fn, steps=5, warmup=3):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--cases", default="minn,combined,park,zc,zcfreq,aa64,rtl,tile")
+    a = ap.parse_args()
+    import numpy as np
+    import torch
+    from ofdm_sync_math_b200 import engine, synth
+    from ofdm_sync_math_b200.zc import build_pss_symbol, generate_zadoff_chu
+    dev = torch.device("cuda", 0)
+    hbm = peaks()
+    cases = a.cases.split(",")
+
+    def emit(name, ms, samples, alg_bytes=None, flops=None, note=""):
+        d = {"case": name, "ms": ms, "Msamples_per_s": samples / (ms * 1e-3) / 1e6, "note": note}
+        if alg_bytes is not None:
+            d["roofline"] = {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                             "frac": alg_bytes / (ms * 1e-3) / 1e9 / hbm}
+        if flops is not None:
+            d["flops"] = {"achieved_tflops": flops / (ms * 1e-3) / 1e12, "fp32_fma_peak_tflops_nominal": 80.0}
+        print(json.dumps(d), flush=True)
+
+    if "minn" in cases:
+        # cfg 3: Minn metric + find_minn_peak + CFO, 1 M-sample captures x 1024 streams
+        F, n = max(int(1024 * a.scale), 8), 1 << 20
+        x = synth.make_batch_device(F, n, "minn", seed=7, device=dev, chunk=16)
+        plan = engine.SyncPlan(F, n, "minn", 2048, "c64", smooth_win=16, gate_threshold=0.5)
+        ms_k = timeit(lambda: plan.run_metric_only(x))
+        ms = timeit(lambda: plan.run(x))
+        emit("cfg3 minn metric kernel (stripe, D=512)", ms_k, F * n, alg_bytes=F * (8 * n + 4 * (n - 2047)))
+        emit("cfg3 minn metric + find_minn_peak + CFO", ms, F * n, alg_bytes=F * (8 * n + 4 * (n - 2047)),
+             note="roofline figure uses the metric kernel's algorithmic bytes over the whole step")
+        del x, plan
+    if "combined" in cases:
+        F, n = max(int(1024 * a.scale), 8), 1 << 19
+        x = synth.make_batch_device(F, n, "minn", seed=8, device=dev, chunk=32)[:, None]
+
+        def run():
+            m = engine.metric(x, "minn", 2048, want_pr=False, path="stripe", want_chunk_max=True)
+            s = engine.metric(x, "sc_both", 2048, want_pr=False, path="stripe")
+            g = engine.sc_gate(s.M, 0.6)
+            return engine.find_minn_peak_gated(m.M, 16, g)
+        ms = timeit(run, steps=3, warmup=2)
+        emit("cfg3 combined: Minn + S&C(both halves) metrics + gate + gated peak", ms, F * n, alg_bytes=2 * F * (8 * n + 4 * (n - 2047)),
+             note="two metric passes over the same samples (16 B read + 8 B written per sample algorithmic) + byte gate mask")
+        del x
+    if "park" in cases:
+        F, n = max(int(64 * a.scale), 2), 1 << 18
+        x = synth.make_batch_device(F, n, "sc", seed=9, device=dev, chunk=16)[:, None]
+        ms = timeit(lambda: engine.park_metric(x, 2048), steps=3, warmup=2)
+        nout = n - 2048
+        emit("cfg3 park metric (1024 complex MACs + 1024 |x|^2 per output)", ms, F * n, flops=F * nout * 1024 * (8 + 4),
+             note="FMA-bound (SURVEY 7.3-4); flops counted as 8 per complex MAC + 4 per energy term")
+        del x
+    if "zc" in cases:
+        # cfg 4 (single root): overlap-save matched filter + zc_v2 streaming detection + gate FSM
+        F, n = max(int(2048 * a.scale), 8), 65536
+        x = synth.make_batch_device(F, n, "sc", seed=10, device=dev, chunk=64)[:, None]
+        ref = build_pss_symbol(include_cp=False)
+
+        def run():
+            corr, mag = engine.zc_matched_filter(x, ref, mode=1, out_f64=False)
+            ls, v, ab = engine.zc_streaming_detection(mag, 2048, 64, 15, 0.3)
+            return engine.zc_events(mag, v, ab, 2048, 256, want_gate_mask=False)
+        ms_mf = timeit(lambda: engine.zc_matched_filter(x, ref, mode=1, out_f64=False), steps=3, warmup=2)
+        ms = timeit(run, steps=3, warmup=2)
+        emit("cfg4 zc matched filter (smem FFT overlap-save, fp32)", ms_mf, F * n, alg_bytes=F * (8 * n + 12 * (n + 2047)),
+             note="8 B in + 8 B corr + 4 B |corr| out per sample")
+        emit("cfg4 zc_v2 pipeline: matched filter + running-sum threshold + gate FSM", ms, F * n)
+        del x
+    if "zcfreq" in cases:
+        F, n = max(int(256 * a.scale), 4), 65536
+        x = synth.make_batch_device(F, n, "sc", seed=11, device=dev, chunk=64)[:, None]
+        half = 31
+        bi = np.concatenate((np.arange(-half, 0), np.arange(1, half + 1)))
+        tb = generate_zadoff_chu(25, 62)
+        ms = timeit(lambda: engine.zc_freq_metric(x, bi, tb, 62.0, out_f64=False), steps=3, warmup=2)
+        emit("cfg4 zc_freq metric (62-bin sliding DFT, float64 prefix)", ms, F * n, flops=F * (n - 2559) * 62 * 2 * 16,
+             note="flops ~ 62 bins x 2 (tile halo) x ~16 per modulated-prefix sample")
+        del x
+    if "aa64" in cases:
+        # cfg 5: 64-antenna [A][A] combining, 8 captures per GPU x 64 antennas x 262144 c64
+        F, A, n = max(int(8 * a.scale), 1), 64, 262144
+        x = synth.make_batch_device(F * A, n, "sc", seed=12, device=dev, chunk=64).reshape(F, A, n)
+
+        def run():
+            r = engine.metric(x, "aa", 512, want_pr=True, out_f64=False, path="tile")
+            return engine.aa_events(r.M, r.P, 512, 0.15, 128, 15.36e6)
+        ms_k = timeit(lambda: engine.metric(x, "aa", 512, want_pr=True, out_f64=False, path="tile"), steps=3, warmup=2)
+        ms = timeit(run, steps=3, warmup=2)
+        emit("cfg5 sync_aa 64-antenna metric (tile kernel, antenna sum on chip)", ms_k, F * A * n, alg_bytes=F * n * (8 * A + 16),
+             note="8*A B in + M,P,R out per output sample")
+        emit("cfg5 sync_aa 64-antenna metric + gate FSM + CFO", ms, F * A * n, alg_bytes=F * n * (8 * A + 16))
+        del x
+    if "rtl" in cases:
+        F, A, n = max(int(2048 * a.scale), 16), 2, 32768
+        iq = torch.randint(-2047, 2048, (F, A, n, 2), dtype=torch.int16, device=dev)
+
+        def run():
+            d = engine.minn_rtl_int(iq, 512, 3, 3276, 15)
+            return engine.minn_rtl_events(d["corr_positive"], d["metric_valid"], d["above_threshold"], 2, 0)
+        ms = timeit(run, steps=3, warmup=2)
+        emit("cfg1 minn_rtl integer datapath + gate FSM (reference-order streams)", ms, F * A * n, alg_bytes=F * n * (4 * A + 4 * 8 + 2),
+             note="one thread per stream; int64 outputs dominate the traffic")
+        del iq
+    if "tile" in cases:
+        F, n = max(int(512 * a.scale), 8), 262144
+        x = synth.make_batch_device(F, n, "sc", seed=13, device=dev, chunk=64)[:, None]
+        ms = timeit(lambda: engine.metric(x, "sc", 2048, want_pr=True, out_f64=False, path="tile"), steps=3, warmup=2)
+        emit("sc metric, precise tile kernel (float64 prefix; M,P,R out)", ms, F * n, alg_bytes=F * (8 * n + 16 * (n - 2047)))
+        del x
+
+
+if __name__ == "__main__":
+    main()

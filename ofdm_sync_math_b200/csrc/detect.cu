@@ -86,78 +86,149 @@ __device__ long long block_min_i64(long long x, long long *sh)
 // F(i) <= max(cm[c(i)-rad_lo .. c(i)+rad_hi]).  Chunks whose bound is below a value already attained are
 // skipped: the result (first maximum) is exactly the one of the full scan.
 struct Prune {
-    const float *cm;      // nullptr: no pruning
+    const float *cm;      // nullptr: no pruning.  Points to SHARED memory after stage().
     int64_t ncm;          // entries in this row of cm
     int toff, rad_lo, rad_hi;
+    // copy the row of chunk maxima into shared memory (coalesced) so that bound() is not a chain of global loads
+    __device__ void stage(float *smem_cm, int64_t nch)
+    {
+        if (cm == nullptr) return;
+        if (nch < ncm) ncm = nch;
+        for (int64_t c = threadIdx.x; c < ncm; c += DNT) smem_cm[c] = __ldg(cm + c);
+        cm = smem_cm;
+        __syncthreads();
+    }
     __device__ __forceinline__ float bound(int64_t c) const
     {
         float b = 0.f;
         int64_t lo = c - rad_lo, hi = c + rad_hi;
         if (lo < 0) lo = 0;
         if (hi > ncm - 1) hi = ncm - 1;
-        for (int64_t k = lo; k <= hi; ++k) b = fmaxf(b, __ldg(cm + k));
+        for (int64_t k = lo; k <= hi; ++k) b = fmaxf(b, cm[k]);
         return b;
     }
 };
 
+// Window functions are evaluated for 8 consecutive outputs at a time (eval8): the window is loaded once and slid,
+// ~4 loads per output instead of w.  Groups are aligned to the causal time t = d + toff (multiples of 8), so that one
+// warp = 32 groups = one 256-sample chunk.  Every pass of a kernel goes through the same grouping, hence sees
+// bit-identical values.
 template <typename F>
 __device__ ArgVal pruned_argmax(const F &fn, int64_t n_out, const Prune &pr, ArgVal *sh_av)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    ArgVal best{0.0, -1};
-    if (pr.cm == nullptr) {
-        for (int64_t i = tid; i < n_out; i += DNT) {
-            const double v = fn(i);
-            if (best.i < 0 || v > best.v) { best.v = v; best.i = i; }
-        }
-        return block_argmax<false>(best, sh_av);
-    }
     const int64_t nch = (n_out + pr.toff + 255) / 256;
-    // phase 0: the chunk with the largest raw maximum
-    ArgVal bc{0.0, -1};
-    for (int64_t c = tid; c < nch && c < pr.ncm; c += DNT) {
-        const double v = (double)__ldg(pr.cm + c);
-        if (bc.i < 0 || v > bc.v) { bc.v = v; bc.i = c; }
-    }
-    bc = block_argmax<false>(bc, sh_av);
-    // phase 1: exact values over that chunk -> a value v* that the maximum is known to reach
+    double v8[8];
     ArgVal vs{0.0, -1};
-    {
-        const int64_t i = bc.i * 256 - pr.toff + tid;
-        if (bc.i >= 0 && i >= 0 && i < n_out) { vs.v = fn(i); vs.i = i; }
-    }
-    vs = block_argmax<false>(vs, sh_av);
-    const bool have = vs.i >= 0;
-    // phase 2: every chunk that could still hold the maximum
-    for (int64_t c = warp; c < nch; c += DNT / 32) {
-        if (have && (double)pr.bound(c) < vs.v) continue;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int64_t i = c * 256 - pr.toff + 32 * k + lane;
-            if (i >= 0 && i < n_out) {
-                const double v = fn(i);
-                if (best.i < 0 || v > best.v) { best.v = v; best.i = i; }
-            }
+    bool have = false;
+    if (pr.cm != nullptr) {
+        // phase 0: the chunk with the largest raw maximum
+        ArgVal bc{0.0, -1};
+        for (int64_t c = tid; c < nch && c < pr.ncm; c += DNT) {
+            const double v = (double)pr.cm[c];
+            if (bc.i < 0 || v > bc.v) { bc.v = v; bc.i = c; }
         }
+        bc = block_argmax<false>(bc, sh_av);
+        // phase 1: exact values over that chunk -> a value v* that the maximum is known to reach
+        if (bc.i >= 0 && warp == 0) {
+            const int64_t i0 = bc.i * 256 - pr.toff + 8 * lane;
+            fn.eval8(i0, v8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (i0 + k >= 0 && i0 + k < n_out && (vs.i < 0 || v8[k] > vs.v)) { vs.v = v8[k]; vs.i = i0 + k; }
+        }
+        vs = block_argmax<false>(vs, sh_av);
+        have = vs.i >= 0;
+    }
+    // phase 2: every chunk that could still hold the maximum (all chunks when there is no pruning information).
+    // The bound test is done 32 chunks at a time (one per lane); survivors are evaluated by the whole warp.
+    ArgVal best{0.0, -1};
+    const int nchi = (int)nch;
+    for (int c0 = warp * 32; c0 < nchi; c0 += (DNT / 32) * 32) {
+        const int cl = c0 + lane;
+        const bool pass = cl < nchi && (!have || (double)pr.bound(cl) >= vs.v);
+        unsigned m = __ballot_sync(0xffffffffu, pass);
+        while (m) {
+            const int c = c0 + __ffs(m) - 1;
+            m &= m - 1;
+            const int64_t i0 = (int64_t)c * 256 - pr.toff + 8 * lane;
+            if (i0 + 7 < 0 || i0 >= n_out) continue;
+            fn.eval8(i0, v8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (i0 + k >= 0 && i0 + k < n_out && (best.i < 0 || v8[k] > best.v)) { best.v = v8[k]; best.i = i0 + k; }
+        }
+    }
+    return block_argmax<false>(best, sh_av);
+}
+
+// first-maximum over an index range [lo, hi) through the same 8-groups
+template <typename F>
+__device__ ArgVal range_argmax(const F &fn, int64_t lo, int64_t hi, int toff, ArgVal *sh_av)
+{
+    ArgVal best{0.0, -1};
+    double v8[8];
+    const int64_t g0 = lo - (((lo + toff) % 8) + 8) % 8;
+    for (int64_t i0 = g0 + 8LL * threadIdx.x; i0 < hi; i0 += 8LL * DNT) {
+        fn.eval8(i0, v8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (i0 + k >= lo && i0 + k < hi && (best.i < 0 || v8[k] > best.v)) { best.v = v8[k]; best.i = i0 + k; }
     }
     return block_argmax<false>(best, sh_av);
 }
 
 // ---- S&C plateau end -------------------------------------------------------------------------------
 struct SmoothSame {   // np.convolve(M, ones(w)/w, "same")[i], sc.py:100
-    RowView r;
-    int64_t row, ms;
-    int w, off;
+    const float *pf;
+    const double *pd;
+    int64_t n, ms;
+    int w, off, toff;
     double h;
+    __device__ __forceinline__ double X(int64_t j) const      // M[j] * (1/w), zero outside the row
+    {
+        const bool ok = j >= 0 && j < n;
+        const int64_t jc = ok ? j : 0;
+        const double v = pd ? pd[jc] : (double)pf[jc];
+        return ok ? v * h : 0.0;
+    }
+    // compile-time window: the W+7 values are fetched by independent (predicated) loads first, then slid
+    template <int W>
+    __device__ __forceinline__ void eval8_t(int64_t i0, double (&o)[8]) const
+    {
+        double y[W + 7];
+        const int64_t j0 = i0 + off - W + 1;
+#pragma unroll
+        for (int q = 0; q < W + 7; ++q) y[q] = X(j0 + q);
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < W; ++q) s += y[q];
+        o[0] = s;
+#pragma unroll
+        for (int k = 1; k < 8; ++k) { s += y[W - 1 + k]; s -= y[k - 1]; o[k] = s; }
+    }
+    __device__ __forceinline__ void eval8(int64_t i0, double (&o)[8]) const
+    {
+        if (w == 16) { eval8_t<16>(i0, o); return; }
+        if (w == 8) { eval8_t<8>(i0, o); return; }
+        if (w == 32) { eval8_t<32>(i0, o); return; }
+        // window of output i: j in [i + off - w + 1, i + off]
+        double s = 0.0;
+        for (int64_t j = i0 + off - w + 1; j <= i0 + off; ++j) s += X(j);
+        o[0] = s;
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+            s += X(i0 + k + off);
+            s -= X(i0 + k + off - w);
+            o[k] = s;
+        }
+    }
     __device__ __forceinline__ double operator()(int64_t i) const
     {
-        const int64_t k = i + off;
-        int64_t jlo = k - w + 1;
-        if (jlo < 0) jlo = 0;
-        const int64_t jhi = k < r.n - 1 ? k : r.n - 1;
-        double s = 0.0;
-        for (int64_t j = jlo; j <= jhi; ++j) s = fma(r.at(row, j), h, s);
-        return s;
+        const int64_t g0 = i - (((i + toff) % 8) + 8) % 8;
+        double o[8];
+        eval8(g0, o);
+        return o[i - g0];
     }
 };
 
@@ -172,13 +243,17 @@ __global__ void __launch_bounds__(DNT) plateau_kernel(RowView r, int cp_len, int
     const int Lk = lookahead < 0 ? cp_len / 4 : (lookahead > 1 ? lookahead : 1);
     const int w = smooth_win > 1 ? smooth_win : 1;
     SmoothSame Ms;
-    Ms.r = r; Ms.row = row; Ms.w = w; Ms.h = 1.0 / (double)w;
+    Ms.pf = r.f64 ? nullptr : reinterpret_cast<const float *>(r.data) + row * r.stride;
+    Ms.pd = r.f64 ? reinterpret_cast<const double *>(r.data) + row * r.stride : nullptr;
+    Ms.n = r.n; Ms.w = w; Ms.h = 1.0 / (double)w; Ms.toff = toff;
     Ms.ms = r.n > w ? r.n : w;
     Ms.off = (int)(((r.n > w ? (int64_t)w : r.n) - 1) / 2);
     const int64_t ms = Ms.ms;
 
     // pass A: center = first argmax of the smoothed metric (sc.py:106), pruned by the chunk maxima
+    extern __shared__ float cm_s[];
     Prune pr{(cm && r.n > w) ? cm + row * cm_stride : nullptr, cm_stride, toff, (w - 1 - Ms.off + 255) / 256, (Ms.off + 255) / 256};
+    pr.stage(cm_s, (ms + toff + 255) / 256);
     ArgVal best = pruned_argmax(Ms, ms, pr, sh_av);
     const int64_t center = best.i;
     const double peak = best.v;
@@ -188,8 +263,16 @@ __global__ void __launch_bounds__(DNT) plateau_kernel(RowView r, int cp_len, int
     if (post_hi > center + 1) {
         const double thr = 0.95 * peak;
         long long first = LLONG_MAX;
-        for (int64_t i = center + tid; i < post_hi; i += DNT)
-            if (Ms(i) <= thr) { first = i; break; }
+        {
+            double v8[8];
+            const int64_t g0 = center - (((center + Ms.toff) % 8) + 8) % 8;
+            for (int64_t i0 = g0 + 8LL * tid; i0 < post_hi && first == LLONG_MAX; i0 += 8LL * DNT) {
+                Ms.eval8(i0, v8);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (first == LLONG_MAX && i0 + k >= center && i0 + k < post_hi && v8[k] <= thr) first = i0 + k;
+            }
+        }
         first = block_min_i64(first, sh_i);
         if (first != LLONG_MAX) { if (tid == 0) out[row] = first; return; }
     }
@@ -254,46 +337,126 @@ __global__ void __launch_bounds__(DNT) plateau_kernel(RowView r, int cp_len, int
 }
 
 // ---- trailing average (minn.py:115-128) as a pure function of the index ---------------------------
-struct Trailing {
-    RowView r;
-    int64_t row;
-    int w;
-    __device__ __forceinline__ double operator()(int64_t i) const
+struct Trailing {   // minn._trailing_average(max(M,0), w)[i], minn.py:115-128
+    const float *pf;
+    const double *pd;
+    int64_t n;
+    int w, toff;
+    __device__ __forceinline__ double X(int64_t j) const      // max(M[j], 0), zero outside the row
     {
-        if (w <= 1) { const double v = r.at(row, i); return v > 0.0 ? v : 0.0; }
-        int64_t jlo = i - w + 1;
-        if (jlo < 0) jlo = 0;
-        double s = 0.0;
-        for (int64_t j = jlo; j <= i; ++j) { const double v = r.at(row, j); s += v > 0.0 ? v : 0.0; }
-        return s / (double)(i >= w - 1 ? w : i + 1);
+        const bool ok = j >= 0 && j < n;
+        const int64_t jc = ok ? j : 0;
+        const double v = pd ? pd[jc] : (double)pf[jc];
+        return (ok && v > 0.0) ? v : 0.0;
     }
-};
-
-// scan a bitmask for the longest run of ones (earliest on ties); single thread, word-at-a-time
-__device__ void longest_run(const unsigned *mask, int64_t n, long long &bs, long long &be)
-{
-    long long best_len = 0, start = -1;
-    bs = 0; be = 0;
-    const int64_t nw = (n + 31) / 32;
-    for (int64_t wi = 0; wi < nw; ++wi) {
-        const unsigned m = mask[wi];
-        const int64_t base = wi * 32;
-        const int nbits = (int)(n - base < 32 ? n - base : 32);
-        if (m == 0u) {
-            if (start >= 0) { if (base - start > best_len) { best_len = base - start; bs = start; be = base; } start = -1; }
-        } else if (nbits == 32 && m == 0xffffffffu) {
-            if (start < 0) start = base;
-        } else {
-            for (int b = 0; b < nbits; ++b) {
-                if ((m >> b) & 1u) { if (start < 0) start = base + b; }
-                else if (start >= 0) {
-                    if (base + b - start > best_len) { best_len = base + b - start; bs = start; be = base + b; }
-                    start = -1;
-                }
-            }
+    __device__ __forceinline__ double denom(int64_t i) const { return (double)(i >= w - 1 ? w : (i >= 0 ? i + 1 : 1)); }
+    template <int W>
+    __device__ __forceinline__ void eval8_t(int64_t i0, double (&o)[8]) const
+    {
+        double y[W + 7];
+        const int64_t j0 = i0 - W + 1;
+#pragma unroll
+        for (int q = 0; q < W + 7; ++q) y[q] = X(j0 + q);
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < W; ++q) s += y[q];
+        // W is a power of two here: s * (1/W) is exactly s / W; only the warm-up outputs (i < W-1) need a true division
+        const bool steady = i0 >= W - 1;
+        o[0] = steady ? s * (1.0 / W) : s / denom(i0);
+#pragma unroll
+        for (int k = 1; k < 8; ++k) { s += y[W - 1 + k]; s -= y[k - 1]; o[k] = steady ? s * (1.0 / W) : s / denom(i0 + k); }
+    }
+    __device__ __forceinline__ void eval8(int64_t i0, double (&o)[8]) const
+    {
+        if (w <= 1) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = X(i0 + k);
+            return;
+        }
+        if (w == 16) { eval8_t<16>(i0, o); return; }
+        if (w == 8) { eval8_t<8>(i0, o); return; }
+        if (w == 32) { eval8_t<32>(i0, o); return; }
+        double s = 0.0;
+        for (int64_t j = i0 - w + 1; j <= i0; ++j) s += X(j);
+        o[0] = s / denom(i0);
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+            s += X(i0 + k);
+            s -= X(i0 + k - w);
+            o[k] = s / denom(i0 + k);
         }
     }
-    if (start >= 0 && n - start > best_len) { bs = start; be = n; }
+    __device__ __forceinline__ double operator()(int64_t i) const
+    {
+        const int64_t g0 = i - (((i + toff) % 8) + 8) % 8;
+        double o[8];
+        eval8(g0, o);
+        return o[i - g0];
+    }
+};
+__device__ __forceinline__ Trailing make_trailing(const RowView &r, int64_t row, int w, int toff)
+{
+    Trailing t;
+    t.pf = r.f64 ? nullptr : reinterpret_cast<const float *>(r.data) + row * r.stride;
+    t.pd = r.f64 ? reinterpret_cast<const double *>(r.data) + row * r.stride : nullptr;
+    t.n = r.n; t.w = w; t.toff = toff;
+    return t;
+}
+
+// Walk the maximal runs of ones of a 32-word group (the words are spread over the lanes of one warp; every lane runs
+// the same code, state is replicated).  on_start(pos) is called at the first bit of a run that begins in this group,
+// on_end(pos) at the first zero after a run (pos = absolute bit index).  `in_run` carries a run across groups.
+template <typename FS, typename FE>
+__device__ __forceinline__ void walk_group(unsigned m, long long base0, bool &in_run, FS on_start, FE on_end)
+{
+    const unsigned nz = __ballot_sync(0xffffffffu, m != 0u);
+    const unsigned nf = __ballot_sync(0xffffffffu, m != 0xffffffffu);
+    if (nz == 0u) { if (in_run) { on_end(base0); in_run = false; } return; }
+    if (nf == 0u) { if (!in_run) { on_start(base0); in_run = true; } return; }
+    unsigned rem = nz;
+    int prevk = -1;
+    while (rem) {
+        const int k = __ffs(rem) - 1;
+        rem &= rem - 1;
+        if (k != prevk + 1 && in_run) { on_end(base0 + 32LL * (prevk + 1)); in_run = false; }   // zero word(s) in between
+        const unsigned mk = __shfl_sync(0xffffffffu, m, k);
+        const long long base = base0 + 32LL * k;
+        int pos = 0;
+        while (pos < 32) {
+            const unsigned rest = mk >> pos;
+            if (rest & 1u) {
+                if (!in_run) { on_start(base + pos); in_run = true; }
+                const unsigned inv = ~rest;                       // zeros shifted in at the top count as "end of word"
+                const int ones = (pos == 0 && inv == 0u) ? 32 : __ffs(inv) - 1;
+                pos += ones;
+                if (pos < 32) { on_end(base + pos); in_run = false; }
+            } else {
+                if (in_run) { on_end(base + pos); in_run = false; }   // a run that reached the end of the previous word stops here
+                pos += rest == 0u ? 32 - pos : __ffs(rest) - 1;
+            }
+        }
+        prevk = k;
+    }
+    if (prevk != 31 && in_run) { on_end(base0 + 32LL * (prevk + 1)); in_run = false; }
+}
+
+// Longest run of ones in a bitmask (earliest on ties, minn.py:159-182), executed by ONE WARP, 32 words per step.
+__device__ void longest_run_warp(const unsigned *mask, int64_t n, long long &bs, long long &be)
+{
+    const int lane = threadIdx.x & 31;
+    long long best_len = 0, start = -1, rbs = 0, rbe = 0;
+    bool in_run = false;
+    const int64_t nw = (n + 31) / 32;
+    for (int64_t w0 = 0; w0 < nw; w0 += 32) {
+        const int64_t wi = w0 + lane;
+        unsigned m = wi < nw ? mask[wi] : 0u;
+        if (wi < nw && (wi + 1) * 32 > n) m &= (n - wi * 32 >= 32) ? 0xffffffffu : ((1u << (n - wi * 32)) - 1u);
+        walk_group(m, w0 * 32, in_run,
+                   [&](long long p) { start = p; },
+                   [&](long long p) { if (p - start > best_len) { best_len = p - start; rbs = start; rbe = p; } });
+    }
+    if (in_run && n - start > best_len) { rbs = start; rbe = n; }
+    bs = rbs; be = rbe;
 }
 
 __global__ void __launch_bounds__(DNT) minn_peak_kernel(RowView r, int smooth_win, double gate_threshold,
@@ -308,16 +471,27 @@ __global__ void __launch_bounds__(DNT) minn_peak_kernel(RowView r, int smooth_wi
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t n = r.n;
     if (n == 0) { if (tid == 0) { peak[row] = -1; gate_span[2 * row] = gate_span[2 * row + 1] = 0; } return; }
-    Trailing Ms{r, row, smooth_win > 1 ? smooth_win : 1};
+    const Trailing Ms = make_trailing(r, row, smooth_win > 1 ? smooth_win : 1, toff);
 
     // pass 1: global first-argmax of Ms (also the fallback answer), optional Ms output
     const int wv = smooth_win > 1 ? smooth_win : 1;
     Prune pr{cm ? cm + row * cm_stride : nullptr, cm_stride, toff, (wv - 1 + 255) / 256, 0};
+    {
+        const int64_t nch0 = (n + toff + 255) / 256;
+        pr.stage(reinterpret_cast<float *>(mask + nch0 * 8 + 4), nch0);      // chunk maxima live after the bitmask
+    }
     if (Ms_out) {
-        for (int64_t i = tid; i < n; i += DNT) {
-            const double v = Ms(i);
-            if (r.f64) reinterpret_cast<double *>(Ms_out)[row * r.stride + i] = v;
-            else reinterpret_cast<float *>(Ms_out)[row * r.stride + i] = (float)v;
+        double v8[8];
+        const int64_t g0 = -(int64_t)(((toff % 8) + 8) % 8);
+        for (int64_t i0 = g0 + 8LL * tid; i0 < n; i0 += 8LL * DNT) {
+            Ms.eval8(i0, v8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int64_t i = i0 + k;
+                if (i < 0 || i >= n) continue;
+                if (r.f64) reinterpret_cast<double *>(Ms_out)[row * r.stride + i] = v8[k];
+                else reinterpret_cast<float *>(Ms_out)[row * r.stride + i] = (float)v8[k];
+            }
         }
     }
     ArgVal best = pruned_argmax(Ms, n, pr, sh_av);
@@ -327,23 +501,39 @@ __global__ void __launch_bounds__(DNT) minn_peak_kernel(RowView r, int smooth_wi
     //         -> longest run (minn.py:155-182)
     const double level = gate_threshold * best.v;
     const int64_t nch = (n + toff + 255) / 256;
-    for (int64_t c = tid >> 5; c < nch; c += DNT / 32) {
-        if (pr.cm && (double)pr.bound(c) < level) {
-            if (lane < 8) mask[c * 8 + lane] = 0u;
-            continue;
-        }
+    {
+        const int nchi = (int)nch, warp = tid >> 5;
+        for (int c0 = warp * 32; c0 < nchi; c0 += (DNT / 32) * 32) {
+            const int cl = c0 + lane;
+            const bool inr = cl < nchi;
+            const bool pass = inr && (!pr.cm || (double)pr.bound(cl) >= level);
+            if (inr && !pass) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int64_t i = c * 256 - toff + 32 * k + lane;
-            const bool f = i >= 0 && i < n && Ms(i) >= level;
-            const unsigned m = __ballot_sync(0xffffffffu, f);
-            if (lane == 0) mask[c * 8 + k] = m;
+                for (int q = 0; q < 8; ++q) mask[cl * 8 + q] = 0u;
+            }
+            unsigned m = __ballot_sync(0xffffffffu, pass);
+            while (m) {
+                const int c = c0 + __ffs(m) - 1;
+                m &= m - 1;
+                // lane = 8 consecutive causal times of the chunk -> one byte of flags; 4 lanes make a mask word
+                const int64_t i0 = (int64_t)c * 256 - toff + 8 * lane;
+                double v8[8];
+                Ms.eval8(i0, v8);
+                unsigned b8 = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (i0 + k >= 0 && i0 + k < n && v8[k] >= level) b8 |= 1u << k;
+                unsigned wv32 = b8 << (8 * (lane & 3));
+                wv32 |= __shfl_xor_sync(0xffffffffu, wv32, 1);
+                wv32 |= __shfl_xor_sync(0xffffffffu, wv32, 2);
+                if ((lane & 3) == 0) mask[c * 8 + (lane >> 2)] = wv32;
+            }
         }
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid < 32) {
         long long bs, be;
-        longest_run(mask, nch * 256, bs, be);
+        longest_run_warp(mask, nch * 256, bs, be);
         bs -= toff; be -= toff;
         if (bs < 0) bs = 0;
         if (be < 0) be = 0;
@@ -353,7 +543,7 @@ __global__ void __launch_bounds__(DNT) minn_peak_kernel(RowView r, int smooth_wi
             bs = bs > s ? bs : s;
             be = be < e ? be : e;
         }
-        sh_span[0] = bs; sh_span[1] = be;
+        if (tid == 0) { sh_span[0] = bs; sh_span[1] = be; }
     }
     __syncthreads();
     const long long gs = sh_span[0], ge = sh_span[1];
@@ -361,12 +551,7 @@ __global__ void __launch_bounds__(DNT) minn_peak_kernel(RowView r, int smooth_wi
         if (tid == 0) { peak[row] = best.i; gate_span[2 * row] = best.i; gate_span[2 * row + 1] = best.i + 1; }
         return;
     }
-    ArgVal pk{0.0, -1};
-    for (int64_t i = gs + tid; i < ge; i += DNT) {
-        const double v = Ms(i);
-        if (pk.i < 0 || v > pk.v) { pk.v = v; pk.i = i; }
-    }
-    pk = block_argmax<false>(pk, sh_av);
+    const ArgVal pk = range_argmax(Ms, gs, ge, Ms.toff, sh_av);
     if (tid == 0) { peak[row] = pk.i; gate_span[2 * row] = gs; gate_span[2 * row + 1] = ge; }
 }
 
@@ -421,13 +606,8 @@ __global__ void __launch_bounds__(DNT) gated_peak_kernel(RowView r, int smooth_w
         if (!g[i]) { stop = i; break; }
     stop = block_min_i64(stop, sh_i);
     if (stop == LLONG_MAX) stop = e;
-    Trailing Ms{r, row, smooth_win > 1 ? smooth_win : 1};
-    ArgVal pk{0.0, -1};
-    for (int64_t i = first + tid; i < stop; i += DNT) {
-        const double v = Ms(i);
-        if (pk.i < 0 || v > pk.v) { pk.v = v; pk.i = i; }
-    }
-    pk = block_argmax<false>(pk, sh_av);
+    const Trailing Ms = make_trailing(r, row, smooth_win > 1 ? smooth_win : 1, 0);
+    const ArgVal pk = range_argmax(Ms, first, stop, 0, sh_av);
     if (tid == 0) peak[row] = pk.i;
 }
 
@@ -550,35 +730,34 @@ __global__ void __launch_bounds__(DNT) fsm_kernel(FsmParams p)
     }
     __syncthreads();
 
-    // 2. gates = clusters of above-runs separated by fewer than heff below-samples
-    if (tid == 0) {
+    // 2. gates = clusters of above-runs separated by fewer than heff below-samples.  Warp 0 walks the mask 32 words
+    //    per step (all-zero / all-one groups cost one ballot); the state is replicated in every lane.
+    if (tid < 32) {
         int cnt = 0; bool open = false; long long gs = 0, last = 0;
         const int64_t nw = (n + 31) / 32;
         long long run_start = -1;
         auto run_begin = [&](long long a) {
             if (open && a - last - 1 >= p.heff) {
-                if (cnt < OFS_MAX_EVENTS) { g_start[cnt] = gs; g_close[cnt] = last + p.heff; g_closed[cnt] = 1; }
+                if (cnt < OFS_MAX_EVENTS && lane == 0) { g_start[cnt] = gs; g_close[cnt] = last + p.heff; g_closed[cnt] = 1; }
                 ++cnt; open = false;
             }
             if (!open) { open = true; gs = a; }
         };
-        for (int64_t wi = 0; wi < nw; ++wi) {
-            const unsigned m = mask[wi];
-            const long long base = wi * 32;
-            if (m == 0u) { if (run_start >= 0) { last = base - 1; run_start = -1; } continue; }
-            if (m == 0xffffffffu) { if (run_start < 0) { run_start = base; run_begin(base); } continue; }
-            for (int b = 0; b < 32; ++b) {
-                if ((m >> b) & 1u) { if (run_start < 0) { run_start = base + b; run_begin(base + b); } }
-                else if (run_start >= 0) { last = base + b - 1; run_start = -1; }
-            }
+        bool in_run = false;
+        for (int64_t w0 = 0; w0 < nw; w0 += 32) {
+            const int64_t wi = w0 + lane;
+            const unsigned m = wi < nw ? mask[wi] : 0u;
+            walk_group(m, w0 * 32, in_run,
+                       [&](long long ps) { run_start = ps; run_begin(ps); },
+                       [&](long long pe) { last = pe - 1; run_start = -1; });
         }
         if (run_start >= 0) { last = n - 1; }
         if (open) {
             const bool closes = (n - 1 - last) >= p.heff;
-            if (cnt < OFS_MAX_EVENTS) { g_start[cnt] = gs; g_close[cnt] = closes ? last + p.heff : n - 1; g_closed[cnt] = closes; }
+            if (cnt < OFS_MAX_EVENTS && lane == 0) { g_start[cnt] = gs; g_close[cnt] = closes ? last + p.heff : n - 1; g_closed[cnt] = closes; }
             ++cnt;
         }
-        g_count = cnt;
+        if (lane == 0) g_count = cnt;
     }
     __syncthreads();
     const int cnt = g_count < OFS_MAX_EVENTS ? g_count : OFS_MAX_EVENTS;
@@ -653,8 +832,11 @@ OFS_API int ofs_find_plateau_end_pruned(const ofs_rows *M, const float *chunk_ma
     OFS_REQUIRE(plateau_end, "ofs_find_plateau_end: null output");
     OFS_REQUIRE(!chunk_max || (toff >= 0 && cm_stride >= (M->n + toff + 255) / 256), "ofs_find_plateau_end: bad chunk_max geometry");
     if (M->n_rows == 0) return OFS_OK;
-    plateau_kernel<<<(unsigned)M->n_rows, DNT, 0, (cudaStream_t)stream>>>(view(M), cp_len, lookahead, smooth_win, plateau_end,
-                                                                         chunk_max, cm_stride, chunk_max ? toff : 0);
+    const size_t cms = chunk_max ? (size_t)((M->n + toff + 255) / 256 + 8) * sizeof(float) : 0;
+    OFS_REQUIRE(cms <= 200 * 1024, "ofs_find_plateau_end: rows too long for the pruned path");
+    if (cms > 48 * 1024) OFS_CUDA(cudaFuncSetAttribute(plateau_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cms));
+    plateau_kernel<<<(unsigned)M->n_rows, DNT, cms, (cudaStream_t)stream>>>(view(M), cp_len, lookahead, smooth_win, plateau_end,
+                                                                           chunk_max, cm_stride, chunk_max ? toff : 0);
     return check_launch("plateau_kernel");
 }
 
@@ -675,7 +857,9 @@ OFS_API int ofs_find_minn_peak_pruned(const ofs_rows *M, const float *chunk_max,
                 (long long)MASK_MAX_N);
     OFS_REQUIRE(!chunk_max || cm_stride >= (M->n + toff + 255) / 256, "ofs_find_minn_peak: bad chunk_max geometry");
     if (M->n_rows == 0) return OFS_OK;
-    const size_t sm = mask_bytes(((M->n + toff + 255) / 256) * 256);
+    const int64_t nch_h = (M->n + toff + 255) / 256;
+    const size_t sm = mask_bytes(nch_h * 256) + (chunk_max ? (size_t)(nch_h + 8) * sizeof(float) : 0);
+    OFS_REQUIRE(sm <= 220 * 1024, "ofs_find_minn_peak: rows too long");
     if (int rc = set_mask_smem(minn_peak_kernel, sm)) return rc;
     minn_peak_kernel<<<(unsigned)M->n_rows, DNT, sm, (cudaStream_t)stream>>>(view(M), smooth_win, gate_threshold, has_bounds,
                                                                             bound_lo, bound_hi, peak, gate_span, Ms, chunk_max,

@@ -23,12 +23,15 @@ template <typename C2> __device__ __forceinline__ C2 csub(C2 a, C2 b) { C2 r; r.
 template <typename C2> __device__ __forceinline__ C2 cmul(C2 a, C2 b) { C2 r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r; }
 template <typename C2> __device__ __forceinline__ C2 cmulc(C2 a, C2 b) { C2 r; r.x = a.x * b.x + a.y * b.y; r.y = a.y * b.x - a.x * b.y; return r; }  // a * conj(b)
 
+// twiddle tables: double2[ZF/2] followed by float2[ZF/2] (same buffer), exp(-2 pi i k / ZF)
 template <typename C2>
-__device__ __forceinline__ C2 ld_tw(const double2 *tw, int i)
+__device__ __forceinline__ C2 ld_tw(const double2 *tw, int i);
+template <>
+__device__ __forceinline__ double2 ld_tw<double2>(const double2 *tw, int i) { return __ldg(tw + i); }
+template <>
+__device__ __forceinline__ float2 ld_tw<float2>(const double2 *tw, int i)
 {
-    const double2 w = __ldg(tw + i);
-    C2 r; r.x = w.x; r.y = w.y;
-    return r;
+    return __ldg(reinterpret_cast<const float2 *>(tw + ZF / 2) + i);
 }
 
 // natural order in -> bit-reversed order out
@@ -69,6 +72,7 @@ __global__ void zc_twiddle_kernel(double2 *tw)
         double s, c;
         sincospi(-2.0 * (double)i / (double)ZF, &s, &c);
         tw[i] = make_double2(c, s);
+        reinterpret_cast<float2 *>(tw + ZF / 2)[i] = make_float2((float)c, (float)s);
     }
 }
 
@@ -105,10 +109,12 @@ __global__ void __launch_bounds__(ZNT) zc_mf_kernel(const void *x, int nb, int64
     using C2 = typename C2T<T>::type;
     using In = typename InT<DT>::type;
     extern __shared__ __align__(16) unsigned char zsm[];
-    C2 *a = reinterpret_cast<C2 *>(zsm);                                          // ZF
-    double *se = reinterpret_cast<double *>(zsm + (size_t)ZF * sizeof(C2));       // ZF + 1 (+1 pad)
-    double *pw = se + ZF + 2;                                                     // V <= ZF
-    double2 *acc = reinterpret_cast<double2 *>(pw + ZF);                          // V, 16-byte aligned
+    // a: ZF complex | se: ZF+4 energy-prefix entries | pw: ZF window energies | acc: ZF branch-summed outputs
+    // (float path: all fp32 -> 72 KB, 3 CTAs/SM; double path: 144 KB)
+    C2 *a = reinterpret_cast<C2 *>(zsm);
+    T *se = reinterpret_cast<T *>(zsm + (size_t)ZF * sizeof(C2));
+    T *pw = se + ZF + 4;
+    C2 *acc = reinterpret_cast<C2 *>(pw + ZF);
     __shared__ double wtot[ZNT / 32];
 
     const int V = ZF - nr + 1;                        // valid outputs per block
@@ -120,7 +126,7 @@ __global__ void __launch_bounds__(ZNT) zc_mf_kernel(const void *x, int nb, int64
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double ref_norm = *ref_norm_p;
 
-    for (int i = tid; i < V; i += ZNT) { pw[i] = 0.0; acc[i] = make_double2(0.0, 0.0); }
+    for (int i = tid; i < V; i += ZNT) { pw[i] = (T)0; acc[i].x = (T)0; acc[i].y = (T)0; }
 
     for (int b = 0; b < nb; ++b) {
         const In *xb = reinterpret_cast<const In *>(x) + (frame * nb + b) * n;
@@ -131,25 +137,25 @@ __global__ void __launch_bounds__(ZNT) zc_mf_kernel(const void *x, int nb, int64
             if (j >= 0 && j < n) { const In s = xb[j]; v.x = (T)s.x; v.y = (T)s.y; }
             a[m] = v;
         }
-        if (tid == 0) se[0] = 0.0;
+        if (tid == 0) se[0] = (T)0;
         __syncthreads();
-        // energy prefix se[i+1] = sum_{m<=i} |a[m]|^2 (float64): thread-serial + warp scan + CTA carry
+        // energy prefix se[i+1] = sum_{m<=i} |a[m]|^2: thread-serial + warp scan + CTA carry (carries in float64)
         {
             constexpr int IPT = ZF / ZNT;          // 16
             const int s0 = tid * IPT;
-            double run = 0.0;
+            T run = (T)0;
             for (int m = 0; m < IPT; ++m) {
                 const C2 v = a[s0 + m];
-                run += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+                run += v.x * v.x + v.y * v.y;
                 se[s0 + m + 1] = run;
             }
-            double t = run;
+            double t = (double)run;
             for (int o = 1; o < 32; o <<= 1) { const double y = shfl_up_f64(t, o); if (lane >= o) t += y; }
             if (lane == 31) wtot[warp] = t;
             __syncthreads();
-            double off = t - run;
+            double off = t - (double)run;
             for (int w = 0; w < warp; ++w) off += wtot[w];
-            for (int m = 0; m < IPT; ++m) se[s0 + m + 1] += off;
+            for (int m = 0; m < IPT; ++m) se[s0 + m + 1] = (T)((double)se[s0 + m + 1] + off);
         }
         __syncthreads();
         fft_dif<C2>(a, tw);
@@ -162,11 +168,11 @@ __global__ void __launch_bounds__(ZNT) zc_mf_kernel(const void *x, int nb, int64
         ifft_dit<C2>(a, tw);
         for (int i = tid; i < V; i += ZNT) {
             // output k0+i is the window of local samples [i, i+nr-1]
-            const double e = se[i + nr] - se[i];
+            const T e = se[i + nr] - se[i];
             const C2 y = a[nr - 1 + i];
-            double yr = (double)y.x / (double)ZF, yi = (double)y.y / (double)ZF;
+            T yr = y.x * (T)(1.0 / ZF), yi = y.y * (T)(1.0 / ZF);
             if (mode == 1) {                                   // zc_v2.py:257-271: per-branch normalisation
-                const double d = ref_norm * sqrt(e > 1e-12 ? e : 1e-12);
+                const T d = (T)ref_norm * sqrt(e > (T)1e-12 ? e : (T)1e-12);
                 yr /= d; yi /= d;
             }
             acc[i].x += yr; acc[i].y += yi;
@@ -177,9 +183,9 @@ __global__ void __launch_bounds__(ZNT) zc_mf_kernel(const void *x, int nb, int64
     for (int i = tid; i < V; i += ZNT) {
         const int64_t k = k0 + i;
         if (k >= out_len) break;
-        double yr = acc[i].x, yi = acc[i].y;
+        double yr = (double)acc[i].x, yi = (double)acc[i].y;
         if (mode == 0) {                                       // zc.py:125-126: normalise after the branch sum
-            const double p = pw[i] > 0.0 ? pw[i] : 0.0;
+            const double p = pw[i] > (T)0 ? (double)pw[i] : 0.0;
             const double d = ref_norm * sqrt(p + 1e-12);
             yr /= d; yi /= d;
         }
@@ -311,7 +317,7 @@ OFS_API int ofs_zc_matched_filter(const void *x, int32_t in_dtype, int64_t n_fra
     cudaStream_t stream = (cudaStream_t)stream_;
     double2 *tw = nullptr, *G = nullptr;
     double *rn = nullptr;
-    OFS_CUDA(cudaMallocAsync((void **)&tw, (ZF / 2) * sizeof(double2), stream));
+    OFS_CUDA(cudaMallocAsync((void **)&tw, (ZF / 2) * (sizeof(double2) + sizeof(float2)), stream));
     OFS_CUDA(cudaMallocAsync((void **)&G, ZF * sizeof(double2), stream));
     OFS_CUDA(cudaMallocAsync((void **)&rn, sizeof(double), stream));
     zc_twiddle_kernel<<<(ZF / 2 + 255) / 256, 256, 0, stream>>>(tw);
@@ -324,7 +330,8 @@ OFS_API int ofs_zc_matched_filter(const void *x, int32_t in_dtype, int64_t n_fra
     const int64_t grid = (int64_t)bpf * n_frames;
     OFS_REQUIRE(grid < (1LL << 31), "ofs_zc_matched_filter: grid too large");
     const bool dbl = in_dtype == OFS_C128 || out_f64;
-    const size_t smem = (size_t)ZF * (dbl ? 16 : 8) + (size_t)(ZF + 2 + ZF) * 8 + (size_t)ZF * 16;
+    const size_t smem = dbl ? (size_t)ZF * 16 + (size_t)(2 * ZF + 4) * 8 + (size_t)ZF * 16
+                            : (size_t)ZF * 8 + (size_t)(2 * ZF + 4) * 4 + (size_t)ZF * 8;
 #define OFS_MF_LAUNCH(T, DT)                                                                                       \
     do {                                                                                                           \
         auto kern = zc_mf_kernel<T, DT>;                                                                           \

@@ -469,3 +469,25 @@ def zc_freq_metric(rx, bin_indices, template_bins, template_energy: float, n_fft
                                        int(k.size), C.c_double(float(template_energy)), int(out_f64), _ptr(out), C.c_int64(n_off),
                                        _stream()), "ofs_zc_freq_metric")
     return out
+
+
+def zc_bank(rx, bin_indices, templates, n_fft: int = 2048, cp: int = 512):
+    """Tensor-core correlator bank: max over offsets of the zc_freq metric for every template row.
+    rx: (frames, n) or (n,) complex64; templates: (n_roots <= 128, nbins <= 64) complex.
+    -> (best_metric float32 [F, R], best_offset int32 [F, R])."""
+    t = rx if isinstance(rx, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(rx))
+    if t.dim() == 1:
+        t = t[None]
+    x = t.to(torch.complex64).to(_device()).contiguous()
+    F, n = x.shape
+    if n - (n_fft + cp) + 1 <= 0:
+        raise ValueError("Received stream is shorter than a single OFDM symbol.")
+    k = np.mod(np.asarray(bin_indices, dtype=np.int64), n_fft).astype(np.int32)
+    bins = torch.as_tensor(k).to(x.device)
+    T = torch.as_tensor(np.ascontiguousarray(np.asarray(templates, dtype=np.complex64))).to(x.device)
+    R, nb = T.shape
+    bm = torch.zeros((F, R), dtype=torch.float32, device=x.device)
+    bo = torch.zeros((F, R), dtype=torch.int32, device=x.device)
+    L.check(L.lib().ofs_zc_bank(_ptr(x), C.c_int64(F), C.c_int64(n), int(n_fft), int(cp), _ptr(bins), _ptr(T), int(nb), int(R),
+                                _ptr(bm), _ptr(bo), _stream()), "ofs_zc_bank")
+    return bm, bo

@@ -9,8 +9,9 @@
 // Two kernels per chunk of captures:
 //  1. zc_bins_kernel  (SIMT, float64 modulated prefix sums = K5's sliding DFT) writes bins^T[k][o] (k = 0..63 real
 //     parts, 64..127 imaginary parts; fp32) -- offsets contiguous, i.e. the MN-major B operand -- and E[o].
+//     zc_bins_transpose_kernel turns it into bins[o][k] (K-major, what the MMA wants).
 //  2. zc_bank_umma_kernel: one CTA per capture.  A = the templates as two K-major 128x128 fp32 matrices (rows = roots;
-//     A_re gives Re Y, A_im gives Im Y), resident in shared memory; B tiles (128 k x 128 offsets, 64 KB) arrive by four
+//     A_re gives Re Y, A_im gives Im Y), resident in shared memory; B tiles (128 offsets x 128 k, 64 KB) arrive by four
 //     tiled TMA copies with 128B swizzle; one elected thread issues 2 x 16 tcgen05.mma.kind::tf32 (M=128, N=128, K=8) into
 //     two TMEM accumulators (256 columns); tcgen05.commit signals an mbarrier; the four warps read their TMEM lane
 //     quadrant with tcgen05.ld (lane = root), form |Y|^2 / (E_r E(o)) and keep a running maximum per root in registers.
@@ -18,6 +19,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace ofs {
 
@@ -113,6 +115,21 @@ __global__ void __launch_bounds__(QB) zc_bins_kernel(const void *x, int64_t n, i
     }
 }
 
+// bins^T [cap][128 k][n_off_pad] -> bins [cap][n_off_pad][128 k]: the K-major B operand of the MMA (a tf32 MMA with an
+// MN-major B operand produced all-zero accumulators on this stack, so K-major it is).  32x32 smem tiles, coalesced both ways.
+__global__ void zc_bins_transpose_kernel(const float *binsT, float *binsK, int64_t n_off_pad)
+{
+    __shared__ float t[32][33];
+    const int64_t cap = blockIdx.z;
+    const int64_t o0 = (int64_t)blockIdx.x * 32;
+    const int k0 = blockIdx.y * 32;
+    const float *src = binsT + cap * (int64_t)BK_K * n_off_pad;
+    float *dst = binsK + cap * n_off_pad * (int64_t)BK_K;
+    for (int r = threadIdx.y; r < 32; r += 8) t[r][threadIdx.x] = src[(int64_t)(k0 + r) * n_off_pad + o0 + threadIdx.x];
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) dst[(o0 + r) * (int64_t)BK_K + k0 + threadIdx.x] = t[threadIdx.x][r];
+}
+
 // templates -> A_re (rows 0..127) and A_im (rows 128..255), K-major [256][128] fp32
 //   Re Y[r] = sum_j Tre[r,j] Bre[j] + Tim[r,j] Bim[j]      Im Y[r] = sum_j Tre[r,j] Bim[j] - Tim[r,j] Bre[j]
 __global__ void zc_bank_templates_kernel(const float2 *templ, int nbins, int n_roots, float *A, float *Er)
@@ -158,7 +175,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        "tcgen05.wait::ld.sync.aligned;"      // same asm statement: the registers are valid when it returns
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
@@ -194,7 +212,7 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity
 __global__ void __launch_bounds__(128, 1)
 zc_bank_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const float *Eo,
                     const float *Er, int64_t n_off, int64_t n_off_pad, int n_roots, int cap0, float *best_metric,
-                    int32_t *best_offset, int out_stride)
+                    int32_t *best_offset, int out_stride, float *ydbg, int dbg_mode)
 {
     extern __shared__ __align__(1024) unsigned char bsm[];
     unsigned char *sA = bsm;                              // 2 x 64 KB: A_re, A_im (each 4 K-chunks of 128 rows x 128 B)
@@ -226,31 +244,59 @@ zc_bank_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
     mbar_wait_bounded(&bars[0], 0);
 
-    // instruction descriptor: D=F32, A=B=TF32, A K-major, B MN-major, N=128, M=128
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(BK_N >> 3) << 17) |
-                           ((uint32_t)(BK_ROOTS >> 4) << 24);
+    // instruction descriptor: D=F32, A=B=TF32, both K-major, N=128, M=128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BK_N >> 3) << 17) | ((uint32_t)(BK_ROOTS >> 4) << 24);
     const float er = Er[tid];                             // this thread's root (TMEM lane = tid)
     float best = -1.f;
     int best_o = 0;
     uint32_t pb = 0, pm = 0;
     const int n_tiles = (int)((n_off + BK_N - 1) / BK_N);
-    const int rowB = (cap0 + cap) * BK_K;                 // first tensor row of this capture in bins^T
+    const int rowB = (int)((cap0 + cap) * n_off_pad);     // first tensor row (= offset) of this capture in bins[o][k]
     for (int tile = 0; tile < n_tiles; ++tile) {
         const int64_t o0 = (int64_t)tile * BK_N;
         if (tid == 0) {
             mbar_expect_tx(&bars[1], 65536);
-            for (int nc = 0; nc < 4; ++nc) tma_load_2d_b(sB + nc * 16384, &mapB, (int)o0 + nc * 32, rowB, &bars[1]);
+            for (int kc = 0; kc < 4; ++kc) tma_load_2d_b(sB + kc * 16384, &mapB, kc * 32, rowB + (int)o0, &bars[1]);
         }
         sE[tid] = Eo[(int64_t)(cap0 + cap) * n_off_pad + o0 + tid];
         mbar_wait_bounded(&bars[1], pb); pb ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (tid == 0) {
-            // K loop: 16 steps of 8 k-rows.  A (K-major SW128): chunk kc = step/4, 32 bytes per step inside the 128B row.
-            // B (MN-major SW128): one 8-row atom (1024 B) per step; the 4 N-chunks are 16 KB apart (LBO).
+        if (dbg_mode == 1) {                               // st/ld self-test: lane*1000 + column
+            const uint32_t tq0 = tmem + ((uint32_t)(warp * 32) << 16);
+            for (int c = 0; c < 256; ++c) {
+                const uint32_t v = __float_as_uint((float)(tid * 1000 + c));
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tq0 + c), "r"(v) : "memory");
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        if (tid == 0 && dbg_mode == 2) {                   // both operands K-major: D = A_re * A_im^T
+            const uint32_t idk = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BK_N >> 3) << 17) | ((uint32_t)(BK_ROOTS >> 4) << 24);
+            for (int step = 0; step < 16; ++step) {
+                const uint64_t ad = umma_desc(smem_u32(sA + (step >> 2) * 16384 + (step & 3) * 32), 16, 1024);
+                const uint64_t bd = umma_desc(smem_u32(sA + 65536 + (step >> 2) * 16384 + (step & 3) * 32), 16, 1024);
+                umma_tf32(tmem, ad, bd, idk, step > 0 ? 1u : 0u);
+                umma_tf32(tmem + BK_N, ad, bd, idk, step > 0 ? 1u : 0u);
+            }
+            umma_commit(&bars[2]);
+        }
+        if (tid == 0 && dbg_mode >= 3) {                   // MN-major B test on known data: D = A_re x A_im (plain matrix product)
+            for (int step = 0; step < 16; ++step) {
+                const uint64_t ad = umma_desc(smem_u32(sA + (step >> 2) * 16384 + (step & 3) * 32), 16, 1024);
+                const uint64_t bd = dbg_mode == 3 ? umma_desc(smem_u32(sA + 65536 + step * 1024), 16384, 1024)
+                                                  : umma_desc(smem_u32(sA + 65536 + step * 1024), 1024, 16384);
+                umma_tf32(tmem, ad, bd, idesc, step > 0 ? 1u : 0u);
+                umma_tf32(tmem + BK_N, ad, bd, idesc, step > 0 ? 1u : 0u);
+            }
+            umma_commit(&bars[2]);
+        }
+        if (tid == 0 && dbg_mode == 1) umma_commit(&bars[2]);
+        if (tid == 0 && dbg_mode == 0) {
+            // K loop: 16 steps of 8 tf32.  Both operands K-major SW128: K-chunk kc = step/4 (a 128-row x 128-byte box), 32 bytes
+            // per step inside the swizzled 128-byte row; 8-row atoms are 1024 B apart (SBO).
             for (int h = 0; h < 2; ++h) {
                 for (int step = 0; step < 16; ++step) {
                     const uint64_t ad = umma_desc(smem_u32(sA + h * 65536 + (step >> 2) * 16384 + (step & 3) * 32), 16, 1024);
-                    const uint64_t bd = umma_desc(smem_u32(sB + step * 1024), 16384, 1024);
+                    const uint64_t bd = umma_desc(smem_u32(sB + (step >> 2) * 16384 + (step & 3) * 32), 16, 1024);
                     umma_tf32(tmem + h * BK_N, ad, bd, idesc, step > 0 ? 1u : 0u);
                 }
             }
@@ -265,15 +311,21 @@ zc_bank_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             uint32_t re[32], im[32];
             tmem_ld32(tq + c, re);
             tmem_ld32(tq + BK_N + c, im);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
                 const float yr = __uint_as_float(re[q]), yi = __uint_as_float(im[q]);
                 const float den = fmaxf(er * sE[c + q], 1e-12f);
                 const float m = (yr * yr + yi * yi) / den;
                 const int64_t o = o0 + c + q;
+                if (ydbg && cap == 0) { ydbg[(int64_t)tid * n_off_pad + o] = yr; ydbg[(int64_t)(128 + tid) * n_off_pad + o] = yi; }
                 if (o < n_off && m > best) { best = m; best_o = (int)o; }
             }
+        }
+        if (ydbg && cap == 0 && tile == 0) {               // debugging aid: raw operand words as they sit in smem
+            ydbg[(int64_t)250 * n_off_pad + tid] = reinterpret_cast<const float *>(sA)[tid];
+            ydbg[(int64_t)251 * n_off_pad + tid] = reinterpret_cast<const float *>(sB)[tid];
+            ydbg[(int64_t)252 * n_off_pad + tid] = reinterpret_cast<const float *>(sA + 65536)[tid];
+            ydbg[(int64_t)253 * n_off_pad + tid] = __uint_as_float(tmem);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();                                   // TMEM and sB / sE may be overwritten by the next tile
@@ -333,11 +385,12 @@ OFS_API int ofs_zc_bank(const void *x_c64, int64_t n_frames, int64_t n, int32_t 
     if (n_frames == 0) return OFS_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     const int64_t n_off_pad = (n_off + BK_N - 1) / BK_N * BK_N;
-    int64_t chunk = (int64_t)(1ull << 30) / (BK_K * n_off_pad * 4);          // <= 1 GB of bins per chunk
+    int64_t chunk = (int64_t)(1ull << 29) / (BK_K * n_off_pad * 4);          // <= 0.5 GB of bins (x2 layouts) per chunk
     if (chunk < 1) chunk = 1;
     if (chunk > n_frames) chunk = n_frames;
-    float *binsT = nullptr, *Eo = nullptr, *A = nullptr, *Er = nullptr;
+    float *binsT = nullptr, *binsK = nullptr, *Eo = nullptr, *A = nullptr, *Er = nullptr;
     OFS_CUDA(cudaMallocAsync((void **)&binsT, (size_t)chunk * BK_K * n_off_pad * 4, stream));
+    OFS_CUDA(cudaMallocAsync((void **)&binsK, (size_t)chunk * BK_K * n_off_pad * 4, stream));
     OFS_CUDA(cudaMallocAsync((void **)&Eo, (size_t)chunk * n_off_pad * 4, stream));
     OFS_CUDA(cudaMallocAsync((void **)&A, (size_t)2 * BK_ROOTS * BK_K * 4, stream));
     OFS_CUDA(cudaMallocAsync((void **)&Er, BK_ROOTS * 4, stream));
@@ -347,7 +400,7 @@ OFS_API int ofs_zc_bank(const void *x_c64, int64_t n_frames, int64_t n, int32_t 
 
     CUtensorMap mapA, mapB;
     OFS_REQUIRE(make_map_f32(&mapA, A, BK_K, 2 * BK_ROOTS, 128), "ofs_zc_bank: cuTensorMapEncodeTiled(A) failed");
-    OFS_REQUIRE(make_map_f32(&mapB, binsT, (uint64_t)n_off_pad, (uint64_t)chunk * BK_K, 128), "ofs_zc_bank: cuTensorMapEncodeTiled(B) failed");
+    OFS_REQUIRE(make_map_f32(&mapB, binsK, BK_K, (uint64_t)chunk * n_off_pad, 128), "ofs_zc_bank: cuTensorMapEncodeTiled(B) failed");
 
     int TO = 2048;
     if (n_off_pad < TO) TO = (int)((n_off_pad + 255) / 256 * 256);
@@ -362,11 +415,36 @@ OFS_API int ofs_zc_bank(const void *x_c64, int64_t n_frames, int64_t n, int32_t 
         zc_bins_kernel<OFS_C64><<<(unsigned)(nc * tiles), QB, smem_b, stream>>>(
             reinterpret_cast<const float2 *>(x_c64) + c0 * n, n, n_fft, cp, bins, nbins, TO, n_off, n_off_pad, binsT, Eo, tiles);
         if (int rc = check_launch("zc_bins_kernel")) return rc;
+        zc_bins_transpose_kernel<<<dim3((unsigned)(n_off_pad / 32), BK_K / 32, (unsigned)nc), dim3(32, 8), 0, stream>>>(binsT, binsK, n_off_pad);
+        if (int rc = check_launch("zc_bins_transpose_kernel")) return rc;
+        float *ydbg = nullptr;
+        const char *dbg = getenv("OFS_BANK_DEBUG");
+        const char *dbgm = getenv("OFS_BANK_DEBUG_MODE");
+        const int dbg_mode = dbgm ? atoi(dbgm) : 0;
+        if (dbg && c0 == 0) OFS_CUDA(cudaMalloc((void **)&ydbg, (size_t)256 * n_off_pad * 4));
         zc_bank_umma_kernel<<<(unsigned)nc, 128, smem_u, stream>>>(mapA, mapB, Eo, Er, n_off, n_off_pad, n_roots, 0,
-                                                                 best_metric + c0 * n_roots, best_offset + c0 * n_roots, n_roots);
+                                                                 best_metric + c0 * n_roots, best_offset + c0 * n_roots, n_roots, ydbg, dbg_mode);
         if (int rc = check_launch("zc_bank_umma_kernel")) return rc;
+        if (ydbg) {   // debugging aid: dump the first capture's operands and accumulators
+            OFS_CUDA(cudaStreamSynchronize(stream));
+            auto dump = [&](const char *name, const void *dptr, size_t bytes) {
+                void *h = malloc(bytes);
+                cudaMemcpy(h, dptr, bytes, cudaMemcpyDeviceToHost);
+                char path[512];
+                snprintf(path, sizeof(path), "%s_%s.bin", dbg, name);
+                FILE *f = fopen(path, "wb");
+                if (f) { fwrite(h, 1, bytes, f); fclose(f); }
+                free(h);
+            };
+            dump("binsT", binsT, (size_t)BK_K * n_off_pad * 4);
+            dump("E", Eo, (size_t)n_off_pad * 4);
+            dump("A", A, (size_t)2 * BK_ROOTS * BK_K * 4);
+            dump("Y", ydbg, (size_t)256 * n_off_pad * 4);
+            cudaFree(ydbg);
+        }
     }
     OFS_CUDA(cudaFreeAsync(binsT, stream));
+    OFS_CUDA(cudaFreeAsync(binsK, stream));
     OFS_CUDA(cudaFreeAsync(Eo, stream));
     OFS_CUDA(cudaFreeAsync(A, stream));
     OFS_CUDA(cudaFreeAsync(Er, stream));

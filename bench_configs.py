@@ -40,7 +40,7 @@ def timeit(fn, steps=5, warmup=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
-    ap.add_argument("--cases", default="minn,combined,park,zc,zcfreq,aa64,rtl,tile")
+    ap.add_argument("--cases", default="minn,combined,park,zc,zcfreq,bank,aa64,rtl,tile")
     a = ap.parse_args()
     import numpy as np
     import torch
@@ -116,6 +116,19 @@ def main():
         ms = timeit(lambda: engine.zc_freq_metric(x, bi, tb, 62.0, out_f64=False), steps=3, warmup=2)
         emit("cfg4 zc_freq metric (62-bin sliding DFT, float64 prefix)", ms, F * n, flops=F * (n - 2559) * 62 * 2 * 16,
              note="flops ~ 62 bins x 2 (tile halo) x ~16 per modulated-prefix sample")
+        del x
+    if "bank" in cases:
+        # cfg 4 (bank): 64 ZC roots x captures x every offset, tcgen05 tf32 MMA (M=128 roots incl. padding, N=128 offsets, K=128)
+        F, n = max(int(256 * a.scale), 2), 65536
+        x = synth.make_batch_device(F, n, "sc", seed=14, device=dev, chunk=64)
+        half = 31
+        bi = np.concatenate((np.arange(-half, 0), np.arange(1, half + 1)))
+        T = np.stack([generate_zadoff_chu(r, 62) for r in range(1, 65)])
+        ms = timeit(lambda: engine.zc_bank(x, bi, T), steps=3, warmup=2)
+        noff = n - 2559
+        emit("cfg4 zc 64-root correlator bank (sliding-DFT bins + transpose + tcgen05 tf32 bank)", ms, F * n,
+             flops=F * noff * 2 * 128 * 128 * 2, note="flops = the two 128x128x128 real MMAs per 128-offset tile that are actually issued "
+             "(64 roots padded to 128 TMEM lanes); 8*K*R with K=62, R=64 would be 31744 per offset (SURVEY 8d)")
         del x
     if "aa64" in cases:
         # cfg 5: 64-antenna [A][A] combining, 8 captures per GPU x 64 antennas x 262144 c64

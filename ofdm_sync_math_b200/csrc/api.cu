@@ -32,6 +32,20 @@ int sm_count()
     return cached;
 }
 
+void keep_pool_cached()
+{
+    static bool done = false;
+    if (done) return;
+    done = true;
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    (void)cudaGetLastError();
+}
+
 int launch_metric_tile(const ofs_metric_desc *d, const void *x, void *M, void *P, void *R, cudaStream_t stream);
 int launch_metric_stripe(const ofs_metric_desc *d, const void *x, float *M, float *chunk_max, int64_t cm_stride,
                          cudaStream_t stream);

@@ -44,6 +44,7 @@ inline int check_launch(const char *what)
 }
 
 int sm_count();  // cached multiprocessor count of the current device
+void keep_pool_cached();  // stream-ordered workspace (cudaMallocAsync): keep freed blocks in the pool between calls
 
 // ---- device helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p)

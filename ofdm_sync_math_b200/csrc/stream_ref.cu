@@ -218,6 +218,7 @@ OFS_API int ofs_minn_rtl_metric(const void *x, int32_t in_dtype, int64_t n_frame
     OFS_REQUIRE(n_branches >= 1 && n >= 0 && n_frames >= 0 && frac_bits >= 0 && frac_bits < 62, "ofs_minn_rtl_metric: bad geometry");
     if (n_frames == 0 || n == 0) return OFS_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
+    keep_pool_cached();
     const int64_t ns = n_frames * n_branches;
     double *C = nullptr, *E = nullptr;
     OFS_CUDA(cudaMallocAsync((void **)&C, (size_t)ns * n * sizeof(double), stream));
@@ -252,6 +253,7 @@ OFS_API int ofs_minn_rtl_int(const int16_t *iq, int64_t n_frames, int32_t n_bran
     OFS_REQUIRE(n_branches >= 1 && n >= 0 && n_frames >= 0 && frac_bits >= 0 && frac_bits < 24, "ofs_minn_rtl_int: bad geometry");
     if (n_frames == 0 || n == 0) return OFS_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
+    keep_pool_cached();
     const int64_t ns = n_frames * n_branches;
     long long *C = nullptr, *E = nullptr;
     OFS_CUDA(cudaMallocAsync((void **)&C, (size_t)ns * n * sizeof(long long), stream));

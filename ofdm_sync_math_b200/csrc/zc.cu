@@ -315,6 +315,7 @@ OFS_API int ofs_zc_matched_filter(const void *x, int32_t in_dtype, int64_t n_fra
     OFS_REQUIRE(out_stride >= n + nr - 1, "ofs_zc_matched_filter: out_stride too small");
     if (n_frames == 0) return OFS_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
+    keep_pool_cached();
     double2 *tw = nullptr, *G = nullptr;
     double *rn = nullptr;
     OFS_CUDA(cudaMallocAsync((void **)&tw, (ZF / 2) * (sizeof(double2) + sizeof(float2)), stream));
@@ -363,6 +364,7 @@ OFS_API int ofs_zc_freq_metric(const void *x, int32_t in_dtype, int64_t n_frames
     OFS_REQUIRE(out_stride >= n_off && n_branches >= 1 && n_frames >= 0, "ofs_zc_freq_metric: bad geometry");
     if (n_frames == 0) return OFS_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
+    keep_pool_cached();
     int TO = 2048;
     if (n_off < TO) TO = (int)((n_off + 255) / 256 * 256);
     const int tiles = (int)((n_off + TO - 1) / TO);

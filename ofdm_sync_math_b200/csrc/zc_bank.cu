@@ -130,6 +130,15 @@ __global__ void zc_bins_transpose_kernel(const float *binsT, float *binsK, int64
     for (int r = threadIdx.y; r < 32; r += 8) dst[(o0 + r) * (int64_t)BK_K + k0 + threadIdx.x] = t[threadIdx.x][r];
 }
 
+__global__ void zc_bank_unpack_kernel(const unsigned long long *packed, int64_t count, float *best_metric, int32_t *best_offset)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const unsigned long long k = packed[i];
+    best_metric[i] = __uint_as_float((unsigned)(k >> 32));
+    best_offset[i] = (int32_t)(0xffffffffu - (unsigned)(k & 0xffffffffull));
+}
+
 // templates -> A_re (rows 0..127) and A_im (rows 128..255), K-major [256][128] fp32
 //   Re Y[r] = sum_j Tre[r,j] Bre[j] + Tim[r,j] Bim[j]      Im Y[r] = sum_j Tre[r,j] Bim[j] - Tim[r,j] Bre[j]
 __global__ void zc_bank_templates_kernel(const float2 *templ, int nbins, int n_roots, float *A, float *Er)
@@ -211,8 +220,8 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity
 // ------------------------------------------------------------------------------------------------ bank kernel
 __global__ void __launch_bounds__(128, 1)
 zc_bank_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const float *Eo,
-                    const float *Er, int64_t n_off, int64_t n_off_pad, int n_roots, int cap0, float *best_metric,
-                    int32_t *best_offset, int out_stride, float *ydbg, int dbg_mode)
+                    const float *Er, int64_t n_off, int64_t n_off_pad, int n_roots, int n_split,
+                    unsigned long long *best_packed, float *ydbg, int dbg_mode)
 {
     extern __shared__ __align__(1024) unsigned char bsm[];
     unsigned char *sA = bsm;                              // 2 x 64 KB: A_re, A_im (each 4 K-chunks of 128 rows x 128 B)
@@ -222,7 +231,9 @@ zc_bank_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     float *sE = reinterpret_cast<float *>(bars + 8);      // E(o) of the tile (128 floats)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cap = blockIdx.x;                           // capture inside the chunk
+    const int cap = blockIdx.x / n_split;                 // capture inside the chunk
+    const int split = blockIdx.x % n_split;               // this CTA takes tiles split, split + n_split, ...
+    constexpr int cap0 = 0;
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -252,7 +263,7 @@ zc_bank_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     uint32_t pb = 0, pm = 0;
     const int n_tiles = (int)((n_off + BK_N - 1) / BK_N);
     const int rowB = (int)((cap0 + cap) * n_off_pad);     // first tensor row (= offset) of this capture in bins[o][k]
-    for (int tile = 0; tile < n_tiles; ++tile) {
+    for (int tile = split; tile < n_tiles; tile += n_split) {
         const int64_t o0 = (int64_t)tile * BK_N;
         if (tid == 0) {
             mbar_expect_tx(&bars[1], 65536);
@@ -330,9 +341,10 @@ zc_bank_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();                                   // TMEM and sB / sE may be overwritten by the next tile
     }
-    if (tid < n_roots) {
-        best_metric[(int64_t)(cap0 + cap) * out_stride + tid] = best;
-        best_offset[(int64_t)(cap0 + cap) * out_stride + tid] = best_o;
+    // combine the splits: max metric, earliest offset on ties (metric >= 0: float bits order like unsigned)
+    if (tid < n_roots && best >= 0.f) {
+        const unsigned long long key = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned long long)(0xffffffffu - (unsigned)best_o);
+        atomicMax(best_packed + (int64_t)cap * n_roots + tid, key);
     }
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
@@ -389,6 +401,9 @@ OFS_API int ofs_zc_bank(const void *x_c64, int64_t n_frames, int64_t n, int32_t 
     if (chunk < 1) chunk = 1;
     if (chunk > n_frames) chunk = n_frames;
     float *binsT = nullptr, *binsK = nullptr, *Eo = nullptr, *A = nullptr, *Er = nullptr;
+    unsigned long long *packed = nullptr;
+    keep_pool_cached();
+    OFS_CUDA(cudaMallocAsync((void **)&packed, (size_t)chunk * n_roots * 8, stream));
     OFS_CUDA(cudaMallocAsync((void **)&binsT, (size_t)chunk * BK_K * n_off_pad * 4, stream));
     OFS_CUDA(cudaMallocAsync((void **)&binsK, (size_t)chunk * BK_K * n_off_pad * 4, stream));
     OFS_CUDA(cudaMallocAsync((void **)&Eo, (size_t)chunk * n_off_pad * 4, stream));
@@ -422,9 +437,17 @@ OFS_API int ofs_zc_bank(const void *x_c64, int64_t n_frames, int64_t n, int32_t 
         const char *dbgm = getenv("OFS_BANK_DEBUG_MODE");
         const int dbg_mode = dbgm ? atoi(dbgm) : 0;
         if (dbg && c0 == 0) OFS_CUDA(cudaMalloc((void **)&ydbg, (size_t)256 * n_off_pad * 4));
-        zc_bank_umma_kernel<<<(unsigned)nc, 128, smem_u, stream>>>(mapA, mapB, Eo, Er, n_off, n_off_pad, n_roots, 0,
-                                                                 best_metric + c0 * n_roots, best_offset + c0 * n_roots, n_roots, ydbg, dbg_mode);
+        const int n_tiles_h = (int)((n_off + BK_N - 1) / BK_N);
+        int n_split = (int)((2 * sm_count() + nc - 1) / nc);
+        if (n_split > n_tiles_h) n_split = n_tiles_h;
+        if (n_split < 1) n_split = 1;
+        OFS_CUDA(cudaMemsetAsync(packed, 0, (size_t)nc * n_roots * 8, stream));
+        zc_bank_umma_kernel<<<(unsigned)(nc * n_split), 128, smem_u, stream>>>(mapA, mapB, Eo, Er, n_off, n_off_pad, n_roots, n_split,
+                                                                           packed, ydbg, dbg_mode);
         if (int rc = check_launch("zc_bank_umma_kernel")) return rc;
+        zc_bank_unpack_kernel<<<(unsigned)((nc * n_roots + 255) / 256), 256, 0, stream>>>(packed, nc * n_roots, best_metric + c0 * n_roots,
+                                                                                      best_offset + c0 * n_roots);
+        if (int rc = check_launch("zc_bank_unpack_kernel")) return rc;
         if (ydbg) {   // debugging aid: dump the first capture's operands and accumulators
             OFS_CUDA(cudaStreamSynchronize(stream));
             auto dump = [&](const char *name, const void *dptr, size_t bytes) {
@@ -443,6 +466,7 @@ OFS_API int ofs_zc_bank(const void *x_c64, int64_t n_frames, int64_t n, int32_t 
             cudaFree(ydbg);
         }
     }
+    OFS_CUDA(cudaFreeAsync(packed, stream));
     OFS_CUDA(cudaFreeAsync(binsT, stream));
     OFS_CUDA(cudaFreeAsync(binsK, stream));
     OFS_CUDA(cudaFreeAsync(Eo, stream));

@@ -155,6 +155,21 @@ def main():
         emit("cfg1 minn_rtl integer datapath + gate FSM (reference-order streams)", ms, F * A * n, alg_bytes=F * n * (4 * A + 4 * 8 + 2),
              note="one thread per stream; int64 outputs dominate the traffic")
         del iq
+    if "agree" in cases:
+        # how often does the float32 fast path pick a different timing index than a float64 metric on the same input?
+        F, n = max(int(1024 * a.scale), 8), 262144
+        x = synth.make_batch_device(F, n, "sc", seed=1234, device=dev)
+        plan = engine.SyncPlan(F, n, "sc", 2048, "c64")
+        fast = plan.run(x).records_numpy()["timing"].copy()
+        diff, big = 0, 0
+        for f0 in range(0, F, 128):
+            r = engine.metric(x[f0:f0 + 128, None], "sc", 2048, want_pr=False, out_f64=True, path="tile")
+            t64 = engine.find_plateau_end(r.M, 512, 128, 16).cpu().numpy()
+            d = np.abs(t64 - fast[f0:f0 + 128])
+            diff += int((d != 0).sum()); big += int((d > 1).sum())
+        print(json.dumps({"case": "agreement of timing indices: float32 stripe path vs float64 tile path (same complex64 input)",
+                          "frames": F, "frames_with_different_index": diff, "of_which_differ_by_more_than_1": big}), flush=True)
+        del x, plan
     if "tile" in cases:
         F, n = max(int(512 * a.scale), 8), 262144
         x = synth.make_batch_device(F, n, "sc", seed=13, device=dev, chunk=64)[:, None]

@@ -117,6 +117,59 @@ __global__ void rtl_window_kernel(const void *x, int64_t n_streams, int64_t n, i
     }
 }
 
+// Integer window sums are exact in any order: a tile-parallel version for the int16 datapath (throughput path of the
+// RTL model).  One CTA = RT outputs of one (frame, antenna) stream: products / powers from coalesced loads, int64
+// inclusive scan in shared memory, C[n] = S[n+1] - S[n-Q+1].
+constexpr int RT = 4096, RNT = 256;
+__global__ void __launch_bounds__(RNT) rtl_window_tile_kernel(const short2 *x, int64_t n, int Q, int D, long long *C, long long *E)
+{
+    extern __shared__ long long rsm[];
+    long long *sp = rsm;                   // RT + Q + 1
+    long long *sw = rsm + (RT + Q + 1);
+    __shared__ long long wtot[2][RNT / 32];
+    const int64_t s = blockIdx.y;
+    const int64_t n0 = (int64_t)blockIdx.x * RT;
+    const short2 *xs = x + s * n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int64_t j0 = n0 - Q + 1;
+    if (j0 < 0) j0 = 0;
+    const int64_t nend = n0 + RT < n ? n0 + RT : n;
+    const int cnt = (int)(nend - j0);
+    for (int k = tid; k < cnt; k += RNT) {
+        const int64_t i = j0 + k;
+        const short2 a = xs[i];
+        long long p = 0;
+        if (i >= D) { const short2 b = xs[i - D]; p = (long long)a.x * b.x + (long long)a.y * b.y; }
+        sp[k + 1] = p;
+        sw[k + 1] = (long long)a.x * a.x + (long long)a.y * a.y;
+    }
+    if (tid == 0) { sp[0] = 0; sw[0] = 0; }
+    __syncthreads();
+    int ipt = (cnt + RNT - 1) / RNT;
+    ipt |= 1;
+    const int s0 = 1 + tid * ipt, s1 = min(s0 + ipt, cnt + 1);
+    long long ap = 0, aw = 0;
+    for (int q = s0; q < s1; ++q) { ap += sp[q]; sp[q] = ap; aw += sw[q]; sw[q] = aw; }
+    long long tp = ap, tw = aw;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long yp = __shfl_up_sync(0xffffffffu, tp, o), yw = __shfl_up_sync(0xffffffffu, tw, o);
+        if (lane >= o) { tp += yp; tw += yw; }
+    }
+    if (lane == 31) { wtot[0][warp] = tp; wtot[1][warp] = tw; }
+    __syncthreads();
+    long long op = tp - ap, ow = tw - aw;
+    for (int w = 0; w < warp; ++w) { op += wtot[0][w]; ow += wtot[1][w]; }
+    for (int q = s0; q < s1; ++q) { sp[q] += op; sw[q] += ow; }
+    __syncthreads();
+    for (int64_t i = n0 + tid; i < nend; i += RNT) {
+        int64_t lo = i - Q + 1;
+        if (lo < 0) lo = 0;
+        C[s * n + i] = sp[i + 1 - j0] - sp[lo - j0];
+        E[s * n + i] = sw[i + 1 - j0] - sw[lo - j0];
+    }
+}
+
 // Combine antennas with the hold-register gating (minn_rtl.py:632-650 / minn_antenna_path.sv:168-194):
 //   corr_recent = C[n] (n >= Q-1), corr_previous = C[n-Q] (n >= 2Q-1),
 //   energy_recent = E[n] (n >= Q-1), energy_previous = E[n-Q] (n >= 2Q-1), energy_previous2 = E[n-2Q] (n >= 3Q-1)
@@ -148,42 +201,67 @@ __global__ void rtl_combine_kernel(const T *C, const T *E, int64_t n_frames, int
     valid[idx] = i >= 3 * (int64_t)Q - 1;
 }
 
-// Smoother + threshold, sequential per frame (minn_rtl.py:707-722 / minn_preamble_detector.sv:277-325).
-__global__ void rtl_smooth_f64_kernel(const double *corr_positive, const double *energy_total, const uint8_t *valid,
-                                      int64_t n_frames, int64_t n, int shift, double thr_value, double cscale,
-                                      double *smooth, double *corr_scaled, double *energy_scaled, uint8_t *above)
+// Smoother + threshold (minn_rtl.py:707-722 / minn_preamble_detector.sv:277-325).  The shift-IIR is a true recurrence
+// (float: rounding order matters; integer: floor shift is non-linear), so it is evaluated sequentially -- but by ONE WARP
+// PER FRAME: the warp loads 32 consecutive samples coalesced and parks them in shared memory, lane 0 runs the 32
+// dependent steps out of registers (all its loads issued up front), and the warp writes the 32 results back coalesced.
+constexpr int SMW = 4;     // warps (frames) per CTA
+template <typename T>
+__global__ void __launch_bounds__(SMW * 32) rtl_smooth_kernel(const T *corr_positive, const T *energy_total, const uint8_t *valid,
+                                                              int64_t n_frames, int64_t n, int shift, T thr_value, int frac_bits,
+                                                              T *smooth, T *corr_scaled, T *energy_scaled, uint8_t *above)
 {
-    const int64_t frame = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ T sc[SMW][32];
+    __shared__ T ss[SMW][32];
+    __shared__ uint8_t sv[SMW][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t frame = (int64_t)blockIdx.x * SMW + w;
     if (frame >= n_frames) return;
-    const double denom = (double)(1LL << (shift > 0 ? shift : 0));
-    double s = 0.0;
-    for (int64_t i = 0; i < n; ++i) {
-        const int64_t o = frame * n + i;
-        const double c = corr_positive[o];
-        if (valid[o]) {
-            if (shift == 0) s = c;
-            else s = __dadd_rn(s, __ddiv_rn(__dsub_rn(c, s), denom));
+    T s = (T)0;
+    const double inv_denom = 1.0 / (double)(1LL << (shift > 0 ? shift : 0));     // exact power of two
+    const double cscale = (double)(1LL << frac_bits);
+    for (int64_t i0 = 0; i0 < n; i0 += 32) {
+        const int64_t i = i0 + lane;
+        const bool in = i < n;
+        const int64_t o = frame * n + (in ? i : 0);
+        const T c = in ? corr_positive[o] : (T)0;
+        const T e = in ? energy_total[o] : (T)0;
+        const uint8_t v = in ? valid[o] : 0;
+        sc[w][lane] = c; sv[w][lane] = v;
+        __syncwarp();
+        if (lane == 0) {
+            T cc[32]; uint8_t vv[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) { cc[q] = sc[w][q]; vv[q] = sv[w][q]; }
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                if (vv[q]) {
+                    if constexpr (std::is_floating_point<T>::value) {
+                        // smooth_val += (corr_positive - smooth_val) / denom   (minn_rtl.py:713)
+                        s = shift == 0 ? cc[q] : (T)__dadd_rn((double)s, __dmul_rn(__dsub_rn((double)cc[q], (double)s), inv_denom));
+                    } else {
+                        s = shift == 0 ? cc[q] : s + ((cc[q] - s) >> shift);        // arithmetic shift = floor (sv:294-296)
+                    }
+                }
+                ss[w][q] = s;
+            }
         }
-        smooth[o] = s;
-        const double cs = __dmul_rn(s, cscale);
-        const double es = thr_value == 0.0 ? 0.0 : __dmul_rn(energy_total[o], thr_value);
-        corr_scaled[o] = cs; energy_scaled[o] = es;
-        above[o] = valid[o] && cs >= es;
-    }
-}
-__global__ void rtl_smooth_i64_kernel(const long long *corr_positive, const long long *energy_total,
-                                      const uint8_t *valid, int64_t n_frames, int64_t n, int shift, long long thr_value,
-                                      int frac_bits, long long *smooth, uint8_t *above)
-{
-    const int64_t frame = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (frame >= n_frames) return;
-    long long s = 0;
-    for (int64_t i = 0; i < n; ++i) {
-        const int64_t o = frame * n + i;
-        const long long c = corr_positive[o];
-        if (valid[o]) s = shift == 0 ? c : s + ((c - s) >> shift);            // arithmetic shift = floor
-        smooth[o] = s;
-        above[o] = valid[o] && ((s << frac_bits) >= energy_total[o] * thr_value);
+        __syncwarp();
+        if (in) {
+            const T sm = ss[w][lane];
+            smooth[o] = sm;
+            bool ab;
+            if constexpr (std::is_floating_point<T>::value) {
+                const double cs = __dmul_rn((double)sm, cscale);
+                const double es = thr_value == (T)0 ? 0.0 : __dmul_rn((double)e, (double)thr_value);
+                corr_scaled[o] = (T)cs; energy_scaled[o] = (T)es;
+                ab = v && cs >= es;
+            } else {
+                ab = v && ((sm << frac_bits) >= e * thr_value);
+            }
+            above[o] = ab;
+        }
+        __syncwarp();
     }
 }
 
@@ -233,10 +311,10 @@ OFS_API int ofs_minn_rtl_metric(const void *x, int32_t in_dtype, int64_t n_frame
     rtl_combine_kernel<double><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(C, E, n_frames, n_branches, n, quarter_len,
                                                                                corr_total, corr_positive, energy_total, metric_valid);
     if (int rc = check_launch("rtl_combine_kernel")) return rc;
-    rtl_smooth_f64_kernel<<<(unsigned)((n_frames + bs - 1) / bs), bs, 0, stream>>>(
-        corr_positive, energy_total, metric_valid, n_frames, n, smooth_shift, (double)threshold_value,
-        (double)(1LL << frac_bits), smooth_metric, corr_scaled, energy_scaled, above);
-    if (int rc = check_launch("rtl_smooth_f64_kernel")) return rc;
+    rtl_smooth_kernel<double><<<(unsigned)((n_frames + SMW - 1) / SMW), SMW * 32, 0, stream>>>(
+        corr_positive, energy_total, metric_valid, n_frames, n, smooth_shift, (double)threshold_value, frac_bits, smooth_metric,
+        corr_scaled, energy_scaled, above);
+    if (int rc = check_launch("rtl_smooth_kernel")) return rc;
     OFS_CUDA(cudaFreeAsync(C, stream));
     OFS_CUDA(cudaFreeAsync(E, stream));
     return OFS_OK;
@@ -259,18 +337,25 @@ OFS_API int ofs_minn_rtl_int(const int16_t *iq, int64_t n_frames, int32_t n_bran
     OFS_CUDA(cudaMallocAsync((void **)&C, (size_t)ns * n * sizeof(long long), stream));
     OFS_CUDA(cudaMallocAsync((void **)&E, (size_t)ns * n * sizeof(long long), stream));
     const int bs = 32;
-    rtl_window_kernel<long long, OFS_IQ16><<<(unsigned)((ns + bs - 1) / bs), bs, 0, stream>>>(iq, ns, n, quarter_len,
-                                                                                           quarter_len + lag_extra, C, E);
+    if (quarter_len <= 8192 && ns < 65536) {
+        const size_t rsmem = (size_t)2 * (RT + quarter_len + 1) * sizeof(long long);
+        OFS_CUDA(cudaFuncSetAttribute(rtl_window_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+        rtl_window_tile_kernel<<<dim3((unsigned)((n + RT - 1) / RT), (unsigned)ns), RNT, rsmem, stream>>>(
+            reinterpret_cast<const short2 *>(iq), n, quarter_len, quarter_len + lag_extra, C, E);
+    } else {
+        rtl_window_kernel<long long, OFS_IQ16><<<(unsigned)((ns + bs - 1) / bs), bs, 0, stream>>>(iq, ns, n, quarter_len,
+                                                                                               quarter_len + lag_extra, C, E);
+    }
     if (int rc = check_launch("rtl_window_kernel")) return rc;
     const int64_t tot = n_frames * n;
     rtl_combine_kernel<long long><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(
         C, E, n_frames, n_branches, n, quarter_len, (long long *)corr_total, (long long *)corr_positive,
         (long long *)energy_total, metric_valid);
     if (int rc = check_launch("rtl_combine_kernel")) return rc;
-    rtl_smooth_i64_kernel<<<(unsigned)((n_frames + bs - 1) / bs), bs, 0, stream>>>(
+    rtl_smooth_kernel<long long><<<(unsigned)((n_frames + SMW - 1) / SMW), SMW * 32, 0, stream>>>(
         (const long long *)corr_positive, (const long long *)energy_total, metric_valid, n_frames, n, smooth_shift,
-        (long long)threshold_value, frac_bits, (long long *)smooth_metric, above);
-    if (int rc = check_launch("rtl_smooth_i64_kernel")) return rc;
+        (long long)threshold_value, frac_bits, (long long *)smooth_metric, nullptr, nullptr, above);
+    if (int rc = check_launch("rtl_smooth_kernel")) return rc;
     OFS_CUDA(cudaFreeAsync(C, stream));
     OFS_CUDA(cudaFreeAsync(E, stream));
     return OFS_OK;

@@ -40,7 +40,7 @@ def timeit(fn, steps=5, warmup=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
-    ap.add_argument("--cases", default="minn,combined,park,zc,zcfreq,bank,aa64,rtl,tile")
+    ap.add_argument("--cases", default="minn,iq16,combined,park,zc,zcfreq,bank,aa64,rtl,tile")
     a = ap.parse_args()
     import numpy as np
     import torch
@@ -70,6 +70,16 @@ def main():
         emit("cfg3 minn metric + find_minn_peak + CFO", ms, F * n, alg_bytes=F * (8 * n + 4 * (n - 2047)),
              note="roofline figure uses the metric kernel's algorithmic bytes over the whole step")
         del x, plan
+    if "iq16" in cases:
+        # cfg 2 with int16-IQ ingest (4 B/sample in, 4 B/sample out)
+        F, n = max(int(4096 * a.scale), 8), 262144
+        xi = torch.randint(-2047, 2048, (F, n, 2), dtype=torch.int16, device=dev)
+        plan = engine.SyncPlan(F, n, "sc", 2048, "iq16")
+        ms_k = timeit(lambda: plan.run_metric_only(xi))
+        ms = timeit(lambda: plan.run(xi))
+        emit("cfg2 sc metric kernel, int16-IQ input (stripe)", ms_k, F * n, alg_bytes=F * (4 * n + 4 * (n - 2047)))
+        emit("cfg2 sc metric + plateau + CFO, int16-IQ input", ms, F * n, alg_bytes=F * (4 * n + 4 * (n - 2047)))
+        del xi, plan
     if "combined" in cases:
         F, n = max(int(1024 * a.scale), 8), 1 << 19
         x = synth.make_batch_device(F, n, "minn", seed=8, device=dev, chunk=32)[:, None]
@@ -135,15 +145,21 @@ def main():
         F, A, n = max(int(8 * a.scale), 1), 64, 262144
         x = synth.make_batch_device(F * A, n, "sc", seed=12, device=dev, chunk=64).reshape(F, A, n)
 
-        def run():
-            r = engine.metric(x, "aa", 512, want_pr=True, out_f64=False, path="tile")
-            return engine.aa_events(r.M, r.P, 512, 0.15, 128, 15.36e6)
-        ms_k = timeit(lambda: engine.metric(x, "aa", 512, want_pr=True, out_f64=False, path="tile"), steps=3, warmup=2)
-        ms = timeit(run, steps=3, warmup=2)
-        emit("cfg5 sync_aa 64-antenna metric (tile kernel, antenna sum on chip)", ms_k, F * A * n, alg_bytes=F * n * (8 * A + 16),
-             note="8*A B in + M,P,R out per output sample")
-        emit("cfg5 sync_aa 64-antenna metric + gate FSM + CFO", ms, F * A * n, alg_bytes=F * n * (8 * A + 16))
-        del x
+        ms_t = timeit(lambda: engine.metric(x, "aa", 512, want_pr=True, out_f64=False, path="tile"), steps=3, warmup=2)
+        ms_k = timeit(lambda: engine.metric(x, "aa", 512, want_pr=True, out_f64=False, path="array"), steps=5, warmup=3)
+        plan = engine.AADetectPlan(F, A, n, 512, 0.15, 128, 15.36e6)
+        ms = timeit(lambda: plan.run(x), steps=5, warmup=3)
+        emit("cfg5 sync_aa 64-antenna metric, tile kernel (float64 prefix; M,P,R out)", ms_t, F * A * n, alg_bytes=F * n * (8 * A + 16))
+        emit("cfg5 sync_aa 64-antenna metric, array kernel (TMA ring, antenna sum on chip; M,P,R out)", ms_k, F * A * n,
+             alg_bytes=F * n * (8 * A + 16), note="8*A B in + M,P,R out per output sample")
+        emit("cfg5 sync_aa 64-antenna fused detector: array kernel (M,P + bitmask) + gate FSM + CFO", ms, F * A * n,
+             alg_bytes=F * n * (8 * A + 12))
+        del x, plan
+        xi = torch.randint(-2047, 2048, (F, A, n, 2), dtype=torch.int16, device=dev)
+        plan = engine.AADetectPlan(F, A, n, 512, 0.15, 128, 15.36e6, in_dtype="iq16")
+        ms = timeit(lambda: plan.run(xi), steps=5, warmup=3)
+        emit("cfg5 sync_aa 64-antenna fused detector, int16-IQ input", ms, F * A * n, alg_bytes=F * n * (4 * A + 12))
+        del xi, plan
     if "rtl" in cases:
         F, A, n = max(int(2048 * a.scale), 16), 2, 32768
         iq = torch.randint(-2047, 2048, (F, A, n, 2), dtype=torch.int16, device=dev)

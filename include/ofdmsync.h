@@ -51,6 +51,7 @@ extern "C" {
 #define OFS_PATH_AUTO 0
 #define OFS_PATH_STRIPE 1 /* fast: fp32 products, fp64 carries, TMA-fed persistent stripes (c64 / iq16 in, f32 out) */
 #define OFS_PATH_TILE 2   /* precise: float64 prefix sums, any lag / branch count / dtype */
+#define OFS_PATH_ARRAY 3  /* antenna arrays (kind AA, any branch count): branch sum on chip, TMA-fed, c64 / iq16 in, f32 out */
 
 typedef struct ofs_metric_desc {
     int32_t kind;        /* OFS_SC ... OFS_AA */
@@ -75,6 +76,8 @@ const char *ofs_last_error_string(void);
 int64_t ofs_metric_out_len(const ofs_metric_desc *d);
 /* 1 if the stripe (fast) path can serve this descriptor and these pointers (alignment rules in DESIGN.md) */
 int ofs_metric_stripe_ok(const ofs_metric_desc *d, const void *x, const void *M);
+/* 1 if the antenna-array kernel (OFS_PATH_ARRAY) can serve this descriptor / input pointer */
+int ofs_metric_array_ok(const ofs_metric_desc *d, const void *x);
 /* outputs covered by one chunk_max entry (stripe path), 256 */
 int32_t ofs_chunk_len(void);
 
@@ -148,6 +151,17 @@ typedef struct ofs_event {
  * same precision as M).  events: ofs_event[n_rows][OFS_MAX_EVENTS]; n_events: int32[n_rows]. */
 int ofs_aa_events(const ofs_rows *M, const void *P, int32_t L, double threshold, int32_t hysteresis,
                   double sample_rate, ofs_event *events, int32_t *n_events, void *stream);
+
+/* Fused antenna-array detector = sync_aa.aa_detect_streaming, sync_aa.py:458-568, for captures of n_antennas branches
+ * (complex64 or int16 IQ on the device; L in {128, 256, 512, 1024}; rows 16-byte aligned).  One pass over x: P, R and M
+ * are formed with the antenna sum kept on chip (sync_aa.py:478-479) and the (n >= L && M >= threshold) flags of
+ * sync_aa.py:511 leave the metric kernel as a bitmask, so the gate FSM never re-reads M.
+ * M float32 / P complex64 [n_frames][out_stride] (out_stride even), R optional; mask_ws: uint32[n_frames][mask_stride],
+ * mask_stride >= ceil(n/32); events / n_events as ofs_aa_events. */
+int ofs_aa_detect(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_antennas, int64_t n,
+                  int64_t x_frame_stride, int64_t x_branch_stride, int32_t L, double threshold, int32_t hysteresis,
+                  double sample_rate, float *M, void *P_c64, float *R, int64_t out_stride, uint32_t *mask_ws,
+                  int64_t mask_stride, ofs_event *events, int32_t *n_events, void *stream);
 
 /* Reference-ORDER [A][A] metric (sync_aa.py:321-386, 458-493): the reference's running-sum recurrences
  * `sum + sample - oldest` in its exact operation order, one thread per frame, float64 outputs

@@ -50,6 +50,10 @@ int launch_metric_tile(const ofs_metric_desc *d, const void *x, void *M, void *P
 int launch_metric_stripe(const ofs_metric_desc *d, const void *x, float *M, float *chunk_max, int64_t cm_stride,
                          cudaStream_t stream);
 bool stripe_supported(const ofs_metric_desc *d);
+bool array_supported(int in_dtype, int64_t n, int64_t xfs, int64_t xbs, int L, const void *x);
+int launch_metric_array(const void *x, int in_dtype, int64_t n_frames, int n_ant, int64_t n, int64_t xfs, int64_t xbs, int L,
+                        float *M, void *P, float *R, int64_t out_stride, unsigned *mask, int64_t mask_stride, double thr,
+                        cudaStream_t stream);
 
 static int check_desc(const ofs_metric_desc *d, const char *who)
 {
@@ -127,6 +131,13 @@ OFS_API int ofs_metric_stripe_ok(const ofs_metric_desc *d, const void *x, const 
     return d && check_desc(d, "ofs_metric_stripe_ok") == OFS_OK && stripe_supported(d) ? 1 : 0;
 }
 
+OFS_API int ofs_metric_array_ok(const ofs_metric_desc *d, const void *x)
+{
+    return d && check_desc(d, "ofs_metric_array_ok") == OFS_OK && d->kind == OFS_AA && !d->out_f64 &&
+                   array_supported(d->in_dtype, d->n_samples, d->x_frame_stride, d->x_branch_stride, d->symbol_len, x)
+               ? 1 : 0;
+}
+
 OFS_API int ofs_metric(const ofs_metric_desc *d, const void *x, void *M, void *P, void *R, float *chunk_max,
                        int64_t cm_stride, void *stream)
 {
@@ -138,7 +149,21 @@ OFS_API int ofs_metric(const ofs_metric_desc *d, const void *x, void *M, void *P
     OFS_REQUIRE(d->out_stride >= out_len, "ofs_metric: out_stride %lld < out_len %lld", (long long)d->out_stride,
                 (long long)out_len);
     int path = d->path;
-    if (path == OFS_PATH_AUTO) path = (stripe_supported(d) && !P && !R) ? OFS_PATH_STRIPE : OFS_PATH_TILE;
+    const bool array_ok = d->kind == OFS_AA && !d->out_f64 && !chunk_max && d->out_stride % 2 == 0 &&
+                          array_supported(d->in_dtype, d->n_samples, d->x_frame_stride, d->x_branch_stride, d->symbol_len, x) &&
+                          !(reinterpret_cast<uintptr_t>(M) & 7) && !(reinterpret_cast<uintptr_t>(P) & 15) &&
+                          !(reinterpret_cast<uintptr_t>(R) & 7);
+    if (path == OFS_PATH_AUTO) {
+        if (stripe_supported(d) && !P && !R) path = OFS_PATH_STRIPE;
+        else if (array_ok && d->n_branches >= 2) path = OFS_PATH_ARRAY;
+        else path = OFS_PATH_TILE;
+    }
+    if (path == OFS_PATH_ARRAY) {
+        OFS_REQUIRE(array_ok, "ofs_metric: the array path needs kind AA, c64/iq16 input, float32 outputs, L in {128,256,512,1024}, "
+                              "16-byte aligned rows and an even out_stride");
+        return launch_metric_array(x, d->in_dtype, d->n_frames, d->n_branches, d->n_samples, d->x_frame_stride, d->x_branch_stride,
+                                   d->symbol_len, (float *)M, P, (float *)R, d->out_stride, nullptr, 0, 0.0, (cudaStream_t)stream);
+    }
     if (path == OFS_PATH_STRIPE) {
         OFS_REQUIRE(!P && !R, "ofs_metric: the stripe path writes M only (P, R must be NULL)");
         OFS_REQUIRE(!chunk_max || cm_stride >= (d->n_samples + 255) / 256, "ofs_metric: cm_stride too small");

@@ -185,6 +185,16 @@ __device__ __forceinline__ double2 load_sample_f64(const void *base, int dtype, 
     }
 }
 
+// One packed int16 IQ word -> (float I, float Q), exactly, without I2F (quarter-rate pipe): bias both halves by 0x8000,
+// drop each 16-bit field into the mantissa of 2^23 (PRMT) and subtract 2^23 + 32768 (FADD).  LOP3 + 2 PRMT + 2 FADD.
+__device__ __forceinline__ float2 cvt_iq16(unsigned w)
+{
+    const unsigned b = w ^ 0x80008000u;
+    const unsigned lo = __byte_perm(b, 0x4b000000u, 0x7610);      // bytes {b0, b1, 0x00, 0x4b}
+    const unsigned hi = __byte_perm(b, 0x4b000000u, 0x7632);      // bytes {b2, b3, 0x00, 0x4b}
+    return make_float2(__uint_as_float(lo) - 8421376.0f, __uint_as_float(hi) - 8421376.0f);
+}
+
 inline size_t dtype_bytes(int dt) { return dt == OFS_C64 ? 8 : (dt == OFS_C128 ? 16 : 4); }
 
 }  // namespace ofs

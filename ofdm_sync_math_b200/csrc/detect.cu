@@ -19,6 +19,10 @@ namespace ofs {
 constexpr int DNT = 256;                    // threads per row-CTA
 constexpr int64_t MASK_MAX_N = 1600000;     // row length limit of the bitmask kernels (200 KB of smem)
 
+int launch_metric_array(const void *x, int in_dtype, int64_t n_frames, int n_ant, int64_t n, int64_t xfs, int64_t xbs, int L,
+                        float *M, void *P, float *R, int64_t out_stride, unsigned *mask, int64_t mask_stride, double thr,
+                        cudaStream_t stream);
+
 struct RowView {
     const void *data;
     int f64;
@@ -687,6 +691,8 @@ struct FsmParams {
     ofs_event *events;
     int32_t *n_events;
     uint8_t *gate_mask;       // ZC optional
+    const unsigned *premask;  // AA optional: above-threshold bitmask already built by the metric kernel (metric_array.cu)
+    int64_t premask_stride;   // words per row
 };
 
 template <int KIND>
@@ -719,6 +725,10 @@ __global__ void __launch_bounds__(DNT) fsm_kernel(FsmParams p)
 
     // 1. above-threshold flags of the valid samples -> bitmask
     const int64_t nround = ((n + 31) / 32) * 32;
+    if (KIND == FSM_AA && p.premask) {
+        const unsigned *pm = p.premask + row * p.premask_stride;
+        for (int64_t w = tid; w < nround / 32; w += DNT) mask[w] = pm[w];
+    } else
     for (int64_t i = tid; i < nround; i += DNT) {
         bool f = false;
         if (i < n) {
@@ -944,6 +954,24 @@ OFS_API int ofs_aa_events(const ofs_rows *M, const void *P, int32_t L, double th
     p.val = view(M); p.P = P; p.L = L; p.heff = hysteresis > 1 ? hysteresis : 1; p.thr = threshold; p.fs = sample_rate;
     p.events = events; p.n_events = n_events;
     return launch_fsm<FSM_AA>(p, M->n_rows, (cudaStream_t)stream);
+}
+
+OFS_API int ofs_aa_detect(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_antennas, int64_t n,
+                          int64_t x_frame_stride, int64_t x_branch_stride, int32_t L, double threshold, int32_t hysteresis,
+                          double sample_rate, float *M, void *P_c64, float *R, int64_t out_stride, uint32_t *mask_ws,
+                          int64_t mask_stride, ofs_event *events, int32_t *n_events, void *stream)
+{
+    OFS_REQUIRE(x && M && P_c64 && mask_ws && events && n_events && L > 0, "ofs_aa_detect: null argument");
+    OFS_REQUIRE(n_frames >= 0 && n_antennas >= 1 && n >= 0 && n_frames < (1LL << 31), "ofs_aa_detect: bad geometry");
+    if (n_frames == 0) return OFS_OK;
+    if (n == 0) { OFS_CUDA(cudaMemsetAsync(n_events, 0, (size_t)n_frames * sizeof(int32_t), (cudaStream_t)stream)); return OFS_OK; }
+    if (int rc = launch_metric_array(x, in_dtype, n_frames, n_antennas, n, x_frame_stride, x_branch_stride, L, M, P_c64, R,
+                                     out_stride, mask_ws, mask_stride, threshold, (cudaStream_t)stream))
+        return rc;
+    FsmParams p{};
+    p.val = RowView{M, 0, n, out_stride}; p.P = P_c64; p.L = L; p.heff = hysteresis > 1 ? hysteresis : 1; p.thr = threshold;
+    p.fs = sample_rate; p.events = events; p.n_events = n_events; p.premask = mask_ws; p.premask_stride = mask_stride;
+    return launch_fsm<FSM_AA>(p, n_frames, (cudaStream_t)stream);
 }
 
 OFS_API int ofs_zc_events(const ofs_rows *corr_mag, const uint8_t *valid, const uint8_t *above, int64_t mask_stride,

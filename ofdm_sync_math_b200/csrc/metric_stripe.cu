@@ -74,7 +74,7 @@ __device__ __forceinline__ void load8_smem<OFS_IQ16>(const unsigned char *stage,
         const int w[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            v[4 * i + k] = make_float2((float)(short)(w[k] & 0xffff), (float)(short)(w[k] >> 16));
+            v[4 * i + k] = cvt_iq16((unsigned)w[k]);
     }
 }
 
@@ -108,7 +108,7 @@ __device__ __forceinline__ void load8_smem_swz<OFS_IQ16>(const unsigned char *st
         const int w[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            v[4 * i + k] = make_float2((float)(short)(w[k] & 0xffff), (float)(short)(w[k] >> 16));
+            v[4 * i + k] = cvt_iq16((unsigned)w[k]);
     }
 }
 

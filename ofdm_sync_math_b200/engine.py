@@ -16,7 +16,7 @@ import torch
 from . import _lib as L
 
 KINDS = {"sc": L.OFS_SC, "sc_both": L.OFS_SC_BOTH, "minn": L.OFS_MINN, "aa": L.OFS_AA}
-PATHS = {"auto": L.OFS_PATH_AUTO, "stripe": L.OFS_PATH_STRIPE, "tile": L.OFS_PATH_TILE}
+PATHS = {"auto": L.OFS_PATH_AUTO, "stripe": L.OFS_PATH_STRIPE, "tile": L.OFS_PATH_TILE, "array": L.OFS_PATH_ARRAY}
 
 
 def _device() -> torch.device:
@@ -112,6 +112,20 @@ def metric(rx, kind: str, symbol_len: int, *, want_pr: bool = True, out_f64: boo
         L.check(lib.ofs_metric(C.byref(d), _ptr(x), C.c_void_p(M.data_ptr()), None, None, _ptr(cm), C.c_int64(cm_stride),
                                _stream()), "ofs_metric(stripe)")
         return MetricOut(M, None, None, cm, "stripe")
+    array_ok = kind == "aa" and not out_f64 and bool(lib.ofs_metric_array_ok(C.byref(d), _ptr(x)))
+    if path == "array" and not array_ok:
+        raise L.OfsError("array path cannot serve this request (kind aa, c64/iq16, float32 out, L in {128,256,512,1024}, 16-byte rows)")
+    if path == "array" or (path == "auto" and array_ok and B >= 2):
+        # antenna-array kernel (metric_array.cu): rows padded to an even pitch for its vector stores
+        pitch = (out_len + 1) // 2 * 2
+        Mb = torch.empty((F, pitch), dtype=torch.float32, device=dev)
+        Pb = torch.empty((F, pitch), dtype=torch.complex64, device=dev) if want_pr else None
+        Rb = torch.empty((F, pitch), dtype=torch.float32, device=dev) if want_pr else None
+        d.out_stride = pitch
+        d.path = L.OFS_PATH_ARRAY if path == "array" else L.OFS_PATH_AUTO
+        L.check(lib.ofs_metric(C.byref(d), _ptr(x), _ptr(Mb), _ptr(Pb), _ptr(Rb), None, C.c_int64(0), _stream()), "ofs_metric(array)")
+        cut = lambda t: None if t is None else t[:, :out_len]
+        return MetricOut(cut(Mb), cut(Pb), cut(Rb), None, "array")
     M = torch.empty((F, out_len), dtype=rdt, device=dev)
     P = torch.empty((F, out_len), dtype=cdt, device=dev) if want_pr else None
     R = torch.empty((F, out_len), dtype=rdt, device=dev) if want_pr else None
@@ -394,6 +408,37 @@ def aa_metric_reference(rx, half_len: int):
     L.check(L.lib().ofs_aa_metric_reference(_ptr(x), code, C.c_int64(F), int(A), C.c_int64(n), int(half_len), _ptr(P), _ptr(R),
                                             _ptr(M), _ptr(valid), _stream()), "ofs_aa_metric_reference")
     return P, R, M, valid
+
+
+class AADetectPlan:
+    """Fused antenna-array detector (ofs_aa_detect): captures [F, A, n] complex64 or int16-IQ [F, A, n, 2] on the device ->
+    M float32 / P complex64 [F, n] + gate events (sync_aa.py:458-568), one pass over the samples."""
+
+    def __init__(self, n_frames: int, n_antennas: int, n: int, half_len: int = 512, threshold: float = 0.15,
+                 hysteresis: int = 128, sample_rate: float = 15.36e6, in_dtype: str = "c64", want_r: bool = False):
+        dev = _device()
+        self.F, self.A, self.n, self.Lh = n_frames, n_antennas, n, half_len
+        self.thr, self.hyst, self.fs = threshold, hysteresis, sample_rate
+        self.code = {"c64": L.OFS_C64, "iq16": L.OFS_IQ16}[in_dtype]
+        self.pitch = (n + 1) // 2 * 2
+        self.Mb = torch.empty((n_frames, self.pitch), dtype=torch.float32, device=dev)
+        self.Pb = torch.empty((n_frames, self.pitch), dtype=torch.complex64, device=dev)
+        self.Rb = torch.empty((n_frames, self.pitch), dtype=torch.float32, device=dev) if want_r else None
+        self.mstride = (n + 31) // 32
+        self.mask = torch.zeros((n_frames, self.mstride), dtype=torch.int32, device=dev)
+        self.ev, self.cnt = _event_buffers(n_frames, dev)
+        self.M, self.P = self.Mb[:, :n], self.Pb[:, :n]
+        self.R = None if self.Rb is None else self.Rb[:, :n]
+
+    def run(self, x: torch.Tensor) -> None:
+        assert x.is_cuda and x.is_contiguous() and x.shape[0] == self.F and x.shape[1] == self.A and x.shape[2] == self.n
+        L.check(L.lib().ofs_aa_detect(_ptr(x), self.code, C.c_int64(self.F), int(self.A), C.c_int64(self.n), C.c_int64(self.A * self.n),
+                                      C.c_int64(self.n), int(self.Lh), C.c_double(self.thr), int(self.hyst), C.c_double(self.fs),
+                                      _ptr(self.Mb), _ptr(self.Pb), _ptr(self.Rb), C.c_int64(self.pitch), _ptr(self.mask),
+                                      C.c_int64(self.mstride), _ptr(self.ev), _ptr(self.cnt), _stream()), "ofs_aa_detect")
+
+    def events(self) -> list[np.ndarray]:
+        return _events_to_numpy(self.ev, self.cnt)
 
 
 # ------------------------------------------------------------------------------------------- minn_rtl

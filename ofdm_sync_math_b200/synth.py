@@ -87,6 +87,32 @@ def tiled_stream_host(n_samples: int, seed: int, kind: str = "sc", cir: np.ndarr
     return apply_channel_host(tx, snr_db, rng, cir, cfo_hz).astype(np.complex64)
 
 
+def aa_capture_host(n_samples: int, n_ant: int, seed: int, half_len: int = 512, snr_db: float = 10.0, cfo_hz: float = 500.0,
+                    fs: float = 15_360_000.0, gap: int = 3000, int12: bool = False):
+    """Antenna-array capture (n_ant, n_samples): [gap zeros][A][A] preambles (two identical halves of half_len samples,
+    the structure of sync_aa.build_aa_preamble, sync_aa.py:699-711) repeated, a random phase and independent AWGN per
+    antenna (sync_aa.py:591-634), CFO.  int12=True -> int16 IQ (n_ant, n_samples, 2) by the 12-bit ADC quantiser at
+    full-scale ratio 2.0 (sync_aa.py:263-291)."""
+    rng = np.random.default_rng(seed)
+    half = (rng.choice([-1.0, 1.0], half_len) + 1j * rng.choice([-1.0, 1.0], half_len)) / np.sqrt(2.0)
+    half = np.fft.ifft(np.fft.fft(half) * (np.abs(np.fft.fftfreq(half_len)) < 0.3))      # band-limit a little
+    half /= np.sqrt(np.mean(np.abs(half) ** 2))
+    unit = np.concatenate((np.zeros(gap, complex), half, half))
+    tx = np.tile(unit, n_samples // unit.size + 1)[:n_samples]
+    std = np.sqrt(1.0 / (10 ** (snr_db / 10)) / 2)
+    t = np.arange(n_samples, dtype=float)
+    rot = np.exp(1j * 2 * np.pi * cfo_hz * t / fs)
+    out = np.empty((n_ant, n_samples), dtype=np.complex64)
+    for a in range(n_ant):
+        ph = np.exp(1j * rng.uniform(0, 2 * np.pi))
+        out[a] = ((tx * ph + std * (rng.standard_normal(n_samples) + 1j * rng.standard_normal(n_samples))) * rot).astype(np.complex64)
+    if not int12:
+        return out
+    peak = np.max(np.abs(np.concatenate((out.real, out.imag), axis=None)))
+    q = np.clip(np.round(np.stack((out.real, out.imag), axis=-1) / (2.0 * peak / 2.0) * 2048.0 / 2.0), -2048, 2047)
+    return q.astype(np.int16)
+
+
 def make_batch_device(n_frames: int, n_samples: int, kind: str = "sc", seed: int = 0, device=None, n_base: int = 32,
                       chunk: int = 64):
     """[n_frames, n_samples] complex64 on the device: base frames tiled, cir1-ch1 (even) / cir2-ch1 (odd) by FFT

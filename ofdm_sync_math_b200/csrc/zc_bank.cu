@@ -1,21 +1,29 @@
-// K6: multi-root Zadoff-Chu correlator bank on the 5th-generation tensor cores (tcgen05 / TMEM / TMA).
+// K6: multi-root Zadoff-Chu correlator bank on the 5th-generation tensor cores (tcgen05 / TMEM), one fused kernel.
 //
-// Generalises zc_freq.compute_frequency_metric (zc_freq.py:62-99, one root: np.vdot(template, bins)) to a bank of
-// up to 128 roots evaluated at every candidate offset:
-//     Y[r, o] = sum_j conj(T[r, j]) * bins[j, o]          (62 used DFT bins -> K = 2 x 64 real columns)
-//     metric[r, o] = |Y|^2 / max(E_r * E(o), 1e-12),  E(o) = sum_j |bins[j, o]|^2
-// Only the maximum over offsets (value + offset) of every root is kept per capture.
+// Generalises zc_freq.compute_frequency_metric (zc_freq.py:62-99, one root: np.vdot(template, bins) at :94) to a bank of
+// up to 64 roots per pass evaluated at every candidate offset o of every capture:
+//     bins[j, o] = DFT bin k_j of x[o+cp : o+cp+N]                        (62 used bins, zc_freq.py:88-93)
+//     Y[r, o]    = sum_j conj(T[r, j]) bins[j, o]
+//     metric     = |Y|^2 / (E_r E(o)),   E(o) = sum_j |bins[j, o]|^2        (zc_freq.py:95-97)
+// and only the maximum over offsets (value + first offset) of every root is kept.
 //
-// Two kernels per chunk of captures:
-//  1. zc_bins_kernel  (SIMT, float64 modulated prefix sums = K5's sliding DFT) writes bins^T[k][o] (k = 0..63 real
-//     parts, 64..127 imaginary parts; fp32) -- offsets contiguous, i.e. the MN-major B operand -- and E[o].
-//     zc_bins_transpose_kernel turns it into bins[o][k] (K-major, what the MMA wants).
-//  2. zc_bank_umma_kernel: one CTA per capture.  A = the templates as two K-major 128x128 fp32 matrices (rows = roots;
-//     A_re gives Re Y, A_im gives Im Y), resident in shared memory; B tiles (128 offsets x 128 k, 64 KB) arrive by four
-//     tiled TMA copies with 128B swizzle; one elected thread issues 2 x 16 tcgen05.mma.kind::tf32 (M=128, N=128, K=8) into
-//     two TMEM accumulators (256 columns); tcgen05.commit signals an mbarrier; the four warps read their TMEM lane
-//     quadrant with tcgen05.ld (lane = root), form |Y|^2 / (E_r E(o)) and keep a running maximum per root in registers.
-// Accuracy: TF32 inputs (10-bit mantissa), FP32 accumulation in TMEM -> |d metric| <= 5e-3 * max(metric) (tested).
+// One persistent CTA per SM, warp-specialised (12 warps):
+//  * 8 PRODUCER warps = 4 chains x 64 bins.  A chain is a quarter of the CTA's offset range walked sample by sample with
+//    the sliding-DFT recurrence  b(o+1) = w (b(o) + x[o+cp+N] - x[o+cp]),  w = e^{+2 pi i k/N}  (one thread per bin; w is
+//    carried as a float pair hi+lo so the rotation is norm-preserving to 1e-14 and rounding errors only random-walk).
+//    Each chain owns 32 of the 128 rows of a tile: every step writes Re/Im of its bin straight into the MMA's A operand
+//    in shared memory (K-major, 128-byte swizzle, the layout a tiled TMA copy would produce) -- the bins never exist in
+//    HBM.  Row energies E(o) come from a transposed warp reduction (31 shuffles per 32 rows).
+//  * MMA issue: one elected thread (lane 0 of the first epilogue warp, one tile ahead of its epilogue work) issues 16 tcgen05.mma.kind::tf32 (M=128 offsets, N=128 = 64 roots x {Re, Im}, K=8)
+//    per tile into one of two TMEM accumulators; tcgen05.commit releases the operand buffer and publishes the accumulator.
+//  * 4 EPILOGUE warps (one per TMEM lane quadrant = one per chain): tcgen05.ld, |Y|^2 / E(o), running maximum per root
+//    in registers (tile number packed into the 10 low mantissa bits so the arg-max costs nothing per element).
+// The templates (B operand, 64 KB) arrive once per CTA by tiled TMA.  Operand and accumulator buffers are double-buffered
+// through mbarriers, so the SIMT producers, the tensor pipe and the epilogue overlap.
+// Accuracy: TF32 operands (10-bit mantissa), FP32 accumulation in TMEM, metric mantissa cut to 13 bits by the arg-max
+// packing -> |d metric| <= 5e-3 * max(metric) (tested against the float64 oracle); arg-max offsets equal on clear peaks.
+// Offsets whose in-band energy is below 1e-7 of the largest seen so far in the chain are skipped (after a burst followed
+// by exact silence the recurrence holds a rounding residue, where the reference sees 0/eps = 0).
 #include "common.cuh"
 #include <cuda.h>
 #include <string.h>
@@ -23,139 +31,14 @@
 
 namespace ofs {
 
-constexpr int BK_ROOTS = 128;     // M: roots (lanes of TMEM)
+constexpr int BK_ROWS = 128;      // M: offsets per tile (TMEM lanes) = 4 chains x 32
 constexpr int BK_K = 128;         // K: 64 real + 64 imaginary bin columns
-constexpr int BK_N = 128;         // N: offsets per tile
-constexpr int QB = 256;           // threads of the bins kernel
-
-// ------------------------------------------------------------------------------------------------ bins kernel
-template <int DT>
-__global__ void __launch_bounds__(QB) zc_bins_kernel(const void *x, int64_t n, int N, int cp, const int *bins, int nbins, int TO,
-                                                     int64_t n_off, int64_t n_off_pad, float *binsT, float *Eo, int tiles_per_cap)
-{
-    using In = typename InT<DT>::type;
-    extern __shared__ __align__(16) unsigned char qsm[];
-    const int span = TO + N - 1;
-    double2 *xs = reinterpret_cast<double2 *>(qsm);               // span
-    double2 *S = xs + span;                                        // span + 1
-    double2 *tw = S + span + 1;                                    // N
-    __shared__ double wtot[2][QB / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t cap = blockIdx.x / tiles_per_cap;
-    const int tile = blockIdx.x % tiles_per_cap;
-    const int64_t o0 = (int64_t)tile * TO;
-    const int64_t jb = o0 + cp;
-    for (int m = tid; m < N; m += QB) {
-        double s, c;
-        sincospi(-2.0 * (double)m / (double)N, &s, &c);
-        tw[m] = make_double2(c, s);
-    }
-    const In *xb = reinterpret_cast<const In *>(x) + cap * n;
-    for (int m = tid; m < span; m += QB) {
-        const int64_t j = jb + m;
-        double2 v = make_double2(0.0, 0.0);
-        if (j < n) { const In s = xb[j]; v = make_double2((double)s.x, (double)s.y); }
-        xs[m] = v;
-    }
-    if (tid == 0) S[0] = make_double2(0.0, 0.0);
-    const int ipt = ((span + QB - 1) / QB) | 1;
-    const int s0 = tid * ipt, s1 = min(s0 + ipt, span);
-    constexpr int OPT = 8;
-    double en[OPT];
-#pragma unroll
-    for (int q = 0; q < OPT; ++q) en[q] = 0.0;
-    float *bt = binsT + cap * (int64_t)BK_K * n_off_pad;
-    __syncthreads();
-    for (int jbin = 0; jbin < nbins; ++jbin) {
-        const int k = bins[jbin];
-        double rr = 0.0, ri = 0.0;
-        int ph = (int)((jb + s0) % N);
-        for (int m = s0; m < s1; ++m) {
-            const double2 w = tw[(int)(((long long)k * ph) % N)];
-            const double2 v = xs[m];
-            rr += v.x * w.x - v.y * w.y;
-            ri += v.x * w.y + v.y * w.x;
-            S[m + 1] = make_double2(rr, ri);
-            ph = ph + 1 == N ? 0 : ph + 1;
-        }
-        double tr = rr, ti = ri;
-        for (int o = 1; o < 32; o <<= 1) {
-            const double yr = shfl_up_f64(tr, o), yi = shfl_up_f64(ti, o);
-            if (lane >= o) { tr += yr; ti += yi; }
-        }
-        if (lane == 31) { wtot[0][warp] = tr; wtot[1][warp] = ti; }
-        __syncthreads();
-        double offr = tr - rr, offi = ti - ri;
-        for (int w = 0; w < warp; ++w) { offr += wtot[0][w]; offi += wtot[1][w]; }
-        for (int m = s0; m < s1; ++m) { S[m + 1].x += offr; S[m + 1].y += offi; }
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < OPT; ++q) {
-            const int i = tid + q * QB;
-            if (i < TO && o0 + i < n_off_pad) {
-                float br = 0.f, bi = 0.f;
-                if (o0 + i < n_off) {
-                    const double2 hi = S[i + N], lo = S[i];
-                    const double dr = hi.x - lo.x, di = hi.y - lo.y;
-                    const double2 w = tw[(int)(((long long)k * ((jb + i) % N)) % N)];
-                    const double b_r = dr * w.x + di * w.y, b_i = di * w.x - dr * w.y;   // conj(w) * d
-                    en[q] += b_r * b_r + b_i * b_i;
-                    br = (float)b_r; bi = (float)b_i;
-                }
-                bt[(int64_t)jbin * n_off_pad + o0 + i] = br;                 // coalesced along the offsets
-                bt[(int64_t)(64 + jbin) * n_off_pad + o0 + i] = bi;
-            }
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int q = 0; q < OPT; ++q) {
-        const int i = tid + q * QB;
-        if (i < TO && o0 + i < n_off_pad) Eo[cap * n_off_pad + o0 + i] = (o0 + i < n_off) ? (float)en[q] : 0.f;
-    }
-}
-
-// bins^T [cap][128 k][n_off_pad] -> bins [cap][n_off_pad][128 k]: the K-major B operand of the MMA (a tf32 MMA with an
-// MN-major B operand produced all-zero accumulators on this stack, so K-major it is).  32x32 smem tiles, coalesced both ways.
-__global__ void zc_bins_transpose_kernel(const float *binsT, float *binsK, int64_t n_off_pad)
-{
-    __shared__ float t[32][33];
-    const int64_t cap = blockIdx.z;
-    const int64_t o0 = (int64_t)blockIdx.x * 32;
-    const int k0 = blockIdx.y * 32;
-    const float *src = binsT + cap * (int64_t)BK_K * n_off_pad;
-    float *dst = binsK + cap * n_off_pad * (int64_t)BK_K;
-    for (int r = threadIdx.y; r < 32; r += 8) t[r][threadIdx.x] = src[(int64_t)(k0 + r) * n_off_pad + o0 + threadIdx.x];
-    __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += 8) dst[(o0 + r) * (int64_t)BK_K + k0 + threadIdx.x] = t[threadIdx.x][r];
-}
-
-__global__ void zc_bank_unpack_kernel(const unsigned long long *packed, int64_t count, float *best_metric, int32_t *best_offset)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    const unsigned long long k = packed[i];
-    best_metric[i] = __uint_as_float((unsigned)(k >> 32));
-    best_offset[i] = (int32_t)(0xffffffffu - (unsigned)(k & 0xffffffffull));
-}
-
-// templates -> A_re (rows 0..127) and A_im (rows 128..255), K-major [256][128] fp32
-//   Re Y[r] = sum_j Tre[r,j] Bre[j] + Tim[r,j] Bim[j]      Im Y[r] = sum_j Tre[r,j] Bim[j] - Tim[r,j] Bre[j]
-__global__ void zc_bank_templates_kernel(const float2 *templ, int nbins, int n_roots, float *A, float *Er)
-{
-    const int r = blockIdx.x, k = threadIdx.x;       // 128 x 128
-    float tre = 0.f, tim = 0.f;
-    const int j = k & 63;
-    if (r < n_roots && j < nbins) { const float2 t = templ[r * nbins + j]; tre = t.x; tim = t.y; }
-    const bool imag_col = k >= 64;
-    A[r * BK_K + k] = imag_col ? tim : tre;
-    A[(BK_ROOTS + r) * BK_K + k] = imag_col ? tre : -tim;
-    if (k == 0) {
-        float e = 0.f;
-        if (r < n_roots) for (int q = 0; q < nbins; ++q) { const float2 t = templ[r * nbins + q]; e += t.x * t.x + t.y * t.y; }
-        Er[r] = e;
-    }
-}
+constexpr int BK_N = 128;         // N: 64 roots x {Re Y, Im Y}
+constexpr int BK_MAXR = 64;       // roots per pass
+constexpr int BK_PW = 8, BK_EW = 4;
+constexpr int BK_THREADS = (BK_PW + BK_EW) * 32;      // 384: 65536 / 384 = 168 registers per thread
+constexpr int BK_TILE = BK_ROWS * BK_K * 4;          // 64 KB
+constexpr int BK_TILES_MAX = 1024;                   // tile number must fit the 10 packed bits
 
 // ------------------------------------------------------------------------------------------------ tcgen05 helpers
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
@@ -217,137 +100,288 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity
     __trap();
 }
 
-// ------------------------------------------------------------------------------------------------ bank kernel
-__global__ void __launch_bounds__(128, 1)
-zc_bank_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const float *Eo,
-                    const float *Er, int64_t n_off, int64_t n_off_pad, int n_roots, int n_split,
-                    unsigned long long *best_packed, float *ydbg, int dbg_mode)
+// ------------------------------------------------------------------------------------------------ prep / unpack
+// B operand [128 rows][128 k] K-major: row r < 64: [Tre_r | Tim_r] (gives Re Y_r), row 64 + r: [-Tim_r | Tre_r] (Im Y_r)
+//   Re Y = sum_j Tre Bre + Tim Bim        Im Y = sum_j Tre Bim - Tim Bre
+// plus E_r and the rotation table w_j = e^{+2 pi i k_j / N} as (hi.re, hi.im, lo.re, lo.im).
+__global__ void zc_bank_prep_kernel(const float2 *templ, int nbins, int n_roots, const int *bins, int N, float *Bmat, float *Er,
+                                    float4 *wtab)
+{
+    const int row = blockIdx.x, k = threadIdx.x;     // 128 x 128
+    const int r = row & 63, j = k & 63;
+    float tre = 0.f, tim = 0.f;
+    if (r < n_roots && j < nbins) { const float2 t = templ[r * nbins + j]; tre = t.x; tim = t.y; }
+    const bool imag_col = k >= 64, imag_row = row >= 64;
+    Bmat[row * BK_K + k] = imag_row ? (imag_col ? tre : -tim) : (imag_col ? tim : tre);
+    if (row < 64 && k == 0) {
+        float e = 0.f;
+        if (r < n_roots) for (int q = 0; q < nbins; ++q) { const float2 t = templ[r * nbins + q]; e += t.x * t.x + t.y * t.y; }
+        Er[r] = e;
+    }
+    if (row == 0 && k < 64) {
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < nbins) {
+            double sn, cs;
+            sincospi(2.0 * (double)bins[k] / (double)N, &sn, &cs);
+            const float hr = (float)cs, hi = (float)sn;
+            w = make_float4(hr, hi, (float)(cs - (double)hr), (float)(sn - (double)hi));
+        }
+        wtab[k] = w;
+    }
+}
+
+__global__ void zc_bank_unpack_kernel(const unsigned long long *packed, int64_t count, int n_roots, const float *Er,
+                                      float *best_metric, int32_t *best_offset)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const unsigned long long k = packed[i];
+    const float er = Er[i % n_roots];
+    const float v = __uint_as_float((unsigned)(k >> 32));
+    best_metric[i] = er > 0.f ? v / er : 0.f;
+    best_offset[i] = k ? (int32_t)(0xffffffffu - (unsigned)(k & 0xffffffffull)) : 0;
+}
+
+// ------------------------------------------------------------------------------------------------ fused bank kernel
+struct BankParams {
+    const float2 *x;
+    int64_t n, n_off, seg_len, n_items;
+    int N, cp, segs_per_cap, n_roots;
+    const float4 *wtab;
+    unsigned long long *best_packed;
+};
+
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v)
+{
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(BK_THREADS, 1)
+zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams p)
 {
     extern __shared__ __align__(1024) unsigned char bsm[];
-    unsigned char *sA = bsm;                              // 2 x 64 KB: A_re, A_im (each 4 K-chunks of 128 rows x 128 B)
-    unsigned char *sB = bsm + 2 * 65536;                  // 64 KB: 4 N-chunks (32 offsets) of 128 k-rows x 128 B
-    uint64_t *bars = reinterpret_cast<uint64_t *>(bsm + 3 * 65536);      // [0] A loaded, [1] B tile loaded, [2] MMA done
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
-    float *sE = reinterpret_cast<float *>(bars + 8);      // E(o) of the tile (128 floats)
+    unsigned char *sT = bsm;                                  // 64 KB templates (B operand)
+    unsigned char *sA = bsm + BK_TILE;                        // 2 x 64 KB bins tiles (A operand)
+    unsigned char *aux = bsm + 3 * BK_TILE;
+    uint64_t *a_full = reinterpret_cast<uint64_t *>(aux);     // [2]
+    uint64_t *a_empty = a_full + 2, *d_full = a_full + 4, *d_empty = a_full + 6, *t_full = a_full + 8;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(aux + 80);
+    unsigned *sBest = reinterpret_cast<unsigned *>(aux + 128);            // [64]
+    unsigned *sOff = sBest + 64;                                          // [64]
+    float *sE = reinterpret_cast<float *>(aux + 1024);                    // [4 slots][2 halves][128 rows]
+    float2 *sC = reinterpret_cast<float2 *>(aux + 1024 + 4096);           // [8 warps][2][32]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cap = blockIdx.x / n_split;                 // capture inside the chunk
-    const int split = blockIdx.x % n_split;               // this CTA takes tiles split, split + n_split, ...
-    constexpr int cap0 = 0;
-    if (warp == 0) {
+    if (warp == BK_PW) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&a_full[b], BK_PW); mbar_init(&a_empty[b], 1); mbar_init(&d_full[b], 1); mbar_init(&d_empty[b], BK_EW); }
+        mbar_init(t_full, 1);
         mbar_fence_init();
     }
+    if (tid < 64) { sBest[tid] = 0u; sOff[tid] = 0xffffffffu; }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
 
-    // templates: 8 boxes of {32 k, 128 rows}
-    if (tid == 0) {
-        mbar_expect_tx(&bars[0], 2 * 65536);
-        for (int h = 0; h < 2; ++h)
-            for (int kc = 0; kc < 4; ++kc) tma_load_2d_b(sA + h * 65536 + kc * 16384, &mapA, kc * 32, h * 128, &bars[0]);
-    }
-    mbar_wait_bounded(&bars[0], 0);
+    // geometry of one work item (capture, segment): 4 chains of Q offsets, Q a multiple of 32
+    auto item_geom = [&](int64_t item, int64_t &cap, int64_t &seg_lo, int64_t &seg_hi, int64_t &Q) {
+        cap = item / p.segs_per_cap;
+        seg_lo = (item % p.segs_per_cap) * p.seg_len;
+        seg_hi = seg_lo + p.seg_len < p.n_off ? seg_lo + p.seg_len : p.n_off;
+        Q = (((seg_hi - seg_lo + 3) >> 2) + 31) & ~(int64_t)31;
+    };
 
-    // instruction descriptor: D=F32, A=B=TF32, both K-major, N=128, M=128
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BK_N >> 3) << 17) | ((uint32_t)(BK_ROOTS >> 4) << 24);
-    const float er = Er[tid];                             // this thread's root (TMEM lane = tid)
-    float best = -1.f;
-    int best_o = 0;
-    uint32_t pb = 0, pm = 0;
-    const int n_tiles = (int)((n_off + BK_N - 1) / BK_N);
-    const int rowB = (int)((cap0 + cap) * n_off_pad);     // first tensor row (= offset) of this capture in bins[o][k]
-    for (int tile = split; tile < n_tiles; tile += n_split) {
-        const int64_t o0 = (int64_t)tile * BK_N;
-        if (tid == 0) {
-            mbar_expect_tx(&bars[1], 65536);
-            for (int kc = 0; kc < 4; ++kc) tma_load_2d_b(sB + kc * 16384, &mapB, kc * 32, rowB + (int)o0, &bars[1]);
-        }
-        sE[tid] = Eo[(int64_t)(cap0 + cap) * n_off_pad + o0 + tid];
-        mbar_wait_bounded(&bars[1], pb); pb ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (dbg_mode == 1) {                               // st/ld self-test: lane*1000 + column
-            const uint32_t tq0 = tmem + ((uint32_t)(warp * 32) << 16);
-            for (int c = 0; c < 256; ++c) {
-                const uint32_t v = __float_as_uint((float)(tid * 1000 + c));
-                asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tq0 + c), "r"(v) : "memory");
+    if (warp < BK_PW) {
+        // ============================================================ producers: sliding DFT -> A operand
+        const int g = warp >> 1, h = warp & 1;
+        const float4 w = p.wtab[32 * h + lane];
+        float2 *sc = sC + warp * 64;
+        // shared-memory byte offsets of this thread's Re column for rows with (row & 7) == m, first row of the chain
+        uint32_t base8[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+            base8[m] = (uint32_t)(h * 16384 + (32 * g) * 128 + (((lane >> 2) ^ m) << 4) + (lane & 3) * 4);
+        const uint32_t sA_u = smem_u32(sA);
+        uint32_t it = 0;
+        for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int64_t cap, seg_lo, seg_hi, Q;
+            item_geom(item, cap, seg_lo, seg_hi, Q);
+            const float2 *xc = p.x + cap * p.n;
+            const int64_t s0 = seg_lo + (int64_t)g * Q + p.cp;           // sample index of the chain's first window
+            const int n_warm = p.N / 32, n_tiles = (int)(Q / 32);
+            auto ldx = [&](int64_t idx) { return idx < p.n ? __ldg(xc + idx) : make_float2(0.f, 0.f); };
+            // feed u: warm-up blocks bring x[s0 + 32u + lane] into an empty window; real blocks the comb x[s+N] - x[s]
+            auto feed = [&](int u) {
+                if (u < n_warm) return ldx(s0 + 32 * (int64_t)u + lane);
+                const int64_t s = s0 + 32 * (int64_t)(u - n_warm) + lane;
+                const float2 a = ldx(s + p.N), b = ldx(s);
+                return make_float2(a.x - b.x, a.y - b.y);
+            };
+            float bx = 0.f, by = 0.f;
+            sc[lane] = feed(0);
+            __syncwarp();
+            const int n_blocks = n_warm + n_tiles;
+            for (int u = 0; u < n_blocks; ++u) {
+                const float2 nxt = (u + 1 < n_blocks) ? feed(u + 1) : make_float2(0.f, 0.f);
+                const float2 *cb = sc + (u & 1) * 32;
+                if (u < n_warm) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float2 c = cb[i];
+                        const float tx = bx + c.x, ty = by + c.y;
+                        bx = fmaf(tx, w.x, fmaf(-ty, w.y, fmaf(tx, w.z, -ty * w.w)));
+                        by = fmaf(tx, w.y, fmaf(ty, w.x, fmaf(tx, w.w, ty * w.z)));
+                    }
+                } else {
+                    const uint32_t buf = it & 1u;
+                    if (it >= 2) mbar_wait_bounded(&a_empty[buf], ((it >> 1) & 1u) ^ 1u);
+                    const uint32_t tb = sA_u + buf * BK_TILE;
+                    float e[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        e[i] = fmaf(bx, bx, by * by);
+                        const uint32_t a = tb + base8[i & 7] + i * 128;
+                        sts_f32(a, bx);
+                        sts_f32(a + 32768, by);
+                        const float2 c = cb[i];
+                        const float tx = bx + c.x, ty = by + c.y;
+                        bx = fmaf(tx, w.x, fmaf(-ty, w.y, fmaf(tx, w.z, -ty * w.w)));
+                        by = fmaf(tx, w.y, fmaf(ty, w.x, fmaf(tx, w.w, ty * w.z)));
+                    }
+                    // transposed reduction: lane i ends with the sum over the warp's 32 bins of e[i]
+#pragma unroll
+                    for (int s = 16; s >= 1; s >>= 1) {
+                        const bool hi = (lane & s) != 0;
+#pragma unroll
+                        for (int k = 0; k < s; ++k) {
+                            const float send = hi ? e[k] : e[k + s];
+                            const float keep = hi ? e[k + s] : e[k];
+                            e[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                        }
+                    }
+                    sE[(it & 3u) * 256 + h * 128 + 32 * g + lane] = e[0];
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cta(&a_full[buf]);
+                    ++it;
+                }
+                sc[((u + 1) & 1) * 32 + lane] = nxt;
+                __syncwarp();
             }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
-        if (tid == 0 && dbg_mode == 2) {                   // both operands K-major: D = A_re * A_im^T
-            const uint32_t idk = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BK_N >> 3) << 17) | ((uint32_t)(BK_ROOTS >> 4) << 24);
-            for (int step = 0; step < 16; ++step) {
-                const uint64_t ad = umma_desc(smem_u32(sA + (step >> 2) * 16384 + (step & 3) * 32), 16, 1024);
-                const uint64_t bd = umma_desc(smem_u32(sA + 65536 + (step >> 2) * 16384 + (step & 3) * 32), 16, 1024);
-                umma_tf32(tmem, ad, bd, idk, step > 0 ? 1u : 0u);
-                umma_tf32(tmem + BK_N, ad, bd, idk, step > 0 ? 1u : 0u);
+    } else {
+        // ============================================================ epilogue: one warp per chain / TMEM lane quadrant
+        const int g = warp - BK_PW;
+        const uint32_t tq = tmem + ((uint32_t)(g * 32) << 16);
+        const int et = tid - BK_PW * 32;                      // 0..127
+        uint32_t it = 0;
+        // MMA issue (lane 0 of the first epilogue warp), kept one tile ahead of the epilogue
+        const bool issuer = (g == 0 && lane == 0);
+        uint32_t mt = 0, tot = 0;
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BK_N >> 3) << 17) | ((uint32_t)(BK_ROWS >> 4) << 24);
+        if (issuer) {
+            for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                int64_t cap, seg_lo, seg_hi, Q;
+                item_geom(item, cap, seg_lo, seg_hi, Q);
+                tot += (uint32_t)(Q / 32);
             }
-            umma_commit(&bars[2]);
+            mbar_expect_tx(t_full, BK_TILE);
+            for (int kc = 0; kc < 4; ++kc) tma_load_2d_b(sT + kc * 16384, &mapT, kc * 32, 0, t_full);
+            mbar_wait_bounded(t_full, 0);
         }
-        if (tid == 0 && dbg_mode >= 3) {                   // MN-major B test on known data: D = A_re x A_im (plain matrix product)
-            for (int step = 0; step < 16; ++step) {
-                const uint64_t ad = umma_desc(smem_u32(sA + (step >> 2) * 16384 + (step & 3) * 32), 16, 1024);
-                const uint64_t bd = dbg_mode == 3 ? umma_desc(smem_u32(sA + 65536 + step * 1024), 16384, 1024)
-                                                  : umma_desc(smem_u32(sA + 65536 + step * 1024), 1024, 16384);
-                umma_tf32(tmem, ad, bd, idesc, step > 0 ? 1u : 0u);
-                umma_tf32(tmem + BK_N, ad, bd, idesc, step > 0 ? 1u : 0u);
-            }
-            umma_commit(&bars[2]);
-        }
-        if (tid == 0 && dbg_mode == 1) umma_commit(&bars[2]);
-        if (tid == 0 && dbg_mode == 0) {
-            // K loop: 16 steps of 8 tf32.  Both operands K-major SW128: K-chunk kc = step/4 (a 128-row x 128-byte box), 32 bytes
-            // per step inside the swizzled 128-byte row; 8-row atoms are 1024 B apart (SBO).
-            for (int h = 0; h < 2; ++h) {
+        auto issue_upto = [&](uint32_t last) {               // issue the MMAs of tiles mt .. min(last, tot-1)
+            while (mt <= last && mt < tot) {
+                const uint32_t buf = mt & 1u, ph = (mt >> 1) & 1u;
+                mbar_wait_bounded(&a_full[buf], ph);
+                if (mt >= 2) mbar_wait_bounded(&d_empty[buf], ph ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned char *At = sA + buf * BK_TILE;
+#pragma unroll
                 for (int step = 0; step < 16; ++step) {
-                    const uint64_t ad = umma_desc(smem_u32(sA + h * 65536 + (step >> 2) * 16384 + (step & 3) * 32), 16, 1024);
-                    const uint64_t bd = umma_desc(smem_u32(sB + (step >> 2) * 16384 + (step & 3) * 32), 16, 1024);
-                    umma_tf32(tmem + h * BK_N, ad, bd, idesc, step > 0 ? 1u : 0u);
+                    // K loop: 16 steps of 8 tf32; K-chunk = step/4 (a 128-row x 128-byte box), 32 bytes per step inside the
+                    // swizzled 128-byte row; 8-row atoms are 1024 B apart (SBO)
+                    const uint64_t ad = umma_desc(smem_u32(At + (step >> 2) * 16384 + (step & 3) * 32), 16, 1024);
+                    const uint64_t bd = umma_desc(smem_u32(sT + (step >> 2) * 16384 + (step & 3) * 32), 16, 1024);
+                    umma_tf32(tmem + buf * BK_N, ad, bd, idesc, step > 0 ? 1u : 0u);
+                }
+                umma_commit(&a_empty[buf]);
+                umma_commit(&d_full[buf]);
+                ++mt;
+            }
+        };
+        for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int64_t cap, seg_lo, seg_hi, Q;
+            item_geom(item, cap, seg_lo, seg_hi, Q);
+            const int n_tiles = (int)(Q / 32);
+            const int64_t q0 = seg_lo + (int64_t)g * Q + lane;          // this thread's offset in tile 0
+            unsigned best[64];
+#pragma unroll
+            for (int r = 0; r < 64; ++r) best[r] = 0u;
+            float emax = 0.f;
+            for (int t = 0; t < n_tiles; ++t, ++it) {
+                const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
+                if (issuer) issue_upto(it + 1);
+                __syncwarp();
+                mbar_wait_bounded(&d_full[buf], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const float *er = sE + (it & 3u) * 256 + 32 * g + lane;
+                const float e = er[0] + er[128];
+                emax = fmaxf(emax, __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(e))));
+                const int64_t o = q0 + 32 * (int64_t)t;
+                const float inv = (o < seg_hi && e > 1e-7f * emax && e > 0.f) ? 1.0f / e : 0.f;
+                const unsigned tb = (unsigned)(BK_TILES_MAX - 1 - t);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t re[32], im[32];
+                    tmem_ld32(tq + buf * BK_N + 32 * half, re);
+                    tmem_ld32(tq + buf * BK_N + 64 + 32 * half, im);
+                    if (half == 1) {
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cta(&d_empty[buf]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        const float yr = __uint_as_float(re[q]), yi = __uint_as_float(im[q]);
+                        const float m = fmaf(yr, yr, yi * yi) * inv;
+                        const unsigned key = (__float_as_uint(m) & 0xfffffc00u) | tb;
+                        best[32 * half + q] = max(best[32 * half + q], key);
+                    }
                 }
             }
-            umma_commit(&bars[2]);
-        }
-        __syncthreads();                                   // sE visible
-        mbar_wait_bounded(&bars[2], pm); pm ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // epilogue: this warp's TMEM lane quadrant, 32 offsets at a time; lane = root
-        const uint32_t tq = tmem + ((uint32_t)(warp * 32) << 16);
-        for (int c = 0; c < BK_N; c += 32) {
-            uint32_t re[32], im[32];
-            tmem_ld32(tq + c, re);
-            tmem_ld32(tq + BK_N + c, im);
+            // ---- reduce over the 128 epilogue threads: max key per root, then the earliest offset holding it
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-                const float yr = __uint_as_float(re[q]), yi = __uint_as_float(im[q]);
-                const float den = fmaxf(er * sE[c + q], 1e-12f);
-                const float m = (yr * yr + yi * yi) / den;
-                const int64_t o = o0 + c + q;
-                if (ydbg && cap == 0) { ydbg[(int64_t)tid * n_off_pad + o] = yr; ydbg[(int64_t)(128 + tid) * n_off_pad + o] = yi; }
-                if (o < n_off && m > best) { best = m; best_o = (int)o; }
+            for (int r = 0; r < 64; ++r)
+                if (r < p.n_roots && (best[r] & 0xfffffc00u)) atomicMax(&sBest[r], best[r]);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+            for (int r = 0; r < 64; ++r) {
+                if (r < p.n_roots && best[r] == sBest[r] && (best[r] & 0xfffffc00u)) {
+                    const int t = BK_TILES_MAX - 1 - (int)(best[r] & 0x3ffu);
+                    atomicMin(&sOff[r], (unsigned)(q0 + 32 * (int64_t)t));
+                }
             }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et < p.n_roots && sBest[et]) {
+                const unsigned long long key = ((unsigned long long)(sBest[et] & 0xfffffc00u) << 32) | (unsigned long long)(0xffffffffu - sOff[et]);
+                atomicMax(p.best_packed + cap * p.n_roots + et, key);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et < 64) { sBest[et] = 0u; sOff[et] = 0xffffffffu; }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
         }
-        if (ydbg && cap == 0 && tile == 0) {               // debugging aid: raw operand words as they sit in smem
-            ydbg[(int64_t)250 * n_off_pad + tid] = reinterpret_cast<const float *>(sA)[tid];
-            ydbg[(int64_t)251 * n_off_pad + tid] = reinterpret_cast<const float *>(sB)[tid];
-            ydbg[(int64_t)252 * n_off_pad + tid] = reinterpret_cast<const float *>(sA + 65536)[tid];
-            ydbg[(int64_t)253 * n_off_pad + tid] = __uint_as_float(tmem);
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();                                   // TMEM and sB / sE may be overwritten by the next tile
     }
-    // combine the splits: max metric, earliest offset on ties (metric >= 0: float bits order like unsigned)
-    if (tid < n_roots && best >= 0.f) {
-        const unsigned long long key = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned long long)(0xffffffffu - (unsigned)best_o);
-        atomicMax(best_packed + (int64_t)cap * n_roots + tid, key);
-    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+    if (warp == BK_PW) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
 }
 
 typedef CUresult (*EncodeTiledFn2)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -390,87 +424,75 @@ OFS_API int ofs_zc_bank(const void *x_c64, int64_t n_frames, int64_t n, int32_t 
                         void *stream_)
 {
     OFS_REQUIRE(x_c64 && bins && templ_c64 && best_metric && best_offset, "ofs_zc_bank: null argument");
-    OFS_REQUIRE(n_fft >= 2 && n_fft <= 2048 && cp >= 0, "ofs_zc_bank: n_fft must be 2..2048");
-    OFS_REQUIRE(nbins >= 1 && nbins <= 64 && n_roots >= 1 && n_roots <= BK_ROOTS, "ofs_zc_bank: nbins <= 64, n_roots <= 128");
+    OFS_REQUIRE(n_fft >= 32 && n_fft <= 65536 && n_fft % 32 == 0 && cp >= 0, "ofs_zc_bank: n_fft must be a multiple of 32 in 32..65536");
+    OFS_REQUIRE(nbins >= 1 && nbins <= 64 && n_roots >= 1 && n_roots <= 128, "ofs_zc_bank: nbins <= 64, n_roots <= 128");
     const int64_t n_off = n - ((int64_t)n_fft + cp) + 1;
     OFS_REQUIRE(n_off > 0, "Received stream is shorter than a single OFDM symbol.");
+    OFS_REQUIRE(n_off < (1LL << 31), "ofs_zc_bank: captures longer than 2^31 offsets unsupported");
     if (n_frames == 0) return OFS_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
-    const int64_t n_off_pad = (n_off + BK_N - 1) / BK_N * BK_N;
-    int64_t chunk = (int64_t)(1ull << 29) / (BK_K * n_off_pad * 4);          // <= 0.5 GB of bins (x2 layouts) per chunk
-    if (chunk < 1) chunk = 1;
-    if (chunk > n_frames) chunk = n_frames;
-    float *binsT = nullptr, *binsK = nullptr, *Eo = nullptr, *A = nullptr, *Er = nullptr;
-    unsigned long long *packed = nullptr;
     keep_pool_cached();
-    OFS_CUDA(cudaMallocAsync((void **)&packed, (size_t)chunk * n_roots * 8, stream));
-    OFS_CUDA(cudaMallocAsync((void **)&binsT, (size_t)chunk * BK_K * n_off_pad * 4, stream));
-    OFS_CUDA(cudaMallocAsync((void **)&binsK, (size_t)chunk * BK_K * n_off_pad * 4, stream));
-    OFS_CUDA(cudaMallocAsync((void **)&Eo, (size_t)chunk * n_off_pad * 4, stream));
-    OFS_CUDA(cudaMallocAsync((void **)&A, (size_t)2 * BK_ROOTS * BK_K * 4, stream));
-    OFS_CUDA(cudaMallocAsync((void **)&Er, BK_ROOTS * 4, stream));
-    OFS_CUDA(cudaMemsetAsync(binsT, 0, (size_t)chunk * BK_K * n_off_pad * 4, stream));     // pad rows 62,63,126,127 stay zero
-    zc_bank_templates_kernel<<<BK_ROOTS, BK_K, 0, stream>>>((const float2 *)templ_c64, nbins, n_roots, A, Er);
-    if (int rc = check_launch("zc_bank_templates_kernel")) return rc;
+    float *Bmat = nullptr, *Er = nullptr;
+    float4 *wtab = nullptr;
+    unsigned long long *packed = nullptr;
+    OFS_CUDA(cudaMallocAsync((void **)&Bmat, (size_t)BK_N * BK_K * 4, stream));
+    OFS_CUDA(cudaMallocAsync((void **)&Er, BK_MAXR * 4, stream));
+    OFS_CUDA(cudaMallocAsync((void **)&wtab, 64 * sizeof(float4), stream));
+    OFS_CUDA(cudaMallocAsync((void **)&packed, (size_t)n_frames * BK_MAXR * 8, stream));
 
-    CUtensorMap mapA, mapB;
-    OFS_REQUIRE(make_map_f32(&mapA, A, BK_K, 2 * BK_ROOTS, 128), "ofs_zc_bank: cuTensorMapEncodeTiled(A) failed");
-    OFS_REQUIRE(make_map_f32(&mapB, binsK, BK_K, (uint64_t)chunk * n_off_pad, 128), "ofs_zc_bank: cuTensorMapEncodeTiled(B) failed");
+    // segments: <= 1024 tiles of 128 offsets per work item; more items when the batch is small (each chain pays an
+    // n_fft-step warm-up, so segments stay >= 8 windows long)
+    const int64_t seg_max = (int64_t)BK_TILES_MAX * BK_ROWS;
+    int64_t segs = (n_off + seg_max - 1) / seg_max;
+    const int64_t want = (2LL * sm_count() + n_frames - 1) / n_frames;
+    const int64_t most = n_off / (8LL * n_fft) > 1 ? n_off / (8LL * n_fft) : 1;
+    if (want > segs) segs = want < most ? want : (most > segs ? most : segs);
+    int64_t seg_len = ((n_off + segs - 1) / segs + BK_ROWS - 1) / BK_ROWS * BK_ROWS;
+    if (seg_len > seg_max) seg_len = seg_max;
+    segs = (n_off + seg_len - 1) / seg_len;
 
-    int TO = 2048;
-    if (n_off_pad < TO) TO = (int)((n_off_pad + 255) / 256 * 256);
-    const int tiles = (int)((n_off_pad + TO - 1) / TO);
-    const int span = TO + n_fft - 1;
-    const size_t smem_b = (size_t)(span + span + 1 + n_fft) * sizeof(double2);
-    OFS_CUDA(cudaFuncSetAttribute(zc_bins_kernel<OFS_C64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-    const size_t smem_u = 3 * 65536 + 64 + 128 * sizeof(float) + 1024;
-    OFS_CUDA(cudaFuncSetAttribute(zc_bank_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_u));
-    for (int64_t c0 = 0; c0 < n_frames; c0 += chunk) {
-        const int64_t nc = (c0 + chunk <= n_frames) ? chunk : n_frames - c0;
-        zc_bins_kernel<OFS_C64><<<(unsigned)(nc * tiles), QB, smem_b, stream>>>(
-            reinterpret_cast<const float2 *>(x_c64) + c0 * n, n, n_fft, cp, bins, nbins, TO, n_off, n_off_pad, binsT, Eo, tiles);
-        if (int rc = check_launch("zc_bins_kernel")) return rc;
-        zc_bins_transpose_kernel<<<dim3((unsigned)(n_off_pad / 32), BK_K / 32, (unsigned)nc), dim3(32, 8), 0, stream>>>(binsT, binsK, n_off_pad);
-        if (int rc = check_launch("zc_bins_transpose_kernel")) return rc;
-        float *ydbg = nullptr;
-        const char *dbg = getenv("OFS_BANK_DEBUG");
-        const char *dbgm = getenv("OFS_BANK_DEBUG_MODE");
-        const int dbg_mode = dbgm ? atoi(dbgm) : 0;
-        if (dbg && c0 == 0) OFS_CUDA(cudaMalloc((void **)&ydbg, (size_t)256 * n_off_pad * 4));
-        const int n_tiles_h = (int)((n_off + BK_N - 1) / BK_N);
-        int n_split = (int)((2 * sm_count() + nc - 1) / nc);
-        if (n_split > n_tiles_h) n_split = n_tiles_h;
-        if (n_split < 1) n_split = 1;
-        OFS_CUDA(cudaMemsetAsync(packed, 0, (size_t)nc * n_roots * 8, stream));
-        zc_bank_umma_kernel<<<(unsigned)(nc * n_split), 128, smem_u, stream>>>(mapA, mapB, Eo, Er, n_off, n_off_pad, n_roots, n_split,
-                                                                           packed, ydbg, dbg_mode);
-        if (int rc = check_launch("zc_bank_umma_kernel")) return rc;
-        zc_bank_unpack_kernel<<<(unsigned)((nc * n_roots + 255) / 256), 256, 0, stream>>>(packed, nc * n_roots, best_metric + c0 * n_roots,
-                                                                                      best_offset + c0 * n_roots);
-        if (int rc = check_launch("zc_bank_unpack_kernel")) return rc;
-        if (ydbg) {   // debugging aid: dump the first capture's operands and accumulators
-            OFS_CUDA(cudaStreamSynchronize(stream));
-            auto dump = [&](const char *name, const void *dptr, size_t bytes) {
-                void *h = malloc(bytes);
-                cudaMemcpy(h, dptr, bytes, cudaMemcpyDeviceToHost);
-                char path[512];
-                snprintf(path, sizeof(path), "%s_%s.bin", dbg, name);
-                FILE *f = fopen(path, "wb");
-                if (f) { fwrite(h, 1, bytes, f); fclose(f); }
-                free(h);
-            };
-            dump("binsT", binsT, (size_t)BK_K * n_off_pad * 4);
-            dump("E", Eo, (size_t)n_off_pad * 4);
-            dump("A", A, (size_t)2 * BK_ROOTS * BK_K * 4);
-            dump("Y", ydbg, (size_t)256 * n_off_pad * 4);
-            cudaFree(ydbg);
+    const size_t smem = 3 * BK_TILE + 1024 + 4096 + 4096 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        OFS_CUDA(cudaFuncSetAttribute(zc_bank_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    for (int r0 = 0; r0 < n_roots; r0 += BK_MAXR) {
+        const int nr = n_roots - r0 < BK_MAXR ? n_roots - r0 : BK_MAXR;
+        zc_bank_prep_kernel<<<BK_N, BK_K, 0, stream>>>(reinterpret_cast<const float2 *>(templ_c64) + (size_t)r0 * nbins, nbins, nr, bins,
+                                                       n_fft, Bmat, Er, wtab);
+        if (int rc = check_launch("zc_bank_prep_kernel")) return rc;
+        CUtensorMap mapT;
+        OFS_REQUIRE(make_map_f32(&mapT, Bmat, BK_K, BK_N, 128), "ofs_zc_bank: cuTensorMapEncodeTiled failed");
+        OFS_CUDA(cudaMemsetAsync(packed, 0, (size_t)n_frames * nr * 8, stream));
+        BankParams p{};
+        p.x = reinterpret_cast<const float2 *>(x_c64); p.n = n; p.n_off = n_off; p.seg_len = seg_len; p.segs_per_cap = (int)segs;
+        p.n_items = n_frames * segs; p.N = n_fft; p.cp = cp; p.n_roots = nr; p.wtab = wtab; p.best_packed = packed;
+        const int64_t grid = p.n_items < sm_count() ? p.n_items : sm_count();
+        zc_bank_fused_kernel<<<(unsigned)grid, BK_THREADS, smem, stream>>>(mapT, p);
+        if (int rc = check_launch("zc_bank_fused_kernel")) return rc;
+        if (n_roots <= BK_MAXR) {
+            zc_bank_unpack_kernel<<<(unsigned)((n_frames * nr + 255) / 256), 256, 0, stream>>>(packed, n_frames * nr, nr, Er, best_metric,
+                                                                                           best_offset);
+            if (int rc = check_launch("zc_bank_unpack_kernel")) return rc;
+        } else {
+            // more than 64 roots: one pass per 64, results scattered into the [frames][n_roots] outputs
+            float *bm_t = nullptr; int32_t *bo_t = nullptr;
+            OFS_CUDA(cudaMallocAsync((void **)&bm_t, (size_t)n_frames * nr * 4, stream));
+            OFS_CUDA(cudaMallocAsync((void **)&bo_t, (size_t)n_frames * nr * 4, stream));
+            zc_bank_unpack_kernel<<<(unsigned)((n_frames * nr + 255) / 256), 256, 0, stream>>>(packed, n_frames * nr, nr, Er, bm_t, bo_t);
+            if (int rc = check_launch("zc_bank_unpack_kernel")) return rc;
+            OFS_CUDA(cudaMemcpy2DAsync(best_metric + r0, (size_t)n_roots * 4, bm_t, (size_t)nr * 4, (size_t)nr * 4, (size_t)n_frames,
+                                       cudaMemcpyDeviceToDevice, stream));
+            OFS_CUDA(cudaMemcpy2DAsync(best_offset + r0, (size_t)n_roots * 4, bo_t, (size_t)nr * 4, (size_t)nr * 4, (size_t)n_frames,
+                                       cudaMemcpyDeviceToDevice, stream));
+            OFS_CUDA(cudaFreeAsync(bm_t, stream));
+            OFS_CUDA(cudaFreeAsync(bo_t, stream));
         }
     }
     OFS_CUDA(cudaFreeAsync(packed, stream));
-    OFS_CUDA(cudaFreeAsync(binsT, stream));
-    OFS_CUDA(cudaFreeAsync(binsK, stream));
-    OFS_CUDA(cudaFreeAsync(Eo, stream));
-    OFS_CUDA(cudaFreeAsync(A, stream));
+    OFS_CUDA(cudaFreeAsync(Bmat, stream));
     OFS_CUDA(cudaFreeAsync(Er, stream));
+    OFS_CUDA(cudaFreeAsync(wtab, stream));
     return OFS_OK;
 }

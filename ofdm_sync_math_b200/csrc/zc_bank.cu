@@ -7,16 +7,16 @@
 //     metric     = |Y|^2 / (E_r E(o)),   E(o) = sum_j |bins[j, o]|^2        (zc_freq.py:95-97)
 // and only the maximum over offsets (value + first offset) of every root is kept.
 //
-// One persistent CTA per SM, warp-specialised (12 warps):
-//  * 8 PRODUCER warps = 4 chains x 64 bins.  A chain is a quarter of the CTA's offset range walked sample by sample with
-//    the sliding-DFT recurrence  b(o+1) = w (b(o) + x[o+cp+N] - x[o+cp]),  w = e^{+2 pi i k/N}  (one thread per bin; w is
-//    carried as a float pair hi+lo so the rotation is norm-preserving to 1e-14 and rounding errors only random-walk).
+// One persistent CTA per SM, warp-specialised (13 warps):
+//  * 4 PRODUCER warps = 4 chains x 64 bins (two bins per thread).  A chain is a quarter of the CTA's offset range walked sample by sample with
+//    the sliding-DFT recurrence  b(o+1) = w (b(o) + x[o+cp+N] - x[o+cp]),  w = e^{+2 pi i k/N}  (two bins per thread; the
+//    systematic error of the float rotation is divided out once per 32 steps, so rounding errors only random-walk).
 //    Each chain owns 32 of the 128 rows of a tile: every step writes Re/Im of its bin straight into the MMA's A operand
 //    in shared memory (K-major, 128-byte swizzle, the layout a tiled TMA copy would produce) -- the bins never exist in
 //    HBM.  Row energies E(o) come from a transposed warp reduction (31 shuffles per 32 rows).
-//  * MMA issue: one elected thread (lane 0 of the first epilogue warp, one tile ahead of its epilogue work) issues 16 tcgen05.mma.kind::tf32 (M=128 offsets, N=128 = 64 roots x {Re, Im}, K=8)
+//  * 1 MMA warp: one elected thread issues 16 tcgen05.mma.kind::tf32 (M=128 offsets, N=128 = 64 roots x {Re, Im}, K=8)
 //    per tile into one of two TMEM accumulators; tcgen05.commit releases the operand buffer and publishes the accumulator.
-//  * 4 EPILOGUE warps (one per TMEM lane quadrant = one per chain): tcgen05.ld, |Y|^2 / E(o), running maximum per root
+//  * 8 EPILOGUE warps (two per TMEM lane quadrant = chain, 32 roots each): tcgen05.ld, |Y|^2 / E(o), running maximum per root
 //    in registers (tile number packed into the 10 low mantissa bits so the arg-max costs nothing per element).
 // The templates (B operand, 64 KB) arrive once per CTA by tiled TMA.  Operand and accumulator buffers are double-buffered
 // through mbarriers, so the SIMT producers, the tensor pipe and the epilogue overlap.
@@ -35,8 +35,8 @@ constexpr int BK_ROWS = 128;      // M: offsets per tile (TMEM lanes) = 4 chains
 constexpr int BK_K = 128;         // K: 64 real + 64 imaginary bin columns
 constexpr int BK_N = 128;         // N: 64 roots x {Re Y, Im Y}
 constexpr int BK_MAXR = 64;       // roots per pass
-constexpr int BK_PW = 8, BK_EW = 4;
-constexpr int BK_THREADS = (BK_PW + BK_EW) * 32;      // 384: 65536 / 384 = 168 registers per thread
+constexpr int BK_PW = 4, BK_EW = 8;
+constexpr int BK_THREADS = (BK_PW + BK_EW + 1) * 32;  // 416 (13 warps): 128 registers per thread
 constexpr int BK_TILE = BK_ROWS * BK_K * 4;          // 64 KB
 constexpr int BK_TILES_MAX = 1024;                   // tile number must fit the 10 packed bits
 
@@ -103,7 +103,7 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity
 // ------------------------------------------------------------------------------------------------ prep / unpack
 // B operand [128 rows][128 k] K-major: row r < 64: [Tre_r | Tim_r] (gives Re Y_r), row 64 + r: [-Tim_r | Tre_r] (Im Y_r)
 //   Re Y = sum_j Tre Bre + Tim Bim        Im Y = sum_j Tre Bim - Tim Bre
-// plus E_r and the rotation table w_j = e^{+2 pi i k_j / N} as (hi.re, hi.im, lo.re, lo.im).
+// plus E_r and the rotation table: w_j = e^{+2 pi i k_j / N} rounded to float, and kappa_j (see below).
 __global__ void zc_bank_prep_kernel(const float2 *templ, int nbins, int n_roots, const int *bins, int N, float *Bmat, float *Er,
                                     float4 *wtab)
 {
@@ -123,8 +123,14 @@ __global__ void zc_bank_prep_kernel(const float2 *templ, int nbins, int n_roots,
         if (k < nbins) {
             double sn, cs;
             sincospi(2.0 * (double)bins[k] / (double)N, &sn, &cs);
+            // rotation in float, plus the per-block correction kappa = (w / w_float)^32 that takes out its systematic
+            // magnitude / phase error (2e-8 per step would otherwise leave a 6e-5 residue per sample leaving the window)
             const float hr = (float)cs, hi = (float)sn;
-            w = make_float4(hr, hi, (float)(cs - (double)hr), (float)(sn - (double)hi));
+            const double mag2 = (double)hr * hr + (double)hi * hi;
+            double qr = (cs * hr + sn * hi) / mag2, qi = (sn * hr - cs * hi) / mag2;      // w / w_float
+            double kr = 1.0, ki = 0.0;
+            for (int q = 0; q < 32; ++q) { const double t = kr * qr - ki * qi; ki = kr * qi + ki * qr; kr = t; }
+            w = make_float4(hr, hi, (float)kr, (float)ki);
         }
         wtab[k] = w;
     }
@@ -147,6 +153,7 @@ struct BankParams {
     const float2 *x;
     int64_t n, n_off, seg_len, n_items;
     int N, cp, segs_per_cap, n_roots;
+    int dbg;      // timing experiments only (OFS_BANK_DBG): 1 skip MMAs, 2 skip epilogue math, 4 skip producer math
     const float4 *wtab;
     unsigned long long *best_packed;
 };
@@ -157,7 +164,9 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar)
 }
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v)
 {
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+    // no "memory" clobber: ordered against the fence / mbarrier arrive (both asm volatile), but the compiler stays free to
+    // hoist the broadcast loads of the comb samples above these stores
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v));
 }
 
 __global__ void __launch_bounds__(BK_THREADS, 1)
@@ -172,7 +181,7 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(aux + 80);
     unsigned *sBest = reinterpret_cast<unsigned *>(aux + 128);            // [64]
     unsigned *sOff = sBest + 64;                                          // [64]
-    float *sE = reinterpret_cast<float *>(aux + 1024);                    // [4 slots][2 halves][128 rows]
+    float *sE = reinterpret_cast<float *>(aux + 1024);                    // [4 slots][128 rows]
     float2 *sC = reinterpret_cast<float2 *>(aux + 1024 + 4096);           // [8 warps][2][32]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -201,14 +210,17 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
 
     if (warp < BK_PW) {
         // ============================================================ producers: sliding DFT -> A operand
-        const int g = warp >> 1, h = warp & 1;
-        const float4 w = p.wtab[32 * h + lane];
+        // warp g = chain g; lane l carries bins l and l + 32 (two independent recurrences per thread: the dependent
+        // FADD -> FMUL -> FFMA chain of one hides behind the other)
+        const int g = warp;
+        const float4 w0 = p.wtab[lane], w1 = p.wtab[32 + lane];
         float2 *sc = sC + warp * 64;
-        // shared-memory byte offsets of this thread's Re column for rows with (row & 7) == m, first row of the chain
+        // shared-memory byte offsets of this thread's first Re column for rows with (row & 7) == m, first row of the chain;
+        // the second bin sits one K-chunk (16 KB) further, the imaginary parts two chunks (32 KB) further
         uint32_t base8[8];
 #pragma unroll
         for (int m = 0; m < 8; ++m)
-            base8[m] = (uint32_t)(h * 16384 + (32 * g) * 128 + (((lane >> 2) ^ m) << 4) + (lane & 3) * 4);
+            base8[m] = (uint32_t)((32 * g) * 128 + (((lane >> 2) ^ m) << 4) + (lane & 3) * 4);
         const uint32_t sA_u = smem_u32(sA);
         uint32_t it = 0;
         for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -219,44 +231,75 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
             const int n_warm = p.N / 32, n_tiles = (int)(Q / 32);
             auto ldx = [&](int64_t idx) { return idx < p.n ? __ldg(xc + idx) : make_float2(0.f, 0.f); };
             // feed u: warm-up blocks bring x[s0 + 32u + lane] into an empty window; real blocks the comb x[s+N] - x[s]
-            auto feed = [&](int u) {
-                if (u < n_warm) return ldx(s0 + 32 * (int64_t)u + lane);
+            auto feed = [&](int u, float2 &a, float2 &b) {      // comb sample = a - b (subtracted when it is stored)
+                if (u < n_warm) { a = ldx(s0 + 32 * (int64_t)u + lane); b = make_float2(0.f, 0.f); return; }
                 const int64_t s = s0 + 32 * (int64_t)(u - n_warm) + lane;
-                const float2 a = ldx(s + p.N), b = ldx(s);
-                return make_float2(a.x - b.x, a.y - b.y);
+                a = ldx(s + p.N); b = ldx(s);
             };
-            float bx = 0.f, by = 0.f;
-            sc[lane] = feed(0);
+            float bx0 = 0.f, by0 = 0.f, bx1 = 0.f, by1 = 0.f;
+            {
+                float2 a, b;
+                feed(0, a, b);
+                sc[lane] = make_float2(a.x - b.x, a.y - b.y);
+            }
             __syncwarp();
             const int n_blocks = n_warm + n_tiles;
             for (int u = 0; u < n_blocks; ++u) {
-                const float2 nxt = (u + 1 < n_blocks) ? feed(u + 1) : make_float2(0.f, 0.f);
-                const float2 *cb = sc + (u & 1) * 32;
+                float2 na = make_float2(0.f, 0.f), nb = na;
+                if (u + 1 < n_blocks) feed(u + 1, na, nb);             // in flight during the 32 steps below
+                const float4 *cb4 = reinterpret_cast<const float4 *>(sc + (u & 1) * 32);
                 if (u < n_warm) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float2 c = cb[i];
-                        const float tx = bx + c.x, ty = by + c.y;
-                        bx = fmaf(tx, w.x, fmaf(-ty, w.y, fmaf(tx, w.z, -ty * w.w)));
-                        by = fmaf(tx, w.y, fmaf(ty, w.x, fmaf(tx, w.w, ty * w.z)));
+                    for (int i2 = 0; i2 < 16; ++i2) {
+                        const float4 c4 = cb4[i2];
+#pragma unroll
+                        for (int v = 0; v < 2; ++v) {
+                            const float cx = v ? c4.z : c4.x, cy = v ? c4.w : c4.y;
+                            const float tx0 = bx0 + cx, ty0 = by0 + cy, tx1 = bx1 + cx, ty1 = by1 + cy;
+                            bx0 = fmaf(tx0, w0.x, -ty0 * w0.y); by0 = fmaf(tx0, w0.y, ty0 * w0.x);
+                            bx1 = fmaf(tx1, w1.x, -ty1 * w1.y); by1 = fmaf(tx1, w1.y, ty1 * w1.x);
+                        }
                     }
                 } else {
                     const uint32_t buf = it & 1u;
                     if (it >= 2) mbar_wait_bounded(&a_empty[buf], ((it >> 1) & 1u) ^ 1u);
                     const uint32_t tb = sA_u + buf * BK_TILE;
                     float e[32];
+                    if (p.dbg & 4) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        e[i] = fmaf(bx, bx, by * by);
-                        const uint32_t a = tb + base8[i & 7] + i * 128;
-                        sts_f32(a, bx);
-                        sts_f32(a + 32768, by);
-                        const float2 c = cb[i];
-                        const float tx = bx + c.x, ty = by + c.y;
-                        bx = fmaf(tx, w.x, fmaf(-ty, w.y, fmaf(tx, w.z, -ty * w.w)));
-                        by = fmaf(tx, w.y, fmaf(ty, w.x, fmaf(tx, w.w, ty * w.z)));
+                        for (int i = 0; i < 32; ++i) e[i] = 0.f;
+                    } else {
+                    // comb samples: 8 steps' worth (4 x LDS.128, warp broadcast) fetched one group ahead of their use --
+                    // ptxas will not move a shared load above a shared store on its own
+                    float4 cg[4], cn[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) cg[q] = cb4[q];
+#pragma unroll
+                    for (int grp = 0; grp < 4; ++grp) {
+                        if (grp < 3) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) cn[q] = cb4[4 * (grp + 1) + q];
+                        }
+#pragma unroll
+                        for (int ii = 0; ii < 8; ++ii) {
+                            const int i = 8 * grp + ii;
+                            e[i] = fmaf(bx0, bx0, fmaf(by0, by0, fmaf(bx1, bx1, by1 * by1)));
+                            const uint32_t a = tb + base8[ii] + i * 128;
+                            sts_f32(a, bx0);
+                            sts_f32(a + 16384, bx1);
+                            sts_f32(a + 32768, by0);
+                            sts_f32(a + 49152, by1);
+                            const float4 c4 = cg[ii >> 1];
+                            const float cx = (ii & 1) ? c4.z : c4.x, cy = (ii & 1) ? c4.w : c4.y;
+                            const float tx0 = bx0 + cx, ty0 = by0 + cy, tx1 = bx1 + cx, ty1 = by1 + cy;
+                            bx0 = fmaf(tx0, w0.x, -ty0 * w0.y); by0 = fmaf(tx0, w0.y, ty0 * w0.x);
+                            bx1 = fmaf(tx1, w1.x, -ty1 * w1.y); by1 = fmaf(tx1, w1.y, ty1 * w1.x);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) cg[q] = cn[q];
                     }
-                    // transposed reduction: lane i ends with the sum over the warp's 32 bins of e[i]
+                    }
+                    // transposed reduction: lane i ends with the sum over all 64 bins of e[i]
 #pragma unroll
                     for (int s = 16; s >= 1; s >>= 1) {
                         const bool hi = (lane & s) != 0;
@@ -267,27 +310,27 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
                             e[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
                         }
                     }
-                    sE[(it & 3u) * 256 + h * 128 + 32 * g + lane] = e[0];
+                    sE[(it & 3u) * 128 + 32 * g + lane] = e[0];
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cta(&a_full[buf]);
                     ++it;
                 }
-                sc[((u + 1) & 1) * 32 + lane] = nxt;
+                asm volatile("" : "+f"(na.x), "+f"(na.y), "+f"(nb.x), "+f"(nb.y));   // keep the subtraction (and the wait) down here
+                sc[((u + 1) & 1) * 32 + lane] = make_float2(na.x - nb.x, na.y - nb.y);
+                {   // per-block correction of the float rotation: b *= kappa
+                    const float kx0 = fmaf(bx0, w0.z, -by0 * w0.w), ky0 = fmaf(bx0, w0.w, by0 * w0.z);
+                    const float kx1 = fmaf(bx1, w1.z, -by1 * w1.w), ky1 = fmaf(bx1, w1.w, by1 * w1.z);
+                    bx0 = kx0; by0 = ky0; bx1 = kx1; by1 = ky1;
+                }
                 __syncwarp();
             }
         }
-    } else {
-        // ============================================================ epilogue: one warp per chain / TMEM lane quadrant
-        const int g = warp - BK_PW;
-        const uint32_t tq = tmem + ((uint32_t)(g * 32) << 16);
-        const int et = tid - BK_PW * 32;                      // 0..127
-        uint32_t it = 0;
-        // MMA issue (lane 0 of the first epilogue warp), kept one tile ahead of the epilogue
-        const bool issuer = (g == 0 && lane == 0);
-        uint32_t mt = 0, tot = 0;
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BK_N >> 3) << 17) | ((uint32_t)(BK_ROWS >> 4) << 24);
-        if (issuer) {
+    } else if (warp == BK_PW + BK_EW) {
+        // ============================================================ MMA issuer (one elected thread)
+        if (lane == 0) {
+            uint32_t mt = 0, tot = 0;
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BK_N >> 3) << 17) | ((uint32_t)(BK_ROWS >> 4) << 24);
             for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 int64_t cap, seg_lo, seg_hi, Q;
                 item_geom(item, cap, seg_lo, seg_hi, Q);
@@ -296,14 +339,13 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
             mbar_expect_tx(t_full, BK_TILE);
             for (int kc = 0; kc < 4; ++kc) tma_load_2d_b(sT + kc * 16384, &mapT, kc * 32, 0, t_full);
             mbar_wait_bounded(t_full, 0);
-        }
-        auto issue_upto = [&](uint32_t last) {               // issue the MMAs of tiles mt .. min(last, tot-1)
-            while (mt <= last && mt < tot) {
+            for (; mt < tot; ++mt) {
                 const uint32_t buf = mt & 1u, ph = (mt >> 1) & 1u;
                 mbar_wait_bounded(&a_full[buf], ph);
                 if (mt >= 2) mbar_wait_bounded(&d_empty[buf], ph ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const unsigned char *At = sA + buf * BK_TILE;
+                if (!(p.dbg & 1))
 #pragma unroll
                 for (int step = 0; step < 16; ++step) {
                     // K loop: 16 steps of 8 tf32; K-chunk = step/4 (a 128-row x 128-byte box), 32 bytes per step inside the
@@ -314,69 +356,74 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
                 }
                 umma_commit(&a_empty[buf]);
                 umma_commit(&d_full[buf]);
-                ++mt;
             }
-        };
+        }
+    } else {
+        // ============================================================ epilogue: two warps per chain / TMEM lane quadrant,
+        // each taking 32 of the 64 roots
+        const int ew = warp - BK_PW;                          // 0..7
+        const int g = warp & 3;                               // TMEM lane quadrant this warp may read (= warp % 4) = chain
+        const int half = ew >> 2;                             // roots 32*half .. 32*half + 31
+        const uint32_t tq = tmem + ((uint32_t)(g * 32) << 16);
+        const int et = tid - BK_PW * 32;                      // 0..255
+        uint32_t it = 0;
         for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int64_t cap, seg_lo, seg_hi, Q;
             item_geom(item, cap, seg_lo, seg_hi, Q);
             const int n_tiles = (int)(Q / 32);
             const int64_t q0 = seg_lo + (int64_t)g * Q + lane;          // this thread's offset in tile 0
-            unsigned best[64];
+            unsigned best[32];
 #pragma unroll
-            for (int r = 0; r < 64; ++r) best[r] = 0u;
+            for (int r = 0; r < 32; ++r) best[r] = 0u;
             float emax = 0.f;
             for (int t = 0; t < n_tiles; ++t, ++it) {
                 const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
-                if (issuer) issue_upto(it + 1);
-                __syncwarp();
                 mbar_wait_bounded(&d_full[buf], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const float *er = sE + (it & 3u) * 256 + 32 * g + lane;
-                const float e = er[0] + er[128];
+                const float e = sE[(it & 3u) * 128 + 32 * g + lane];
                 emax = fmaxf(emax, __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(e))));
                 const int64_t o = q0 + 32 * (int64_t)t;
                 const float inv = (o < seg_hi && e > 1e-7f * emax && e > 0.f) ? 1.0f / e : 0.f;
                 const unsigned tb = (unsigned)(BK_TILES_MAX - 1 - t);
+                uint32_t re[32], im[32];
+                if (p.dbg & 2) {
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t re[32], im[32];
-                    tmem_ld32(tq + buf * BK_N + 32 * half, re);
-                    tmem_ld32(tq + buf * BK_N + 64 + 32 * half, im);
-                    if (half == 1) {
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_cta(&d_empty[buf]);
-                    }
+                    for (int q = 0; q < 32; ++q) re[q] = im[q] = 0u;
+                } else {
+                tmem_ld32(tq + buf * BK_N + 32 * half, re);
+                tmem_ld32(tq + buf * BK_N + 64 + 32 * half, im);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cta(&d_empty[buf]);
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) {
-                        const float yr = __uint_as_float(re[q]), yi = __uint_as_float(im[q]);
-                        const float m = fmaf(yr, yr, yi * yi) * inv;
-                        const unsigned key = (__float_as_uint(m) & 0xfffffc00u) | tb;
-                        best[32 * half + q] = max(best[32 * half + q], key);
-                    }
+                for (int q = 0; q < 32; ++q) {
+                    const float yr = __uint_as_float(re[q]), yi = __uint_as_float(im[q]);
+                    const float m = fmaf(yr, yr, yi * yi) * inv;
+                    const unsigned key = (__float_as_uint(m) & 0xfffffc00u) | tb;
+                    best[q] = max(best[q], key);
                 }
             }
-            // ---- reduce over the 128 epilogue threads: max key per root, then the earliest offset holding it
+            // ---- reduce over the 256 epilogue threads: max key per root, then the earliest offset holding it
 #pragma unroll
-            for (int r = 0; r < 64; ++r)
-                if (r < p.n_roots && (best[r] & 0xfffffc00u)) atomicMax(&sBest[r], best[r]);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int r = 0; r < 32; ++r)
+                if (32 * half + r < p.n_roots && (best[r] & 0xfffffc00u)) atomicMax(&sBest[32 * half + r], best[r]);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
-            for (int r = 0; r < 64; ++r) {
-                if (r < p.n_roots && best[r] == sBest[r] && (best[r] & 0xfffffc00u)) {
+            for (int r = 0; r < 32; ++r) {
+                if (32 * half + r < p.n_roots && best[r] == sBest[32 * half + r] && (best[r] & 0xfffffc00u)) {
                     const int t = BK_TILES_MAX - 1 - (int)(best[r] & 0x3ffu);
-                    atomicMin(&sOff[r], (unsigned)(q0 + 32 * (int64_t)t));
+                    atomicMin(&sOff[32 * half + r], (unsigned)(q0 + 32 * (int64_t)t));
                 }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (et < p.n_roots && sBest[et]) {
                 const unsigned long long key = ((unsigned long long)(sBest[et] & 0xfffffc00u) << 32) | (unsigned long long)(0xffffffffu - sOff[et]);
                 atomicMax(p.best_packed + cap * p.n_roots + et, key);
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (et < 64) { sBest[et] = 0u; sOff[et] = 0xffffffffu; }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -467,6 +514,7 @@ OFS_API int ofs_zc_bank(const void *x_c64, int64_t n_frames, int64_t n, int32_t 
         OFS_CUDA(cudaMemsetAsync(packed, 0, (size_t)n_frames * nr * 8, stream));
         BankParams p{};
         p.x = reinterpret_cast<const float2 *>(x_c64); p.n = n; p.n_off = n_off; p.seg_len = seg_len; p.segs_per_cap = (int)segs;
+        { const char *dbg = getenv("OFS_BANK_DBG"); p.dbg = dbg ? atoi(dbg) : 0; }
         p.n_items = n_frames * segs; p.N = n_fft; p.cp = cp; p.n_roots = nr; p.wtab = wtab; p.best_packed = packed;
         const int64_t grid = p.n_items < sm_count() ? p.n_items : sm_count();
         zc_bank_fused_kernel<<<(unsigned)grid, BK_THREADS, smem, stream>>>(mapT, p);

@@ -8,15 +8,15 @@
 // and only the maximum over offsets (value + first offset) of every root is kept.
 //
 // One persistent CTA per SM, warp-specialised (13 warps):
-//  * 4 PRODUCER warps = 4 chains x 64 bins (two bins per thread).  A chain is a quarter of the CTA's offset range walked sample by sample with
+//  * 8 PRODUCER warps = 8 chains x 64 bins (two bins per thread).  A chain is an eighth of the CTA's offset range walked sample by sample with
 //    the sliding-DFT recurrence  b(o+1) = w (b(o) + x[o+cp+N] - x[o+cp]),  w = e^{+2 pi i k/N}  (two bins per thread; the
 //    systematic error of the float rotation is divided out once per 32 steps, so rounding errors only random-walk).
-//    Each chain owns 32 of the 128 rows of a tile: every step writes Re/Im of its bin straight into the MMA's A operand
+//    Each chain owns 16 of the 128 rows of a tile: every step writes Re/Im of its bin straight into the MMA's A operand
 //    in shared memory (K-major, 128-byte swizzle, the layout a tiled TMA copy would produce) -- the bins never exist in
-//    HBM.  Row energies E(o) come from a transposed warp reduction (31 shuffles per 32 rows).
+//    HBM.  Row energies E(o) come from a transposed warp reduction (16 shuffles per 16 rows).
 //  * 1 MMA warp: one elected thread issues 16 tcgen05.mma.kind::tf32 (M=128 offsets, N=128 = 64 roots x {Re, Im}, K=8)
 //    per tile into one of two TMEM accumulators; tcgen05.commit releases the operand buffer and publishes the accumulator.
-//  * 8 EPILOGUE warps (two per TMEM lane quadrant = chain, 32 roots each): tcgen05.ld, |Y|^2 / E(o), running maximum per root
+//  * 4 EPILOGUE warps (one per TMEM lane quadrant = two chains): tcgen05.ld, |Y|^2 / E(o), running maximum per root
 //    in registers (tile number packed into the 10 low mantissa bits so the arg-max costs nothing per element).
 // The templates (B operand, 64 KB) arrive once per CTA by tiled TMA.  Operand and accumulator buffers are double-buffered
 // through mbarriers, so the SIMT producers, the tensor pipe and the epilogue overlap.
@@ -31,11 +31,12 @@
 
 namespace ofs {
 
-constexpr int BK_ROWS = 128;      // M: offsets per tile (TMEM lanes) = 4 chains x 32
+constexpr int BK_ROWS = 128;      // M: offsets per tile (TMEM lanes) = 8 chains x 16
 constexpr int BK_K = 128;         // K: 64 real + 64 imaginary bin columns
 constexpr int BK_N = 128;         // N: 64 roots x {Re Y, Im Y}
 constexpr int BK_MAXR = 64;       // roots per pass
-constexpr int BK_PW = 4, BK_EW = 8;
+constexpr int BK_PW = 8, BK_EW = 4;
+constexpr int BK_CH = 8;          // chains per work item, 16 rows of every tile each
 constexpr int BK_THREADS = (BK_PW + BK_EW + 1) * 32;  // 416 (13 warps): 128 registers per thread
 constexpr int BK_TILE = BK_ROWS * BK_K * 4;          // 64 KB
 constexpr int BK_TILES_MAX = 1024;                   // tile number must fit the 10 packed bits
@@ -73,6 +74,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
 }
@@ -153,6 +165,7 @@ struct BankParams {
     const float2 *x;
     int64_t n, n_off, seg_len, n_items;
     int N, cp, segs_per_cap, n_roots;
+    long long *prof;   // OFS_BANK_DBG & 8: per-CTA cycle counters [grid][16]
     int dbg;      // timing experiments only (OFS_BANK_DBG): 1 skip MMAs, 2 skip epilogue math, 4 skip producer math
     const float4 *wtab;
     unsigned long long *best_packed;
@@ -205,13 +218,13 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
         cap = item / p.segs_per_cap;
         seg_lo = (item % p.segs_per_cap) * p.seg_len;
         seg_hi = seg_lo + p.seg_len < p.n_off ? seg_lo + p.seg_len : p.n_off;
-        Q = (((seg_hi - seg_lo + 3) >> 2) + 31) & ~(int64_t)31;
+        Q = (((seg_hi - seg_lo + BK_CH - 1) / BK_CH) + 31) & ~(int64_t)31;
     };
 
     if (warp < BK_PW) {
         // ============================================================ producers: sliding DFT -> A operand
-        // warp g = chain g; lane l carries bins l and l + 32 (two independent recurrences per thread: the dependent
-        // FADD -> FMUL -> FFMA chain of one hides behind the other)
+        // warp g = chain g = rows 16g .. 16g+15 of every tile; lane l carries bins l and l + 32 (two independent recurrences
+        // per thread, two producer warps per scheduler: the dependent FADD -> FMUL -> FFMA chains hide behind each other)
         const int g = warp;
         const float4 w0 = p.wtab[lane], w1 = p.wtab[32 + lane];
         float2 *sc = sC + warp * 64;
@@ -220,15 +233,18 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
         uint32_t base8[8];
 #pragma unroll
         for (int m = 0; m < 8; ++m)
-            base8[m] = (uint32_t)((32 * g) * 128 + (((lane >> 2) ^ m) << 4) + (lane & 3) * 4);
+            base8[m] = (uint32_t)((16 * g) * 128 + (((lane >> 2) ^ m) << 4) + (lane & 3) * 4);
         const uint32_t sA_u = smem_u32(sA);
         uint32_t it = 0;
+        long long c_wait = 0, c_math = 0, c_red = 0, c_tail = 0, c_warm = 0, tk = 0;
+        const bool prof = (p.dbg & 8) && g == 0;
+#define BK_TICK(acc) do { if (prof) { const long long now = clock64(); acc += now - tk; tk = now; } } while (0)
         for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int64_t cap, seg_lo, seg_hi, Q;
             item_geom(item, cap, seg_lo, seg_hi, Q);
             const float2 *xc = p.x + cap * p.n;
             const int64_t s0 = seg_lo + (int64_t)g * Q + p.cp;           // sample index of the chain's first window
-            const int n_warm = p.N / 32, n_tiles = (int)(Q / 32);
+            const int n_warm = p.N / 32, n_pairs = (int)(Q / 32);       // blocks of 32 samples: warm-up, then 2 tiles each
             auto ldx = [&](int64_t idx) { return idx < p.n ? __ldg(xc + idx) : make_float2(0.f, 0.f); };
             // feed u: warm-up blocks bring x[s0 + 32u + lane] into an empty window; real blocks the comb x[s+N] - x[s]
             auto feed = [&](int u, float2 &a, float2 &b) {      // comb sample = a - b (subtracted when it is stored)
@@ -243,11 +259,12 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
                 sc[lane] = make_float2(a.x - b.x, a.y - b.y);
             }
             __syncwarp();
-            const int n_blocks = n_warm + n_tiles;
+            const int n_blocks = n_warm + n_pairs;
             for (int u = 0; u < n_blocks; ++u) {
                 float2 na = make_float2(0.f, 0.f), nb = na;
                 if (u + 1 < n_blocks) feed(u + 1, na, nb);             // in flight during the 32 steps below
                 const float4 *cb4 = reinterpret_cast<const float4 *>(sc + (u & 1) * 32);
+                if (prof) tk = clock64();
                 if (u < n_warm) {
 #pragma unroll
                     for (int i2 = 0; i2 < 16; ++i2) {
@@ -260,61 +277,69 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
                             bx1 = fmaf(tx1, w1.x, -ty1 * w1.y); by1 = fmaf(tx1, w1.y, ty1 * w1.x);
                         }
                     }
+                    BK_TICK(c_warm);
                 } else {
-                    const uint32_t buf = it & 1u;
-                    if (it >= 2) mbar_wait_bounded(&a_empty[buf], ((it >> 1) & 1u) ^ 1u);
-                    const uint32_t tb = sA_u + buf * BK_TILE;
-                    float e[32];
-                    if (p.dbg & 4) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) e[i] = 0.f;
-                    } else {
-                    // comb samples: 8 steps' worth (4 x LDS.128, warp broadcast) fetched one group ahead of their use --
-                    // ptxas will not move a shared load above a shared store on its own
-                    float4 cg[4], cn[4];
+                    for (int tl = 0; tl < 2; ++tl) {                  // two tiles (16 rows each) per 32-sample block
+                        const uint32_t buf = it & 1u;
+                        if (it >= 2) mbar_wait_bounded(&a_empty[buf], ((it >> 1) & 1u) ^ 1u);
+                        const uint32_t tb = sA_u + buf * BK_TILE;
+                        BK_TICK(c_wait);
+                        float e[16];
+                        if (p.dbg & 4) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) cg[q] = cb4[q];
+                            for (int i = 0; i < 16; ++i) e[i] = 0.f;
+                        } else {
+                            // comb samples: 8 steps' worth (4 x LDS.128, warp broadcast) fetched before the stores of their
+                            // group -- ptxas will not move a shared load above a shared store on its own
+                            float4 cg[4], cn[4];
 #pragma unroll
-                    for (int grp = 0; grp < 4; ++grp) {
-                        if (grp < 3) {
+                            for (int q = 0; q < 4; ++q) cg[q] = cb4[8 * tl + q];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) cn[q] = cb4[4 * (grp + 1) + q];
+                            for (int grp = 0; grp < 2; ++grp) {
+                                if (grp < 1) {
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) cn[q] = cb4[8 * tl + 4 + q];
+                                }
+#pragma unroll
+                                for (int ii = 0; ii < 8; ++ii) {
+                                    const int i = 8 * grp + ii;
+                                    e[i] = fmaf(bx0, bx0, fmaf(by0, by0, fmaf(bx1, bx1, by1 * by1)));
+                                    const uint32_t a = tb + base8[ii] + i * 128;
+                                    sts_f32(a, bx0);
+                                    sts_f32(a + 16384, bx1);
+                                    sts_f32(a + 32768, by0);
+                                    sts_f32(a + 49152, by1);
+                                    const float4 c4 = cg[ii >> 1];
+                                    const float cx = (ii & 1) ? c4.z : c4.x, cy = (ii & 1) ? c4.w : c4.y;
+                                    const float tx0 = bx0 + cx, ty0 = by0 + cy, tx1 = bx1 + cx, ty1 = by1 + cy;
+                                    bx0 = fmaf(tx0, w0.x, -ty0 * w0.y); by0 = fmaf(tx0, w0.y, ty0 * w0.x);
+                                    bx1 = fmaf(tx1, w1.x, -ty1 * w1.y); by1 = fmaf(tx1, w1.y, ty1 * w1.x);
+                                }
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) cg[q] = cn[q];
+                            }
                         }
+                        BK_TICK(c_math);
+                        // transposed reduction of the 16 row energies over the 32 lanes (= 64 bins): lanes 2r, 2r+1 end with row r
 #pragma unroll
-                        for (int ii = 0; ii < 8; ++ii) {
-                            const int i = 8 * grp + ii;
-                            e[i] = fmaf(bx0, bx0, fmaf(by0, by0, fmaf(bx1, bx1, by1 * by1)));
-                            const uint32_t a = tb + base8[ii] + i * 128;
-                            sts_f32(a, bx0);
-                            sts_f32(a + 16384, bx1);
-                            sts_f32(a + 32768, by0);
-                            sts_f32(a + 49152, by1);
-                            const float4 c4 = cg[ii >> 1];
-                            const float cx = (ii & 1) ? c4.z : c4.x, cy = (ii & 1) ? c4.w : c4.y;
-                            const float tx0 = bx0 + cx, ty0 = by0 + cy, tx1 = bx1 + cx, ty1 = by1 + cy;
-                            bx0 = fmaf(tx0, w0.x, -ty0 * w0.y); by0 = fmaf(tx0, w0.y, ty0 * w0.x);
-                            bx1 = fmaf(tx1, w1.x, -ty1 * w1.y); by1 = fmaf(tx1, w1.y, ty1 * w1.x);
+                        for (int s = 16; s >= 2; s >>= 1) {
+                            const bool hi = (lane & s) != 0;
+#pragma unroll
+                            for (int k = 0; k < s / 2; ++k) {
+                                const float send = hi ? e[k] : e[k + s / 2];
+                                const float keep = hi ? e[k + s / 2] : e[k];
+                                e[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                            }
                         }
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) cg[q] = cn[q];
+                        e[0] += __shfl_xor_sync(0xffffffffu, e[0], 1);
+                        if (!(lane & 1)) sE[(it & 3u) * 128 + 16 * g + (lane >> 1)] = e[0];
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cta(&a_full[buf]);
+                        ++it;
+                        BK_TICK(c_red);
                     }
-                    }
-                    // transposed reduction: lane i ends with the sum over all 64 bins of e[i]
-#pragma unroll
-                    for (int s = 16; s >= 1; s >>= 1) {
-                        const bool hi = (lane & s) != 0;
-#pragma unroll
-                        for (int k = 0; k < s; ++k) {
-                            const float send = hi ? e[k] : e[k + s];
-                            const float keep = hi ? e[k + s] : e[k];
-                            e[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-                        }
-                    }
-                    sE[(it & 3u) * 128 + 32 * g + lane] = e[0];
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cta(&a_full[buf]);
-                    ++it;
                 }
                 asm volatile("" : "+f"(na.x), "+f"(na.y), "+f"(nb.x), "+f"(nb.y));   // keep the subtraction (and the wait) down here
                 sc[((u + 1) & 1) * 32 + lane] = make_float2(na.x - nb.x, na.y - nb.y);
@@ -324,7 +349,12 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
                     bx0 = kx0; by0 = ky0; bx1 = kx1; by1 = ky1;
                 }
                 __syncwarp();
+                BK_TICK(c_tail);
             }
+        }
+        if (prof && lane == 0) {
+            long long *o = p.prof + (size_t)blockIdx.x * 16;
+            o[0] = c_wait; o[1] = c_math; o[2] = c_red; o[3] = c_tail; o[4] = c_warm; o[5] = it;
         }
     } else if (warp == BK_PW + BK_EW) {
         // ============================================================ MMA issuer (one elected thread)
@@ -334,15 +364,19 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
             for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 int64_t cap, seg_lo, seg_hi, Q;
                 item_geom(item, cap, seg_lo, seg_hi, Q);
-                tot += (uint32_t)(Q / 32);
+                tot += (uint32_t)(Q / 16);
             }
             mbar_expect_tx(t_full, BK_TILE);
             for (int kc = 0; kc < 4; ++kc) tma_load_2d_b(sT + kc * 16384, &mapT, kc * 32, 0, t_full);
             mbar_wait_bounded(t_full, 0);
+            long long m_wa = 0, m_wd = 0, m_is = 0, tk = clock64();
+            const bool prof = (p.dbg & 8) != 0;
             for (; mt < tot; ++mt) {
                 const uint32_t buf = mt & 1u, ph = (mt >> 1) & 1u;
                 mbar_wait_bounded(&a_full[buf], ph);
+                BK_TICK(m_wa);
                 if (mt >= 2) mbar_wait_bounded(&d_empty[buf], ph ^ 1u);
+                BK_TICK(m_wd);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const unsigned char *At = sA + buf * BK_TILE;
                 if (!(p.dbg & 1))
@@ -356,76 +390,88 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
                 }
                 umma_commit(&a_empty[buf]);
                 umma_commit(&d_full[buf]);
+                BK_TICK(m_is);
             }
+            if (prof) { long long *o = p.prof + (size_t)blockIdx.x * 16; o[6] = m_wa; o[7] = m_wd; o[8] = m_is; }
         }
     } else {
-        // ============================================================ epilogue: two warps per chain / TMEM lane quadrant,
-        // each taking 32 of the 64 roots
-        const int ew = warp - BK_PW;                          // 0..7
-        const int g = warp & 3;                               // TMEM lane quadrant this warp may read (= warp % 4) = chain
-        const int half = ew >> 2;                             // roots 32*half .. 32*half + 31
-        const uint32_t tq = tmem + ((uint32_t)(g * 32) << 16);
-        const int et = tid - BK_PW * 32;                      // 0..255
+        // ============================================================ epilogue: one warp per TMEM lane quadrant (= two chains)
+        const int q4 = warp & 3;                              // lane quadrant this warp may read (warp % 4)
+        const uint32_t tq = tmem + ((uint32_t)(q4 * 32) << 16);
+        const int et = tid - BK_PW * 32;                      // 0..127
+        const int chain = 2 * q4 + (lane >> 4);
         uint32_t it = 0;
+        long long e_wait = 0, e_work = 0, tk = clock64();
+        const bool prof = (p.dbg & 8) && q4 == 0;
         for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int64_t cap, seg_lo, seg_hi, Q;
             item_geom(item, cap, seg_lo, seg_hi, Q);
-            const int n_tiles = (int)(Q / 32);
-            const int64_t q0 = seg_lo + (int64_t)g * Q + lane;          // this thread's offset in tile 0
-            unsigned best[32];
+            const int n_tiles = (int)(Q / 16);
+            const int64_t q0 = seg_lo + (int64_t)chain * Q + (lane & 15);       // this thread's offset in tile 0
+            const int64_t q_end = seg_lo + (int64_t)(chain + 1) * Q < seg_hi ? seg_lo + (int64_t)(chain + 1) * Q : seg_hi;
+            unsigned best[64];
 #pragma unroll
-            for (int r = 0; r < 32; ++r) best[r] = 0u;
+            for (int r = 0; r < 64; ++r) best[r] = 0u;
             float emax = 0.f;
             for (int t = 0; t < n_tiles; ++t, ++it) {
                 const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
                 mbar_wait_bounded(&d_full[buf], ph);
+                BK_TICK(e_wait);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const float e = sE[(it & 3u) * 128 + 32 * g + lane];
+                const float e = sE[(it & 3u) * 128 + 32 * q4 + lane];
                 emax = fmaxf(emax, __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(e))));
-                const int64_t o = q0 + 32 * (int64_t)t;
-                const float inv = (o < seg_hi && e > 1e-7f * emax && e > 0.f) ? 1.0f / e : 0.f;
+                const int64_t o = q0 + 16 * (int64_t)t;
+                const float inv = (o < q_end && e > 1e-7f * emax && e > 0.f) ? 1.0f / e : 0.f;
                 const unsigned tb = (unsigned)(BK_TILES_MAX - 1 - t);
-                uint32_t re[32], im[32];
-                if (p.dbg & 2) {
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) re[q] = im[q] = 0u;
-                } else {
-                tmem_ld32(tq + buf * BK_N + 32 * half, re);
-                tmem_ld32(tq + buf * BK_N + 64 + 32 * half, im);
-                }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cta(&d_empty[buf]);
+                for (int c = 0; c < 4; ++c) {                 // 16 roots at a time: Re columns 16c.., Im columns 64 + 16c..
+                    uint32_t re[16], im[16];
+                    if (p.dbg & 2) {
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const float yr = __uint_as_float(re[q]), yi = __uint_as_float(im[q]);
-                    const float m = fmaf(yr, yr, yi * yi) * inv;
-                    const unsigned key = (__float_as_uint(m) & 0xfffffc00u) | tb;
-                    best[q] = max(best[q], key);
+                        for (int q = 0; q < 16; ++q) re[q] = im[q] = 0u;
+                    } else {
+                        tmem_ld16(tq + buf * BK_N + 16 * c, re);
+                        tmem_ld16(tq + buf * BK_N + 64 + 16 * c, im);
+                    }
+                    if (c == 3) {
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cta(&d_empty[buf]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const float yr = __uint_as_float(re[q]), yi = __uint_as_float(im[q]);
+                        const float m = fmaf(yr, yr, yi * yi) * inv;
+                        const unsigned key = (__float_as_uint(m) & 0xfffffc00u) | tb;
+                        best[16 * c + q] = max(best[16 * c + q], key);
+                    }
                 }
+                BK_TICK(e_work);
             }
-            // ---- reduce over the 256 epilogue threads: max key per root, then the earliest offset holding it
+            // ---- reduce over the 128 epilogue threads: max key per root, then the earliest offset holding it
 #pragma unroll
-            for (int r = 0; r < 32; ++r)
-                if (32 * half + r < p.n_roots && (best[r] & 0xfffffc00u)) atomicMax(&sBest[32 * half + r], best[r]);
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int r = 0; r < 64; ++r)
+                if (r < p.n_roots && (best[r] & 0xfffffc00u)) atomicMax(&sBest[r], best[r]);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
-                if (32 * half + r < p.n_roots && best[r] == sBest[32 * half + r] && (best[r] & 0xfffffc00u)) {
+            for (int r = 0; r < 64; ++r) {
+                if (r < p.n_roots && best[r] == sBest[r] && (best[r] & 0xfffffc00u)) {
                     const int t = BK_TILES_MAX - 1 - (int)(best[r] & 0x3ffu);
-                    atomicMin(&sOff[32 * half + r], (unsigned)(q0 + 32 * (int64_t)t));
+                    atomicMin(&sOff[r], (unsigned)(q0 + 16 * (int64_t)t));
                 }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
             if (et < p.n_roots && sBest[et]) {
                 const unsigned long long key = ((unsigned long long)(sBest[et] & 0xfffffc00u) << 32) | (unsigned long long)(0xffffffffu - sOff[et]);
                 atomicMax(p.best_packed + cap * p.n_roots + et, key);
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
             if (et < 64) { sBest[et] = 0u; sOff[et] = 0xffffffffu; }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
         }
+        if (prof && lane == 0) { long long *o = p.prof + (size_t)blockIdx.x * 16; o[9] = e_wait; o[10] = e_work; }
     }
+#undef BK_TICK
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == BK_PW) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
@@ -515,10 +561,23 @@ OFS_API int ofs_zc_bank(const void *x_c64, int64_t n_frames, int64_t n, int32_t 
         BankParams p{};
         p.x = reinterpret_cast<const float2 *>(x_c64); p.n = n; p.n_off = n_off; p.seg_len = seg_len; p.segs_per_cap = (int)segs;
         { const char *dbg = getenv("OFS_BANK_DBG"); p.dbg = dbg ? atoi(dbg) : 0; }
+        const int64_t grid_dbg = n_frames * segs < sm_count() ? n_frames * segs : sm_count();
+        if (p.dbg & 8) { OFS_CUDA(cudaMalloc((void **)&p.prof, (size_t)grid_dbg * 16 * 8)); OFS_CUDA(cudaMemset(p.prof, 0, (size_t)grid_dbg * 16 * 8)); }
         p.n_items = n_frames * segs; p.N = n_fft; p.cp = cp; p.n_roots = nr; p.wtab = wtab; p.best_packed = packed;
         const int64_t grid = p.n_items < sm_count() ? p.n_items : sm_count();
         zc_bank_fused_kernel<<<(unsigned)grid, BK_THREADS, smem, stream>>>(mapT, p);
         if (int rc = check_launch("zc_bank_fused_kernel")) return rc;
+        if (p.dbg & 8) {       // timing experiment: average cycles per tile spent in each phase (stderr)
+            OFS_CUDA(cudaStreamSynchronize(stream));
+            long long *h = (long long *)malloc((size_t)grid * 16 * 8);
+            cudaMemcpy(h, p.prof, (size_t)grid * 16 * 8, cudaMemcpyDeviceToHost);
+            double a[16] = {0}; double tiles = 0;
+            for (int64_t b = 0; b < grid; ++b) { for (int q = 0; q < 16; ++q) a[q] += (double)h[b * 16 + q]; tiles += (double)h[b * 16 + 5]; }
+            fprintf(stderr, "bank cycles/tile: producer wait %.0f math %.0f reduce+arrive %.0f tail/2 %.0f warm %.0f | mma wait_a %.0f wait_d %.0f issue %.0f | "
+                            "epilogue wait %.0f work %.0f (tiles/CTA %.0f)\n", a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles, a[4] / tiles,
+                    a[6] / tiles, a[7] / tiles, a[8] / tiles, a[9] / tiles, a[10] / tiles, tiles / (double)grid);
+            free(h); cudaFree(p.prof);
+        }
         if (n_roots <= BK_MAXR) {
             zc_bank_unpack_kernel<<<(unsigned)((n_frames * nr + 255) / 256), 256, 0, stream>>>(packed, n_frames * nr, nr, Er, best_metric,
                                                                                            best_offset);

@@ -7,25 +7,27 @@
 //     metric     = |Y|^2 / (E_r E(o)),   E(o) = sum_j |bins[j, o]|^2        (zc_freq.py:95-97)
 // and only the maximum over offsets (value + first offset) of every root is kept.
 //
-// One persistent CTA per SM, warp-specialised (13 warps):
+// One persistent CTA per SM, warp-specialised (17 warps):
 //  * 8 PRODUCER warps = 8 chains x 64 bins (two bins per thread).  A chain is an eighth of the CTA's offset range walked sample by sample with
 //    the sliding-DFT recurrence  b(o+1) = w (b(o) + x[o+cp+N] - x[o+cp]),  w = e^{+2 pi i k/N}  (two bins per thread; the
 //    systematic error of the float rotation is divided out once per 32 steps, so rounding errors only random-walk).
 //    Each chain owns 16 of the 128 rows of a tile: every step writes Re/Im of its bin straight into the MMA's A operand
 //    in shared memory (K-major, 128-byte swizzle, the layout a tiled TMA copy would produce) -- the bins never exist in
 //    HBM.  Row energies E(o) come from a transposed warp reduction (16 shuffles per 16 rows).
-//  * 1 MMA warp: one elected thread issues 16 tcgen05.mma.kind::tf32 (M=128 offsets, N=128 = 64 roots x {Re, Im}, K=8)
+//  * 1 MMA warp: one elected thread issues 8 tcgen05.mma.kind::f16 (M=128 offsets, N=128 = 64 roots x {Re, Im}, K=16)
 //    per tile into one of two TMEM accumulators; tcgen05.commit releases the operand buffer and publishes the accumulator.
-//  * 4 EPILOGUE warps (one per TMEM lane quadrant = two chains): tcgen05.ld, |Y|^2 / E(o), running maximum per root
+//  * 8 EPILOGUE warps (two per TMEM lane quadrant = two chains, 32 roots each): tcgen05.ld, |Y|^2 / E(o), running maximum per root
 //    in registers (tile number packed into the 10 low mantissa bits so the arg-max costs nothing per element).
-// The templates (B operand, 64 KB) arrive once per CTA by tiled TMA.  Operand and accumulator buffers are double-buffered
+// The templates (B operand, 32 KB) arrive once per CTA by tiled TMA.  A 4-stage operand ring and two accumulators hang together
 // through mbarriers, so the SIMT producers, the tensor pipe and the epilogue overlap.
-// Accuracy: TF32 operands (10-bit mantissa), FP32 accumulation in TMEM, metric mantissa cut to 13 bits by the arg-max
+// Accuracy: FP16 operands (10-bit mantissa like TF32, half the shared-memory traffic -- the 128x128 tile is operand-fetch
+// bound; every chain is rescaled by a power of two so the range fits), FP32 accumulation in TMEM, metric mantissa cut to 13 bits by the arg-max
 // packing -> |d metric| <= 5e-3 * max(metric) (tested against the float64 oracle); arg-max offsets equal on clear peaks.
 // Offsets whose in-band energy is below 1e-7 of the largest seen so far in the chain are skipped (after a burst followed
 // by exact silence the recurrence holds a rounding residue, where the reference sees 0/eps = 0).
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <string.h>
 #include <stdlib.h>
 
@@ -35,10 +37,11 @@ constexpr int BK_ROWS = 128;      // M: offsets per tile (TMEM lanes) = 8 chains
 constexpr int BK_K = 128;         // K: 64 real + 64 imaginary bin columns
 constexpr int BK_N = 128;         // N: 64 roots x {Re Y, Im Y}
 constexpr int BK_MAXR = 64;       // roots per pass
-constexpr int BK_PW = 8, BK_EW = 4;
+constexpr int BK_PW = 8, BK_EW = 8;
 constexpr int BK_CH = 8;          // chains per work item, 16 rows of every tile each
-constexpr int BK_THREADS = (BK_PW + BK_EW + 1) * 32;  // 416 (13 warps): 128 registers per thread
-constexpr int BK_TILE = BK_ROWS * BK_K * 4;          // 64 KB
+constexpr int BK_THREADS = (BK_PW + BK_EW + 1) * 32;  // 544 (17 warps): 96 registers per thread
+constexpr int BK_TILE = BK_ROWS * BK_K * 2;          // 32 KB: fp16 operands
+constexpr int BK_ST = 4;                             // operand stages (A ring)
 constexpr int BK_TILES_MAX = 1024;                   // tile number must fit the 10 packed bits
 
 // ------------------------------------------------------------------------------------------------ tcgen05 helpers
@@ -48,45 +51,37 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
     return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46) | (2ull << 61);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// 8 columns of this thread's TMEM lane, NOT waited for: the registers may only be read after tmem_wait8 on them
+__device__ __forceinline__ void tmem_ld8_async(uint32_t taddr, uint32_t (&r)[8])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+// tcgen05.wait::ld with the loaded registers as in/out operands, so no consumer can be scheduled above the wait
+__device__ __forceinline__ void tmem_wait8(uint32_t (&a)[8], uint32_t (&b)[8])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(b[0]), "+r"(b[1]),
+                   "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        "tcgen05.wait::ld.sync.aligned;"      // same asm statement: the registers are valid when it returns
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_b(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
 {
@@ -113,22 +108,31 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity
 }
 
 // ------------------------------------------------------------------------------------------------ prep / unpack
-// B operand [128 rows][128 k] K-major: row r < 64: [Tre_r | Tim_r] (gives Re Y_r), row 64 + r: [-Tim_r | Tre_r] (Im Y_r)
-//   Re Y = sum_j Tre Bre + Tim Bim        Im Y = sum_j Tre Bim - Tim Bre
-// plus E_r and the rotation table: w_j = e^{+2 pi i k_j / N} rounded to float, and kappa_j (see below).
-__global__ void zc_bank_prep_kernel(const float2 *templ, int nbins, int n_roots, const int *bins, int N, float *Bmat, float *Er,
+// B operand [128 rows][128 k] fp16, K-major, k = 2j (pairs with Re bins_j) and 2j+1 (pairs with Im bins_j):
+//   row r < 64:  (Tre_r, Tim_r)   -> Re Y_r = sum_j Tre Bre + Tim Bim
+//   row 64 + r: (-Tim_r, Tre_r)   -> Im Y_r = sum_j Tre Bim - Tim Bre
+// scaled by beta = 1 / max|T| so any template set fits fp16 (E_r is scaled alike: the metric does not change),
+// plus the rotation table: w_j = e^{+2 pi i k_j / N} rounded to float, and kappa_j (see below).
+__global__ void zc_bank_prep_kernel(const float2 *templ, int nbins, int n_roots, const int *bins, int N, __half *Bmat, float *Er,
                                     float4 *wtab)
 {
+    __shared__ float smax[128];
     const int row = blockIdx.x, k = threadIdx.x;     // 128 x 128
-    const int r = row & 63, j = k & 63;
+    float mx = 0.f;
+    for (int q = k; q < n_roots * nbins; q += 128) { const float2 t = templ[q]; mx = fmaxf(mx, fmaxf(fabsf(t.x), fabsf(t.y))); }
+    smax[k] = mx;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) { if (k < o) smax[k] = fmaxf(smax[k], smax[k + o]); __syncthreads(); }
+    const float beta = smax[0] > 0.f ? 1.0f / smax[0] : 1.0f;
+    const int r = row & 63, j = k >> 1, c = k & 1;
     float tre = 0.f, tim = 0.f;
-    if (r < n_roots && j < nbins) { const float2 t = templ[r * nbins + j]; tre = t.x; tim = t.y; }
-    const bool imag_col = k >= 64, imag_row = row >= 64;
-    Bmat[row * BK_K + k] = imag_row ? (imag_col ? tre : -tim) : (imag_col ? tim : tre);
+    if (r < n_roots && j < nbins) { const float2 t = templ[r * nbins + j]; tre = t.x * beta; tim = t.y * beta; }
+    const bool imag_row = row >= 64;
+    Bmat[row * BK_K + k] = __float2half_rn(imag_row ? (c ? tre : -tim) : (c ? tim : tre));
     if (row < 64 && k == 0) {
         float e = 0.f;
         if (r < n_roots) for (int q = 0; q < nbins; ++q) { const float2 t = templ[r * nbins + q]; e += t.x * t.x + t.y * t.y; }
-        Er[r] = e;
+        Er[r] = e * beta * beta;
     }
     if (row == 0 && k < 64) {
         float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -175,26 +179,27 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void sts_f32(uint32_t addr, float v)
+// (re, im) -> packed fp16 pair (saturating: a burst the scale estimate missed must not become inf), one 32-bit store
+__device__ __forceinline__ void sts_h2(uint32_t addr, float re, float im)
 {
-    // no "memory" clobber: ordered against the fence / mbarrier arrive (both asm volatile), but the compiler stays free to
-    // hoist the broadcast loads of the comb samples above these stores
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v));
+    uint32_t v;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(v) : "f"(im), "f"(re));      // low half = re
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v));
 }
 
 __global__ void __launch_bounds__(BK_THREADS, 1)
 zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams p)
 {
     extern __shared__ __align__(1024) unsigned char bsm[];
-    unsigned char *sT = bsm;                                  // 64 KB templates (B operand)
-    unsigned char *sA = bsm + BK_TILE;                        // 2 x 64 KB bins tiles (A operand)
-    unsigned char *aux = bsm + 3 * BK_TILE;
-    uint64_t *a_full = reinterpret_cast<uint64_t *>(aux);     // [2]
-    uint64_t *a_empty = a_full + 2, *d_full = a_full + 4, *d_empty = a_full + 6, *t_full = a_full + 8;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(aux + 80);
+    unsigned char *sT = bsm;                                  // 32 KB templates (B operand)
+    unsigned char *sA = bsm + BK_TILE;                        // BK_ST x 32 KB bins tiles (A operand ring)
+    unsigned char *aux = bsm + (1 + BK_ST) * BK_TILE;
+    uint64_t *a_full = reinterpret_cast<uint64_t *>(aux);     // [BK_ST]
+    uint64_t *a_empty = a_full + BK_ST, *d_full = a_full + 2 * BK_ST, *d_empty = d_full + 2, *t_full = d_full + 4;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(aux + 120);
     unsigned *sBest = reinterpret_cast<unsigned *>(aux + 128);            // [64]
     unsigned *sOff = sBest + 64;                                          // [64]
-    float *sE = reinterpret_cast<float *>(aux + 1024);                    // [4 slots][128 rows]
+    float *sE = reinterpret_cast<float *>(aux + 1024);                    // [8 slots][128 rows]
     float2 *sC = reinterpret_cast<float2 *>(aux + 1024 + 4096);           // [8 warps][2][32]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -203,7 +208,8 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        for (int b = 0; b < 2; ++b) { mbar_init(&a_full[b], BK_PW); mbar_init(&a_empty[b], 1); mbar_init(&d_full[b], 1); mbar_init(&d_empty[b], BK_EW); }
+        for (int b = 0; b < BK_ST; ++b) { mbar_init(&a_full[b], BK_PW); mbar_init(&a_empty[b], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&d_full[b], 1); mbar_init(&d_empty[b], BK_EW); }
         mbar_init(t_full, 1);
         mbar_fence_init();
     }
@@ -228,8 +234,8 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
         const int g = warp;
         const float4 w0 = p.wtab[lane], w1 = p.wtab[32 + lane];
         float2 *sc = sC + warp * 64;
-        // shared-memory byte offsets of this thread's first Re column for rows with (row & 7) == m, first row of the chain;
-        // the second bin sits one K-chunk (16 KB) further, the imaginary parts two chunks (32 KB) further
+        // shared-memory byte offsets of this thread's first (Re, Im) fp16 pair for rows with (row & 7) == m, first row of the
+        // chain; the second bin sits one K-chunk (16 KB) further
         uint32_t base8[8];
 #pragma unroll
         for (int m = 0; m < 8; ++m)
@@ -246,6 +252,26 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
             const int64_t s0 = seg_lo + (int64_t)g * Q + p.cp;           // sample index of the chain's first window
             const int n_warm = p.N / 32, n_pairs = (int)(Q / 32);       // blocks of 32 samples: warm-up, then 2 tiles each
             auto ldx = [&](int64_t idx) { return idx < p.n ? __ldg(xc + idx) : make_float2(0.f, 0.f); };
+            // fp16 operands: the chain works on alpha * x with alpha = 2^k chosen so that even a fully coherent window
+            // (|bins| <= N max|x|) stays below 32768; every row may carry its own scale because the metric divides by
+            // the row's own energy.  max|x| is estimated from 64 blocks of 32 samples spread over the chain's range.
+            float alpha;
+            {
+                float m2 = 0.f;
+                const int64_t span = Q + p.N;
+                for (int q = 0; q < 64; ++q) {
+                    const float2 v = ldx(s0 + (span * q >> 6) + lane);
+                    m2 = fmaxf(m2, fmaf(v.x, v.x, v.y * v.y));
+                }
+                m2 = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m2)));
+                alpha = 1.f;
+                if (m2 > 0.f) {
+                    int ex;
+                    (void)frexpf(32768.0f / ((float)p.N * sqrtf(m2)), &ex);      // value = f * 2^ex, f in [0.5, 1)
+                    ex = ex - 1 < -100 ? -100 : (ex - 1 > 100 ? 100 : ex - 1);
+                    alpha = ldexpf(1.0f, ex);
+                }
+            }
             // feed u: warm-up blocks bring x[s0 + 32u + lane] into an empty window; real blocks the comb x[s+N] - x[s]
             auto feed = [&](int u, float2 &a, float2 &b) {      // comb sample = a - b (subtracted when it is stored)
                 if (u < n_warm) { a = ldx(s0 + 32 * (int64_t)u + lane); b = make_float2(0.f, 0.f); return; }
@@ -256,7 +282,7 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
             {
                 float2 a, b;
                 feed(0, a, b);
-                sc[lane] = make_float2(a.x - b.x, a.y - b.y);
+                sc[lane] = make_float2(alpha * (a.x - b.x), alpha * (a.y - b.y));
             }
             __syncwarp();
             const int n_blocks = n_warm + n_pairs;
@@ -281,8 +307,8 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
                 } else {
 #pragma unroll
                     for (int tl = 0; tl < 2; ++tl) {                  // two tiles (16 rows each) per 32-sample block
-                        const uint32_t buf = it & 1u;
-                        if (it >= 2) mbar_wait_bounded(&a_empty[buf], ((it >> 1) & 1u) ^ 1u);
+                        const uint32_t buf = it % BK_ST;
+                        if (it >= BK_ST) mbar_wait_bounded(&a_empty[buf], ((it / BK_ST) & 1u) ^ 1u);
                         const uint32_t tb = sA_u + buf * BK_TILE;
                         BK_TICK(c_wait);
                         float e[16];
@@ -292,32 +318,24 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
                         } else {
                             // comb samples: 8 steps' worth (4 x LDS.128, warp broadcast) fetched before the stores of their
                             // group -- ptxas will not move a shared load above a shared store on its own
-                            float4 cg[4], cn[4];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) cg[q] = cb4[8 * tl + q];
+                            float4 cg[4];
 #pragma unroll
                             for (int grp = 0; grp < 2; ++grp) {
-                                if (grp < 1) {
 #pragma unroll
-                                    for (int q = 0; q < 4; ++q) cn[q] = cb4[8 * tl + 4 + q];
-                                }
+                                for (int q = 0; q < 4; ++q) cg[q] = cb4[8 * tl + 4 * grp + q];
 #pragma unroll
                                 for (int ii = 0; ii < 8; ++ii) {
                                     const int i = 8 * grp + ii;
                                     e[i] = fmaf(bx0, bx0, fmaf(by0, by0, fmaf(bx1, bx1, by1 * by1)));
                                     const uint32_t a = tb + base8[ii] + i * 128;
-                                    sts_f32(a, bx0);
-                                    sts_f32(a + 16384, bx1);
-                                    sts_f32(a + 32768, by0);
-                                    sts_f32(a + 49152, by1);
+                                    sts_h2(a, bx0, by0);
+                                    sts_h2(a + 16384, bx1, by1);
                                     const float4 c4 = cg[ii >> 1];
                                     const float cx = (ii & 1) ? c4.z : c4.x, cy = (ii & 1) ? c4.w : c4.y;
                                     const float tx0 = bx0 + cx, ty0 = by0 + cy, tx1 = bx1 + cx, ty1 = by1 + cy;
                                     bx0 = fmaf(tx0, w0.x, -ty0 * w0.y); by0 = fmaf(tx0, w0.y, ty0 * w0.x);
                                     bx1 = fmaf(tx1, w1.x, -ty1 * w1.y); by1 = fmaf(tx1, w1.y, ty1 * w1.x);
                                 }
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) cg[q] = cn[q];
                             }
                         }
                         BK_TICK(c_math);
@@ -333,7 +351,7 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
                             }
                         }
                         e[0] += __shfl_xor_sync(0xffffffffu, e[0], 1);
-                        if (!(lane & 1)) sE[(it & 3u) * 128 + 16 * g + (lane >> 1)] = e[0];
+                        if (!(lane & 1)) sE[(it & 7u) * 128 + 16 * g + (lane >> 1)] = e[0];
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cta(&a_full[buf]);
@@ -342,7 +360,7 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
                     }
                 }
                 asm volatile("" : "+f"(na.x), "+f"(na.y), "+f"(nb.x), "+f"(nb.y));   // keep the subtraction (and the wait) down here
-                sc[((u + 1) & 1) * 32 + lane] = make_float2(na.x - nb.x, na.y - nb.y);
+                sc[((u + 1) & 1) * 32 + lane] = make_float2(alpha * (na.x - nb.x), alpha * (na.y - nb.y));
                 {   // per-block correction of the float rotation: b *= kappa
                     const float kx0 = fmaf(bx0, w0.z, -by0 * w0.w), ky0 = fmaf(bx0, w0.w, by0 * w0.z);
                     const float kx1 = fmaf(bx1, w1.z, -by1 * w1.w), ky1 = fmaf(bx1, w1.w, by1 * w1.z);
@@ -360,114 +378,126 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
         // ============================================================ MMA issuer (one elected thread)
         if (lane == 0) {
             uint32_t mt = 0, tot = 0;
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BK_N >> 3) << 17) | ((uint32_t)(BK_ROWS >> 4) << 24);
+            // instruction descriptor: D = F32 (bit 4), A = B = F16 (format 0), both K-major, N = 128, M = 128
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(BK_N >> 3) << 17) | ((uint32_t)(BK_ROWS >> 4) << 24);
             for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 int64_t cap, seg_lo, seg_hi, Q;
                 item_geom(item, cap, seg_lo, seg_hi, Q);
                 tot += (uint32_t)(Q / 16);
             }
             mbar_expect_tx(t_full, BK_TILE);
-            for (int kc = 0; kc < 4; ++kc) tma_load_2d_b(sT + kc * 16384, &mapT, kc * 32, 0, t_full);
+            for (int kc = 0; kc < 2; ++kc) tma_load_2d_b(sT + kc * 16384, &mapT, kc * 64, 0, t_full);
             mbar_wait_bounded(t_full, 0);
             long long m_wa = 0, m_wd = 0, m_is = 0, tk = clock64();
             const bool prof = (p.dbg & 8) != 0;
             for (; mt < tot; ++mt) {
-                const uint32_t buf = mt & 1u, ph = (mt >> 1) & 1u;
-                mbar_wait_bounded(&a_full[buf], ph);
+                const uint32_t buf = mt % BK_ST, acc = mt & 1u;
+                mbar_wait_bounded(&a_full[buf], (mt / BK_ST) & 1u);
                 BK_TICK(m_wa);
-                if (mt >= 2) mbar_wait_bounded(&d_empty[buf], ph ^ 1u);
+                if (mt >= 2) mbar_wait_bounded(&d_empty[acc], ((mt >> 1) & 1u) ^ 1u);
                 BK_TICK(m_wd);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const unsigned char *At = sA + buf * BK_TILE;
                 if (!(p.dbg & 1))
 #pragma unroll
-                for (int step = 0; step < 16; ++step) {
-                    // K loop: 16 steps of 8 tf32; K-chunk = step/4 (a 128-row x 128-byte box), 32 bytes per step inside the
+                for (int step = 0; step < 8; ++step) {
+                    // K loop: 8 steps of 16 fp16; K-chunk = step/4 (a 128-row x 128-byte box), 32 bytes per step inside the
                     // swizzled 128-byte row; 8-row atoms are 1024 B apart (SBO)
                     const uint64_t ad = umma_desc(smem_u32(At + (step >> 2) * 16384 + (step & 3) * 32), 16, 1024);
                     const uint64_t bd = umma_desc(smem_u32(sT + (step >> 2) * 16384 + (step & 3) * 32), 16, 1024);
-                    umma_tf32(tmem + buf * BK_N, ad, bd, idesc, step > 0 ? 1u : 0u);
+                    umma_f16(tmem + acc * BK_N, ad, bd, idesc, step > 0 ? 1u : 0u);
                 }
                 umma_commit(&a_empty[buf]);
-                umma_commit(&d_full[buf]);
+                umma_commit(&d_full[acc]);
                 BK_TICK(m_is);
             }
             if (prof) { long long *o = p.prof + (size_t)blockIdx.x * 16; o[6] = m_wa; o[7] = m_wd; o[8] = m_is; }
         }
     } else {
-        // ============================================================ epilogue: one warp per TMEM lane quadrant (= two chains)
+        // ============================================================ epilogue: two warps per TMEM lane quadrant (= two chains),
+        // 32 roots each; eight warps keep enough TMEM reads in flight to hide their latency
         const int q4 = warp & 3;                              // lane quadrant this warp may read (warp % 4)
-        const uint32_t tq = tmem + ((uint32_t)(q4 * 32) << 16);
-        const int et = tid - BK_PW * 32;                      // 0..127
+        const int half = (warp - BK_PW) >> 2;                 // roots 32*half .. 32*half + 31
+        const uint32_t tq = tmem + ((uint32_t)(q4 * 32) << 16) + 32 * half;
+        const int et = tid - BK_PW * 32;                      // 0..255
         const int chain = 2 * q4 + (lane >> 4);
         uint32_t it = 0;
         long long e_wait = 0, e_work = 0, tk = clock64();
-        const bool prof = (p.dbg & 8) && q4 == 0;
+        const bool prof = (p.dbg & 8) && warp == BK_PW;
         for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int64_t cap, seg_lo, seg_hi, Q;
             item_geom(item, cap, seg_lo, seg_hi, Q);
             const int n_tiles = (int)(Q / 16);
             const int64_t q0 = seg_lo + (int64_t)chain * Q + (lane & 15);       // this thread's offset in tile 0
             const int64_t q_end = seg_lo + (int64_t)(chain + 1) * Q < seg_hi ? seg_lo + (int64_t)(chain + 1) * Q : seg_hi;
-            unsigned best[64];
+            unsigned best[32];
 #pragma unroll
-            for (int r = 0; r < 64; ++r) best[r] = 0u;
+            for (int r = 0; r < 32; ++r) best[r] = 0u;
             float emax = 0.f;
             for (int t = 0; t < n_tiles; ++t, ++it) {
                 const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
                 mbar_wait_bounded(&d_full[buf], ph);
                 BK_TICK(e_wait);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const float e = sE[(it & 3u) * 128 + 32 * q4 + lane];
-                emax = fmaxf(emax, __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(e))));
+                const float e = sE[(it & 7u) * 128 + 32 * q4 + lane];
+                // running maximum per chain (= half warp: the two chains of a quadrant carry different scales)
+                emax = fmaxf(emax, __uint_as_float(__reduce_max_sync(lane < 16 ? 0x0000ffffu : 0xffff0000u, __float_as_uint(e))));
                 const int64_t o = q0 + 16 * (int64_t)t;
                 const float inv = (o < q_end && e > 1e-7f * emax && e > 0.f) ? 1.0f / e : 0.f;
                 const unsigned tb = (unsigned)(BK_TILES_MAX - 1 - t);
+                // 8 roots at a time (Re columns 32 half + 8c.., Im columns 64 more); the loads of chunk c+1 are in flight while chunk c is
+                // reduced, so the TMEM read latency is paid once per tile, not once per chunk
+                uint32_t re[2][8], im[2][8];
+                if (p.dbg & 2) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {                 // 16 roots at a time: Re columns 16c.., Im columns 64 + 16c..
-                    uint32_t re[16], im[16];
-                    if (p.dbg & 2) {
+                    for (int q = 0; q < 8; ++q) re[0][q] = im[0][q] = re[1][q] = im[1][q] = 0u;
+                } else {
+                    tmem_ld8_async(tq + buf * BK_N, re[0]);
+                    tmem_ld8_async(tq + buf * BK_N + 64, im[0]);
+                    tmem_wait8(re[0], im[0]);
+                }
 #pragma unroll
-                        for (int q = 0; q < 16; ++q) re[q] = im[q] = 0u;
-                    } else {
-                        tmem_ld16(tq + buf * BK_N + 16 * c, re);
-                        tmem_ld16(tq + buf * BK_N + 64 + 16 * c, im);
+                for (int c = 0; c < 4; ++c) {
+                    if (c < 3 && !(p.dbg & 2)) {
+                        tmem_ld8_async(tq + buf * BK_N + 8 * (c + 1), re[(c + 1) & 1]);
+                        tmem_ld8_async(tq + buf * BK_N + 64 + 8 * (c + 1), im[(c + 1) & 1]);
                     }
-                    if (c == 3) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float yr = __uint_as_float(re[c & 1][q]), yi = __uint_as_float(im[c & 1][q]);
+                        const float m = fmaf(yr, yr, yi * yi) * inv;
+                        const unsigned key = (__float_as_uint(m) & 0xfffffc00u) | tb;
+                        best[8 * c + q] = max(best[8 * c + q], key);
+                    }
+                    if (c < 3 && !(p.dbg & 2)) tmem_wait8(re[(c + 1) & 1], im[(c + 1) & 1]);
+                    if (c == 2) {                             // the last loads have landed: the accumulator may be overwritten
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cta(&d_empty[buf]);
                     }
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const float yr = __uint_as_float(re[q]), yi = __uint_as_float(im[q]);
-                        const float m = fmaf(yr, yr, yi * yi) * inv;
-                        const unsigned key = (__float_as_uint(m) & 0xfffffc00u) | tb;
-                        best[16 * c + q] = max(best[16 * c + q], key);
-                    }
                 }
                 BK_TICK(e_work);
             }
-            // ---- reduce over the 128 epilogue threads: max key per root, then the earliest offset holding it
+            // ---- reduce over the 256 epilogue threads: max key per root, then the earliest offset holding it
 #pragma unroll
-            for (int r = 0; r < 64; ++r)
-                if (r < p.n_roots && (best[r] & 0xfffffc00u)) atomicMax(&sBest[r], best[r]);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int r = 0; r < 32; ++r)
+                if (32 * half + r < p.n_roots && (best[r] & 0xfffffc00u)) atomicMax(&sBest[32 * half + r], best[r]);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
-            for (int r = 0; r < 64; ++r) {
-                if (r < p.n_roots && best[r] == sBest[r] && (best[r] & 0xfffffc00u)) {
+            for (int r = 0; r < 32; ++r) {
+                if (32 * half + r < p.n_roots && best[r] == sBest[32 * half + r] && (best[r] & 0xfffffc00u)) {
                     const int t = BK_TILES_MAX - 1 - (int)(best[r] & 0x3ffu);
-                    atomicMin(&sOff[r], (unsigned)(q0 + 16 * (int64_t)t));
+                    atomicMin(&sOff[32 * half + r], (unsigned)(q0 + 16 * (int64_t)t));
                 }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (et < p.n_roots && sBest[et]) {
                 const unsigned long long key = ((unsigned long long)(sBest[et] & 0xfffffc00u) << 32) | (unsigned long long)(0xffffffffu - sOff[et]);
                 atomicMax(p.best_packed + cap * p.n_roots + et, key);
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (et < 64) { sBest[et] = 0u; sOff[et] = 0xffffffffu; }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
         }
         if (prof && lane == 0) { long long *o = p.prof + (size_t)blockIdx.x * 16; o[9] = e_wait; o[10] = e_work; }
     }
@@ -496,15 +526,15 @@ static EncodeTiledFn2 encode_fn2()
     }
     return fn;
 }
-static bool make_map_f32(CUtensorMap *map, const void *base, uint64_t inner, uint64_t rows, uint32_t box_rows)
+static bool make_map_f16(CUtensorMap *map, const void *base, uint64_t inner, uint64_t rows, uint32_t box_rows)
 {
     EncodeTiledFn2 fn = encode_fn2();
     if (!fn) return false;
     const cuuint64_t gdim[2] = {inner, rows};
-    const cuuint64_t gstride[1] = {inner * 4};
-    const cuuint32_t box[2] = {32, box_rows};
+    const cuuint64_t gstride[1] = {inner * 2};
+    const cuuint32_t box[2] = {64, box_rows};          // 64 halfs = one 128-byte swizzle row
     const cuuint32_t estr[2] = {1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -525,10 +555,11 @@ OFS_API int ofs_zc_bank(const void *x_c64, int64_t n_frames, int64_t n, int32_t 
     if (n_frames == 0) return OFS_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     keep_pool_cached();
-    float *Bmat = nullptr, *Er = nullptr;
+    __half *Bmat = nullptr;
+    float *Er = nullptr;
     float4 *wtab = nullptr;
     unsigned long long *packed = nullptr;
-    OFS_CUDA(cudaMallocAsync((void **)&Bmat, (size_t)BK_N * BK_K * 4, stream));
+    OFS_CUDA(cudaMallocAsync((void **)&Bmat, (size_t)BK_N * BK_K * 2, stream));
     OFS_CUDA(cudaMallocAsync((void **)&Er, BK_MAXR * 4, stream));
     OFS_CUDA(cudaMallocAsync((void **)&wtab, 64 * sizeof(float4), stream));
     OFS_CUDA(cudaMallocAsync((void **)&packed, (size_t)n_frames * BK_MAXR * 8, stream));
@@ -544,7 +575,7 @@ OFS_API int ofs_zc_bank(const void *x_c64, int64_t n_frames, int64_t n, int32_t 
     if (seg_len > seg_max) seg_len = seg_max;
     segs = (n_off + seg_len - 1) / seg_len;
 
-    const size_t smem = 3 * BK_TILE + 1024 + 4096 + 4096 + 1024;
+    const size_t smem = (1 + BK_ST) * BK_TILE + 1024 + 4096 + 4096 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         OFS_CUDA(cudaFuncSetAttribute(zc_bank_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -556,7 +587,7 @@ OFS_API int ofs_zc_bank(const void *x_c64, int64_t n_frames, int64_t n, int32_t 
                                                        n_fft, Bmat, Er, wtab);
         if (int rc = check_launch("zc_bank_prep_kernel")) return rc;
         CUtensorMap mapT;
-        OFS_REQUIRE(make_map_f32(&mapT, Bmat, BK_K, BK_N, 128), "ofs_zc_bank: cuTensorMapEncodeTiled failed");
+        OFS_REQUIRE(make_map_f16(&mapT, Bmat, BK_K, BK_N, 128), "ofs_zc_bank: cuTensorMapEncodeTiled failed");
         OFS_CUDA(cudaMemsetAsync(packed, 0, (size_t)n_frames * nr * 8, stream));
         BankParams p{};
         p.x = reinterpret_cast<const float2 *>(x_c64); p.n = n; p.n_off = n_off; p.seg_len = seg_len; p.segs_per_cap = (int)segs;

@@ -128,7 +128,7 @@ def main():
              note="flops ~ 62 bins x 2 (tile halo) x ~16 per modulated-prefix sample")
         del x
     if "bank" in cases:
-        # cfg 4 (bank): 64 ZC roots x 2048 captures x every offset; fused sliding-DFT producer + tcgen05 tf32 MMA
+        # cfg 4 (bank): 64 ZC roots x 2048 captures x every offset; fused sliding-DFT producer + tcgen05 kind::f16 MMA
         # (M=128 offsets, N=128 = 64 roots x {Re,Im}, K=128 = 62 bins x {Re,Im} padded)
         F, n = max(int(2048 * a.scale), 2), 65536
         x = synth.make_batch_device(F, n, "sc", seed=14, device=dev, chunk=64)
@@ -137,11 +137,11 @@ def main():
         T = np.stack([generate_zadoff_chu(r, 62) for r in range(1, 65)])
         ms = timeit(lambda: engine.zc_bank(x, bi, T), steps=3, warmup=2)
         noff = n - 2559
-        d = {"case": "cfg4 zc 64-root correlator bank (fused sliding-DFT producers + tcgen05 tf32 MMA + TMEM epilogue)", "ms": ms,
+        d = {"case": "cfg4 zc 64-root correlator bank (fused sliding-DFT producers + tcgen05 f16 MMA, fp32 TMEM accumulators + epilogue)", "ms": ms,
              "Msamples_per_s": F * n / (ms * 1e-3) / 1e6, "captures": F,
              "tensor": {"issued_tflops": F * noff * 2.0 * 128 * 128 / (ms * 1e-3) / 1e12,
                         "useful_tflops_8KR": F * noff * 8.0 * 62 * 64 / (ms * 1e-3) / 1e12,
-                        "note": "issued = one 128x128x128 tf32 MMA group per 128 offsets; useful = 8*K*R, K=62 bins, R=64 roots (SURVEY 8d)"}}
+                        "note": "issued = one 128x128x128 fp16 MMA group (fp32 accumulate) per 128 offsets; useful = 8*K*R, K=62 bins, R=64 roots (SURVEY 8d)"}}
         print(json.dumps(d), flush=True)
         del x
     if "aa64" in cases:

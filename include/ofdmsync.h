@@ -219,12 +219,15 @@ int ofs_zc_matched_filter(const void *x, int32_t in_dtype, int64_t n_frames, int
 int ofs_zc_freq_metric(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_branches, int64_t n,
                        int32_t n_fft, int32_t cp, const int32_t *bins, const void *templ_c128, int32_t nbins,
                        double templ_energy, int32_t out_f64, void *metric, int64_t out_stride, void *stream);
-/* Multi-root correlator bank on the tensor cores (tcgen05.mma kind::tf32, TMEM accumulators, TMA-fed): for every
- * capture and every root r < n_roots (<= 128), the maximum over all candidate offsets o of
- *     | sum_j conj(T[r, j]) bins[j, o] |^2 / max(E_r * E(o), 1e-12)
+/* Multi-root correlator bank on the tensor cores (one fused kernel: sliding-DFT producers -> tcgen05.mma kind::f16 with
+ * FP32 accumulators in TMEM -> epilogue): for every capture and every root r < n_roots (<= 128; 64 per pass), the maximum
+ * over all candidate offsets o of
+ *     | sum_j conj(T[r, j]) bins[j, o] |^2 / (E_r * E(o))
  * i.e. zc_freq.compute_frequency_metric (zc_freq.py:62-99; np.vdot at :94) evaluated for a bank of templates at once.
- * x: complex64 (n_frames, n) on the device, one branch.  templ: complex64[n_roots][nbins] (device), nbins <= 64.
- * best_metric / best_offset: [n_frames][n_roots].  TF32 inputs, FP32 accumulation: |d metric| <= 5e-3 * max. */
+ * x: complex64 (n_frames, n) on the device, one branch.  bins: int32[nbins] (device), templ: complex64[n_roots][nbins]
+ * (device), nbins <= 64, n_fft a multiple of 32.  best_metric / best_offset: [n_frames][n_roots].
+ * FP16 operands (10-bit mantissa), FP32 accumulation: |d metric| <= 5e-3 * max(metric); offsets whose in-band energy is
+ * below 1e-7 of the largest seen in their stretch of the capture count as silence (metric 0, as the reference's eps clamp). */
 int ofs_zc_bank(const void *x_c64, int64_t n_frames, int64_t n, int32_t n_fft, int32_t cp, const int32_t *bins,
                 const void *templ_c64, int32_t nbins, int32_t n_roots, float *best_metric, int32_t *best_offset,
                 void *stream);

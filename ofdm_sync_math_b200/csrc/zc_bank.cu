@@ -200,7 +200,7 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
     unsigned *sBest = reinterpret_cast<unsigned *>(aux + 128);            // [64]
     unsigned *sOff = sBest + 64;                                          // [64]
     float *sE = reinterpret_cast<float *>(aux + 1024);                    // [8 slots][128 rows]
-    float2 *sC = reinterpret_cast<float2 *>(aux + 1024 + 4096);           // [8 warps][2][32]
+    float4 *sC = reinterpret_cast<float4 *>(aux + 1024 + 4096);           // [8 warps][2][32] comb samples as (x, x, y, y)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (warp == BK_PW) {
@@ -232,8 +232,11 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
         // warp g = chain g = rows 16g .. 16g+15 of every tile; lane l carries bins l and l + 32 (two independent recurrences
         // per thread, two producer warps per scheduler: the dependent FADD -> FMUL -> FFMA chains hide behind each other)
         const int g = warp;
+        // both bins ride in the halves of packed fp32 registers (FADD2 / FMUL2 / FFMA2): the kernel is issue-bound
         const float4 w0 = p.wtab[lane], w1 = p.wtab[32 + lane];
-        float2 *sc = sC + warp * 64;
+        const float2 WX = make_float2(w0.x, w1.x), WY = make_float2(w0.y, w1.y), NWY = make_float2(-w0.y, -w1.y);
+        const float2 KX = make_float2(w0.z, w1.z), KY = make_float2(w0.w, w1.w), NKY = make_float2(-w0.w, -w1.w);
+        float4 *sc = sC + warp * 64;
         // shared-memory byte offsets of this thread's first (Re, Im) fp16 pair for rows with (row & 7) == m, first row of the
         // chain; the second bin sits one K-chunk (16 KB) further
         uint32_t base8[8];
@@ -278,30 +281,27 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
                 const int64_t s = s0 + 32 * (int64_t)(u - n_warm) + lane;
                 a = ldx(s + p.N); b = ldx(s);
             };
-            float bx0 = 0.f, by0 = 0.f, bx1 = 0.f, by1 = 0.f;
+            float2 Bx = make_float2(0.f, 0.f), By = Bx;          // (bin lane, bin lane + 32)
             {
                 float2 a, b;
                 feed(0, a, b);
-                sc[lane] = make_float2(alpha * (a.x - b.x), alpha * (a.y - b.y));
+                const float vx = alpha * (a.x - b.x), vy = alpha * (a.y - b.y);
+                sc[lane] = make_float4(vx, vx, vy, vy);
             }
             __syncwarp();
             const int n_blocks = n_warm + n_pairs;
             for (int u = 0; u < n_blocks; ++u) {
                 float2 na = make_float2(0.f, 0.f), nb = na;
                 if (u + 1 < n_blocks) feed(u + 1, na, nb);             // in flight during the 32 steps below
-                const float4 *cb4 = reinterpret_cast<const float4 *>(sc + (u & 1) * 32);
+                const float4 *cb4 = sc + (u & 1) * 32;
                 if (prof) tk = clock64();
                 if (u < n_warm) {
 #pragma unroll
-                    for (int i2 = 0; i2 < 16; ++i2) {
-                        const float4 c4 = cb4[i2];
-#pragma unroll
-                        for (int v = 0; v < 2; ++v) {
-                            const float cx = v ? c4.z : c4.x, cy = v ? c4.w : c4.y;
-                            const float tx0 = bx0 + cx, ty0 = by0 + cy, tx1 = bx1 + cx, ty1 = by1 + cy;
-                            bx0 = fmaf(tx0, w0.x, -ty0 * w0.y); by0 = fmaf(tx0, w0.y, ty0 * w0.x);
-                            bx1 = fmaf(tx1, w1.x, -ty1 * w1.y); by1 = fmaf(tx1, w1.y, ty1 * w1.x);
-                        }
+                    for (int i = 0; i < 32; ++i) {
+                        const float4 c = cb4[i];
+                        const float2 T = __fadd2_rn(Bx, make_float2(c.x, c.y)), U = __fadd2_rn(By, make_float2(c.z, c.w));
+                        Bx = __ffma2_rn(T, WX, __fmul2_rn(U, NWY));
+                        By = __ffma2_rn(T, WY, __fmul2_rn(U, WX));
                     }
                     BK_TICK(c_warm);
                 } else {
@@ -316,25 +316,30 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
 #pragma unroll
                             for (int i = 0; i < 16; ++i) e[i] = 0.f;
                         } else {
-                            // comb samples: 8 steps' worth (4 x LDS.128, warp broadcast) fetched before the stores of their
+                            // comb samples: 4 steps' worth (4 x LDS.128, warp broadcast) fetched before the stores of their
                             // group -- ptxas will not move a shared load above a shared store on its own
-                            float4 cg[4];
 #pragma unroll
-                            for (int grp = 0; grp < 2; ++grp) {
+                            for (int grp = 0; grp < 4; ++grp) {
+                                float4 cg[4];
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) cg[q] = cb4[8 * tl + 4 * grp + q];
+                                for (int q = 0; q < 4; ++q) cg[q] = cb4[16 * tl + 4 * grp + q];
 #pragma unroll
-                                for (int ii = 0; ii < 8; ++ii) {
-                                    const int i = 8 * grp + ii;
-                                    e[i] = fmaf(bx0, bx0, fmaf(by0, by0, fmaf(bx1, bx1, by1 * by1)));
-                                    const uint32_t a = tb + base8[ii] + i * 128;
-                                    sts_h2(a, bx0, by0);
-                                    sts_h2(a + 16384, bx1, by1);
-                                    const float4 c4 = cg[ii >> 1];
-                                    const float cx = (ii & 1) ? c4.z : c4.x, cy = (ii & 1) ? c4.w : c4.y;
-                                    const float tx0 = bx0 + cx, ty0 = by0 + cy, tx1 = bx1 + cx, ty1 = by1 + cy;
-                                    bx0 = fmaf(tx0, w0.x, -ty0 * w0.y); by0 = fmaf(tx0, w0.y, ty0 * w0.x);
-                                    bx1 = fmaf(tx1, w1.x, -ty1 * w1.y); by1 = fmaf(tx1, w1.y, ty1 * w1.x);
+                                for (int ii = 0; ii < 4; ++ii) {
+                                    const int i = 4 * grp + ii;
+                                    if (p.dbg & 32) e[i] = Bx.x;
+                                    else {
+                                    const float2 e2 = __ffma2_rn(Bx, Bx, __fmul2_rn(By, By));
+                                    e[i] = e2.x + e2.y;
+                                    }
+                                    const uint32_t a = tb + base8[i & 7] + i * 128;
+                                    if (!(p.dbg & 16)) {
+                                        sts_h2(a, Bx.x, By.x);
+                                        sts_h2(a + 16384, Bx.y, By.y);
+                                    }
+                                    const float4 c = cg[ii];
+                                    const float2 T = __fadd2_rn(Bx, make_float2(c.x, c.y)), U = __fadd2_rn(By, make_float2(c.z, c.w));
+                                    Bx = __ffma2_rn(T, WX, __fmul2_rn(U, NWY));
+                                    By = __ffma2_rn(T, WY, __fmul2_rn(U, WX));
                                 }
                             }
                         }
@@ -360,11 +365,13 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
                     }
                 }
                 asm volatile("" : "+f"(na.x), "+f"(na.y), "+f"(nb.x), "+f"(nb.y));   // keep the subtraction (and the wait) down here
-                sc[((u + 1) & 1) * 32 + lane] = make_float2(alpha * (na.x - nb.x), alpha * (na.y - nb.y));
+                {
+                    const float vx = alpha * (na.x - nb.x), vy = alpha * (na.y - nb.y);
+                    sc[((u + 1) & 1) * 32 + lane] = make_float4(vx, vx, vy, vy);
+                }
                 {   // per-block correction of the float rotation: b *= kappa
-                    const float kx0 = fmaf(bx0, w0.z, -by0 * w0.w), ky0 = fmaf(bx0, w0.w, by0 * w0.z);
-                    const float kx1 = fmaf(bx1, w1.z, -by1 * w1.w), ky1 = fmaf(bx1, w1.w, by1 * w1.z);
-                    bx0 = kx0; by0 = ky0; bx1 = kx1; by1 = ky1;
+                    const float2 nx = __ffma2_rn(Bx, KX, __fmul2_rn(By, NKY)), ny = __ffma2_rn(Bx, KY, __fmul2_rn(By, KX));
+                    Bx = nx; By = ny;
                 }
                 __syncwarp();
                 BK_TICK(c_tail);
@@ -463,11 +470,12 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
                         tmem_ld8_async(tq + buf * BK_N + 64 + 8 * (c + 1), im[(c + 1) & 1]);
                     }
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float yr = __uint_as_float(re[c & 1][q]), yi = __uint_as_float(im[c & 1][q]);
-                        const float m = fmaf(yr, yr, yi * yi) * inv;
-                        const unsigned key = (__float_as_uint(m) & 0xfffffc00u) | tb;
-                        best[8 * c + q] = max(best[8 * c + q], key);
+                    for (int q = 0; q < 8; q += 2) {
+                        const float2 yr = make_float2(__uint_as_float(re[c & 1][q]), __uint_as_float(re[c & 1][q + 1]));
+                        const float2 yi = make_float2(__uint_as_float(im[c & 1][q]), __uint_as_float(im[c & 1][q + 1]));
+                        const float2 m = __fmul2_rn(__ffma2_rn(yr, yr, __fmul2_rn(yi, yi)), make_float2(inv, inv));
+                        best[8 * c + q] = max(best[8 * c + q], (__float_as_uint(m.x) & 0xfffffc00u) | tb);
+                        best[8 * c + q + 1] = max(best[8 * c + q + 1], (__float_as_uint(m.y) & 0xfffffc00u) | tb);
                     }
                     if (c < 3 && !(p.dbg & 2)) tmem_wait8(re[(c + 1) & 1], im[(c + 1) & 1]);
                     if (c == 2) {                             // the last loads have landed: the accumulator may be overwritten
@@ -575,7 +583,7 @@ OFS_API int ofs_zc_bank(const void *x_c64, int64_t n_frames, int64_t n, int32_t 
     if (seg_len > seg_max) seg_len = seg_max;
     segs = (n_off + seg_len - 1) / seg_len;
 
-    const size_t smem = (1 + BK_ST) * BK_TILE + 1024 + 4096 + 4096 + 1024;
+    const size_t smem = (1 + BK_ST) * BK_TILE + 1024 + 4096 + 8192 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         OFS_CUDA(cudaFuncSetAttribute(zc_bank_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turn gpurun_out/*.ncu-rep / launches.csv into the tracked summaries under profiles/ (run in the build container).
 
-    python profiles/summarize.py <round> <prof.ncu-rep> [launches.csv]
+    python profiles/summarize.py <round> <prof.ncu-rep> [launches.csv] [--tag stripe] [--cmd "..."]
 Writes profiles/r<round>_stripe_ncu.md, profiles/r<round>_launches.md and profiles/traffic.json
 (dram bytes per launch of the dominant kernel, read by bench.py for roofline.traffic)."""
 import collections
@@ -20,7 +20,10 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
-        "lts__t_sector_hit_rate.pct", "sm__cycles_elapsed.max"]
+        "lts__t_sector_hit_rate.pct", "sm__cycles_elapsed.max", "sm__inst_executed_pipe_tensor.sum",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "smsp__mem_tensor_writes_op_utcmma.sum", "smsp__mem_tensor_reads_op_ldt.sum"]
 
 
 def raw(rep):
@@ -30,10 +33,15 @@ def raw(rep):
 
 
 def main():
+    tag, cmd = "stripe", "python bench.py ..."
+    if "--tag" in sys.argv:
+        i = sys.argv.index("--tag"); tag = sys.argv[i + 1]; del sys.argv[i:i + 2]
+    if "--cmd" in sys.argv:
+        i = sys.argv.index("--cmd"); cmd = sys.argv[i + 1]; del sys.argv[i:i + 2]
     rnd, rep = sys.argv[1], sys.argv[2]
     hdr, units, rows = raw(rep)
     lines = [f"# ncu --set full summary, round {rnd}: `{Path(rep).name}`", "",
-             "Command: `ncu --set full --clock-control none --import-source on -k regex:metric_stripe -s 3 -c 1 python bench.py ...`",
+             f"Command: `ncu --set full --clock-control none --import-source on -k regex:<kernel> -c 1 {cmd}`",
              "(per-launch values; ncu replays the kernel ~40x with cold caches: compare SHARES and byte counts, not absolute times)", ""]
     traffic = {}
     for r in rows:
@@ -93,10 +101,10 @@ def main():
         lines.append(", ".join(f"{op} {100 * c / tot:.1f}%" for op, c in ops.most_common(16)))
         lines.append("")
         tma = sorted({re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_.]+)", d["Source"]).group(2) for d in data
-                      if re.search(r"UBLKCP|UTMALDG|UTMASTG|SYNCS|REDUX", d["Source"])})
-        lines.append("TMA / mbarrier / REDUX SASS seen in the kernel: " + ", ".join(tma))
+                      if re.search(r"UBLKCP|UTMALDG|UTMASTG|SYNCS|REDUX|UTC|LDTM|STTM|FFMA2|FMUL2|FADD2|F2FP", d["Source"])})
+        lines.append("TMA / mbarrier / tcgen05 (UTC*MMA, LDTM) / REDUX / packed-FP32 SASS seen in the kernel: " + ", ".join(tma))
         lines.append("")
-    (HERE / f"r{rnd}_stripe_ncu.md").write_text("\n".join(lines))
+    (HERE / f"r{rnd}_{tag}_ncu.md").write_text("\n".join(lines))
     if traffic:
         (HERE / "traffic.json").write_text(json.dumps(traffic, indent=1))
     if len(sys.argv) > 3:
@@ -115,7 +123,7 @@ def main():
                "| kernel | launches | total us | share |", "|---|---|---|---|"]
         for name, v in agg.items():
             out.append(f"| `{name}` | {len(v)} | {sum(v) / 1e3:.1f} | {100 * sum(v) / tot:.1f}% |")
-        (HERE / f"r{rnd}_launches.md").write_text("\n".join(out) + "\n")
+        (HERE / (f"r{rnd}_launches.md" if tag == "stripe" else f"r{rnd}_{tag}_launches.md")).write_text("\n".join(out) + "\n")
 
 
 if __name__ == "__main__":

@@ -126,6 +126,9 @@ def main():
         ms = timeit(lambda: engine.zc_freq_metric(x, bi, tb, 62.0, out_f64=False), steps=3, warmup=2)
         emit("cfg4 zc_freq metric (62-bin sliding DFT, float64 prefix)", ms, F * n, flops=F * (n - 2559) * 62 * 2 * 16,
              note="flops ~ 62 bins x 2 (tile halo) x ~16 per modulated-prefix sample")
+        ms = timeit(lambda: engine.zc_freq_metric(x, bi, tb, 62.0, out_f64=False, fast=True), steps=3, warmup=2)
+        emit("cfg4 zc_freq metric, fast path (bank kernel: sliding-DFT recurrence + tcgen05, one template)", ms, F * n,
+             alg_bytes=F * (8 * n + 4 * (n - 2559)), note="8 B in + 4 B metric out per sample; FP16 operands, 5e-3 tolerance")
         del x
     if "bank" in cases:
         # cfg 4 (bank): 64 ZC roots x 2048 captures x every offset; fused sliding-DFT producer + tcgen05 kind::f16 MMA

@@ -232,6 +232,13 @@ int ofs_zc_bank(const void *x_c64, int64_t n_frames, int64_t n, int32_t n_fft, i
                 const void *templ_c64, int32_t nbins, int32_t n_roots, float *best_metric, int32_t *best_offset,
                 void *stream);
 
+/* zc_freq.compute_frequency_metric through the bank kernel (one template): the whole metric row, float32, for complex64
+ * single-branch captures.  FP16 tensor-core operands: |d metric| <= 5e-3 * max(metric) (ofs_zc_freq_metric is the
+ * float64-prefix version for when 1e-11 is wanted).  bins int32[nbins], templ complex64[nbins] on the device. */
+int ofs_zc_freq_metric_fast(const void *x_c64, int64_t n_frames, int64_t n, int32_t n_fft, int32_t cp, const int32_t *bins,
+                            const void *templ_c64, int32_t nbins, double templ_energy, float *metric,
+                            int64_t out_stride, void *stream);
+
 /* End-to-end sync over HOST buffers --------------------------------------------------------------- */
 typedef struct ofs_ctx ofs_ctx;
 int ofs_ctx_create(ofs_ctx **ctx, int device);

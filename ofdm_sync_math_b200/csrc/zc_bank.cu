@@ -136,6 +136,7 @@ __global__ void zc_bank_prep_kernel(const float2 *templ, int nbins, int n_roots,
         if (r < n_roots) for (int q = 0; q < nbins; ++q) { const float2 t = templ[r * nbins + q]; e += t.x * t.x + t.y * t.y; }
         Er[r] = e * beta * beta;
     }
+    if (row == 0 && k == 0) Er[BK_MAXR] = beta * beta;
     if (row == 0 && k < 64) {
         float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
         if (k < nbins) {
@@ -175,6 +176,10 @@ struct BankParams {
     int dbg;      // timing experiments only (OFS_BANK_DBG): 1 skip MMAs, 2 skip epilogue math, 4 skip producer math
     const float4 *wtab;
     unsigned long long *best_packed;
+    float *metric_out;          // optional: the full metric row of root 0 (zc_freq fast path), [frames][metric_stride]
+    int64_t metric_stride;
+    const float *Er;            // [64] E_r * beta^2, [64] = beta^2
+    float templ_energy;         // metric_out = |Y_0|^2 / (templ_energy * E(o))
 };
 
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar)
@@ -430,6 +435,7 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
         const uint32_t tq = tmem + ((uint32_t)(q4 * 32) << 16) + 32 * half;
         const int et = tid - BK_PW * 32;                      // 0..255
         const int chain = 2 * q4 + (lane >> 4);
+        const float mscale = p.metric_out ? 1.0f / (p.Er[BK_MAXR] * p.templ_energy) : 0.f;
         uint32_t it = 0;
         long long e_wait = 0, e_work = 0, tk = clock64();
         const bool prof = (p.dbg & 8) && warp == BK_PW;
@@ -476,6 +482,7 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
                         const float2 yr = make_float2(__uint_as_float(re[c & 1][q]), __uint_as_float(re[c & 1][q + 1]));
                         const float2 yi = make_float2(__uint_as_float(im[c & 1][q]), __uint_as_float(im[c & 1][q + 1]));
                         const float2 m = __fmul2_rn(__ffma2_rn(yr, yr, __fmul2_rn(yi, yi)), make_float2(inv, inv));
+                        if (c == 0 && q == 0 && half == 0 && p.metric_out && o < q_end) p.metric_out[cap * p.metric_stride + o] = m.x * mscale;
                         best[8 * c + q] = max(best[8 * c + q], (__float_as_uint(m.x) & 0xfffffc00u) | tb);
                         best[8 * c + q + 1] = max(best[8 * c + q + 1], (__float_as_uint(m.y) & 0xfffffc00u) | tb);
                     }
@@ -552,11 +559,11 @@ static bool make_map_f16(CUtensorMap *map, const void *base, uint64_t inner, uin
 
 using namespace ofs;
 
-OFS_API int ofs_zc_bank(const void *x_c64, int64_t n_frames, int64_t n, int32_t n_fft, int32_t cp, const int32_t *bins,
-                        const void *templ_c64, int32_t nbins, int32_t n_roots, float *best_metric, int32_t *best_offset,
-                        void *stream_)
+static int bank_run(const void *x_c64, int64_t n_frames, int64_t n, int32_t n_fft, int32_t cp, const int32_t *bins,
+                    const void *templ_c64, int32_t nbins, int32_t n_roots, float *best_metric, int32_t *best_offset,
+                    float *metric_out, int64_t metric_stride, float templ_energy, void *stream_)
 {
-    OFS_REQUIRE(x_c64 && bins && templ_c64 && best_metric && best_offset, "ofs_zc_bank: null argument");
+    OFS_REQUIRE(x_c64 && bins && templ_c64 && ((best_metric && best_offset) || metric_out), "ofs_zc_bank: null argument");
     OFS_REQUIRE(n_fft >= 32 && n_fft <= 65536 && n_fft % 32 == 0 && cp >= 0, "ofs_zc_bank: n_fft must be a multiple of 32 in 32..65536");
     OFS_REQUIRE(nbins >= 1 && nbins <= 64 && n_roots >= 1 && n_roots <= 128, "ofs_zc_bank: nbins <= 64, n_roots <= 128");
     const int64_t n_off = n - ((int64_t)n_fft + cp) + 1;
@@ -570,7 +577,7 @@ OFS_API int ofs_zc_bank(const void *x_c64, int64_t n_frames, int64_t n, int32_t 
     float4 *wtab = nullptr;
     unsigned long long *packed = nullptr;
     OFS_CUDA(cudaMallocAsync((void **)&Bmat, (size_t)BK_N * BK_K * 2, stream));
-    OFS_CUDA(cudaMallocAsync((void **)&Er, BK_MAXR * 4, stream));
+    OFS_CUDA(cudaMallocAsync((void **)&Er, (BK_MAXR + 1) * 4, stream));
     OFS_CUDA(cudaMallocAsync((void **)&wtab, 64 * sizeof(float4), stream));
     OFS_CUDA(cudaMallocAsync((void **)&packed, (size_t)n_frames * BK_MAXR * 8, stream));
 
@@ -605,6 +612,7 @@ OFS_API int ofs_zc_bank(const void *x_c64, int64_t n_frames, int64_t n, int32_t 
         const int64_t grid_dbg = n_frames * segs < sm_count() ? n_frames * segs : sm_count();
         if (p.dbg & 8) { OFS_CUDA(cudaMalloc((void **)&p.prof, (size_t)grid_dbg * 16 * 8)); OFS_CUDA(cudaMemset(p.prof, 0, (size_t)grid_dbg * 16 * 8)); }
         p.n_items = n_frames * segs; p.N = n_fft; p.cp = cp; p.n_roots = nr; p.wtab = wtab; p.best_packed = packed;
+        p.metric_out = metric_out; p.metric_stride = metric_stride; p.Er = Er; p.templ_energy = templ_energy;
         const int64_t grid = p.n_items < sm_count() ? p.n_items : sm_count();
         zc_bank_fused_kernel<<<(unsigned)grid, BK_THREADS, smem, stream>>>(mapT, p);
         if (int rc = check_launch("zc_bank_fused_kernel")) return rc;
@@ -619,7 +627,9 @@ OFS_API int ofs_zc_bank(const void *x_c64, int64_t n_frames, int64_t n, int32_t 
                     a[6] / tiles, a[7] / tiles, a[8] / tiles, a[9] / tiles, a[10] / tiles, tiles / (double)grid);
             free(h); cudaFree(p.prof);
         }
-        if (n_roots <= BK_MAXR) {
+        if (!best_metric) {
+            // metric-row mode (zc_freq fast path): nothing to unpack
+        } else if (n_roots <= BK_MAXR) {
             zc_bank_unpack_kernel<<<(unsigned)((n_frames * nr + 255) / 256), 256, 0, stream>>>(packed, n_frames * nr, nr, Er, best_metric,
                                                                                            best_offset);
             if (int rc = check_launch("zc_bank_unpack_kernel")) return rc;
@@ -643,4 +653,24 @@ OFS_API int ofs_zc_bank(const void *x_c64, int64_t n_frames, int64_t n, int32_t 
     OFS_CUDA(cudaFreeAsync(Er, stream));
     OFS_CUDA(cudaFreeAsync(wtab, stream));
     return OFS_OK;
+}
+
+OFS_API int ofs_zc_bank(const void *x_c64, int64_t n_frames, int64_t n, int32_t n_fft, int32_t cp, const int32_t *bins,
+                        const void *templ_c64, int32_t nbins, int32_t n_roots, float *best_metric, int32_t *best_offset,
+                        void *stream)
+{
+    OFS_REQUIRE(best_metric && best_offset, "ofs_zc_bank: null output");
+    return bank_run(x_c64, n_frames, n, n_fft, cp, bins, templ_c64, nbins, n_roots, best_metric, best_offset, nullptr, 0, 1.0f, stream);
+}
+
+OFS_API int ofs_zc_freq_metric_fast(const void *x_c64, int64_t n_frames, int64_t n, int32_t n_fft, int32_t cp, const int32_t *bins,
+                                    const void *templ_c64, int32_t nbins, double templ_energy, float *metric,
+                                    int64_t out_stride, void *stream)
+{
+    OFS_REQUIRE(metric && templ_energy > 0.0, "ofs_zc_freq_metric_fast: bad arguments");
+    const int64_t n_off = n - ((int64_t)n_fft + cp) + 1;
+    OFS_REQUIRE(n_off > 0, "Received stream is shorter than a single OFDM symbol.");   /* zc_freq.py:76-78 */
+    OFS_REQUIRE(out_stride >= n_off, "ofs_zc_freq_metric_fast: out_stride < number of offsets");
+    return bank_run(x_c64, n_frames, n, n_fft, cp, bins, templ_c64, nbins, 1, nullptr, nullptr, metric, out_stride, (float)templ_energy,
+                    stream);
 }

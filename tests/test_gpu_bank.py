@@ -37,3 +37,40 @@ def test_bank_vs_oracle(golden, tag):
     assert int(bo[1, 24]) == int(bo[0, 24]) + 777
     if tag == "awgn":
         assert int(bo[0, 24]) == int(g["peak"])
+
+
+@pytest.mark.parametrize("tag", ["awgn", "cir1"])
+def test_zc_freq_fast_path_vs_oracle(golden, tag):
+    """zc_freq metric row through the bank kernel (ofs_zc_freq_metric_fast): |d metric| <= 5e-3 * max, same arg-max."""
+    from ofdm_sync_math_b200 import engine
+    g = golden(f"zc_freq_{tag}")
+    rx = g["rx"][0].astype(np.complex64)
+    caps = np.stack([rx, np.roll(rx, -1234), rx[::-1].copy()])
+    tb = zadoff_chu(25)
+    m = engine.zc_freq_metric(caps[:, None, :], g["bin_indices"], tb, 62.0, out_f64=False, fast=True).cpu().numpy()
+    for c, x in enumerate(caps):
+        ref = orc.compute_frequency_metric(x.astype(np.complex128), g["bin_indices"], tb, 62.0)
+        assert m[c].shape == ref.shape
+        assert np.abs(m[c] - ref).max() <= 5e-3 * ref.max(), (c, np.abs(m[c] - ref).max(), ref.max())
+        if c < 2:
+            assert int(np.argmax(m[c])) == int(np.argmax(ref))
+
+
+def test_bank_more_than_64_roots_and_segments(golden):
+    """128 templates = two passes of 64; a long capture is cut into several work items per capture."""
+    from ofdm_sync_math_b200 import engine
+    g = golden("zc_freq_awgn")
+    rx = g["rx"][0].astype(np.complex64)
+    rng = np.random.default_rng(3)
+    noise = lambda k: 0.3 * (rng.standard_normal(k) + 1j * rng.standard_normal(k)).astype(np.complex64)
+    long_cap = np.concatenate([noise(20000), rx, noise(12000)])
+    T = np.stack([zadoff_chu(i % 61 + 1) * (1.0 + 0.01 * i) for i in range(128)])      # template i = root i % 61 + 1, own scale
+    bm, bo = engine.zc_bank(long_cap[None], g["bin_indices"], T)
+    bm = bm.cpu().numpy()[0]; bo = bo.cpu().numpy()[0]
+    assert bm.shape == (128,)
+    for i in (24, 85, 127):                   # 24 and 85 are both root 25, the transmitted one (one per pass)
+        ref = orc.compute_frequency_metric(long_cap.astype(np.complex128), g["bin_indices"], T[i], float(np.sum(np.abs(T[i]) ** 2)))
+        assert abs(bm[i] - ref.max()) <= 5e-3 * max(ref.max(), 1e-3), (i, bm[i], ref.max())
+        if i != 127:
+            assert int(bo[i]) == int(np.argmax(ref)) == 20000 + int(g["peak"])
+    assert set(np.argsort(bm)[-2:].tolist()) == {24, 85}

@@ -1,8 +1,9 @@
 // Zadoff-Chu kernels.
 //
-// K4  zc_mf_kernel      matched filter by FFT overlap-save, hand-written shared-memory radix-2 FFT
-//                       (DIF forward -> pointwise multiply in bit-reversed order -> DIT inverse, so no
-//                       bit-reversal pass), fused with the sliding-energy normalisation.
+// K4  zc_mf_kernel      matched filter by FFT overlap-save, hand-written 4096-point FFT: three passes of radix-16
+//                       butterflies in registers with two shared-memory transposes (forward -> pointwise multiply in
+//                       digit-reversed order -> inverse, so no reordering pass), fused with the sliding-energy
+//                       normalisation.
 //                       Replaces np.convolve(x, conj(ref[::-1])) and np.convolve(|x|^2, ones) of
 //                       zc.py:115-126 and zc_v2.py:244-271, 486-495.
 // K5  zc_freq_kernel    zc_freq.compute_frequency_metric (zc_freq.py:62-99) as a sliding DFT of the used
@@ -34,35 +35,122 @@ __device__ __forceinline__ float2 ld_tw<float2>(const double2 *tw, int i)
     return __ldg(reinterpret_cast<const float2 *>(tw + ZF / 2) + i);
 }
 
-// natural order in -> bit-reversed order out
+// ---- 4096-point FFT = three passes of radix-16 butterflies held in registers ------------------------------------
+// 256 threads x 16 elements; between the passes the data is transposed through shared memory (two round trips per
+// transform instead of the twelve of a radix-2 ladder).  The array is padded by one element every 16 (index i lives at
+// i + i/16), which makes the stride-1, stride-16 and stride-256 access patterns of the three passes all conflict-free.
+// Forward: natural order in -> digit-reversed out (X[k0 + 16 k1 + 256 k2] at position 256 k0 + 16 k1 + k2); the inverse
+// runs the same flow graph backwards, so the pointwise product with the (equally permuted) filter spectrum needs no
+// reordering pass.
+constexpr int ZFP = ZF + ZF / 16;
+__device__ __forceinline__ int zpad(int i) { return i + (i >> 4); }
+
+template <typename C2>
+__device__ __forceinline__ C2 tw4096(const double2 *tw, int i)          // exp(-2 pi i * i / 4096), 0 <= i < 4096
+{
+    C2 w = ld_tw<C2>(tw, i & (ZF / 2 - 1));
+    if (i & (ZF / 2)) { w.x = -w.x; w.y = -w.y; }
+    return w;
+}
+
+// 16-point DFT in registers (radix-2 DIF, 4 stages, constants folded), natural order in and out.  INV: conjugate kernel.
+template <typename C2, bool INV>
+__device__ __forceinline__ void dft16(C2 (&v)[16])
+{
+    using T = decltype(v[0].x);
+    const T c1 = (T)0.92387953251128675613, s1 = (T)0.38268343236508977173, r2 = (T)0.70710678118654752440;
+    // W16^j, j = 0..7 (forward: exp(-2 pi i j / 16))
+    const T wr[8] = {(T)1, c1, r2, s1, (T)0, -s1, -r2, -c1};
+    const T wi[8] = {(T)0, -s1, -r2, -c1, (T)-1, -c1, -r2, -s1};
+#pragma unroll
+    for (int h = 8; h >= 1; h >>= 1) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if ((i & h) == 0) {
+                const int j = (i & (h - 1)) * (8 / h);         // twiddle exponent in units of W16
+                const C2 u = v[i], w = v[i + h];
+                v[i].x = u.x + w.x; v[i].y = u.y + w.y;
+                const T dx = u.x - w.x, dy = u.y - w.y;
+                if (j == 0) { v[i + h].x = dx; v[i + h].y = dy; }
+                else if (j == 4) { v[i + h].x = INV ? -dy : dy; v[i + h].y = INV ? dx : -dx; }
+                else {
+                    const T cr = wr[j], ci = INV ? -wi[j] : wi[j];
+                    v[i + h].x = dx * cr - dy * ci;
+                    v[i + h].y = dx * ci + dy * cr;
+                }
+            }
+        }
+    }
+    // bit-reversed -> natural
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int r = ((i & 1) << 3) | ((i & 2) << 1) | ((i & 4) >> 1) | ((i & 8) >> 3);
+        if (i < r) { const C2 t = v[i]; v[i] = v[r]; v[r] = t; }
+    }
+}
+
+// natural order in -> digit-reversed order out
 template <typename C2>
 __device__ void fft_dif(C2 *a, const double2 *tw)
 {
-    for (int s = 0; s < ZLOG; ++s) {
-        const int span = ZF >> (s + 1);
-        for (int t = threadIdx.x; t < ZF / 2; t += ZNT) {
-            const int j = t & (span - 1), i0 = ((t - j) << 1) + j, i1 = i0 + span;
-            const C2 u = a[i0], v = a[i1];
-            a[i0] = cadd(u, v);
-            a[i1] = cmul(csub(u, v), ld_tw<C2>(tw, j << s));
-        }
-        __syncthreads();
-    }
+    const int t = threadIdx.x;
+    C2 v[16];
+    // pass 1: stride 256, twiddle W4096^(t k0)
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = a[zpad(q * 256 + t)];
+    dft16<C2, false>(v);
+#pragma unroll
+    for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], tw4096<C2>(tw, t * q));
+#pragma unroll
+    for (int q = 0; q < 16; ++q) a[zpad(q * 256 + t)] = v[q];
+    __syncthreads();
+    // pass 2: inside each block of 256, stride 16, twiddle W256^(n0 k1)
+    const int k0 = t >> 4, n0 = t & 15;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = a[zpad(k0 * 256 + q * 16 + n0)];
+    dft16<C2, false>(v);
+#pragma unroll
+    for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], tw4096<C2>(tw, 16 * n0 * q));
+#pragma unroll
+    for (int q = 0; q < 16; ++q) a[zpad(k0 * 256 + q * 16 + n0)] = v[q];
+    __syncthreads();
+    // pass 3: 16 consecutive elements
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = a[t * 17 + q];
+    dft16<C2, false>(v);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) a[t * 17 + q] = v[q];
+    __syncthreads();
 }
-// bit-reversed order in -> natural order out, unscaled (multiply by 1/ZF afterwards)
+// digit-reversed order in -> natural order out, unscaled (multiply by 1/ZF afterwards)
 template <typename C2>
 __device__ void ifft_dit(C2 *a, const double2 *tw)
 {
-    for (int s = ZLOG - 1; s >= 0; --s) {
-        const int span = ZF >> (s + 1);
-        for (int t = threadIdx.x; t < ZF / 2; t += ZNT) {
-            const int j = t & (span - 1), i0 = ((t - j) << 1) + j, i1 = i0 + span;
-            const C2 u = a[i0], v = cmulc(a[i1], ld_tw<C2>(tw, j << s));
-            a[i0] = cadd(u, v);
-            a[i1] = csub(u, v);
-        }
-        __syncthreads();
-    }
+    const int t = threadIdx.x;
+    C2 v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = a[t * 17 + q];
+    dft16<C2, true>(v);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) a[t * 17 + q] = v[q];
+    __syncthreads();
+    const int k0 = t >> 4, n0 = t & 15;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = a[zpad(k0 * 256 + q * 16 + n0)];
+#pragma unroll
+    for (int q = 1; q < 16; ++q) v[q] = cmulc(v[q], tw4096<C2>(tw, 16 * n0 * q));
+    dft16<C2, true>(v);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) a[zpad(k0 * 256 + q * 16 + n0)] = v[q];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = a[zpad(q * 256 + t)];
+#pragma unroll
+    for (int q = 1; q < 16; ++q) v[q] = cmulc(v[q], tw4096<C2>(tw, t * q));
+    dft16<C2, true>(v);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) a[zpad(q * 256 + t)] = v[q];
+    __syncthreads();
 }
 
 __global__ void zc_twiddle_kernel(double2 *tw)
@@ -87,13 +175,13 @@ __global__ void __launch_bounds__(ZNT) zc_spectrum_kernel(const double2 *ref, in
     for (int m = threadIdx.x; m < ZF; m += ZNT) {
         double2 v = make_double2(0.0, 0.0);
         if (m < nr) { const double2 r = ref[nr - 1 - m]; v = make_double2(r.x, -r.y); e += r.x * r.x + r.y * r.y; }
-        a[m] = v;
+        a[zpad(m)] = v;
     }
     for (int o = 16; o > 0; o >>= 1) e += shfl_xor_f64(e, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
     __syncthreads();
     fft_dif<double2>(a, tw);
-    for (int m = threadIdx.x; m < ZF; m += ZNT) G[m] = a[m];
+    for (int m = threadIdx.x; m < ZF; m += ZNT) G[m] = a[zpad(m)];
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int w = 0; w < ZNT / 32; ++w) t += red[w];
@@ -112,7 +200,7 @@ __global__ void __launch_bounds__(ZNT) zc_mf_kernel(const void *x, int nb, int64
     // a: ZF complex | se: ZF+4 energy-prefix entries | pw: ZF window energies | acc: ZF branch-summed outputs
     // (float path: all fp32 -> 72 KB, 3 CTAs/SM; double path: 144 KB)
     C2 *a = reinterpret_cast<C2 *>(zsm);
-    T *se = reinterpret_cast<T *>(zsm + (size_t)ZF * sizeof(C2));
+    T *se = reinterpret_cast<T *>(zsm + (size_t)ZFP * sizeof(C2));
     T *pw = se + ZF + 4;
     C2 *acc = reinterpret_cast<C2 *>(pw + ZF);
     __shared__ double wtot[ZNT / 32];
@@ -135,7 +223,7 @@ __global__ void __launch_bounds__(ZNT) zc_mf_kernel(const void *x, int nb, int64
             const int64_t j = jb + m;
             C2 v; v.x = 0; v.y = 0;
             if (j >= 0 && j < n) { const In s = xb[j]; v.x = (T)s.x; v.y = (T)s.y; }
-            a[m] = v;
+            a[zpad(m)] = v;
         }
         if (tid == 0) se[0] = (T)0;
         __syncthreads();
@@ -145,7 +233,7 @@ __global__ void __launch_bounds__(ZNT) zc_mf_kernel(const void *x, int nb, int64
             const int s0 = tid * IPT;
             T run = (T)0;
             for (int m = 0; m < IPT; ++m) {
-                const C2 v = a[s0 + m];
+                const C2 v = a[zpad(s0 + m)];
                 run += v.x * v.x + v.y * v.y;
                 se[s0 + m + 1] = run;
             }
@@ -162,14 +250,14 @@ __global__ void __launch_bounds__(ZNT) zc_mf_kernel(const void *x, int nb, int64
         for (int m = tid; m < ZF; m += ZNT) {
             const double2 g = __ldg(G + m);
             C2 gg; gg.x = (T)g.x; gg.y = (T)g.y;
-            a[m] = cmul(a[m], gg);
+            a[zpad(m)] = cmul(a[zpad(m)], gg);
         }
         __syncthreads();
         ifft_dit<C2>(a, tw);
         for (int i = tid; i < V; i += ZNT) {
             // output k0+i is the window of local samples [i, i+nr-1]
             const T e = se[i + nr] - se[i];
-            const C2 y = a[nr - 1 + i];
+            const C2 y = a[zpad(nr - 1 + i)];
             T yr = y.x * (T)(1.0 / ZF), yi = y.y * (T)(1.0 / ZF);
             if (mode == 1) {                                   // zc_v2.py:257-271: per-branch normalisation
                 const T d = (T)ref_norm * sqrt(e > (T)1e-12 ? e : (T)1e-12);
@@ -323,16 +411,16 @@ OFS_API int ofs_zc_matched_filter(const void *x, int32_t in_dtype, int64_t n_fra
     OFS_CUDA(cudaMallocAsync((void **)&rn, sizeof(double), stream));
     zc_twiddle_kernel<<<(ZF / 2 + 255) / 256, 256, 0, stream>>>(tw);
     if (int rc = check_launch("zc_twiddle_kernel")) return rc;
-    OFS_CUDA(cudaFuncSetAttribute(zc_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ZF * sizeof(double2))));
-    zc_spectrum_kernel<<<1, ZNT, ZF * sizeof(double2), stream>>>((const double2 *)ref_c128, nr, tw, G, rn);
+    OFS_CUDA(cudaFuncSetAttribute(zc_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ZFP * sizeof(double2))));
+    zc_spectrum_kernel<<<1, ZNT, ZFP * sizeof(double2), stream>>>((const double2 *)ref_c128, nr, tw, G, rn);
     if (int rc = check_launch("zc_spectrum_kernel")) return rc;
     const int V = ZF - nr + 1;
     const int bpf = (int)((n + nr - 1 + V - 1) / V);
     const int64_t grid = (int64_t)bpf * n_frames;
     OFS_REQUIRE(grid < (1LL << 31), "ofs_zc_matched_filter: grid too large");
     const bool dbl = in_dtype == OFS_C128 || out_f64;
-    const size_t smem = dbl ? (size_t)ZF * 16 + (size_t)(2 * ZF + 4) * 8 + (size_t)ZF * 16
-                            : (size_t)ZF * 8 + (size_t)(2 * ZF + 4) * 4 + (size_t)ZF * 8;
+    const size_t smem = dbl ? (size_t)ZFP * 16 + (size_t)(2 * ZF + 4) * 8 + (size_t)ZF * 16
+                            : (size_t)ZFP * 8 + (size_t)(2 * ZF + 4) * 4 + (size_t)ZF * 8;
 #define OFS_MF_LAUNCH(T, DT)                                                                                       \
     do {                                                                                                           \
         auto kern = zc_mf_kernel<T, DT>;                                                                           \

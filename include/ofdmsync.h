@@ -239,6 +239,29 @@ int ofs_zc_freq_metric_fast(const void *x_c64, int64_t n_frames, int64_t n, int3
                             const void *templ_c64, int32_t nbins, double templ_energy, float *metric,
                             int64_t out_stride, void *stream);
 
+/* Impairment chain = channel.apply_channel (channel.py:51-98) -> core.apply_cfo (core.py:123-138) ->
+ * sync_aa.quantize_adc (sync_aa.py:263-291), batched on the device.
+ *   tx: complex64 / complex128 [n_rows][n_tx]; taps (optional): complex128[n_taps] -> full convolution, n_out = n_tx+n_taps-1
+ *   (no taps: n_out = n_tx).  Stream s reads faded row row_of_stream[s] (NULL: s), adds std_s * unit_noise[s][.] with
+ *   std_s = sqrt(mean|faded row|^2 / 10^(snr_db[s]/10) / 2) (unit_noise NULL: no noise), rotates by
+ *   exp(j 2 pi cfo_hz[s] n / fs) (cfo_hz NULL: none) and, when full_scale is given, quantises to `bits` bits:
+ *   out gets the quantised samples, out_iq (optional) the integer codes as int16 IQ.
+ *   All per-stream arrays live on the device.  faded_ws: [n_rows][n_out] samples of `dtype`; power_ws: double[n_rows]. */
+int ofs_channel_apply(const void *tx, int32_t dtype, int64_t n_rows, int64_t n_tx, const void *taps_c128, int32_t n_taps,
+                      int64_t n_streams, const int32_t *row_of_stream, const void *unit_noise, int64_t noise_stride,
+                      const double *snr_db, const double *cfo_hz, double fs, const double *full_scale, int32_t bits,
+                      void *out, int16_t *out_iq, int64_t out_stride, void *faded_ws, double *power_ws, void *stream);
+
+/* CP-correlation CFO estimators, one result per frame; x: (n_frames, n_branches, n), branches summed.
+ *   mode 0  core.estimate_cfo_from_cp               core.py:179-196   P = sum_n x[start+n] conj(x[start+n+N]), n < cp_len
+ *   mode 1  core.estimate_cfo_from_cp_robust        core.py:199-230   sum of P(d), window win_len, d in [start-span, start+span)
+ *   mode 2  core.estimate_cfo_from_cp_peak(_with_index) / find_cp_start_via_corr  core.py:233-336   first max of |P(d)|
+ * cfo_hz = -angle(P) fs / (2 pi N); best_d (optional): the offset used (mode 2), else start; P_c128 (optional).
+ * A frame whose windows leave the capture gets cfo = NaN, best_d = -1 (the reference raises on the mismatched slices). */
+int ofs_cp_cfo(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_branches, int64_t n, int64_t x_frame_stride,
+               int64_t x_branch_stride, const int64_t *starts, int32_t n_fft, int32_t cp_len, int32_t span, int32_t win_len,
+               int32_t mode, double fs, double *cfo_hz, int64_t *best_d, void *P_c128, void *stream);
+
 /* End-to-end sync over HOST buffers --------------------------------------------------------------- */
 typedef struct ofs_ctx ofs_ctx;
 int ofs_ctx_create(ofs_ctx **ctx, int device);

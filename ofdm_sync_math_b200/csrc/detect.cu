@@ -16,7 +16,7 @@
 
 namespace ofs {
 
-constexpr int DNT = 256;                    // threads per row-CTA
+constexpr int DNT = 256;                   // threads per row-CTA
 constexpr int64_t MASK_MAX_N = 1600000;     // row length limit of the bitmask kernels (200 KB of smem)
 
 int launch_metric_array(const void *x, int in_dtype, int64_t n_frames, int n_ant, int64_t n, int64_t xfs, int64_t xbs, int L,

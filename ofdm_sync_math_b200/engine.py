@@ -548,3 +548,65 @@ def zc_bank(rx, bin_indices, templates, n_fft: int = 2048, cp: int = 512):
     L.check(L.lib().ofs_zc_bank(_ptr(x), C.c_int64(F), C.c_int64(n), int(n_fft), int(cp), _ptr(bins), _ptr(T), int(nb), int(R),
                                 _ptr(bm), _ptr(bo), _stream()), "ofs_zc_bank")
     return bm, bo
+
+
+# ------------------------------------------------------------------------------------------- channel / CFO
+def channel_apply(tx, taps=None, *, row_of_stream=None, unit_noise=None, snr_db=None, cfo_hz=None, fs: float = 30.72e6,
+                  full_scale=None, bits: int = 12, want_iq: bool = False):
+    """channel.apply_channel -> core.apply_cfo -> sync_aa.quantize_adc on the device (ofs_channel_apply).
+    tx: [rows, n_tx] complex64 / complex128; taps: 1-D complex or None; unit_noise: [streams, n_out] unit-variance complex
+    normal samples per component (or None); snr_db / cfo_hz / full_scale: per-stream arrays (or None).
+    -> (out [streams, n_out] complex, out_iq int16 [streams, n_out, 2] or None)."""
+    t = tx if isinstance(tx, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(tx))
+    if t.dim() == 1:
+        t = t[None]
+    if t.dtype not in (torch.complex64, torch.complex128):
+        t = t.to(torch.complex128)
+    dev = _device()
+    t = t.to(dev).contiguous()
+    code = L.OFS_C64 if t.dtype == torch.complex64 else L.OFS_C128
+    rows, n_tx = t.shape
+    n_taps = 0
+    tp = None
+    if taps is not None:
+        tp = torch.as_tensor(np.ascontiguousarray(np.asarray(taps, dtype=np.complex128).reshape(-1))).to(dev)
+        n_taps = tp.numel()
+    n_out = n_tx + n_taps - 1 if tp is not None else n_tx
+    ros = None
+    S = rows
+    if row_of_stream is not None:
+        ros = torch.as_tensor(np.asarray(row_of_stream, dtype=np.int32)).to(dev)
+        S = ros.numel()
+    dv = lambda a: None if a is None else torch.as_tensor(np.broadcast_to(np.asarray(a, dtype=np.float64), (S,)).copy()).to(dev)
+    snr, cfo, fsc = dv(snr_db), dv(cfo_hz), dv(full_scale)
+    nz = None
+    if unit_noise is not None:
+        nz = unit_noise if isinstance(unit_noise, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(unit_noise))
+        nz = nz.to(device=dev, dtype=t.dtype).reshape(S, -1).contiguous()
+    out = torch.empty((S, n_out), dtype=t.dtype, device=dev)
+    iq = torch.empty((S, n_out, 2), dtype=torch.int16, device=dev) if want_iq else None
+    ws = torch.empty((rows, n_out), dtype=t.dtype, device=dev)
+    pw = torch.zeros(rows, dtype=torch.float64, device=dev)
+    L.check(L.lib().ofs_channel_apply(_ptr(t), code, C.c_int64(rows), C.c_int64(n_tx), _ptr(tp), int(n_taps), C.c_int64(S), _ptr(ros),
+                                      _ptr(nz), C.c_int64(0 if nz is None else nz.shape[1]), _ptr(snr), _ptr(cfo), C.c_double(fs),
+                                      _ptr(fsc), int(bits), _ptr(out), _ptr(iq), C.c_int64(n_out), _ptr(ws), _ptr(pw), _stream()),
+            "ofs_channel_apply")
+    return out, iq
+
+
+def cp_cfo(rx, starts, n_fft: int = 2048, cp_len: int = 512, fs: float = 30.72e6, mode: str = "plain", span: int | None = None,
+           win_len: int | None = None):
+    """core.estimate_cfo_from_cp / _robust / _peak_with_index (core.py:179-308) for a batch of frames.
+    -> (cfo_hz float64[F], best_d int64[F], P complex128[F]) tensors."""
+    x, code, _ = to_device(rx)
+    F, B, n = x.shape[0], x.shape[1], x.shape[2]
+    st = torch.as_tensor(np.broadcast_to(np.asarray(starts, dtype=np.int64), (F,)).copy()).to(x.device)
+    m = {"plain": 0, "robust": 1, "peak": 2}[mode]
+    sp = cp_len // 2 if span is None else int(max(0, span))                     # core.py:217,246
+    wl = cp_len // 2 if win_len is None else int(max(1, win_len))               # core.py:218
+    cfo = torch.empty(F, dtype=torch.float64, device=x.device)
+    bd = torch.empty(F, dtype=torch.int64, device=x.device)
+    P = torch.empty(F, dtype=torch.complex128, device=x.device)
+    L.check(L.lib().ofs_cp_cfo(_ptr(x), code, C.c_int64(F), int(B), C.c_int64(n), C.c_int64(B * n), C.c_int64(n), _ptr(st), int(n_fft),
+                               int(cp_len), int(sp), int(wl), int(m), C.c_double(fs), _ptr(cfo), _ptr(bd), _ptr(P), _stream()), "ofs_cp_cfo")
+    return cfo, bd, P

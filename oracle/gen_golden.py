@@ -362,6 +362,41 @@ def gen_cir_and_scale(out: Path) -> None:
     print("scale_sc", ends)
 
 
+def gen_channel_and_cfo(out: Path) -> None:
+    """the impairment chain channel.apply_channel (channel.py:51-98) -> core.apply_cfo (core.py:123-138)
+    -> sync_aa.quantize_adc (sync_aa.py:263-291) and the CP-correlation CFO estimators (core.py:179-336), run UNMODIFIED on
+    seeded inputs.  The AWGN is reproducible from `seed`: channel._compute_awgn_noise draws rng.standard_normal(shape) for
+    the real part, then again for the imaginary part."""
+    import channel, core, sc, sync_aa
+    cases = {}
+    for ci, (cir_name, snr, cfo, seed) in enumerate([("cir1", 10.0, 1000.0, 11), ("cir2", 0.0, -7500.0, 12), (None, 20.0, 250.0, 13)]):
+        rng = np.random.default_rng(seed)
+        pre = sc.build_sc_preamble(rng, include_cp=True)
+        pilot, _ = core.build_random_qpsk_symbol(rng, include_cp=True)
+        data, _ = core.build_random_qpsk_symbol(rng, include_cp=True)
+        tx = np.concatenate((np.zeros(core.TX_PRE_PAD_SAMPLES, complex), pre, pilot, data, np.zeros(300, complex)))
+        cir = None if cir_name is None else channel.load_measured_cir(cir_name)
+        rng2 = np.random.default_rng(1000 + seed)
+        rx = channel.apply_channel(tx, snr, rng2, channel_impulse_response=cir)
+        rx_cfo = core.apply_cfo(rx, cfo, core.SAMPLE_RATE_HZ)
+        fs_adc = 2.0 * float(np.sqrt(np.mean(np.abs(rx_cfo) ** 2)))
+        rx_q = sync_aa.quantize_adc(rx_cfo, fs_adc, 12)
+        pilot_cp_start = core.TX_PRE_PAD_SAMPLES + pre.size + (0 if cir is None else 170)
+        est = {}
+        for d_name, start in (("exact", pilot_cp_start), ("early", pilot_cp_start - 37), ("edge", 5), ("late", rx_cfo.shape[1] - 2560 - 120)):
+            r = [core.estimate_cfo_from_cp(rx_cfo, start, core.N_FFT, core.CYCLIC_PREFIX, core.SAMPLE_RATE_HZ),
+                 core.estimate_cfo_from_cp_robust(rx_cfo, start, core.N_FFT, core.CYCLIC_PREFIX, core.SAMPLE_RATE_HZ),
+                 core.estimate_cfo_from_cp_peak(rx_cfo, start, core.N_FFT, core.CYCLIC_PREFIX, core.SAMPLE_RATE_HZ)]
+            c4, d4 = core.estimate_cfo_from_cp_peak_with_index(rx_cfo, start, core.N_FFT, core.CYCLIC_PREFIX, core.SAMPLE_RATE_HZ, span=100)
+            d5 = core.find_cp_start_via_corr(rx_cfo, start, core.N_FFT, core.CYCLIC_PREFIX, search_half=300)
+            est[d_name] = np.array([start, *r, c4, d4, d5], dtype=np.float64)
+        cases.update({f"tx{ci}": tx, f"cir{ci}": np.zeros((0, 0), complex) if cir is None else cir, f"snr{ci}": snr, f"cfo{ci}": cfo,
+                      f"noise_seed{ci}": 1000 + seed, f"rx{ci}": rx, f"rx_cfo{ci}": rx_cfo, f"rx_q{ci}": rx_q, f"fs_adc{ci}": fs_adc,
+                      **{f"est_{k}{ci}": v for k, v in est.items()}})
+        print("channel/cfo", ci, cir_name, rx.shape, {k: v[:4].round(2).tolist() for k, v in est.items()})
+    np.savez_compressed(out / "channel_cfo.npz", **cases)
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -373,7 +408,7 @@ def main() -> None:
     _setup(a.ref)
     gens = dict(sc=gen_sc, minn=gen_minn, park=gen_park, combined=gen_combined, zc=gen_zc, zc_v2=gen_zc_v2,
                 zc_freq=gen_zc_freq, minn_rtl=gen_minn_rtl, detector_cases=gen_detector_cases,
-                cir_scale=gen_cir_and_scale)
+                cir_scale=gen_cir_and_scale, channel_cfo=gen_channel_and_cfo)
     for name, fn in gens.items():
         if a.only and name not in a.only.split(","):
             continue

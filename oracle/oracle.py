@@ -322,3 +322,81 @@ def metric_prefix_c64(x_c64: np.ndarray, n_fft: int, kind: int, want_pr: bool = 
     lib().orc_metric_prefix_c64(_p(x), i64(x.size), i64(n_fft), C.c_int(kind), _p(M),
                                 _p(P) if want_pr else None, _p(R) if want_pr else None)
     return (M, _cplx(P), R) if want_pr else M
+
+
+# ----------------------------------------------------------------------------- channel / impairments / CP-CFO
+# numpy restatements (small inputs only): these stages are float64 library calls in the reference.
+def channel_apply(tx, cir, snr_db: float, unit_noise):
+    """channel.apply_channel (channel.py:78-98) with the AWGN of channel._compute_awgn_noise (channel.py:51-75) expressed on
+    given unit-normal draws: noise = noise_std * unit_noise, noise_std = sqrt(mean|faded|^2 / snr / 2) per branch row.
+    cir: (branches, taps) or None -> (branches, L)."""
+    tx = np.asarray(tx)
+    faded = tx[np.newaxis, :] if cir is None else np.stack([np.convolve(tx, taps, mode="full") for taps in np.atleast_2d(cir)])
+    p = np.mean(np.abs(faded) ** 2, axis=1, keepdims=True)
+    std = np.sqrt(p / (10 ** (snr_db / 10)) / 2)
+    noise = std * np.asarray(unit_noise).reshape(faded.shape)
+    noise[p.squeeze(axis=1) == 0] = 0
+    return faded + noise
+
+
+def unit_noise_like_reference(seed: int, shape) -> np.ndarray:
+    """The draws channel._compute_awgn_noise makes from np.random.default_rng(seed): real part first, then imaginary."""
+    rng = np.random.default_rng(seed)
+    return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+
+def apply_cfo(x, cfo_hz: float, fs_hz: float):
+    """core.apply_cfo (core.py:123-138)."""
+    x = np.asarray(x)
+    n = np.arange(x.shape[-1], dtype=float)
+    return x * np.exp(1j * 2 * np.pi * cfo_hz * n / fs_hz)
+
+
+def quantize_adc(x, full_scale: float, bits: int = 12):
+    """sync_aa.quantize_adc (sync_aa.py:263-291) -> (quantised complex, integer codes [.., 2])."""
+    levels = 2 ** (bits - 1)
+    def q(v):
+        return np.round(np.clip(v / full_scale, -1.0, 1.0 - 1.0 / levels) * levels)
+    qr, qi = q(np.real(x)), q(np.imag(x))
+    return (qr + 1j * qi) / levels * full_scale, np.stack((qr, qi), axis=-1).astype(np.int16)
+
+
+def _cp_P(x, d, n_fft, w):
+    return np.sum(x[:, d:d + w] * np.conj(x[:, d + n_fft:d + n_fft + w]))
+
+
+def estimate_cfo_from_cp(rx, start, n_fft, cp_len, fs_hz):
+    """core.py:179-196."""
+    x = np.atleast_2d(np.asarray(rx))
+    return float(-np.angle(_cp_P(x, start, n_fft, cp_len)) * fs_hz / (2 * np.pi * n_fft))
+
+
+def estimate_cfo_from_cp_robust(rx, start, n_fft, cp_len, fs_hz, span=None, win_len=None):
+    """core.py:199-230."""
+    x = np.atleast_2d(np.asarray(rx))
+    L = x.shape[1]
+    span = cp_len // 2 if span is None else int(max(0, span))
+    win = cp_len // 2 if win_len is None else int(max(1, win_len))
+    d_lo, d_hi = max(0, start - span), min(L - (n_fft + win), start + span)
+    if d_hi <= d_lo:
+        return estimate_cfo_from_cp(x, start, n_fft, min(cp_len, win), fs_hz)
+    P = 0j
+    for d in range(d_lo, d_hi):
+        P += _cp_P(x, d, n_fft, win)
+    return float(-np.angle(P) * fs_hz / (2 * np.pi * n_fft))
+
+
+def estimate_cfo_from_cp_peak_with_index(rx, start, n_fft, cp_len, fs_hz, span=None):
+    """core.py:233-308 (first maximum of |P(d)|, strict >) -> (cfo_hz, best_d)."""
+    x = np.atleast_2d(np.asarray(rx))
+    L = x.shape[1]
+    span = cp_len // 2 if span is None else int(max(0, span))
+    d_lo, d_hi = max(0, start - span), min(L - (n_fft + cp_len), start + span)
+    if d_hi <= d_lo:
+        return estimate_cfo_from_cp(x, start, n_fft, cp_len, fs_hz), start
+    best, bm, bd = 0j, -1.0, d_lo
+    for d in range(d_lo, d_hi):
+        P = _cp_P(x, d, n_fft, cp_len)
+        if abs(P) > bm:
+            bm, best, bd = abs(P), P, d
+    return float(-np.angle(best) * fs_hz / (2 * np.pi * n_fft)), int(bd)

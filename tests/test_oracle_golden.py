@@ -229,3 +229,33 @@ def test_prefix_scale_path_matches_literal():
         M0, P0, R0 = fn(x.astype(np.complex128))
         close(P, P0, 1e-12 * 50); close(R, R0, 1e-12)
         assert np.max(np.abs(M - M0) / np.maximum(M0, 1e-6)) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------- SURVEY 8(f) rows 1-2
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_oracle_channel_chain_vs_reference(golden, ci):
+    """channel.apply_channel -> core.apply_cfo -> sync_aa.quantize_adc and the CP-CFO estimators: oracle restatement vs the
+    outputs of the unmodified reference (oracle/gen_golden.py::gen_channel_and_cfo)."""
+    g = golden("channel_cfo")
+    tx, cir = g[f"tx{ci}"], g[f"cir{ci}"]
+    cir = None if cir.size == 0 else cir
+    rx_ref = g[f"rx{ci}"]
+    unit = orc.unit_noise_like_reference(int(g[f"noise_seed{ci}"]), rx_ref.shape)
+    rx = orc.channel_apply(tx, cir, float(g[f"snr{ci}"]), unit)
+    assert rx.shape == rx_ref.shape and np.abs(rx - rx_ref).max() <= 1e-12 * np.abs(rx_ref).max()
+    rc = orc.apply_cfo(rx, float(g[f"cfo{ci}"]), 30.72e6)
+    assert np.abs(rc - g[f"rx_cfo{ci}"]).max() <= 1e-12 * np.abs(rx_ref).max()
+    q, codes = orc.quantize_adc(g[f"rx_cfo{ci}"], float(g[f"fs_adc{ci}"]), 12)
+    assert np.array_equal(q, g[f"rx_q{ci}"])
+    assert codes.min() >= -2048 and codes.max() <= 2047
+    for name in ("exact", "early", "edge", "late"):
+        e = g[f"est_{name}{ci}"]
+        start = int(e[0])
+        x = g[f"rx_cfo{ci}"]
+        assert abs(orc.estimate_cfo_from_cp(x, start, 2048, 512, 30.72e6) - e[1]) <= 1e-6
+        assert abs(orc.estimate_cfo_from_cp_robust(x, start, 2048, 512, 30.72e6) - e[2]) <= 1e-6
+        c, d = orc.estimate_cfo_from_cp_peak_with_index(x, start, 2048, 512, 30.72e6)
+        assert abs(c - e[3]) <= 1e-6
+        c, d = orc.estimate_cfo_from_cp_peak_with_index(x, start, 2048, 512, 30.72e6, span=100)
+        assert abs(c - e[4]) <= 1e-6 and d == int(e[5])
+        assert orc.estimate_cfo_from_cp_peak_with_index(x, start, 2048, 512, 1.0, span=300)[1] == int(e[6])

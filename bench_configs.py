@@ -40,7 +40,7 @@ def timeit(fn, steps=5, warmup=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
-    ap.add_argument("--cases", default="minn,iq16,combined,park,zc,zcfreq,bank,aa64,rtl,tile")
+    ap.add_argument("--cases", default="minn,iq16,chan,combined,park,zc,zcfreq,bank,aa64,rtl,tile")
     a = ap.parse_args()
     import numpy as np
     import torch
@@ -80,6 +80,21 @@ def main():
         emit("cfg2 sc metric kernel, int16-IQ input (stripe)", ms_k, F * n, alg_bytes=F * (4 * n + 4 * (n - 2047)))
         emit("cfg2 sc metric + plateau + CFO, int16-IQ input", ms, F * n, alg_bytes=F * (4 * n + 4 * (n - 2047)))
         del xi, plan
+    if "chan" in cases:
+        # impairment chain, 32 tx rows -> 1024 streams x 262144 (FIR once per row; noise + CFO + ADC per stream)
+        S, n, nb = max(int(1024 * a.scale), 8), 262144, 32
+        cirs = synth.load_cirs()
+        rng = np.random.default_rng(3)
+        n_tx = n - (cirs["cir1"].shape[1] - 1)
+        base = torch.as_tensor(np.stack([np.tile(synth.frame(rng, "sc"), (n_tx + 9016) // 9017)[:n_tx] for _ in range(nb)]).astype(np.complex64)).to(dev)
+        noise = torch.view_as_complex(torch.randn((S, n, 2), device=dev, dtype=torch.float32))
+        rows = (np.arange(S) % nb).astype(np.int32)
+        snr = np.array([0.0, 5.0, 10.0, 15.0, 20.0])[np.arange(S) % 5]; cfo = np.linspace(-10e3, 10e3, S); fsc = np.full(S, 4.0)
+        ms = timeit(lambda: engine.channel_apply(base, cirs["cir1"][1], row_of_stream=rows, unit_noise=noise, snr_db=snr, cfo_hz=cfo,
+                                                 fs=30.72e6, full_scale=fsc, want_iq=True), steps=3, warmup=2)
+        emit("8f-1 impairment chain: 1100-tap FIR (overlap-save FFT) + AWGN + CFO + 12-bit ADC -> c64 + int16 IQ", ms, S * n,
+             alg_bytes=S * n * (8 + 8 + 8 + 4), note="per stream sample: faded row 8 B (L2) + noise 8 B in, c64 8 B + iq 4 B out")
+        del base, noise
     if "combined" in cases:
         F, n = max(int(1024 * a.scale), 8), 1 << 19
         x = synth.make_batch_device(F, n, "minn", seed=8, device=dev, chunk=32)[:, None]

@@ -58,50 +58,58 @@ template <typename T>
 __global__ void __launch_bounds__(256) chan_impair_kernel(const ImpairParams p)
 {
     using C2 = typename CT<T>::type;
+    constexpr int PER = 4;                                     // samples per thread: 1024 per CTA
+    __shared__ double s_std, s_ratio;
     const int64_t s = blockIdx.y;
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= p.n) return;
     const int64_t row = p.row_of_stream ? p.row_of_stream[s] : s;
-    const C2 f = reinterpret_cast<const C2 *>(p.faded)[row * p.faded_stride + i];
-    double vr = (double)f.x, vi = (double)f.y;
-    if (p.noise) {
+    if (threadIdx.x == 0) {
         // channel.py:55-75: noise_std = sqrt(signal_power / snr_linear / 2); all-zero rows get no noise
-        const double pw = p.power[row];
-        if (pw > 0.0) {
-            const double std = sqrt(pw / pow(10.0, p.snr_db[s] / 10.0) / 2.0);
-            const C2 nz = reinterpret_cast<const C2 *>(p.noise)[s * p.noise_stride + i];
-            vr += std * (double)nz.x; vi += std * (double)nz.y;
+        double sd = 0.0;
+        if (p.noise) { const double pw = p.power[row]; if (pw > 0.0) sd = sqrt(pw / pow(10.0, p.snr_db[s] / 10.0) / 2.0); }
+        s_std = sd;
+        s_ratio = p.cfo_hz ? p.cfo_hz[s] / p.fs : 0.0;
+    }
+    __syncthreads();
+    const double std = s_std;
+    const double fsc = p.full_scale ? p.full_scale[s] : 1.0, levels = (double)(1 << (p.bits - 1));
+    const double hi = 1.0 - 1.0 / levels;
+    const C2 *frow = reinterpret_cast<const C2 *>(p.faded) + row * p.faded_stride;
+    const C2 *nrow = p.noise ? reinterpret_cast<const C2 *>(p.noise) + s * p.noise_stride : nullptr;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int64_t i = ((int64_t)blockIdx.x * PER + k) * 256 + threadIdx.x;
+        if (i >= p.n) break;
+        const C2 f = frow[i];
+        double vr = (double)f.x, vi = (double)f.y;
+        if (nrow && std > 0.0) { const C2 nz = nrow[i]; vr += std * (double)nz.x; vi += std * (double)nz.y; }
+        if (p.cfo_hz) {
+            // core.py:131-132: tone = exp(1j * 2 pi cfo n / fs)
+            double sn, cs;
+            if (sizeof(T) == 8) {
+                sincos(2.0 * 3.14159265358979323846 * p.cfo_hz[s] * (double)i / p.fs, &sn, &cs);
+            } else {
+                const double turns = s_ratio * (double)i;
+                float fs_, fc_;
+                sincospif((float)(2.0 * (turns - rint(turns))), &fs_, &fc_);
+                sn = fs_; cs = fc_;
+            }
+            const double r = vr * cs - vi * sn;
+            vi = vr * sn + vi * cs;
+            vr = r;
         }
-    }
-    if (p.cfo_hz) {
-        // core.py:131-132: tone = exp(1j * 2 pi cfo n / fs)
-        double sn, cs;
-        if (sizeof(T) == 8) {
-            sincos(2.0 * 3.14159265358979323846 * p.cfo_hz[s] * (double)i / p.fs, &sn, &cs);
-        } else {
-            const double turns = p.cfo_hz[s] * (double)i / p.fs;
-            float fs_, fc_;
-            sincospif((float)(2.0 * (turns - rint(turns))), &fs_, &fc_);
-            sn = fs_; cs = fc_;
+        if (p.full_scale) {
+            // sync_aa.py:276-289: x / full_scale -> clip [-1, 1 - 1/levels] -> round half to even (np.round) -> rescale
+            double a = vr / fsc, b = vi / fsc;
+            a = a < -1.0 ? -1.0 : (a > hi ? hi : a);
+            b = b < -1.0 ? -1.0 : (b > hi ? hi : b);
+            const double qa = rint(a * levels), qb = rint(b * levels);
+            if (p.out_iq) p.out_iq[s * p.out_stride + i] = make_short2((short)qa, (short)qb);
+            vr = qa / levels * fsc; vi = qb / levels * fsc;
         }
-        const double r = vr * cs - vi * sn;
-        vi = vr * sn + vi * cs;
-        vr = r;
-    }
-    if (p.full_scale) {
-        // sync_aa.py:276-289: x / full_scale -> clip [-1, 1 - 1/levels] -> round half to even (np.round) -> rescale
-        const double fsc = p.full_scale[s], levels = (double)(1 << (p.bits - 1));
-        const double hi = 1.0 - 1.0 / levels;
-        double a = vr / fsc, b = vi / fsc;
-        a = a < -1.0 ? -1.0 : (a > hi ? hi : a);
-        b = b < -1.0 ? -1.0 : (b > hi ? hi : b);
-        const double qa = rint(a * levels), qb = rint(b * levels);
-        if (p.out_iq) p.out_iq[s * p.out_stride + i] = make_short2((short)qa, (short)qb);
-        vr = qa / levels * fsc; vi = qb / levels * fsc;
-    }
-    if (p.out) {
-        C2 o; o.x = (T)vr; o.y = (T)vi;
-        reinterpret_cast<C2 *>(p.out)[s * p.out_stride + i] = o;
+        if (p.out) {
+            C2 o; o.x = (T)vr; o.y = (T)vi;
+            reinterpret_cast<C2 *>(p.out)[s * p.out_stride + i] = o;
+        }
     }
 }
 
@@ -274,7 +282,7 @@ OFS_API int ofs_channel_apply(const void *tx, int32_t dtype, int64_t n_rows, int
     p.full_scale = full_scale; p.out = out; p.out_iq = reinterpret_cast<short2 *>(out_iq); p.n = n_out; p.faded_stride = n_out;
     p.noise_stride = noise_stride; p.out_stride = out_stride; p.fs = fs; p.bits = bits;
     OFS_REQUIRE(n_streams < 65536, "ofs_channel_apply: at most 65535 streams per call");
-    const dim3 grid((unsigned)((n_out + 255) / 256), (unsigned)n_streams);
+    const dim3 grid((unsigned)((n_out + 1023) / 1024), (unsigned)n_streams);
     if (dtype == OFS_C64) chan_impair_kernel<float><<<grid, 256, 0, stream>>>(p);
     else chan_impair_kernel<double><<<grid, 256, 0, stream>>>(p);
     return check_launch("chan_impair_kernel");

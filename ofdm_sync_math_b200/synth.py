@@ -114,10 +114,12 @@ def aa_capture_host(n_samples: int, n_ant: int, seed: int, half_len: int = 512, 
 
 
 def make_batch_device(n_frames: int, n_samples: int, kind: str = "sc", seed: int = 0, device=None, n_base: int = 32,
-                      chunk: int = 64):
-    """[n_frames, n_samples] complex64 on the device: base frames tiled, cir1-ch1 (even) / cir2-ch1 (odd) by FFT
-    convolution, SNR cycling {0,5,10,15,20} dB, CFO = linspace(-10 kHz, +10 kHz) (SURVEY.md 8d cfg 2)."""
+                      chunk: int = 1024, want_iq: bool = False, full_scale_ratio: float = 4.0):
+    """[n_frames, n_samples] complex64 on the device (and int16 IQ with want_iq): base frames tiled, cir1-ch1 (even) /
+    cir2-ch1 (odd), SNR cycling {0,5,10,15,20} dB, CFO = linspace(-10 kHz, +10 kHz) (SURVEY.md 8d cfg 2), generated by the
+    package's own impairment chain (ofs_channel_apply: overlap-save FIR, AWGN, CFO, ADC); torch only draws the Philox noise."""
     import torch
+    from . import engine
     device = device or torch.device("cuda", torch.cuda.current_device())
     cirs = load_cirs()
     taps = cirs["cir1"].shape[1]
@@ -125,25 +127,22 @@ def make_batch_device(n_frames: int, n_samples: int, kind: str = "sc", seed: int
     rng = np.random.default_rng(seed)
     base = np.stack([np.tile(frame(rng, kind), (n_tx + 9016) // 9017)[:n_tx] for _ in range(n_base)]).astype(np.complex64)
     base_d = torch.as_tensor(base).to(device)
-    nfft = 1 << int(np.ceil(np.log2(n_samples)))
-    H = [torch.fft.fft(torch.as_tensor(cirs[k][1].astype(np.complex64)).to(device), n=nfft) for k in ("cir1", "cir2")]
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
     out = torch.empty((n_frames, n_samples), dtype=torch.complex64, device=device)
-    snrs = torch.tensor([0.0, 5.0, 10.0, 15.0, 20.0], device=device)
-    cfos = torch.linspace(-10e3, 10e3, max(n_frames, 2), device=device)[:n_frames]
-    t = torch.arange(n_samples, device=device, dtype=torch.float32)
-    for f0 in range(0, n_frames, chunk):
-        f1 = min(f0 + chunk, n_frames)
-        fidx = torch.arange(f0, f1, device=device)
-        tx = base_d[fidx % n_base]
-        X = torch.fft.fft(tx, n=nfft)
-        Hsel = torch.stack([H[int(i) & 1] for i in range(f0, f1)])
-        faded = torch.fft.ifft(X * Hsel)[:, :n_samples]
-        p = faded.abs().square().mean(dim=1, keepdim=True)
-        std = torch.sqrt(p / torch.pow(10.0, snrs[fidx % 5][:, None] / 10.0) / 2.0)
-        noise = torch.randn((f1 - f0, n_samples, 2), generator=gen, device=device, dtype=torch.float32)
-        rx = faded + std * torch.view_as_complex(noise)
-        ph = (2.0 * np.pi / FS) * cfos[fidx][:, None] * t[None, :]
-        out[f0:f1] = rx * torch.polar(torch.ones_like(ph), ph)
-    return out
+    iq = torch.empty((n_frames, n_samples, 2), dtype=torch.int16, device=device) if want_iq else None
+    snrs = np.array([0.0, 5.0, 10.0, 15.0, 20.0])
+    cfos = np.linspace(-10e3, 10e3, max(n_frames, 2))[:n_frames]
+    for par, name in ((0, "cir1"), (1, "cir2")):
+        idx = np.arange(par, n_frames, 2)
+        for c0 in range(0, idx.size, chunk):
+            f = idx[c0:c0 + chunk]
+            noise = torch.view_as_complex(torch.randn((f.size, n_samples, 2), generator=gen, device=device, dtype=torch.float32))
+            o, q = engine.channel_apply(base_d, cirs[name][1], row_of_stream=(f % n_base).astype(np.int32), unit_noise=noise,
+                                        snr_db=snrs[f % 5], cfo_hz=cfos[f], fs=FS,
+                                        full_scale=np.full(f.size, full_scale_ratio) if want_iq else None, want_iq=want_iq)
+            fi = torch.as_tensor(f).to(device)
+            out[fi] = o
+            if want_iq:
+                iq[fi] = q
+    return (out, iq) if want_iq else out

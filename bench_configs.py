@@ -101,8 +101,8 @@ def main():
 
         def run():
             m = engine.metric(x, "minn", 2048, want_pr=False, path="stripe", want_chunk_max=True)
-            s = engine.metric(x, "sc_both", 2048, want_pr=False, path="stripe")
-            g = engine.sc_gate(s.M, 0.6)
+            s = engine.metric(x, "sc_both", 2048, want_pr=False, path="stripe", want_chunk_max=True)
+            g = engine.sc_gate(s.M, 0.6, chunk_max=s.chunk_max, toff=2047)
             return engine.find_minn_peak_gated(m.M, 16, g)
         ms = timeit(run, steps=3, warmup=2)
         emit("cfg3 combined: Minn + S&C(both halves) metrics + gate + gated peak", ms, F * n, alg_bytes=2 * F * (8 * n + 4 * (n - 2047)),

@@ -125,6 +125,9 @@ int ofs_find_minn_peak_pruned(const ofs_rows *M, const float *chunk_max, int64_t
 
 /* combined_sc_min: S&C gate construction :337-351 (gate = M_sc/max >= thr, seeded with argmax) */
 int ofs_sc_gate(const ofs_rows *Msc, double threshold, uint8_t *gate, int64_t gate_stride, void *stream);
+/* same, reading M only in the chunks whose maximum (chunk_max of the stripe metric kernel) can reach the gate level */
+int ofs_sc_gate_pruned(const ofs_rows *Msc, const float *chunk_max, int64_t cm_stride, int32_t toff, double threshold,
+                       uint8_t *gate, int64_t gate_stride, void *stream);
 /* combined_sc_min.find_minn_peak :212-259 + _streaming_peak_detector :183-209.
  * peak: -1 empty M (reference returns 0), -3 empty gate region (ValueError). */
 int ofs_find_minn_peak_gated(const ofs_rows *M, int32_t smooth_win, const uint8_t *gate, int64_t gate_stride,

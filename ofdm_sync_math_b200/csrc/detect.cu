@@ -636,6 +636,49 @@ __global__ void __launch_bounds__(DNT) sc_gate_kernel(RowView r, double thr, uin
     if (any == LLONG_MAX && tid == 0) gate[row * gstride + best.i] = 1;   // seed with the strongest sample
 }
 
+// Same gate with the chunk maxima of the stripe metric kernel: the row maximum comes from the maxima alone, and a chunk
+// whose maximum cannot reach thr * max is all zeros -- M is read only where the gate can be set (a few chunks per frame).
+// One warp per chunk; identical output to sc_gate_kernel (the per-sample test is the same float64 expression).
+__global__ void __launch_bounds__(DNT) sc_gate_pruned_kernel(RowView r, double thr, uint8_t *gate, int64_t gstride, const float *cm,
+                                                             int64_t cm_stride, int toff)
+{
+    __shared__ ArgVal sh_av[DNT / 32];
+    const int64_t row = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t n = r.n;
+    const int64_t nch = (n + toff + 255) / 256;
+    const float *cmr = cm + row * cm_stride;
+    ArgVal best{0.0, -1};
+    for (int64_t c = tid; c < nch; c += DNT) {
+        const double v = (double)cmr[c];
+        if (best.i < 0 || v > best.v) { best.v = v; best.i = c; }
+    }
+    best = block_argmax<false>(best, sh_av);
+    const double mx = best.v;                        // > 0 and thr <= 1 guaranteed by the launcher's fallback rule
+    const double level_lo = thr * mx * (1.0 - 1e-9);
+    uint8_t *g = gate + row * gstride;
+    for (int64_t c = warp; c < nch; c += DNT / 32) {
+        const int64_t d0 = c * 256 - toff;           // metric index of the chunk's first sample
+        const bool live = (double)cmr[c] >= level_lo;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int64_t d = d0 + 32 * k + lane;
+            if (d < 0 || d >= n) continue;
+            g[d] = live ? (uint8_t)(r.at(row, d) / mx >= thr) : (uint8_t)0;
+        }
+    }
+}
+
+// all-zero rows (every chunk maximum 0): v >= thr is false everywhere, the reference seeds the gate with argmax = index 0
+__global__ void sc_gate_seed_kernel(const float *cm, int64_t cm_stride, int64_t nch, int64_t n_rows, uint8_t *gate, int64_t gstride)
+{
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    float m = 0.f;
+    for (int64_t c = 0; c < nch; ++c) m = fmaxf(m, cm[row * cm_stride + c]);
+    if (!(m > 0.f)) gate[row * gstride] = 1;
+}
+
 __global__ void __launch_bounds__(DNT) gated_peak_kernel(RowView r, int smooth_win, const uint8_t *gate,
                                                          int64_t gstride, int has_bounds, int64_t b_lo,
                                                          int64_t b_hi, int64_t *peak)
@@ -937,13 +980,32 @@ OFS_API int ofs_find_minn_peak(const ofs_rows *M, int32_t smooth_win, double gat
                                      gate_span, Ms, stream);
 }
 
-OFS_API int ofs_sc_gate(const ofs_rows *Msc, double threshold, uint8_t *gate, int64_t gate_stride, void *stream)
+OFS_API int ofs_sc_gate_pruned(const ofs_rows *Msc, const float *chunk_max, int64_t cm_stride, int32_t toff, double threshold,
+                               uint8_t *gate, int64_t gate_stride, void *stream)
 {
     if (int rc = rows_ok(Msc, "ofs_sc_gate")) return rc;
     OFS_REQUIRE(gate && gate_stride >= Msc->n, "ofs_sc_gate: bad gate buffer");
+    OFS_REQUIRE(!chunk_max || (toff >= 0 && cm_stride >= (Msc->n + toff + 255) / 256), "ofs_sc_gate: bad chunk_max geometry");
     if (Msc->n_rows == 0 || Msc->n == 0) return OFS_OK;
+    // pruned form: float32 rows from the stripe kernel (non-negative metric, so a positive row maximum exists unless the row
+    // is all zero -- then chunk maxima are all zero, nothing passes and the seed rule needs the full kernel) and thr in (0, 1]
+    if (chunk_max && !Msc->f64 && threshold > 0.0 && threshold <= 1.0) {
+        sc_gate_pruned_kernel<<<(unsigned)Msc->n_rows, DNT, 0, (cudaStream_t)stream>>>(view(Msc), threshold, gate, gate_stride, chunk_max,
+                                                                                     cm_stride, toff);
+        if (int rc = check_launch("sc_gate_pruned_kernel")) return rc;
+        // rows whose maximum is zero get the reference's seed (argmax of an all-zero row = index 0)
+        sc_gate_seed_kernel<<<(unsigned)((Msc->n_rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(chunk_max, cm_stride,
+                                                                                                 (Msc->n + toff + 255) / 256, Msc->n_rows, gate,
+                                                                                                 gate_stride);
+        return check_launch("sc_gate_seed_kernel");
+    }
     sc_gate_kernel<<<(unsigned)Msc->n_rows, DNT, 0, (cudaStream_t)stream>>>(view(Msc), threshold, gate, gate_stride);
     return check_launch("sc_gate_kernel");
+}
+
+OFS_API int ofs_sc_gate(const ofs_rows *Msc, double threshold, uint8_t *gate, int64_t gate_stride, void *stream)
+{
+    return ofs_sc_gate_pruned(Msc, nullptr, 0, 0, threshold, gate, gate_stride, stream);
 }
 
 OFS_API int ofs_find_minn_peak_gated(const ofs_rows *M, int32_t smooth_win, const uint8_t *gate, int64_t gate_stride,

@@ -176,12 +176,14 @@ def find_minn_peak(M: torch.Tensor, smooth_win: int = 8, gate_threshold: float =
     return peak, span, Ms
 
 
-def sc_gate(M_sc: torch.Tensor, threshold: float = 0.6) -> torch.Tensor:
-    """combined_sc_min.py:337-351 -> uint8 gate [rows, n]."""
+def sc_gate(M_sc: torch.Tensor, threshold: float = 0.6, chunk_max: torch.Tensor | None = None, toff: int = 0) -> torch.Tensor:
+    """combined_sc_min.py:337-351 -> uint8 gate [rows, n].  chunk_max / toff (from the stripe metric) skip the chunks that
+    cannot reach the gate level."""
     rows, M_sc = _rows(M_sc)
-    gate = torch.zeros(M_sc.shape, dtype=torch.uint8, device=M_sc.device)
-    L.check(L.lib().ofs_sc_gate(C.byref(rows), C.c_double(threshold), _ptr(gate), C.c_int64(gate.stride(0) if gate.shape[0] > 1 else gate.shape[1]),
-                                _stream()), "ofs_sc_gate")
+    gate = torch.empty(M_sc.shape, dtype=torch.uint8, device=M_sc.device)
+    L.check(L.lib().ofs_sc_gate_pruned(C.byref(rows), _ptr(chunk_max), C.c_int64(0 if chunk_max is None else chunk_max.stride(0)), int(toff),
+                                       C.c_double(threshold), _ptr(gate), C.c_int64(gate.stride(0) if gate.shape[0] > 1 else gate.shape[1]),
+                                       _stream()), "ofs_sc_gate")
     return gate
 
 

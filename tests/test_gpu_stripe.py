@@ -138,6 +138,16 @@ def test_batched_detectors_vs_oracle():
         assert np.array_equal(gh[f], orc.sc_gate(Msch[f], 0.6))
     pg = engine.find_minn_peak_gated(Mm, 16, gate).cpu().numpy()
     assert pg.tolist() == [orc.find_minn_peak_gated(Mmh[f], 16, gh[f]) for f in range(xm.shape[0])]
+    # the chunk-max pruned gate must be the same mask, for several thresholds and with an all-zero row (seed rule)
+    xz = xm.copy(); xz[2] = 0
+    rs = engine.metric(_dev(xz), "sc_both", 2048, want_pr=False, path="stripe", want_chunk_max=True)
+    for thr in (0.6, 0.05, 1.0):
+        g0 = engine.sc_gate(rs.M, thr).cpu().numpy()
+        g1 = engine.sc_gate(rs.M, thr, chunk_max=rs.chunk_max, toff=2047).cpu().numpy()
+        assert np.array_equal(g0, g1)
+        Mz = rs.M.cpu().numpy().astype(np.float64)
+        for f in range(xz.shape[0]):
+            assert np.array_equal(g1[f].astype(bool), orc.sc_gate(Mz[f], thr))
 
 
 def test_pruned_detectors_equal_unpruned():

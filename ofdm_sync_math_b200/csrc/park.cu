@@ -98,10 +98,134 @@ __global__ void __launch_bounds__(PNT) park_kernel(const void *x, int nb, int64_
     }
 }
 
+// ---- fast variant (h % 8 == 0): 8 outputs x 8 lags per register group, de-interleaved shared memory ------------------
+// Thread t owns outputs 8t .. 8t+7 of the tile, so every sample index it touches is 8t + (compile-time constant) + (a
+// multiple of 8).  Samples are staged de-interleaved by 8 (logical i -> sub-array i % 8, slot i / 8): the sub-array is
+// then a compile-time choice and the slot is t + const, i.e. consecutive across the warp -- conflict-free LDS, where
+// the plain layout had an 8-way bank conflict on every load (32-byte thread stride).  30 loads feed 64 complex MACs
+// (30 B per FMA instruction: under the 128 B/clk shared-memory port at the full FMA rate).  The energy E(d) is a sliding
+// sum and is no longer recomputed per lag (it was 1/3 of the FMAs).
+constexpr int QNT2 = 128, QO = 8, QK = 8, QTILE = QNT2 * QO;
+
+template <typename T, int DT>
+__global__ void __launch_bounds__(QNT2) park_kernel_v2(const void *x, int nb, int64_t L, int64_t xfs, int64_t xbs, int h,
+                                                      int64_t n_out, int64_t out_stride, int out_f64, void *M, void *P, void *E,
+                                                      int tiles_per_frame)
+{
+    extern __shared__ __align__(16) unsigned char psm[];
+    Cx<T> *xs = reinterpret_cast<Cx<T> *>(psm);
+    const int64_t frame = blockIdx.x / tiles_per_frame;
+    const int tile = blockIdx.x % tiles_per_frame;
+    const int64_t i0 = (int64_t)tile * QTILE;                // first output index of the tile (d = h + i)
+    // logical index s <-> sample j = jbase + s, jbase = i0 - 8 (a multiple of 8 below the first sample needed, i0 + 1 - ...)
+    const int span = QTILE + 2 * h + 16;                     // multiple of 8
+    const int sub = span / 8;                                // slots per sub-array
+    using In = typename InT<DT>::type;
+    const int tid = threadIdx.x;
+    const int64_t jbase = i0 - 8;
+    double accr[QO], acci[QO], acce[QO];
+#pragma unroll
+    for (int i = 0; i < QO; ++i) accr[i] = acci[i] = acce[i] = 0.0;
+
+    for (int b = 0; b < nb; ++b) {
+        const In *xb = reinterpret_cast<const In *>(x) + frame * xfs + (int64_t)b * xbs;
+        __syncthreads();
+        for (int s = tid; s < span; s += QNT2) {
+            const int64_t j = jbase + s;
+            Cx<T> v{(T)0, (T)0};
+            if (j >= 0 && j < L) { const In a = xb[j]; v.x = (T)a.x; v.y = (T)a.y; }
+            xs[(s & 7) * sub + (s >> 3)] = v;
+        }
+        __syncthreads();
+        // x[d_o] for output o of this thread sits at logical index c = h + 8 + 8 tid + o  (d = h + i0 + 8 tid + o)
+        const int cslot = (h >> 3) + 1 + tid;                // slot of logical index h + 8 + 8 tid (sub-array 0)
+        T pr[QO], pi[QO];
+#pragma unroll
+        for (int o = 0; o < QO; ++o) pr[o] = pi[o] = (T)0;
+        for (int k0 = 0; k0 < h; k0 += QK) {
+            // a[q] = x[d_0 - k0 - 7 + q], q = 0..14: logical c - k0 - 7 + q = 8 (cslot - k0/8 - 1) + (q + 1)
+            // bb[q] = x[d_0 + k0 + q],    q = 0..14: logical c + k0 + q     = 8 (cslot + k0/8) + q
+            Cx<T> a[QO + QK - 1], bb[QO + QK - 1];
+            const int sa = cslot - (k0 >> 3) - 1, sb = cslot + (k0 >> 3);
+#pragma unroll
+            for (int q = 0; q < QO + QK - 1; ++q) {
+                a[q] = xs[((q + 1) & 7) * sub + sa + ((q + 1) >> 3)];
+                bb[q] = xs[(q & 7) * sub + sb + (q >> 3)];
+            }
+#pragma unroll
+            for (int o = 0; o < QO; ++o) {
+#pragma unroll
+                for (int kk = 0; kk < QK; ++kk) {
+                    const Cx<T> u = a[o - kk + QK - 1], v = bb[o + kk];
+                    pr[o] = fma(u.x, v.x, pr[o]); pr[o] = fma(-u.y, v.y, pr[o]);
+                    pi[o] = fma(u.x, v.y, pi[o]); pi[o] = fma(u.y, v.x, pi[o]);
+                }
+            }
+            if (sizeof(T) == 4 && ((k0 + QK) % 128 == 0)) {   // bounded fp32 error: flush partial sums
+#pragma unroll
+                for (int o = 0; o < QO; ++o) { accr[o] += (double)pr[o]; acci[o] += (double)pi[o]; pr[o] = pi[o] = (T)0; }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < QO; ++o) { accr[o] += (double)pr[o]; acci[o] += (double)pi[o]; }
+        // E(d) = sum_{k<h} |x[d+k]|^2: direct for the thread's first output (float partials flushed every 128 terms), then slid
+        {
+            double e0 = 0.0;
+            for (int k1 = 0; k1 < h; k1 += 128) {
+                T part = (T)0;
+                const int kend = k1 + 128 < h ? k1 + 128 : h;
+                for (int k = k1; k < kend; ++k) {
+                    const int li = h + 8 + 8 * tid + k;
+                    const Cx<T> v = xs[(li & 7) * sub + (li >> 3)];
+                    part = fma(v.x, v.x, part); part = fma(v.y, v.y, part);
+                }
+                e0 += (double)part;
+            }
+            acce[0] += e0;
+#pragma unroll
+            for (int o = 1; o < QO; ++o) {
+                const int lo = h + 8 + 8 * tid + o - 1, hi = lo + h;
+                const Cx<T> vl = xs[(lo & 7) * sub + (lo >> 3)], vh = xs[(hi & 7) * sub + (hi >> 3)];
+                e0 += ((double)vh.x * vh.x + (double)vh.y * vh.y) - ((double)vl.x * vl.x + (double)vl.y * vl.y);
+                acce[o] += e0;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < QO; ++o) {
+        const int64_t i = i0 + tid * QO + o;
+        if (i >= n_out) break;
+        const double ee = acce[o] > 1e-12 ? acce[o] : 1e-12;
+        const double m = (accr[o] * accr[o] + acci[o] * acci[o]) / (ee * ee);
+        const int64_t oi = frame * out_stride + i;
+        if (out_f64) {
+            if (M) reinterpret_cast<double *>(M)[oi] = m;
+            if (P) reinterpret_cast<double2 *>(P)[oi] = make_double2(accr[o], acci[o]);
+            if (E) reinterpret_cast<double *>(E)[oi] = acce[o];
+        } else {
+            if (M) reinterpret_cast<float *>(M)[oi] = (float)m;
+            if (P) reinterpret_cast<float2 *>(P)[oi] = make_float2((float)accr[o], (float)acci[o]);
+            if (E) reinterpret_cast<float *>(E)[oi] = (float)acce[o];
+        }
+    }
+}
+
 template <typename T, int DT>
 static int launch_park(const ofs_metric_desc *d, const void *x, void *M, void *P, void *E, int64_t n_out, cudaStream_t st)
 {
     const int h = d->symbol_len / 2;
+    if (h % 8 == 0 && h >= 8) {
+        const int tiles2 = (int)((n_out + QTILE - 1) / QTILE);
+        const size_t smem2 = (size_t)(QTILE + 2 * h + 16) * sizeof(Cx<T>);
+        auto kern2 = park_kernel_v2<T, DT>;
+        OFS_REQUIRE(smem2 <= 200 * 1024, "ofs_park_metric: symbol_len too large");
+        OFS_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        const int64_t grid2 = (int64_t)tiles2 * d->n_frames;
+        OFS_REQUIRE(grid2 < (1LL << 31), "ofs_park_metric: grid too large");
+        kern2<<<(unsigned)grid2, QNT2, smem2, st>>>(x, d->n_branches, d->n_samples, d->x_frame_stride, d->x_branch_stride, h, n_out,
+                                                  d->out_stride, d->out_f64, M, P, E, tiles2);
+        return check_launch("park_kernel_v2");
+    }
     const int tiles = (int)((n_out + PTILE - 1) / PTILE);
     const size_t smem = (size_t)(PTILE + 2 * h + 2 * PK) * sizeof(Cx<T>);
     auto kern = park_kernel<T, DT>;

@@ -59,7 +59,7 @@ __device__ __forceinline__ float4 ld_pair<OFS_IQ16>(const unsigned char *stage, 
 }
 
 template <int DT, int NT>
-__global__ void __launch_bounds__(NT, 1) aa_array_kernel(const ArrayParams p)
+__global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1)) aa_array_kernel(const ArrayParams p)
 {
     constexpr int L = 2 * NT;
     constexpr int ESZ = InT<DT>::bytes;
@@ -252,12 +252,22 @@ bool array_supported(int in_dtype, int64_t n, int64_t xfs, int64_t xbs, int L, c
     return true;
 }
 
+// ring depth: ~160 KB in flight per SM.  Large CTAs (L >= 512) take the whole SM and deepen their ring (int16 rows are half
+// the bytes: 8 stages); short rows keep 4 stages and share the SM between several CTAs instead.
+static int array_stages(int L, int esz)
+{
+    // two CTAs per SM (L <= 512), ~80 KB of ring each
+    const int stage_bytes = AR_NQ * L * esz;
+    int st = (L >= 1024 ? 160 * 1024 : 80 * 1024) / stage_bytes;
+    return st > 8 ? 8 : (st < 2 ? 2 : st);
+}
+
 static int array_ctas_per_sm(int L, int esz)
 {
     const int stage_bytes = AR_NQ * L * esz;
-    const int smem = (stage_bytes <= 40 * 1024 ? 4 : 2) * stage_bytes + 1024;
+    const int smem = array_stages(L, esz) * stage_bytes + 1024;
     int c = (220 * 1024) / smem;
-    const int by_regs = 65536 / ((L / 2) * 192);
+    const int by_regs = 65536 / ((L / 2) * (L >= 1024 ? 128 : 128));
     if (c > by_regs) c = by_regs;
     return c < 1 ? 1 : c;
 }
@@ -268,7 +278,7 @@ static int launch_array_t(ArrayParams &p, cudaStream_t stream)
     constexpr int L = 2 * NT;
     constexpr int stage_bytes = AR_NQ * L * InT<DT>::bytes;
     // ring: ~160 KB in flight per SM; short rows (small CTAs) share an SM instead of deepening one ring
-    const int stages = stage_bytes <= 40 * 1024 ? 4 : 2;
+    const int stages = array_stages(L, InT<DT>::bytes);
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes;
     static bool attr_set = false;

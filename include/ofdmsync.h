@@ -265,6 +265,22 @@ int ofs_cp_cfo(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_bran
                int64_t x_branch_stride, const int64_t *starts, int32_t n_fft, int32_t cp_len, int32_t span, int32_t win_len,
                int32_t mode, double fs, double *cfo_hz, int64_t *best_d, void *P_c128, void *stream);
 
+/* Receive chain after the detector, one result per frame: apply_cfo(rx, -cfo_hz) (core.py:123-138), branch
+ * mean, pilot and data symbol FFT + used bins (core.ofdm_fft_used, core.py:171-176), LS channel estimate (core.py:339-341),
+ * phase-slope timing (core.py:443-469), equalise (core.py:344-345), complex-gain alignment (core.py:357-362), EVM
+ * (core.py:365-370).  x: (n_frames, n_branches, n); the pilot symbol's CP starts at pilot_cp_start[f], the data symbol follows
+ * it (sc.py:286-309).  bins: DFT bin numbers of the used subcarriers (device int32[n_used]); k_index: the same as signed
+ * indices (device float64[n_used]); pilot_used: complex128[n_used]; data_used: complex128[n_frames][data_stride] (stride 0:
+ * shared).  n_fft must divide 4096.  Outputs: h_est, xhat (aligned): complex128[n_frames][n_used]; scalars:
+ * float64[n_frames][8] = evm_rms, evm_db, slope (rad/bin), timing offset (samples), gain re, gain im, 0, valid.
+ * Symbols that run past the end of the capture are zero-padded (numpy slicing + np.fft.fft(td, n=N)); a start outside the
+ * capture gives valid = 0 and NaN. */
+int ofs_rx_chain(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_branches, int64_t n, int64_t x_frame_stride,
+                 int64_t x_branch_stride, const int64_t *pilot_cp_start, const double *cfo_hz, double fs, int32_t n_fft,
+                 int32_t cp_len, const int32_t *bins, const double *k_index, int32_t n_used, const void *pilot_used_c128,
+                 const void *data_used_c128, int64_t data_stride, void *h_est_c128, void *xhat_c128, double *scalars,
+                 void *stream);
+
 /* End-to-end sync over HOST buffers --------------------------------------------------------------- */
 typedef struct ofs_ctx ofs_ctx;
 int ofs_ctx_create(ofs_ctx **ctx, int device);

@@ -195,6 +195,7 @@ __device__ __forceinline__ float2 cvt_iq16(unsigned w)
     return make_float2(__uint_as_float(lo) - 8421376.0f, __uint_as_float(hi) - 8421376.0f);
 }
 
+__device__ __forceinline__ size_t dtype_bytes_dev(int dt) { return dt == OFS_C64 ? 8 : (dt == OFS_C128 ? 16 : 4); }
 inline size_t dtype_bytes(int dt) { return dt == OFS_C64 ? 8 : (dt == OFS_C128 ? 16 : 4); }
 
 }  // namespace ofs

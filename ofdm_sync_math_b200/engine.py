@@ -612,3 +612,35 @@ def cp_cfo(rx, starts, n_fft: int = 2048, cp_len: int = 512, fs: float = 30.72e6
     L.check(L.lib().ofs_cp_cfo(_ptr(x), code, C.c_int64(F), int(B), C.c_int64(n), C.c_int64(B * n), C.c_int64(n), _ptr(st), int(n_fft),
                                int(cp_len), int(sp), int(wl), int(m), C.c_double(fs), _ptr(cfo), _ptr(bd), _ptr(P), _stream()), "ofs_cp_cfo")
     return cfo, bd, P
+
+
+def rx_chain(rx, pilot_cp_start, cfo_hz, pilot_used, data_used, *, fs: float = 30.72e6, n_fft: int = 2048, cp_len: int = 512,
+             used_indices=None):
+    """The receive chain after the detector, batched (ofs_rx_chain): CFO correction, pilot FFT -> LS estimate -> phase-slope
+    timing, data FFT -> equalise -> gain alignment -> EVM (sc.py:286-309 / core.py:171-176, 339-370, 443-469).
+    rx: (frames, branches, n); pilot_cp_start, cfo_hz: per frame; pilot_used: [n_used]; data_used: [n_used] or [frames, n_used].
+    -> dict(h_est [F, n_used] c128, xhat [F, n_used] c128, evm_rms, evm_db, slope, sto, gain)."""
+    x, code, _ = to_device(rx)
+    F, B, n = x.shape[0], x.shape[1], x.shape[2]
+    dev = x.device
+    if used_indices is None:
+        half = len(np.asarray(pilot_used)) // 2
+        used_indices = np.concatenate((np.arange(-half, 0), np.arange(1, half + 1)))      # core.centered_subcarrier_indices
+    k = np.asarray(used_indices, dtype=np.int64)
+    nu = k.size
+    bins = torch.as_tensor(np.mod(k, n_fft).astype(np.int32)).to(dev)
+    kf = torch.as_tensor(k.astype(np.float64)).to(dev)
+    st = torch.as_tensor(np.broadcast_to(np.asarray(pilot_cp_start, dtype=np.int64), (F,)).copy()).to(dev)
+    cf = torch.as_tensor(np.broadcast_to(np.asarray(cfo_hz, dtype=np.float64), (F,)).copy()).to(dev)
+    pu = torch.as_tensor(np.ascontiguousarray(np.asarray(pilot_used, dtype=np.complex128))).to(dev)
+    du = np.asarray(data_used, dtype=np.complex128)
+    dstride = 0 if du.ndim == 1 else nu
+    dd = torch.as_tensor(np.ascontiguousarray(du)).to(dev)
+    h = torch.empty((F, nu), dtype=torch.complex128, device=dev)
+    xh = torch.empty((F, nu), dtype=torch.complex128, device=dev)
+    sc = torch.zeros((F, 8), dtype=torch.float64, device=dev)
+    L.check(L.lib().ofs_rx_chain(_ptr(x), code, C.c_int64(F), int(B), C.c_int64(n), C.c_int64(B * n), C.c_int64(n), _ptr(st), _ptr(cf),
+                                 C.c_double(fs), int(n_fft), int(cp_len), _ptr(bins), _ptr(kf), int(nu), _ptr(pu), _ptr(dd),
+                                 C.c_int64(dstride), _ptr(h), _ptr(xh), _ptr(sc), _stream()), "ofs_rx_chain")
+    return dict(h_est=h, xhat=xh, evm_rms=sc[:, 0], evm_db=sc[:, 1], slope=sc[:, 2], sto=sc[:, 3],
+                gain=torch.complex(sc[:, 4], sc[:, 5]), valid=sc[:, 7])

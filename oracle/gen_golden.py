@@ -397,6 +397,25 @@ def gen_channel_and_cfo(out: Path) -> None:
     np.savez_compressed(out / "channel_cfo.npz", **cases)
 
 
+def gen_rx_chain(out: Path) -> None:
+    """the stage after the detector in every script -- CFO correction, pilot FFT -> LS channel estimate ->
+    phase-slope timing -> equalise -> gain alignment -> EVM (core.py:171-176, 339-370, 443-469; call sites sc.py:286-309,
+    minn.py:546-568).  Captured from the locals of the unmodified run_simulation() of sc.py (1 branch) and minn.py (2)."""
+    import sc, minn
+    for mod, name in ((sc, "sc"), (minn, "minn")):
+        for ch, sub in SCEN:
+            loc = _run_capture(mod, "run_simulation", (ch, sub))
+            tag = ch or "awgn"
+            np.savez_compressed(
+                out / f"rxchain_{name}_{tag}.npz",
+                rx=np.atleast_2d(loc["rx_samples"]), pilot_cp_start=np.int64(loc["pilot_cp_start"]), cfo_est_hz=np.float64(loc["cfo_est_hz"]),
+                pilot_used=loc["pilot_used"], data_used=loc["data_used"], h_est=loc["h_est"], xhat_aligned=loc["xhat_aligned"],
+                gain=np.complex128(loc["gain"]), evm_rms=np.float64(loc["evm_rms"]), evm_db=np.float64(loc["evm_db"]),
+                slope=np.float64(loc["slope_rad_per_bin"]), sto=np.float64(loc["timing_offset_samples"]),
+            )
+            print("rxchain", name, tag, int(loc["pilot_cp_start"]), float(loc["evm_db"]), float(loc["timing_offset_samples"]))
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -408,7 +427,7 @@ def main() -> None:
     _setup(a.ref)
     gens = dict(sc=gen_sc, minn=gen_minn, park=gen_park, combined=gen_combined, zc=gen_zc, zc_v2=gen_zc_v2,
                 zc_freq=gen_zc_freq, minn_rtl=gen_minn_rtl, detector_cases=gen_detector_cases,
-                cir_scale=gen_cir_and_scale, channel_cfo=gen_channel_and_cfo)
+                cir_scale=gen_cir_and_scale, channel_cfo=gen_channel_and_cfo, rx_chain=gen_rx_chain)
     for name, fn in gens.items():
         if a.only and name not in a.only.split(","):
             continue

@@ -400,3 +400,30 @@ def estimate_cfo_from_cp_peak_with_index(rx, start, n_fft, cp_len, fs_hz, span=N
         if abs(P) > bm:
             bm, best, bd = abs(P), P, d
     return float(-np.angle(best) * fs_hz / (2 * np.pi * n_fft)), int(bd)
+
+
+def rx_chain(rx, pilot_cp_start: int, cfo_hz: float, pilot_used, data_used, fs=30.72e6, n_fft=2048, cp_len=512):
+    """sc.py:286-309 / minn.py:546-568 with core.apply_cfo, ofdm_fft_used (core.py:171-176), ls_channel_estimate, equalize
+    (core.py:339-345), align_complex_gain (core.py:357-362), evm_rms_db (core.py:365-370) and
+    estimate_timing_offset_from_phase_slope (core.py:443-469)."""
+    x = apply_cfo(np.atleast_2d(np.asarray(rx)), -cfo_hz, fs)
+    eff = np.mean(x, axis=0)
+    nu = len(pilot_used); half = nu // 2
+    idx = np.concatenate((np.arange(-half, 0), np.arange(1, half + 1)))
+    def used(td):
+        return np.fft.fftshift(np.fft.fft(td, n=n_fft))[(n_fft // 2 + idx) % n_fft]
+    yp = used(eff[pilot_cp_start + cp_len: pilot_cp_start + cp_len + n_fft])
+    h = yp / (np.asarray(pilot_used) + 1e-9)
+    k = idx.astype(np.float64)
+    phi = np.unwrap(np.angle(h))
+    kz, pz = k - np.mean(k), phi - np.mean(phi)
+    slope = float(np.sum(kz * pz) / (float(np.sum(kz * kz)) + 1e-12))
+    d0 = pilot_cp_start + cp_len + n_fft
+    yd = used(eff[d0 + cp_len: d0 + cp_len + n_fft])
+    xh = yd / (h + 1e-9)
+    ref = np.asarray(data_used)
+    g = np.vdot(xh, ref) / (np.vdot(xh, xh) + 1e-12)
+    xa = xh * g
+    evm = float(np.sqrt(np.mean(np.abs(xa - ref) ** 2) / np.mean(np.abs(ref) ** 2)))
+    return dict(h_est=h, xhat=xa, gain=g, evm_rms=evm, evm_db=float(20 * np.log10(evm + 1e-12)), slope=slope,
+                sto=float(-slope * n_fft / (2 * np.pi)))

@@ -105,3 +105,32 @@ def test_cp_cfo_estimators_vs_reference(golden, ci):
     assert np.isnan(cfo.cpu().numpy()[0]) and int(bd.cpu().numpy()[0]) == -1
     with pytest.raises(ValueError):
         core.estimate_cfo_from_cp(x, x.shape[1] - 1000, 2048, 512, FS)
+
+
+@pytest.mark.parametrize("name", ["sc_cir1", "sc_awgn", "minn_cir1", "minn_awgn"])
+def test_rx_chain_vs_reference(golden, name):
+    """SURVEY 8f-3 on the GPU (ofs_rx_chain) vs the reference's own run (1 and 2 branches), plus a batch against the oracle."""
+    from ofdm_sync_math_b200 import engine
+    g = golden(f"rxchain_{name}")
+    rx = g["rx"]
+    st, cfo = int(g["pilot_cp_start"]), float(g["cfo_est_hz"])
+    r = engine.rx_chain(rx[None], st, cfo, g["pilot_used"], g["data_used"])
+    h, xh = r["h_est"].cpu().numpy()[0], r["xhat"].cpu().numpy()[0]
+    assert np.abs(h - g["h_est"]).max() <= 1e-9 * np.abs(g["h_est"]).max()
+    assert np.abs(xh - g["xhat_aligned"]).max() <= 1e-8 * np.abs(g["xhat_aligned"]).max()
+    assert abs(complex(r["gain"].cpu().numpy()[0]) - complex(g["gain"])) <= 1e-9 * abs(complex(g["gain"]))
+    assert abs(float(r["evm_rms"][0]) - float(g["evm_rms"])) <= 1e-9 and abs(float(r["evm_db"][0]) - float(g["evm_db"])) <= 1e-7
+    assert abs(float(r["slope"][0]) - float(g["slope"])) <= 1e-9 and abs(float(r["sto"][0]) - float(g["sto"])) <= 1e-6
+    # a batch: shifted starts / other CFO values, complex64 input, per-frame data symbols -> oracle on the same input
+    rx32 = rx.astype(np.complex64)
+    starts = np.array([st, st - 3, st + 5, st - 40]); cfos = np.array([cfo, 0.0, cfo + 300.0, -cfo])
+    du = np.stack([g["data_used"], np.roll(g["data_used"], 1), g["data_used"].conj(), g["data_used"]])
+    rb = engine.rx_chain(np.broadcast_to(rx32, (4,) + rx32.shape).copy(), starts, cfos, g["pilot_used"], du)
+    for f in range(4):
+        o = orc.rx_chain(rx32.astype(np.complex128), int(starts[f]), float(cfos[f]), g["pilot_used"], du[f])
+        assert np.abs(rb["h_est"][f].cpu().numpy() - o["h_est"]).max() <= 1e-9 * np.abs(o["h_est"]).max()
+        assert abs(float(rb["evm_rms"][f]) - o["evm_rms"]) <= 1e-8 * max(o["evm_rms"], 1.0)
+        assert abs(float(rb["sto"][f]) - o["sto"]) <= 1e-6
+    # a start outside the capture is flagged (symbols that merely run past the end are zero-padded like np.fft.fft(td, n=N))
+    bad = engine.rx_chain(rx32[None], rx.shape[1] + 5, 0.0, g["pilot_used"], g["data_used"])
+    assert float(bad["valid"][0]) == 0.0 and np.isnan(float(bad["evm_rms"][0]))

@@ -259,3 +259,16 @@ def test_oracle_channel_chain_vs_reference(golden, ci):
         c, d = orc.estimate_cfo_from_cp_peak_with_index(x, start, 2048, 512, 30.72e6, span=100)
         assert abs(c - e[4]) <= 1e-6 and d == int(e[5])
         assert orc.estimate_cfo_from_cp_peak_with_index(x, start, 2048, 512, 1.0, span=300)[1] == int(e[6])
+
+
+@pytest.mark.parametrize("name", ["sc_cir1", "sc_awgn", "minn_cir1", "minn_awgn"])
+def test_oracle_rx_chain_vs_reference(golden, name):
+    """CFO correction -> pilot LS estimate -> phase-slope timing -> equalise -> align -> EVM, oracle vs the locals
+    of the unmodified run_simulation() (oracle/gen_golden.py::gen_rx_chain)."""
+    g = golden(f"rxchain_{name}")
+    r = orc.rx_chain(g["rx"], int(g["pilot_cp_start"]), float(g["cfo_est_hz"]), g["pilot_used"], g["data_used"])
+    assert np.abs(r["h_est"] - g["h_est"]).max() <= 1e-10 * np.abs(g["h_est"]).max()
+    assert np.abs(r["xhat"] - g["xhat_aligned"]).max() <= 1e-9 * np.abs(g["xhat_aligned"]).max()
+    assert abs(r["gain"] - complex(g["gain"])) <= 1e-10 * abs(complex(g["gain"]))
+    assert abs(r["evm_rms"] - float(g["evm_rms"])) <= 1e-10 and abs(r["evm_db"] - float(g["evm_db"])) <= 1e-8
+    assert abs(r["slope"] - float(g["slope"])) <= 1e-10 and abs(r["sto"] - float(g["sto"])) <= 1e-7

@@ -173,7 +173,8 @@ struct BankParams {
     int64_t n, n_off, seg_len, n_items;
     int N, cp, segs_per_cap, n_roots;
     long long *prof;   // OFS_BANK_DBG & 8: per-CTA cycle counters [grid][16]
-    int dbg;      // timing experiments only (OFS_BANK_DBG): 1 skip MMAs, 2 skip epilogue math, 4 skip producer math
+    int dbg;      // timing experiments only (build with -DOFS_BANK_EXPERIMENTS, then OFS_BANK_DBG): 1 skip MMAs, 2 skip epilogue
+                  // math, 4 skip producer math, 8 cycle counters, 16 skip operand stores, 32 skip energies; 0 in the shipped library
     const float4 *wtab;
     unsigned long long *best_packed;
     float *metric_out;          // optional: the full metric row of root 0 (zc_freq fast path), [frames][metric_stride]
@@ -608,7 +609,11 @@ static int bank_run(const void *x_c64, int64_t n_frames, int64_t n, int32_t n_ff
         OFS_CUDA(cudaMemsetAsync(packed, 0, (size_t)n_frames * nr * 8, stream));
         BankParams p{};
         p.x = reinterpret_cast<const float2 *>(x_c64); p.n = n; p.n_off = n_off; p.seg_len = seg_len; p.segs_per_cap = (int)segs;
+#ifdef OFS_BANK_EXPERIMENTS      // timing experiments (skip stages, cycle counters): compiled out of the shipped library
         { const char *dbg = getenv("OFS_BANK_DBG"); p.dbg = dbg ? atoi(dbg) : 0; }
+#else
+        p.dbg = 0;
+#endif
         const int64_t grid_dbg = n_frames * segs < sm_count() ? n_frames * segs : sm_count();
         if (p.dbg & 8) { OFS_CUDA(cudaMalloc((void **)&p.prof, (size_t)grid_dbg * 16 * 8)); OFS_CUDA(cudaMemset(p.prof, 0, (size_t)grid_dbg * 16 * 8)); }
         p.n_items = n_frames * segs; p.N = n_fft; p.cp = cp; p.n_roots = nr; p.wtab = wtab; p.best_packed = packed;

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(ZNT) zc_spectrum_kernel(const double2 *ref, in
 }
 
 template <typename T, int DT>
-__global__ void __launch_bounds__(ZNT) zc_mf_kernel(const void *x, int nb, int64_t n, int nr, const double2 *tw,
+__global__ void __launch_bounds__(ZNT, (sizeof(T) == 4 ? 3 : 1)) zc_mf_kernel(const void *x, int nb, int64_t n, int nr, const double2 *tw,
                                                     const double2 *G, const double *ref_norm_p, int mode, int out_f64,
                                                     void *corr_out, void *mag_out, int64_t out_stride, int blocks_per_frame)
 {
@@ -75,7 +75,10 @@ __global__ void __launch_bounds__(ZNT) zc_mf_kernel(const void *x, int nb, int64
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double ref_norm = *ref_norm_p;
 
-    for (int i = tid; i < V; i += ZNT) { pw[i] = (T)0; acc[i].x = (T)0; acc[i].y = (T)0; }
+    // one branch: results leave straight from the inverse FFT, pw / acc are neither allocated nor touched (51 KB -> more CTAs per SM)
+    const bool single = nb == 1;
+    if (!single)
+        for (int i = tid; i < V; i += ZNT) { pw[i] = (T)0; acc[i].x = (T)0; acc[i].y = (T)0; }
 
     for (int b = 0; b < nb; ++b) {
         const In *xb = reinterpret_cast<const In *>(x) + (frame * nb + b) * n;
@@ -124,10 +127,30 @@ __global__ void __launch_bounds__(ZNT) zc_mf_kernel(const void *x, int nb, int64
                 const T d = (T)ref_norm * sqrt(e > (T)1e-12 ? e : (T)1e-12);
                 yr /= d; yi /= d;
             }
-            acc[i].x += yr; acc[i].y += yi;
-            pw[i] += e;
+            if (single) {
+                const int64_t k = k0 + i;
+                if (k >= out_len) break;
+                double wr = (double)yr, wi = (double)yi;
+                if (mode == 0) {                               // zc.py:125-126
+                    const double pp = e > (T)0 ? (double)e : 0.0;
+                    const double d = ref_norm * sqrt(pp + 1e-12);
+                    wr /= d; wi /= d;
+                }
+                const int64_t o = frame * out_stride + k;
+                if (out_f64) {
+                    if (corr_out) reinterpret_cast<double2 *>(corr_out)[o] = make_double2(wr, wi);
+                    if (mag_out) reinterpret_cast<double *>(mag_out)[o] = hypot(wr, wi);
+                } else {
+                    if (corr_out) reinterpret_cast<float2 *>(corr_out)[o] = make_float2((float)wr, (float)wi);
+                    if (mag_out) reinterpret_cast<float *>(mag_out)[o] = (float)hypot(wr, wi);
+                }
+            } else {
+                acc[i].x += yr; acc[i].y += yi;
+                pw[i] += e;
+            }
         }
     }
+    if (single) return;
     __syncthreads();
     for (int i = tid; i < V; i += ZNT) {
         const int64_t k = k0 + i;
@@ -280,8 +303,9 @@ OFS_API int ofs_zc_matched_filter(const void *x, int32_t in_dtype, int64_t n_fra
     const int64_t grid = (int64_t)bpf * n_frames;
     OFS_REQUIRE(grid < (1LL << 31), "ofs_zc_matched_filter: grid too large");
     const bool dbl = in_dtype == OFS_C128 || out_f64;
-    const size_t smem = dbl ? (size_t)ZFP * 16 + (size_t)(2 * ZF + 4) * 8 + (size_t)ZF * 16
-                            : (size_t)ZFP * 8 + (size_t)(2 * ZF + 4) * 4 + (size_t)ZF * 8;
+    // a + se (+ pw + acc when branches are summed)
+    const size_t esz_t = dbl ? 8 : 4;
+    const size_t smem = (size_t)ZFP * 2 * esz_t + (size_t)(ZF + 4) * esz_t + (n_branches > 1 ? (size_t)ZF * esz_t + (size_t)ZF * 2 * esz_t : 0);
 #define OFS_MF_LAUNCH(T, DT)                                                                                       \
     do {                                                                                                           \
         auto kern = zc_mf_kernel<T, DT>;                                                                           \

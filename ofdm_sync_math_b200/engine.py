@@ -215,9 +215,16 @@ assert _EVENT_NP.itemsize == C.sizeof(L.Event)
 
 
 def _events_to_numpy(ev: torch.Tensor, cnt: torch.Tensor) -> list[np.ndarray]:
-    raw = ev.cpu().numpy().view(_EVENT_NP).reshape(ev.shape[0], L.OFS_MAX_EVENTS)
-    c = cnt.cpu().numpy()
-    return [raw[i, : min(int(c[i]), L.OFS_MAX_EVENTS)].copy() for i in range(raw.shape[0])]
+    """Device event buffers -> one structured array per row.  Only the occupied part of the buffers crosses PCIe (a row holds
+    up to OFS_MAX_EVENTS events of 72 bytes; typical captures use a handful)."""
+    c = np.minimum(cnt.cpu().numpy(), L.OFS_MAX_EVENTS)
+    rows = ev.shape[0]
+    mc = int(c.max()) if rows else 0
+    if mc == 0:
+        return [np.zeros(0, dtype=_EVENT_NP) for _ in range(rows)]
+    esz = C.sizeof(L.Event)
+    raw = ev.view(rows, L.OFS_MAX_EVENTS, esz)[:, :mc].contiguous().cpu().numpy().view(_EVENT_NP).reshape(rows, mc)
+    return [raw[i, : int(c[i])] for i in range(rows)]
 
 
 def _event_buffers(n_rows: int, dev):
@@ -244,8 +251,8 @@ def zc_streaming_detection(corr_mag: torch.Tensor, window: int, thresh_value: in
     m = m.contiguous()
     rows, m = _rows(m)
     ls = torch.empty_like(m)
-    valid = torch.zeros(m.shape, dtype=torch.uint8, device=m.device)
-    above = torch.zeros(m.shape, dtype=torch.uint8, device=m.device)
+    valid = torch.empty(m.shape, dtype=torch.uint8, device=m.device)       # every element is written by the kernel
+    above = torch.empty(m.shape, dtype=torch.uint8, device=m.device)
     L.check(L.lib().ofs_zc_streaming_detection(C.byref(rows), int(window), int(thresh_value), int(frac_bits),
                                                C.c_double(min_corr_mag), _ptr(ls), _ptr(valid), _ptr(above),
                                                C.c_int64(m.shape[1]), _stream()), "ofs_zc_streaming_detection")

@@ -174,7 +174,7 @@ struct BankParams {
     int N, cp, segs_per_cap, n_roots;
     long long *prof;   // OFS_BANK_DBG & 8: per-CTA cycle counters [grid][16]
     int dbg;      // timing experiments only (build with -DOFS_BANK_EXPERIMENTS, then OFS_BANK_DBG): 1 skip MMAs, 2 skip epilogue
-                  // math, 4 skip producer math, 8 cycle counters, 16 skip operand stores, 32 skip energies; 0 in the shipped library
+                  // math, 4 skip producer math, 8 cycle counters; 0 in the shipped library
     const float4 *wtab;
     unsigned long long *best_packed;
     float *metric_out;          // optional: the full metric row of root 0 (zc_freq fast path), [frames][metric_stride]
@@ -194,6 +194,13 @@ __device__ __forceinline__ void sts_h2(uint32_t addr, float re, float im)
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(v) : "f"(im), "f"(re));      // low half = re
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v));
 }
+
+// timing-experiment switches are a compile-time zero in the shipped library: the branches disappear from the step loops
+#ifdef OFS_BANK_EXPERIMENTS
+#define BK_DBG (p.dbg)
+#else
+#define BK_DBG 0
+#endif
 
 __global__ void __launch_bounds__(BK_THREADS, 1)
 zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams p)
@@ -254,7 +261,7 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
         const uint32_t sA_u = smem_u32(sA);
         uint32_t it = 0;
         long long c_wait = 0, c_math = 0, c_red = 0, c_tail = 0, c_warm = 0, tk = 0;
-        const bool prof = (p.dbg & 8) && g == 0;
+        const bool prof = (BK_DBG & 8) && g == 0;
 #define BK_TICK(acc) do { if (prof) { const long long now = clock64(); acc += now - tk; tk = now; } } while (0)
         for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int64_t cap, seg_lo, seg_hi, Q;
@@ -320,7 +327,7 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
                         const uint32_t tb = sA_u + buf * BK_TILE;
                         BK_TICK(c_wait);
                         float e[16];
-                        if (p.dbg & 4) {
+                        if (BK_DBG & 4) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) e[i] = 0.f;
                         } else {
@@ -334,16 +341,11 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
 #pragma unroll
                                 for (int ii = 0; ii < 4; ++ii) {
                                     const int i = 4 * grp + ii;
-                                    if (p.dbg & 32) e[i] = Bx.x;
-                                    else {
                                     const float2 e2 = __ffma2_rn(Bx, Bx, __fmul2_rn(By, By));
                                     e[i] = e2.x + e2.y;
-                                    }
                                     const uint32_t a = tb + base8[i & 7] + i * 128;
-                                    if (!(p.dbg & 16)) {
-                                        sts_h2(a, Bx.x, By.x);
-                                        sts_h2(a + 16384, Bx.y, By.y);
-                                    }
+                                    sts_h2(a, Bx.x, By.x);
+                                    sts_h2(a + 16384, Bx.y, By.y);
                                     const float4 c = cg[ii];
                                     const float2 T = __fadd2_rn(Bx, make_float2(c.x, c.y)), U = __fadd2_rn(By, make_float2(c.z, c.w));
                                     Bx = __ffma2_rn(T, WX, __fmul2_rn(U, NWY));
@@ -404,7 +406,7 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
             for (int kc = 0; kc < 2; ++kc) tma_load_2d_b(sT + kc * 16384, &mapT, kc * 64, 0, t_full);
             mbar_wait_bounded(t_full, 0);
             long long m_wa = 0, m_wd = 0, m_is = 0, tk = clock64();
-            const bool prof = (p.dbg & 8) != 0;
+            const bool prof = (BK_DBG & 8) != 0;
             for (; mt < tot; ++mt) {
                 const uint32_t buf = mt % BK_ST, acc = mt & 1u;
                 mbar_wait_bounded(&a_full[buf], (mt / BK_ST) & 1u);
@@ -413,7 +415,7 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
                 BK_TICK(m_wd);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const unsigned char *At = sA + buf * BK_TILE;
-                if (!(p.dbg & 1))
+                if (!(BK_DBG & 1))
 #pragma unroll
                 for (int step = 0; step < 8; ++step) {
                     // K loop: 8 steps of 16 fp16; K-chunk = step/4 (a 128-row x 128-byte box), 32 bytes per step inside the
@@ -439,7 +441,7 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
         const float mscale = p.metric_out ? 1.0f / (p.Er[BK_MAXR] * p.templ_energy) : 0.f;
         uint32_t it = 0;
         long long e_wait = 0, e_work = 0, tk = clock64();
-        const bool prof = (p.dbg & 8) && warp == BK_PW;
+        const bool prof = (BK_DBG & 8) && warp == BK_PW;
         for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int64_t cap, seg_lo, seg_hi, Q;
             item_geom(item, cap, seg_lo, seg_hi, Q);
@@ -464,7 +466,7 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
                 // 8 roots at a time (Re columns 32 half + 8c.., Im columns 64 more); the loads of chunk c+1 are in flight while chunk c is
                 // reduced, so the TMEM read latency is paid once per tile, not once per chunk
                 uint32_t re[2][8], im[2][8];
-                if (p.dbg & 2) {
+                if (BK_DBG & 2) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) re[0][q] = im[0][q] = re[1][q] = im[1][q] = 0u;
                 } else {
@@ -474,7 +476,7 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
                 }
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    if (c < 3 && !(p.dbg & 2)) {
+                    if (c < 3 && !(BK_DBG & 2)) {
                         tmem_ld8_async(tq + buf * BK_N + 8 * (c + 1), re[(c + 1) & 1]);
                         tmem_ld8_async(tq + buf * BK_N + 64 + 8 * (c + 1), im[(c + 1) & 1]);
                     }
@@ -487,7 +489,7 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
                         best[8 * c + q] = max(best[8 * c + q], (__float_as_uint(m.x) & 0xfffffc00u) | tb);
                         best[8 * c + q + 1] = max(best[8 * c + q + 1], (__float_as_uint(m.y) & 0xfffffc00u) | tb);
                     }
-                    if (c < 3 && !(p.dbg & 2)) tmem_wait8(re[(c + 1) & 1], im[(c + 1) & 1]);
+                    if (c < 3 && !(BK_DBG & 2)) tmem_wait8(re[(c + 1) & 1], im[(c + 1) & 1]);
                     if (c == 2) {                             // the last loads have landed: the accumulator may be overwritten
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         __syncwarp();

@@ -40,7 +40,7 @@ def timeit(fn, steps=5, warmup=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
-    ap.add_argument("--cases", default="minn,iq16,chan,combined,park,zc,zcfreq,bank,aa64,rtl,tile")
+    ap.add_argument("--cases", default="minn,iq16,chan,combined,park,zc,zcfreq,bank,aa64,rtl,dropin,tile")
     a = ap.parse_args()
     import numpy as np
     import torch
@@ -208,6 +208,25 @@ def main():
         print(json.dumps({"case": "agreement of timing indices: float32 stripe path vs float64 tile path (same complex64 input)",
                           "frames": F, "frames_with_different_index": diff, "of_which_differ_by_more_than_1": big}), flush=True)
         del x, plan
+    if "dropin" in cases:
+        # the reference's own call signature: numpy complex128 in -> numpy float64 / complex128 out (H2D + kernel + D2H per call)
+        import time
+        from ofdm_sync_math_b200 import sc as sc_shim, minn as minn_shim, sync_aa as aa_shim
+        rng = np.random.default_rng(0)
+        rx = (rng.standard_normal(1 << 20) + 1j * rng.standard_normal(1 << 20)).astype(np.complex128)
+        for name, fn in (("sc.sc_streaming_metric", lambda: sc_shim.sc_streaming_metric(rx)),
+                         ("minn.minn_streaming_metric", lambda: minn_shim.minn_streaming_metric(rx)),
+                         ("sync_aa.aa_detect_streaming", lambda: aa_shim.aa_detect_streaming(rx[: 1 << 18], L=512))):
+            fn(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / 3
+            ns = rx.size if "aa" not in name else 1 << 18
+            print(json.dumps({"case": f"drop-in {name}: numpy complex128 in -> numpy out, one capture of {ns} samples", "ms": dt * 1e3,
+                              "Msamples_per_s": ns / dt / 1e6,
+                              "note": "wall clock incl. H2D, float64 kernel, D2H; the reference Python runs these at 0.21 / 0.04 / 0.12 Msamples/s (BASELINE.md)"}), flush=True)
     if "tile" in cases:
         F, n = max(int(512 * a.scale), 8), 262144
         x = synth.make_batch_device(F, n, "sc", seed=13, device=dev, chunk=64)[:, None]

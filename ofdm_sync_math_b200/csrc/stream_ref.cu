@@ -73,6 +73,88 @@ __global__ void aa_reference_kernel(const void *x, int dtype, int64_t n_frames, 
     }
 }
 
+// Same results bit for bit, one CTA per frame: only the three running sums of each antenna are a true recurrence
+// (s = (s + new) - oldest, two dependent float64 adds per step); the lag products feeding them and the antenna totals
+// leaving them are computed by all threads from coalesced loads, 128 time steps at a time, antennas in groups of 6 (the
+// totals are accumulated in antenna order, as sync_aa.py:478-479 does).  137 ms -> ~2 ms for one 262144-sample capture.
+constexpr int AAK = 128, AAG = 6;
+__global__ void __launch_bounds__(AAK) aa_reference_kernel_v2(const void *x, int dtype, int na, int64_t n, int L,
+                                                              double2 *P, double *R, double *M, uint8_t *valid)
+{
+    __shared__ double tot[3][AAK];
+    __shared__ double buf[AAG][6][AAK];           // qr, qi, or, oi, pw, po -> overwritten by psr, psi, -, -, rs, -
+    __shared__ double state[64][3];
+    const int64_t frame = blockIdx.x;
+    const int tid = threadIdx.x;
+    const size_t esz = dtype == OFS_C64 ? 8 : (dtype == OFS_C128 ? 16 : 4);
+    const unsigned char *xf = reinterpret_cast<const unsigned char *>(x) + (size_t)frame * na * n * esz;
+    if (tid < 64) { state[tid][0] = 0.0; state[tid][1] = 0.0; state[tid][2] = 0.0; }
+    const double floor_ = 1e-6 * (double)L;
+    for (int64_t t0 = 0; t0 < n; t0 += AAK) {
+        tot[0][tid] = 0.0; tot[1][tid] = 0.0; tot[2][tid] = 0.0;
+        const int kmax = (int)(n - t0 < AAK ? n - t0 : AAK);
+        for (int a0 = 0; a0 < na; a0 += AAG) {
+            __syncthreads();
+            for (int idx = tid; idx < AAG * AAK; idx += AAK) {
+                const int al = idx / AAK, k = idx % AAK;
+                const int a = a0 + al;
+                const int64_t t = t0 + k;
+                if (a >= na || t >= n) continue;
+                const void *xa = xf + (size_t)a * n * esz;
+                const double2 xn = load_sample_f64(xa, dtype, t);
+                double qr = 0.0, qi = 0.0, orr = 0.0, oi = 0.0, po = 0.0;
+                if (t >= L) {
+                    const double2 xd = load_sample_f64(xa, dtype, t - L);
+                    qr = __dadd_rn(__dmul_rn(xn.x, xd.x), __dmul_rn(xn.y, xd.y));          // x[n] * conj(x[n-L]) (sync_aa.py:470)
+                    qi = __dsub_rn(__dmul_rn(xn.y, xd.x), __dmul_rn(xn.x, xd.y));
+                    po = __dadd_rn(__dmul_rn(xd.x, xd.x), __dmul_rn(xd.y, xd.y));
+                    if (t >= 2 * (int64_t)L) {
+                        const double2 a2 = load_sample_f64(xa, dtype, t - 2 * (int64_t)L);
+                        orr = __dadd_rn(__dmul_rn(xd.x, a2.x), __dmul_rn(xd.y, a2.y));
+                        oi = __dsub_rn(__dmul_rn(xd.y, a2.x), __dmul_rn(xd.x, a2.y));
+                    }
+                }
+                buf[al][0][k] = qr; buf[al][1][k] = qi; buf[al][2][k] = orr; buf[al][3][k] = oi;
+                buf[al][4][k] = __dadd_rn(__dmul_rn(xn.x, xn.x), __dmul_rn(xn.y, xn.y));
+                buf[al][5][k] = po;
+            }
+            __syncthreads();
+            if (tid < AAG && a0 + tid < na) {
+                double psr = state[a0 + tid][0], psi = state[a0 + tid][1], rs = state[a0 + tid][2];
+                for (int k = 0; k < kmax; ++k) {
+                    psr = __dsub_rn(__dadd_rn(psr, buf[tid][0][k]), buf[tid][2][k]);       // sum + sample - oldest (sync_aa.py:337)
+                    psi = __dsub_rn(__dadd_rn(psi, buf[tid][1][k]), buf[tid][3][k]);
+                    rs = __dsub_rn(__dadd_rn(rs, buf[tid][4][k]), buf[tid][5][k]);
+                    buf[tid][0][k] = psr; buf[tid][1][k] = psi; buf[tid][4][k] = rs;
+                }
+                state[a0 + tid][0] = psr; state[a0 + tid][1] = psi; state[a0 + tid][2] = rs;
+            }
+            __syncthreads();
+            if (tid < kmax) {
+                double Pr = tot[0][tid], Pi = tot[1][tid], Rs = tot[2][tid];
+                for (int al = 0; al < AAG && a0 + al < na; ++al) {
+                    Pr = __dadd_rn(Pr, buf[al][0][tid]); Pi = __dadd_rn(Pi, buf[al][1][tid]); Rs = __dadd_rn(Rs, buf[al][4][tid]);
+                }
+                tot[0][tid] = Pr; tot[1][tid] = Pi; tot[2][tid] = Rs;
+            }
+        }
+        if (tid < kmax) {
+            const int64_t t = t0 + tid;
+            const double Pr = tot[0][tid], Pi = tot[1][tid], Rs = tot[2][tid];
+            const bool v = t >= L;
+            const int64_t o = frame * n + t;
+            P[o] = make_double2(Pr, Pi); R[o] = Rs; valid[o] = v;
+            double m = 0.0;
+            if (v && Rs > floor_) {
+                m = __ddiv_rn(__dadd_rn(__dmul_rn(Pr, Pr), __dmul_rn(Pi, Pi)), __dmul_rn(Rs, Rs));
+                m = m < 1.0 ? m : 1.0;
+            }
+            M[o] = m;
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------ minn_rtl
 // Per (frame, antenna): running Q-window sums of the lag product and of the power.
 //   C[n] = sum_{k=n-Q+1..n} prod[k],  prod[k] = re*re_d + im*im_d with the delayed sample x[k-D]
@@ -289,6 +371,11 @@ OFS_API int ofs_aa_metric_reference(const void *x, int32_t in_dtype, int64_t n_f
     OFS_REQUIRE(n_antennas >= 1 && n_antennas <= 64, "ofs_aa_metric_reference: 1..64 antennas");
     OFS_REQUIRE(L > 0 && n >= 0 && n_frames >= 0, "ofs_aa_metric_reference: bad geometry");
     if (n_frames == 0 || n == 0) return OFS_OK;
+    // few long frames: one CTA per frame (recurrence only where it is one); many short frames: one thread per frame
+    if (n_frames < 4096 && n_frames < (1LL << 31)) {
+        aa_reference_kernel_v2<<<(unsigned)n_frames, AAK, 0, (cudaStream_t)stream>>>(x, in_dtype, n_antennas, n, L, (double2 *)P_c128, R, M, valid);
+        return check_launch("aa_reference_kernel_v2");
+    }
     const int bs = 32;
     aa_reference_kernel<<<(unsigned)((n_frames + bs - 1) / bs), bs, 0, (cudaStream_t)stream>>>(
         x, in_dtype, n_frames, n_antennas, n, L, (double2 *)P_c128, R, M, valid);

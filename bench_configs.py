@@ -211,19 +211,22 @@ def main():
     if "dropin" in cases:
         # the reference's own call signature: numpy complex128 in -> numpy float64 / complex128 out (H2D + kernel + D2H per call)
         import time
-        from ofdm_sync_math_b200 import sc as sc_shim, minn as minn_shim, sync_aa as aa_shim
+        from ofdm_sync_math_b200 import sc as sc_shim, minn as minn_shim, sync_aa as aa_shim, minn_rtl as rtl_shim, park as park_shim
         rng = np.random.default_rng(0)
         rx = (rng.standard_normal(1 << 20) + 1j * rng.standard_normal(1 << 20)).astype(np.complex128)
         for name, fn in (("sc.sc_streaming_metric", lambda: sc_shim.sc_streaming_metric(rx)),
                          ("minn.minn_streaming_metric", lambda: minn_shim.minn_streaming_metric(rx)),
-                         ("sync_aa.aa_detect_streaming", lambda: aa_shim.aa_detect_streaming(rx[: 1 << 18], L=512))):
+                         ("sync_aa.aa_detect_streaming", lambda: aa_shim.aa_detect_streaming(rx[: 1 << 18], L=512)),
+                         ("minn_rtl.minn_rtl_streaming_metric", lambda: rtl_shim.minn_rtl_streaming_metric(
+                             rx[: 1 << 18].reshape(2, -1), smooth_shift=3, threshold_value=3276, threshold_frac_bits=15)),
+                         ("park.park_streaming_metric", lambda: park_shim.park_streaming_metric(rx[: 1 << 18]))):
             fn(); torch.cuda.synchronize()
             t0 = time.perf_counter()
             for _ in range(3):
                 fn()
             torch.cuda.synchronize()
             dt = (time.perf_counter() - t0) / 3
-            ns = rx.size if "aa" not in name else 1 << 18
+            ns = rx.size if name.startswith(("sc.", "minn.")) else 1 << 18
             print(json.dumps({"case": f"drop-in {name}: numpy complex128 in -> numpy out, one capture of {ns} samples", "ms": dt * 1e3,
                               "Msamples_per_s": ns / dt / 1e6,
                               "note": "wall clock incl. H2D, float64 kernel, D2H; the reference Python runs these at 0.21 / 0.04 / 0.12 Msamples/s (BASELINE.md)"}), flush=True)

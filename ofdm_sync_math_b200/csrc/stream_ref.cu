@@ -199,6 +199,54 @@ __global__ void rtl_window_kernel(const void *x, int64_t n_streams, int64_t n, i
     }
 }
 
+// Float mirror, few long streams: one CTA per stream.  The products are computed by all threads from coalesced loads, 256
+// steps at a time; only c = (c + p) - p_old and e = (e + w) - w_old run on one thread each (same operation order as
+// minn_rtl._RunningSum.step, so the results stay bit-equal to the reference).
+constexpr int RWK = 256;
+template <int DT>
+__global__ void __launch_bounds__(RWK) rtl_window_kernel_v2(const void *x, int64_t n, int Q, int D, double *C, double *E)
+{
+    __shared__ double bp[RWK], bo[RWK], bw[RWK], bwo[RWK];
+    __shared__ double st[2];
+    using In = typename InT<DT>::type;
+    const int64_t s = blockIdx.x;
+    const In *xs = reinterpret_cast<const In *>(x) + s * n;
+    double *Cs = C + s * n, *Es = E + s * n;
+    const int tid = threadIdx.x;
+    auto prod_at = [&](int64_t k) -> double {
+        if (k < D) return 0.0;
+        const In a = xs[k], b = xs[k - D];
+        return __dadd_rn(__dmul_rn((double)b.x, (double)a.x), __dmul_rn((double)b.y, (double)a.y));
+    };
+    auto pow_at = [&](int64_t k) -> double {
+        const In a = xs[k];
+        return __dadd_rn(__dmul_rn((double)a.x, (double)a.x), __dmul_rn((double)a.y, (double)a.y));
+    };
+    if (tid < 2) st[tid] = 0.0;
+    for (int64_t i0 = 0; i0 < n; i0 += RWK) {
+        const int64_t i = i0 + tid;
+        __syncthreads();
+        if (i < n) {
+            bp[tid] = prod_at(i); bw[tid] = pow_at(i);
+            bo[tid] = i >= Q ? prod_at(i - Q) : 0.0;
+            bwo[tid] = i >= Q ? pow_at(i - Q) : 0.0;
+        }
+        __syncthreads();
+        const int kmax = (int)(n - i0 < RWK ? n - i0 : RWK);
+        if (tid == 0) {
+            double c = st[0];
+            for (int k = 0; k < kmax; ++k) { c = __dsub_rn(__dadd_rn(c, bp[k]), bo[k]); bp[k] = c; }     // sum_reg + val - oldest
+            st[0] = c;
+        } else if (tid == 32) {
+            double e = st[1];
+            for (int k = 0; k < kmax; ++k) { e = __dsub_rn(__dadd_rn(e, bw[k]), bwo[k]); bw[k] = e; }
+            st[1] = e;
+        }
+        __syncthreads();
+        if (i < n) { Cs[i] = bp[tid]; Es[i] = bw[tid]; }
+    }
+}
+
 // Integer window sums are exact in any order: a tile-parallel version for the int16 datapath (throughput path of the
 // RTL model).  One CTA = RT outputs of one (frame, antenna) stream: products / powers from coalesced loads, int64
 // inclusive scan in shared memory, C[n] = S[n+1] - S[n-Q+1].
@@ -401,10 +449,13 @@ OFS_API int ofs_minn_rtl_metric(const void *x, int32_t in_dtype, int64_t n_frame
     OFS_CUDA(cudaMallocAsync((void **)&C, (size_t)ns * n * sizeof(double), stream));
     OFS_CUDA(cudaMallocAsync((void **)&E, (size_t)ns * n * sizeof(double), stream));
     const int bs = 32;
-    if (in_dtype == OFS_C64)
-        rtl_window_kernel<double, OFS_C64><<<(unsigned)((ns + bs - 1) / bs), bs, 0, stream>>>(x, ns, n, quarter_len, quarter_len, C, E);
-    else
-        rtl_window_kernel<double, OFS_C128><<<(unsigned)((ns + bs - 1) / bs), bs, 0, stream>>>(x, ns, n, quarter_len, quarter_len, C, E);
+    if (in_dtype == OFS_C64) {
+        if (ns < 8192) rtl_window_kernel_v2<OFS_C64><<<(unsigned)ns, RWK, 0, stream>>>(x, n, quarter_len, quarter_len, C, E);
+        else rtl_window_kernel<double, OFS_C64><<<(unsigned)((ns + bs - 1) / bs), bs, 0, stream>>>(x, ns, n, quarter_len, quarter_len, C, E);
+    } else {
+        if (ns < 8192) rtl_window_kernel_v2<OFS_C128><<<(unsigned)ns, RWK, 0, stream>>>(x, n, quarter_len, quarter_len, C, E);
+        else rtl_window_kernel<double, OFS_C128><<<(unsigned)((ns + bs - 1) / bs), bs, 0, stream>>>(x, ns, n, quarter_len, quarter_len, C, E);
+    }
     if (int rc = check_launch("rtl_window_kernel")) return rc;
     const int64_t tot = n_frames * n;
     rtl_combine_kernel<double><<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(C, E, n_frames, n_branches, n, quarter_len,

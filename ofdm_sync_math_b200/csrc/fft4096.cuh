@@ -80,6 +80,21 @@ __device__ __forceinline__ void dft16(C2 (&v)[16])
     }
 }
 
+// w[q] = w1^q for q = 1..15 from ONE table load: squarings and products, depth 4 (error <= 4 roundings) -- the 15 scattered
+// table loads per pass were the long-scoreboard stalls of the kernel; the FMA pipe has room.
+template <typename C2>
+__device__ __forceinline__ void tw_powers(C2 w1, C2 (&w)[16])
+{
+    w[1] = w1;
+    w[2] = cmul(w1, w1);
+    w[3] = cmul(w[2], w1);
+    w[4] = cmul(w[2], w[2]);
+    w[5] = cmul(w[4], w1); w[6] = cmul(w[4], w[2]); w[7] = cmul(w[4], w[3]);
+    w[8] = cmul(w[4], w[4]);
+#pragma unroll
+    for (int q = 9; q < 16; ++q) w[q] = cmul(w[8], w[q - 8]);
+}
+
 // natural order in -> digit-reversed order out
 template <typename C2>
 __device__ void fft_dif(C2 *a, const double2 *tw)
@@ -90,8 +105,10 @@ __device__ void fft_dif(C2 *a, const double2 *tw)
 #pragma unroll
     for (int q = 0; q < 16; ++q) v[q] = a[zpad(q * 256 + t)];
     dft16<C2, false>(v);
+    C2 w[16];
+    tw_powers<C2>(tw4096<C2>(tw, t), w);
 #pragma unroll
-    for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], tw4096<C2>(tw, t * q));
+    for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], w[q]);
 #pragma unroll
     for (int q = 0; q < 16; ++q) a[zpad(q * 256 + t)] = v[q];
     __syncthreads();
@@ -100,8 +117,9 @@ __device__ void fft_dif(C2 *a, const double2 *tw)
 #pragma unroll
     for (int q = 0; q < 16; ++q) v[q] = a[zpad(k0 * 256 + q * 16 + n0)];
     dft16<C2, false>(v);
+    tw_powers<C2>(tw4096<C2>(tw, 16 * n0), w);
 #pragma unroll
-    for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], tw4096<C2>(tw, 16 * n0 * q));
+    for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], w[q]);
 #pragma unroll
     for (int q = 0; q < 16; ++q) a[zpad(k0 * 256 + q * 16 + n0)] = v[q];
     __syncthreads();
@@ -128,16 +146,19 @@ __device__ void ifft_dit(C2 *a, const double2 *tw)
     const int k0 = t >> 4, n0 = t & 15;
 #pragma unroll
     for (int q = 0; q < 16; ++q) v[q] = a[zpad(k0 * 256 + q * 16 + n0)];
+    C2 w[16];
+    tw_powers<C2>(tw4096<C2>(tw, 16 * n0), w);
 #pragma unroll
-    for (int q = 1; q < 16; ++q) v[q] = cmulc(v[q], tw4096<C2>(tw, 16 * n0 * q));
+    for (int q = 1; q < 16; ++q) v[q] = cmulc(v[q], w[q]);
     dft16<C2, true>(v);
 #pragma unroll
     for (int q = 0; q < 16; ++q) a[zpad(k0 * 256 + q * 16 + n0)] = v[q];
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < 16; ++q) v[q] = a[zpad(q * 256 + t)];
+    tw_powers<C2>(tw4096<C2>(tw, t), w);
 #pragma unroll
-    for (int q = 1; q < 16; ++q) v[q] = cmulc(v[q], tw4096<C2>(tw, t * q));
+    for (int q = 1; q < 16; ++q) v[q] = cmulc(v[q], w[q]);
     dft16<C2, true>(v);
 #pragma unroll
     for (int q = 0; q < 16; ++q) a[zpad(q * 256 + t)] = v[q];

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(ZNT, (sizeof(T) == 4 ? 3 : 1)) zc_mf_kernel(co
     // (float path: all fp32 -> 72 KB, 3 CTAs/SM; double path: 144 KB)
     C2 *a = reinterpret_cast<C2 *>(zsm);
     T *se = reinterpret_cast<T *>(zsm + (size_t)ZFP * sizeof(C2));
-    T *pw = se + ZF + 4;
+    T *pw = se + ZFP + 8;
     C2 *acc = reinterpret_cast<C2 *>(pw + ZF);
     __shared__ double wtot[ZNT / 32];
 
@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(ZNT, (sizeof(T) == 4 ? 3 : 1)) zc_mf_kernel(co
             if (j >= 0 && j < n) { const In s = xb[j]; v.x = (T)s.x; v.y = (T)s.y; }
             a[zpad(m)] = v;
         }
-        if (tid == 0) se[0] = (T)0;
+        if (tid == 0) se[0] = (T)0;                      // se is padded like a (index i at i + i/16): the 16-element thread stride
+                                                         // of the serial prefix below would otherwise be a 16-way bank conflict
         __syncthreads();
         // energy prefix se[i+1] = sum_{m<=i} |a[m]|^2: thread-serial + warp scan + CTA carry (carries in float64)
         {
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(ZNT, (sizeof(T) == 4 ? 3 : 1)) zc_mf_kernel(co
             for (int m = 0; m < IPT; ++m) {
                 const C2 v = a[zpad(s0 + m)];
                 run += v.x * v.x + v.y * v.y;
-                se[s0 + m + 1] = run;
+                se[zpad(s0 + m + 1)] = run;
             }
             double t = (double)run;
             for (int o = 1; o < 32; o <<= 1) { const double y = shfl_up_f64(t, o); if (lane >= o) t += y; }
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(ZNT, (sizeof(T) == 4 ? 3 : 1)) zc_mf_kernel(co
             __syncthreads();
             double off = t - (double)run;
             for (int w = 0; w < warp; ++w) off += wtot[w];
-            for (int m = 0; m < IPT; ++m) se[s0 + m + 1] = (T)((double)se[s0 + m + 1] + off);
+            for (int m = 0; m < IPT; ++m) se[zpad(s0 + m + 1)] = (T)((double)se[zpad(s0 + m + 1)] + off);
         }
         __syncthreads();
         fft_dif<C2>(a, tw);
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(ZNT, (sizeof(T) == 4 ? 3 : 1)) zc_mf_kernel(co
         ifft_dit<C2>(a, tw);
         for (int i = tid; i < V; i += ZNT) {
             // output k0+i is the window of local samples [i, i+nr-1]
-            const T e = se[i + nr] - se[i];
+            const T e = se[zpad(i + nr)] - se[zpad(i)];
             const C2 y = a[zpad(nr - 1 + i)];
             T yr = y.x * (T)(1.0 / ZF), yi = y.y * (T)(1.0 / ZF);
             if (mode == 1) {                                   // zc_v2.py:257-271: per-branch normalisation
@@ -305,7 +306,7 @@ OFS_API int ofs_zc_matched_filter(const void *x, int32_t in_dtype, int64_t n_fra
     const bool dbl = in_dtype == OFS_C128 || out_f64;
     // a + se (+ pw + acc when branches are summed)
     const size_t esz_t = dbl ? 8 : 4;
-    const size_t smem = (size_t)ZFP * 2 * esz_t + (size_t)(ZF + 4) * esz_t + (n_branches > 1 ? (size_t)ZF * esz_t + (size_t)ZF * 2 * esz_t : 0);
+    const size_t smem = (size_t)ZFP * 2 * esz_t + (size_t)(ZFP + 8) * esz_t + (n_branches > 1 ? (size_t)ZF * esz_t + (size_t)ZF * 2 * esz_t : 0);
 #define OFS_MF_LAUNCH(T, DT)                                                                                       \
     do {                                                                                                           \
         auto kern = zc_mf_kernel<T, DT>;                                                                           \

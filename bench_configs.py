@@ -235,6 +235,8 @@ def main():
         x = synth.make_batch_device(F, n, "sc", seed=13, device=dev, chunk=64)[:, None]
         ms = timeit(lambda: engine.metric(x, "sc", 2048, want_pr=True, out_f64=False, path="tile"), steps=3, warmup=2)
         emit("sc metric, precise tile kernel (float64 prefix; M,P,R out)", ms, F * n, alg_bytes=F * (8 * n + 16 * (n - 2047)))
+        ms = timeit(lambda: engine.metric(x, "sc", 2048, want_pr=True, out_f64=False, path="stripe"), steps=3, warmup=2)
+        emit("sc metric, stripe kernel with P and R outputs (M,P,R out)", ms, F * n, alg_bytes=F * (8 * n + 16 * (n - 2047)))
         del x
 
 

@@ -49,7 +49,8 @@ extern "C" {
 
 /* kernel family selection */
 #define OFS_PATH_AUTO 0
-#define OFS_PATH_STRIPE 1 /* fast: fp32 products, fp64 carries, TMA-fed persistent stripes (c64 / iq16 in, f32 out) */
+#define OFS_PATH_STRIPE 1 /* fast: fp32 products, fp64 carries, TMA-fed persistent stripes (c64 / iq16 in, f32 out; M always,
+                             P complex64 / R float32 optionally, same pitch and offset as M) */
 #define OFS_PATH_TILE 2   /* precise: float64 prefix sums, any lag / branch count / dtype */
 #define OFS_PATH_ARRAY 3  /* antenna arrays (kind AA, any branch count): branch sum on chip, TMA-fed, c64 / iq16 in, f32 out */
 

@@ -47,7 +47,7 @@ void keep_pool_cached()
 }
 
 int launch_metric_tile(const ofs_metric_desc *d, const void *x, void *M, void *P, void *R, cudaStream_t stream);
-int launch_metric_stripe(const ofs_metric_desc *d, const void *x, float *M, float *chunk_max, int64_t cm_stride,
+int launch_metric_stripe(const ofs_metric_desc *d, const void *x, float *M, void *P, float *R, float *chunk_max, int64_t cm_stride,
                          cudaStream_t stream);
 bool stripe_supported(const ofs_metric_desc *d);
 bool array_supported(int in_dtype, int64_t n, int64_t xfs, int64_t xbs, int L, const void *x);
@@ -165,9 +165,9 @@ OFS_API int ofs_metric(const ofs_metric_desc *d, const void *x, void *M, void *P
                                    d->symbol_len, (float *)M, P, (float *)R, d->out_stride, nullptr, 0, 0.0, (cudaStream_t)stream);
     }
     if (path == OFS_PATH_STRIPE) {
-        OFS_REQUIRE(!P && !R, "ofs_metric: the stripe path writes M only (P, R must be NULL)");
+        OFS_REQUIRE(M, "ofs_metric: the stripe path always writes M");
         OFS_REQUIRE(!chunk_max || cm_stride >= (d->n_samples + 255) / 256, "ofs_metric: cm_stride too small");
-        return launch_metric_stripe(d, x, (float *)M, chunk_max, cm_stride, (cudaStream_t)stream);
+        return launch_metric_stripe(d, x, (float *)M, P, (float *)R, chunk_max, cm_stride, (cudaStream_t)stream);
     }
     OFS_REQUIRE(path == OFS_PATH_TILE, "ofs_metric: unknown path %d", path);
     OFS_REQUIRE(!chunk_max, "ofs_metric: chunk_max is produced by the stripe path only");

@@ -39,6 +39,8 @@ constexpr int SSTAGES = 4;
 struct StripeParams {
     const void *x;
     float *M;
+    float2 *P;                // optional (WPR variant): window sums P (complex64) and R (float32), same pitch / offset as M
+    float *R;
     float *chunk_max;
     int64_t L, xfs, out_stride, cm_stride;
     int64_t stripe_len;       // multiple of BK
@@ -164,8 +166,10 @@ __device__ __forceinline__ float rcp_approx(float x)
 }
 
 // KIND: OFS_SC / OFS_SC_BOTH / OFS_MINN / OFS_AA.   WARPS: D = WARPS*256.
-template <int WARPS, int KIND, int DT>
-__global__ void __launch_bounds__(WARPS * 32, (((KIND == OFS_MINN || KIND == OFS_SC_BOTH) ? 384 : OFS_STRIPE_THREADS) / (WARPS * 32)))
+// WPR: also write P and R (reference-shaped outputs M, P, R at 24 B per sample; 3 CTA-slots of 128 threads per SM for the
+// 24 extra registers).
+template <int WARPS, int KIND, int DT, bool WPR>
+__global__ void __launch_bounds__(WARPS * 32, (((KIND == OFS_MINN && WPR) ? 256 : (KIND == OFS_MINN || KIND == OFS_SC_BOTH || WPR) ? 384 : OFS_STRIPE_THREADS) / (WARPS * 32)))
 metric_stripe_kernel(const StripeParams p, const __grid_constant__ CUtensorMap tmap)
 {
     constexpr int BK = WARPS * SCH;
@@ -211,7 +215,11 @@ metric_stripe_kernel(const StripeParams p, const __grid_constant__ CUtensorMap t
         const int nblk = (int)((t1 - tb + BK - 1) / BK);
         const unsigned char *xrow = reinterpret_cast<const unsigned char *>(p.x) + (size_t)frame * p.xfs * ESZ;
         float *Mrow_t = p.M ? p.M + frame * p.out_stride - p.toff : nullptr;    // indexed by causal t
-        const bool m_vec_ok = p.M && ((reinterpret_cast<uintptr_t>(Mrow_t) & 15) == 0);
+        float2 *Prow_t = (WPR && p.P) ? p.P + frame * p.out_stride - p.toff : nullptr;
+        float *Rrow_t = (WPR && p.R) ? p.R + frame * p.out_stride - p.toff : nullptr;
+        const bool m_vec_ok = p.M && ((reinterpret_cast<uintptr_t>(Mrow_t) & 15) == 0) &&
+                              (!Prow_t || (reinterpret_cast<uintptr_t>(Prow_t) & 15) == 0) &&
+                              (!Rrow_t || (reinterpret_cast<uintptr_t>(Rrow_t) & 15) == 0);
         // first causal time whose output exists and is fully valid (AA: the window must be full, t >= L)
         const int64_t tlo = max(t0, (int64_t)(KIND == OFS_AA ? p.aa_L : p.toff));
         // blocks [i_fast0, i_fast1) are "steady state": fully inside [tlo, t1), loaded by one full bulk copy,
@@ -348,6 +356,8 @@ metric_stripe_kernel(const StripeParams p, const __grid_constant__ CUtensorMap t
 
             // ---- windows, metric --------------------------------------------------------------
             float Mv[SK];
+            float2 Pv[WPR ? SK : 1];
+            float Rw[WPR ? SK : 1];
 #pragma unroll
             for (int j = 0; j < SK; ++j) {
                 const float wqr = br + (cur.sqr[j] - prev.sqr[j]);
@@ -367,6 +377,7 @@ metric_stripe_kernel(const StripeParams p, const __grid_constant__ CUtensorMap t
                     const float num = (KIND == OFS_MINN) ? pp * pp : fmaf(Pr, Pr, Pi * Pi);
                     Mv[j] = num * (r * r);
                 }
+                if (WPR) { Pv[j] = make_float2(Pr, KIND == OFS_AA ? -Pi : Pi); Rw[j] = Rv; }   // sync_aa's P is the conjugate lag product
                 if (H2) { wqr2[j] = wqr1[j]; wqi2[j] = wqi1[j]; we2[j] = we1[j]; }
                 if (H1) { wqr1[j] = wqr; wqi1[j] = wqi; we1[j] = we; }
             }
@@ -409,11 +420,26 @@ metric_stripe_kernel(const StripeParams p, const __grid_constant__ CUtensorMap t
                     float4 *g4 = reinterpret_cast<float4 *>(Mrow_t + wpos + lane * SK);
                     g4[0] = make_float4(Mv[0], Mv[1], Mv[2], Mv[3]);
                     g4[1] = make_float4(Mv[4], Mv[5], Mv[6], Mv[7]);
+                    if (WPR) {
+                        if (Prow_t) {
+                            float4 *p4 = reinterpret_cast<float4 *>(Prow_t + wpos + lane * SK);
+#pragma unroll
+                            for (int q = 0; q < SK / 2; ++q) p4[q] = make_float4(Pv[2 * q].x, Pv[2 * q].y, Pv[2 * q + 1].x, Pv[2 * q + 1].y);
+                        }
+                        if (Rrow_t) {
+                            float4 *r4 = reinterpret_cast<float4 *>(Rrow_t + wpos + lane * SK);
+                            r4[0] = make_float4(Rw[0], Rw[1], Rw[2], Rw[3]);
+                            r4[1] = make_float4(Rw[4], Rw[5], Rw[6], Rw[7]);
+                        }
+                    }
                 } else {
 #pragma unroll
                     for (int j = 0; j < SK; ++j) {
                         const int64_t t = blkpos + myoff + j;
-                        if (t >= p.toff && t < t1) Mrow_t[t] = Mv[j];
+                        if (t >= p.toff && t < t1) {
+                            Mrow_t[t] = Mv[j];
+                            if (WPR) { if (Prow_t) Prow_t[t] = Pv[j]; if (Rrow_t) Rrow_t[t] = Rw[j]; }
+                        }
                     }
                 }
             }
@@ -477,14 +503,14 @@ static bool make_input_map(CUtensorMap *map, const void *x, size_t total_bytes, 
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int WARPS, int KIND, int DT>
+template <int WARPS, int KIND, int DT, bool WPR>
 static int launch_one(StripeParams p, int64_t total_work, cudaStream_t stream)
 {
     constexpr int BK = WARPS * SCH;
     constexpr int ESZ = InT<DT>::bytes;
     const size_t smem = (size_t)SSTAGES * BK * ESZ + (size_t)WARPS * 2 * SCH * sizeof(float) +
                         (size_t)3 * WARPS * 4 * sizeof(double) + SSTAGES * sizeof(uint64_t);
-    auto kern = metric_stripe_kernel<WARPS, KIND, DT>;
+    auto kern = metric_stripe_kernel<WARPS, KIND, DT, WPR>;
     static bool attr_set = false;
     static int occ = 0;
     if (!attr_set) {
@@ -508,10 +534,18 @@ static int launch_one(StripeParams p, int64_t total_work, cudaStream_t stream)
 template <int KIND, int DT>
 static int launch_by_lag(int D, const StripeParams &p, int64_t total_work, cudaStream_t stream)
 {
+    if (p.P || p.R) {
+        switch (D) {
+        case 1024: return launch_one<4, KIND, DT, true>(p, total_work, stream);
+        case 512: return launch_one<2, KIND, DT, true>(p, total_work, stream);
+        case 256: return launch_one<1, KIND, DT, true>(p, total_work, stream);
+        default: set_error("ofs_metric(stripe): lag %d not in {256,512,1024}", D); return OFS_EUNSUPPORTED;
+        }
+    }
     switch (D) {
-    case 1024: return launch_one<4, KIND, DT>(p, total_work, stream);
-    case 512: return launch_one<2, KIND, DT>(p, total_work, stream);
-    case 256: return launch_one<1, KIND, DT>(p, total_work, stream);
+    case 1024: return launch_one<4, KIND, DT, false>(p, total_work, stream);
+    case 512: return launch_one<2, KIND, DT, false>(p, total_work, stream);
+    case 256: return launch_one<1, KIND, DT, false>(p, total_work, stream);
     default: set_error("ofs_metric(stripe): lag %d not in {256,512,1024}", D); return OFS_EUNSUPPORTED;
     }
 }
@@ -545,7 +579,7 @@ bool stripe_supported(const ofs_metric_desc *d)
            (d->in_dtype == OFS_C64 || d->in_dtype == OFS_IQ16) && ofs_metric_out_len(d) > 0;
 }
 
-int launch_metric_stripe(const ofs_metric_desc *d, const void *x, float *M, float *chunk_max, int64_t cm_stride,
+int launch_metric_stripe(const ofs_metric_desc *d, const void *x, float *M, void *P, float *R, float *chunk_max, int64_t cm_stride,
                          cudaStream_t stream)
 {
     if (!stripe_supported(d)) {
@@ -555,11 +589,11 @@ int launch_metric_stripe(const ofs_metric_desc *d, const void *x, float *M, floa
     const int D = stripe_lag(d);
     const int esz = d->in_dtype == OFS_C64 ? 8 : 4;
     StripeParams p{};
-    p.x = x; p.M = M; p.chunk_max = chunk_max;
+    p.x = x; p.M = M; p.P = (float2 *)P; p.R = R; p.chunk_max = chunk_max;
     p.L = d->n_samples; p.xfs = d->x_frame_stride; p.out_stride = d->out_stride; p.cm_stride = cm_stride;
     p.n_frames = d->n_frames;
     p.toff = d->kind == OFS_AA ? 0 : d->symbol_len - 1;
-    p.store_mode = d->store_mode;
+    p.store_mode = (P || R) ? 0 : d->store_mode;          // the bulk-store variant carries M only
     p.aa_L = d->symbol_len; p.aa_floor = 1e-6f * (float)d->symbol_len;
     // bulk copies need 16-byte aligned sources: base pointer and frame pitch
     p.use_tma = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (((size_t)d->x_frame_stride * esz) % 16 == 0);

@@ -92,9 +92,11 @@ def metric(rx, kind: str, symbol_len: int, *, want_pr: bool = True, out_f64: boo
                      n_branches=B, n_frames=F, n_samples=n, x_frame_stride=B * n, x_branch_stride=n,
                      out_stride=0, store_mode=store_mode, reserved=1 if tma_mode == 1 else 0)
     lib = L.lib()
-    use_stripe = path != "tile" and not want_pr and not out_f64 and bool(lib.ofs_metric_stripe_ok(C.byref(d), _ptr(x), None))
+    stripe_ok = not out_f64 and bool(lib.ofs_metric_stripe_ok(C.byref(d), _ptr(x), None))
+    # auto keeps P / R requests on the precise kernels; path="stripe" serves them from the fast kernel (float32 windows)
+    use_stripe = stripe_ok and (path == "stripe" or (path == "auto" and not want_pr))
     if path == "stripe" and not use_stripe:
-        raise L.OfsError("stripe path cannot serve this request (needs c64/iq16, 1 branch, lag in {256,512,1024}, M only)")
+        raise L.OfsError("stripe path cannot serve this request (needs c64/iq16, 1 branch, lag in {256,512,1024}, float32 outputs)")
     if use_stripe:
         # causal-time rows: element d of a frame lives at column toff + d, so the kernel's 16-byte
         # vector / bulk stores (which work in t = d + toff) are aligned.
@@ -102,6 +104,10 @@ def metric(rx, kind: str, symbol_len: int, *, want_pr: bool = True, out_f64: boo
         pitch = (n + 3) // 4 * 4
         buf = torch.empty((F, pitch), dtype=torch.float32, device=dev)
         M = buf[:, toff:toff + out_len]
+        Pb = torch.empty((F, pitch), dtype=torch.complex64, device=dev) if want_pr else None
+        Rb = torch.empty((F, pitch), dtype=torch.float32, device=dev) if want_pr else None
+        P = None if Pb is None else Pb[:, toff:toff + out_len]
+        R = None if Rb is None else Rb[:, toff:toff + out_len]
         cm = None
         cm_stride = 0
         if want_chunk_max:
@@ -109,9 +115,9 @@ def metric(rx, kind: str, symbol_len: int, *, want_pr: bool = True, out_f64: boo
             cm = torch.zeros((F, cm_stride), dtype=torch.float32, device=dev)
         d.out_stride = pitch
         d.path = L.OFS_PATH_STRIPE
-        L.check(lib.ofs_metric(C.byref(d), _ptr(x), C.c_void_p(M.data_ptr()), None, None, _ptr(cm), C.c_int64(cm_stride),
-                               _stream()), "ofs_metric(stripe)")
-        return MetricOut(M, None, None, cm, "stripe")
+        L.check(lib.ofs_metric(C.byref(d), _ptr(x), C.c_void_p(M.data_ptr()), C.c_void_p(0 if P is None else P.data_ptr()),
+                               C.c_void_p(0 if R is None else R.data_ptr()), _ptr(cm), C.c_int64(cm_stride), _stream()), "ofs_metric(stripe)")
+        return MetricOut(M, P, R, cm, "stripe")
     array_ok = kind == "aa" and not out_f64 and bool(lib.ofs_metric_array_ok(C.byref(d), _ptr(x)))
     if path == "array" and not array_ok:
         raise L.OfsError("array path cannot serve this request (kind aa, c64/iq16, float32 out, L in {128,256,512,1024}, 16-byte rows)")

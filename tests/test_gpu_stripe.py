@@ -259,3 +259,32 @@ def test_minn_sync_pipeline():
         c = int(rec["coarse"][f])
         M0, P0, R0 = orc.metric_prefix_c64(x[f], 2048, 2, want_pr=True)
         assert abs(rec["cfo"][f] + np.angle(P0[c]) / (2 * np.pi * 512)) * 2 * np.pi <= 1e-5
+
+
+@pytest.mark.parametrize("kind,N", [("sc", 2048), ("sc_both", 2048), ("minn", 2048), ("aa", 512), ("sc", 512)])
+@pytest.mark.parametrize("dtype", ["c64", "iq16"])
+def test_stripe_pr_outputs_vs_oracle(kind, N, dtype):
+    """The stripe kernel's P / R outputs (path="stripe", want_pr=True): reference-shaped (M, P, R) at HBM speed.
+    P, R within 2e-5 of their scale (float32 windows with float64 carries), M to the usual 1e-4."""
+    from ofdm_sync_math_b200 import engine
+    n = 20480 + 3 * 1024 + 4
+    x = _captures(3, n, "minn" if kind == "minn" else "sc", seed=21)
+    if dtype == "iq16":
+        q = np.round(np.stack((x.real, x.imag), axis=-1) * 300.0).clip(-2047, 2047).astype(np.int16)
+        xd = torch.as_tensor(q).cuda()[:, None]
+        x = (q[..., 0].astype(np.float32) + 1j * q[..., 1].astype(np.float32)).astype(np.complex64)
+    else:
+        xd = _dev(x)
+    r = engine.metric(xd, kind, N, want_pr=True, path="stripe")
+    assert r.path == "stripe" and r.P is not None and r.R is not None
+    M, P, R = r.M.cpu().numpy(), r.P.cpu().numpy(), r.R.cpu().numpy()
+    for f in range(x.shape[0]):
+        if kind == "aa":
+            o = orc.aa_detect_streaming(x[f].astype(np.complex128), L=N)
+            Mo, Po, Ro = o["M"], o["P"], o["R"]
+        else:
+            k = {"sc": 0, "sc_both": 1, "minn": 2}[kind]
+            Mo, Po, Ro = orc.metric_prefix_c64(x[f], N, k, want_pr=True)
+        _check_metric(M[f:f + 1], Mo[None])
+        assert np.abs(P[f] - Po).max() <= 2e-5 * np.abs(Po).max()
+        assert np.abs(R[f] - Ro).max() <= 2e-5 * Ro.max()

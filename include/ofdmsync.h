@@ -256,6 +256,16 @@ int ofs_channel_apply(const void *tx, int32_t dtype, int64_t n_rows, int64_t n_t
                       const double *snr_db, const double *cfo_hz, double fs, const double *full_scale, int32_t bits,
                       void *out, int16_t *out_iq, int64_t out_stride, void *faded_ws, double *power_ws, void *stream);
 
+/* 12-bit wire formats of the RTL side <-> the int16 IQ layout [n_channels][n][2] the OFS_IQ16 kernels ingest.
+ *   OFS_WIRE_HEX24   uint32 words, {Re[11:0], Im[11:0]} with Re in the upper 12 bits -- docs/preamble_test_vector.hex; 1 channel
+ *   OFS_WIRE_AXIS48  uint64 words, {ch1_q, ch1_i, ch0_q, ch0_i} x 12 bits, ch0_i lowest -- ref/test_minn_preamble_detector.py:41-47,
+ *                    minn_preamble_detector.sv:23,98-101; 2 channels
+ * pack keeps the low 12 bits of every component (two's complement), unpack sign-extends them.  Device pointers. */
+#define OFS_WIRE_HEX24 0
+#define OFS_WIRE_AXIS48 1
+int ofs_wire_pack(const int16_t *iq, int64_t n, int32_t format, void *words, void *stream);
+int ofs_wire_unpack(const void *words, int64_t n, int32_t format, int16_t *iq, void *stream);
+
 /* CP-correlation CFO estimators, one result per frame; x: (n_frames, n_branches, n), branches summed.
  *   mode 0  core.estimate_cfo_from_cp               core.py:179-196   P = sum_n x[start+n] conj(x[start+n+N]), n < cp_len
  *   mode 1  core.estimate_cfo_from_cp_robust        core.py:199-230   sum of P(d), window win_len, d in [start-span, start+span)

@@ -15,6 +15,7 @@ LIB_PATH = _PKG / "libofdmsync.so"
 OFS_C64, OFS_C128, OFS_IQ16 = 0, 1, 2
 OFS_SC, OFS_SC_BOTH, OFS_MINN, OFS_AA = 0, 1, 2, 3
 OFS_PATH_AUTO, OFS_PATH_STRIPE, OFS_PATH_TILE, OFS_PATH_ARRAY = 0, 1, 2, 3
+OFS_WIRE_HEX24, OFS_WIRE_AXIS48 = 0, 1
 OFS_MAX_EVENTS = 64
 
 i32, i64, f64, vp = C.c_int32, C.c_int64, C.c_double, C.c_void_p

@@ -317,3 +317,61 @@ OFS_API int ofs_cp_cfo(const void *x, int32_t in_dtype, int64_t n_frames, int32_
 #undef OFS_CFO_LAUNCH
     return check_launch("cp_cfo_kernel");
 }
+
+// -------------------------------------------------------------------------------------------------------------------
+// 12-bit wire formats of the RTL side: one launch moves every word once, coalesced both ways.
+//   OFS_WIRE_HEX24   uint32 word = {Re[11:0], Im[11:0]}, Re in the upper 12 bits         (docs/preamble_test_vector.hex)
+//   OFS_WIRE_AXIS48  uint64 word = {ch1_q, ch1_i, ch0_q, ch0_i} x 12 bits, ch0_i lowest   (ref/test_minn_preamble_detector.py:41-47,
+//                                                                                          minn_preamble_detector.sv:23,98-101)
+// int16 IQ layout on the other side: [n_channels][n][2], the layout every OFS_IQ16 kernel ingests.
+__device__ __forceinline__ int sext12(unsigned v) { return (int)(v << 20) >> 20; }
+
+__global__ void __launch_bounds__(256) wire_pack_kernel(const short2 *__restrict__ iq, int64_t n, int64_t ch_stride, int fmt, void *__restrict__ words)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const short2 a = iq[i];
+    if (fmt == OFS_WIRE_HEX24) {
+        reinterpret_cast<uint32_t *>(words)[i] = (((unsigned)a.x & 0xfffu) << 12) | ((unsigned)a.y & 0xfffu);
+    } else {
+        const short2 b = iq[ch_stride + i];
+        const uint64_t lo = ((unsigned)a.x & 0xfffu) | (((unsigned)a.y & 0xfffu) << 12);
+        const uint64_t hi = ((unsigned)b.x & 0xfffu) | (((unsigned)b.y & 0xfffu) << 12);
+        reinterpret_cast<uint64_t *>(words)[i] = lo | (hi << 24);
+    }
+}
+
+__global__ void __launch_bounds__(256) wire_unpack_kernel(const void *__restrict__ words, int64_t n, int64_t ch_stride, int fmt, short2 *__restrict__ iq)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    if (fmt == OFS_WIRE_HEX24) {
+        const uint32_t w = reinterpret_cast<const uint32_t *>(words)[i];
+        iq[i] = make_short2((short)sext12(w >> 12), (short)sext12(w));
+    } else {
+        const uint64_t w = reinterpret_cast<const uint64_t *>(words)[i];
+        const unsigned lo = (unsigned)(w & 0xffffffu), hi = (unsigned)((w >> 24) & 0xffffffu);
+        iq[i] = make_short2((short)sext12(lo), (short)sext12(lo >> 12));
+        iq[ch_stride + i] = make_short2((short)sext12(hi), (short)sext12(hi >> 12));
+    }
+}
+
+OFS_API int ofs_wire_pack(const int16_t *iq, int64_t n, int32_t format, void *words, void *stream)
+{
+    OFS_REQUIRE(iq && words, "ofs_wire_pack: null argument");
+    OFS_REQUIRE(format == OFS_WIRE_HEX24 || format == OFS_WIRE_AXIS48, "ofs_wire_pack: unknown format");
+    OFS_REQUIRE(n >= 0, "ofs_wire_pack: bad length");
+    if (n == 0) return OFS_OK;
+    wire_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const short2 *>(iq), n, n, format, words);
+    return check_launch("wire_pack_kernel");
+}
+
+OFS_API int ofs_wire_unpack(const void *words, int64_t n, int32_t format, int16_t *iq, void *stream)
+{
+    OFS_REQUIRE(iq && words, "ofs_wire_unpack: null argument");
+    OFS_REQUIRE(format == OFS_WIRE_HEX24 || format == OFS_WIRE_AXIS48, "ofs_wire_unpack: unknown format");
+    OFS_REQUIRE(n >= 0, "ofs_wire_unpack: bad length");
+    if (n == 0) return OFS_OK;
+    wire_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(words, n, n, format, reinterpret_cast<short2 *>(iq));
+    return check_launch("wire_unpack_kernel");
+}

@@ -596,7 +596,7 @@ def channel_apply(tx, taps=None, *, row_of_stream=None, unit_noise=None, snr_db=
     snr, cfo, fsc = dv(snr_db), dv(cfo_hz), dv(full_scale)
     nz = None
     if unit_noise is not None:
-        nz = unit_noise if isinstance(unit_noise, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(unit_noise))
+        nz = unit_noise if isinstance(unit_noise, torch.Tensor) else torch.as_tensor(np.array(unit_noise, order="C"))
         nz = nz.to(device=dev, dtype=t.dtype).reshape(S, -1).contiguous()
     out = torch.empty((S, n_out), dtype=t.dtype, device=dev)
     iq = torch.empty((S, n_out, 2), dtype=torch.int16, device=dev) if want_iq else None
@@ -607,6 +607,44 @@ def channel_apply(tx, taps=None, *, row_of_stream=None, unit_noise=None, snr_db=
                                       _ptr(fsc), int(bits), _ptr(out), _ptr(iq), C.c_int64(n_out), _ptr(ws), _ptr(pw), _stream()),
             "ofs_channel_apply")
     return out, iq
+
+
+def wire_pack(iq, fmt: str) -> torch.Tensor:
+    """int16 IQ -> the RTL side's 12-bit words (ofs_wire_pack).  fmt "hex24": iq [n, 2] -> int32[n] words {Re, Im}
+    (docs/preamble_test_vector.hex); fmt "axis48": iq [2, n, 2] -> int64[n] words {ch1_q, ch1_i, ch0_q, ch0_i}
+    (ref/test_minn_preamble_detector.py:41-47)."""
+    t = iq if isinstance(iq, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(iq))
+    if t.dtype != torch.int16 or t.shape[-1] != 2:
+        raise TypeError("wire_pack takes int16 IQ with a trailing axis of 2")
+    t = t.to(_device()).contiguous()
+    if fmt == "hex24":
+        if t.dim() != 2:
+            raise ValueError("hex24 packs one channel: iq [n, 2]")
+        n, code, w = t.shape[0], L.OFS_WIRE_HEX24, torch.empty(t.shape[0], dtype=torch.int32, device=t.device)
+    elif fmt == "axis48":
+        if t.dim() != 3 or t.shape[0] != 2:
+            raise ValueError("axis48 packs two channels: iq [2, n, 2]")
+        n, code, w = t.shape[1], L.OFS_WIRE_AXIS48, torch.empty(t.shape[1], dtype=torch.int64, device=t.device)
+    else:
+        raise ValueError(f"unknown wire format {fmt!r}")
+    if n:
+        L.check(L.lib().ofs_wire_pack(_ptr(t), C.c_int64(n), int(code), _ptr(w), _stream()), "ofs_wire_pack")
+    return w
+
+
+def wire_unpack(words, fmt: str) -> torch.Tensor:
+    """The inverse of wire_pack (ofs_wire_unpack): words -> int16 IQ [n, 2] (hex24) or [2, n, 2] (axis48), sign-extended."""
+    dt = {"hex24": torch.int32, "axis48": torch.int64}.get(fmt)
+    if dt is None:
+        raise ValueError(f"unknown wire format {fmt!r}")
+    w = words if isinstance(words, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(np.asarray(words).astype(np.int64)))
+    w = w.to(device=_device(), dtype=dt).reshape(-1).contiguous()
+    n = w.numel()
+    iq = torch.empty((n, 2) if fmt == "hex24" else (2, n, 2), dtype=torch.int16, device=w.device)
+    code = L.OFS_WIRE_HEX24 if fmt == "hex24" else L.OFS_WIRE_AXIS48
+    if n:
+        L.check(L.lib().ofs_wire_unpack(_ptr(w), C.c_int64(n), int(code), _ptr(iq), _stream()), "ofs_wire_unpack")
+    return iq
 
 
 def cp_cfo(rx, starts, n_fft: int = 2048, cp_len: int = 512, fs: float = 30.72e6, mode: str = "plain", span: int | None = None,

@@ -416,6 +416,56 @@ def gen_rx_chain(out: Path) -> None:
             print("rxchain", name, tag, int(loc["pilot_cp_start"]), float(loc["evm_db"]), float(loc["timing_offset_samples"]))
 
 
+def gen_aa_grid(out: Path) -> None:
+    """the 135-case grid of sync_aa.main (sync_aa.py:1102-1109 -> run_grid_test :829-897 -> run_single_test
+    :669-823), run UNMODIFIED and serially; one row of TestResult fields per case, in the reference's loop order."""
+    import contextlib
+    import io
+    import time
+    import sync_aa as aa
+    kw = dict(snr_values=[-5, 0, 5, 10, 15], channels=[None, "cir1", "cir2"], full_scale_ratios=[0.5, 1.0, 2.0],
+              preamble_lengths=list(aa.PREAMBLE_LENGTHS), cfo_hz=500.0, plot_samples=False)
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        res = aa.run_grid_test(**kw)
+    dt = time.perf_counter() - t0
+    chan_code = {"awgn": 0, "cir1": 1, "cir2": 2}
+    np.savez_compressed(
+        out / "aa_grid.npz",
+        snr_db=np.array([r.snr_db for r in res], dtype=np.float64), channel=np.array([chan_code[r.channel] for r in res], dtype=np.int64),
+        fs_ratio=np.array([r.full_scale_ratio for r in res], dtype=np.float64),
+        preamble_length=np.array([r.preamble_length for r in res], dtype=np.int64),
+        timing_error=np.array([r.timing_error for r in res], dtype=np.int64),
+        cfo_estimated_hz=np.array([r.cfo_estimated_hz for r in res], dtype=np.float64),
+        cfo_error_hz=np.array([r.cfo_error_hz for r in res], dtype=np.float64),
+        detected=np.array([r.detected for r in res], dtype=np.bool_), num_events=np.array([r.num_events for r in res], dtype=np.int64),
+        clipping_pct=np.array([r.clipping_pct for r in res], dtype=np.float64),
+        effective_bits=np.array([r.effective_bits for r in res], dtype=np.float64),
+        metric_peak=np.array([r.metric_peak for r in res], dtype=np.float64), reference_seconds=np.float64(dt),
+    )
+    print(f"aa grid: {len(res)} cases, {sum(r.detected for r in res)} detected, reference run_grid_test took {dt:.1f} s")
+
+
+def gen_wire(out: Path, ref: str) -> None:
+    """The RTL testbench's AXIS word packer (ref/test_minn_preamble_detector.py:41-47), executed UNMODIFIED: the module imports
+    cocotb (absent here), so the one function and the INPUT_WIDTH constant it uses are pulled out of the parsed file."""
+    import ast
+    src = (Path(ref) / "ref" / "test_minn_preamble_detector.py").read_text()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body
+            if (isinstance(n, ast.FunctionDef) and n.name == "_pack_axis_samples")
+            or (isinstance(n, ast.Assign) and any(isinstance(t, ast.Name) and t.id == "INPUT_WIDTH" for t in n.targets))]
+    ns: dict = {}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), "test_minn_preamble_detector.py", "exec"), ns)
+    rng = np.random.default_rng(5)
+    iq = rng.integers(-2048, 2048, size=(2, 4096, 2)).astype(np.int16)
+    iq[:, :4] = [[[-2048, 2047], [2047, -2048], [0, -1], [-1, 0]]] * 2
+    words = np.array([ns["_pack_axis_samples"](int(iq[0, i, 0]), int(iq[0, i, 1]), int(iq[1, i, 0]), int(iq[1, i, 1]))
+                      for i in range(iq.shape[1])], dtype=np.int64)
+    np.savez_compressed(out / "wire_axis.npz", iq=iq, words=words, input_width=np.int64(ns["INPUT_WIDTH"]))
+    print("wire axis", iq.shape, hex(int(words[0])), "INPUT_WIDTH", ns["INPUT_WIDTH"])
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -427,13 +477,16 @@ def main() -> None:
     _setup(a.ref)
     gens = dict(sc=gen_sc, minn=gen_minn, park=gen_park, combined=gen_combined, zc=gen_zc, zc_v2=gen_zc_v2,
                 zc_freq=gen_zc_freq, minn_rtl=gen_minn_rtl, detector_cases=gen_detector_cases,
-                cir_scale=gen_cir_and_scale, channel_cfo=gen_channel_and_cfo, rx_chain=gen_rx_chain)
+                cir_scale=gen_cir_and_scale, channel_cfo=gen_channel_and_cfo, rx_chain=gen_rx_chain,
+                aa_grid=gen_aa_grid)
     for name, fn in gens.items():
         if a.only and name not in a.only.split(","):
             continue
         fn(out)
     if not a.only or "sync_aa" in a.only.split(","):
         gen_sync_aa(out, a.ref)
+    if not a.only or "wire" in a.only.split(","):
+        gen_wire(out, a.ref)
     total = sum(p.stat().st_size for p in out.glob("*.npz"))
     print(f"wrote {len(list(out.glob('*.npz')))} fixtures, {total / 1e6:.1f} MB -> {out}")
 

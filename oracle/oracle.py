@@ -361,6 +361,34 @@ def quantize_adc(x, full_scale: float, bits: int = 12):
     return (qr + 1j * qi) / levels * full_scale, np.stack((qr, qi), axis=-1).astype(np.int16)
 
 
+def wire_pack_hex24(iq):
+    """docs/preamble_test_vector.hex: one 24-bit word per sample, {Re[11:0], Im[11:0]}, Re in the upper 12 bits."""
+    q = np.asarray(iq, dtype=np.int64)
+    return ((q[..., 0] & 0xFFF) << 12) | (q[..., 1] & 0xFFF)
+
+
+def wire_pack_axis48(iq):
+    """ref/test_minn_preamble_detector.py:41-47 (_pack_axis_samples): {ch1_q, ch1_i, ch0_q, ch0_i} x 12 bits, ch0_i lowest.
+    iq: int [2, n, 2]."""
+    q = np.asarray(iq, dtype=np.int64) & 0xFFF
+    return q[0, :, 0] | (q[0, :, 1] << 12) | (q[1, :, 0] << 24) | (q[1, :, 1] << 36)
+
+
+def _sext12(v):
+    v = np.asarray(v, dtype=np.int64) & 0xFFF
+    return np.where(v >= 2048, v - 4096, v).astype(np.int16)
+
+
+def wire_unpack_hex24(words):
+    w = np.asarray(words, dtype=np.int64)
+    return np.stack((_sext12(w >> 12), _sext12(w)), axis=-1)
+
+
+def wire_unpack_axis48(words):
+    w = np.asarray(words, dtype=np.int64)
+    return np.stack((np.stack((_sext12(w), _sext12(w >> 12)), axis=-1), np.stack((_sext12(w >> 24), _sext12(w >> 36)), axis=-1)))
+
+
 def _cp_P(x, d, n_fft, w):
     return np.sum(x[:, d:d + w] * np.conj(x[:, d + n_fft:d + n_fft + w]))
 

@@ -272,3 +272,25 @@ def test_oracle_rx_chain_vs_reference(golden, name):
     assert abs(r["gain"] - complex(g["gain"])) <= 1e-10 * abs(complex(g["gain"]))
     assert abs(r["evm_rms"] - float(g["evm_rms"])) <= 1e-10 and abs(r["evm_db"] - float(g["evm_db"])) <= 1e-8
     assert abs(r["slope"] - float(g["slope"])) <= 1e-10 and abs(r["sto"] - float(g["sto"])) <= 1e-7
+
+
+def test_oracle_wire_formats_vs_reference_vectors(golden):
+    """12-bit wire words: docs/preamble_test_vector.hex (with the csv's integer columns) and the words of
+    the RTL testbench's own packer (ref/test_minn_preamble_detector.py:41-47, tests/golden/wire_axis.npz)."""
+    d = golden("sync_aa_docs")
+    _, codes = orc.quantize_adc(d["preamble"], 2.0)
+    assert np.array_equal(codes, d["csv_preamble"][:, 3:5].astype(np.int16))
+    assert np.array_equal(orc.wire_pack_hex24(codes), d["hex_preamble"])
+    assert np.array_equal(orc.wire_unpack_hex24(d["hex_preamble"]), codes)
+    g = golden("wire_axis")
+    assert int(g["input_width"]) == 12
+    assert np.array_equal(orc.wire_pack_axis48(g["iq"]), g["words"])
+    assert np.array_equal(orc.wire_unpack_axis48(g["words"]), g["iq"])
+
+
+def test_aa_grid_fixture_shape(golden):
+    """The 135-case grid fixture (sync_aa.main's parameters, sync_aa.py:1102-1109) in the reference's loop order."""
+    g = golden("aa_grid")
+    assert g["detected"].shape == (135,) and g["preamble_length"][0] == 1024 and g["preamble_length"][-1] == 256
+    assert np.all(g["num_events"][~g["detected"]] == 0) and np.all(g["num_events"][g["detected"]] >= 1)
+    assert np.all(g["timing_error"][~g["detected"]] == 0)

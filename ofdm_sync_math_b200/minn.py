@@ -65,3 +65,56 @@ def find_minn_peak(M, smooth_win: int = 8, gate_threshold: float = 0.5, search_b
         gate = torch.zeros(n, dtype=torch.bool, device=M.device)
         gate[s:e] = True
     return pk, gate, out(Ms, as_np)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the block-length sweep of minn.py on the batched engine.
+SNR_DB = 0.0
+CFO_HZ = 1000.0
+
+
+def build_minn_preamble_parameterized(rng: np.random.Generator, symbol_len: int, cp_len: int, include_cp: bool = True) -> np.ndarray:
+    """minn.build_minn_preamble_parameterized (minn.py:656-694): random BPSK quarter A -> [A A -A -A], unit power, CP."""
+    if symbol_len % 4 != 0:
+        raise ValueError(f"symbol_len must be divisible by 4, got {symbol_len}")
+    a = rng.choice([-1.0, 1.0], size=symbol_len // 4) + 0j
+    sym = np.concatenate((a, a, -a, -a))
+    pw = np.mean(np.abs(sym) ** 2)
+    if pw > 0:
+        sym = sym / np.sqrt(pw)
+    if not include_cp:
+        return sym
+    return np.concatenate((sym[-cp_len:] if cp_len <= symbol_len else sym, sym))
+
+
+def compare_block_lengths(block_lengths, channel_name=None, snr_db=None):
+    """minn.compare_block_lengths (minn.py:754-871): {N: {peak, par, pmr, timing_error, preamble_len, overhead_pct, metric,
+    P_sum, R_sum}}.  Extension: snr_db may be a sequence -> {snr: {N: {...}}} with all SNRs of a block length evaluated as
+    one batch on the device (what plot_snr_sweep, minn.py:1011-1022, loops over)."""
+    from . import sweeps
+    from .core import TX_PRE_PAD_SAMPLES
+    many = isinstance(snr_db, (list, tuple, np.ndarray))
+    snrs = [float(s) for s in snr_db] if many else [SNR_DB if snr_db is None else float(snr_db)]
+    cir, delay = sweeps.channel_bank(channel_name)
+    res = {s: {} for s in snrs}
+    for N in block_lengths:
+        rng = np.random.default_rng(0)
+        cp_len = N // 4
+        pre = build_minn_preamble_parameterized(rng, N, cp_len, include_cp=True)
+        tx, frame_len = sweeps.two_frame_stream(pre, rng)
+        base = dict(preamble_len=cp_len + N, overhead_pct=100.0 * (cp_len + N) / frame_len)
+        rx = sweeps.received_batch(tx, snrs, cir, CFO_HZ)
+        if rx.shape[2] - N + 1 <= 0:
+            for s in snrs:
+                res[s][N] = dict(peak=0, par=0, pmr=0, timing_error=0, **base)
+            continue
+        r = engine.metric(rx, "minn", int(N), want_pr=True, out_f64=True, path="tile")
+        pk = sweeps.first_frame_argmax(r.M, TX_PRE_PAD_SAMPLES + frame_len + frame_len // 2)
+        peak, par, pmr = (t.cpu().numpy() for t in sweeps.peak_statistics(r.M, pk))
+        pk_h = pk.cpu().numpy()
+        expected = TX_PRE_PAD_SAMPLES + delay + cp_len
+        M, P, R = r.M.cpu().numpy(), r.P.cpu().numpy(), r.R.cpu().numpy()
+        for i, s in enumerate(snrs):
+            res[s][N] = dict(peak=float(peak[i]), par=float(par[i]), pmr=float(pmr[i]), timing_error=int(pk_h[i]) - expected,
+                             metric=M[i], P_sum=P[i], R_sum=R[i], **base)
+    return res if many else res[snrs[0]]

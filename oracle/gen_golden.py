@@ -466,6 +466,40 @@ def gen_wire(out: Path, ref: str) -> None:
     print("wire axis", iq.shape, hex(int(words[0])), "INPUT_WIDTH", ns["INPUT_WIDTH"])
 
 
+def gen_sweeps(out: Path) -> None:
+    """minn.compare_block_lengths (minn.py:754-871) at SNR 0 / 10 dB and minn_rtl.compare_q_values
+    (minn_rtl.py:1493-1592), run UNMODIFIED for flat AWGN and cir1; scalar results per sweep point, plus the TX builders'
+    outputs the host-side tests pin (minn_rtl.build_minn_preamble_generic for every sequence type)."""
+    import time
+    import minn
+    import minn_rtl
+    d = {}
+    Ns, Qs = [256, 512, 1024, 2048], [64, 128, 256, 512]
+    keys = ("peak", "par", "pmr", "timing_error", "preamble_len", "overhead_pct")
+    t0 = time.perf_counter()
+    for ch, _ in SCEN:
+        tag = ch or "awgn"
+        for snr in (0.0, 10.0):
+            r = minn.compare_block_lengths(Ns, ch, snr)
+            for k in keys:
+                d[f"block_{tag}_snr{int(snr)}_{k}"] = np.array([r[N][k] for N in Ns], dtype=np.float64)
+            print("block lengths", tag, snr, [r[N]["timing_error"] for N in Ns], [round(r[N]["peak"], 4) for N in Ns])
+        d[f"block_{tag}_metric256"] = r[256]["metric"]
+        r = minn_rtl.compare_q_values(Qs, ch)
+        for k in keys:
+            d[f"q_{tag}_{k}"] = np.array([r[Q][k] for Q in Qs], dtype=np.float64)
+        print("q values", tag, [r[Q]["timing_error"] for Q in Qs], [round(r[Q]["peak"], 2) for Q in Qs])
+    d["reference_seconds"] = np.float64(time.perf_counter() - t0)
+    d["block_lengths"], d["q_values"] = np.array(Ns), np.array(Qs)
+    types = ["bpsk_freq", "qpsk_freq", "zc_time", "zc_freq", "chirp", "gold", "const", "random_phase"]
+    d["seq_types"] = np.array(types)
+    for t in types:
+        d[f"pre_{t}"] = minn_rtl.build_minn_preamble_generic(t, np.random.default_rng(3), Q=64)
+    d["pre_param_256"] = minn.build_minn_preamble_parameterized(np.random.default_rng(0), 256, 64)
+    np.savez_compressed(out / "sweeps.npz", **d)
+    print(f"sweeps: reference took {float(d['reference_seconds']):.1f} s")
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -478,7 +512,7 @@ def main() -> None:
     gens = dict(sc=gen_sc, minn=gen_minn, park=gen_park, combined=gen_combined, zc=gen_zc, zc_v2=gen_zc_v2,
                 zc_freq=gen_zc_freq, minn_rtl=gen_minn_rtl, detector_cases=gen_detector_cases,
                 cir_scale=gen_cir_and_scale, channel_cfo=gen_channel_and_cfo, rx_chain=gen_rx_chain,
-                aa_grid=gen_aa_grid)
+                aa_grid=gen_aa_grid, sweeps=gen_sweeps)
     for name, fn in gens.items():
         if a.only and name not in a.only.split(","):
             continue

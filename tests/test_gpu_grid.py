@@ -107,3 +107,49 @@ def test_wire_rejects_bad_input():
     with pytest.raises(ValueError):
         engine.wire_unpack(np.zeros(4, np.int64), "nope")
     assert engine.wire_pack(np.zeros((0, 2), np.int16), "hex24").numel() == 0
+
+
+# ------------------------------------------------------------------------------------------------- minn / minn_rtl sweeps
+SWEEP_KEYS = ("peak", "par", "pmr", "preamble_len", "overhead_pct")
+
+
+def _check_sweep(got, g, prefix, points):
+    """timing_error equal; peak / PAR / PMR 1e-9 relative (float64 metric 1e-12 away from the reference's sequential sums;
+    the noise-floor mean is a different summation order)."""
+    assert [int(got[p]["timing_error"]) for p in points] == g[f"{prefix}_timing_error"].astype(int).tolist(), prefix
+    for k in SWEEP_KEYS:
+        ref = g[f"{prefix}_{k}"]
+        val = np.array([got[p][k] for p in points], dtype=np.float64)
+        assert np.all(np.abs(val - ref) <= 1e-9 * np.maximum(np.abs(ref), 1e-30)), (prefix, k, val, ref)
+
+
+@pytest.mark.parametrize("ch", [None, "cir1"])
+def test_compare_block_lengths_vs_reference_run(golden, ch):
+    from ofdm_sync_math_b200 import minn
+    g = golden("sweeps")
+    Ns = g["block_lengths"].tolist()
+    tag = ch or "awgn"
+    for snr in (0.0, 10.0):
+        r = minn.compare_block_lengths(Ns, ch, snr)
+        _check_sweep(r, g, f"block_{tag}_snr{int(snr)}", Ns)
+    assert np.abs(r[256]["metric"] - g[f"block_{tag}_metric256"]).max() <= 1e-10 * g[f"block_{tag}_metric256"].max()
+    assert r[256]["P_sum"].dtype == np.complex128 and r[256]["R_sum"].shape == r[256]["metric"].shape
+    # batched over SNR: the same numbers from one device pass per block length
+    both = minn.compare_block_lengths(Ns, ch, [0.0, 10.0])
+    for snr in (0.0, 10.0):
+        _check_sweep(both[snr], g, f"block_{tag}_snr{int(snr)}", Ns)
+    # default SNR is the module's SNR_DB = 0 dB
+    _check_sweep(minn.compare_block_lengths(Ns[:1], ch), {k: v[:1] for k, v in g.items() if k.startswith(f"block_{tag}_snr0_")},
+                 f"block_{tag}_snr0", Ns[:1])
+
+
+@pytest.mark.parametrize("ch", [None, "cir1"])
+def test_compare_q_values_vs_reference_run(golden, ch):
+    from ofdm_sync_math_b200 import minn_rtl
+    g = golden("sweeps")
+    Qs = g["q_values"].tolist()
+    tag = ch or "awgn"
+    _check_sweep(minn_rtl.compare_q_values(Qs, ch), g, f"q_{tag}", Qs)
+    many = minn_rtl.compare_q_values(Qs, ch, snr_db=[0.0, 20.0])
+    _check_sweep(many[0.0], g, f"q_{tag}", Qs)
+    assert all(many[20.0][q]["peak"] > 0 for q in Qs)

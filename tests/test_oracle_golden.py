@@ -294,3 +294,29 @@ def test_aa_grid_fixture_shape(golden):
     assert g["detected"].shape == (135,) and g["preamble_length"][0] == 1024 and g["preamble_length"][-1] == 256
     assert np.all(g["num_events"][~g["detected"]] == 0) and np.all(g["num_events"][g["detected"]] >= 1)
     assert np.all(g["timing_error"][~g["detected"]] == 0)
+
+
+def test_sweep_tx_builders_vs_reference(golden):
+    """Host-side transmit builders of the sweep layer against the reference's outputs for the same seeds:
+    minn_rtl.build_minn_preamble_generic (minn_rtl.py:335-358, all sequence types), minn.build_minn_preamble_parameterized
+    (minn.py:656-694), sync_aa.build_aa_preamble (sync_aa.py:160-235)."""
+    from ofdm_sync_math_b200 import minn, minn_rtl, sync_aa
+    g = golden("sweeps")
+    for t in g["seq_types"].tolist():
+        got = minn_rtl.build_minn_preamble_generic(t, np.random.default_rng(3), Q=64)
+        assert got.shape == (320,) and np.abs(got - g[f"pre_{t}"]).max() <= 1e-14, t
+    assert np.array_equal(minn.build_minn_preamble_parameterized(np.random.default_rng(0), 256, 64), g["pre_param_256"])
+    with pytest.raises(ValueError):
+        minn.build_minn_preamble_parameterized(np.random.default_rng(0), 250, 64)
+    with pytest.raises(ValueError):
+        minn_rtl.build_minn_preamble_generic("nope", np.random.default_rng(0))
+    with pytest.raises(ValueError):
+        minn_rtl.build_minn_preamble_generic("qpsk_freq", None)
+    d = golden("sync_aa_docs")
+    pre, zc, papr = sync_aa.build_aa_preamble(1024)
+    assert np.abs(pre - d["preamble"]).max() <= 1e-14 and zc.size == 300
+    for total in (512, 256):
+        p2, _, _ = sync_aa.build_aa_preamble(total)
+        assert p2.size == total and np.abs(p2[: total // 2] - p2[total // 2:]).max() <= 1e-12
+    with pytest.raises(ValueError):
+        sync_aa.build_aa_preamble(300)

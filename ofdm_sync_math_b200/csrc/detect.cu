@@ -806,14 +806,13 @@ __device__ __forceinline__ double fsm_track_value(const FsmParams &p, int64_t ro
     return p.val.at(row, i);
 }
 
+// Two launches per call.  fsm_gates_kernel: one CTA per row builds the bitmask and walks it into gate intervals (written into
+// the row's event slots).  fsm_peaks_kernel: the peak search of the gates, one CTA per (row, gate slice) -- a capture with
+// dozens of gates (64 preambles in a 262 144-sample sync_aa capture) would otherwise scan them one after the other on one SM.
 template <int KIND>
-__global__ void __launch_bounds__(DNT) fsm_kernel(FsmParams p)
+__global__ void __launch_bounds__(DNT) fsm_gates_kernel(FsmParams p)
 {
     extern __shared__ unsigned mask[];
-    __shared__ ArgVal sh_av[DNT / 32];
-    __shared__ long long g_start[OFS_MAX_EVENTS], g_close[OFS_MAX_EVENTS];
-    __shared__ int g_closed[OFS_MAX_EVENTS];
-    __shared__ int g_count;
     const int64_t row = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t n = p.val.n;
@@ -838,14 +837,20 @@ __global__ void __launch_bounds__(DNT) fsm_kernel(FsmParams p)
     // 2. gates = clusters of above-runs separated by fewer than heff below-samples.  Warp 0 walks the mask 32 words
     //    per step (all-zero / all-one groups cost one ballot); the state is replicated in every lane.
     if (tid < 32) {
+        ofs_event *evs = p.events + row * OFS_MAX_EVENTS;
         int cnt = 0; bool open = false; long long gs = 0, last = 0;
         const int64_t nw = (n + 31) / 32;
         long long run_start = -1;
-        auto run_begin = [&](long long a) {
-            if (open && a - last - 1 >= p.heff) {
-                if (cnt < OFS_MAX_EVENTS && lane == 0) { g_start[cnt] = gs; g_close[cnt] = last + p.heff; g_closed[cnt] = 1; }
-                ++cnt; open = false;
+        auto emit = [&](long long close, int closed) {
+            if (cnt < OFS_MAX_EVENTS && lane == 0) {
+                ofs_event ev{};
+                ev.gate_start = gs; ev.gate_end = close; ev.closed = closed; ev.peak_index = -1;
+                evs[cnt] = ev;
             }
+            ++cnt;
+        };
+        auto run_begin = [&](long long a) {
+            if (open && a - last - 1 >= p.heff) { emit(last + p.heff, 1); open = false; }
             if (!open) { open = true; gs = a; }
         };
         bool in_run = false;
@@ -859,52 +864,62 @@ __global__ void __launch_bounds__(DNT) fsm_kernel(FsmParams p)
         if (run_start >= 0) { last = n - 1; }
         if (open) {
             const bool closes = (n - 1 - last) >= p.heff;
-            if (cnt < OFS_MAX_EVENTS && lane == 0) { g_start[cnt] = gs; g_close[cnt] = closes ? last + p.heff : n - 1; g_closed[cnt] = closes; }
-            ++cnt;
+            emit(closes ? last + p.heff : n - 1, closes);
         }
-        if (lane == 0) g_count = cnt;
+        if (lane == 0) p.n_events[row] = cnt;
     }
-    __syncthreads();
-    const int cnt = g_count < OFS_MAX_EVENTS ? g_count : OFS_MAX_EVENTS;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(DNT) fsm_peaks_kernel(FsmParams p)
+{
+    __shared__ ArgVal sh_av[DNT / 32];
+    const int64_t row = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int64_t n = p.val.n;
+    const int total = p.n_events[row];
+    const int cnt = total < OFS_MAX_EVENTS ? total : OFS_MAX_EVENTS;
 
     // 3. peak of each gate over [open, close] with the reference's tie rule
-    for (int e = 0; e < cnt; ++e) {
-        const long long gs = g_start[e], gc = g_close[e];
+    for (int e = blockIdx.y; e < cnt; e += gridDim.y) {
+        ofs_event *slot = p.events + row * OFS_MAX_EVENTS + e;
+        const long long gs = slot->gate_start, gc = slot->gate_end;
+        const int closed = slot->closed;
         ArgVal pk{0.0, -1};
         for (int64_t i = gs + tid; i <= gc; i += DNT) {
             const double v = fsm_track_value<KIND>(p, row, i);
             if (KIND == FSM_RTL) { if (pk.i < 0 || v >= pk.v) { pk.v = v; pk.i = i; } }
             else { if (pk.i < 0 || v > pk.v) { pk.v = v; pk.i = i; } }
         }
-        pk = block_argmax<KIND == FSM_RTL>(pk, sh_av);
+        pk = block_argmax<KIND == FSM_RTL>(pk, sh_av);     // (barriers inside: every thread has read the slot by now)
         if (KIND == FSM_ZC && p.gate_mask) {   // zc_v2.py:409,444: (open, close] when closed, [open, n) otherwise
-            const int64_t a = g_closed[e] ? gs + 1 : gs;
+            const int64_t a = closed ? gs + 1 : gs;
             for (int64_t i = a + tid; i <= gc; i += DNT) p.gate_mask[row * p.mstride + i] = 1;
         }
         if (tid == 0) {
             ofs_event ev{};
-            ev.peak_index = pk.i; ev.gate_start = gs; ev.closed = g_closed[e];
+            ev.peak_index = pk.i; ev.gate_start = gs; ev.closed = closed;
             if (KIND == FSM_AA) {
-                ev.gate_end = g_closed[e] ? gc : n;
+                ev.gate_end = closed ? gc : n;
                 ev.aux = pk.i - 2LL * p.L + 1;
                 ev.value = p.val.at(row, pk.i);
                 if (p.val.f64) { const double2 z = reinterpret_cast<const double2 *>(p.P)[row * p.val.stride + pk.i]; ev.p_re = z.x; ev.p_im = z.y; }
                 else { const float2 z = reinterpret_cast<const float2 *>(p.P)[row * p.val.stride + pk.i]; ev.p_re = z.x; ev.p_im = z.y; }
                 ev.cfo = atan2(ev.p_im, ev.p_re) * p.fs / (2.0 * 3.14159265358979323846 * (double)p.L);
             } else if (KIND == FSM_ZC) {
-                ev.gate_end = g_closed[e] ? gc : n;
+                ev.gate_end = closed ? gc : n;
                 const long long ds = pk.i - p.L + 1;
                 ev.aux = ds > 0 ? ds : 0;
                 ev.value = pk.v;
             } else {
-                ev.gate_end = g_closed[e] ? gc + 1 : n;     // segment end (exclusive), minn_rtl.py:799
+                ev.gate_end = closed ? gc + 1 : n;     // segment end (exclusive), minn_rtl.py:799
                 ev.aux = pk.i + p.L;
                 ev.value = pk.v;
             }
-            p.events[row * OFS_MAX_EVENTS + e] = ev;
+            *slot = ev;
         }
+        __syncthreads();
     }
-    if (tid == 0) p.n_events[row] = g_count;
 }
 
 // ---- host launchers ----------------------------------------------------------------------------------
@@ -1054,9 +1069,15 @@ static int launch_fsm(FsmParams &p, int64_t n_rows, cudaStream_t stream)
     OFS_REQUIRE(p.val.n <= MASK_MAX_N, "gate FSM: rows longer than %lld unsupported", (long long)MASK_MAX_N);
     if (n_rows == 0) return OFS_OK;
     const size_t sm = mask_bytes(p.val.n);
-    if (int rc = set_mask_smem(fsm_kernel<KIND>, sm)) return rc;
-    fsm_kernel<KIND><<<(unsigned)n_rows, DNT, sm, stream>>>(p);
-    return check_launch("fsm_kernel");
+    if (int rc = set_mask_smem(fsm_gates_kernel<KIND>, sm)) return rc;
+    fsm_gates_kernel<KIND><<<(unsigned)n_rows, DNT, sm, stream>>>(p);
+    if (int rc = check_launch("fsm_gates_kernel")) return rc;
+    // gate slices per row: enough CTAs to fill the machine a few times over when the rows are few
+    int64_t slices = (4LL * sm_count() + n_rows - 1) / n_rows;
+    if (slices > OFS_MAX_EVENTS) slices = OFS_MAX_EVENTS;
+    if (slices < 1) slices = 1;
+    fsm_peaks_kernel<KIND><<<dim3((unsigned)n_rows, (unsigned)slices), DNT, 0, stream>>>(p);
+    return check_launch("fsm_peaks_kernel");
 }
 
 OFS_API int ofs_aa_events(const ofs_rows *M, const void *P, int32_t L, double threshold, int32_t hysteresis,

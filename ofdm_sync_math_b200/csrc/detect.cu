@@ -834,40 +834,115 @@ __global__ void __launch_bounds__(DNT) fsm_gates_kernel(FsmParams p)
     }
     __syncthreads();
 
-    // 2. gates = clusters of above-runs separated by fewer than heff below-samples.  Warp 0 walks the mask 32 words
-    //    per step (all-zero / all-one groups cost one ballot); the state is replicated in every lane.
-    if (tid < 32) {
-        ofs_event *evs = p.events + row * OFS_MAX_EVENTS;
-        int cnt = 0; bool open = false; long long gs = 0, last = 0;
-        const int64_t nw = (n + 31) / 32;
-        long long run_start = -1;
-        auto emit = [&](long long close, int closed) {
-            if (cnt < OFS_MAX_EVENTS && lane == 0) {
-                ofs_event ev{};
-                ev.gate_start = gs; ev.gate_end = close; ev.closed = closed; ev.peak_index = -1;
-                evs[cnt] = ev;
-            }
-            ++cnt;
-        };
-        auto run_begin = [&](long long a) {
-            if (open && a - last - 1 >= p.heff) { emit(last + p.heff, 1); open = false; }
-            if (!open) { open = true; gs = a; }
-        };
-        bool in_run = false;
-        for (int64_t w0 = 0; w0 < nw; w0 += 32) {
-            const int64_t wi = w0 + lane;
-            const unsigned m = wi < nw ? mask[wi] : 0u;
-            walk_group(m, w0 * 32, in_run,
-                       [&](long long ps) { run_start = ps; run_begin(ps); },
-                       [&](long long pe) { last = pe - 1; run_start = -1; });
+    // 2. gates = clusters of above-runs separated by fewer than heff below-samples (the reference's open / hysteresis-count /
+    //    close loop, sync_aa.py:495-568, as interval logic): a run start opens a gate when the previous above-sample lies at
+    //    least heff samples back (or does not exist); a run end is the last above-sample of its gate when the next one is at
+    //    least heff samples ahead (or does not exist); the k-th opening pairs with the k-th closing.  Every thread owns an odd
+    //    number of consecutive mask words (conflict-free), the "previous / next above-sample" across threads comes from a block
+    //    prefix-max / suffix-min, the event slots from a block prefix sum of the per-thread counts.
+    constexpr int NW = DNT / 32;
+    __shared__ long long s_last[NW], s_first[NW];
+    __shared__ int s_cs[NW], s_ce[NW];
+    const int warp = tid >> 5;
+    const int64_t nw = (n + 31) / 32;
+    int wpt = (int)((nw + DNT - 1) / DNT);
+    wpt |= 1;
+    const int64_t w_lo = (int64_t)tid * wpt < nw ? (int64_t)tid * wpt : nw;
+    const int64_t w_hi = w_lo + wpt < nw ? w_lo + wpt : nw;
+    long long last = -1, first = LLONG_MAX;
+    for (int64_t w = w_lo; w < w_hi; ++w) {
+        const unsigned m = mask[w];
+        if (m) {
+            if (first == LLONG_MAX) first = w * 32 + __ffs(m) - 1;
+            last = w * 32 + 31 - __clz(m);
         }
-        if (run_start >= 0) { last = n - 1; }
-        if (open) {
-            const bool closes = (n - 1 - last) >= p.heff;
-            emit(closes ? last + p.heff : n - 1, closes);
-        }
-        if (lane == 0) p.n_events[row] = cnt;
     }
+    long long xl = last, xf = first;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long yl = __shfl_up_sync(0xffffffffu, xl, o), yf = __shfl_down_sync(0xffffffffu, xf, o);
+        if (lane >= o && yl > xl) xl = yl;
+        if (lane + o < 32 && yf < xf) xf = yf;
+    }
+    if (lane == 31) s_last[warp] = xl;
+    if (lane == 0) s_first[warp] = xf;
+    long long prev_last = __shfl_up_sync(0xffffffffu, xl, 1), next_first = __shfl_down_sync(0xffffffffu, xf, 1);
+    if (lane == 0) prev_last = -1;
+    if (lane == 31) next_first = LLONG_MAX;
+    __syncthreads();
+    for (int w = 0; w < warp; ++w) if (s_last[w] > prev_last) prev_last = s_last[w];
+    for (int w = warp + 1; w < NW; ++w) if (s_first[w] < next_first) next_first = s_first[w];
+
+    ofs_event *evs = p.events + row * OFS_MAX_EVENTS;
+    auto walk_starts = [&](bool write, int off) -> int {
+        long long run_last = prev_last;
+        int c = 0;
+        for (int64_t w = w_lo; w < w_hi; ++w) {
+            const unsigned m = mask[w];
+            if (!m) continue;
+            const unsigned carry = w > 0 ? mask[w - 1] >> 31 : 0u;
+            unsigned st = m & ~((m << 1) | carry);
+            const long long base = w * 32;
+            while (st) {
+                const int a = __ffs(st) - 1;
+                st &= st - 1;
+                const unsigned below = m & ((1u << a) - 1u);
+                const long long prev = below ? base + 31 - __clz(below) : run_last;
+                if (prev < 0 || base + a - prev - 1 >= p.heff) {
+                    if (write && off + c < OFS_MAX_EVENTS) evs[off + c].gate_start = base + a;
+                    ++c;
+                }
+            }
+            run_last = base + 31 - __clz(m);
+        }
+        return c;
+    };
+    auto walk_ends = [&](bool write, int off_end) -> int {      // descending; off_end = slot after this thread's last closing
+        long long run_first = next_first;
+        int c = 0;
+        for (int64_t w = w_hi - 1; w >= w_lo; --w) {
+            const unsigned m = mask[w];
+            if (!m) continue;
+            const unsigned nb = w + 1 < nw ? mask[w + 1] & 1u : 0u;
+            unsigned en = m & ~((m >> 1) | (nb << 31));
+            const long long base = w * 32;
+            while (en) {
+                const int b = 31 - __clz(en);
+                en &= ~(1u << b);
+                const unsigned above = b == 31 ? 0u : m & ~((2u << b) - 1u);
+                const long long next = above ? base + __ffs(above) - 1 : run_first;
+                const long long pos = base + b;
+                if (next == LLONG_MAX || next - pos - 1 >= p.heff) {
+                    const int idx = off_end - 1 - c;
+                    if (write && idx < OFS_MAX_EVENTS) {
+                        const bool closes = next != LLONG_MAX || (n - 1 - pos) >= p.heff;
+                        evs[idx].gate_end = closes ? pos + p.heff : n - 1;
+                        evs[idx].closed = closes;
+                    }
+                    ++c;
+                }
+            }
+            run_first = base + __ffs(m) - 1;
+        }
+        return c;
+    };
+    const int cs = walk_starts(false, 0), ce = walk_ends(false, 0);
+    int xs = cs, xe = ce;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int ys = __shfl_up_sync(0xffffffffu, xs, o), ye = __shfl_up_sync(0xffffffffu, xe, o);
+        if (lane >= o) { xs += ys; xe += ye; }
+    }
+    if (lane == 31) { s_cs[warp] = xs; s_ce[warp] = xe; }
+    __syncthreads();
+    int off_s = xs - cs, off_e = xe - ce, total = 0;
+    for (int w = 0; w < NW; ++w) {
+        if (w < warp) { off_s += s_cs[w]; off_e += s_ce[w]; }
+        total += s_cs[w];
+    }
+    if (cs) walk_starts(true, off_s);
+    if (ce) walk_ends(true, off_e + ce);
+    if (tid == 0) p.n_events[row] = total;
 }
 
 template <int KIND>

@@ -5,7 +5,8 @@ antenna-array workload.)
 
 One step = every capture of this rank through ofs_aa_detect (array kernel: per-antenna P, R over a TMA ring, antenna sum
 on chip, M / P rows + threshold bitmask out; then the gate FSM + CFO read-out, sync_aa.py:458-568) followed, for N > 1,
-by one all_gather of the event records (64 x 72 B + a count per capture).  No collective touches the samples.
+by one all_gather of the event records (64 x 72 B + a count per capture), issued on a side stream so that it overlaps the
+next step (dist.PipelinedGatherer; --sync-gather keeps it on the compute stream).  No collective touches the samples.
 
     python bench_array.py [--gpus N] [--steps K] [--warmup W] [--captures 8] [--antennas 64] [--samples 262144] [--dtype c64|iq16]
 For N > 1 launch with torchrun, one rank per GPU (weak scaling: --captures is PER GPU).
@@ -37,6 +38,7 @@ def main() -> None:
     ap.add_argument("--samples", type=int, default=262144)
     ap.add_argument("--dtype", default="c64", choices=["c64", "iq16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sync-gather", action="store_true", help="all_gather on the compute stream instead of overlapped with the next step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -66,17 +68,19 @@ def main() -> None:
     x = torch.stack(caps).contiguous()
     del caps, base
     plan = engine.AADetectPlan(F, A, n, HALF_LEN, THRESH, HYST, FS, in_dtype=args.dtype)
-    gather_ev = odist.RecordGatherer(plan.ev) if world > 1 else None
-    gather_cnt = odist.RecordGatherer(plan.cnt.view(torch.uint8).reshape(F, 4)) if world > 1 else None
+    gather = None                                                                      # event slots + counts, one buffer
+    if world > 1:
+        gather = (odist.RecordGatherer if args.sync_gather else odist.PipelinedGatherer)(plan.records.view(1, -1))
 
     def step():
         plan.run(x)
-        if gather_ev is not None:
-            gather_ev.run()
-            gather_cnt.run()
+        if gather is not None:
+            gather.run() if args.sync_gather else gather.push()
 
     for _ in range(args.warmup):
         step()
+    if gather is not None and not args.sync_gather:
+        gather.drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -90,6 +94,8 @@ def main() -> None:
     e0.record()
     for _ in range(args.steps):
         step()
+    if gather is not None and not args.sync_gather:
+        gather.drain()                                   # the last gathers finish inside the timed region
     e1.record()
     torch.cuda.synchronize()
     t1 = time.time()
@@ -132,7 +138,8 @@ def main() -> None:
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"sync_aa.py {A}-antenna [A][A] array detector, {F} captures x {A} antennas x {n} {args.dtype} per GPU, "
-                                   f"captures sharded over {world} GPU(s), NCCL gather of event records only",
+                                   f"captures sharded over {world} GPU(s), NCCL gather of event records only"
+                                   + ("" if world == 1 else (" (on the compute stream)" if args.sync_gather else " (overlapped with the next step)")),
                        "captures_per_gpu": F, "antennas": A, "samples": n, "half_len": HALF_LEN,
                        "l2": f"inputs larger than L2 ({x.numel() * x.element_size() / 1e9:.2f} GB per GPU, no flush needed)"},
             "roofline": {"bound": "hbm", "kernel": "aa_array_kernel + aa gate FSM (whole ofs_aa_detect call)", "achieved": ach, "peak": hbm,

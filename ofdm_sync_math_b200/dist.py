@@ -39,6 +39,44 @@ class RecordGatherer:
         return self.out
 
 
+class PipelinedGatherer:
+    """RecordGatherer off the critical path: the records of step k are snapshotted into one of two staging buffers on the
+    compute stream (a few KB, device to device) and all-gathered on a side stream while step k + 1 computes.  push() after
+    every step; drain() before reading results (or the clock).  result(k) = the gathered list for the step pushed k-th
+    (only the two most recent are kept)."""
+
+    def __init__(self, rec: torch.Tensor):
+        self.world = dist.get_world_size()
+        self.rec = rec
+        self.stage = [torch.zeros_like(rec) for _ in range(2)]
+        self.out = [[torch.zeros_like(rec) for _ in range(self.world)] for _ in range(2)]
+        self.comm = torch.cuda.Stream(device=rec.device)
+        self.ready = [torch.cuda.Event() for _ in range(2)]      # snapshot k written (compute stream)
+        self.done = [torch.cuda.Event() for _ in range(2)]       # gather k finished (side stream)
+        self.k = 0
+
+    def push(self) -> None:
+        b = self.k & 1
+        cur = torch.cuda.current_stream(self.rec.device)
+        if self.k >= 2:
+            cur.wait_event(self.done[b])                         # the gather that last read this staging buffer
+        self.stage[b].copy_(self.rec, non_blocking=True)
+        self.ready[b].record(cur)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.ready[b])
+            dist.all_gather(self.out[b], self.stage[b])
+            self.done[b].record(self.comm)
+        self.k += 1
+
+    def drain(self) -> None:
+        cur = torch.cuda.current_stream(self.rec.device)
+        for b in range(min(self.k, 2)):
+            cur.wait_event(self.done[b])
+
+    def result(self, k: int) -> list[torch.Tensor]:
+        return self.out[k & 1]
+
+
 def gather_records(rec: torch.Tensor, n_total: int) -> np.ndarray | None:
     """Gather every rank's records (sharded with shard_range over n_total frames) and return them in global
     frame order as a uint8 array [n_total, record_bytes] (on every rank)."""

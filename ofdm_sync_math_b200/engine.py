@@ -233,10 +233,14 @@ def _events_to_numpy(ev: torch.Tensor, cnt: torch.Tensor) -> list[np.ndarray]:
     return [raw[i, : int(c[i])] for i in range(rows)]
 
 
-def _event_buffers(n_rows: int, dev):
-    ev = torch.zeros((n_rows, L.OFS_MAX_EVENTS * C.sizeof(L.Event)), dtype=torch.uint8, device=dev)
-    cnt = torch.zeros(n_rows, dtype=torch.int32, device=dev)
-    return ev, cnt
+def _event_buffers(n_rows: int, dev, want_flat: bool = False):
+    """Event slots [n_rows, OFS_MAX_EVENTS * 72 B] and counts int32[n_rows] as two views of ONE allocation, so that a multi-GPU
+    caller ships both with a single all_gather (flat uint8 tensor, want_flat=True)."""
+    row_b = L.OFS_MAX_EVENTS * C.sizeof(L.Event)
+    flat = torch.zeros(n_rows * (row_b + 4), dtype=torch.uint8, device=dev)
+    ev = flat[: n_rows * row_b].view(n_rows, row_b)
+    cnt = flat[n_rows * row_b:].view(torch.int32)
+    return (ev, cnt, flat) if want_flat else (ev, cnt)
 
 
 def aa_events(M: torch.Tensor, P: torch.Tensor, half_len: int, threshold: float, hysteresis: int, sample_rate: float):
@@ -441,7 +445,7 @@ class AADetectPlan:
         self.Rb = torch.empty((n_frames, self.pitch), dtype=torch.float32, device=dev) if want_r else None
         self.mstride = (n + 31) // 32
         self.mask = torch.zeros((n_frames, self.mstride), dtype=torch.int32, device=dev)
-        self.ev, self.cnt = _event_buffers(n_frames, dev)
+        self.ev, self.cnt, self.records = _event_buffers(n_frames, dev, want_flat=True)   # records: what a rank gathers
         self.M, self.P = self.Mb[:, :n], self.Pb[:, :n]
         self.R = None if self.Rb is None else self.Rb[:, :n]
 

@@ -86,3 +86,29 @@ def test_fused_aa_detect_vs_oracle(A, int12):
         assert np.array_equal(got[:, 0], ref["ev_i"][:, 0])
         cfo_err = np.abs(e["cfo"] - ref["ev_f"][:, 3]) * 2 * np.pi / 15.36e6
         assert cfo_err.max() <= 1e-5
+
+
+def test_pipelined_record_gather_single_rank_nccl():
+    """dist.PipelinedGatherer (records of step k all-gathered on a side stream while step k + 1 runs): world-size-1 NCCL group,
+    the gathered copy of every step must be that step's records even though the source buffer is overwritten right after."""
+    import os
+    import socket
+    import torch.distributed as dist
+    from ofdm_sync_math_b200 import dist as odist
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        rec = torch.zeros((1, 4096), dtype=torch.uint8, device="cuda")
+        g = odist.PipelinedGatherer(rec)
+        for k in range(7):
+            rec.fill_(k + 1)
+            g.push()
+            rec.fill_(255)                                   # "the next step" scribbles over the live buffer
+            if k >= 1:
+                g.drain()
+                torch.cuda.synchronize()
+                assert int(g.result(k)[0][0, 0]) == k + 1 and int(g.result(k)[0].min()) == k + 1
+                assert int(g.result(k - 1)[0][0, 17]) == k
+    finally:
+        dist.destroy_process_group()

@@ -1,5 +1,6 @@
 // C-ABI entry points of libofdmsync: library/error plumbing, ofs_metric dispatch and the
 // end-to-end "sync metric + CFO" pipeline (device and host-buffer versions).
+#include <cstdlib>
 #include "common.cuh"
 #include <string.h>
 #include <new>
@@ -293,7 +294,13 @@ OFS_API int ofs_sync_host(ofs_ctx *c, const ofs_metric_desc *d, const void *x_ho
     const int64_t xpitch = (L + 3) / 4 * 4;                 // samples; keeps every frame 16-byte aligned
     const int64_t mpitch = (L + 3) / 4 * 4;                 // floats, causal-time rows (d = t - toff)
     const int64_t cmpitch = (L + 255) / 256;
-    int64_t FB = (int64_t)(256ull << 20) / (int64_t)(xpitch * esz);   // ~256 MB of samples per batch
+    // Frames per pipeline batch.  PCIe is the bound of this call (8 B/sample in, 4 B/sample out, the kernels need < 2 % of the
+    // copy time), so what matters is the fill (first H2D) and the drain (last D2H), both proportional to the batch: 32 MB of
+    // samples per batch keeps them near 0.5 ms each while a batch is still ~0.6 ms of DMA, far above the launch overheads
+    // (measured, profiles/r1_e2e_probe.jsonl: 256 MB 6.02, 64 MB 6.41, 32 MB 6.55, 16 MB 6.56, 8 MB 5.99 Gsamples/s; plain H2D copy 6.95).
+    int64_t batch_mb = 32;
+    if (const char *e = getenv("OFS_HOST_BATCH_MB")) { const long v = atol(e); if (v >= 1 && v <= 4096) batch_mb = v; }
+    int64_t FB = (int64_t)((uint64_t)batch_mb << 20) / (int64_t)(xpitch * esz);
     if (FB < 1) FB = 1;
     if (FB > d->n_frames) FB = d->n_frames;
     const size_t x_need = (size_t)FB * xpitch * esz, m_need = (size_t)FB * mpitch * sizeof(float) + 64;

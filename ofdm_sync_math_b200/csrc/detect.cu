@@ -117,7 +117,7 @@ struct Prune {
 // ~4 loads per output instead of w.  Groups are aligned to the causal time t = d + toff (multiples of 8), so that one
 // warp = 32 groups = one 256-sample chunk.  Every pass of a kernel goes through the same grouping, hence sees
 // bit-identical values.
-template <typename F>
+template <int K = 1, typename F>
 __device__ ArgVal pruned_argmax(const F &fn, int64_t n_out, const Prune &pr, ArgVal *sh_av)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -152,15 +152,26 @@ __device__ ArgVal pruned_argmax(const F &fn, int64_t n_out, const Prune &pr, Arg
         const int cl = c0 + lane;
         const bool pass = cl < nchi && (!have || (double)pr.bound(cl) >= vs.v);
         unsigned m = __ballot_sync(0xffffffffu, pass);
-        while (m) {
-            const int c = c0 + __ffs(m) - 1;
-            m &= m - 1;
-            const int64_t i0 = (int64_t)c * 256 - pr.toff + 8 * lane;
-            if (i0 + 7 < 0 || i0 >= n_out) continue;
-            fn.eval8(i0, v8);
+        while (m) {                              // K surviving chunks per round, in ascending order (first maximum wins)
+            int64_t i0s[K];
+            double vk[K][8];
+            int cnt = 0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (i0 + k >= 0 && i0 + k < n_out && (best.i < 0 || v8[k] > best.v)) { best.v = v8[k]; best.i = i0 + k; }
+            for (int u = 0; u < K; ++u)
+                if (m) {                         // warp-uniform; slots fill in order, out-of-row lanes evaluate zeros
+                    const int c = c0 + __ffs(m) - 1;
+                    m &= m - 1;
+                    i0s[u] = (int64_t)c * 256 - pr.toff + 8 * lane;
+                    cnt = u + 1;
+                }
+            fn.template eval8_multi<K>(i0s, cnt, vk);
+#pragma unroll
+            for (int u = 0; u < K; ++u)
+                if (u < cnt) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (i0s[u] + k >= 0 && i0s[u] + k < n_out && (best.i < 0 || vk[u][k] > best.v)) { best.v = vk[u][k]; best.i = i0s[u] + k; }
+                }
         }
     }
     return block_argmax<false>(best, sh_av);
@@ -182,6 +193,52 @@ __device__ ArgVal range_argmax(const F &fn, int64_t lo, int64_t hi, int toff, Ar
     return block_argmax<false>(best, sh_av);
 }
 
+// Window of W + 7 floats starting SKIP elements after index a, as aligned 16-byte loads (6 instead of 23 predicated scalar
+// loads for W = 16).  Only when the whole span lies inside the row and is 16-byte aligned -- the detectors' 8-groups are
+// aligned to the causal time t = d + toff, which is how the stripe kernel lays M out; anything else takes the scalar path.
+template <int W, int SKIP>
+__device__ __forceinline__ bool load_window_vec(const float *p, int64_t a, int64_t n, float (&y)[W + 7])
+{
+    constexpr int NV = (SKIP + W + 7 + 3) / 4;
+    if (a < 0 || a + 4 * NV > n || (reinterpret_cast<uintptr_t>(p + a) & 15)) return false;
+    const float4 *q = reinterpret_cast<const float4 *>(p + a);
+    float tmp[4 * NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const float4 f = q[v];
+        tmp[4 * v] = f.x; tmp[4 * v + 1] = f.y; tmp[4 * v + 2] = f.z; tmp[4 * v + 3] = f.w;
+    }
+#pragma unroll
+    for (int k = 0; k < W + 7; ++k) y[k] = tmp[SKIP + k];
+    return true;
+}
+
+// Eight consecutive window sums from W + 7 terms with a short dependency chain: pairwise tree for the first window, then
+// o[k] = o[0] + prefix_k(t[W-1+j] - t[j-1]).  (A slid accumulator is a chain of 2 W dependent float64 additions per group; with
+// eight warps per SM that latency, not bandwidth, was what the detectors waited on.  Rounding differs from a slid sum by
+// ~1e-16 of the window sum; every pass of a kernel uses this one function, so all passes see identical values.)
+template <int W>
+__device__ __forceinline__ void window_sums8(double (&t)[W + 7], double (&o)[8])
+{
+    static_assert(W == 8 || W == 16, "power-of-two windows only");
+    double d[8];
+    d[0] = 0.0;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) d[k] = t[W - 1 + k] - t[k - 1];
+#pragma unroll
+    for (int st = 1; st < W; st <<= 1) {
+#pragma unroll
+        for (int q = 0; q < W; q += 2 * st) t[q] += t[q + st];
+    }
+#pragma unroll
+    for (int st = 1; st < 8; st <<= 1) {
+#pragma unroll
+        for (int k = 7; k >= st; --k) d[k] += d[k - st];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = t[0] + d[k];
+}
+
 // ---- S&C plateau end -------------------------------------------------------------------------------
 struct SmoothSame {   // np.convolve(M, ones(w)/w, "same")[i], sc.py:100
     const float *pf;
@@ -196,26 +253,39 @@ struct SmoothSame {   // np.convolve(M, ones(w)/w, "same")[i], sc.py:100
         const double v = pd ? pd[jc] : (double)pf[jc];
         return ok ? v * h : 0.0;
     }
-    // compile-time window: the W+7 values are fetched by independent (predicated) loads first, then slid
+    // compile-time window: the W+7 values are fetched by independent (predicated) loads first, then slid.  The window is held
+    // in the row's own type (float rows: half the registers of a double window; the conversion at use is exact).
+    template <int W, typename T>
+    __device__ __forceinline__ void eval8_raw(const T *p, int64_t i0, double (&o)[8]) const
+    {
+        T y[W + 7];
+        const int64_t j0 = i0 + off - W + 1;
+        bool done = false;
+        if constexpr (sizeof(T) == 4) done = load_window_vec<W, 0>(p, j0, n, y);
+        if (!done) {
+#pragma unroll
+            for (int q = 0; q < W + 7; ++q) {
+                const int64_t j = j0 + q;
+                const bool ok = j >= 0 && j < n;
+                const T v = p[ok ? j : 0];
+                y[q] = ok ? v : T(0);
+            }
+        }
+        double t[W + 7];
+#pragma unroll
+        for (int q = 0; q < W + 7; ++q) t[q] = (double)y[q] * h;
+        window_sums8<W>(t, o);
+    }
     template <int W>
     __device__ __forceinline__ void eval8_t(int64_t i0, double (&o)[8]) const
     {
-        double y[W + 7];
-        const int64_t j0 = i0 + off - W + 1;
-#pragma unroll
-        for (int q = 0; q < W + 7; ++q) y[q] = X(j0 + q);
-        double s = 0.0;
-#pragma unroll
-        for (int q = 0; q < W; ++q) s += y[q];
-        o[0] = s;
-#pragma unroll
-        for (int k = 1; k < 8; ++k) { s += y[W - 1 + k]; s -= y[k - 1]; o[k] = s; }
+        if (pd) eval8_raw<W, double>(pd, i0, o);
+        else eval8_raw<W, float>(pf, i0, o);
     }
     __device__ __forceinline__ void eval8(int64_t i0, double (&o)[8]) const
     {
         if (w == 16) { eval8_t<16>(i0, o); return; }
         if (w == 8) { eval8_t<8>(i0, o); return; }
-        if (w == 32) { eval8_t<32>(i0, o); return; }
         // window of output i: j in [i + off - w + 1, i + off]
         double s = 0.0;
         for (int64_t j = i0 + off - w + 1; j <= i0 + off; ++j) s += X(j);
@@ -227,6 +297,13 @@ struct SmoothSame {   // np.convolve(M, ones(w)/w, "same")[i], sc.py:100
             o[k] = s;
         }
     }
+    template <int K>
+    __device__ __forceinline__ void eval8_multi(const int64_t (&i0)[K], int cnt, double (&o)[K][8]) const
+    {
+#pragma unroll
+        for (int u = 0; u < K; ++u)
+            if (u < cnt) eval8(i0[u], o[u]);
+    }
     __device__ __forceinline__ double operator()(int64_t i) const
     {
         const int64_t g0 = i - (((i + toff) % 8) + 8) % 8;
@@ -236,7 +313,8 @@ struct SmoothSame {   // np.convolve(M, ones(w)/w, "same")[i], sc.py:100
     }
 };
 
-__global__ void __launch_bounds__(DNT) plateau_kernel(RowView r, int cp_len, int lookahead, int smooth_win,
+template <bool F64>
+__global__ void __launch_bounds__(DNT, F64 ? 2 : 3) plateau_kernel(RowView r, int cp_len, int lookahead, int smooth_win,
                                                       int64_t *out, const float *cm, int64_t cm_stride, int toff)
 {
     __shared__ ArgVal sh_av[DNT / 32];
@@ -247,8 +325,8 @@ __global__ void __launch_bounds__(DNT) plateau_kernel(RowView r, int cp_len, int
     const int Lk = lookahead < 0 ? cp_len / 4 : (lookahead > 1 ? lookahead : 1);
     const int w = smooth_win > 1 ? smooth_win : 1;
     SmoothSame Ms;
-    Ms.pf = r.f64 ? nullptr : reinterpret_cast<const float *>(r.data) + row * r.stride;
-    Ms.pd = r.f64 ? reinterpret_cast<const double *>(r.data) + row * r.stride : nullptr;
+    Ms.pf = F64 ? nullptr : reinterpret_cast<const float *>(r.data) + row * r.stride;
+    Ms.pd = F64 ? reinterpret_cast<const double *>(r.data) + row * r.stride : nullptr;
     Ms.n = r.n; Ms.w = w; Ms.h = 1.0 / (double)w; Ms.toff = toff;
     Ms.ms = r.n > w ? r.n : w;
     Ms.off = (int)(((r.n > w ? (int64_t)w : r.n) - 1) / 2);
@@ -354,21 +432,68 @@ struct Trailing {   // minn._trailing_average(max(M,0), w)[i], minn.py:115-128
         return (ok && v > 0.0) ? v : 0.0;
     }
     __device__ __forceinline__ double denom(int64_t i) const { return (double)(i >= w - 1 ? w : (i >= 0 ? i + 1 : 1)); }
+    template <int W, typename T>
+    __device__ __forceinline__ void load_win(const T *p, int64_t i0, T (&y)[W + 7]) const
+    {
+        const int64_t j0 = i0 - W + 1;               // max(M, 0) in the row's own type (zero outside the row)
+        if constexpr (sizeof(T) == 4) {
+            if (load_window_vec<W, 1>(p, j0 - 1, n, y)) {
+#pragma unroll
+                for (int q = 0; q < W + 7; ++q) y[q] = y[q] > 0.f ? y[q] : 0.f;
+                return;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < W + 7; ++q) {
+            const int64_t j = j0 + q;
+            const bool ok = j >= 0 && j < n;
+            const T v = p[ok ? j : 0];
+            y[q] = (ok && v > T(0)) ? v : T(0);
+        }
+    }
+    template <int W, typename T>
+    __device__ __forceinline__ void slide_win(const T (&y)[W + 7], int64_t i0, double (&o)[8]) const
+    {
+        double t[W + 7];
+#pragma unroll
+        for (int q = 0; q < W + 7; ++q) t[q] = (double)y[q];
+        window_sums8<W>(t, o);
+        // W is a power of two here: s * (1/W) is exactly s / W; only the warm-up outputs (i < W-1) need a true division
+        const bool steady = i0 >= W - 1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = steady ? o[k] * (1.0 / W) : o[k] / denom(i0 + k);
+    }
+    template <int W, typename T>
+    __device__ __forceinline__ void eval8_raw(const T *p, int64_t i0, double (&o)[8]) const
+    {
+        T y[W + 7];
+        load_win<W, T>(p, i0, y);
+        slide_win<W, T>(y, i0, o);
+    }
+    // K windows at once: all loads are issued before the first sum, so one warp keeps K chunks in flight (the detectors are
+    // bound by the latency of these scattered reads, not by bandwidth).  Same values as K calls of eval8.
+    template <int K>
+    __device__ __forceinline__ void eval8_multi(const int64_t (&i0)[K], int cnt, double (&o)[K][8]) const
+    {
+        if (K > 1 && w == 16 && pf) {
+            float y[K][23];
+#pragma unroll
+            for (int u = 0; u < K; ++u)
+                if (u < cnt) load_win<16, float>(pf, i0[u], y[u]);
+#pragma unroll
+            for (int u = 0; u < K; ++u)
+                if (u < cnt) slide_win<16, float>(y[u], i0[u], o[u]);
+            return;
+        }
+#pragma unroll
+        for (int u = 0; u < K; ++u)
+            if (u < cnt) eval8(i0[u], o[u]);
+    }
     template <int W>
     __device__ __forceinline__ void eval8_t(int64_t i0, double (&o)[8]) const
     {
-        double y[W + 7];
-        const int64_t j0 = i0 - W + 1;
-#pragma unroll
-        for (int q = 0; q < W + 7; ++q) y[q] = X(j0 + q);
-        double s = 0.0;
-#pragma unroll
-        for (int q = 0; q < W; ++q) s += y[q];
-        // W is a power of two here: s * (1/W) is exactly s / W; only the warm-up outputs (i < W-1) need a true division
-        const bool steady = i0 >= W - 1;
-        o[0] = steady ? s * (1.0 / W) : s / denom(i0);
-#pragma unroll
-        for (int k = 1; k < 8; ++k) { s += y[W - 1 + k]; s -= y[k - 1]; o[k] = steady ? s * (1.0 / W) : s / denom(i0 + k); }
+        if (pd) eval8_raw<W, double>(pd, i0, o);
+        else eval8_raw<W, float>(pf, i0, o);
     }
     __device__ __forceinline__ void eval8(int64_t i0, double (&o)[8]) const
     {
@@ -379,7 +504,6 @@ struct Trailing {   // minn._trailing_average(max(M,0), w)[i], minn.py:115-128
         }
         if (w == 16) { eval8_t<16>(i0, o); return; }
         if (w == 8) { eval8_t<8>(i0, o); return; }
-        if (w == 32) { eval8_t<32>(i0, o); return; }
         double s = 0.0;
         for (int64_t j = i0 - w + 1; j <= i0; ++j) s += X(j);
         o[0] = s / denom(i0);
@@ -398,11 +522,14 @@ struct Trailing {   // minn._trailing_average(max(M,0), w)[i], minn.py:115-128
         return o[i - g0];
     }
 };
+// F64 is the row type as a compile-time constant: the window code of the other type is eliminated, and with it its registers
+// (a double window is 46 registers, a float one 23: float rows run three CTAs per SM instead of two).
+template <bool F64>
 __device__ __forceinline__ Trailing make_trailing(const RowView &r, int64_t row, int w, int toff)
 {
     Trailing t;
-    t.pf = r.f64 ? nullptr : reinterpret_cast<const float *>(r.data) + row * r.stride;
-    t.pd = r.f64 ? reinterpret_cast<const double *>(r.data) + row * r.stride : nullptr;
+    t.pf = F64 ? nullptr : reinterpret_cast<const float *>(r.data) + row * r.stride;
+    t.pd = F64 ? reinterpret_cast<const double *>(r.data) + row * r.stride : nullptr;
     t.n = r.n; t.w = w; t.toff = toff;
     return t;
 }
@@ -463,49 +590,62 @@ __device__ void longest_run_warp(const unsigned *mask, int64_t n, long long &bs,
     bs = rbs; be = rbe;
 }
 
-// Longest run of ones (earliest on ties), executed by the WHOLE CTA: every warp walks its own slice of the mask and reports
-// (run touching the slice start, best run strictly inside, run still open at the slice end); thread 0 stitches the slices in
-// order.  Same answer as longest_run_warp, 1/8 of its latency (it was 2/3 of minn_peak_kernel: seven warps idling at a barrier).
+// Longest run of ones (earliest on ties), executed by the WHOLE CTA: every thread scans its own odd-sized slice of mask words
+// (conflict-free, a zero or all-one word costs a handful of instructions) and reports (run glued to the slice start, best run
+// strictly inside, run still open at the slice end); thread 0 stitches the DNT slices in order.  Same answer as
+// longest_run_warp.  (History: one warp walking the row was 2/3 of minn_peak_kernel; eight warps walking 32-word groups with
+// shuffles still spent 150 k warp-instructions per 1 M-sample row, 29 % of the kernel; this form needs about a tenth.)
 __device__ void longest_run_block(const unsigned *mask, int64_t n, long long &bs, long long &be)
 {
-    constexpr int NW = DNT / 32;
-    __shared__ long long s_pre[NW], s_suf[NW], s_bl[NW], s_bs[NW], s_be[NW], s_res[2];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ long long s_pre[DNT], s_suf[DNT], s_bl[DNT], s_bs[DNT], s_be[DNT], s_res[2];
+    const int tid = threadIdx.x;
     const int64_t nw = (n + 31) / 32;
-    const int64_t groups = (nw + 31) / 32;
-    const int64_t gper = (groups + NW - 1) / NW;
-    const int64_t w_lo = (int64_t)warp * gper * 32, w_hi = w_lo + gper * 32 < nw ? w_lo + gper * 32 : nw;
+    int64_t wpt = (nw + DNT - 1) / DNT;
+    wpt |= 1;
+    const int64_t w_lo = (int64_t)tid * wpt < nw ? (int64_t)tid * wpt : nw;
+    const int64_t w_hi = w_lo + wpt < nw ? w_lo + wpt : nw;
     const long long seg0 = w_lo * 32, seg1 = w_hi * 32 < n ? w_hi * 32 : n;
-    long long best_len = 0, start = -1, rbs = 0, rbe = 0, pre_end = seg0;
-    bool in_run = false;
-    for (int64_t w0 = w_lo; w0 < w_hi; w0 += 32) {
-        const int64_t wi = w0 + lane;
-        unsigned m = wi < w_hi ? mask[wi] : 0u;
-        if (wi < nw && (wi + 1) * 32 > n) m &= (n - wi * 32 >= 32) ? 0xffffffffu : ((1u << (n - wi * 32)) - 1u);
-        walk_group(m, w0 * 32, in_run,
-                   [&](long long p) { start = p; },
-                   [&](long long p) {
-                       const long long e = p < seg1 ? p : seg1;
-                       if (start == seg0) pre_end = e;                                   // run glued to the slice start
-                       else if (e - start > best_len) { best_len = e - start; rbs = start; rbe = e; }
-                   });
+    long long best_len = 0, rbs = 0, rbe = 0, pre_end = seg0, cur = -1;
+    auto close = [&](long long e) {                          // the run [cur, e) ends
+        if (cur == seg0) pre_end = e;
+        else if (e - cur > best_len) { best_len = e - cur; rbs = cur; rbe = e; }
+        cur = -1;
+    };
+    for (int64_t w = w_lo; w < w_hi; ++w) {
+        unsigned m = mask[w];
+        if ((w + 1) * 32 > n) m &= (1u << (int)(n - w * 32)) - 1u;
+        const long long base = w * 32;
+        if (m == 0u) { if (cur >= 0) close(base); continue; }
+        if (m == 0xffffffffu) { if (cur < 0) cur = base; continue; }
+        int pos = 0;
+        while (pos < 32) {
+            const unsigned rest = m >> pos;
+            if (rest & 1u) {
+                if (cur < 0) cur = base + pos;
+                pos += __ffs(~rest) - 1;                      // zeros shifted in at the top end the count at the word boundary
+                if (pos < 32) close(base + pos);
+            } else {
+                if (cur >= 0) close(base + pos);
+                pos += rest == 0u ? 32 - pos : __ffs(rest) - 1;
+            }
+        }
     }
     long long suf = -1;
-    if (in_run) { suf = start; if (start == seg0) pre_end = seg1; }
-    if (lane == 0) { s_pre[warp] = pre_end; s_suf[warp] = suf; s_bl[warp] = best_len; s_bs[warp] = rbs; s_be[warp] = rbe; }
+    if (cur >= 0) { suf = cur; if (cur == seg0) pre_end = seg1; }
+    s_pre[tid] = pre_end; s_suf[tid] = suf; s_bl[tid] = best_len; s_bs[tid] = rbs; s_be[tid] = rbe;
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         long long bl = 0, b0 = 0, b1 = 0, carry = -1;
-        for (int w = 0; w < NW; ++w) {
-            const long long a0 = (long long)w * gper * 32 * 32;
+        for (int t = 0; t < DNT; ++t) {
+            const long long a0 = (long long)t * wpt * 32;
             if (a0 >= n) break;
-            const long long a1 = a0 + gper * 32 * 32 < n ? a0 + gper * 32 * 32 : n;
-            const long long pe = s_pre[w];
-            if (pe >= a1 && s_suf[w] == a0) { if (carry < 0) carry = a0; continue; }     // slice is all ones
+            const long long a1 = a0 + wpt * 32 < n ? a0 + wpt * 32 : n;
+            const long long pe = s_pre[t];
+            if (pe >= a1 && s_suf[t] == a0) { if (carry < 0) carry = a0; continue; }     // slice is all ones
             if (carry >= 0) { if (pe - carry > bl) { bl = pe - carry; b0 = carry; b1 = pe; } carry = -1; }
             else if (pe > a0 && pe - a0 > bl) { bl = pe - a0; b0 = a0; b1 = pe; }
-            if (s_bl[w] > bl) { bl = s_bl[w]; b0 = s_bs[w]; b1 = s_be[w]; }
-            carry = s_suf[w];
+            if (s_bl[t] > bl) { bl = s_bl[t]; b0 = s_bs[t]; b1 = s_be[t]; }
+            carry = s_suf[t];
         }
         if (carry >= 0 && n - carry > bl) { b0 = carry; b1 = n; }
         s_res[0] = b0; s_res[1] = b1;
@@ -514,7 +654,8 @@ __device__ void longest_run_block(const unsigned *mask, int64_t n, long long &bs
     bs = s_res[0]; be = s_res[1];
 }
 
-__global__ void __launch_bounds__(DNT) minn_peak_kernel(RowView r, int smooth_win, double gate_threshold,
+template <bool F64>
+__global__ void __launch_bounds__(DNT, F64 ? 2 : 3) minn_peak_kernel(RowView r, int smooth_win, double gate_threshold,
                                                         int has_bounds, int64_t b_lo, int64_t b_hi, int64_t *peak,
                                                         int64_t *gate_span, void *Ms_out, const float *cm,
                                                         int64_t cm_stride, int toff)
@@ -526,7 +667,7 @@ __global__ void __launch_bounds__(DNT) minn_peak_kernel(RowView r, int smooth_wi
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t n = r.n;
     if (n == 0) { if (tid == 0) { peak[row] = -1; gate_span[2 * row] = gate_span[2 * row + 1] = 0; } return; }
-    const Trailing Ms = make_trailing(r, row, smooth_win > 1 ? smooth_win : 1, toff);
+    const Trailing Ms = make_trailing<F64>(r, row, smooth_win > 1 ? smooth_win : 1, toff);
 
     // pass 1: global first-argmax of Ms (also the fallback answer), optional Ms output
     const int wv = smooth_win > 1 ? smooth_win : 1;
@@ -549,7 +690,8 @@ __global__ void __launch_bounds__(DNT) minn_peak_kernel(RowView r, int smooth_wi
             }
         }
     }
-    ArgVal best = pruned_argmax(Ms, n, pr, sh_av);
+    constexpr int KW = 1;                            // chunks in flight per warp (4 was tried: the code outgrew the instruction cache)
+    ArgVal best = pruned_argmax<KW>(Ms, n, pr, sh_av);
     if (!(best.v > 0.0)) { if (tid == 0) { peak[row] = -2; gate_span[2 * row] = gate_span[2 * row + 1] = 0; } return; }
 
     // pass 2: gate flags -> bitmask (bit index = causal time t = d + toff, so words align with the chunks)
@@ -568,20 +710,32 @@ __global__ void __launch_bounds__(DNT) minn_peak_kernel(RowView r, int smooth_wi
             }
             unsigned m = __ballot_sync(0xffffffffu, pass);
             while (m) {
-                const int c = c0 + __ffs(m) - 1;
-                m &= m - 1;
-                // lane = 8 consecutive causal times of the chunk -> one byte of flags; 4 lanes make a mask word
-                const int64_t i0 = (int64_t)c * 256 - toff + 8 * lane;
-                double v8[8];
-                Ms.eval8(i0, v8);
-                unsigned b8 = 0;
+                int64_t i0s[KW];
+                int cs[KW];
+                double vk[KW][8];
+                int cnt = 0;
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (i0 + k >= 0 && i0 + k < n && v8[k] >= level) b8 |= 1u << k;
-                unsigned wv32 = b8 << (8 * (lane & 3));
-                wv32 |= __shfl_xor_sync(0xffffffffu, wv32, 1);
-                wv32 |= __shfl_xor_sync(0xffffffffu, wv32, 2);
-                if ((lane & 3) == 0) mask[c * 8 + (lane >> 2)] = wv32;
+                for (int u = 0; u < KW; ++u)
+                    if (m) {
+                        cs[u] = c0 + __ffs(m) - 1;
+                        m &= m - 1;
+                        // lane = 8 consecutive causal times of the chunk -> one byte of flags; 4 lanes make a mask word
+                        i0s[u] = (int64_t)cs[u] * 256 - toff + 8 * lane;
+                        cnt = u + 1;
+                    }
+                Ms.template eval8_multi<KW>(i0s, cnt, vk);
+#pragma unroll
+                for (int u = 0; u < KW; ++u)
+                    if (u < cnt) {
+                        unsigned b8 = 0;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (i0s[u] + k >= 0 && i0s[u] + k < n && vk[u][k] >= level) b8 |= 1u << k;
+                        unsigned wv32 = b8 << (8 * (lane & 3));
+                        wv32 |= __shfl_xor_sync(0xffffffffu, wv32, 1);
+                        wv32 |= __shfl_xor_sync(0xffffffffu, wv32, 2);
+                        if ((lane & 3) == 0) mask[cs[u] * 8 + (lane >> 2)] = wv32;
+                    }
             }
         }
     }
@@ -679,7 +833,8 @@ __global__ void sc_gate_seed_kernel(const float *cm, int64_t cm_stride, int64_t 
     if (!(m > 0.f)) gate[row * gstride] = 1;
 }
 
-__global__ void __launch_bounds__(DNT) gated_peak_kernel(RowView r, int smooth_win, const uint8_t *gate,
+template <bool F64>
+__global__ void __launch_bounds__(DNT, F64 ? 2 : 3) gated_peak_kernel(RowView r, int smooth_win, const uint8_t *gate,
                                                          int64_t gstride, int has_bounds, int64_t b_lo,
                                                          int64_t b_hi, int64_t *peak)
 {
@@ -705,7 +860,7 @@ __global__ void __launch_bounds__(DNT) gated_peak_kernel(RowView r, int smooth_w
         if (!g[i]) { stop = i; break; }
     stop = block_min_i64(stop, sh_i);
     if (stop == LLONG_MAX) stop = e;
-    const Trailing Ms = make_trailing(r, row, smooth_win > 1 ? smooth_win : 1, 0);
+    const Trailing Ms = make_trailing<F64>(r, row, smooth_win > 1 ? smooth_win : 1, 0);
     const ArgVal pk = range_argmax(Ms, first, stop, 0, sh_av);
     if (tid == 0) peak[row] = pk.i;
 }
@@ -1029,10 +1184,13 @@ OFS_API int ofs_find_plateau_end_pruned(const ofs_rows *M, const float *chunk_ma
     if (M->n_rows == 0) return OFS_OK;
     const size_t cms = chunk_max ? (size_t)((M->n + toff + 255) / 256 + 8) * sizeof(float) : 0;
     OFS_REQUIRE(cms <= 200 * 1024, "ofs_find_plateau_end: rows too long for the pruned path");
-    if (cms > 48 * 1024) OFS_CUDA(cudaFuncSetAttribute(plateau_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cms));
-    plateau_kernel<<<(unsigned)M->n_rows, DNT, cms, (cudaStream_t)stream>>>(view(M), cp_len, lookahead, smooth_win, plateau_end,
-                                                                           chunk_max, cm_stride, chunk_max ? toff : 0);
-    return check_launch("plateau_kernel");
+    auto go = [&](auto kern) -> int {
+        if (cms > 48 * 1024) OFS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cms));
+        kern<<<(unsigned)M->n_rows, DNT, cms, (cudaStream_t)stream>>>(view(M), cp_len, lookahead, smooth_win, plateau_end, chunk_max,
+                                                                     cm_stride, chunk_max ? toff : 0);
+        return check_launch("plateau_kernel");
+    };
+    return M->f64 ? go(plateau_kernel<true>) : go(plateau_kernel<false>);
 }
 
 OFS_API int ofs_find_plateau_end(const ofs_rows *M, int32_t cp_len, int32_t lookahead, int32_t smooth_win,
@@ -1054,12 +1212,14 @@ OFS_API int ofs_find_minn_peak_pruned(const ofs_rows *M, const float *chunk_max,
     if (M->n_rows == 0) return OFS_OK;
     const int64_t nch_h = (M->n + toff + 255) / 256;
     const size_t sm = mask_bytes(nch_h * 256) + (chunk_max ? (size_t)(nch_h + 8) * sizeof(float) : 0);
-    OFS_REQUIRE(sm <= 220 * 1024, "ofs_find_minn_peak: rows too long");
-    if (int rc = set_mask_smem(minn_peak_kernel, sm)) return rc;
-    minn_peak_kernel<<<(unsigned)M->n_rows, DNT, sm, (cudaStream_t)stream>>>(view(M), smooth_win, gate_threshold, has_bounds,
-                                                                            bound_lo, bound_hi, peak, gate_span, Ms, chunk_max,
-                                                                            cm_stride, toff);
-    return check_launch("minn_peak_kernel");
+    OFS_REQUIRE(sm <= 216 * 1024, "ofs_find_minn_peak: rows too long");   // + 10.4 KB static (longest_run_block) <= 227 KB
+    auto go = [&](auto kern) -> int {
+        if (int rc = set_mask_smem(kern, sm)) return rc;
+        kern<<<(unsigned)M->n_rows, DNT, sm, (cudaStream_t)stream>>>(view(M), smooth_win, gate_threshold, has_bounds, bound_lo, bound_hi,
+                                                                    peak, gate_span, Ms, chunk_max, cm_stride, toff);
+        return check_launch("minn_peak_kernel");
+    };
+    return M->f64 ? go(minn_peak_kernel<true>) : go(minn_peak_kernel<false>);
 }
 
 OFS_API int ofs_find_minn_peak(const ofs_rows *M, int32_t smooth_win, double gate_threshold, int32_t has_bounds,
@@ -1104,8 +1264,12 @@ OFS_API int ofs_find_minn_peak_gated(const ofs_rows *M, int32_t smooth_win, cons
     if (int rc = rows_ok(M, "ofs_find_minn_peak_gated")) return rc;
     OFS_REQUIRE(peak && (gate || M->n == 0) && gate_stride >= M->n, "ofs_find_minn_peak_gated: bad arguments");
     if (M->n_rows == 0) return OFS_OK;
-    gated_peak_kernel<<<(unsigned)M->n_rows, DNT, 0, (cudaStream_t)stream>>>(view(M), smooth_win, gate, gate_stride, has_bounds,
-                                                                            bound_lo, bound_hi, peak);
+    if (M->f64)
+        gated_peak_kernel<true><<<(unsigned)M->n_rows, DNT, 0, (cudaStream_t)stream>>>(view(M), smooth_win, gate, gate_stride, has_bounds,
+                                                                                      bound_lo, bound_hi, peak);
+    else
+        gated_peak_kernel<false><<<(unsigned)M->n_rows, DNT, 0, (cudaStream_t)stream>>>(view(M), smooth_win, gate, gate_stride, has_bounds,
+                                                                                       bound_lo, bound_hi, peak);
     return check_launch("gated_peak_kernel");
 }
 

@@ -590,9 +590,30 @@ __device__ void longest_run_warp(const unsigned *mask, int64_t n, long long &bs,
     bs = rbs; be = rbe;
 }
 
+// Summary of the runs of ones in a bit range [a0, a1): pre = end of the run glued to a0 (a0 if none; a1 if the range is all
+// ones), suf = start of the run glued to a1 (-1 if none), (bl, bs, be) = longest run touching neither end, earliest on ties.
+struct RunSum { long long a0, a1, pre, suf, bl, bs, be; };
+// Summary of [A.a0, B.a1) from two adjacent ranges.  Associative; candidates are compared in order of their start with a strict
+// '>' so that the earliest of equally long runs wins (minn.py:159-182).
+__device__ __forceinline__ RunSum run_join(const RunSum &A, const RunSum &B)
+{
+    if (A.a0 >= A.a1) return B;
+    if (B.a0 >= B.a1) return A;
+    const bool a_all = A.pre >= A.a1, b_all = B.pre >= B.a1;
+    const long long s = A.suf >= 0 ? A.suf : B.a0, e = B.pre;        // the run across the seam: [s, e)
+    RunSum R;
+    R.a0 = A.a0; R.a1 = B.a1;
+    R.bl = A.bl; R.bs = A.bs; R.be = A.be;
+    if (!a_all && !b_all && e - s > R.bl) { R.bl = e - s; R.bs = s; R.be = e; }
+    if (B.bl > R.bl) { R.bl = B.bl; R.bs = B.bs; R.be = B.be; }
+    R.pre = a_all ? e : A.pre;
+    R.suf = b_all ? s : B.suf;
+    return R;
+}
+
 // Longest run of ones (earliest on ties), executed by the WHOLE CTA: every thread scans its own odd-sized slice of mask words
 // (conflict-free, a zero or all-one word costs a handful of instructions) and reports (run glued to the slice start, best run
-// strictly inside, run still open at the slice end); thread 0 stitches the DNT slices in order.  Same answer as
+// strictly inside, run still open at the slice end); warp 0 joins the DNT summaries (run_join: 8 per lane, then a 5-step tree).  Same answer as
 // longest_run_warp.  (History: one warp walking the row was 2/3 of minn_peak_kernel; eight warps walking 32-word groups with
 // shuffles still spent 150 k warp-instructions per 1 M-sample row, 29 % of the kernel; this form needs about a tenth.)
 __device__ void longest_run_block(const unsigned *mask, int64_t n, long long &bs, long long &be)
@@ -634,21 +655,34 @@ __device__ void longest_run_block(const unsigned *mask, int64_t n, long long &bs
     if (cur >= 0) { suf = cur; if (cur == seg0) pre_end = seg1; }
     s_pre[tid] = pre_end; s_suf[tid] = suf; s_bl[tid] = best_len; s_bs[tid] = rbs; s_be[tid] = rbe;
     __syncthreads();
-    if (tid == 0) {
-        long long bl = 0, b0 = 0, b1 = 0, carry = -1;
-        for (int t = 0; t < DNT; ++t) {
-            const long long a0 = (long long)t * wpt * 32;
-            if (a0 >= n) break;
-            const long long a1 = a0 + wpt * 32 < n ? a0 + wpt * 32 : n;
-            const long long pe = s_pre[t];
-            if (pe >= a1 && s_suf[t] == a0) { if (carry < 0) carry = a0; continue; }     // slice is all ones
-            if (carry >= 0) { if (pe - carry > bl) { bl = pe - carry; b0 = carry; b1 = pe; } carry = -1; }
-            else if (pe > a0 && pe - a0 > bl) { bl = pe - a0; b0 = a0; b1 = pe; }
-            if (s_bl[t] > bl) { bl = s_bl[t]; b0 = s_bs[t]; b1 = s_be[t]; }
-            carry = s_suf[t];
+    if (tid < 32) {                                          // warp 0 stitches: 8 slices per lane in order, then a 5-step tree
+        auto slice = [&](int t) {
+            RunSum r;
+            r.a0 = (long long)t * wpt * 32 < n ? (long long)t * wpt * 32 : n;
+            r.a1 = r.a0 + wpt * 32 < n ? r.a0 + wpt * 32 : n;
+            r.pre = s_pre[t]; r.suf = s_suf[t]; r.bl = s_bl[t]; r.bs = s_bs[t]; r.be = s_be[t];
+            return r;
+        };
+        constexpr int PER = DNT / 32;
+        RunSum R = slice(tid * PER);
+#pragma unroll 1
+        for (int k = 1; k < PER; ++k) R = run_join(R, slice(tid * PER + k));
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            RunSum B;
+            B.a0 = __shfl_down_sync(0xffffffffu, R.a0, o); B.a1 = __shfl_down_sync(0xffffffffu, R.a1, o);
+            B.pre = __shfl_down_sync(0xffffffffu, R.pre, o); B.suf = __shfl_down_sync(0xffffffffu, R.suf, o);
+            B.bl = __shfl_down_sync(0xffffffffu, R.bl, o); B.bs = __shfl_down_sync(0xffffffffu, R.bs, o);
+            B.be = __shfl_down_sync(0xffffffffu, R.be, o);
+            if ((tid & (2 * o - 1)) == 0) R = run_join(R, B);
         }
-        if (carry >= 0 && n - carry > bl) { b0 = carry; b1 = n; }
-        s_res[0] = b0; s_res[1] = b1;
+        if (tid == 0) {                                      // candidates in order of their start: glued-to-0 run, inside best, tail run
+            long long bl = 0, b0 = 0, b1 = 0;
+            if (R.pre > R.a0) { bl = R.pre - R.a0; b0 = R.a0; b1 = R.pre; }
+            if (R.bl > bl) { bl = R.bl; b0 = R.bs; b1 = R.be; }
+            if (R.suf >= 0 && R.a1 - R.suf > bl) { b0 = R.suf; b1 = R.a1; }
+            s_res[0] = b0; s_res[1] = b1;
+        }
     }
     __syncthreads();
     bs = s_res[0]; be = s_res[1];

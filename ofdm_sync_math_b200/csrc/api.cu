@@ -90,7 +90,8 @@ __global__ void sync_record_kernel(const void *x, int dtype, int64_t L, int64_t 
     const int nwin = kind == OFS_MINN ? 2 : 1;
     for (int wdw = 0; wdw < nwin; ++wdw) {
         const int64_t base = coarse + (int64_t)wdw * 2 * lag;
-        for (int m = lane; m < lag; m += 32) {
+#pragma unroll 8
+        for (int m = lane; m < lag; m += 32) {      // 8 independent sample pairs in flight per lane (the loop is pure load latency)
             const double2 a = load_sample_f64(xr, dtype, base + m);
             const double2 b = load_sample_f64(xr, dtype, base + lag + m);
             pr += a.x * b.x + a.y * b.y;

@@ -995,6 +995,18 @@ __device__ __forceinline__ double fsm_track_value(const FsmParams &p, int64_t ro
     return p.val.at(row, i);
 }
 
+// Byte flags -> mask bits, four at a time: (valid != 0 && above != 0) per byte, then the four 0/1 bytes are gathered into a
+// nibble by one multiply (byte k lands on bit 24 + k; the partial products occupy distinct bits, so nothing carries).
+__device__ __forceinline__ unsigned flag_nibble(unsigned v, unsigned a)
+{
+    const unsigned f = __vcmpne4(v, 0u) & __vcmpne4(a, 0u) & 0x01010101u;
+    return (f * 0x01020408u) >> 24;
+}
+__device__ __forceinline__ bool flags_vectorisable(const uint8_t *v, const uint8_t *a)
+{
+    return v && a && ((reinterpret_cast<uintptr_t>(v) ^ reinterpret_cast<uintptr_t>(a)) & 15) == 0;
+}
+
 // Two launches per call.  fsm_gates_kernel: one CTA per row builds the bitmask and walks it into gate intervals (written into
 // the row's event slots).  fsm_peaks_kernel: the peak search of the gates, one CTA per (row, gate slice) -- a capture with
 // dozens of gates (64 preambles in a 262 144-sample sync_aa capture) would otherwise scan them one after the other on one SM.
@@ -1011,6 +1023,33 @@ __global__ void __launch_bounds__(DNT) fsm_gates_kernel(FsmParams p)
     if (KIND == FSM_AA && p.premask) {
         const unsigned *pm = p.premask + row * p.premask_stride;
         for (int64_t w = tid; w < nround / 32; w += DNT) mask[w] = pm[w];
+    } else if (KIND != FSM_AA && flags_vectorisable(p.valid + row * p.mstride, p.above + row * p.mstride)) {
+        // byte flags, 16 per thread and load: a 16-byte load of each array -> 16 mask bits, OR-ed into the (zeroed) mask at
+        // their bit position.  Rows need not be 16-byte aligned, only equally misaligned in both arrays: the first `peel`
+        // and the last few samples go one by one.
+        const uint8_t *vr = p.valid + row * p.mstride, *ar = p.above + row * p.mstride;
+        for (int64_t w = tid; w < nround / 32; w += DNT) mask[w] = 0u;
+        __syncthreads();
+        int64_t peel = (16 - (int64_t)(reinterpret_cast<uintptr_t>(vr) & 15)) & 15;
+        if (peel > n) peel = n;
+        const int64_t nfull = (n - peel) / 16;
+        const uint4 *v4 = reinterpret_cast<const uint4 *>(vr + peel);
+        const uint4 *a4 = reinterpret_cast<const uint4 *>(ar + peel);
+        for (int64_t g = tid; g < nfull; g += DNT) {
+            const uint4 v = v4[g], a = a4[g];
+            const unsigned bits = flag_nibble(v.x, a.x) | (flag_nibble(v.y, a.y) << 4) | (flag_nibble(v.z, a.z) << 8) | (flag_nibble(v.w, a.w) << 12);
+            if (bits) {
+                const int64_t pos = peel + 16 * g;
+                const int sh = (int)(pos & 31);
+                atomicOr(&mask[pos >> 5], bits << sh);
+                if (sh > 16) atomicOr(&mask[(pos >> 5) + 1], bits >> (32 - sh));
+            }
+        }
+        const int64_t tail0 = peel + 16 * nfull;                      // < 31 samples left: head [0, peel) and tail [tail0, n)
+        for (int64_t i = tid; i < peel + (n - tail0); i += DNT) {
+            const int64_t j = i < peel ? i : tail0 + (i - peel);
+            if (vr[j] && ar[j]) atomicOr(&mask[j >> 5], 1u << (j & 31));
+        }
     } else
     for (int64_t i = tid; i < nround; i += DNT) {
         bool f = false;

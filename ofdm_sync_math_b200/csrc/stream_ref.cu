@@ -300,6 +300,76 @@ __global__ void __launch_bounds__(RNT) rtl_window_tile_kernel(const short2 *x, i
     }
 }
 
+// Window sums AND antenna combining of the integer datapath in one pass (ref/minn_antenna_path.sv:63-194 summed over the
+// antennas as in ref/minn_preamble_detector.sv:247-275).  Integer addition is exact in any order, and the hold-register
+// gating of the combiner depends on the index only, so the per-sample lag products and powers are summed over the antennas
+// FIRST and a single int64 prefix per tile gives every window:
+//   corr_total[i]   = [i >= Q-1] (Sp[i+1] - Sp[i-Q+1]) + [i >= 2Q-1] (Sp[i-Q+1] - Sp[i-2Q+1])
+//   energy_total[i] = the same two terms on the powers + [i >= 3Q-1] (Sw[i-2Q+1] - Sw[i-3Q+1])          (lower ends clamped at 0)
+// One CTA = RT outputs of one frame; it reads RT + 3Q - 1 samples of every antenna (int16 IQ, 4 B) and writes 25 B per output;
+// the per-antenna window arrays (16 B per antenna-sample written, then read again by a combine kernel) no longer exist.
+__global__ void __launch_bounds__(RNT) rtl_int_fused_kernel(const short2 *x, int nb, int64_t n, int Q, int D, long long *corr_total,
+                                                            long long *corr_positive, long long *energy_total, uint8_t *valid)
+{
+    extern __shared__ long long rsm[];
+    const int halo = 3 * Q - 1;
+    long long *sp = rsm;                   // RT + halo + 1
+    long long *sw = rsm + (RT + halo + 1);
+    __shared__ long long wtot[2][RNT / 32];
+    const int64_t frame = blockIdx.y;
+    const int64_t n0 = (int64_t)blockIdx.x * RT;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int64_t j0 = n0 - halo;
+    if (j0 < 0) j0 = 0;
+    const int64_t nend = n0 + RT < n ? n0 + RT : n;
+    const int cnt = (int)(nend - j0);
+    for (int k = tid; k < cnt; k += RNT) {
+        const int64_t i = j0 + k;
+        long long p = 0, w = 0;
+        for (int b = 0; b < nb; ++b) {
+            const short2 *xs = x + (frame * nb + b) * n;
+            const short2 a = xs[i];
+            if (i >= D) { const short2 c = xs[i - D]; p += (long long)a.x * c.x + (long long)a.y * c.y; }
+            w += (long long)a.x * a.x + (long long)a.y * a.y;
+        }
+        sp[k + 1] = p;
+        sw[k + 1] = w;
+    }
+    if (tid == 0) { sp[0] = 0; sw[0] = 0; }
+    __syncthreads();
+    int ipt = (cnt + RNT - 1) / RNT;
+    ipt |= 1;
+    const int s0 = 1 + tid * ipt, s1 = min(s0 + ipt, cnt + 1);
+    long long ap = 0, aw = 0;
+    for (int q = s0; q < s1; ++q) { ap += sp[q]; sp[q] = ap; aw += sw[q]; sw[q] = aw; }
+    long long tp = ap, tw = aw;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long yp = __shfl_up_sync(0xffffffffu, tp, o), yw = __shfl_up_sync(0xffffffffu, tw, o);
+        if (lane >= o) { tp += yp; tw += yw; }
+    }
+    if (lane == 31) { wtot[0][warp] = tp; wtot[1][warp] = tw; }
+    __syncthreads();
+    long long op = tp - ap, ow = tw - aw;
+    for (int w = 0; w < warp; ++w) { op += wtot[0][w]; ow += wtot[1][w]; }
+    for (int q = s0; q < s1; ++q) { sp[q] += op; sw[q] += ow; }
+    __syncthreads();
+    // S(k) = sum of the samples below index k (k clamped at 0; everything below j0 is outside every window that is used)
+    auto P = [&](int64_t k) { return sp[(k < j0 ? j0 : k) - j0]; };
+    auto W = [&](int64_t k) { return sw[(k < j0 ? j0 : k) - j0]; };
+    for (int64_t i = n0 + tid; i < nend; i += RNT) {
+        long long ct = 0, et = 0;
+        if (i >= Q - 1) { ct += P(i + 1) - P(i - Q + 1); et += W(i + 1) - W(i - Q + 1); }
+        if (i >= 2 * (int64_t)Q - 1) { ct += P(i - Q + 1) - P(i - 2 * (int64_t)Q + 1); et += W(i - Q + 1) - W(i - 2 * (int64_t)Q + 1); }
+        if (i >= 3 * (int64_t)Q - 1) et += W(i - 2 * (int64_t)Q + 1) - W(i - 3 * (int64_t)Q + 1);
+        const int64_t o = frame * n + i;
+        corr_total[o] = ct;
+        corr_positive[o] = ct > 0 ? ct : 0;
+        energy_total[o] = et;
+        valid[o] = i >= 3 * (int64_t)Q - 1;
+    }
+}
+
 // Combine antennas with the hold-register gating (minn_rtl.py:632-650 / minn_antenna_path.sv:168-194):
 //   corr_recent = C[n] (n >= Q-1), corr_previous = C[n-Q] (n >= 2Q-1),
 //   energy_recent = E[n] (n >= Q-1), energy_previous = E[n-Q] (n >= 2Q-1), energy_previous2 = E[n-2Q] (n >= 3Q-1)
@@ -481,6 +551,18 @@ OFS_API int ofs_minn_rtl_int(const int16_t *iq, int64_t n_frames, int32_t n_bran
     OFS_REQUIRE(n_branches >= 1 && n >= 0 && n_frames >= 0 && frac_bits >= 0 && frac_bits < 24, "ofs_minn_rtl_int: bad geometry");
     if (n_frames == 0 || n == 0) return OFS_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t fsmem = (size_t)2 * (RT + 3 * (size_t)quarter_len) * sizeof(long long);
+    if (fsmem <= 200 * 1024 && n_frames < 65536) {          // window sums + antenna combining fused (Q <= 2133)
+        OFS_CUDA(cudaFuncSetAttribute(rtl_int_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+        rtl_int_fused_kernel<<<dim3((unsigned)((n + RT - 1) / RT), (unsigned)n_frames), RNT, fsmem, stream>>>(
+            reinterpret_cast<const short2 *>(iq), n_branches, n, quarter_len, quarter_len + lag_extra, (long long *)corr_total,
+            (long long *)corr_positive, (long long *)energy_total, metric_valid);
+        if (int rc = check_launch("rtl_int_fused_kernel")) return rc;
+        rtl_smooth_kernel<long long><<<(unsigned)((n_frames + SMW - 1) / SMW), SMW * 32, 0, stream>>>(
+            (const long long *)corr_positive, (const long long *)energy_total, metric_valid, n_frames, n, smooth_shift,
+            (long long)threshold_value, frac_bits, (long long *)smooth_metric, nullptr, nullptr, above);
+        return check_launch("rtl_smooth_kernel");
+    }
     keep_pool_cached();
     const int64_t ns = n_frames * n_branches;
     long long *C = nullptr, *E = nullptr;

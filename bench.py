@@ -9,7 +9,7 @@ with the inputs resident in HBM (`value`), and through ofs_sync_host with HOST b
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames F] [--samples S]
 For N > 1 launch with torchrun (one rank per GPU); frames are sharded (weak scaling: F frames PER GPU), no
-collective on the sample path, one all_gather of the detection records per step.
+collective on the sample path, one all_gather of the detection records per step (overlapped with the next step).
 --impl reference times the CPU restatement of the reference's algorithm (oracle/, kind "port": the reference is
 pure Python and cannot travel to the GPU box) on all host cores.
 """
@@ -168,16 +168,19 @@ def main() -> None:
     F, n = args.frames, args.samples
     x = synth.make_batch_device(F, n, "sc", seed=1234 + rank, device=dev)
     plan = engine.SyncPlan(F, n, "sc", N_FFT, "c64", cp_len=CP_LEN, smooth_win=SMOOTH, sc_delta=SC_DELTA, store_mode=args.store_mode, tma_mode=args.tma_mode)
-    gather = odist.RecordGatherer(plan.rec) if world > 1 else None
+    # detection records of step k are all-gathered on a side stream while step k + 1 computes (dist.PipelinedGatherer)
+    gather = odist.PipelinedGatherer(plan.rec) if world > 1 else None
 
     def step():
         plan.run_metric_only(x)
         plan.run_detect_only(x)
         if gather is not None:
-            gather.run()
+            gather.push()
 
     for _ in range(args.warmup):
         step()
+    if gather is not None:
+        gather.drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -196,7 +199,9 @@ def main() -> None:
         ev[k][1].record()
         plan.run_detect_only(x)
         if gather is not None:
-            gather.run()
+            gather.push()
+            if k == args.steps - 1:
+                gather.drain()                  # every gather finishes inside the timed region
         ev[k][2].record()
     torch.cuda.synchronize()
     t_wall1 = time.time()

@@ -118,3 +118,14 @@ def compare_block_lengths(block_lengths, channel_name=None, snr_db=None):
             res[s][N] = dict(peak=float(peak[i]), par=float(par[i]), pmr=float(pmr[i]), timing_error=int(pk_h[i]) - expected,
                              metric=M[i], P_sum=P[i], R_sum=R[i], **base)
     return res if many else res[snrs[0]]
+
+
+def run_block_length_comparison(channel_name=None) -> None:
+    """minn.run_block_length_comparison (minn.py:874-896): the sweep over N = 256 ... 2048 as a printed table."""
+    lengths = [256, 512, 1024, 2048]
+    res = compare_block_lengths(lengths, channel_name)
+    print(f"BLOCK LENGTH COMPARISON (Classical Minn) - {'Measured CIR ' + repr(channel_name) if channel_name else 'Flat AWGN'}")
+    print(f"{'N':>6} | {'CP+N':>6} | {'Overhead':>8} | {'Peak':>10} | {'PAR':>8} | {'PMR':>8} | {'Timing':>8}")
+    for N in lengths:
+        r = res[N]
+        print(f"{N:>6} | {r['preamble_len']:>6} | {r['overhead_pct']:>7.1f}% | {r['peak']:>10.4f} | {r['par']:>8.1f} | {r['pmr']:>8.2f} | {r['timing_error']:>+8}")

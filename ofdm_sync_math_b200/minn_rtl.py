@@ -195,3 +195,14 @@ def compare_q_values(q_values, channel_name=None, snr_db=None):
             res[s][Q] = dict(peak=float(peak[i]), par=float(par[i]), pmr=float(pmr[i]), timing_error=int(terr[i]),
                              preamble_len=5 * Q, overhead_pct=100.0 * 5 * Q / frame_len)
     return res if many else res[snrs[0]]
+
+
+def run_q_comparison(channel_name=None) -> None:
+    """minn_rtl.run_q_comparison (minn_rtl.py:1595-1617): the sweep over Q = 64 ... 512 as a printed table."""
+    qs = [64, 128, 256, 512]
+    res = compare_q_values(qs, channel_name)
+    print(f"Q VALUE COMPARISON - {'Measured CIR ' + repr(channel_name) if channel_name else 'Flat AWGN'}")
+    print(f"{'Q':>6} | {'5Q':>6} | {'Overhead':>8} | {'Peak':>12} | {'PAR':>8} | {'PMR':>8} | {'Timing':>8}")
+    for q in qs:
+        r = res[q]
+        print(f"{q:>6} | {r['preamble_len']:>6} | {r['overhead_pct']:>7.1f}% | {r['peak']:>12.1f} | {r['par']:>8.1f} | {r['pmr']:>8.2f} | {r['timing_error']:>+8}")

@@ -246,3 +246,47 @@ def run_grid_test(snr_values=(-5, 0, 5, 10, 15), channels=(None, "cir1", "cir2")
                   f"{'hit ' if r.detected else 'miss'} timing_err={r.timing_error:+4d} cfo_err={r.cfo_error_hz:+7.1f}Hz "
                   f"clip={r.clipping_pct:5.1f}%")
     return out
+
+
+def print_summary_table(results) -> None:
+    """sync_aa.print_summary_table (sync_aa.py:900-960): timing error (or MISS) per SNR x full-scale ratio for every preamble
+    length and channel, then the detection rate per (preamble length, channel)."""
+    lengths = sorted({r.preamble_length for r in results}, reverse=True)
+    chans = sorted({r.channel for r in results})
+    snrs = sorted({r.snr_db for r in results})
+    ratios = sorted({r.full_scale_ratio for r in results})
+    key = {(r.preamble_length, r.channel, r.snr_db, r.full_scale_ratio): r for r in results}
+    for plen in lengths:
+        print(f"\nPREAMBLE LENGTH: {plen} samples (L={plen // 2})")
+        for ch in chans:
+            print(f"\n--- {ch.upper()} ---")
+            print(f"{'SNR':>6s}" + "".join(f" | FS={fs:.2f}" for fs in ratios))
+            for snr in snrs:
+                cells = []
+                for fs in ratios:
+                    r = key.get((plen, ch, snr, fs))
+                    cells.append("   N/A" if r is None else (f"{r.timing_error:+6d}" if r.detected else "  MISS"))
+                print(f"{snr:+5.0f}dB" + "".join(f" | {c}" for c in cells))
+    print("\nDETECTION RATE BY PREAMBLE LENGTH AND CHANNEL")
+    for plen in lengths:
+        print(f"\nPreamble L={plen // 2}:")
+        for ch in chans:
+            sel = [r for r in results if r.channel == ch and r.preamble_length == plen]
+            hit = sum(r.detected for r in sel)
+            print(f"  {ch:6s}: {hit}/{len(sel)} ({100 * hit / len(sel) if sel else 0:.0f}%)")
+
+
+def main() -> None:
+    """sync_aa.main (sync_aa.py:1073-1119) without the figures: preamble characteristics, the 135-case grid, the summary."""
+    for plen in PREAMBLE_LENGTHS:
+        pre, _, papr = build_aa_preamble(plen)
+        a, b = pre[: plen // 2], pre[plen // 2:]
+        corr = np.abs(np.vdot(a, b)) / (np.linalg.norm(a) * np.linalg.norm(b))
+        print(f"  Length {plen:4d}: L={plen // 2:3d}, PAPR={papr:.2f}dB, duration={plen / SAMPLE_RATE_HZ * 1e6:.1f}us, [A][A] corr={corr:.6f}")
+    results = run_grid_test(snr_values=[-5, 0, 5, 10, 15], channels=[None, "cir1", "cir2"], full_scale_ratios=[0.5, 1.0, 2.0],
+                            preamble_lengths=PREAMBLE_LENGTHS, cfo_hz=500.0, plot_samples=False, verbose=True)
+    print_summary_table(results)
+
+
+if __name__ == "__main__":
+    main()

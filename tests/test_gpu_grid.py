@@ -153,3 +153,18 @@ def test_compare_q_values_vs_reference_run(golden, ch):
     many = minn_rtl.compare_q_values(Qs, ch, snr_db=[0.0, 20.0])
     _check_sweep(many[0.0], g, f"q_{tag}", Qs)
     assert all(many[20.0][q]["peak"] > 0 for q in Qs)
+
+
+def test_sweep_tables_print(capsys):
+    """The printing front ends of the sweep layer (sync_aa.print_summary_table, minn.run_block_length_comparison,
+    minn_rtl.run_q_comparison) run on the device results and show the reference's known answers."""
+    from ofdm_sync_math_b200 import minn, minn_rtl, sync_aa
+    res = sync_aa.run_grid_test(snr_values=[10], channels=[None, "cir1"], full_scale_ratios=[1.0, 2.0], preamble_lengths=[1024],
+                                plot_samples=False)
+    sync_aa.print_summary_table(res)
+    minn.run_block_length_comparison(None)
+    minn_rtl.run_q_comparison(None)
+    out = capsys.readouterr().out
+    assert "PREAMBLE LENGTH: 1024 samples (L=512)" in out and "AWGN" in out and "CIR1" in out and "(100%)" in out
+    assert "BLOCK LENGTH COMPARISON" in out and "Q VALUE COMPARISON" in out
+    assert out.count("      +0") >= 4                   # flat AWGN: every block length lands on the expected index (fixture: 0, 0, 0, 0)

@@ -319,7 +319,9 @@ int ofs_sync_detect(const ofs_metric_desc *d, const void *x, const float *M, con
                     ofs_sync_record *records, int64_t *scratch, void *stream);
 /* Host version: x_host (n_frames x n_samples, dtype per d->in_dtype), M_host optional (float32
  * [n_frames][out_stride]); records_host[n_frames].  Frames are pipelined through the ctx workspace
- * in batches (H2D, kernels, D2H overlapped on three streams). */
+ * in batches (H2D, kernels, D2H overlapped on three streams, two buffer sets).  A batch holds 32 MB of
+ * samples (environment variable OFS_HOST_BATCH_MB overrides, 1..4096); pinned host memory (ofs_host_alloc)
+ * is what lets the copies run asynchronously.  M_host == NULL: only the records come back. */
 int ofs_sync_host(ofs_ctx *ctx, const ofs_metric_desc *d, const void *x_host, float *M_host,
                   int32_t cp_len, int32_t smooth_win, int32_t sc_delta, double gate_threshold,
                   ofs_sync_record *records_host);

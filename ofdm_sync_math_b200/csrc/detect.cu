@@ -17,6 +17,7 @@
 namespace ofs {
 
 constexpr int DNT = 256;                   // threads per row-CTA
+constexpr int MNT = 768;                   // minn_peak_kernel on long float rows: the 128 KB gate mask allows one CTA per SM, so the CTA is wider
 constexpr int64_t MASK_MAX_N = 1600000;     // row length limit of the bitmask kernels (200 KB of smem)
 
 int launch_metric_array(const void *x, int in_dtype, int64_t n_frames, int n_ant, int64_t n, int64_t xfs, int64_t xbs, int L,
@@ -64,7 +65,7 @@ __device__ ArgVal block_argmax(ArgVal x, ArgVal *sh /* DNT/32 */)
     if (lane == 0) sh[warp] = x;
     __syncthreads();
     ArgVal r = sh[0];
-    for (int w = 1; w < DNT / 32; ++w) r = better<LAST>(r, sh[w]);
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = better<LAST>(r, sh[w]);
     return r;
 }
 __device__ long long block_min_i64(long long x, long long *sh)
@@ -79,7 +80,7 @@ __device__ long long block_min_i64(long long x, long long *sh)
     if (lane == 0) sh[warp] = x;
     __syncthreads();
     long long r = sh[0];
-    for (int w = 1; w < DNT / 32; ++w) r = sh[w] < r ? sh[w] : r;
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = sh[w] < r ? sh[w] : r;
     return r;
 }
 
@@ -98,7 +99,7 @@ struct Prune {
     {
         if (cm == nullptr) return;
         if (nch < ncm) ncm = nch;
-        for (int64_t c = threadIdx.x; c < ncm; c += DNT) smem_cm[c] = __ldg(cm + c);
+        for (int64_t c = threadIdx.x; c < ncm; c += blockDim.x) smem_cm[c] = __ldg(cm + c);
         cm = smem_cm;
         __syncthreads();
     }
@@ -128,7 +129,7 @@ __device__ ArgVal pruned_argmax(const F &fn, int64_t n_out, const Prune &pr, Arg
     if (pr.cm != nullptr) {
         // phase 0: the chunk with the largest raw maximum
         ArgVal bc{0.0, -1};
-        for (int64_t c = tid; c < nch && c < pr.ncm; c += DNT) {
+        for (int64_t c = tid; c < nch && c < pr.ncm; c += blockDim.x) {
             const double v = (double)pr.cm[c];
             if (bc.i < 0 || v > bc.v) { bc.v = v; bc.i = c; }
         }
@@ -148,7 +149,7 @@ __device__ ArgVal pruned_argmax(const F &fn, int64_t n_out, const Prune &pr, Arg
     // The bound test is done 32 chunks at a time (one per lane); survivors are evaluated by the whole warp.
     ArgVal best{0.0, -1};
     const int nchi = (int)nch;
-    for (int c0 = warp * 32; c0 < nchi; c0 += (DNT / 32) * 32) {
+    for (int c0 = warp * 32; c0 < nchi; c0 += (int)blockDim.x) {
         const int cl = c0 + lane;
         const bool pass = cl < nchi && (!have || (double)pr.bound(cl) >= vs.v);
         unsigned m = __ballot_sync(0xffffffffu, pass);
@@ -184,7 +185,7 @@ __device__ ArgVal range_argmax(const F &fn, int64_t lo, int64_t hi, int toff, Ar
     ArgVal best{0.0, -1};
     double v8[8];
     const int64_t g0 = lo - (((lo + toff) % 8) + 8) % 8;
-    for (int64_t i0 = g0 + 8LL * threadIdx.x; i0 < hi; i0 += 8LL * DNT) {
+    for (int64_t i0 = g0 + 8LL * threadIdx.x; i0 < hi; i0 += 8LL * blockDim.x) {
         fn.eval8(i0, v8);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -618,10 +619,10 @@ __device__ __forceinline__ RunSum run_join(const RunSum &A, const RunSum &B)
 // shuffles still spent 150 k warp-instructions per 1 M-sample row, 29 % of the kernel; this form needs about a tenth.)
 __device__ void longest_run_block(const unsigned *mask, int64_t n, long long &bs, long long &be)
 {
-    __shared__ long long s_pre[DNT], s_suf[DNT], s_bl[DNT], s_bs[DNT], s_be[DNT], s_res[2];
+    __shared__ long long s_pre[MNT], s_suf[MNT], s_bl[MNT], s_bs[MNT], s_be[MNT], s_res[2];   // blockDim.x <= MNT slices
     const int tid = threadIdx.x;
     const int64_t nw = (n + 31) / 32;
-    int64_t wpt = (nw + DNT - 1) / DNT;
+    int64_t wpt = (nw + blockDim.x - 1) / blockDim.x;
     wpt |= 1;
     const int64_t w_lo = (int64_t)tid * wpt < nw ? (int64_t)tid * wpt : nw;
     const int64_t w_hi = w_lo + wpt < nw ? w_lo + wpt : nw;
@@ -663,7 +664,7 @@ __device__ void longest_run_block(const unsigned *mask, int64_t n, long long &bs
             r.pre = s_pre[t]; r.suf = s_suf[t]; r.bl = s_bl[t]; r.bs = s_bs[t]; r.be = s_be[t];
             return r;
         };
-        constexpr int PER = DNT / 32;
+        const int PER = (int)(blockDim.x >> 5);
         RunSum R = slice(tid * PER);
 #pragma unroll 1
         for (int k = 1; k < PER; ++k) R = run_join(R, slice(tid * PER + k));
@@ -689,13 +690,13 @@ __device__ void longest_run_block(const unsigned *mask, int64_t n, long long &bs
 }
 
 template <bool F64>
-__global__ void __launch_bounds__(DNT, F64 ? 2 : 3) minn_peak_kernel(RowView r, int smooth_win, double gate_threshold,
+__global__ void __launch_bounds__(F64 ? DNT : MNT, F64 ? 2 : 1) minn_peak_kernel(RowView r, int smooth_win, double gate_threshold,
                                                         int has_bounds, int64_t b_lo, int64_t b_hi, int64_t *peak,
                                                         int64_t *gate_span, void *Ms_out, const float *cm,
                                                         int64_t cm_stride, int toff)
 {
     extern __shared__ unsigned mask[];
-    __shared__ ArgVal sh_av[DNT / 32];
+    __shared__ ArgVal sh_av[MNT / 32];
     __shared__ long long sh_span[2];
     const int64_t row = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -713,7 +714,7 @@ __global__ void __launch_bounds__(DNT, F64 ? 2 : 3) minn_peak_kernel(RowView r, 
     if (Ms_out) {
         double v8[8];
         const int64_t g0 = -(int64_t)(((toff % 8) + 8) % 8);
-        for (int64_t i0 = g0 + 8LL * tid; i0 < n; i0 += 8LL * DNT) {
+        for (int64_t i0 = g0 + 8LL * tid; i0 < n; i0 += 8LL * blockDim.x) {
             Ms.eval8(i0, v8);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -734,7 +735,7 @@ __global__ void __launch_bounds__(DNT, F64 ? 2 : 3) minn_peak_kernel(RowView r, 
     const int64_t nch = (n + toff + 255) / 256;
     {
         const int nchi = (int)nch, warp = tid >> 5;
-        for (int c0 = warp * 32; c0 < nchi; c0 += (DNT / 32) * 32) {
+        for (int c0 = warp * 32; c0 < nchi; c0 += (int)blockDim.x) {
             const int cl = c0 + lane;
             const bool inr = cl < nchi;
             const bool pass = inr && (!pr.cm || (double)pr.bound(cl) >= level);
@@ -1285,11 +1286,13 @@ OFS_API int ofs_find_minn_peak_pruned(const ofs_rows *M, const float *chunk_max,
     if (M->n_rows == 0) return OFS_OK;
     const int64_t nch_h = (M->n + toff + 255) / 256;
     const size_t sm = mask_bytes(nch_h * 256) + (chunk_max ? (size_t)(nch_h + 8) * sizeof(float) : 0);
-    OFS_REQUIRE(sm <= 216 * 1024, "ofs_find_minn_peak: rows too long");   // + 10.4 KB static (longest_run_block) <= 227 KB
+    OFS_REQUIRE(sm <= 195 * 1024, "ofs_find_minn_peak: rows too long");   // + 31 KB static (longest_run_block) <= 227 KB
+    // float rows whose mask leaves room for one CTA per SM only: 24 warps instead of 8 hide the latency of the window fetches
+    const int nt = (!M->f64 && sm > 72 * 1024) ? MNT : DNT;
     auto go = [&](auto kern) -> int {
         if (int rc = set_mask_smem(kern, sm)) return rc;
-        kern<<<(unsigned)M->n_rows, DNT, sm, (cudaStream_t)stream>>>(view(M), smooth_win, gate_threshold, has_bounds, bound_lo, bound_hi,
-                                                                    peak, gate_span, Ms, chunk_max, cm_stride, toff);
+        kern<<<(unsigned)M->n_rows, nt, sm, (cudaStream_t)stream>>>(view(M), smooth_win, gate_threshold, has_bounds, bound_lo, bound_hi,
+                                                                   peak, gate_span, Ms, chunk_max, cm_stride, toff);
         return check_launch("minn_peak_kernel");
     };
     return M->f64 ? go(minn_peak_kernel<true>) : go(minn_peak_kernel<false>);

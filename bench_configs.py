@@ -107,6 +107,15 @@ def main():
         ms = timeit(run, steps=3, warmup=2)
         emit("cfg3 combined: Minn + S&C(both halves) metrics + gate + gated peak", ms, F * n, alg_bytes=2 * F * (8 * n + 4 * (n - 2047)),
              note="two metric passes over the same samples (16 B read + 8 B written per sample algorithmic) + byte gate mask")
+
+        def run_fused():
+            m = engine.metric(x, "minn", 2048, want_pr=False, path="stripe", want_chunk_max=True)
+            s = engine.metric(x, "sc_both", 2048, want_pr=False, path="stripe", want_chunk_max=True)
+            return engine.combined_peak(m.M, s.M, s.chunk_max, 2047, 0.6, 16)
+        ms = timeit(run_fused, steps=3, warmup=2)
+        same = bool(torch.equal(run()[: F], run_fused()[0]))
+        emit("cfg3 combined, fused detector (no gate array): Minn + S&C(both halves) metrics + ofs_combined_peak", ms, F * n,
+             alg_bytes=2 * F * (8 * n + 4 * (n - 2047)), note=f"peaks equal to the gate + gated-peak path: {same}")
         del x
     if "park" in cases:
         F, n = max(int(64 * a.scale), 2), 1 << 18

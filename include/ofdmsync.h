@@ -133,6 +133,14 @@ int ofs_sc_gate_pruned(const ofs_rows *Msc, const float *chunk_max, int64_t cm_s
  * peak: -1 empty M (reference returns 0), -3 empty gate region (ValueError). */
 int ofs_find_minn_peak_gated(const ofs_rows *M, int32_t smooth_win, const uint8_t *gate, int64_t gate_stride,
                              int32_t has_bounds, int64_t bound_lo, int64_t bound_hi, int64_t *peak, void *stream);
+/* combined_sc_min detector in one launch, without a gate array: the S&C gate test M_sc[d] / max(M_sc) >= threshold
+ * (combined_sc_min.py:337-351) is evaluated only around the first gate segment, located through the S&C chunk maxima of the
+ * stripe kernel; peak = first maximum of the trailing-averaged Minn metric inside that segment (:183-259).  Same result as
+ * ofs_sc_gate_pruned + ofs_find_minn_peak_gated.  float32 rows of equal shape, 0 < threshold <= 1.
+ * peak: int64[n_rows] (-1 empty metric, -3 empty gate); gate_span (optional): int64[n_rows][2] = [first, stop). */
+int ofs_combined_peak(const ofs_rows *M_minn, const ofs_rows *M_sc, const float *chunk_max_sc, int64_t cm_stride, int32_t toff,
+                      double threshold, int32_t smooth_win, int32_t has_bounds, int64_t bound_lo, int64_t bound_hi,
+                      int64_t *peak, int64_t *gate_span, void *stream);
 
 /* argmax with numpy semantics (first maximum): park.py:161, zc.py:128, zc_freq.py:147 */
 int ofs_argmax(const ofs_rows *M, int64_t *index, void *stream);

@@ -900,6 +900,84 @@ __global__ void __launch_bounds__(DNT, F64 ? 2 : 3) gated_peak_kernel(RowView r,
     if (tid == 0) peak[row] = pk.i;
 }
 
+// combined_sc_min in one kernel, no gate array: S&C gate (combined_sc_min.py:337-351) -> first gate segment -> first maximum
+// of the trailing-averaged Minn metric inside it (:183-259).  The gate of sample d is the float64 test
+// M_sc[d] / max(M_sc) >= thr -- the same expression sc_gate_kernel writes into a byte per sample; here it is evaluated only
+// where it matters: the row maximum and the first chunk that can reach the level come from the S&C chunk maxima, the segment
+// [first, stop) is walked 2048 samples per step.  Same peak as ofs_sc_gate_pruned + ofs_find_minn_peak_gated, which move a byte
+// per sample through HBM twice (0.94 ms of the 3.26 ms combined step on 512 x 1 M-sample rows).
+__global__ void __launch_bounds__(DNT, 3) combined_peak_kernel(RowView rm, RowView rs, double thr, const float *cm, int64_t cm_stride,
+                                                               int toff, int smooth_win, int has_bounds, int64_t b_lo, int64_t b_hi,
+                                                               int64_t *peak, int64_t *gate_span)
+{
+    __shared__ ArgVal sh_av[DNT / 32];
+    __shared__ long long sh_i[DNT / 32];
+    const int64_t row = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int64_t n = rs.n;
+    auto done = [&](long long pk, long long a, long long b) {
+        if (tid == 0) { peak[row] = pk; if (gate_span) { gate_span[2 * row] = a; gate_span[2 * row + 1] = b; } }
+    };
+    if (n == 0) { done(-1, 0, 0); return; }
+    int64_t s = 0, e = n;
+    if (has_bounds) {
+        s = b_lo > 0 ? b_lo : 0; e = b_hi < n ? b_hi : n;
+        if (s >= e) { s = 0; e = n; }
+    }
+    const int64_t nch = (n + toff + 255) / 256;
+    const float *cmr = cm + row * cm_stride;
+    ArgVal best{0.0, -1};
+    for (int64_t c = tid; c < nch; c += DNT) {
+        const double v = (double)cmr[c];
+        if (best.i < 0 || v > best.v) { best.v = v; best.i = c; }
+    }
+    best = block_argmax<false>(best, sh_av);
+    const double mx = best.v;
+    long long first = LLONG_MAX;
+    if (!(mx > 0.0)) {
+        // all-zero row: nothing passes, the reference seeds the gate at argmax = index 0
+        if (s == 0) first = 0;
+        if (first == LLONG_MAX) { done(-3, 0, 0); return; }
+        const Trailing Ms0 = make_trailing<false>(rm, row, smooth_win > 1 ? smooth_win : 1, 0);
+        const ArgVal pk0 = range_argmax(Ms0, 0, 1 < e ? 1 : e, 0, sh_av);
+        done(pk0.i, 0, 1);
+        return;
+    }
+    const float *ps = reinterpret_cast<const float *>(rs.data) + row * rs.stride;
+    auto pass = [&](int64_t d) { return (double)ps[d] / mx >= thr; };
+    const double level_lo = thr * mx * (1.0 - 1e-9);
+    // first sample of [s, e) that passes: chunks that can reach the level, in order (normally the first one holds it)
+    int64_t c_from = (s + toff) / 256;
+    while (first == LLONG_MAX) {
+        long long cl = LLONG_MAX;
+        for (int64_t c = c_from + tid; c < nch; c += DNT)
+            if ((double)cmr[c] >= level_lo) { cl = c; break; }
+        cl = block_min_i64(cl, sh_i);
+        if (cl == LLONG_MAX) break;
+        const int64_t d = cl * 256 - toff + tid;                       // one sample per thread
+        long long cand = (d >= s && d < e && pass(d)) ? d : LLONG_MAX;
+        first = block_min_i64(cand, sh_i);
+        c_from = cl + 1;
+        if (cl * 256 - toff >= e) break;
+    }
+    if (first == LLONG_MAX) { done(-3, 0, 0); return; }
+    // the gate drops -> the streaming detector returns: first failing sample after `first`
+    long long stop = LLONG_MAX;
+    for (int64_t base = first + 1; base < e && stop == LLONG_MAX; base += 8LL * DNT) {
+        long long cand = LLONG_MAX;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int64_t d = base + k * DNT + tid;
+            if (cand == LLONG_MAX && d < e && !pass(d)) cand = d;
+        }
+        stop = block_min_i64(cand, sh_i);
+    }
+    if (stop == LLONG_MAX) stop = e;
+    const Trailing Ms = make_trailing<false>(rm, row, smooth_win > 1 ? smooth_win : 1, 0);
+    const ArgVal pk = range_argmax(Ms, first, stop, 0, sh_av);
+    done(pk.i, first, stop);
+}
+
 __global__ void __launch_bounds__(DNT) argmax_kernel(RowView r, int64_t *out)
 {
     __shared__ ArgVal sh_av[DNT / 32];
@@ -1347,6 +1425,24 @@ OFS_API int ofs_find_minn_peak_gated(const ofs_rows *M, int32_t smooth_win, cons
         gated_peak_kernel<false><<<(unsigned)M->n_rows, DNT, 0, (cudaStream_t)stream>>>(view(M), smooth_win, gate, gate_stride, has_bounds,
                                                                                        bound_lo, bound_hi, peak);
     return check_launch("gated_peak_kernel");
+}
+
+OFS_API int ofs_combined_peak(const ofs_rows *M_minn, const ofs_rows *M_sc, const float *chunk_max_sc, int64_t cm_stride, int32_t toff,
+                              double threshold, int32_t smooth_win, int32_t has_bounds, int64_t bound_lo, int64_t bound_hi,
+                              int64_t *peak, int64_t *gate_span, void *stream)
+{
+    if (int rc = rows_ok(M_minn, "ofs_combined_peak")) return rc;
+    if (int rc = rows_ok(M_sc, "ofs_combined_peak")) return rc;
+    OFS_REQUIRE(peak && chunk_max_sc, "ofs_combined_peak: null argument");
+    OFS_REQUIRE(!M_minn->f64 && !M_sc->f64, "ofs_combined_peak: float32 rows (the stripe kernel's output) only");
+    OFS_REQUIRE(M_minn->n == M_sc->n && M_minn->n_rows == M_sc->n_rows, "ofs_combined_peak: the two metrics must have the same shape");
+    OFS_REQUIRE(threshold > 0.0 && threshold <= 1.0, "ofs_combined_peak: threshold must be in (0, 1]");
+    OFS_REQUIRE(toff >= 0 && cm_stride >= (M_sc->n + toff + 255) / 256, "ofs_combined_peak: bad chunk_max geometry");
+    if (M_sc->n_rows == 0) return OFS_OK;
+    combined_peak_kernel<<<(unsigned)M_sc->n_rows, DNT, 0, (cudaStream_t)stream>>>(view(M_minn), view(M_sc), threshold, chunk_max_sc, cm_stride,
+                                                                                 toff, smooth_win, has_bounds, bound_lo, bound_hi, peak,
+                                                                                 gate_span);
+    return check_launch("combined_peak_kernel");
 }
 
 OFS_API int ofs_argmax(const ofs_rows *M, int64_t *index, void *stream)

@@ -208,6 +208,22 @@ def find_minn_peak_gated(M: torch.Tensor, smooth_win: int, gate: torch.Tensor, s
     return peak
 
 
+def combined_peak(M_minn: torch.Tensor, M_sc: torch.Tensor, chunk_max_sc: torch.Tensor, toff: int, threshold: float = 0.6,
+                  smooth_win: int = 16, search_bounds=None):
+    """S&C-gated Minn peak (combined_sc_min.py:183-259, 337-351) in one launch, no gate array (ofs_combined_peak).
+    float32 metrics of equal shape from the stripe kernel + the S&C chunk maxima -> (peak int64[rows], gate_span int64[rows, 2])."""
+    rm, M_minn = _rows(M_minn)
+    rs, M_sc = _rows(M_sc)
+    peak = torch.zeros(M_sc.shape[0], dtype=torch.int64, device=M_sc.device)
+    span = torch.zeros((M_sc.shape[0], 2), dtype=torch.int64, device=M_sc.device)
+    hb = search_bounds is not None
+    lo, hi = (int(search_bounds[0]), int(search_bounds[1])) if hb else (0, 0)
+    L.check(L.lib().ofs_combined_peak(C.byref(rm), C.byref(rs), _ptr(chunk_max_sc), C.c_int64(chunk_max_sc.stride(0)), int(toff),
+                                      C.c_double(threshold), int(smooth_win), int(hb), C.c_int64(lo), C.c_int64(hi), _ptr(peak),
+                                      _ptr(span), _stream()), "ofs_combined_peak")
+    return peak, span
+
+
 def argmax(M: torch.Tensor) -> torch.Tensor:
     rows, M = _rows(M)
     out = torch.zeros(M.shape[0], dtype=torch.int64, device=M.device)

@@ -148,6 +148,18 @@ def test_batched_detectors_vs_oracle():
         Mz = rs.M.cpu().numpy().astype(np.float64)
         for f in range(xz.shape[0]):
             assert np.array_equal(g1[f].astype(bool), orc.sc_gate(Mz[f], thr))
+        # fused detector (no gate array): same peak as gate + gated peak and as the oracle, same first gate segment
+        rm = engine.metric(_dev(xz), "minn", 2048, want_pr=False, path="stripe")
+        Mmz = rm.M.cpu().numpy().astype(np.float64)
+        for bounds in (None, (5000, 20000), (27000, 27940), (0, 1), (40000, 3)):
+            pk2 = engine.find_minn_peak_gated(rm.M, 16, torch.as_tensor(g1, device=rm.M.device), bounds).cpu().numpy()
+            pkf, spanf = engine.combined_peak(rm.M, rs.M, rs.chunk_max, 2047, thr, 16, bounds)
+            assert pkf.cpu().numpy().tolist() == pk2.tolist(), (thr, bounds)
+            for f in range(xz.shape[0]):
+                if pk2[f] >= 0:
+                    assert pk2[f] == orc.find_minn_peak_gated(Mmz[f], 16, g1[f].astype(bool), bounds), (thr, bounds, f)
+                    a, b = spanf[f].cpu().numpy().tolist()
+                    assert g1[f][a:b].all() and (b == len(g1[f]) or not g1[f][b] or (bounds and b == min(bounds[1], len(g1[f])))), (thr, bounds, f)
 
 
 def test_pruned_detectors_equal_unpruned():

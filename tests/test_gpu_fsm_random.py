@@ -99,7 +99,7 @@ def test_minn_peak_longest_run_random(style):
     """find_minn_peak's gate = longest run of (smoothed metric >= threshold * peak), earliest on ties (minn.py:155-182)."""
     from ofdm_sync_math_b200 import engine
     rng = np.random.default_rng(3 + len(style))
-    for n in (40, 257, 1000, 8193, 70001):
+    for n in (40, 257, 1000, 8193, 70001, 700001):                   # > 576 k samples: the 768-thread form of minn_peak_kernel
         # a two-level metric: the gate mask of the smoothed metric follows `m`, with equal-length runs to exercise the tie rule
         m = _mask(rng, n, style)
         M = np.where(m, 1.0, 0.05) + 1e-3 * rng.random(n)

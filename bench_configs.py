@@ -140,6 +140,15 @@ def main():
         emit("cfg4 zc matched filter (smem FFT overlap-save, fp32)", ms_mf, F * n, alg_bytes=F * (8 * n + 12 * (n + 2047)),
              note="8 B in + 8 B corr + 4 B |corr| out per sample")
         emit("cfg4 zc_v2 pipeline: matched filter + running-sum threshold + gate FSM", ms, F * n)
+
+        def run_fused():
+            corr, mag = engine.zc_matched_filter(x, ref, mode=1, out_f64=False)
+            return engine.zc_detect(mag, 2048, 64, 15, 0.3, 2048, 256)
+        ms = timeit(run_fused, steps=3, warmup=2)
+        a3, a2 = run()[0], run_fused()
+        same = all(u.tolist() == v.tolist() for u, v in zip(a3, a2))
+        emit("cfg4 zc_v2 pipeline, threshold kernel and gate FSM exchanging a bitmask (ofs_zc_detect)", ms, F * n,
+             note=f"events equal to the three-call path: {same}")
         del x
     if "zcfreq" in cases:
         F, n = max(int(256 * a.scale), 4), 65536

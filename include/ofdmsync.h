@@ -191,6 +191,13 @@ int ofs_zc_streaming_detection(const ofs_rows *corr_mag, int32_t window, int32_t
 int ofs_zc_events(const ofs_rows *corr_mag, const uint8_t *valid, const uint8_t *above, int64_t mask_stride,
                   int32_t reference_length, int32_t hysteresis, ofs_event *events, int32_t *n_events,
                   uint8_t *gate_mask, void *stream);
+/* ofs_zc_streaming_detection + ofs_zc_events in two launches that exchange one BIT per sample: the threshold kernel
+ * (zc_v2.py:288-336) writes the above-threshold flags of the valid samples as a bitmask (mask_ws: uint32[n_rows][mask_stride],
+ * mask_stride >= ceil(n / 32)) and the gate FSM (zc_v2.py:360-450) walks that -- the local_sum / valid / above arrays
+ * (6 bytes per sample written, 2 read back) are not produced.  Same events as the two separate calls. */
+int ofs_zc_detect(const ofs_rows *corr_mag, int32_t window, int32_t thresh_value, int32_t frac_bits, double min_corr_mag,
+                  int32_t reference_length, int32_t hysteresis, uint32_t *mask_ws, int64_t mask_stride, ofs_event *events,
+                  int32_t *n_events, void *stream);
 
 /* minn_rtl.detect_minn_rtl -- minn_rtl.py:750-825 (== ref/minn_preamble_detector.sv:337-384).
  * corr_positive rows: float64, or int64 when is_int != 0 (integer RTL mode).  An unclosed tail gate

@@ -998,7 +998,7 @@ __global__ void __launch_bounds__(DNT) argmax_kernel(RowView r, int64_t *out)
 constexpr int ZT = 2048;
 __global__ void __launch_bounds__(DNT) zc_stream_kernel(RowView r, int W, double thresh_value, double scale,
                                                         double min_mag, void *local_sum, uint8_t *valid,
-                                                        uint8_t *above, int64_t mstride)
+                                                        uint8_t *above, int64_t mstride, unsigned *bitmask, int64_t bm_stride)
 {
     extern __shared__ double zs[];              // zs[k] = sum of mag[j0 .. j0+k-1]
     __shared__ double wtot[DNT / 32];
@@ -1026,16 +1026,28 @@ __global__ void __launch_bounds__(DNT) zc_stream_kernel(RowView r, int W, double
     for (int w = 0; w < warp; ++w) off += wtot[w];
     for (int s = s0; s < s1; ++s) zs[s] += off;
     __syncthreads();
-    for (int64_t i = i0 + tid; i < iend; i += DNT) {
-        int64_t lo = i - W + 1;
-        if (lo < 0) lo = 0;
-        const double sum = zs[i + 1 - j0] - zs[lo - j0];
-        const double m = r.at(row, i);
-        const bool v = i >= W;
-        if (r.f64) reinterpret_cast<double *>(local_sum)[row * r.stride + i] = sum;
-        else reinterpret_cast<float *>(local_sum)[row * r.stride + i] = (float)sum;
-        valid[row * mstride + i] = v;
-        above[row * mstride + i] = v && (m * scale >= sum * thresh_value) && (m >= min_mag);
+    // (the tile start is a multiple of 32 and every warp walks whole 32-sample groups, so a ballot is one word of the bitmask)
+    for (int64_t ib = i0; ib < iend; ib += DNT) {
+        const int64_t i = ib + tid;
+        bool ab = false;
+        if (i < iend) {
+            int64_t lo = i - W + 1;
+            if (lo < 0) lo = 0;
+            const double sum = zs[i + 1 - j0] - zs[lo - j0];
+            const double m = r.at(row, i);
+            const bool v = i >= W;
+            ab = v && (m * scale >= sum * thresh_value) && (m >= min_mag);
+            if (local_sum) {
+                if (r.f64) reinterpret_cast<double *>(local_sum)[row * r.stride + i] = sum;
+                else reinterpret_cast<float *>(local_sum)[row * r.stride + i] = (float)sum;
+            }
+            if (valid) valid[row * mstride + i] = v;
+            if (above) above[row * mstride + i] = ab;
+        }
+        if (bitmask) {
+            const unsigned word = __ballot_sync(0xffffffffu, ab);
+            if (lane == 0 && ib + (tid & ~31) < iend) bitmask[row * bm_stride + (ib + tid) / 32] = word;
+        }
     }
 }
 
@@ -1099,7 +1111,7 @@ __global__ void __launch_bounds__(DNT) fsm_gates_kernel(FsmParams p)
 
     // 1. above-threshold flags of the valid samples -> bitmask
     const int64_t nround = ((n + 31) / 32) * 32;
-    if (KIND == FSM_AA && p.premask) {
+    if (p.premask) {
         const unsigned *pm = p.premask + row * p.premask_stride;
         for (int64_t w = tid; w < nround / 32; w += DNT) mask[w] = pm[w];
     } else if (KIND != FSM_AA && flags_vectorisable(p.valid + row * p.mstride, p.above + row * p.mstride)) {
@@ -1470,7 +1482,7 @@ OFS_API int ofs_zc_streaming_detection(const ofs_rows *corr_mag, int32_t window,
     OFS_CUDA(cudaFuncSetAttribute(zc_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsm));
     zc_stream_kernel<<<grid, DNT, zsm, (cudaStream_t)stream>>>(view(corr_mag), W, (double)thresh_value,
                                                             (double)(1LL << frac_bits), min_corr_mag, local_sum, valid, above,
-                                                            mask_stride);
+                                                            mask_stride, nullptr, 0);
     return check_launch("zc_stream_kernel");
 }
 
@@ -1531,6 +1543,29 @@ OFS_API int ofs_zc_events(const ofs_rows *corr_mag, const uint8_t *valid, const 
     FsmParams p{};
     p.val = view(corr_mag); p.valid = valid; p.above = above; p.mstride = mask_stride; p.L = reference_length;
     p.heff = hysteresis > 1 ? hysteresis : 1; p.events = events; p.n_events = n_events; p.gate_mask = gate_mask;
+    return launch_fsm<FSM_ZC>(p, corr_mag->n_rows, (cudaStream_t)stream);
+}
+
+OFS_API int ofs_zc_detect(const ofs_rows *corr_mag, int32_t window, int32_t thresh_value, int32_t frac_bits, double min_corr_mag,
+                          int32_t reference_length, int32_t hysteresis, uint32_t *mask_ws, int64_t mask_stride, ofs_event *events,
+                          int32_t *n_events, void *stream)
+{
+    if (int rc = rows_ok(corr_mag, "ofs_zc_detect")) return rc;
+    OFS_REQUIRE(mask_ws && events && n_events && mask_stride >= (corr_mag->n + 31) / 32, "ofs_zc_detect: bad arguments");
+    OFS_REQUIRE(frac_bits >= 0 && frac_bits < 62, "ofs_zc_detect: bad frac_bits");
+    if (corr_mag->n_rows == 0 || corr_mag->n == 0) return OFS_OK;
+    const int W = window > 1 ? window : 1;
+    OFS_REQUIRE(W <= 16384, "ofs_zc_detect: window > 16384 unsupported");
+    OFS_REQUIRE(corr_mag->n_rows < 65536, "ofs_zc_detect: too many rows");
+    dim3 grid((unsigned)((corr_mag->n + ZT - 1) / ZT), (unsigned)corr_mag->n_rows);
+    const size_t zsm = (size_t)(ZT + W + 2) * sizeof(double);
+    OFS_CUDA(cudaFuncSetAttribute(zc_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsm));
+    zc_stream_kernel<<<grid, DNT, zsm, (cudaStream_t)stream>>>(view(corr_mag), W, (double)thresh_value, (double)(1LL << frac_bits),
+                                                            min_corr_mag, nullptr, nullptr, nullptr, 0, mask_ws, mask_stride);
+    if (int rc = check_launch("zc_stream_kernel")) return rc;
+    FsmParams p{};
+    p.val = view(corr_mag); p.L = reference_length; p.heff = hysteresis > 1 ? hysteresis : 1; p.events = events; p.n_events = n_events;
+    p.premask = mask_ws; p.premask_stride = mask_stride;
     return launch_fsm<FSM_ZC>(p, corr_mag->n_rows, (cudaStream_t)stream);
 }
 

@@ -300,6 +300,21 @@ def zc_events(corr_mag: torch.Tensor, valid: torch.Tensor, above: torch.Tensor, 
     return _events_to_numpy(ev, cnt), gm
 
 
+def zc_detect(corr_mag: torch.Tensor, window: int, thresh_value: int, frac_bits: int, min_corr_mag: float, reference_length: int,
+              hysteresis: int):
+    """zc_v2 streaming threshold + gate FSM (zc_v2.py:288-336, 360-450) exchanging a bitmask (ofs_zc_detect) -> events per row."""
+    rows, m = _rows(corr_mag)
+    m = m.contiguous()
+    rows, m = _rows(m)
+    mstride = (m.shape[1] + 31) // 32
+    mask = torch.empty((m.shape[0], mstride), dtype=torch.int32, device=m.device)
+    ev, cnt = _event_buffers(m.shape[0], m.device)
+    L.check(L.lib().ofs_zc_detect(C.byref(rows), int(window), int(thresh_value), int(frac_bits), C.c_double(min_corr_mag),
+                                  int(reference_length), int(hysteresis), _ptr(mask), C.c_int64(mstride), _ptr(ev), _ptr(cnt),
+                                  _stream()), "ofs_zc_detect")
+    return _events_to_numpy(ev, cnt)
+
+
 def minn_rtl_events(corr_positive: torch.Tensor, valid: torch.Tensor, above: torch.Tensor, hysteresis: int, timing_offset: int):
     """minn_rtl.py:750-825 -> events per row (closed == 0 marks an unclosed tail segment)."""
     cp = corr_positive if corr_positive.dim() == 2 else corr_positive[None]

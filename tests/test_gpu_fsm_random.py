@@ -112,3 +112,26 @@ def test_minn_peak_longest_run_random(style):
                 seg = np.flatnonzero(gate_o)
                 assert int(peak[0]) == pk_o, (style, n, w, thr, dt)
                 assert (s, e) == (int(seg[0]), int(seg[-1]) + 1), (style, n, w, thr, dt)
+
+
+@pytest.mark.parametrize("n", [100, 2049, 4096, 8193, 70000])
+def test_zc_detect_bitmask_path_equals_three_step_path(n):
+    """ofs_zc_detect (threshold kernel -> bitmask -> gate FSM) against ofs_zc_streaming_detection + ofs_zc_events and the oracle."""
+    from ofdm_sync_math_b200 import engine
+    rng = np.random.default_rng(n)
+    rows = 4
+    mag = (rng.random((rows, n)) * 0.2).astype(np.float32)
+    for r in range(rows):                                           # a few correlation peaks well above the running mean
+        for p in rng.integers(0, n, size=max(1, n // 3000)):
+            mag[r, p:p + int(rng.integers(1, 40))] += 3.0
+    m = torch.as_tensor(mag).cuda()
+    for window, hyst in ((64, 16), (2048, 256)):
+        ls, v, ab = engine.zc_streaming_detection(m, window, 64, 15, 0.3)
+        ev3, _ = engine.zc_events(m, v, ab, 62, hyst, want_gate_mask=False)
+        ev2 = engine.zc_detect(m, window, 64, 15, 0.3, 62, hyst)
+        for r in range(rows):
+            assert ev2[r].tolist() == ev3[r].tolist(), (n, window, hyst, r)
+            st = orc.zc_streaming_detection(mag[r].astype(np.float64), window, 64, 15, 0.3)
+            ev_o, vals_o, _ = orc.detect_zc_peaks(st, 62, hyst)
+            got = [(int(e["peak_index"]), int(e["gate_start"]), int(e["gate_end"]), int(e["aux"])) for e in ev2[r]]
+            assert got == [tuple(int(x) for x in row) for row in ev_o.tolist()], (n, window, hyst, r)

@@ -856,16 +856,11 @@ __global__ void __launch_bounds__(DNT) sc_gate_pruned_kernel(RowView r, double t
             g[d] = live ? (uint8_t)(r.at(row, d) / mx >= thr) : (uint8_t)0;
         }
     }
-}
-
-// all-zero rows (every chunk maximum 0): v >= thr is false everywhere, the reference seeds the gate with argmax = index 0
-__global__ void sc_gate_seed_kernel(const float *cm, int64_t cm_stride, int64_t nch, int64_t n_rows, uint8_t *gate, int64_t gstride)
-{
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= n_rows) return;
-    float m = 0.f;
-    for (int64_t c = 0; c < nch; ++c) m = fmaxf(m, cm[row * cm_stride + c]);
-    if (!(m > 0.f)) gate[row * gstride] = 1;
+    // all-zero row (every chunk maximum 0): nothing passes, the reference seeds the gate with argmax = index 0
+    if (!(mx > 0.0)) {
+        __syncthreads();
+        if (tid == 0) g[0] = 1;
+    }
 }
 
 template <bool F64>
@@ -1408,12 +1403,7 @@ OFS_API int ofs_sc_gate_pruned(const ofs_rows *Msc, const float *chunk_max, int6
     if (chunk_max && !Msc->f64 && threshold > 0.0 && threshold <= 1.0) {
         sc_gate_pruned_kernel<<<(unsigned)Msc->n_rows, DNT, 0, (cudaStream_t)stream>>>(view(Msc), threshold, gate, gate_stride, chunk_max,
                                                                                      cm_stride, toff);
-        if (int rc = check_launch("sc_gate_pruned_kernel")) return rc;
-        // rows whose maximum is zero get the reference's seed (argmax of an all-zero row = index 0)
-        sc_gate_seed_kernel<<<(unsigned)((Msc->n_rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(chunk_max, cm_stride,
-                                                                                                 (Msc->n + toff + 255) / 256, Msc->n_rows, gate,
-                                                                                                 gate_stride);
-        return check_launch("sc_gate_seed_kernel");
+        return check_launch("sc_gate_pruned_kernel");      // (rows whose maximum is zero are seeded at index 0 by the same kernel)
     }
     sc_gate_kernel<<<(unsigned)Msc->n_rows, DNT, 0, (cudaStream_t)stream>>>(view(Msc), threshold, gate, gate_stride);
     return check_launch("sc_gate_kernel");

@@ -75,3 +75,35 @@ def test_product_never_imports_oracle():
     for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
         txt = f.read_text()
         assert "import oracle" not in txt and "from oracle" not in txt and "libofs_oracle" not in txt, f
+
+
+def test_patch_reference_tables_and_imported_helpers():
+    """patch_reference swaps the hot functions by name; with sweeps=True also the sweep drivers and the channel / core helpers a
+    script imported into its own namespace (only bindings that really came from channel.py / core.py)."""
+    import importlib
+    import types
+    import ofdm_sync_math_b200 as b200
+    for table in (b200.HOT_FUNCTIONS, b200.SWEEP_FUNCTIONS):
+        for name, fns in table.items():
+            ours = importlib.import_module(f"ofdm_sync_math_b200.{name}")
+            assert [f for f in fns if not hasattr(ours, f)] == [], name
+
+    def stub(mod):
+        f = lambda *a, **k: None
+        f.__module__ = mod
+        return f
+    fake = types.ModuleType("minn")
+    for fn, mod in (("minn_streaming_metric", "minn"), ("find_minn_peak", "minn"), ("compare_block_lengths", "minn"),
+                    ("apply_channel", "channel"), ("apply_cfo", "core"), ("estimate_cfo_from_cp", "core"), ("load_measured_cir", "channel")):
+        setattr(fake, fn, stub(mod))
+    own_cfo = stub("minn")                                   # a script's own function that merely shares a helper's name stays
+    fake.estimate_cfo_from_cp_robust = own_cfo
+    keep = fake.compare_block_lengths
+    assert sorted(b200.patch_reference(fake)) == ["find_minn_peak", "minn_streaming_metric"]
+    assert fake.compare_block_lengths is keep
+    done = b200.patch_reference(fake, sweeps=True)
+    assert {"compare_block_lengths", "apply_channel", "apply_cfo", "estimate_cfo_from_cp"} <= set(done)
+    from ofdm_sync_math_b200 import channel, core, minn
+    assert fake.apply_channel is channel.apply_channel and fake.apply_cfo is core.apply_cfo
+    assert fake.compare_block_lengths is minn.compare_block_lengths
+    assert fake.estimate_cfo_from_cp_robust is own_cfo and "load_measured_cir" not in done

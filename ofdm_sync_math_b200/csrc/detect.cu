@@ -535,62 +535,6 @@ __device__ __forceinline__ Trailing make_trailing(const RowView &r, int64_t row,
     return t;
 }
 
-// Walk the maximal runs of ones of a 32-word group (the words are spread over the lanes of one warp; every lane runs
-// the same code, state is replicated).  on_start(pos) is called at the first bit of a run that begins in this group,
-// on_end(pos) at the first zero after a run (pos = absolute bit index).  `in_run` carries a run across groups.
-template <typename FS, typename FE>
-__device__ __forceinline__ void walk_group(unsigned m, long long base0, bool &in_run, FS on_start, FE on_end)
-{
-    const unsigned nz = __ballot_sync(0xffffffffu, m != 0u);
-    const unsigned nf = __ballot_sync(0xffffffffu, m != 0xffffffffu);
-    if (nz == 0u) { if (in_run) { on_end(base0); in_run = false; } return; }
-    if (nf == 0u) { if (!in_run) { on_start(base0); in_run = true; } return; }
-    unsigned rem = nz;
-    int prevk = -1;
-    while (rem) {
-        const int k = __ffs(rem) - 1;
-        rem &= rem - 1;
-        if (k != prevk + 1 && in_run) { on_end(base0 + 32LL * (prevk + 1)); in_run = false; }   // zero word(s) in between
-        const unsigned mk = __shfl_sync(0xffffffffu, m, k);
-        const long long base = base0 + 32LL * k;
-        int pos = 0;
-        while (pos < 32) {
-            const unsigned rest = mk >> pos;
-            if (rest & 1u) {
-                if (!in_run) { on_start(base + pos); in_run = true; }
-                const unsigned inv = ~rest;                       // zeros shifted in at the top count as "end of word"
-                const int ones = (pos == 0 && inv == 0u) ? 32 : __ffs(inv) - 1;
-                pos += ones;
-                if (pos < 32) { on_end(base + pos); in_run = false; }
-            } else {
-                if (in_run) { on_end(base + pos); in_run = false; }   // a run that reached the end of the previous word stops here
-                pos += rest == 0u ? 32 - pos : __ffs(rest) - 1;
-            }
-        }
-        prevk = k;
-    }
-    if (prevk != 31 && in_run) { on_end(base0 + 32LL * (prevk + 1)); in_run = false; }
-}
-
-// Longest run of ones in a bitmask (earliest on ties, minn.py:159-182), executed by ONE WARP, 32 words per step.
-__device__ void longest_run_warp(const unsigned *mask, int64_t n, long long &bs, long long &be)
-{
-    const int lane = threadIdx.x & 31;
-    long long best_len = 0, start = -1, rbs = 0, rbe = 0;
-    bool in_run = false;
-    const int64_t nw = (n + 31) / 32;
-    for (int64_t w0 = 0; w0 < nw; w0 += 32) {
-        const int64_t wi = w0 + lane;
-        unsigned m = wi < nw ? mask[wi] : 0u;
-        if (wi < nw && (wi + 1) * 32 > n) m &= (n - wi * 32 >= 32) ? 0xffffffffu : ((1u << (n - wi * 32)) - 1u);
-        walk_group(m, w0 * 32, in_run,
-                   [&](long long p) { start = p; },
-                   [&](long long p) { if (p - start > best_len) { best_len = p - start; rbs = start; rbe = p; } });
-    }
-    if (in_run && n - start > best_len) { rbs = start; rbe = n; }
-    bs = rbs; be = rbe;
-}
-
 // Summary of the runs of ones in a bit range [a0, a1): pre = end of the run glued to a0 (a0 if none; a1 if the range is all
 // ones), suf = start of the run glued to a1 (-1 if none), (bl, bs, be) = longest run touching neither end, earliest on ties.
 struct RunSum { long long a0, a1, pre, suf, bl, bs, be; };
@@ -614,8 +558,8 @@ __device__ __forceinline__ RunSum run_join(const RunSum &A, const RunSum &B)
 
 // Longest run of ones (earliest on ties), executed by the WHOLE CTA: every thread scans its own odd-sized slice of mask words
 // (conflict-free, a zero or all-one word costs a handful of instructions) and reports (run glued to the slice start, best run
-// strictly inside, run still open at the slice end); warp 0 joins the DNT summaries (run_join: 8 per lane, then a 5-step tree).  Same answer as
-// longest_run_warp.  (History: one warp walking the row was 2/3 of minn_peak_kernel; eight warps walking 32-word groups with
+// strictly inside, run still open at the slice end); warp 0 joins the summaries (run_join: blockDim/32 per lane, then a 5-step tree).
+// (History: one warp walking the row was 2/3 of minn_peak_kernel; eight warps walking 32-word groups with
 // shuffles still spent 150 k warp-instructions per 1 M-sample row, 29 % of the kernel; this form needs about a tenth.)
 __device__ void longest_run_block(const unsigned *mask, int64_t n, long long &bs, long long &be)
 {

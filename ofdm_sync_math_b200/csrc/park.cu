@@ -107,11 +107,14 @@ __global__ void __launch_bounds__(PNT) park_kernel(const void *x, int nb, int64_
 // sum and is no longer recomputed per lag (it was 1/3 of the FMAs).
 constexpr int QNT2 = 128, QO = 8, QK = 8, QTILE = QNT2 * QO;
 
-template <typename T, int DT>
-__global__ void __launch_bounds__(QNT2) park_kernel_v2(const void *x, int nb, int64_t L, int64_t xfs, int64_t xbs, int h,
+// HC = h as a compile-time constant (0: runtime).  With it the sub-array pitch is a constant and every one of the 30 loads of
+// a lag group is base + immediate; with a runtime pitch each load carried its own IMAD / LEA (13 % of the issue slots).
+template <typename T, int DT, int HC>
+__global__ void __launch_bounds__(QNT2) park_kernel_v2(const void *x, int nb, int64_t L, int64_t xfs, int64_t xbs, int h_rt,
                                                       int64_t n_out, int64_t out_stride, int out_f64, void *M, void *P, void *E,
                                                       int tiles_per_frame)
 {
+    const int h = HC ? HC : h_rt;
     extern __shared__ __align__(16) unsigned char psm[];
     Cx<T> *xs = reinterpret_cast<Cx<T> *>(psm);
     const int64_t frame = blockIdx.x / tiles_per_frame;
@@ -217,14 +220,16 @@ static int launch_park(const ofs_metric_desc *d, const void *x, void *M, void *P
     if (h % 8 == 0 && h >= 8) {
         const int tiles2 = (int)((n_out + QTILE - 1) / QTILE);
         const size_t smem2 = (size_t)(QTILE + 2 * h + 16) * sizeof(Cx<T>);
-        auto kern2 = park_kernel_v2<T, DT>;
         OFS_REQUIRE(smem2 <= 200 * 1024, "ofs_park_metric: symbol_len too large");
-        OFS_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         const int64_t grid2 = (int64_t)tiles2 * d->n_frames;
         OFS_REQUIRE(grid2 < (1LL << 31), "ofs_park_metric: grid too large");
-        kern2<<<(unsigned)grid2, QNT2, smem2, st>>>(x, d->n_branches, d->n_samples, d->x_frame_stride, d->x_branch_stride, h, n_out,
-                                                  d->out_stride, d->out_f64, M, P, E, tiles2);
-        return check_launch("park_kernel_v2");
+        auto go = [&](auto kern2) -> int {
+            OFS_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            kern2<<<(unsigned)grid2, QNT2, smem2, st>>>(x, d->n_branches, d->n_samples, d->x_frame_stride, d->x_branch_stride, h, n_out,
+                                                      d->out_stride, d->out_f64, M, P, E, tiles2);
+            return check_launch("park_kernel_v2");
+        };
+        return h == 1024 ? go(park_kernel_v2<T, DT, 1024>) : go(park_kernel_v2<T, DT, 0>);   // N_FFT = 2048 is the scripts' geometry
     }
     const int tiles = (int)((n_out + PTILE - 1) / PTILE);
     const size_t smem = (size_t)(PTILE + 2 * h + 2 * PK) * sizeof(Cx<T>);

@@ -40,7 +40,7 @@ def timeit(fn, steps=5, warmup=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
-    ap.add_argument("--cases", default="minn,iq16,chan,combined,park,zc,zcfreq,bank,aa64,rtl,dropin,tile")
+    ap.add_argument("--cases", default="minn,iq16,chan,rx,combined,park,zc,zcfreq,bank,aa64,rtl,dropin,tile")
     a = ap.parse_args()
     import numpy as np
     import torch
@@ -95,6 +95,24 @@ def main():
         emit("8f-1 impairment chain: 1100-tap FIR (overlap-save FFT) + AWGN + CFO + 12-bit ADC -> c64 + int16 IQ", ms, S * n,
              alg_bytes=S * n * (8 + 8 + 8 + 4), note="per stream sample: faded row 8 B (L2) + noise 8 B in, c64 8 B + iq 4 B out")
         del base, noise
+    if "rx" in cases:
+        # 8f-2 / 8f-3: the stages after the detector, one result per frame: CP-correlation CFO estimators and the pilot / data
+        # receive chain (CFO correction, 2 x 2048-point FFT, LS estimate, phase-slope timing, equalise, EVM)
+        F, n = max(int(4096 * a.scale), 8), 65536
+        x = synth.make_batch_device(F, n, "sc", seed=21, device=dev)[:, None]
+        starts = np.full(F, 1337 + 2560, dtype=np.int64)                      # CP start of the first pilot symbol of every capture
+        for mode in ("plain", "robust", "peak"):
+            ms = timeit(lambda: engine.cp_cfo(x, starts, 2048, 512, 30.72e6, mode), steps=5, warmup=2)
+            emit(f"8f-2 CP-correlation CFO estimator, mode {mode} (core.py:179-336), one estimate per capture", ms, F * n,
+                 note=f"{F} captures; only the ~3 k samples around each CP are read")
+        rng = np.random.default_rng(3)
+        pu = (rng.choice([-1.0, 1.0], 1200) + 1j * rng.choice([-1.0, 1.0], 1200)) / np.sqrt(2)
+        du = (rng.choice([-1.0, 1.0], 1200) + 1j * rng.choice([-1.0, 1.0], 1200)) / np.sqrt(2)
+        cfo = np.full(F, 1000.0)
+        ms = timeit(lambda: engine.rx_chain(x, starts, cfo, pu, du), steps=5, warmup=2)
+        emit("8f-3 receive chain per capture: CFO correction + pilot / data FFT + LS + phase-slope STO + equalise + EVM (float64)", ms, F * n,
+             note=f"{F} captures, 2 OFDM symbols each, 1200 used subcarriers; {F / (ms * 1e-3) / 1e6:.2f} M frames/s")
+        del x
     if "combined" in cases:
         F, n = max(int(1024 * a.scale), 8), 1 << 19
         x = synth.make_batch_device(F, n, "minn", seed=8, device=dev, chunk=32)[:, None]

@@ -934,7 +934,7 @@ __global__ void __launch_bounds__(DNT) argmax_kernel(RowView r, int64_t *out)
 // local_sum[i] = sum_{j=max(0,i-W+1)}^{i} mag[j]; valid[i] = i >= W.  (The reference's recurrence
 // `acc + sample - oldest` drifts by ~1e-16 relative; this is the drift-free windowed sum.)
 // One CTA per (row, tile of ZT outputs): float64 inclusive prefix of tile + W-sample halo in smem.
-constexpr int ZT = 2048;
+constexpr int ZT = 4096;
 __global__ void __launch_bounds__(DNT) zc_stream_kernel(RowView r, int W, double thresh_value, double scale,
                                                         double min_mag, void *local_sum, uint8_t *valid,
                                                         uint8_t *above, int64_t mstride, unsigned *bitmask, int64_t bm_stride)

@@ -98,23 +98,27 @@ __global__ void __launch_bounds__(ZNT) rx_chain_kernel(const RxParams p)
                 p.h_est[f * p.n_used + u] = h;
             }
             __syncthreads();
-            // np.unwrap (sequential by definition; 1200 steps) then the line fit of core.py:457-468
-            if (tid == 0) {
+            // np.unwrap, then the line fit of core.py:457-468.  The correction of sample u depends on the ORIGINAL phases u-1, u
+            // only (numpy: dd = diff(p); ph_correct = f(dd); up[1:] = p[1:] + cumsum(ph_correct)), so the fmod-heavy part runs on
+            // all threads; what stays sequential is numpy's left-to-right cumulative sum, two additions per bin.
+            double *cadd = reinterpret_cast<double *>(a);          // the FFT buffer is free: every used bin sits in yp / phi by now
+            {
                 const double PI = 3.14159265358979323846;
-                double corr = 0.0, prev = phi[0];
-                for (int u = 1; u < p.n_used; ++u) {
-                    const double cur = phi[u];
-                    const double dd = cur - prev;
+                for (int u = 1 + tid; u < p.n_used; u += ZNT) {
+                    const double dd = phi[u] - phi[u - 1];
                     double ddm = fmod(dd + PI, 2.0 * PI);
                     if (ddm < 0.0) ddm += 2.0 * PI;                 // numpy's mod is non-negative
                     ddm -= PI;
                     if (ddm == -PI && dd > 0.0) ddm = PI;
                     double c = ddm - dd;
                     if (fabs(dd) < PI) c = 0.0;
-                    corr += c;
-                    prev = cur;
-                    phi[u] = cur + corr;
+                    cadd[u] = c;
                 }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double corr = 0.0;
+                for (int u = 1; u < p.n_used; ++u) { corr += cadd[u]; phi[u] += corr; }
             }
             __syncthreads();
             double sk = 0.0, sp = 0.0;

@@ -361,6 +361,59 @@ def quantize_adc(x, full_scale: float, bits: int = 12):
     return (qr + 1j * qi) / levels * full_scale, np.stack((qr, qi), axis=-1).astype(np.int16)
 
 
+def aa_single_test(tx, cir, snr_db: float, full_scale_ratio: float, half_len: int, unit_noise, cfo_hz: float = 500.0,
+                   fs_hz: float = 15_360_000.0, true_start: int = 500):
+    """One case of the sync_aa grid after the transmit side -- sync_aa.run_single_test, sync_aa.py:716-823: per-antenna channel +
+    AWGN (:577-634, on given unit-normal draws), CFO (:637-645), full scale = rms x ratio (:727-728), clipping statistics
+    (:294-315), 12-bit quantiser (:263-291), detector (:421-571), strongest event (:741) -> dict of the TestResult fields.
+    cir: (antennas, taps); unit_noise: (antennas, n_out) complex."""
+    rx = channel_apply(tx, cir, snr_db, unit_noise)
+    rx = apply_cfo(rx, cfo_hz, fs_hz)
+    rms = np.sqrt(np.mean(np.abs(rx) ** 2))
+    full_scale = rms * full_scale_ratio
+    flat = rx.reshape(-1)
+    clip = np.sum((np.abs(flat.real) >= full_scale) | (np.abs(flat.imag) >= full_scale)) / flat.size
+    eff = max(0.0, 12 + np.log2(rms / full_scale)) if full_scale > 0 else 0.0
+    q = np.stack([quantize_adc(r, full_scale, 12)[0] for r in rx])
+    d = aa_detect_streaming(q, half_len, 0.15, 128, fs_hz)
+    out = dict(clipping_pct=100.0 * clip, effective_bits=eff)
+    if len(d["ev_i"]):
+        k = int(np.argmax(d["ev_f"][:, 2]))                  # max M_at_peak, first on ties
+        out.update(detected=True, num_events=len(d["ev_i"]), timing_error=int(d["ev_i"][k, 3]) - true_start,
+                   cfo_estimated_hz=float(d["ev_f"][k, 3]), metric_peak=float(d["ev_f"][k, 2]))
+    else:
+        out.update(detected=False, num_events=0, timing_error=0, cfo_estimated_hz=0.0,
+                   metric_peak=float(np.max(d["M"])) if np.any(d["valid"]) else 0.0)
+    return out
+
+
+def peak_noise_statistics(metric, peak_idx: int, pre_pad: int = 1337, guard: int = 500):
+    """Peak value, peak / mean(noise), peak / max(noise) with the noise floor taken outside [peak - guard, peak + guard) and past
+    the leading pad -- minn.py:841-858 == minn_rtl.py:1561-1580."""
+    m = np.asarray(metric, dtype=np.float64)
+    keep = np.ones(m.size, dtype=bool)
+    keep[max(0, peak_idx - guard):min(m.size, peak_idx + guard)] = False
+    keep[:pre_pad] = False
+    noise = m[keep]
+    peak = float(m[peak_idx])
+    if noise.size == 0:
+        return peak, float("inf"), float("inf")
+    avg, mx = float(np.mean(noise)), float(np.max(noise))
+    return peak, (peak / avg if avg > 0 else float("inf")), (peak / mx if mx > 0 else float("inf"))
+
+
+def block_length_point(tx, frame_len: int, cir, snr_db: float, symbol_len: int, unit_noise, cfo_hz: float = 1000.0,
+                       fs_hz: float = 30.72e6, pre_pad: int = 1337, delay: int = 0):
+    """One point of minn.compare_block_lengths after the transmit side (minn.py:812-858): channel + CFO, parameterised Minn
+    metric, arg-max over the first frame region, noise statistics -> (peak, par, pmr, timing_error)."""
+    rx = apply_cfo(channel_apply(tx, cir, snr_db, unit_noise), cfo_hz, fs_hz)
+    M, _, _ = minn_streaming_metric(rx, symbol_len)
+    end = pre_pad + frame_len + frame_len // 2
+    pk = int(np.argmax(M[:min(end, M.size)]))
+    peak, par, pmr = peak_noise_statistics(M, pk, pre_pad)
+    return peak, par, pmr, pk - (pre_pad + delay + symbol_len // 4)
+
+
 def wire_pack_hex24(iq):
     """docs/preamble_test_vector.hex: one 24-bit word per sample, {Re[11:0], Im[11:0]}, Re in the upper 12 bits."""
     q = np.asarray(iq, dtype=np.int64)

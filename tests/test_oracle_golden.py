@@ -320,3 +320,60 @@ def test_sweep_tx_builders_vs_reference(golden):
         assert p2.size == total and np.abs(p2[: total // 2] - p2[total // 2:]).max() <= 1e-12
     with pytest.raises(ValueError):
         sync_aa.build_aa_preamble(300)
+
+
+def test_oracle_aa_grid_vs_reference_run(golden):
+    """The whole 135-case grid of sync_aa.main through the oracle (C detector + numpy impairment chain) against the unmodified
+    reference run (tests/golden/aa_grid.npz): detection, event count and timing error equal, CFO 1e-6 Hz, peak metric 1e-9,
+    clipping statistics 1e-9.  The transmit side comes from the host builders, pinned separately against the reference."""
+    from ofdm_sync_math_b200 import sync_aa, synth
+    g = golden("aa_grid")
+    cirs = synth.load_cirs()
+    cache = {}
+    for i in range(g["detected"].size):
+        plen, ch = int(g["preamble_length"][i]), int(g["channel"][i])
+        if (plen, ch) not in cache:
+            rng = np.random.default_rng(42)
+            pre, _, _ = sync_aa.build_aa_preamble(plen)
+            pilot, _ = sync_aa.build_random_qpsk_symbol(rng)
+            data, _ = sync_aa.build_random_qpsk_symbol(rng)
+            tx = np.concatenate((np.zeros(500, complex), pre, pilot, data, np.zeros(500, complex)))
+            cir = np.ones((2, 1), complex) if ch == 0 else cirs["cir1" if ch == 1 else "cir2"][:2]
+            n_out = tx.size + cir.shape[1] - 1
+            unit = np.stack([rng.standard_normal(n_out) + 1j * rng.standard_normal(n_out) for _ in range(2)])
+            off = 0 if ch == 0 else int(np.argmax(np.sum(np.abs(cir) ** 2, axis=0)))
+            cache[(plen, ch)] = (tx, cir, unit, off)
+        tx, cir, unit, off = cache[(plen, ch)]
+        r = orc.aa_single_test(tx, cir, float(g["snr_db"][i]), float(g["fs_ratio"][i]), plen // 2, unit, 500.0, true_start=500 + off)
+        tag = f"case {i}"
+        assert r["detected"] == bool(g["detected"][i]) and r["num_events"] == int(g["num_events"][i]), tag
+        assert r["timing_error"] == int(g["timing_error"][i]), tag
+        assert abs(r["cfo_estimated_hz"] - g["cfo_estimated_hz"][i]) <= 1e-6, tag
+        assert abs(r["metric_peak"] - g["metric_peak"][i]) <= 1e-9 * max(abs(g["metric_peak"][i]), 1e-12), tag
+        assert abs(r["clipping_pct"] - g["clipping_pct"][i]) <= 1e-9 and abs(r["effective_bits"] - g["effective_bits"][i]) <= 1e-9, tag
+
+
+@pytest.mark.parametrize("ch", [None, "cir1"])
+def test_oracle_block_length_sweep_vs_reference_run(golden, ch):
+    """minn.compare_block_lengths (minn.py:754-871) through the oracle against the unmodified reference run
+    (tests/golden/sweeps.npz): timing errors equal, peak / PAR / PMR 1e-9 relative."""
+    from ofdm_sync_math_b200 import minn, sweeps
+    g = golden("sweeps")
+    tag = ch or "awgn"
+    cir, delay = sweeps.channel_bank(ch)
+    for snr in (0.0, 10.0):
+        got = []
+        for N in g["block_lengths"].tolist():
+            rng = np.random.default_rng(0)
+            pre = minn.build_minn_preamble_parameterized(rng, N, N // 4, include_cp=True)
+            tx, frame_len = sweeps.two_frame_stream(pre, rng)
+            B = 1 if cir is None else cir.shape[0]
+            n_out = tx.size + (0 if cir is None else cir.shape[1] - 1)
+            unit = orc.unit_noise_like_reference(0, (B, n_out))
+            got.append(orc.block_length_point(tx, frame_len, cir, snr, N, unit, delay=delay))
+        got = np.array(got)
+        pre_ = f"block_{tag}_snr{int(snr)}"
+        assert got[:, 3].astype(int).tolist() == g[f"{pre_}_timing_error"].astype(int).tolist()
+        for col, key in enumerate(("peak", "par", "pmr")):
+            ref = g[f"{pre_}_{key}"]
+            assert np.all(np.abs(got[:, col] - ref) <= 1e-9 * np.abs(ref)), (pre_, key, got[:, col], ref)

@@ -414,6 +414,26 @@ def block_length_point(tx, frame_len: int, cir, snr_db: float, symbol_len: int, 
     return peak, par, pmr, pk - (pre_pad + delay + symbol_len // 4)
 
 
+def q_value_point(tx, cir, snr_db: float, quarter_len: int, unit_noise, cfo_hz: float = 1000.0, fs_hz: float = 30.72e6,
+                  pre_pad: int = 1337, delay: int = 0, cp_len: int = 512, smooth_shift: int = 3, threshold_value: int = 3276,
+                  frac_bits: int = 15, hysteresis: int = 2, timing_offset: int = 0):
+    """One point of minn_rtl.compare_q_values after the transmit side (minn_rtl.py:1535-1580): channel + CFO, the RTL-style metric
+    and detector at segment length Q, first event (else arg-max of the smoothed metric), noise statistics of corr_positive
+    -> (peak, par, pmr, timing_error)."""
+    rx = apply_cfo(channel_apply(tx, cir, snr_db, unit_noise), cfo_hz, fs_hz)
+    st = minn_rtl_streaming_metric(rx, smooth_shift=smooth_shift, threshold_value=threshold_value, threshold_frac_bits=frac_bits,
+                                   quarter_len=quarter_len)
+    ev, _ = detect_minn_rtl(st, hysteresis=hysteresis, timing_offset=timing_offset)
+    target = pre_pad + delay + 5 * quarter_len + cp_len
+    if len(ev):
+        pk, terr = int(ev[0, 0]), int(ev[0, 1]) - target
+    else:
+        pk = int(np.argmax(st["smooth_metric"]))
+        terr = pk - target
+    peak, par, pmr = peak_noise_statistics(st["corr_positive"], pk, pre_pad)
+    return peak, par, pmr, terr
+
+
 def wire_pack_hex24(iq):
     """docs/preamble_test_vector.hex: one 24-bit word per sample, {Re[11:0], Im[11:0]}, Re in the upper 12 bits."""
     q = np.asarray(iq, dtype=np.int64)

@@ -377,3 +377,25 @@ def test_oracle_block_length_sweep_vs_reference_run(golden, ch):
         for col, key in enumerate(("peak", "par", "pmr")):
             ref = g[f"{pre_}_{key}"]
             assert np.all(np.abs(got[:, col] - ref) <= 1e-9 * np.abs(ref)), (pre_, key, got[:, col], ref)
+
+
+@pytest.mark.parametrize("ch", [None, "cir1"])
+def test_oracle_q_sweep_vs_reference_run(golden, ch):
+    """minn_rtl.compare_q_values (minn_rtl.py:1493-1592) through the oracle against the unmodified reference run."""
+    from ofdm_sync_math_b200 import minn_rtl, sweeps
+    g = golden("sweeps")
+    tag = ch or "awgn"
+    cir, delay = sweeps.channel_bank(ch)
+    got = []
+    for Q in g["q_values"].tolist():
+        rng = np.random.default_rng(0)
+        pre = minn_rtl.build_minn_preamble_generic("qpsk_freq", rng, Q=Q)
+        tx, _ = sweeps.two_frame_stream(pre, rng)
+        B = 1 if cir is None else cir.shape[0]
+        n_out = tx.size + (0 if cir is None else cir.shape[1] - 1)
+        got.append(orc.q_value_point(tx, cir, 0.0, Q, orc.unit_noise_like_reference(0, (B, n_out)), delay=delay))
+    got = np.array(got)
+    assert got[:, 3].astype(int).tolist() == g[f"q_{tag}_timing_error"].astype(int).tolist()
+    for col, key in enumerate(("peak", "par", "pmr")):
+        ref = g[f"q_{tag}_{key}"]
+        assert np.all(np.abs(got[:, col] - ref) <= 1e-9 * np.abs(ref)), (key, got[:, col], ref)

@@ -11,9 +11,11 @@ hook grabs the local variables of `run_simulation` at return, so every array sto
 computed by reference code (sc.py:159-368, minn.py:300-653, park.py:123-348,
 combined_sc_min.py:272-580, zc.py:57-283, zc_v2.py:522-787, zc_freq.py:102-290,
 minn_rtl.py:849-1100).  sync_aa / minn_rtl function-level cases call the reference functions
-directly on inputs built with the reference's own builders.
+directly on inputs built with the reference's own builders.  SURVEY 8(f) fixtures: the impairment chain and the CP-CFO
+estimators (channel_cfo), the receive chain (rxchain_*), the 135-case sync_aa grid (aa_grid), the block-length / Q
+sweeps (sweeps) and the RTL testbench's AXIS word packer (wire_axis) -- all outputs of reference code, never of ours.
 
-Usage:  python oracle/gen_golden.py [--ref /root/reference] [--out tests/golden]
+Usage:  python oracle/gen_golden.py [--ref /root/reference] [--out tests/golden] [--only sc,minn,...,aa_grid,sweeps,wire]
 """
 from __future__ import annotations
 

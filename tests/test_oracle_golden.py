@@ -399,3 +399,23 @@ def test_oracle_q_sweep_vs_reference_run(golden, ch):
     for col, key in enumerate(("peak", "par", "pmr")):
         ref = g[f"q_{tag}_{key}"]
         assert np.all(np.abs(got[:, col] - ref) <= 1e-9 * np.abs(ref)), (key, got[:, col], ref)
+
+
+def test_sweep_peak_statistics_host_logic_vs_oracle():
+    """sweeps.peak_statistics (torch, device-agnostic) against the oracle's restatement of minn.py:841-858 on CPU tensors:
+    random metrics, peaks at the row ends, a guard that swallows the whole row (-> inf), all-zero noise floor (-> inf)."""
+    import torch
+    from ofdm_sync_math_b200 import sweeps
+    rng = np.random.default_rng(0)
+    rows = []
+    for n, pk in ((5000, 2500), (5000, 0), (5000, 4999), (1400, 1350), (900, 450), (3000, 1500)):
+        m = rng.random(n)
+        if n == 3000:
+            m[:] = 0.0; m[pk] = 1.0                       # zero noise floor
+        rows.append((m, pk))
+    for m, pk in rows:
+        peak, par, pmr = sweeps.peak_statistics(torch.as_tensor(m)[None], torch.as_tensor([pk]))
+        ref = orc.peak_noise_statistics(m, pk)
+        got = (float(peak[0]), float(par[0]), float(pmr[0]))
+        for a, b in zip(got, ref):
+            assert (np.isinf(a) and np.isinf(b)) or abs(a - b) <= 1e-12 * abs(b), (m.size, pk, got, ref)

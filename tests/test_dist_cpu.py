@@ -57,3 +57,51 @@ def test_gloo_world2_gather_records(n_total):
         assert p.exitcode == 0
     assert res[0][1] == 0 and res[0][2] == res[1][1] and res[1][2] == n_total
     assert all(r[3] for r in res)
+
+
+def _worker_events(rank, world, port, caps_per_rank, q):
+    """bench_array.py's N > 1 exchange on CPU: every rank owns caps_per_rank captures, fills its event slots + counts (one flat
+    buffer, engine._event_buffers(want_flat=True)), all-gathers the flat buffers and decodes everybody's events."""
+    sys.path.insert(0, str(ROOT))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ofdm_sync_math_b200 import _lib as L, dist as odist, engine
+    ev, cnt, flat = engine._event_buffers(caps_per_rank, torch.device("cpu"), want_flat=True)
+    esz = ev.shape[1] // L.OFS_MAX_EVENTS
+    evn = ev.numpy().reshape(caps_per_rank, L.OFS_MAX_EVENTS, esz).view(engine._EVENT_NP).reshape(caps_per_rank, L.OFS_MAX_EVENTS)
+    for c in range(caps_per_rank):
+        k = (rank * caps_per_rank + c) % 5                       # 0..4 events in this capture
+        cnt[c] = k
+        for e in range(k):
+            evn[c, e]["peak_index"] = 1000 * (rank * caps_per_rank + c) + e
+            evn[c, e]["cfo"] = 0.5 * e + rank
+            evn[c, e]["closed"] = 1
+    parts = odist.RecordGatherer(flat.view(1, -1)).run()
+    ok = len(parts) == world
+    row_b = L.OFS_MAX_EVENTS * esz
+    for r in range(world):
+        f = parts[r].reshape(-1)
+        ev_r = f[: caps_per_rank * row_b].view(caps_per_rank, row_b)
+        cnt_r = f[caps_per_rank * row_b:].view(torch.int32)
+        dec = engine._events_to_numpy(ev_r, cnt_r)
+        for c in range(caps_per_rank):
+            g = r * caps_per_rank + c
+            ok &= len(dec[c]) == g % 5
+            ok &= [int(x) for x in dec[c]["peak_index"]] == [1000 * g + e for e in range(g % 5)]
+            ok &= all(float(x) == 0.5 * e + r for e, x in enumerate(dec[c]["cfo"]))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_gather_event_records():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_events, args=(r, 2, port, 3, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]

@@ -39,6 +39,35 @@ def peaks() -> tuple[float, str]:
     return 6650.0, "fallback"
 
 
+class StdoutToStderr:
+    """While active, whatever is written to file descriptor 1 goes to stderr.  NCCL prints its version banner on stdout when
+    NCCL_DEBUG is set in the environment; with this around the process-group set-up and the run, rank 0's stdout carries
+    exactly one line, the JSON.  Any failure to juggle the descriptors leaves stdout as it was."""
+
+    def __init__(self):
+        self.saved = None
+
+    def start(self):
+        try:
+            sys.stdout.flush()
+            self.saved = os.dup(1)
+            os.dup2(2, 1)
+        except OSError:
+            self.saved = None
+        return self
+
+    def stop(self):
+        if self.saved is None:
+            return
+        try:
+            sys.stdout.flush()
+            os.dup2(self.saved, 1)
+            os.close(self.saved)
+        except OSError:
+            pass
+        self.saved = None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (recipe of B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -161,6 +190,7 @@ def main() -> None:
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    quiet = StdoutToStderr().start() if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -282,6 +312,8 @@ def main() -> None:
                "sample": f"{ns} frames x {n} complex64 of this workload, {cores} threads, C restatement of sc.py:42-146 (oracle/)",
                "parity_in_run": {"timing_indices_equal": bool(idx_ok), "max_rel_metric_err": merr}}
 
+    if quiet is not None:
+        quiet.stop()
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -23,7 +23,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-from bench import ClockSampler, peaks  # noqa: E402
+from bench import ClockSampler, StdoutToStderr, peaks  # noqa: E402
 
 HALF_LEN, THRESH, HYST, FS = 512, 0.15, 128, 15.36e6
 
@@ -51,6 +51,7 @@ def main() -> None:
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    quiet = StdoutToStderr().start() if world > 1 else None      # NCCL's version banner goes to stderr, stdout = the JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -132,6 +133,8 @@ def main() -> None:
                "sample": f"1 capture x {A} antennas x {ns} samples, C restatement of sync_aa.py:421-571 (oracle/), one thread",
                "parity_in_run": {"event_peaks_equal": bool(same), "events": len(ev_o)}}
 
+    if quiet is not None:
+        quiet.stop()
     if rank == 0:
         print(json.dumps({
             "metric": "Msamples/s (complex baseband antenna samples, whole box) sync_aa array detector", "value": value, "unit": "Msamples/s",

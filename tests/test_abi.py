@@ -107,3 +107,22 @@ def test_patch_reference_tables_and_imported_helpers():
     assert fake.apply_channel is channel.apply_channel and fake.apply_cfo is core.apply_cfo
     assert fake.compare_block_lengths is minn.compare_block_lengths
     assert fake.estimate_cfo_from_cp_robust is own_cfo and "load_measured_cir" not in done
+
+
+def test_bench_stdout_guard_keeps_one_json_line():
+    """bench.StdoutToStderr: what a library writes to fd 1 during a multi-GPU run (NCCL's version banner) must not reach stdout,
+    which carries exactly the JSON line."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    code = ("import os, bench\n"
+            "g = bench.StdoutToStderr().start()\n"
+            "os.write(1, b'NCCL version 2.28.9+cuda12.9\\n')\n"
+            "print('python-level noise')\n"
+            "g.stop()\n"
+            "print('{\"ok\": 1}')\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == '{"ok": 1}\n'
+    assert "NCCL version" in r.stderr and "python-level noise" in r.stderr

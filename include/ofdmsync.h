@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define OFS_ABI_VERSION 1
+#define OFS_ABI_VERSION 2
 
 #define OFS_OK 0
 #define OFS_EINVAL (-1)      /* bad descriptor / null pointer / unsupported size */
@@ -145,7 +145,10 @@ int ofs_combined_peak(const ofs_rows *M_minn, const ofs_rows *M_sc, const float 
 /* argmax with numpy semantics (first maximum): park.py:161, zc.py:128, zc_freq.py:147 */
 int ofs_argmax(const ofs_rows *M, int64_t *index, void *stream);
 
-/* Gate / hysteresis state machines ------------------------------------------------------------- */
+/* Gate / hysteresis state machines -------------------------------------------------------------
+ * Event buffers hold max_events slots per row (caller's choice, >= 1; OFS_MAX_EVENTS is the default the Python layer starts
+ * with).  n_events[row] is always the TRUE number of gates of the row: a value above max_events means the list was cut and
+ * the call should be repeated with a larger buffer (the reference returns unbounded lists). */
 #define OFS_MAX_EVENTS 64
 typedef struct ofs_event {
     int64_t peak_index;
@@ -160,9 +163,9 @@ typedef struct ofs_event {
 } ofs_event;
 
 /* sync_aa.aa_detect_streaming loop 2 -- sync_aa.py:495-568.  M, P: rows of length n (P complex,
- * same precision as M).  events: ofs_event[n_rows][OFS_MAX_EVENTS]; n_events: int32[n_rows]. */
+ * same precision as M).  events: ofs_event[n_rows][max_events]; n_events: int32[n_rows]. */
 int ofs_aa_events(const ofs_rows *M, const void *P, int32_t L, double threshold, int32_t hysteresis,
-                  double sample_rate, ofs_event *events, int32_t *n_events, void *stream);
+                  double sample_rate, ofs_event *events, int32_t *n_events, int32_t max_events, void *stream);
 
 /* Fused antenna-array detector = sync_aa.aa_detect_streaming, sync_aa.py:458-568, for captures of n_antennas branches
  * (complex64 or int16 IQ on the device; L in {128, 256, 512, 1024}; rows 16-byte aligned).  One pass over x: P, R and M
@@ -173,7 +176,7 @@ int ofs_aa_events(const ofs_rows *M, const void *P, int32_t L, double threshold,
 int ofs_aa_detect(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_antennas, int64_t n,
                   int64_t x_frame_stride, int64_t x_branch_stride, int32_t L, double threshold, int32_t hysteresis,
                   double sample_rate, float *M, void *P_c64, float *R, int64_t out_stride, uint32_t *mask_ws,
-                  int64_t mask_stride, ofs_event *events, int32_t *n_events, void *stream);
+                  int64_t mask_stride, ofs_event *events, int32_t *n_events, int32_t max_events, void *stream);
 
 /* Reference-ORDER [A][A] metric (sync_aa.py:321-386, 458-493): the reference's running-sum recurrences
  * `sum + sample - oldest` in its exact operation order, one thread per frame, float64 outputs
@@ -190,21 +193,21 @@ int ofs_zc_streaming_detection(const ofs_rows *corr_mag, int32_t window, int32_t
 /* zc_v2.detect_zc_peaks -- zc_v2.py:360-450.  gate_mask optional. */
 int ofs_zc_events(const ofs_rows *corr_mag, const uint8_t *valid, const uint8_t *above, int64_t mask_stride,
                   int32_t reference_length, int32_t hysteresis, ofs_event *events, int32_t *n_events,
-                  uint8_t *gate_mask, void *stream);
+                  int32_t max_events, uint8_t *gate_mask, void *stream);
 /* ofs_zc_streaming_detection + ofs_zc_events in two launches that exchange one BIT per sample: the threshold kernel
  * (zc_v2.py:288-336) writes the above-threshold flags of the valid samples as a bitmask (mask_ws: uint32[n_rows][mask_stride],
  * mask_stride >= ceil(n / 32)) and the gate FSM (zc_v2.py:360-450) walks that -- the local_sum / valid / above arrays
  * (6 bytes per sample written, 2 read back) are not produced.  Same events as the two separate calls. */
 int ofs_zc_detect(const ofs_rows *corr_mag, int32_t window, int32_t thresh_value, int32_t frac_bits, double min_corr_mag,
                   int32_t reference_length, int32_t hysteresis, uint32_t *mask_ws, int64_t mask_stride, ofs_event *events,
-                  int32_t *n_events, void *stream);
+                  int32_t *n_events, int32_t max_events, void *stream);
 
 /* minn_rtl.detect_minn_rtl -- minn_rtl.py:750-825 (== ref/minn_preamble_detector.sv:337-384).
  * corr_positive rows: float64, or int64 when is_int != 0 (integer RTL mode).  An unclosed tail gate
  * is returned as an event with closed == 0 (the reference reports it as a segment, not an event). */
 int ofs_minn_rtl_events(const void *corr_positive, int32_t is_int, const uint8_t *valid, const uint8_t *above,
                         int64_t n_rows, int64_t n, int64_t stride, int32_t hysteresis, int32_t timing_offset,
-                        ofs_event *events, int32_t *n_events, void *stream);
+                        ofs_event *events, int32_t *n_events, int32_t max_events, void *stream);
 
 /* minn_rtl metric ------------------------------------------------------------------------------
  * Float mirror -- minn_rtl.minn_rtl_streaming_metric, minn_rtl.py:583-733.
@@ -233,6 +236,12 @@ int ofs_minn_rtl_int(const int16_t *iq, int64_t n_frames, int32_t n_branches, in
 int ofs_zc_matched_filter(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_branches, int64_t n,
                           const void *ref_c128, int32_t nr, int32_t mode, int32_t out_f64, void *corr_out,
                           void *mag_out, int64_t out_stride, void *stream);
+/* zc_v2.normalize_correlation -- zc_v2.py:257-271 -- applied to a correlation the CALLER supplies (any array of the full
+ * length n + nr - 1, not necessarily this library's matched-filter output): out = corr / (ref_norm * sqrt(max(E, 1e-12))),
+ * E = np.convolve(|x|^2, ones(nr), "full") in float64.  x: (n_frames, n), one branch; corr / out: complex64 (f64 = 0) or
+ * complex128 (f64 = 1) [n_frames][stride]; out may alias corr. */
+int ofs_zc_normalize(const void *corr, const void *x, int32_t in_dtype, int64_t n_frames, int64_t n, int32_t nr,
+                     double ref_norm, int32_t f64, void *out, int64_t stride, void *stream);
 /* zc_freq.compute_frequency_metric -- zc_freq.py:62-99, as a sliding DFT of the used bins.
  * bins: DFT bin numbers k_j in [0, n_fft); templ: complex128[nbins].  metric: [n_frames][n-(n_fft+cp)+1]. */
 int ofs_zc_freq_metric(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_branches, int64_t n,

@@ -10,8 +10,8 @@ from . import engine, synth
 
 
 def load_measured_cir(name: str) -> np.ndarray:
-    """channel.load_measured_cir: (channels, taps) complex128.  The measured profiles ship as tests/golden/cir.npz
-    (made from the reference's channel_models/*.csv by oracle/gen_golden.py)."""
+    """channel.load_measured_cir: (channels, taps) complex128.  The measured profiles ship as package data (data/channel_models.npz,
+    made from the reference's channel_models/*.csv by oracle/gen_golden.py)."""
     cirs = synth.load_cirs()
     if name not in cirs:
         raise ValueError(f"Unknown channel profile '{name}'")

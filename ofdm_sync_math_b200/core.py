@@ -64,5 +64,12 @@ def estimate_cfo_from_cp_peak_with_index(rx, cp_start_est: int, n_fft: int, cp_l
 
 
 def find_cp_start_via_corr(rx, est_start: int, n_fft: int, cp_len: int, search_half: int = 1024) -> int:
-    """core.py:311-336."""
+    """core.py:311-336.  An empty search range returns est_start without touching the data (core.py:323-324)."""
+    np = _np()
+    x = np.asarray(rx)
+    L = x.shape[-1]
+    lo = max(0, int(est_start) - int(search_half))
+    hi = min(L - (n_fft + cp_len), int(est_start) + int(search_half))
+    if hi <= lo:
+        return int(est_start)
     return _cfo(rx, est_start, n_fft, cp_len, 1.0, "peak", search_half)[1]

@@ -19,25 +19,32 @@ void set_error(const char *fmt, ...)
 }
 int64_t &launch_counter() { return g_launches; }
 
+int current_device()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); dev = 0; }
+    return dev < 0 ? 0 : (dev >= OFS_MAX_DEVICES ? OFS_MAX_DEVICES - 1 : dev);
+}
+
 int sm_count()
 {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
-        else
-            cached = 148;
+    static int cached[OFS_MAX_DEVICES] = {0};
+    const int dev = current_device();
+    int v = __atomic_load_n(&cached[dev], __ATOMIC_RELAXED);
+    if (v == 0) {
+        int n = 0;
+        v = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+        (void)cudaGetLastError();
+        __atomic_store_n(&cached[dev], v, __ATOMIC_RELAXED);
     }
-    return cached;
+    return v;
 }
 
 void keep_pool_cached()
 {
-    static bool done = false;
-    if (done) return;
-    done = true;
+    static PerDeviceOnce once;
+    if (once.done()) return;
+    once.mark();
     int dev = 0;
     cudaMemPool_t pool;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {

@@ -266,9 +266,9 @@ OFS_API int ofs_channel_apply(const void *tx, int32_t dtype, int64_t n_rows, int
         OFS_CUDA(cudaMallocAsync((void **)&ref, (size_t)n_taps * sizeof(double2), stream));
         chan_ref_kernel<<<(n_taps + 255) / 256, 256, 0, stream>>>((const double2 *)taps_c128, n_taps, ref);
         if (int rc = check_launch("chan_ref_kernel")) return rc;
-        if (int rc = ofs_zc_matched_filter(tx, dtype, n_rows, 1, n_tx, ref, n_taps, 2, dtype == OFS_C128, faded_ws, nullptr, n_out, stream_))
-            return rc;
-        OFS_CUDA(cudaFreeAsync(ref, stream));
+        const int rc = ofs_zc_matched_filter(tx, dtype, n_rows, 1, n_tx, ref, n_taps, 2, dtype == OFS_C128, faded_ws, nullptr, n_out, stream_);
+        OFS_CUDA(cudaFreeAsync(ref, stream));              // stream-ordered: also on the error path
+        if (rc) return rc;
     } else {
         OFS_CUDA(cudaMemcpyAsync(faded_ws, tx, (size_t)n_rows * n_tx * esz, cudaMemcpyDeviceToDevice, stream));
     }
@@ -304,7 +304,10 @@ OFS_API int ofs_cp_cfo(const void *x, int32_t in_dtype, int64_t n_frames, int32_
     p.P = (double2 *)P_c128;
     const int W = mode == 1 ? win_len : cp_len;
     int64_t nq = (mode == 0 ? 1 : 2LL * span) + W;
-    if (nq > CFO_MAXQ) nq = CFO_MAXQ;
+    if (nq > CFO_MAXQ) {
+        set_error("ofs_cp_cfo: 2*span + window = %lld lag products exceed the %d this build holds in shared memory", (long long)nq, CFO_MAXQ);
+        return OFS_EUNSUPPORTED;
+    }
     const size_t smem = (size_t)(nq + 2) * sizeof(double2);
 #define OFS_CFO_LAUNCH(DT)                                                                                     \
     do {                                                                                                       \

@@ -43,7 +43,17 @@ inline int check_launch(const char *what)
     return OFS_OK;
 }
 
-int sm_count();  // cached multiprocessor count of the current device
+int sm_count();  // multiprocessor count of the CURRENT device (cached per device)
+int current_device();  // cudaGetDevice, clamped to [0, OFS_MAX_DEVICES)
+constexpr int OFS_MAX_DEVICES = 64;
+// One-time per-DEVICE set-up (function attributes, occupancy queries are per device: a process may drive several GPUs through
+// ofs_ctx_create(ctx, device)).  `if (!once.done()) { ...idempotent set-up...; once.mark(); }` -- two threads racing on the same
+// device both run the set-up, which is harmless; nobody launches before its own set-up has finished.
+struct PerDeviceOnce {
+    unsigned long long bits = 0;
+    bool done() const { return (__atomic_load_n(&bits, __ATOMIC_ACQUIRE) >> current_device()) & 1ull; }
+    void mark() { __atomic_fetch_or(&bits, 1ull << current_device(), __ATOMIC_RELEASE); }
+};
 void keep_pool_cached();  // stream-ordered workspace (cudaMallocAsync): keep freed blocks in the pool between calls
 
 // ---- device helpers -----------------------------------------------------------------------------

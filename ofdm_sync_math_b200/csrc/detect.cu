@@ -1004,6 +1004,7 @@ struct FsmParams {
     double thr, fs;
     ofs_event *events;
     int32_t *n_events;
+    int max_events;           // event slots per row (>= 1); n_events carries the true gate count
     uint8_t *gate_mask;       // ZC optional
     const unsigned *premask;  // AA optional: above-threshold bitmask already built by the metric kernel (metric_array.cu)
     int64_t premask_stride;   // words per row
@@ -1131,7 +1132,7 @@ __global__ void __launch_bounds__(DNT) fsm_gates_kernel(FsmParams p)
     for (int w = 0; w < warp; ++w) if (s_last[w] > prev_last) prev_last = s_last[w];
     for (int w = warp + 1; w < NW; ++w) if (s_first[w] < next_first) next_first = s_first[w];
 
-    ofs_event *evs = p.events + row * OFS_MAX_EVENTS;
+    ofs_event *evs = p.events + row * (int64_t)p.max_events;
     auto walk_starts = [&](bool write, int off) -> int {
         long long run_last = prev_last;
         int c = 0;
@@ -1147,7 +1148,7 @@ __global__ void __launch_bounds__(DNT) fsm_gates_kernel(FsmParams p)
                 const unsigned below = m & ((1u << a) - 1u);
                 const long long prev = below ? base + 31 - __clz(below) : run_last;
                 if (prev < 0 || base + a - prev - 1 >= p.heff) {
-                    if (write && off + c < OFS_MAX_EVENTS) evs[off + c].gate_start = base + a;
+                    if (write && off + c < p.max_events) evs[off + c].gate_start = base + a;
                     ++c;
                 }
             }
@@ -1172,7 +1173,7 @@ __global__ void __launch_bounds__(DNT) fsm_gates_kernel(FsmParams p)
                 const long long pos = base + b;
                 if (next == LLONG_MAX || next - pos - 1 >= p.heff) {
                     const int idx = off_end - 1 - c;
-                    if (write && idx < OFS_MAX_EVENTS) {
+                    if (write && idx < p.max_events) {
                         const bool closes = next != LLONG_MAX || (n - 1 - pos) >= p.heff;
                         evs[idx].gate_end = closes ? pos + p.heff : n - 1;
                         evs[idx].closed = closes;
@@ -1211,11 +1212,11 @@ __global__ void __launch_bounds__(DNT) fsm_peaks_kernel(FsmParams p)
     const int tid = threadIdx.x;
     const int64_t n = p.val.n;
     const int total = p.n_events[row];
-    const int cnt = total < OFS_MAX_EVENTS ? total : OFS_MAX_EVENTS;
+    const int cnt = total < p.max_events ? total : p.max_events;
 
     // 3. peak of each gate over [open, close] with the reference's tie rule
     for (int e = blockIdx.y; e < cnt; e += gridDim.y) {
-        ofs_event *slot = p.events + row * OFS_MAX_EVENTS + e;
+        ofs_event *slot = p.events + row * (int64_t)p.max_events + e;
         const long long gs = slot->gate_start, gc = slot->gate_end;
         const int closed = slot->closed;
         ArgVal pk{0.0, -1};
@@ -1424,6 +1425,7 @@ template <int KIND>
 static int launch_fsm(FsmParams &p, int64_t n_rows, cudaStream_t stream)
 {
     OFS_REQUIRE(p.val.n <= MASK_MAX_N, "gate FSM: rows longer than %lld unsupported", (long long)MASK_MAX_N);
+    OFS_REQUIRE(p.max_events >= 1, "gate FSM: max_events must be >= 1");
     if (n_rows == 0) return OFS_OK;
     const size_t sm = mask_bytes(p.val.n);
     if (int rc = set_mask_smem(fsm_gates_kernel<KIND>, sm)) return rc;
@@ -1431,27 +1433,28 @@ static int launch_fsm(FsmParams &p, int64_t n_rows, cudaStream_t stream)
     if (int rc = check_launch("fsm_gates_kernel")) return rc;
     // gate slices per row: enough CTAs to fill the machine a few times over when the rows are few
     int64_t slices = (4LL * sm_count() + n_rows - 1) / n_rows;
-    if (slices > OFS_MAX_EVENTS) slices = OFS_MAX_EVENTS;
+    if (slices > p.max_events) slices = p.max_events;
+    if (slices > 65535) slices = 65535;
     if (slices < 1) slices = 1;
     fsm_peaks_kernel<KIND><<<dim3((unsigned)n_rows, (unsigned)slices), DNT, 0, stream>>>(p);
     return check_launch("fsm_peaks_kernel");
 }
 
 OFS_API int ofs_aa_events(const ofs_rows *M, const void *P, int32_t L, double threshold, int32_t hysteresis,
-                          double sample_rate, ofs_event *events, int32_t *n_events, void *stream)
+                          double sample_rate, ofs_event *events, int32_t *n_events, int32_t max_events, void *stream)
 {
     if (int rc = rows_ok(M, "ofs_aa_events")) return rc;
     OFS_REQUIRE(P && events && n_events && L > 0, "ofs_aa_events: bad arguments");
     FsmParams p{};
     p.val = view(M); p.P = P; p.L = L; p.heff = hysteresis > 1 ? hysteresis : 1; p.thr = threshold; p.fs = sample_rate;
-    p.events = events; p.n_events = n_events;
+    p.events = events; p.n_events = n_events; p.max_events = max_events;
     return launch_fsm<FSM_AA>(p, M->n_rows, (cudaStream_t)stream);
 }
 
 OFS_API int ofs_aa_detect(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_antennas, int64_t n,
                           int64_t x_frame_stride, int64_t x_branch_stride, int32_t L, double threshold, int32_t hysteresis,
                           double sample_rate, float *M, void *P_c64, float *R, int64_t out_stride, uint32_t *mask_ws,
-                          int64_t mask_stride, ofs_event *events, int32_t *n_events, void *stream)
+                          int64_t mask_stride, ofs_event *events, int32_t *n_events, int32_t max_events, void *stream)
 {
     OFS_REQUIRE(x && M && P_c64 && mask_ws && events && n_events && L > 0, "ofs_aa_detect: null argument");
     OFS_REQUIRE(n_frames >= 0 && n_antennas >= 1 && n >= 0 && n_frames < (1LL << 31), "ofs_aa_detect: bad geometry");
@@ -1462,13 +1465,13 @@ OFS_API int ofs_aa_detect(const void *x, int32_t in_dtype, int64_t n_frames, int
         return rc;
     FsmParams p{};
     p.val = RowView{M, 0, n, out_stride}; p.P = P_c64; p.L = L; p.heff = hysteresis > 1 ? hysteresis : 1; p.thr = threshold;
-    p.fs = sample_rate; p.events = events; p.n_events = n_events; p.premask = mask_ws; p.premask_stride = mask_stride;
+    p.fs = sample_rate; p.events = events; p.n_events = n_events; p.max_events = max_events; p.premask = mask_ws; p.premask_stride = mask_stride;
     return launch_fsm<FSM_AA>(p, n_frames, (cudaStream_t)stream);
 }
 
 OFS_API int ofs_zc_events(const ofs_rows *corr_mag, const uint8_t *valid, const uint8_t *above, int64_t mask_stride,
                           int32_t reference_length, int32_t hysteresis, ofs_event *events, int32_t *n_events,
-                          uint8_t *gate_mask, void *stream)
+                          int32_t max_events, uint8_t *gate_mask, void *stream)
 {
     if (int rc = rows_ok(corr_mag, "ofs_zc_events")) return rc;
     OFS_REQUIRE(valid && above && events && n_events && mask_stride >= corr_mag->n, "ofs_zc_events: bad arguments");
@@ -1476,13 +1479,13 @@ OFS_API int ofs_zc_events(const ofs_rows *corr_mag, const uint8_t *valid, const 
         OFS_CUDA(cudaMemsetAsync(gate_mask, 0, (size_t)corr_mag->n_rows * mask_stride, (cudaStream_t)stream));
     FsmParams p{};
     p.val = view(corr_mag); p.valid = valid; p.above = above; p.mstride = mask_stride; p.L = reference_length;
-    p.heff = hysteresis > 1 ? hysteresis : 1; p.events = events; p.n_events = n_events; p.gate_mask = gate_mask;
+    p.heff = hysteresis > 1 ? hysteresis : 1; p.events = events; p.n_events = n_events; p.max_events = max_events; p.gate_mask = gate_mask;
     return launch_fsm<FSM_ZC>(p, corr_mag->n_rows, (cudaStream_t)stream);
 }
 
 OFS_API int ofs_zc_detect(const ofs_rows *corr_mag, int32_t window, int32_t thresh_value, int32_t frac_bits, double min_corr_mag,
                           int32_t reference_length, int32_t hysteresis, uint32_t *mask_ws, int64_t mask_stride, ofs_event *events,
-                          int32_t *n_events, void *stream)
+                          int32_t *n_events, int32_t max_events, void *stream)
 {
     if (int rc = rows_ok(corr_mag, "ofs_zc_detect")) return rc;
     OFS_REQUIRE(mask_ws && events && n_events && mask_stride >= (corr_mag->n + 31) / 32, "ofs_zc_detect: bad arguments");
@@ -1499,18 +1502,18 @@ OFS_API int ofs_zc_detect(const ofs_rows *corr_mag, int32_t window, int32_t thre
     if (int rc = check_launch("zc_stream_kernel")) return rc;
     FsmParams p{};
     p.val = view(corr_mag); p.L = reference_length; p.heff = hysteresis > 1 ? hysteresis : 1; p.events = events; p.n_events = n_events;
-    p.premask = mask_ws; p.premask_stride = mask_stride;
+    p.max_events = max_events; p.premask = mask_ws; p.premask_stride = mask_stride;
     return launch_fsm<FSM_ZC>(p, corr_mag->n_rows, (cudaStream_t)stream);
 }
 
 OFS_API int ofs_minn_rtl_events(const void *corr_positive, int32_t is_int, const uint8_t *valid, const uint8_t *above,
                                 int64_t n_rows, int64_t n, int64_t stride, int32_t hysteresis, int32_t timing_offset,
-                                ofs_event *events, int32_t *n_events, void *stream)
+                                ofs_event *events, int32_t *n_events, int32_t max_events, void *stream)
 {
     OFS_REQUIRE(corr_positive && valid && above && events && n_events, "ofs_minn_rtl_events: null argument");
     OFS_REQUIRE(n_rows >= 0 && n >= 0 && stride >= n && n_rows < (1LL << 31), "ofs_minn_rtl_events: bad geometry");
     FsmParams p{};
     p.val = RowView{corr_positive, 1, n, stride}; p.is_int = is_int; p.valid = valid; p.above = above; p.mstride = stride;
-    p.L = timing_offset; p.heff = hysteresis > 1 ? hysteresis : 1; p.events = events; p.n_events = n_events;
+    p.L = timing_offset; p.heff = hysteresis > 1 ? hysteresis : 1; p.events = events; p.n_events = n_events; p.max_events = max_events;
     return launch_fsm<FSM_RTL>(p, n_rows, (cudaStream_t)stream);
 }

@@ -281,10 +281,10 @@ static int launch_array_t(ArrayParams &p, cudaStream_t stream)
     const int stages = array_stages(L, InT<DT>::bytes);
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce once;
+    if (!once.done()) {
         OFS_CUDA(cudaFuncSetAttribute(aa_array_kernel<DT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_SMEM));
-        attr_set = true;
+        once.mark();
     }
     const int64_t slots = (int64_t)sm_count() * array_ctas_per_sm(L, InT<DT>::bytes);
     const int64_t grid = p.n_tiles < slots ? p.n_tiles : slots;

@@ -511,14 +511,16 @@ static int launch_one(StripeParams p, int64_t total_work, cudaStream_t stream)
     const size_t smem = (size_t)SSTAGES * BK * ESZ + (size_t)WARPS * 2 * SCH * sizeof(float) +
                         (size_t)3 * WARPS * 4 * sizeof(double) + SSTAGES * sizeof(uint64_t);
     auto kern = metric_stripe_kernel<WARPS, KIND, DT, WPR>;
-    static bool attr_set = false;
-    static int occ = 0;
-    if (!attr_set) {
+    static PerDeviceOnce once;
+    static int occ_dev[OFS_MAX_DEVICES];
+    if (!once.done()) {
+        int o = 0;
         OFS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        OFS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
-        if (occ < 1) occ = 1;
-        attr_set = true;
+        OFS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, WARPS * 32, smem));
+        occ_dev[current_device()] = o < 1 ? 1 : o;
+        once.mark();
     }
+    const int occ = occ_dev[current_device()];
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     // tiled (swizzled) copies need 128-byte rows: frame pitch a multiple of 128 bytes; the batch is one tensor

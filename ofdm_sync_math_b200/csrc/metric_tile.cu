@@ -237,10 +237,10 @@ int launch_metric_tile(const ofs_metric_desc *d, const void *x, void *M, void *P
     OFS_REQUIRE(grid < (1LL << 31), "ofs_metric(tile): grid too large");
 #define OFS_TILE_LAUNCH(DT)                                                                                          \
     do {                                                                                                             \
-        static bool attr_set = false;                                                                                \
-        if (!attr_set) {                                                                                             \
+        static PerDeviceOnce once;                                                                                   \
+        if (!once.done()) {                                                                                          \
             OFS_CUDA(cudaFuncSetAttribute(metric_tile_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, NP_MAX * 24 + 64)); \
-            attr_set = true;                                                                                         \
+            once.mark();                                                                                             \
         }                                                                                                            \
         metric_tile_kernel<DT><<<(unsigned)grid, TILE_NT, smem, stream>>>(p);                                        \
     } while (0)

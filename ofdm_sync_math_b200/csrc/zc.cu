@@ -173,6 +173,57 @@ __global__ void __launch_bounds__(ZNT, (sizeof(T) == 4 ? 3 : 1)) zc_mf_kernel(co
     }
 }
 
+// ---- zc_v2.normalize_correlation (zc_v2.py:257-271) on a correlation the CALLER supplies ---------------------
+// out[k] = corr[k] / (ref_norm * sqrt(max(E[k], 1e-12))), E[k] = sum of |x[j]|^2 over j in [k-nr+1, k] inside the capture
+// (np.convolve(|x|^2, ones(nr), "full")).  One CTA per (frame, tile of NZT outputs): float64 prefix of the tile + halo.
+constexpr int NZT = 4096;
+template <int DT>
+__global__ void __launch_bounds__(256) zc_normalize_kernel(const void *corr, const void *x, int64_t n, int nr, double ref_norm,
+                                                           int f64, void *out, int64_t stride)
+{
+    using In = typename InT<DT>::type;
+    extern __shared__ double nzs[];             // nzs[k] = sum of |x|^2 over [j0, j0 + k)
+    __shared__ double wtot[8];
+    const int64_t frame = blockIdx.y, k0 = (int64_t)blockIdx.x * NZT, out_len = n + nr - 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t kend = k0 + NZT < out_len ? k0 + NZT : out_len;
+    int64_t j0 = k0 - nr + 1;
+    if (j0 < 0) j0 = 0;
+    const int64_t j1 = kend < n ? kend : n;      // samples [j0, j1)
+    const int cnt = (int)(j1 - j0 > 0 ? j1 - j0 : 0);
+    const In *xr = reinterpret_cast<const In *>(x) + frame * n;
+    for (int k = tid; k < cnt; k += 256) { const In v = xr[j0 + k]; nzs[k + 1] = (double)v.x * v.x + (double)v.y * v.y; }
+    if (tid == 0) nzs[0] = 0.0;
+    __syncthreads();
+    const int ipt = ((cnt + 255) / 256) | 1;
+    const int s0 = 1 + tid * ipt, s1 = min(s0 + ipt, cnt + 1);
+    double acc = 0.0;
+    for (int q = s0; q < s1; ++q) { acc += nzs[q]; nzs[q] = acc; }
+    double t = acc;
+    for (int o = 1; o < 32; o <<= 1) { const double y = shfl_up_f64(t, o); if (lane >= o) t += y; }
+    if (lane == 31) wtot[warp] = t;
+    __syncthreads();
+    double off = t - acc;
+    for (int w = 0; w < warp; ++w) off += wtot[w];
+    for (int q = s0; q < s1; ++q) nzs[q] += off;
+    __syncthreads();
+    for (int64_t k = k0 + tid; k < kend; k += 256) {
+        int64_t lo = k - nr + 1, hi = k + 1;
+        if (lo < j0) lo = j0;
+        if (hi > j1) hi = j1;
+        const double e = hi > lo ? nzs[hi - j0] - nzs[lo - j0] : 0.0;
+        const double dnm = ref_norm * sqrt(e > 1e-12 ? e : 1e-12);
+        const int64_t o = frame * stride + k;
+        if (f64) {
+            const double2 c = reinterpret_cast<const double2 *>(corr)[o];
+            reinterpret_cast<double2 *>(out)[o] = make_double2(c.x / dnm, c.y / dnm);
+        } else {
+            const float2 c = reinterpret_cast<const float2 *>(corr)[o];
+            reinterpret_cast<float2 *>(out)[o] = make_float2((float)((double)c.x / dnm), (float)((double)c.y / dnm));
+        }
+    }
+}
+
 // ---- zc_freq: sliding DFT of the used bins --------------------------------------------------------
 constexpr int QNT = 256;
 
@@ -325,6 +376,28 @@ OFS_API int ofs_zc_matched_filter(const void *x, int32_t in_dtype, int64_t n_fra
     OFS_CUDA(cudaFreeAsync(G, stream));
     OFS_CUDA(cudaFreeAsync(rn, stream));
     return OFS_OK;
+}
+
+OFS_API int ofs_zc_normalize(const void *corr, const void *x, int32_t in_dtype, int64_t n_frames, int64_t n, int32_t nr,
+                             double ref_norm, int32_t f64, void *out, int64_t stride, void *stream)
+{
+    OFS_REQUIRE(corr && x && out, "ofs_zc_normalize: null argument");
+    OFS_REQUIRE(in_dtype >= OFS_C64 && in_dtype <= OFS_IQ16, "ofs_zc_normalize: unknown dtype");
+    OFS_REQUIRE(n >= 1 && nr >= 1 && n_frames >= 0 && n_frames < 65536 && stride >= n + nr - 1, "ofs_zc_normalize: bad geometry");
+    OFS_REQUIRE(nr <= 65536 && ref_norm > 0.0, "ofs_zc_normalize: reference length 1..65536, positive norm");
+    if (n_frames == 0) return OFS_OK;
+    const size_t smem = (size_t)(NZT + nr + 2) * sizeof(double);
+    const dim3 grid((unsigned)((n + nr - 1 + NZT - 1) / NZT), (unsigned)n_frames);
+#define OFS_NZ_LAUNCH(DT)                                                                                          \
+    do {                                                                                                           \
+        OFS_CUDA(cudaFuncSetAttribute(zc_normalize_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        zc_normalize_kernel<DT><<<grid, 256, smem, (cudaStream_t)stream>>>(corr, x, n, nr, ref_norm, f64, out, stride); \
+    } while (0)
+    if (in_dtype == OFS_C128) OFS_NZ_LAUNCH(OFS_C128);
+    else if (in_dtype == OFS_C64) OFS_NZ_LAUNCH(OFS_C64);
+    else OFS_NZ_LAUNCH(OFS_IQ16);
+#undef OFS_NZ_LAUNCH
+    return check_launch("zc_normalize_kernel");
 }
 
 OFS_API int ofs_zc_freq_metric(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_branches, int64_t n,

@@ -596,10 +596,10 @@ static int bank_run(const void *x_c64, int64_t n_frames, int64_t n, int32_t n_ff
     segs = (n_off + seg_len - 1) / seg_len;
 
     const size_t smem = (1 + BK_ST) * BK_TILE + 1024 + 4096 + 8192 + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce once;
+    if (!once.done()) {
         OFS_CUDA(cudaFuncSetAttribute(zc_bank_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        once.mark();
     }
     for (int r0 = 0; r0 < n_roots; r0 += BK_MAXR) {
         const int nr = n_roots - r0 < BK_MAXR ? n_roots - r0 : BK_MAXR;

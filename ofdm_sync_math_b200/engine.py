@@ -236,39 +236,69 @@ _EVENT_NP = np.dtype([("peak_index", "<i8"), ("gate_start", "<i8"), ("gate_end",
 assert _EVENT_NP.itemsize == C.sizeof(L.Event)
 
 
-def _events_to_numpy(ev: torch.Tensor, cnt: torch.Tensor) -> list[np.ndarray]:
+class EventOverflow(L.OfsError):
+    """A row produced more gates than the slots of the event buffer it was given (the reference returns unbounded lists)."""
+
+
+def _events_to_numpy(ev: torch.Tensor, cnt: torch.Tensor, cap: int = L.OFS_MAX_EVENTS, overflow: str = "raise") -> list[np.ndarray]:
     """Device event buffers -> one structured array per row.  Only the occupied part of the buffers crosses PCIe (a row holds
-    up to OFS_MAX_EVENTS events of 72 bytes; typical captures use a handful)."""
-    c = np.minimum(cnt.cpu().numpy(), L.OFS_MAX_EVENTS)
+    up to `cap` events of 72 bytes; typical captures use a handful).  n_events carries the TRUE number of gates of a row: when
+    it exceeds the slots, overflow="raise" raises EventOverflow (with .needed = the largest count) and overflow="truncate" keeps
+    the first `cap` events -- nothing is ever cut silently."""
+    craw = cnt.cpu().numpy()
+    if overflow == "raise" and craw.size and int(craw.max()) > cap:
+        r = int(np.argmax(craw))
+        err = EventOverflow(f"row {r} has {int(craw[r])} gates but the event buffer holds {cap}")
+        err.needed = int(craw.max())
+        raise err
+    c = np.minimum(craw, cap)
     rows = ev.shape[0]
     mc = int(c.max()) if rows else 0
     if mc == 0:
         return [np.zeros(0, dtype=_EVENT_NP) for _ in range(rows)]
     esz = C.sizeof(L.Event)
-    raw = ev.view(rows, L.OFS_MAX_EVENTS, esz)[:, :mc].contiguous().cpu().numpy().view(_EVENT_NP).reshape(rows, mc)
+    raw = ev.view(rows, cap, esz)[:, :mc].contiguous().cpu().numpy().view(_EVENT_NP).reshape(rows, mc)
     return [raw[i, : int(c[i])] for i in range(rows)]
 
 
-def _event_buffers(n_rows: int, dev, want_flat: bool = False):
-    """Event slots [n_rows, OFS_MAX_EVENTS * 72 B] and counts int32[n_rows] as two views of ONE allocation, so that a multi-GPU
+def _event_buffers(n_rows: int, dev, want_flat: bool = False, cap: int = L.OFS_MAX_EVENTS):
+    """Event slots [n_rows, cap * 72 B] and counts int32[n_rows] as two views of ONE allocation, so that a multi-GPU
     caller ships both with a single all_gather (flat uint8 tensor, want_flat=True)."""
-    row_b = L.OFS_MAX_EVENTS * C.sizeof(L.Event)
+    row_b = cap * C.sizeof(L.Event)
     flat = torch.zeros(n_rows * (row_b + 4), dtype=torch.uint8, device=dev)
     ev = flat[: n_rows * row_b].view(n_rows, row_b)
     cnt = flat[n_rows * row_b:].view(torch.int32)
     return (ev, cnt, flat) if want_flat else (ev, cnt)
 
 
-def aa_events(M: torch.Tensor, P: torch.Tensor, half_len: int, threshold: float, hysteresis: int, sample_rate: float):
-    """sync_aa.py:495-568 -> list (per row) of structured event arrays."""
+def _with_event_buffers(n_rows: int, dev, launch, max_events: int | None):
+    """Run `launch(ev, cnt, cap)` and decode its events.  max_events=None (the drop-ins): start with OFS_MAX_EVENTS slots and,
+    when a row holds more gates than that, repeat the launch with exactly as many slots as the fullest row needs -- lists are
+    unbounded like the reference's.  An explicit max_events is a hard cap: overflow raises EventOverflow."""
+    cap = L.OFS_MAX_EVENTS if max_events is None else int(max_events)
+    while True:
+        ev, cnt = _event_buffers(n_rows, dev, cap=cap)
+        launch(ev, cnt, cap)
+        try:
+            return _events_to_numpy(ev, cnt, cap)
+        except EventOverflow as e:
+            if max_events is not None:
+                raise
+            cap = e.needed
+
+
+def aa_events(M: torch.Tensor, P: torch.Tensor, half_len: int, threshold: float, hysteresis: int, sample_rate: float,
+              max_events: int | None = None):
+    """sync_aa.py:495-568 -> list (per row) of structured event arrays (unbounded; max_events: hard cap, EventOverflow beyond)."""
     rows, M = _rows(M)
     if P.dim() == 1:
         P = P[None]
     P = P.to(torch.complex128 if M.dtype == torch.float64 else torch.complex64).contiguous()
-    ev, cnt = _event_buffers(M.shape[0], M.device)
-    L.check(L.lib().ofs_aa_events(C.byref(rows), _ptr(P), int(half_len), C.c_double(threshold), int(hysteresis),
-                                  C.c_double(sample_rate), _ptr(ev), _ptr(cnt), _stream()), "ofs_aa_events")
-    return _events_to_numpy(ev, cnt)
+
+    def launch(ev, cnt, cap):
+        L.check(L.lib().ofs_aa_events(C.byref(rows), _ptr(P), int(half_len), C.c_double(threshold), int(hysteresis),
+                                      C.c_double(sample_rate), _ptr(ev), _ptr(cnt), int(cap), _stream()), "ofs_aa_events")
+    return _with_event_buffers(M.shape[0], M.device, launch, max_events)
 
 
 def zc_streaming_detection(corr_mag: torch.Tensor, window: int, thresh_value: int, frac_bits: int, min_corr_mag: float):
@@ -286,7 +316,7 @@ def zc_streaming_detection(corr_mag: torch.Tensor, window: int, thresh_value: in
 
 
 def zc_events(corr_mag: torch.Tensor, valid: torch.Tensor, above: torch.Tensor, reference_length: int, hysteresis: int,
-              want_gate_mask: bool = True):
+              want_gate_mask: bool = True, max_events: int | None = None):
     """zc_v2.py:360-450 -> (events per row, gate_mask uint8 or None)."""
     rows, m = _rows(corr_mag)
     m = m.contiguous()
@@ -294,28 +324,31 @@ def zc_events(corr_mag: torch.Tensor, valid: torch.Tensor, above: torch.Tensor, 
     v = valid.to(device=m.device, dtype=torch.uint8).reshape(m.shape).contiguous()
     a = above.to(device=m.device, dtype=torch.uint8).reshape(m.shape).contiguous()
     gm = torch.zeros(m.shape, dtype=torch.uint8, device=m.device) if want_gate_mask else None
-    ev, cnt = _event_buffers(m.shape[0], m.device)
-    L.check(L.lib().ofs_zc_events(C.byref(rows), _ptr(v), _ptr(a), C.c_int64(m.shape[1]), int(reference_length), int(hysteresis),
-                                  _ptr(ev), _ptr(cnt), _ptr(gm), _stream()), "ofs_zc_events")
-    return _events_to_numpy(ev, cnt), gm
+
+    def launch(ev, cnt, cap):
+        L.check(L.lib().ofs_zc_events(C.byref(rows), _ptr(v), _ptr(a), C.c_int64(m.shape[1]), int(reference_length), int(hysteresis),
+                                      _ptr(ev), _ptr(cnt), int(cap), _ptr(gm), _stream()), "ofs_zc_events")
+    return _with_event_buffers(m.shape[0], m.device, launch, max_events), gm
 
 
 def zc_detect(corr_mag: torch.Tensor, window: int, thresh_value: int, frac_bits: int, min_corr_mag: float, reference_length: int,
-              hysteresis: int):
+              hysteresis: int, max_events: int | None = None):
     """zc_v2 streaming threshold + gate FSM (zc_v2.py:288-336, 360-450) exchanging a bitmask (ofs_zc_detect) -> events per row."""
     rows, m = _rows(corr_mag)
     m = m.contiguous()
     rows, m = _rows(m)
     mstride = (m.shape[1] + 31) // 32
     mask = torch.empty((m.shape[0], mstride), dtype=torch.int32, device=m.device)
-    ev, cnt = _event_buffers(m.shape[0], m.device)
-    L.check(L.lib().ofs_zc_detect(C.byref(rows), int(window), int(thresh_value), int(frac_bits), C.c_double(min_corr_mag),
-                                  int(reference_length), int(hysteresis), _ptr(mask), C.c_int64(mstride), _ptr(ev), _ptr(cnt),
-                                  _stream()), "ofs_zc_detect")
-    return _events_to_numpy(ev, cnt)
+
+    def launch(ev, cnt, cap):
+        L.check(L.lib().ofs_zc_detect(C.byref(rows), int(window), int(thresh_value), int(frac_bits), C.c_double(min_corr_mag),
+                                      int(reference_length), int(hysteresis), _ptr(mask), C.c_int64(mstride), _ptr(ev), _ptr(cnt),
+                                      int(cap), _stream()), "ofs_zc_detect")
+    return _with_event_buffers(m.shape[0], m.device, launch, max_events)
 
 
-def minn_rtl_events(corr_positive: torch.Tensor, valid: torch.Tensor, above: torch.Tensor, hysteresis: int, timing_offset: int):
+def minn_rtl_events(corr_positive: torch.Tensor, valid: torch.Tensor, above: torch.Tensor, hysteresis: int, timing_offset: int,
+                    max_events: int | None = None):
     """minn_rtl.py:750-825 -> events per row (closed == 0 marks an unclosed tail segment)."""
     cp = corr_positive if corr_positive.dim() == 2 else corr_positive[None]
     is_int = cp.dtype == torch.int64
@@ -324,11 +357,11 @@ def minn_rtl_events(corr_positive: torch.Tensor, valid: torch.Tensor, above: tor
     cp = cp.to(_device()).contiguous()
     v = valid.to(device=cp.device, dtype=torch.uint8).reshape(cp.shape).contiguous()
     a = above.to(device=cp.device, dtype=torch.uint8).reshape(cp.shape).contiguous()
-    ev, cnt = _event_buffers(cp.shape[0], cp.device)
-    L.check(L.lib().ofs_minn_rtl_events(_ptr(cp), int(is_int), _ptr(v), _ptr(a), C.c_int64(cp.shape[0]), C.c_int64(cp.shape[1]),
-                                        C.c_int64(cp.shape[1]), int(hysteresis), int(timing_offset), _ptr(ev), _ptr(cnt),
-                                        _stream()), "ofs_minn_rtl_events")
-    return _events_to_numpy(ev, cnt)
+    def launch(ev, cnt, cap):
+        L.check(L.lib().ofs_minn_rtl_events(_ptr(cp), int(is_int), _ptr(v), _ptr(a), C.c_int64(cp.shape[0]), C.c_int64(cp.shape[1]),
+                                            C.c_int64(cp.shape[1]), int(hysteresis), int(timing_offset), _ptr(ev), _ptr(cnt),
+                                            int(cap), _stream()), "ofs_minn_rtl_events")
+    return _with_event_buffers(cp.shape[0], cp.device, launch, max_events)
 
 
 # ------------------------------------------------------------------------------------------- sync pipeline
@@ -413,10 +446,28 @@ class HostSync:
     def run(self, x_host: torch.Tensor, M_host: torch.Tensor | None, records_host: torch.Tensor, *, kind="sc", symbol_len=2048,
             cp_len=512, smooth_win=16, sc_delta=16, gate_threshold=0.5):
         F, n = x_host.shape[0], x_host.shape[1]
-        code = L.OFS_IQ16 if x_host.dtype == torch.int16 else L.OFS_C64
-        out_stride = M_host.stride(0) if M_host is not None else max(n - symbol_len + 1, 0)
+        if x_host.dtype == torch.int16:
+            # int16 IQ [F, n, 2]: ofs_metric_desc strides count SAMPLES (4 bytes each), torch strides count int16 elements
+            if x_host.dim() != 3 or x_host.shape[2] != 2 or x_host.stride(2) != 1 or x_host.stride(1) != 2 or x_host.stride(0) % 2:
+                raise ValueError("int16 IQ host frames must be [frames, n, 2] with interleaved (I, Q) pairs")
+            code, xfs = L.OFS_IQ16, x_host.stride(0) // 2
+        elif x_host.dtype == torch.complex64:
+            if x_host.dim() != 2 or x_host.stride(1) != 1:
+                raise ValueError("complex64 host frames must be [frames, n] with unit sample stride")
+            code, xfs = L.OFS_C64, x_host.stride(0)
+        else:
+            raise TypeError(f"ofs_sync_host takes complex64 or int16 IQ frames, not {x_host.dtype}")
+        out_len = max(n - symbol_len + 1, 0)
+        if F > 1 and xfs < n:
+            raise ValueError("frame stride shorter than a frame")
+        if M_host is not None and (M_host.dtype != torch.float32 or M_host.dim() != 2 or M_host.shape[0] < F or M_host.shape[1] < out_len
+                                   or M_host.stride(1) != 1 or (F > 1 and M_host.stride(0) < out_len)):
+            raise ValueError(f"M_host must be float32 [frames, >= {out_len}] with unit element stride")
+        if records_host.numel() * records_host.element_size() < F * C.sizeof(L.SyncRecord):
+            raise ValueError("records_host too small")
+        out_stride = M_host.stride(0) if M_host is not None else out_len
         d = L.MetricDesc(kind=KINDS[kind], in_dtype=code, out_f64=0, path=L.OFS_PATH_AUTO, symbol_len=symbol_len, n_branches=1,
-                         n_frames=F, n_samples=n, x_frame_stride=x_host.stride(0), x_branch_stride=n, out_stride=out_stride,
+                         n_frames=F, n_samples=n, x_frame_stride=xfs, x_branch_stride=n, out_stride=out_stride,
                          store_mode=0, reserved=0)
         L.check(L.lib().ofs_sync_host(self.ctx, C.byref(d), _ptr(x_host), _ptr(M_host), int(cp_len), int(smooth_win), int(sc_delta),
                                       C.c_double(gate_threshold), _ptr(records_host)), "ofs_sync_host")
@@ -465,7 +516,8 @@ class AADetectPlan:
     M float32 / P complex64 [F, n] + gate events (sync_aa.py:458-568), one pass over the samples."""
 
     def __init__(self, n_frames: int, n_antennas: int, n: int, half_len: int = 512, threshold: float = 0.15,
-                 hysteresis: int = 128, sample_rate: float = 15.36e6, in_dtype: str = "c64", want_r: bool = False):
+                 hysteresis: int = 128, sample_rate: float = 15.36e6, in_dtype: str = "c64", want_r: bool = False,
+                 max_events: int = L.OFS_MAX_EVENTS):
         dev = _device()
         self.F, self.A, self.n, self.Lh = n_frames, n_antennas, n, half_len
         self.thr, self.hyst, self.fs = threshold, hysteresis, sample_rate
@@ -476,7 +528,8 @@ class AADetectPlan:
         self.Rb = torch.empty((n_frames, self.pitch), dtype=torch.float32, device=dev) if want_r else None
         self.mstride = (n + 31) // 32
         self.mask = torch.zeros((n_frames, self.mstride), dtype=torch.int32, device=dev)
-        self.ev, self.cnt, self.records = _event_buffers(n_frames, dev, want_flat=True)   # records: what a rank gathers
+        self.cap = int(max_events)
+        self.ev, self.cnt, self.records = _event_buffers(n_frames, dev, want_flat=True, cap=self.cap)   # records: what a rank gathers
         self.M, self.P = self.Mb[:, :n], self.Pb[:, :n]
         self.R = None if self.Rb is None else self.Rb[:, :n]
 
@@ -485,10 +538,12 @@ class AADetectPlan:
         L.check(L.lib().ofs_aa_detect(_ptr(x), self.code, C.c_int64(self.F), int(self.A), C.c_int64(self.n), C.c_int64(self.A * self.n),
                                       C.c_int64(self.n), int(self.Lh), C.c_double(self.thr), int(self.hyst), C.c_double(self.fs),
                                       _ptr(self.Mb), _ptr(self.Pb), _ptr(self.Rb), C.c_int64(self.pitch), _ptr(self.mask),
-                                      C.c_int64(self.mstride), _ptr(self.ev), _ptr(self.cnt), _stream()), "ofs_aa_detect")
+                                      C.c_int64(self.mstride), _ptr(self.ev), _ptr(self.cnt), int(self.cap), _stream()), "ofs_aa_detect")
 
-    def events(self) -> list[np.ndarray]:
-        return _events_to_numpy(self.ev, self.cnt)
+    def events(self, overflow: str = "raise") -> list[np.ndarray]:
+        """Events of the last run.  A capture with more gates than the plan's max_events slots raises EventOverflow
+        (overflow="truncate": the first max_events, the counts in self.cnt stay true)."""
+        return _events_to_numpy(self.ev, self.cnt, self.cap, overflow)
 
 
 # ------------------------------------------------------------------------------------------- minn_rtl
@@ -543,6 +598,28 @@ def zc_matched_filter(rx, ref, mode: int = 0, out_f64: bool | None = None):
     L.check(L.lib().ofs_zc_matched_filter(_ptr(x), code, C.c_int64(F), int(B), C.c_int64(n), _ptr(r), int(nr), int(mode),
                                           int(out_f64), _ptr(corr), _ptr(mag), C.c_int64(n_out), _stream()), "ofs_zc_matched_filter")
     return corr, mag
+
+
+def zc_normalize(corr, rx, reference):
+    """zc_v2.normalize_correlation (zc_v2.py:257-271) of a caller-supplied correlation: corr (..., n + nr - 1) complex,
+    rx (frames, n) or (n,) one branch -> corr / (||ref|| * sqrt(max(sliding energy, 1e-12))), same dtype as corr."""
+    x, code, _ = to_device(rx)
+    F, B, n = x.shape
+    if B != 1:
+        raise ValueError("normalize_correlation takes one branch")
+    c = corr if isinstance(corr, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(corr))
+    if c.dtype not in (torch.complex64, torch.complex128):
+        c = c.to(torch.complex128)
+    ref = np.asarray(reference)
+    nr = ref.size
+    c = c.to(x.device).reshape(F, -1).contiguous()
+    if c.shape[1] != n + nr - 1:
+        raise ValueError(f"corr has {c.shape[1]} samples per row, expected n + len(reference) - 1 = {n + nr - 1}")
+    o = torch.empty_like(c)
+    ref_norm = float(np.sqrt(np.sum(np.abs(ref) ** 2)))
+    L.check(L.lib().ofs_zc_normalize(_ptr(c), _ptr(x), code, C.c_int64(F), C.c_int64(n), int(nr), C.c_double(ref_norm),
+                                     int(c.dtype == torch.complex128), _ptr(o), C.c_int64(c.shape[1]), _stream()), "ofs_zc_normalize")
+    return o
 
 
 def zc_freq_metric(rx, bin_indices, template_bins, template_energy: float, n_fft: int = 2048, cp: int = 512,

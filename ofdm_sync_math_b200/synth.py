@@ -11,7 +11,7 @@ from pathlib import Path
 import numpy as np
 
 N_FFT, NUM_ACTIVE, CP, PRE_PAD, FS = 2048, 1200, 512, 1337, 30_720_000.0
-_CIR_FIXTURE = Path(__file__).resolve().parent.parent / "tests" / "golden" / "cir.npz"
+_CIR_DATA = Path(__file__).resolve().parent / "data" / "channel_models.npz"
 
 
 def centered_idx(width: int) -> np.ndarray:
@@ -60,8 +60,8 @@ def frame(rng: np.random.Generator, kind: str = "sc") -> np.ndarray:
 
 
 def load_cirs() -> dict:
-    """cir1 / cir2 (2 RX channels x 1100 taps) from the committed fixture (made from channel_models/*.csv)."""
-    d = np.load(_CIR_FIXTURE)
+    """cir1 / cir2 (2 RX channels x 1100 taps) from the package data file data/channel_models.npz (made from the reference's channel_models/*.csv by oracle/gen_golden.py)."""
+    d = np.load(_CIR_DATA)
     return {"cir1": d["cir1"], "cir2": d["cir2"]}
 
 

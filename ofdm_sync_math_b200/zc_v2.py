@@ -61,9 +61,11 @@ def matched_filter_correlation(rx_samples, reference):
 
 
 def normalize_correlation(corr, rx_samples, reference):
-    """corr / (||ref|| * sqrt(max(sliding energy, 1e-12))): recomputed by the mode-1 matched filter of one branch."""
-    as_np = is_numpy_like(rx_samples)
-    c, _ = engine.zc_matched_filter(np.asarray(rx_samples) if as_np else rx_samples, reference, mode=1)
+    """zc_v2.py:257-271: the SUPPLIED corr divided by ||ref|| * sqrt(max(sliding energy of rx_samples, 1e-12)) -- only the
+    normaliser is computed from rx_samples (float64 prefix on the device, ofs_zc_normalize)."""
+    as_np = is_numpy_like(rx_samples) and is_numpy_like(corr)
+    c = engine.zc_normalize(np.asarray(corr) if is_numpy_like(corr) else corr,
+                            np.asarray(rx_samples) if is_numpy_like(rx_samples) else rx_samples, reference)
     return out(c, as_np)
 
 

@@ -343,7 +343,7 @@ def gen_cir_and_scale(out: Path) -> None:
     parity set made with the REAL channel.py / core.apply_cfo: tiled sc.py frames, cir1/cir2 ch1, AWGN, CFO,
     cast to complex64; expected outputs from the unmodified sc.py functions on the cast input."""
     import channel, core, sc
-    np.savez_compressed(out / "cir.npz", cir1=channel.load_measured_cir("cir1"), cir2=channel.load_measured_cir("cir2"))
+    np.savez_compressed(HERE.parent / "ofdm_sync_math_b200" / "data" / "channel_models.npz", cir1=channel.load_measured_cir("cir1"), cir2=channel.load_measured_cir("cir2"))
     n_samples, n_frames = 24576, 4
     xs, Ms, ends = [], [], []
     for f in range(n_frames):

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 20
     missing = [s for s in syms if not hasattr(lib, s)]
     assert not missing, f"declared in ofdmsync.h but not exported: {missing}"
-    assert lib.ofs_version() == 1
+    assert lib.ofs_version() == 2
     assert lib.ofs_chunk_len() == 256
 
 

@@ -50,8 +50,6 @@ def test_rtl_gate_fsm_random_masks(style):
             cp = rng.integers(0, 50, n).astype(np.float64)          # many ties: the RTL rule keeps the LAST maximum
             ev_o, seg_o = orc.detect_minn_rtl(dict(corr_positive=cp, above=above, metric_valid=valid), hysteresis=hyst, timing_offset=-3)
             ev_g = engine.minn_rtl_events(torch.as_tensor(cp), torch.as_tensor(valid), torch.as_tensor(above), hyst, -3)[0]
-            if len(seg_o) > 64:
-                continue                                             # more gates than event slots: covered by the count test below
             seg_g = [(int(e["gate_start"]), int(e["gate_end"])) for e in ev_g]
             assert seg_g == [tuple(s) for s in seg_o.tolist()], (style, n, hyst)
             closed = [e for e in ev_g if e["closed"]]
@@ -73,8 +71,6 @@ def test_zc_gate_fsm_random_masks_batched(style):
             for r in range(rows):
                 st = orc.ZCState(mag[r], np.zeros(n), np.zeros(n), np.zeros(n), above[r], valid[r])
                 ev_o, vals_o, gm_o = orc.detect_zc_peaks(st, 62, hyst)
-                if len(ev_o) >= 64:
-                    continue
                 got = [(int(e["peak_index"]), int(e["gate_start"]), int(e["gate_end"]), int(e["aux"])) for e in ev_g[r]]
                 assert got == [tuple(int(v) for v in row) for row in ev_o.tolist()], (style, n, hyst, r)
                 assert np.array_equal(gm[r].cpu().numpy().astype(bool), gm_o), (style, n, hyst, r)
@@ -82,16 +78,28 @@ def test_zc_gate_fsm_random_masks_batched(style):
 
 
 def test_gate_count_beyond_event_slots():
-    """More gates than OFS_MAX_EVENTS: the count is the true number of gates, the first 64 slots are filled in order."""
+    """More gates than OFS_MAX_EVENTS (the reference's lists are unbounded): the drop-in call repeats with as many slots as the
+    row needs and returns every gate; an explicit max_events is a hard cap that raises instead of cutting the list silently."""
     from ofdm_sync_math_b200 import engine
     n = 64 * 40
     above = np.zeros(n, bool); above[5::20] = True                   # 128 isolated gates with hysteresis 2
     valid = np.ones(n, bool)
     cp = np.arange(n, dtype=np.float64)
     ev_o, seg_o = orc.detect_minn_rtl(dict(corr_positive=cp, above=above, metric_valid=valid), hysteresis=2, timing_offset=0)
-    ev_g = engine.minn_rtl_events(torch.as_tensor(cp), torch.as_tensor(valid), torch.as_tensor(above), 2, 0)[0]
-    assert len(seg_o) == 128 and len(ev_g) == 64
-    assert [(int(e["gate_start"]), int(e["gate_end"])) for e in ev_g] == [tuple(s) for s in seg_o[:64].tolist()]
+    args = (torch.as_tensor(cp), torch.as_tensor(valid), torch.as_tensor(above), 2, 0)
+    ev_g = engine.minn_rtl_events(*args)[0]
+    assert len(seg_o) == 128 and len(ev_g) == 128
+    assert [(int(e["gate_start"]), int(e["gate_end"])) for e in ev_g] == [tuple(s) for s in seg_o.tolist()]
+    assert [int(e["peak_index"]) for e in ev_g if e["closed"]] == [int(r[0]) for r in ev_o]
+    with pytest.raises(engine.EventOverflow) as ei:
+        engine.minn_rtl_events(*args, max_events=64)
+    assert ei.value.needed == 128
+    # zc_v2 and sync_aa FSMs share the buffers: same behaviour through their entry points
+    mag = np.where(above, 1.0, 0.0)
+    ev_z, _ = engine.zc_events(torch.as_tensor(mag), torch.as_tensor(valid), torch.as_tensor(above), 62, 2)
+    st = orc.ZCState(mag, np.zeros(n), np.zeros(n), np.zeros(n), above, valid)
+    ev_zo, _, _ = orc.detect_zc_peaks(st, 62, 2)
+    assert len(ev_zo) > 64 and [int(e["peak_index"]) for e in ev_z[0]] == [int(r[0]) for r in ev_zo]
 
 
 @pytest.mark.parametrize("style", ["sparse", "half", "bursts", "dense", "ones"])

@@ -323,32 +323,55 @@ void ofs_ctx_destroy(ofs_ctx *ctx);
 void *ofs_host_alloc(size_t bytes);  /* pinned */
 void ofs_host_free(void *p);
 
+/* status bits of a sync record (exact mode) */
+#define OFS_ST_EXACT 1       /* a decision lay inside the float32 band and was re-evaluated in float64 from the samples */
+#define OFS_ST_CHANGED 2     /* ... and the float64 evaluation moved the index */
+#define OFS_ST_UNRESOLVED 4  /* a decision inside the band could not be settled in the kernel (more than 64 candidates, or one
+                                of the reference's fallback branches): timing is the float32 decision; ofs_sync_f64 settles it */
+#define OFS_EXACT_BAND 1e-4  /* default relative half-width of the band = the asserted accuracy of the float32 metric */
+
 typedef struct ofs_sync_record {
     int64_t timing;      /* SC: plateau_end; MINN: peak */
     int64_t coarse;      /* SC: max(plateau_end - delta, 0); MINN: peak */
     float metric;        /* M at the timing index */
     float p_re, p_im;    /* P at the coarse/timing index (float64 recompute, stored as float) */
     float cfo;           /* -angle(P)/(2*pi*lag) cycles/sample (lag = N/2 for SC, N/4 for MINN) */
+    int32_t status;      /* OFS_ST_* */
+    int32_t reserved;
 } ofs_sync_record;
+
+typedef struct ofs_sync_params {
+    int32_t cp_len;        /* SC: sc.find_plateau_end_from_metric(M, cp_len, lookahead = cp_len / 4, smooth_win), sc.py:81-146 */
+    int32_t smooth_win;    /* SC: np.convolve "same" window; MINN: trailing average (minn.py:115-128) */
+    int32_t sc_delta;      /* SC: coarse = max(plateau_end - delta, 0), sc.py:211 */
+    int32_t exact;         /* 0: decide on the float32 metric.  1: every comparison of the detector whose operands lie within
+                              exact_band of each other is re-evaluated in float64 from the samples, so that timing equals the
+                              index the reference finds on its float64 metric (status says when that happened) */
+    double gate_threshold; /* MINN: minn.find_minn_peak gate_threshold, minn.py:131-205 */
+    double exact_band;     /* <= 0: OFS_EXACT_BAND */
+} ofs_sync_params;
 
 /* One call = "sync metric + CFO" for a batch of frames (the BASELINE.json headline):
  *   metric (ofs_metric, stripe path) -> detector (SC: plateau, MINN: find_minn_peak) -> P at the
- *   detected index -> CFO.  Device version: x, M, records are device pointers. */
+ *   detected index -> CFO.  Device version: x, M, records are device pointers; branches are summed (sc.py:73-74).
+ *   scratch: int64[4 * n_frames]. */
 int ofs_sync(const ofs_metric_desc *d, const void *x, float *M, float *chunk_max, int64_t cm_stride,
-             int32_t cp_len, int32_t smooth_win, int32_t sc_delta, double gate_threshold,
-             ofs_sync_record *records, int64_t *scratch /* int64[3*n_frames] */, void *stream);
+             const ofs_sync_params *params, ofs_sync_record *records, int64_t *scratch, void *stream);
 /* Second half of ofs_sync alone (detector + P/CFO records on an already computed metric). */
 int ofs_sync_detect(const ofs_metric_desc *d, const void *x, const float *M, const float *chunk_max, int64_t cm_stride,
-                    int32_t cp_len, int32_t smooth_win, int32_t sc_delta, double gate_threshold,
-                    ofs_sync_record *records, int64_t *scratch, void *stream);
-/* Host version: x_host (n_frames x n_samples, dtype per d->in_dtype), M_host optional (float32
+                    const ofs_sync_params *params, ofs_sync_record *records, int64_t *scratch, void *stream);
+/* The same pipeline entirely in float64 (precise tile kernel with float64 outputs -> float64 detector -> records), any branch
+ * count / dtype / symbol length: the path frames flagged OFS_ST_UNRESOLVED are re-run through.  Workspace (8 bytes per output)
+ * comes from the stream's memory pool.  records: device pointer, status = OFS_ST_EXACT. */
+int ofs_sync_f64(const ofs_metric_desc *d, const void *x, const ofs_sync_params *params, ofs_sync_record *records, void *stream);
+/* Host version: x_host (n_frames x n_samples, dtype per d->in_dtype; x_frame_stride in SAMPLES), M_host optional (float32
  * [n_frames][out_stride]); records_host[n_frames].  Frames are pipelined through the ctx workspace
  * in batches (H2D, kernels, D2H overlapped on three streams, two buffer sets).  A batch holds 32 MB of
  * samples (environment variable OFS_HOST_BATCH_MB overrides, 1..4096); pinned host memory (ofs_host_alloc)
- * is what lets the copies run asynchronously.  M_host == NULL: only the records come back. */
+ * is what lets the copies run asynchronously.  M_host == NULL: only the records come back.  With params->exact, frames the
+ * kernels flag OFS_ST_UNRESOLVED are re-run through ofs_sync_f64 before the call returns. */
 int ofs_sync_host(ofs_ctx *ctx, const ofs_metric_desc *d, const void *x_host, float *M_host,
-                  int32_t cp_len, int32_t smooth_win, int32_t sc_delta, double gate_threshold,
-                  ofs_sync_record *records_host);
+                  const ofs_sync_params *params, ofs_sync_record *records_host);
 /* kernels launched by this library on the calling thread since load (for bench.py's gpu_launches) */
 int64_t ofs_launch_count(void);
 

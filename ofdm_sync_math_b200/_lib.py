@@ -38,7 +38,16 @@ class Event(C.Structure):
 
 class SyncRecord(C.Structure):
     _fields_ = [("timing", i64), ("coarse", i64), ("metric", C.c_float), ("p_re", C.c_float),
-                ("p_im", C.c_float), ("cfo", C.c_float)]
+                ("p_im", C.c_float), ("cfo", C.c_float), ("status", i32), ("reserved", i32)]
+
+
+class SyncParams(C.Structure):
+    _fields_ = [("cp_len", i32), ("smooth_win", i32), ("sc_delta", i32), ("exact", i32), ("gate_threshold", f64),
+                ("exact_band", f64)]
+
+
+OFS_ST_EXACT, OFS_ST_CHANGED, OFS_ST_UNRESOLVED = 1, 2, 4
+OFS_EXACT_BAND = 1e-4
 
 
 class OfsError(RuntimeError):

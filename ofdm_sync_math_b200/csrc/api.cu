@@ -2,6 +2,7 @@
 // end-to-end "sync metric + CFO" pipeline (device and host-buffer versions).
 #include <cstdlib>
 #include "common.cuh"
+#include "exact.cuh"
 #include <string.h>
 #include <new>
 
@@ -58,6 +59,11 @@ int launch_metric_tile(const ofs_metric_desc *d, const void *x, void *M, void *P
 int launch_metric_stripe(const ofs_metric_desc *d, const void *x, float *M, void *P, float *R, float *chunk_max, int64_t cm_stride,
                          cudaStream_t stream);
 bool stripe_supported(const ofs_metric_desc *d);
+int launch_plateau(const ofs_rows *M, const float *chunk_max, int64_t cm_stride, int32_t toff, int32_t cp_len, int32_t lookahead,
+                   int32_t smooth_win, int64_t *plateau_end, const ExactSrc *ex, int32_t *status, void *stream);
+int launch_minn_peak(const ofs_rows *M, const float *chunk_max, int64_t cm_stride, int32_t toff, int32_t smooth_win,
+                     double gate_threshold, int32_t has_bounds, int64_t bound_lo, int64_t bound_hi, int64_t *peak,
+                     int64_t *gate_span, void *Ms, const ExactSrc *ex, int32_t *status, void *stream);
 bool array_supported(int in_dtype, int64_t n, int64_t xfs, int64_t xbs, int L, const void *x);
 int launch_metric_array(const void *x, int in_dtype, int64_t n_frames, int n_ant, int64_t n, int64_t xfs, int64_t xbs, int L,
                         float *M, void *P, float *R, int64_t out_stride, unsigned *mask, int64_t mask_stride, double thr,
@@ -78,9 +84,9 @@ static int check_desc(const ofs_metric_desc *d, const char *who)
 }
 
 // ---- P at one index per frame, in float64, + record (one warp per frame) -------------------------
-__global__ void sync_record_kernel(const void *x, int dtype, int64_t L, int64_t xfs, int kind, int N,
-                                   const float *M, int64_t out_stride, int64_t out_len, const int64_t *timing,
-                                   int sc_delta, ofs_sync_record *rec, int64_t n_frames)
+__global__ void sync_record_kernel(const void *x, int dtype, int64_t L, int64_t xfs, int64_t xbs, int nb, int kind, int N,
+                                   const float *M, const double *M64, int64_t out_stride, int64_t out_len, const int64_t *timing,
+                                   const int32_t *status, int status_or, int sc_delta, ofs_sync_record *rec, int64_t n_frames)
 {
     const int64_t frame = (int64_t)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -91,18 +97,20 @@ __global__ void sync_record_kernel(const void *x, int dtype, int64_t L, int64_t 
     if (coarse > out_len - 1) coarse = out_len - 1;
     if (coarse < 0) coarse = 0;
     const size_t esz = dtype == OFS_C64 ? 8 : (dtype == OFS_C128 ? 16 : 4);
-    const void *xr = reinterpret_cast<const unsigned char *>(x) + (size_t)frame * xfs * esz;
     double pr = 0.0, pi = 0.0;
     const int lag = kind == OFS_MINN ? N / 4 : N / 2;
     const int nwin = kind == OFS_MINN ? 2 : 1;
-    for (int wdw = 0; wdw < nwin; ++wdw) {
-        const int64_t base = coarse + (int64_t)wdw * 2 * lag;
+    for (int b = 0; b < nb; ++b) {                                            // branches summed (sc.py:73-74)
+        const void *xr = reinterpret_cast<const unsigned char *>(x) + ((size_t)frame * xfs + (size_t)b * xbs) * esz;
+        for (int wdw = 0; wdw < nwin; ++wdw) {
+            const int64_t base = coarse + (int64_t)wdw * 2 * lag;
 #pragma unroll 8
-        for (int m = lane; m < lag; m += 32) {      // 8 independent sample pairs in flight per lane (the loop is pure load latency)
-            const double2 a = load_sample_f64(xr, dtype, base + m);
-            const double2 b = load_sample_f64(xr, dtype, base + lag + m);
-            pr += a.x * b.x + a.y * b.y;
-            pi += a.y * b.x - a.x * b.y;
+            for (int m = lane; m < lag; m += 32) {      // 8 independent sample pairs in flight per lane (the loop is pure load latency)
+                const double2 a = load_sample_f64(xr, dtype, base + m);
+                const double2 c = load_sample_f64(xr, dtype, base + lag + m);
+                pr += a.x * c.x + a.y * c.y;
+                pi += a.y * c.x - a.x * c.y;
+            }
         }
     }
 #pragma unroll
@@ -110,11 +118,22 @@ __global__ void sync_record_kernel(const void *x, int dtype, int64_t L, int64_t 
     if (lane == 0) {
         ofs_sync_record r;
         r.timing = t; r.coarse = coarse;
-        r.metric = M ? M[frame * out_stride + coarse] : 0.f;
+        r.metric = M ? M[frame * out_stride + coarse] : (M64 ? (float)M64[frame * out_stride + coarse] : 0.f);
         r.p_re = (float)pr; r.p_im = (float)pi;
         r.cfo = (float)(-atan2(pi, pr) / (2.0 * 3.14159265358979323846 * (double)lag));
+        r.status = (status ? status[frame] : 0) | status_or;
+        r.reserved = 0;
         rec[frame] = r;
     }
+}
+
+static int check_sync_params(const ofs_sync_params *sp, const char *who)
+{
+    OFS_REQUIRE(sp, "%s: null parameters", who);
+    OFS_REQUIRE(sp->cp_len >= 0 && sp->smooth_win >= 0 && sp->sc_delta >= 0, "%s: negative detector parameter", who);
+    OFS_REQUIRE(sp->exact == 0 || sp->exact == 1, "%s: exact must be 0 or 1", who);
+    OFS_REQUIRE(!(sp->exact_band > 0.01), "%s: exact_band must be <= 0.01", who);
+    return OFS_OK;
 }
 
 }  // namespace ofs
@@ -184,44 +203,91 @@ OFS_API int ofs_metric(const ofs_metric_desc *d, const void *x, void *M, void *P
 }
 
 OFS_API int ofs_sync_detect(const ofs_metric_desc *d, const void *x, const float *M, const float *chunk_max,
-                            int64_t cm_stride, int32_t cp_len, int32_t smooth_win, int32_t sc_delta, double gate_threshold,
-                            ofs_sync_record *records, int64_t *scratch, void *stream)
+                            int64_t cm_stride, const ofs_sync_params *sp, ofs_sync_record *records, int64_t *scratch,
+                            void *stream)
 {
     if (int rc = check_desc(d, "ofs_sync_detect")) return rc;
+    if (int rc = check_sync_params(sp, "ofs_sync_detect")) return rc;
     OFS_REQUIRE(d->kind == OFS_SC || d->kind == OFS_SC_BOTH || d->kind == OFS_MINN, "ofs_sync: kind must be SC or MINN");
     OFS_REQUIRE(x && M && records && scratch, "ofs_sync: null argument");
-    OFS_REQUIRE(d->n_branches == 1, "ofs_sync: one branch per frame");
     const int64_t out_len = ofs_metric_out_len(d);
     OFS_REQUIRE(out_len > 0, "ofs_sync: frames shorter than one symbol");
     if (d->n_frames == 0) return OFS_OK;
     ofs_rows rows{M, 0, 0, d->n_frames, out_len, d->out_stride};
     int64_t *timing = scratch;
+    int32_t *status = reinterpret_cast<int32_t *>(scratch + 3 * d->n_frames);
     const int toff = d->symbol_len - 1;
+    ExactSrc ex{};
+    if (sp->exact) {
+        ex.x = x; ex.dtype = d->in_dtype; ex.kind = d->kind; ex.N = d->symbol_len; ex.nb = d->n_branches;
+        ex.L = d->n_samples; ex.xfs = d->x_frame_stride; ex.xbs = d->x_branch_stride;
+        ex.band = sp->exact_band > 0.0 ? sp->exact_band : OFS_EXACT_BAND;
+    }
     if (d->kind == OFS_MINN) {
-        if (int rc = ofs_find_minn_peak_pruned(&rows, chunk_max, cm_stride, toff, smooth_win, gate_threshold, 0, 0, 0, timing,
-                                               scratch + d->n_frames, nullptr, stream))
+        if (int rc = launch_minn_peak(&rows, chunk_max, cm_stride, toff, sp->smooth_win, sp->gate_threshold, 0, 0, 0, timing,
+                                      scratch + d->n_frames, nullptr, sp->exact ? &ex : nullptr, status, stream))
             return rc;
     } else {
-        if (int rc = ofs_find_plateau_end_pruned(&rows, chunk_max, cm_stride, toff, cp_len, cp_len / 4, smooth_win, timing, stream))
+        if (int rc = launch_plateau(&rows, chunk_max, cm_stride, toff, sp->cp_len, sp->cp_len / 4, sp->smooth_win, timing,
+                                    sp->exact ? &ex : nullptr, status, stream))
             return rc;
     }
     const int wpb = 4;
     sync_record_kernel<<<(unsigned)((d->n_frames + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
-        x, d->in_dtype, d->n_samples, d->x_frame_stride, d->kind, d->symbol_len, M, d->out_stride, out_len, timing,
-        sc_delta, records, d->n_frames);
+        x, d->in_dtype, d->n_samples, d->x_frame_stride, d->x_branch_stride, d->n_branches, d->kind, d->symbol_len, M, nullptr,
+        d->out_stride, out_len, timing, status, 0, sp->sc_delta, records, d->n_frames);
     return check_launch("sync_record_kernel");
 }
 
+// The same pipeline entirely in float64 (tile metric kernel with float64 outputs -> float64 detector -> records): what a frame
+// flagged OFS_ST_UNRESOLVED is re-run through, and the yardstick of the exact mode in the tests.  Workspace from the stream's pool.
+OFS_API int ofs_sync_f64(const ofs_metric_desc *d, const void *x, const ofs_sync_params *sp, ofs_sync_record *records, void *stream_)
+{
+    if (int rc = check_desc(d, "ofs_sync_f64")) return rc;
+    if (int rc = check_sync_params(sp, "ofs_sync_f64")) return rc;
+    OFS_REQUIRE(d->kind == OFS_SC || d->kind == OFS_SC_BOTH || d->kind == OFS_MINN, "ofs_sync_f64: kind must be SC or MINN");
+    OFS_REQUIRE(x && records, "ofs_sync_f64: null argument");
+    const int64_t out_len = ofs_metric_out_len(d);
+    OFS_REQUIRE(out_len > 0, "ofs_sync_f64: frames shorter than one symbol");
+    if (d->n_frames == 0) return OFS_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    keep_pool_cached();
+    double *M64 = nullptr;
+    int64_t *scratch = nullptr;
+    OFS_CUDA(cudaMallocAsync((void **)&M64, (size_t)d->n_frames * out_len * sizeof(double), stream));
+    OFS_CUDA(cudaMallocAsync((void **)&scratch, (size_t)d->n_frames * 3 * sizeof(int64_t), stream));
+    ofs_metric_desc dd = *d;
+    dd.out_f64 = 1; dd.out_stride = out_len; dd.path = OFS_PATH_TILE;
+    int rc = launch_metric_tile(&dd, x, M64, nullptr, nullptr, stream);
+    ofs_rows rows{M64, 1, 0, d->n_frames, out_len, out_len};
+    if (!rc) {
+        if (d->kind == OFS_MINN)
+            rc = launch_minn_peak(&rows, nullptr, 0, 0, sp->smooth_win, sp->gate_threshold, 0, 0, 0, scratch, scratch + d->n_frames,
+                                  nullptr, nullptr, nullptr, stream_);
+        else
+            rc = launch_plateau(&rows, nullptr, 0, 0, sp->cp_len, sp->cp_len / 4, sp->smooth_win, scratch, nullptr, nullptr, stream_);
+    }
+    if (!rc) {
+        const int wpb = 4;
+        sync_record_kernel<<<(unsigned)((d->n_frames + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+            x, d->in_dtype, d->n_samples, d->x_frame_stride, d->x_branch_stride, d->n_branches, d->kind, d->symbol_len, nullptr, M64,
+            out_len, out_len, scratch, nullptr, OFS_ST_EXACT, sp->sc_delta, records, d->n_frames);
+        rc = check_launch("sync_record_kernel");
+    }
+    OFS_CUDA(cudaFreeAsync(M64, stream));
+    OFS_CUDA(cudaFreeAsync(scratch, stream));
+    return rc;
+}
+
 OFS_API int ofs_sync(const ofs_metric_desc *d, const void *x, float *M, float *chunk_max, int64_t cm_stride,
-                     int32_t cp_len, int32_t smooth_win, int32_t sc_delta, double gate_threshold,
-                     ofs_sync_record *records, int64_t *scratch, void *stream)
+                     const ofs_sync_params *sp, ofs_sync_record *records, int64_t *scratch, void *stream)
 {
     if (int rc = check_desc(d, "ofs_sync")) return rc;
     OFS_REQUIRE(x && M && records && scratch, "ofs_sync: null argument");
     OFS_REQUIRE(d->out_f64 == 0, "ofs_sync: float32 metric only");
     if (d->n_frames == 0) return OFS_OK;
     if (int rc = ofs_metric(d, x, M, nullptr, nullptr, chunk_max, cm_stride, stream)) return rc;
-    return ofs_sync_detect(d, x, M, chunk_max, cm_stride, cp_len, smooth_win, sc_delta, gate_threshold, records, scratch, stream);
+    return ofs_sync_detect(d, x, M, chunk_max, cm_stride, sp, records, scratch, stream);
 }
 
 // ---- host-buffer pipeline -------------------------------------------------------------------------
@@ -285,13 +351,16 @@ OFS_API void *ofs_host_alloc(size_t bytes)
 }
 OFS_API void ofs_host_free(void *p) { if (p) cudaFreeHost(p); }
 
-OFS_API int ofs_sync_host(ofs_ctx *c, const ofs_metric_desc *d, const void *x_host, float *M_host, int32_t cp_len,
-                          int32_t smooth_win, int32_t sc_delta, double gate_threshold, ofs_sync_record *records_host)
+OFS_API int ofs_sync_host(ofs_ctx *c, const ofs_metric_desc *d, const void *x_host, float *M_host, const ofs_sync_params *sp,
+                          ofs_sync_record *records_host)
 {
     OFS_REQUIRE(c, "ofs_sync_host: null context");
     if (int rc = check_desc(d, "ofs_sync_host")) return rc;
+    if (int rc = check_sync_params(sp, "ofs_sync_host")) return rc;
     OFS_REQUIRE(x_host && records_host, "ofs_sync_host: null argument");
     OFS_REQUIRE(d->n_branches == 1, "ofs_sync_host: one branch per frame");
+    OFS_REQUIRE(d->x_frame_stride >= d->n_samples || d->n_frames <= 1, "ofs_sync_host: frame stride (in samples) < n_samples");
+    OFS_REQUIRE(!M_host || d->out_stride >= ofs_metric_out_len(d), "ofs_sync_host: out_stride < out_len");
     const int64_t out_len = ofs_metric_out_len(d);
     OFS_REQUIRE(out_len > 0, "ofs_sync_host: frames shorter than one symbol");
     if (d->n_frames == 0) return OFS_OK;
@@ -321,7 +390,7 @@ OFS_API int ofs_sync_host(ofs_ctx *c, const ofs_metric_desc *d, const void *x_ho
             OFS_CUDA(cudaMalloc((void **)&c->m_dev[i], m_need));
             OFS_CUDA(cudaMalloc((void **)&c->cm_dev[i], cm_need));
             OFS_CUDA(cudaMalloc((void **)&c->rec_dev[i], rec_need * sizeof(ofs_sync_record)));
-            OFS_CUDA(cudaMalloc((void **)&c->scratch[i], rec_need * 3 * sizeof(int64_t)));
+            OFS_CUDA(cudaMalloc((void **)&c->scratch[i], rec_need * 4 * sizeof(int64_t)));
         }
         c->x_cap = x_need; c->m_cap = m_need; c->cm_cap = cm_need; c->rec_cap = rec_need;
     }
@@ -340,8 +409,7 @@ OFS_API int ofs_sync_host(ofs_ctx *c, const ofs_metric_desc *d, const void *x_ho
         ofs_metric_desc dd = *d;
         dd.n_frames = nf; dd.x_frame_stride = xpitch; dd.out_stride = mpitch; dd.path = OFS_PATH_AUTO;
         float *Md0 = c->m_dev[s] + toff;      // element d = 0 of frame 0; (Md0 - toff) is 256-byte aligned
-        if (int rc = ofs_sync(&dd, c->x_dev[s], Md0, c->cm_dev[s], cmpitch, cp_len, smooth_win, sc_delta, gate_threshold,
-                              c->rec_dev[s], c->scratch[s], c->s_comp))
+        if (int rc = ofs_sync(&dd, c->x_dev[s], Md0, c->cm_dev[s], cmpitch, sp, c->rec_dev[s], c->scratch[s], c->s_comp))
             return rc;
         OFS_CUDA(cudaEventRecord(c->ev_comp[s], c->s_comp));
         OFS_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_comp[s], 0));
@@ -355,5 +423,19 @@ OFS_API int ofs_sync_host(ofs_ctx *c, const ofs_metric_desc *d, const void *x_ho
     }
     OFS_CUDA(cudaStreamSynchronize(c->s_d2h));
     OFS_CUDA(cudaStreamSynchronize(c->s_comp));
+    // frames whose decision the kernels could not settle inside the float32 band: once more through the float64 pipeline
+    // (rare -- a flat-topped or noiseless metric; the metric row M_host stays the float32 one)
+    if (sp->exact) {
+        for (int64_t f = 0; f < d->n_frames; ++f) {
+            if (!(records_host[f].status & OFS_ST_UNRESOLVED)) continue;
+            OFS_CUDA(cudaMemcpyAsync(c->x_dev[0], (const unsigned char *)x_host + (size_t)f * d->x_frame_stride * esz, (size_t)L * esz,
+                                     cudaMemcpyHostToDevice, c->s_comp));
+            ofs_metric_desc d1 = *d;
+            d1.n_frames = 1; d1.x_frame_stride = L; d1.x_branch_stride = L;
+            if (int rc = ofs_sync_f64(&d1, c->x_dev[0], sp, c->rec_dev[0], c->s_comp)) return rc;
+            OFS_CUDA(cudaMemcpyAsync(records_host + f, c->rec_dev[0], sizeof(ofs_sync_record), cudaMemcpyDeviceToHost, c->s_comp));
+            OFS_CUDA(cudaStreamSynchronize(c->s_comp));
+        }
+    }
     return OFS_OK;
 }

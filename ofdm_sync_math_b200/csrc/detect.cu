@@ -13,6 +13,7 @@
 // hysteresis; it closes at (last above) + H; the peak is a block-parallel arg-max over
 // [open, close] with the reference's tie rule (first max for `>`, last max for `>=`).
 #include "common.cuh"
+#include "exact.cuh"
 
 namespace ofs {
 
@@ -314,15 +315,84 @@ struct SmoothSame {   // np.convolve(M, ones(w)/w, "same")[i], sc.py:100
     }
 };
 
+// Collect every index i < n_out with fn(i) >= lvl into sc.idx (ascending order is NOT guaranteed), through the same chunk
+// pruning and 8-groups as pruned_argmax.  Returns the number found (may exceed EXCAP: then the list is incomplete).
+template <typename F>
+__device__ int collect_at_least(const F &fn, int64_t n_out, const Prune &pr, double lvl, ExactScratch &sc)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nchi = (int)((n_out + pr.toff + 255) / 256);
+    if (tid == 0) sc.cnt = 0;
+    __syncthreads();
+    double v8[8];
+    for (int c0 = warp * 32; c0 < nchi; c0 += (int)blockDim.x) {
+        const int cl = c0 + lane;
+        const bool pass = cl < nchi && (pr.cm == nullptr || (double)pr.bound(cl) >= lvl);
+        unsigned m = __ballot_sync(0xffffffffu, pass);
+        while (m) {
+            const int c = c0 + __ffs(m) - 1;
+            m &= m - 1;
+            const int64_t i0 = (int64_t)c * 256 - pr.toff + 8 * lane;
+            fn.eval8(i0, v8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (i0 + k >= 0 && i0 + k < n_out && v8[k] >= lvl) {
+                    const int slot = atomicAdd(&sc.cnt, 1);
+                    if (slot < EXCAP) sc.idx[slot] = i0 + k;
+                }
+        }
+    }
+    __syncthreads();
+    return sc.cnt;
+}
+// same over an index range [lo, hi)
+template <typename F>
+__device__ int collect_range_at_least(const F &fn, int64_t lo, int64_t hi, int toff, double lvl, ExactScratch &sc)
+{
+    if (threadIdx.x == 0) sc.cnt = 0;
+    __syncthreads();
+    double v8[8];
+    const int64_t g0 = lo - (((lo + toff) % 8) + 8) % 8;
+    for (int64_t i0 = g0 + 8LL * threadIdx.x; i0 < hi; i0 += 8LL * blockDim.x) {
+        fn.eval8(i0, v8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (i0 + k >= lo && i0 + k < hi && v8[k] >= lvl) {
+                const int slot = atomicAdd(&sc.cnt, 1);
+                if (slot < EXCAP) sc.idx[slot] = i0 + k;
+            }
+    }
+    __syncthreads();
+    return sc.cnt;
+}
+// first maximum of the re-evaluated list (cnt <= EXCAP entries, evaluated by exact_eval_list); every thread gets the result
+__device__ __forceinline__ ArgVal exact_list_argmax(const ExactScratch &sc, int cnt)
+{
+    ArgVal b{0.0, -1};
+    for (int k = 0; k < cnt; ++k) {
+        const double v = sc.val[k];
+        const long long i = sc.idx[k];
+        if (b.i < 0 || v > b.v || (v == b.v && i < b.i)) { b.v = v; b.i = i; }
+    }
+    return b;
+}
+
+// ex.x != nullptr (fused sync pipeline, float32 rows from the stripe kernel): decisions whose operands lie within ex.band of
+// each other are re-evaluated in float64 from the samples (exact.cuh), so the index equals the one the reference finds on its
+// float64 metric; status[row] reports what happened (OFS_ST_*).
 template <bool F64>
 __global__ void __launch_bounds__(DNT, F64 ? 2 : 3) plateau_kernel(RowView r, int cp_len, int lookahead, int smooth_win,
-                                                      int64_t *out, const float *cm, int64_t cm_stride, int toff)
+                                                      int64_t *out, const float *cm, int64_t cm_stride, int toff,
+                                                      const __grid_constant__ ExactSrc ex, int32_t *status)
 {
     __shared__ ArgVal sh_av[DNT / 32];
     __shared__ long long sh_i[DNT / 32];
+    __shared__ ExactScratch sc;
     const int64_t row = blockIdx.x;
     const int tid = threadIdx.x;
-    if (r.n == 0) { if (tid == 0) out[row] = 0; return; }
+    int st = 0;
+    auto finish = [&](long long v) { if (tid == 0) { out[row] = v; if (status) status[row] = st; } };
+    if (r.n == 0) { finish(0); return; }
     const int Lk = lookahead < 0 ? cp_len / 4 : (lookahead > 1 ? lookahead : 1);
     const int w = smooth_win > 1 ? smooth_win : 1;
     SmoothSame Ms;
@@ -338,38 +408,103 @@ __global__ void __launch_bounds__(DNT, F64 ? 2 : 3) plateau_kernel(RowView r, in
     Prune pr{(cm && r.n > w) ? cm + row * cm_stride : nullptr, cm_stride, toff, (w - 1 - Ms.off + 255) / 256, (Ms.off + 255) / 256};
     pr.stage(cm_s, (ms + toff + 255) / 256);
     ArgVal best = pruned_argmax(Ms, ms, pr, sh_av);
-    const int64_t center = best.i;
-    const double peak = best.v;
+    int64_t center = best.i;
+    double peak = best.v;
+    const bool exact_on = !F64 && ex.x != nullptr && r.n > w && w <= 32 && peak > 0.0;
+    const int woff = Ms.off;
+    auto exact_ms = [&](long long i) { return exact_smooth_same(ex, row, i, w, woff); };
+    bool peak_exact = false;
+    if (exact_on) {
+        // every index whose float32 value is within the band of the float32 maximum can be the float64 maximum
+        const int cnt = collect_at_least(Ms, ms, pr, peak * (1.0 - ex.band), sc);
+        if (cnt > EXCAP) st |= OFS_ST_UNRESOLVED;
+        else if (cnt > 1) {
+            exact_eval_list(sc, cnt, exact_ms);
+            const ArgVal b = exact_list_argmax(sc, cnt);
+            st |= OFS_ST_EXACT | (b.i != center ? OFS_ST_CHANGED : 0);
+            center = b.i; peak = b.v; peak_exact = true;
+            __syncthreads();
+        }
+    }
 
     // pass B: first index in [center, center+cp) at or below 95 % of the maximum (sc.py:107-114)
     const int64_t post_hi = ms < center + cp_len ? ms : center + cp_len;
     if (post_hi > center + 1) {
         const double thr = 0.95 * peak;
-        long long first = LLONG_MAX;
+        // float32 value v, float64 value V: v <= thr_def  =>  V <= 0.95 peak64;  v > thr_unc  =>  V > 0.95 peak64
+        const double bw = exact_on ? (peak_exact ? ex.band : 2.0 * ex.band) : 0.0;
+        const double thr_def = thr * (1.0 - bw), thr_unc = thr * (1.0 + bw);
+        long long first = LLONG_MAX, first32 = LLONG_MAX;
+        if (exact_on) { if (tid == 0) sc.cnt = 0; __syncthreads(); }
         {
             double v8[8];
             const int64_t g0 = center - (((center + Ms.toff) % 8) + 8) % 8;
             for (int64_t i0 = g0 + 8LL * tid; i0 < post_hi && first == LLONG_MAX; i0 += 8LL * DNT) {
                 Ms.eval8(i0, v8);
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (first == LLONG_MAX && i0 + k >= center && i0 + k < post_hi && v8[k] <= thr) first = i0 + k;
+                for (int k = 0; k < 8; ++k) {
+                    if (i0 + k < center || i0 + k >= post_hi) continue;
+                    if (first32 == LLONG_MAX && v8[k] <= thr) first32 = i0 + k;
+                    if (first == LLONG_MAX) {
+                        if (v8[k] <= thr_def) first = i0 + k;
+                        else if (v8[k] <= thr_unc) {            // inside the band: float64 decides
+                            const int slot = atomicAdd(&sc.cnt, 1);
+                            if (slot < EXCAP) sc.idx[slot] = i0 + k;
+                        }
+                    }
+                }
             }
         }
         first = block_min_i64(first, sh_i);
-        if (first != LLONG_MAX) { if (tid == 0) out[row] = first; return; }
+        if (exact_on) {
+            first32 = block_min_i64(first32, sh_i);
+            const int cnt = sc.cnt;                            // (block_min_i64 has synchronised the block)
+            // only in-band indices BEFORE the first certain one matter
+            bool any = false;
+            for (int k = 0; k < cnt && k < EXCAP; ++k) any |= sc.idx[k] < first;
+            if (cnt >= EXCAP) { st |= OFS_ST_UNRESOLVED; first = first32; }
+            else if (any) {
+                __syncthreads();
+                if (tid == 0) {                                 // drop the ones behind `first`, append the centre (for peak64)
+                    int q = 0;
+                    for (int k = 0; k < cnt; ++k) if (sc.idx[k] < first) sc.idx[q++] = sc.idx[k];
+                    if (!peak_exact && q < EXCAP) sc.idx[q++] = -1 - center;      // tagged: not a candidate
+                    sc.cnt = q;
+                }
+                __syncthreads();
+                const int q = sc.cnt;
+                exact_eval_list(sc, q, [&](long long i) { return exact_ms(i < 0 ? -1 - i : i); });
+                double pk64 = peak;
+                for (int k = 0; k < q; ++k) if (sc.idx[k] < 0) pk64 = sc.val[k];
+                const double thr64 = 0.95 * pk64;
+                long long fx = first;
+                for (int k = 0; k < q; ++k) if (sc.idx[k] >= 0 && sc.val[k] <= thr64 && sc.idx[k] < fx) fx = sc.idx[k];
+                st |= OFS_ST_EXACT | (fx != first32 ? OFS_ST_CHANGED : 0);
+                first = fx;
+                __syncthreads();
+            }
+        }
+        if (first != LLONG_MAX) { finish(first); return; }
     }
+    // the remaining paths are the reference's fallbacks (no sample within cp_len of the maximum drops below 95 %): rare, and
+    // their decisions are not re-evaluated here -- a row that gets this far with the exact mode on is reported as unresolved
+    // unless nothing it compares lies inside the band.
+    const double bwc = exact_on ? 2.0 * ex.band : 0.0;
 
     // pass C: right edge of the earliest run >= 60 % of the peak with length >= max(8, cp/2) (sc.py:117-133)
     if (peak > 0.0) {
         const double thr = 0.6 * peak;
         const int64_t min_run = cp_len / 2 > 8 ? cp_len / 2 : 8;
         __shared__ long long sh_res;
+        __shared__ int sh_unc;
         if (tid < 32) {                      // warp 0 walks the row, 32 flags per step
             long long res = -1, run_start = -1;
+            unsigned unc = 0u;
             for (int64_t base = 0; base < ms && res < 0; base += 32) {
                 const int64_t i = base + tid;
-                const bool f = i < ms && Ms(i) >= thr;
+                const double v = i < ms ? Ms(i) : 0.0;
+                const bool f = i < ms && v >= thr;
+                unc |= __ballot_sync(0xffffffffu, i < ms && fabs(v - thr) <= bwc * thr);
                 const unsigned m = __ballot_sync(0xffffffffu, f);
                 const int nbits = (int)(ms - base < 32 ? ms - base : 32);
                 if (m == 0u) {
@@ -388,14 +523,16 @@ __global__ void __launch_bounds__(DNT, F64 ? 2 : 3) plateau_kernel(RowView r, in
                 }
             }
             if (res < 0 && run_start >= 0 && ms - run_start >= min_run) res = ms - 1;
-            if (tid == 0) sh_res = res;
+            if (tid == 0) { sh_res = res; sh_unc = (exact_on && unc != 0u) ? 1 : 0; }
         }
         __syncthreads();
-        if (sh_res >= 0) { if (tid == 0) out[row] = sh_res; return; }
+        if (sh_unc) st |= OFS_ST_UNRESOLVED;
+        if (sh_res >= 0) { finish(sh_res); return; }
     }
 
     // pass D: largest drop over the lookahead around the strongest plateau (sc.py:136-146)
     {
+        if (exact_on) st |= OFS_ST_UNRESOLVED;     // an arg-max of differences: not re-evaluated (never seen on real frames)
         const int64_t lo = center - cp_len > 0 ? center - cp_len : 0;
         const int64_t hi = ms - Lk - 1 < center + cp_len ? ms - Lk - 1 : center + cp_len;
         int64_t hi_eff = hi;                       // python slice semantics for a negative stop
@@ -408,14 +545,14 @@ __global__ void __launch_bounds__(DNT, F64 ? 2 : 3) plateau_kernel(RowView r, in
         if (hi2 > ms) hi2 = ms;
         if (lo2 > ms) lo2 = ms;
         const int64_t wl = hi_eff - lo, al = hi2 - lo2;
-        if (wl <= 0 || al <= 0 || wl != al) { if (tid == 0) out[row] = center; return; }
+        if (wl <= 0 || al <= 0 || wl != al) { finish(center); return; }
         ArgVal bd{0.0, -1};
         for (int64_t i = tid; i < wl; i += DNT) {
             const double dv = Ms(lo + i) - Ms(lo2 + i);
             if (bd.i < 0 || dv > bd.v) { bd.v = dv; bd.i = i; }
         }
         bd = block_argmax<false>(bd, sh_av);
-        if (tid == 0) out[row] = lo + bd.i + Lk / 2;
+        finish(lo + bd.i + Lk / 2);
     }
 }
 
@@ -637,15 +774,20 @@ template <bool F64>
 __global__ void __launch_bounds__(F64 ? DNT : MNT, F64 ? 2 : 1) minn_peak_kernel(RowView r, int smooth_win, double gate_threshold,
                                                         int has_bounds, int64_t b_lo, int64_t b_hi, int64_t *peak,
                                                         int64_t *gate_span, void *Ms_out, const float *cm,
-                                                        int64_t cm_stride, int toff)
+                                                        int64_t cm_stride, int toff, const __grid_constant__ ExactSrc ex, int32_t *status)
 {
     extern __shared__ unsigned mask[];
     __shared__ ArgVal sh_av[MNT / 32];
     __shared__ long long sh_span[2];
+    __shared__ ExactScratch sc;
     const int64_t row = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31;
     const int64_t n = r.n;
-    if (n == 0) { if (tid == 0) { peak[row] = -1; gate_span[2 * row] = gate_span[2 * row + 1] = 0; } return; }
+    int st = 0;
+    auto finish = [&](long long pk, long long a, long long b) {
+        if (tid == 0) { peak[row] = pk; gate_span[2 * row] = a; gate_span[2 * row + 1] = b; if (status) status[row] = st; }
+    };
+    if (n == 0) { finish(-1, 0, 0); return; }
     const Trailing Ms = make_trailing<F64>(r, row, smooth_win > 1 ? smooth_win : 1, toff);
 
     // pass 1: global first-argmax of Ms (also the fallback answer), optional Ms output
@@ -671,18 +813,36 @@ __global__ void __launch_bounds__(F64 ? DNT : MNT, F64 ? 2 : 1) minn_peak_kernel
     }
     constexpr int KW = 1;                            // chunks in flight per warp (4 was tried: the code outgrew the instruction cache)
     ArgVal best = pruned_argmax<KW>(Ms, n, pr, sh_av);
-    if (!(best.v > 0.0)) { if (tid == 0) { peak[row] = -2; gate_span[2 * row] = gate_span[2 * row + 1] = 0; } return; }
+    if (!(best.v > 0.0)) { finish(-2, 0, 0); return; }
+
+    // exact mode (fused sync pipeline): the float64 value of the maximum always (it scales the gate level), every
+    // float32 value within the band of a decision is re-evaluated from the samples (exact.cuh)
+    const bool exact_on = !F64 && ex.x != nullptr && wv <= 32;
+    auto exact_ms = [&](long long i) { return exact_trailing(ex, row, i, wv); };
+    if (exact_on) {
+        const int cnt = collect_at_least(Ms, n, pr, best.v * (1.0 - ex.band), sc);
+        if (cnt > EXCAP) st |= OFS_ST_UNRESOLVED;
+        else {
+            exact_eval_list(sc, cnt, exact_ms);
+            const ArgVal b = exact_list_argmax(sc, cnt);
+            if (cnt > 1) st |= OFS_ST_EXACT | (b.i != best.i ? OFS_ST_CHANGED : 0);
+            best = b;
+            __syncthreads();
+        }
+    }
 
     // pass 2: gate flags -> bitmask (bit index = causal time t = d + toff, so words align with the chunks)
     //         -> longest run (minn.py:155-182)
     const double level = gate_threshold * best.v;
+    const double lvl_lo = exact_on ? level * (1.0 - ex.band) : level, lvl_hi = exact_on ? level * (1.0 + ex.band) : level;
     const int64_t nch = (n + toff + 255) / 256;
+    if (exact_on) { if (tid == 0) sc.cnt = 0; __syncthreads(); }
     {
         const int nchi = (int)nch, warp = tid >> 5;
         for (int c0 = warp * 32; c0 < nchi; c0 += (int)blockDim.x) {
             const int cl = c0 + lane;
             const bool inr = cl < nchi;
-            const bool pass = inr && (!pr.cm || (double)pr.bound(cl) >= level);
+            const bool pass = inr && (!pr.cm || (double)pr.bound(cl) >= lvl_lo);
             if (inr && !pass) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) mask[cl * 8 + q] = 0u;
@@ -708,8 +868,14 @@ __global__ void __launch_bounds__(F64 ? DNT : MNT, F64 ? 2 : 1) minn_peak_kernel
                     if (u < cnt) {
                         unsigned b8 = 0;
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            if (i0s[u] + k >= 0 && i0s[u] + k < n && vk[u][k] >= level) b8 |= 1u << k;
+                        for (int k = 0; k < 8; ++k) {
+                            const bool inrow = i0s[u] + k >= 0 && i0s[u] + k < n;
+                            if (inrow && vk[u][k] >= level) b8 |= 1u << k;
+                            if (exact_on && inrow && vk[u][k] >= lvl_lo && vk[u][k] <= lvl_hi) {   // float64 decides this flag
+                                const int slot = atomicAdd(&sc.cnt, 1);
+                                if (slot < EXCAP) sc.idx[slot] = i0s[u] + k;
+                            }
+                        }
                         unsigned wv32 = b8 << (8 * (lane & 3));
                         wv32 |= __shfl_xor_sync(0xffffffffu, wv32, 1);
                         wv32 |= __shfl_xor_sync(0xffffffffu, wv32, 2);
@@ -719,6 +885,21 @@ __global__ void __launch_bounds__(F64 ? DNT : MNT, F64 ? 2 : 1) minn_peak_kernel
         }
     }
     __syncthreads();
+    if (exact_on) {
+        const int cnt = sc.cnt;
+        if (cnt > EXCAP) st |= OFS_ST_UNRESOLVED;
+        else if (cnt > 0) {
+            exact_eval_list(sc, cnt, exact_ms);
+            if (tid < cnt) {
+                const long long t = sc.idx[tid] + toff;
+                const bool on = sc.val[tid] >= level, was = (mask[t >> 5] >> (t & 31)) & 1u;
+                if (on && !was) atomicOr(&mask[t >> 5], 1u << (t & 31));
+                if (!on && was) atomicAnd(&mask[t >> 5], ~(1u << (t & 31)));
+            }
+            st |= OFS_ST_EXACT;
+            __syncthreads();
+        }
+    }
     long long bs_all, be_all;
     longest_run_block(mask, nch * 256, bs_all, be_all);
     if (tid < 32) {
@@ -737,11 +918,21 @@ __global__ void __launch_bounds__(F64 ? DNT : MNT, F64 ? 2 : 1) minn_peak_kernel
     __syncthreads();
     const long long gs = sh_span[0], ge = sh_span[1];
     if (gs >= ge) {                                          // empty gate -> global argmax (minn.py:195-200)
-        if (tid == 0) { peak[row] = best.i; gate_span[2 * row] = best.i; gate_span[2 * row + 1] = best.i + 1; }
+        finish(best.i, best.i, best.i + 1);
         return;
     }
-    const ArgVal pk = range_argmax(Ms, gs, ge, Ms.toff, sh_av);
-    if (tid == 0) { peak[row] = pk.i; gate_span[2 * row] = gs; gate_span[2 * row + 1] = ge; }
+    ArgVal pk = range_argmax(Ms, gs, ge, Ms.toff, sh_av);
+    if (exact_on) {                                          // first float64 maximum inside the gate
+        const int cnt = collect_range_at_least(Ms, gs, ge, Ms.toff, pk.v * (1.0 - ex.band), sc);
+        if (cnt > EXCAP) st |= OFS_ST_UNRESOLVED;
+        else if (cnt > 1) {
+            exact_eval_list(sc, cnt, exact_ms);
+            const ArgVal b = exact_list_argmax(sc, cnt);
+            st |= OFS_ST_EXACT | (b.i != pk.i ? OFS_ST_CHANGED : 0);
+            pk = b;
+        }
+    }
+    finish(pk.i, gs, ge);
 }
 
 // ---- combined_sc_min: S&C gate (:337-351) and gated first-segment peak (:183-259) -----------------
@@ -1274,13 +1465,9 @@ static int set_mask_smem(K kern, size_t bytes)
 }
 static size_t mask_bytes(int64_t n) { return (size_t)((n + 31) / 32) * 4 + 16; }
 
-}  // namespace ofs
-
-using namespace ofs;
-
-OFS_API int ofs_find_plateau_end_pruned(const ofs_rows *M, const float *chunk_max, int64_t cm_stride, int32_t toff,
-                                        int32_t cp_len, int32_t lookahead, int32_t smooth_win, int64_t *plateau_end,
-                                        void *stream)
+// plateau detector; ex != nullptr: exact mode of the fused sync pipeline (status: int32[n_rows], OFS_ST_* bits)
+int launch_plateau(const ofs_rows *M, const float *chunk_max, int64_t cm_stride, int32_t toff, int32_t cp_len, int32_t lookahead,
+                   int32_t smooth_win, int64_t *plateau_end, const ExactSrc *ex, int32_t *status, void *stream)
 {
     if (int rc = rows_ok(M, "ofs_find_plateau_end")) return rc;
     OFS_REQUIRE(plateau_end, "ofs_find_plateau_end: null output");
@@ -1291,10 +1478,20 @@ OFS_API int ofs_find_plateau_end_pruned(const ofs_rows *M, const float *chunk_ma
     auto go = [&](auto kern) -> int {
         if (cms > 48 * 1024) OFS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cms));
         kern<<<(unsigned)M->n_rows, DNT, cms, (cudaStream_t)stream>>>(view(M), cp_len, lookahead, smooth_win, plateau_end, chunk_max,
-                                                                     cm_stride, chunk_max ? toff : 0);
+                                                                     cm_stride, chunk_max ? toff : 0, ex ? *ex : ExactSrc{}, status);
         return check_launch("plateau_kernel");
     };
     return M->f64 ? go(plateau_kernel<true>) : go(plateau_kernel<false>);
+}
+
+}  // namespace ofs
+using namespace ofs;
+
+OFS_API int ofs_find_plateau_end_pruned(const ofs_rows *M, const float *chunk_max, int64_t cm_stride, int32_t toff,
+                                        int32_t cp_len, int32_t lookahead, int32_t smooth_win, int64_t *plateau_end,
+                                        void *stream)
+{
+    return launch_plateau(M, chunk_max, cm_stride, toff, cp_len, lookahead, smooth_win, plateau_end, nullptr, nullptr, stream);
 }
 
 OFS_API int ofs_find_plateau_end(const ofs_rows *M, int32_t cp_len, int32_t lookahead, int32_t smooth_win,
@@ -1303,9 +1500,10 @@ OFS_API int ofs_find_plateau_end(const ofs_rows *M, int32_t cp_len, int32_t look
     return ofs_find_plateau_end_pruned(M, nullptr, 0, 0, cp_len, lookahead, smooth_win, plateau_end, stream);
 }
 
-OFS_API int ofs_find_minn_peak_pruned(const ofs_rows *M, const float *chunk_max, int64_t cm_stride, int32_t toff,
-                                      int32_t smooth_win, double gate_threshold, int32_t has_bounds, int64_t bound_lo,
-                                      int64_t bound_hi, int64_t *peak, int64_t *gate_span, void *Ms, void *stream)
+namespace ofs {
+int launch_minn_peak(const ofs_rows *M, const float *chunk_max, int64_t cm_stride, int32_t toff, int32_t smooth_win,
+                     double gate_threshold, int32_t has_bounds, int64_t bound_lo, int64_t bound_hi, int64_t *peak,
+                     int64_t *gate_span, void *Ms, const ExactSrc *ex, int32_t *status, void *stream)
 {
     if (int rc = rows_ok(M, "ofs_find_minn_peak")) return rc;
     OFS_REQUIRE(peak && gate_span, "ofs_find_minn_peak: null output");
@@ -1322,10 +1520,20 @@ OFS_API int ofs_find_minn_peak_pruned(const ofs_rows *M, const float *chunk_max,
     auto go = [&](auto kern) -> int {
         if (int rc = set_mask_smem(kern, sm)) return rc;
         kern<<<(unsigned)M->n_rows, nt, sm, (cudaStream_t)stream>>>(view(M), smooth_win, gate_threshold, has_bounds, bound_lo, bound_hi,
-                                                                   peak, gate_span, Ms, chunk_max, cm_stride, toff);
+                                                                   peak, gate_span, Ms, chunk_max, cm_stride, toff, ex ? *ex : ExactSrc{},
+                                                                   status);
         return check_launch("minn_peak_kernel");
     };
     return M->f64 ? go(minn_peak_kernel<true>) : go(minn_peak_kernel<false>);
+}
+}  // namespace ofs
+
+OFS_API int ofs_find_minn_peak_pruned(const ofs_rows *M, const float *chunk_max, int64_t cm_stride, int32_t toff,
+                                      int32_t smooth_win, double gate_threshold, int32_t has_bounds, int64_t bound_lo,
+                                      int64_t bound_hi, int64_t *peak, int64_t *gate_span, void *Ms, void *stream)
+{
+    return launch_minn_peak(M, chunk_max, cm_stride, toff, smooth_win, gate_threshold, has_bounds, bound_lo, bound_hi, peak, gate_span,
+                            Ms, nullptr, nullptr, stream);
 }
 
 OFS_API int ofs_find_minn_peak(const ofs_rows *M, int32_t smooth_win, double gate_threshold, int32_t has_bounds,

@@ -365,30 +365,57 @@ def minn_rtl_events(corr_positive: torch.Tensor, valid: torch.Tensor, above: tor
 
 
 # ------------------------------------------------------------------------------------------- sync pipeline
-_REC_NP = np.dtype([("timing", "<i8"), ("coarse", "<i8"), ("metric", "<f4"), ("p_re", "<f4"), ("p_im", "<f4"), ("cfo", "<f4")])
+_REC_NP = np.dtype([("timing", "<i8"), ("coarse", "<i8"), ("metric", "<f4"), ("p_re", "<f4"), ("p_im", "<f4"), ("cfo", "<f4"),
+                    ("status", "<i4"), ("reserved", "<i4")])
 assert _REC_NP.itemsize == C.sizeof(L.SyncRecord)
+REC_BYTES = C.sizeof(L.SyncRecord)
+
+
+def _sync_params(cp_len, smooth_win, sc_delta, gate_threshold, exact, exact_band) -> L.SyncParams:
+    return L.SyncParams(cp_len=int(cp_len), smooth_win=int(smooth_win), sc_delta=int(sc_delta), exact=int(bool(exact)),
+                        gate_threshold=float(gate_threshold), exact_band=float(exact_band or 0.0))
 
 
 @dataclass
 class SyncOut:
     M: torch.Tensor            # [F, out_len] float32 view
-    records: torch.Tensor      # [F, 32] uint8 (ofs_sync_record); use records_numpy()
+    records: torch.Tensor      # [F, REC_BYTES] uint8 (ofs_sync_record); use records_numpy()
     chunk_max: torch.Tensor
 
     def records_numpy(self) -> np.ndarray:
         return self.records.cpu().numpy().view(_REC_NP).reshape(-1)
 
 
+def sync_f64(x: torch.Tensor, kind: str, symbol_len: int, *, cp_len: int = 512, smooth_win: int = 16, sc_delta: int = 16,
+             gate_threshold: float = 0.5) -> torch.Tensor:
+    """ofs_sync_f64: the sync pipeline entirely in float64 for frames [F, B, L] (int16 IQ: [F, B, L, 2]) -> records [F, REC_BYTES]."""
+    if x.dim() != (4 if x.dtype == torch.int16 else 3):
+        raise ValueError("sync_f64 takes frames [F, B, L] (int16 IQ: [F, B, L, 2])")
+    xd, code, _ = to_device(x)
+    F, B, n = xd.shape[0], xd.shape[1], xd.shape[2]
+    rec = torch.zeros((F, REC_BYTES), dtype=torch.uint8, device=xd.device)
+    d = L.MetricDesc(kind=KINDS[kind], in_dtype=code, out_f64=1, path=L.OFS_PATH_TILE, symbol_len=int(symbol_len), n_branches=B,
+                     n_frames=F, n_samples=n, x_frame_stride=B * n, x_branch_stride=n, out_stride=max(n - symbol_len + 1, 0),
+                     store_mode=0, reserved=0)
+    sp = _sync_params(cp_len, smooth_win, sc_delta, gate_threshold, False, 0.0)
+    L.check(L.lib().ofs_sync_f64(C.byref(d), _ptr(xd), C.byref(sp), _ptr(rec), _stream()), "ofs_sync_f64")
+    return rec
+
+
 class SyncPlan:
-    """Pre-allocated buffers for repeated ofs_sync calls on device-resident frames [F, L] complex64/int16-IQ."""
+    """Pre-allocated buffers for repeated ofs_sync calls on device-resident frames [F, L] (or [F, B, L], branches summed)
+    complex64 / int16-IQ.  exact=True (default): detector decisions inside the float32 error band of the stripe metric are
+    re-evaluated in float64 from the samples, so `timing` equals what the reference finds on its float64 metric
+    (records["status"]: OFS_ST_EXACT / _CHANGED / _UNRESOLVED; resolve() settles the rare unresolved frames)."""
 
     def __init__(self, n_frames: int, n_samples: int, kind: str = "sc", symbol_len: int = 2048, in_dtype: str = "c64",
                  cp_len: int = 512, smooth_win: int = 16, sc_delta: int = 16, gate_threshold: float = 0.5, store_mode: int = 0,
-                 tma_mode: int = 2):
+                 tma_mode: int = 2, n_branches: int = 1, exact: bool = True, exact_band: float = 0.0):
         dev = _device()
-        self.F, self.n, self.kind, self.N = n_frames, n_samples, kind, symbol_len
+        self.F, self.n, self.kind, self.N, self.B = n_frames, n_samples, kind, symbol_len, n_branches
         self.code = {"c64": L.OFS_C64, "iq16": L.OFS_IQ16}[in_dtype]
         self.cp_len, self.smooth_win, self.sc_delta, self.gate_threshold = cp_len, smooth_win, sc_delta, gate_threshold
+        self.params = _sync_params(cp_len, smooth_win, sc_delta, gate_threshold, exact, exact_band)
         self.toff = symbol_len - 1
         self.pitch = (n_samples + 3) // 4 * 4
         self.out_len = max(n_samples - symbol_len + 1, 0)
@@ -396,27 +423,40 @@ class SyncPlan:
         self.M = self.buf[:, self.toff:self.toff + self.out_len]
         self.cm_stride = (n_samples + 255) // 256
         self.cm = torch.zeros((n_frames, self.cm_stride), dtype=torch.float32, device=dev)
-        self.rec = torch.zeros((n_frames, C.sizeof(L.SyncRecord)), dtype=torch.uint8, device=dev)
-        self.scratch = torch.zeros(3 * n_frames, dtype=torch.int64, device=dev)
+        self.rec = torch.zeros((n_frames, REC_BYTES), dtype=torch.uint8, device=dev)
+        self.scratch = torch.zeros(4 * n_frames, dtype=torch.int64, device=dev)
         self.desc = L.MetricDesc(kind=KINDS[kind], in_dtype=self.code, out_f64=0, path=L.OFS_PATH_AUTO, symbol_len=symbol_len,
-                                 n_branches=1, n_frames=n_frames, n_samples=n_samples, x_frame_stride=n_samples,
+                                 n_branches=n_branches, n_frames=n_frames, n_samples=n_samples, x_frame_stride=n_branches * n_samples,
                                  x_branch_stride=n_samples, out_stride=self.pitch, store_mode=store_mode,
                                  reserved=1 if tma_mode == 1 else 0)
 
     def run(self, x: torch.Tensor) -> SyncOut:
         assert x.is_cuda and x.is_contiguous() and x.shape[0] == self.F
         L.check(L.lib().ofs_sync(C.byref(self.desc), _ptr(x), C.c_void_p(self.M.data_ptr()), _ptr(self.cm), C.c_int64(self.cm_stride),
-                                 int(self.cp_len), int(self.smooth_win), int(self.sc_delta), C.c_double(self.gate_threshold),
-                                 _ptr(self.rec), _ptr(self.scratch), _stream()), "ofs_sync")
+                                 C.byref(self.params), _ptr(self.rec), _ptr(self.scratch), _stream()), "ofs_sync")
         return SyncOut(self.M, self.rec, self.cm)
 
     def records_numpy(self) -> np.ndarray:
         return self.rec.cpu().numpy().view(_REC_NP).reshape(-1)
 
+    def resolve(self, x: torch.Tensor) -> int:
+        """Re-run the frames the kernels flagged OFS_ST_UNRESOLVED through the float64 pipeline (ofs_sync_f64) and patch their
+        records in place.  Synchronises (reads the status column).  -> number of frames re-run."""
+        st = self.rec.view(torch.int32).view(self.F, -1)[:, 8]
+        idx = torch.nonzero((st & L.OFS_ST_UNRESOLVED) != 0).flatten()
+        if idx.numel() == 0:
+            return 0
+        xs = x.index_select(0, idx).contiguous()
+        if xs.dim() == 2 + (self.code == L.OFS_IQ16):          # [F, L(, 2)] -> [F, 1, L(, 2)]
+            xs = xs[:, None]
+        rec = sync_f64(xs, self.kind, self.N, cp_len=self.cp_len, smooth_win=self.smooth_win, sc_delta=self.sc_delta,
+                       gate_threshold=self.gate_threshold)
+        self.rec.index_copy_(0, idx, rec)
+        return int(idx.numel())
+
     def run_detect_only(self, x: torch.Tensor) -> None:
         L.check(L.lib().ofs_sync_detect(C.byref(self.desc), _ptr(x), C.c_void_p(self.M.data_ptr()), _ptr(self.cm),
-                                        C.c_int64(self.cm_stride), int(self.cp_len),
-                                        int(self.smooth_win), int(self.sc_delta), C.c_double(self.gate_threshold), _ptr(self.rec),
+                                        C.c_int64(self.cm_stride), C.byref(self.params), _ptr(self.rec),
                                         _ptr(self.scratch), _stream()), "ofs_sync_detect")
 
     def run_metric_only(self, x: torch.Tensor) -> None:
@@ -444,7 +484,7 @@ class HostSync:
             pass
 
     def run(self, x_host: torch.Tensor, M_host: torch.Tensor | None, records_host: torch.Tensor, *, kind="sc", symbol_len=2048,
-            cp_len=512, smooth_win=16, sc_delta=16, gate_threshold=0.5):
+            cp_len=512, smooth_win=16, sc_delta=16, gate_threshold=0.5, exact=True, exact_band=0.0):
         F, n = x_host.shape[0], x_host.shape[1]
         if x_host.dtype == torch.int16:
             # int16 IQ [F, n, 2]: ofs_metric_desc strides count SAMPLES (4 bytes each), torch strides count int16 elements
@@ -463,15 +503,15 @@ class HostSync:
         if M_host is not None and (M_host.dtype != torch.float32 or M_host.dim() != 2 or M_host.shape[0] < F or M_host.shape[1] < out_len
                                    or M_host.stride(1) != 1 or (F > 1 and M_host.stride(0) < out_len)):
             raise ValueError(f"M_host must be float32 [frames, >= {out_len}] with unit element stride")
-        if records_host.numel() * records_host.element_size() < F * C.sizeof(L.SyncRecord):
+        if records_host.numel() * records_host.element_size() < F * REC_BYTES:
             raise ValueError("records_host too small")
         out_stride = M_host.stride(0) if M_host is not None else out_len
         d = L.MetricDesc(kind=KINDS[kind], in_dtype=code, out_f64=0, path=L.OFS_PATH_AUTO, symbol_len=symbol_len, n_branches=1,
                          n_frames=F, n_samples=n, x_frame_stride=xfs, x_branch_stride=n, out_stride=out_stride,
                          store_mode=0, reserved=0)
-        L.check(L.lib().ofs_sync_host(self.ctx, C.byref(d), _ptr(x_host), _ptr(M_host), int(cp_len), int(smooth_win), int(sc_delta),
-                                      C.c_double(gate_threshold), _ptr(records_host)), "ofs_sync_host")
-        return records_host.numpy().view(_REC_NP).reshape(-1)
+        sp = _sync_params(cp_len, smooth_win, sc_delta, gate_threshold, exact, exact_band)
+        L.check(L.lib().ofs_sync_host(self.ctx, C.byref(d), _ptr(x_host), _ptr(M_host), C.byref(sp), _ptr(records_host)), "ofs_sync_host")
+        return records_host.numpy().reshape(-1)[: F * REC_BYTES].view(_REC_NP).reshape(-1)
 
 
 # ------------------------------------------------------------------------------------------- park

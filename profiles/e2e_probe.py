@@ -10,7 +10,7 @@ dev = torch.device("cuda", 0)
 x = synth.make_batch_device(F, n, "sc", seed=1234, device=dev)
 xh = torch.empty((F, n), dtype=torch.complex64).pin_memory(); xh.copy_(x)
 Mh = torch.empty((F, n - 2047), dtype=torch.float32).pin_memory()
-rh = torch.zeros((F, 32), dtype=torch.uint8).pin_memory()
+rh = torch.zeros((F, engine.REC_BYTES), dtype=torch.uint8).pin_memory()
 xd = torch.empty_like(x)
 torch.cuda.synchronize()
 for name, fn, nbytes in (("h2d only", lambda: xd.copy_(xh, non_blocking=True), xh.numel() * 8),

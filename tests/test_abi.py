@@ -35,8 +35,8 @@ def test_struct_layouts():
     assert C.sizeof(_lib.MetricDesc) == 72
     assert C.sizeof(_lib.Rows) == 40
     assert C.sizeof(_lib.Event) == 72
-    assert C.sizeof(_lib.SyncRecord) == 32
-    assert engine._EVENT_NP.itemsize == 72 and engine._REC_NP.itemsize == 32
+    assert C.sizeof(_lib.SyncRecord) == 40 and C.sizeof(_lib.SyncParams) == 32
+    assert engine._EVENT_NP.itemsize == 72 and engine._REC_NP.itemsize == 40
 
 
 def test_out_len_and_stripe_predicate_without_gpu():

@@ -223,16 +223,20 @@ def test_sync_pipeline_device_and_host(golden):
     n = 49152
     x = _captures(5, n, "sc", seed=9)
     Mref = _oracle_metric(x, "sc", 2048)
-    ends = [orc.find_plateau_end_from_metric(r.astype(np.float32).astype(np.float64), 512, 128, 16) for r in Mref]
+    ends = [orc.find_plateau_end_from_metric(r, 512, 128, 16) for r in Mref]          # float64 metric of the oracle
     plan = engine.SyncPlan(5, n, "sc", 2048, "c64", cp_len=512, smooth_win=16, sc_delta=16)
     out = plan.run(torch.as_tensor(x).cuda())
     torch.cuda.synchronize()
     rec = out.records_numpy()
     Mg = out.M.cpu().numpy()
     _check_metric(Mg, Mref)
+    plan.resolve(torch.as_tensor(x).cuda())
+    rec = plan.records_numpy()
+    assert rec["timing"].tolist() == ends                 # exact mode (default): equal to the float64 reference, no near-tie allowance
+    plain = engine.SyncPlan(5, n, "sc", 2048, "c64", cp_len=512, smooth_win=16, sc_delta=16, exact=False)
+    rec32 = plain.run(torch.as_tensor(x).cuda()).records_numpy()
     ends_gpuM = [orc.find_plateau_end_from_metric(r.astype(np.float64), 512, 128, 16) for r in Mg]
-    assert rec["timing"].tolist() == ends_gpuM            # detector parity on the GPU's own metric: exact
-    assert sum(int(a != b) for a, b in zip(rec["timing"].tolist(), ends)) <= 1   # vs float64 metric: near-ties only
+    assert rec32["timing"].tolist() == ends_gpuM          # float32-only mode: the detector on the GPU's own metric, exactly
     for f in range(5):
         c = int(rec["coarse"][f]); assert c == max(int(rec["timing"][f]) - 16, 0)
         M0, P0, R0 = orc.metric_prefix_c64(x[f], 2048, 0, want_pr=True)
@@ -242,7 +246,7 @@ def test_sync_pipeline_device_and_host(golden):
     # host-buffer path
     xh = torch.as_tensor(x).pin_memory()
     Mh = torch.zeros((5, n - 2047), dtype=torch.float32).pin_memory()
-    rh = torch.zeros((5, 32), dtype=torch.uint8).pin_memory()
+    rh = torch.zeros((5, engine.REC_BYTES), dtype=torch.uint8).pin_memory()
     hs = engine.HostSync()
     rec2 = hs.run(xh, Mh, rh, kind="sc", symbol_len=2048, cp_len=512, smooth_win=16, sc_delta=16)
     assert np.array_equal(Mh.numpy(), Mg)
@@ -266,7 +270,10 @@ def test_minn_sync_pipeline():
     torch.cuda.synchronize()
     rec = out.records_numpy()
     Mg = out.M.cpu().numpy().astype(np.float64)
-    assert rec["timing"].tolist() == [orc.find_minn_peak(r, 16, 0.5)[0] for r in Mg]
+    assert rec["timing"].tolist() == [orc.find_minn_peak(orc.metric_prefix_c64(r, 2048, 2), 16, 0.5)[0] for r in x]   # float64 oracle
+    plain = engine.SyncPlan(4, n, "minn", 2048, "c64", smooth_win=16, gate_threshold=0.5, exact=False)
+    rec32 = plain.run(torch.as_tensor(x).cuda()).records_numpy()
+    assert rec32["timing"].tolist() == [orc.find_minn_peak(r, 16, 0.5)[0] for r in Mg]
     for f in range(4):
         c = int(rec["coarse"][f])
         M0, P0, R0 = orc.metric_prefix_c64(x[f], 2048, 2, want_pr=True)

@@ -178,6 +178,8 @@ def main() -> None:
     ap.add_argument("--store-mode", type=int, default=0)
     ap.add_argument("--tma-mode", type=int, default=2, help="2: tiled tensor-map copies with 128B swizzle, 1: 1-D bulk copies")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-exact", action="store_true", help="decide on the float32 metric only (no float64 re-evaluation of in-band decisions)")
+    ap.add_argument("--exact-band", type=float, default=0.0, help="relative half-width of the float32 uncertainty band (0: library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -200,7 +202,8 @@ def main() -> None:
 
     F, n = args.frames, args.samples
     x = synth.make_batch_device(F, n, "sc", seed=1234 + rank, device=dev)
-    plan = engine.SyncPlan(F, n, "sc", N_FFT, "c64", cp_len=CP_LEN, smooth_win=SMOOTH, sc_delta=SC_DELTA, store_mode=args.store_mode, tma_mode=args.tma_mode)
+    plan = engine.SyncPlan(F, n, "sc", N_FFT, "c64", cp_len=CP_LEN, smooth_win=SMOOTH, sc_delta=SC_DELTA, store_mode=args.store_mode,
+                           tma_mode=args.tma_mode, exact=not args.no_exact, exact_band=args.exact_band)
     # detection records of step k are all-gathered on a side stream while step k + 1 computes (dist.PipelinedGatherer)
     gather = odist.PipelinedGatherer(plan.rec) if world > 1 else None
 
@@ -276,7 +279,8 @@ def main() -> None:
     Mh = torch.empty((Fe, out_len), dtype=torch.float32).pin_memory()
     rh = torch.zeros((Fe, engine.REC_BYTES), dtype=torch.uint8).pin_memory()
     hs = engine.HostSync(local)
-    kw = dict(kind="sc", symbol_len=N_FFT, cp_len=CP_LEN, smooth_win=SMOOTH, sc_delta=SC_DELTA)
+    kw = dict(kind="sc", symbol_len=N_FFT, cp_len=CP_LEN, smooth_win=SMOOTH, sc_delta=SC_DELTA, exact=not args.no_exact,
+              exact_band=args.exact_band)
     hs.run(xh, Mh, rh, **kw)
     torch.cuda.synchronize()
     if world > 1:

@@ -328,7 +328,9 @@ void ofs_host_free(void *p);
 #define OFS_ST_CHANGED 2     /* ... and the float64 evaluation moved the index */
 #define OFS_ST_UNRESOLVED 4  /* a decision inside the band could not be settled in the kernel (more than 64 candidates, or one
                                 of the reference's fallback branches): timing is the float32 decision; ofs_sync_f64 settles it */
-#define OFS_EXACT_BAND 1e-4  /* default relative half-width of the band = the asserted accuracy of the float32 metric */
+#define OFS_EXACT_BAND 1e-5  /* default relative half-width of the band: 8x the largest error of the (smoothed) float32 metric
+                                measured where decisions are taken (>= 0.45 of the row maximum: 5.4e-7, profiles/
+                                r2_exact_band_probe.json; tests/test_gpu_exact.py asserts <= 2.5e-6 = band / 4) */
 
 typedef struct ofs_sync_record {
     int64_t timing;      /* SC: plateau_end; MINN: peak */

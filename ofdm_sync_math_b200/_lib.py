@@ -10,7 +10,7 @@ import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libofdmsync.so"
+LIB_PATH = Path(os.environ.get("OFS_LIB") or (_PKG / "libofdmsync.so"))   # OFS_LIB: A/B builds during kernel work
 
 OFS_C64, OFS_C128, OFS_IQ16 = 0, 1, 2
 OFS_SC, OFS_SC_BOTH, OFS_MINN, OFS_AA = 0, 1, 2, 3
@@ -47,7 +47,7 @@ class SyncParams(C.Structure):
 
 
 OFS_ST_EXACT, OFS_ST_CHANGED, OFS_ST_UNRESOLVED = 1, 2, 4
-OFS_EXACT_BAND = 1e-4
+OFS_EXACT_BAND = 1e-5
 
 
 class OfsError(RuntimeError):

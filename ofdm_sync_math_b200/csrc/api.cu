@@ -58,7 +58,7 @@ void keep_pool_cached()
 int launch_metric_tile(const ofs_metric_desc *d, const void *x, void *M, void *P, void *R, cudaStream_t stream);
 int launch_metric_stripe(const ofs_metric_desc *d, const void *x, float *M, void *P, float *R, float *chunk_max, int64_t cm_stride,
                          cudaStream_t stream);
-bool stripe_supported(const ofs_metric_desc *d);
+bool stripe_supported(const ofs_metric_desc *d, const void *x, bool want_pr);
 int launch_plateau(const ofs_rows *M, const float *chunk_max, int64_t cm_stride, int32_t toff, int32_t cp_len, int32_t lookahead,
                    int32_t smooth_win, int64_t *plateau_end, const ExactSrc *ex, int32_t *status, void *stream);
 int launch_minn_peak(const ofs_rows *M, const float *chunk_max, int64_t cm_stride, int32_t toff, int32_t smooth_win,
@@ -156,7 +156,7 @@ OFS_API int64_t ofs_metric_out_len(const ofs_metric_desc *d)
 OFS_API int ofs_metric_stripe_ok(const ofs_metric_desc *d, const void *x, const void *M)
 {
     (void)x; (void)M;
-    return d && check_desc(d, "ofs_metric_stripe_ok") == OFS_OK && stripe_supported(d) ? 1 : 0;
+    return d && check_desc(d, "ofs_metric_stripe_ok") == OFS_OK && stripe_supported(d, x, false) ? 1 : 0;
 }
 
 OFS_API int ofs_metric_array_ok(const ofs_metric_desc *d, const void *x)
@@ -182,7 +182,7 @@ OFS_API int ofs_metric(const ofs_metric_desc *d, const void *x, void *M, void *P
                           !(reinterpret_cast<uintptr_t>(M) & 7) && !(reinterpret_cast<uintptr_t>(P) & 15) &&
                           !(reinterpret_cast<uintptr_t>(R) & 7);
     if (path == OFS_PATH_AUTO) {
-        if (stripe_supported(d) && !P && !R) path = OFS_PATH_STRIPE;
+        if (stripe_supported(d, x, false) && !P && !R) path = OFS_PATH_STRIPE;
         else if (array_ok && d->n_branches >= 2) path = OFS_PATH_ARRAY;
         else path = OFS_PATH_TILE;
     }

@@ -119,8 +119,11 @@ struct Prune {
 // ~4 loads per output instead of w.  Groups are aligned to the causal time t = d + toff (multiples of 8), so that one
 // warp = 32 groups = one 256-sample chunk.  Every pass of a kernel goes through the same grouping, hence sees
 // bit-identical values.
+// slack / n_near (exact mode): chunks are kept while their bound reaches v* (1 - slack), and *n_near receives how many values
+// reach that level -- 1 means the maximum has no contender inside the band and needs no float64 re-evaluation; -1 = unknown
+// (no chunk maxima to derive v* from).
 template <int K = 1, typename F>
-__device__ ArgVal pruned_argmax(const F &fn, int64_t n_out, const Prune &pr, ArgVal *sh_av)
+__device__ ArgVal pruned_argmax(const F &fn, int64_t n_out, const Prune &pr, ArgVal *sh_av, double slack = 0.0, int *n_near = nullptr)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t nch = (n_out + pr.toff + 255) / 256;
@@ -150,9 +153,11 @@ __device__ ArgVal pruned_argmax(const F &fn, int64_t n_out, const Prune &pr, Arg
     // The bound test is done 32 chunks at a time (one per lane); survivors are evaluated by the whole warp.
     ArgVal best{0.0, -1};
     const int nchi = (int)nch;
+    const double near_lvl = vs.v * (1.0 - slack);
+    int near = 0;
     for (int c0 = warp * 32; c0 < nchi; c0 += (int)blockDim.x) {
         const int cl = c0 + lane;
-        const bool pass = cl < nchi && (!have || (double)pr.bound(cl) >= vs.v);
+        const bool pass = cl < nchi && (!have || (double)pr.bound(cl) >= near_lvl);
         unsigned m = __ballot_sync(0xffffffffu, pass);
         while (m) {                              // K surviving chunks per round, in ascending order (first maximum wins)
             int64_t i0s[K];
@@ -172,9 +177,23 @@ __device__ ArgVal pruned_argmax(const F &fn, int64_t n_out, const Prune &pr, Arg
                 if (u < cnt) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
-                        if (i0s[u] + k >= 0 && i0s[u] + k < n_out && (best.i < 0 || vk[u][k] > best.v)) { best.v = vk[u][k]; best.i = i0s[u] + k; }
+                        if (i0s[u] + k >= 0 && i0s[u] + k < n_out) {
+                            if (best.i < 0 || vk[u][k] > best.v) { best.v = vk[u][k]; best.i = i0s[u] + k; }
+                            near += vk[u][k] >= near_lvl;
+                        }
                 }
         }
+    }
+    if (n_near) {
+        int w = near;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+        __shared__ int sh_near;
+        if (tid == 0) sh_near = 0;
+        __syncthreads();
+        if (lane == 0 && w) atomicAdd(&sh_near, w);
+        __syncthreads();
+        *n_near = have ? sh_near : -1;
     }
     return block_argmax<false>(best, sh_av);
 }
@@ -315,6 +334,18 @@ struct SmoothSame {   // np.convolve(M, ones(w)/w, "same")[i], sc.py:100
     }
 };
 
+// append the indices i0 + k (k = set bits of hits) to the list; kept out of the unrolled 8-loops
+__device__ __forceinline__ void push_hits(ExactScratch &sc, int64_t i0, unsigned hits)
+{
+#pragma unroll 1
+    while (hits) {
+        const int k = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const int slot = atomicAdd(&sc.cnt, 1);
+        if (slot < EXCAP) sc.idx[slot] = i0 + k;
+    }
+}
+
 // Collect every index i < n_out with fn(i) >= lvl into sc.idx (ascending order is NOT guaranteed), through the same chunk
 // pruning and 8-groups as pruned_argmax.  Returns the number found (may exceed EXCAP: then the list is incomplete).
 template <typename F>
@@ -334,12 +365,11 @@ __device__ int collect_at_least(const F &fn, int64_t n_out, const Prune &pr, dou
             m &= m - 1;
             const int64_t i0 = (int64_t)c * 256 - pr.toff + 8 * lane;
             fn.eval8(i0, v8);
+            unsigned hits = 0u;
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-                if (i0 + k >= 0 && i0 + k < n_out && v8[k] >= lvl) {
-                    const int slot = atomicAdd(&sc.cnt, 1);
-                    if (slot < EXCAP) sc.idx[slot] = i0 + k;
-                }
+                if (i0 + k >= 0 && i0 + k < n_out && v8[k] >= lvl) hits |= 1u << k;
+            push_hits(sc, i0, hits);
         }
     }
     __syncthreads();
@@ -355,12 +385,11 @@ __device__ int collect_range_at_least(const F &fn, int64_t lo, int64_t hi, int t
     const int64_t g0 = lo - (((lo + toff) % 8) + 8) % 8;
     for (int64_t i0 = g0 + 8LL * threadIdx.x; i0 < hi; i0 += 8LL * blockDim.x) {
         fn.eval8(i0, v8);
+        unsigned hits = 0u;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-            if (i0 + k >= lo && i0 + k < hi && v8[k] >= lvl) {
-                const int slot = atomicAdd(&sc.cnt, 1);
-                if (slot < EXCAP) sc.idx[slot] = i0 + k;
-            }
+            if (i0 + k >= lo && i0 + k < hi && v8[k] >= lvl) hits |= 1u << k;
+        push_hits(sc, i0, hits);
     }
     __syncthreads();
     return sc.cnt;
@@ -380,8 +409,12 @@ __device__ __forceinline__ ArgVal exact_list_argmax(const ExactScratch &sc, int 
 // ex.x != nullptr (fused sync pipeline, float32 rows from the stripe kernel): decisions whose operands lie within ex.band of
 // each other are re-evaluated in float64 from the samples (exact.cuh), so the index equals the one the reference finds on its
 // float64 metric; status[row] reports what happened (OFS_ST_*).
-template <bool F64>
-__global__ void __launch_bounds__(DNT, F64 ? 2 : 3) plateau_kernel(RowView r, int cp_len, int lookahead, int smooth_win,
+#ifndef OFS_DET_EXACT_CTAS
+#define OFS_DET_EXACT_CTAS 3
+#endif
+// EXACT is a compile-time switch: the plain detector API (metric rows are the caller's data) carries none of the exact-mode code.
+template <bool F64, bool EXACT>
+__global__ void __launch_bounds__(DNT, F64 ? 2 : (EXACT ? OFS_DET_EXACT_CTAS : 3)) plateau_kernel(RowView r, int cp_len, int lookahead, int smooth_win,
                                                       int64_t *out, const float *cm, int64_t cm_stride, int toff,
                                                       const __grid_constant__ ExactSrc ex, int32_t *status)
 {
@@ -407,19 +440,20 @@ __global__ void __launch_bounds__(DNT, F64 ? 2 : 3) plateau_kernel(RowView r, in
     extern __shared__ float cm_s[];
     Prune pr{(cm && r.n > w) ? cm + row * cm_stride : nullptr, cm_stride, toff, (w - 1 - Ms.off + 255) / 256, (Ms.off + 255) / 256};
     pr.stage(cm_s, (ms + toff + 255) / 256);
-    ArgVal best = pruned_argmax(Ms, ms, pr, sh_av);
+    int n_near = -1;
+    ArgVal best = EXACT ? pruned_argmax(Ms, ms, pr, sh_av, ex.band, &n_near) : pruned_argmax(Ms, ms, pr, sh_av);
     int64_t center = best.i;
     double peak = best.v;
-    const bool exact_on = !F64 && ex.x != nullptr && r.n > w && w <= 32 && peak > 0.0;
-    const int woff = Ms.off;
-    auto exact_ms = [&](long long i) { return exact_smooth_same(ex, row, i, w, woff); };
+    const bool exact_on = EXACT && !F64 && ex.x != nullptr && r.n > w && w <= 32 && peak > 0.0;
+    const ExactSmooth esm{w, w - 1 - Ms.off, false};
     bool peak_exact = false;
-    if (exact_on) {
+    if (exact_on && n_near != 1) {
         // every index whose float32 value is within the band of the float32 maximum can be the float64 maximum
+        // (n_near == 1: the scan above saw no second value near the maximum -- the usual case, nothing to do)
         const int cnt = collect_at_least(Ms, ms, pr, peak * (1.0 - ex.band), sc);
         if (cnt > EXCAP) st |= OFS_ST_UNRESOLVED;
         else if (cnt > 1) {
-            exact_eval_list(sc, cnt, exact_ms);
+            exact_eval_list(ex, row, sc, cnt, esm);
             const ArgVal b = exact_list_argmax(sc, cnt);
             st |= OFS_ST_EXACT | (b.i != center ? OFS_ST_CHANGED : 0);
             center = b.i; peak = b.v; peak_exact = true;
@@ -441,18 +475,18 @@ __global__ void __launch_bounds__(DNT, F64 ? 2 : 3) plateau_kernel(RowView r, in
             const int64_t g0 = center - (((center + Ms.toff) % 8) + 8) % 8;
             for (int64_t i0 = g0 + 8LL * tid; i0 < post_hi && first == LLONG_MAX; i0 += 8LL * DNT) {
                 Ms.eval8(i0, v8);
+                unsigned m32 = 0u, mdef = 0u, munc = 0u;        // bit k: value k at or below thr / thr_def / thr_unc
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    if (i0 + k < center || i0 + k >= post_hi) continue;
-                    if (first32 == LLONG_MAX && v8[k] <= thr) first32 = i0 + k;
-                    if (first == LLONG_MAX) {
-                        if (v8[k] <= thr_def) first = i0 + k;
-                        else if (v8[k] <= thr_unc) {            // inside the band: float64 decides
-                            const int slot = atomicAdd(&sc.cnt, 1);
-                            if (slot < EXCAP) sc.idx[slot] = i0 + k;
-                        }
-                    }
+                    const unsigned in = (i0 + k >= center && i0 + k < post_hi) ? 1u << k : 0u;
+                    if (v8[k] <= thr) m32 |= in;
+                    if (v8[k] <= thr_def) mdef |= in;
+                    if (v8[k] <= thr_unc) munc |= in;
                 }
+                if (m32 && first32 == LLONG_MAX) first32 = i0 + __ffs(m32) - 1;
+                if (mdef) { first = i0 + __ffs(mdef) - 1; munc &= (1u << (__ffs(mdef) - 1)) - 1u; }
+                munc &= ~mdef;                                  // inside the band, before the first certain one: float64 decides
+                if (exact_on) push_hits(sc, i0, munc);
             }
         }
         first = block_min_i64(first, sh_i);
@@ -467,18 +501,18 @@ __global__ void __launch_bounds__(DNT, F64 ? 2 : 3) plateau_kernel(RowView r, in
                 __syncthreads();
                 if (tid == 0) {                                 // drop the ones behind `first`, append the centre (for peak64)
                     int q = 0;
-                    for (int k = 0; k < cnt; ++k) if (sc.idx[k] < first) sc.idx[q++] = sc.idx[k];
-                    if (!peak_exact && q < EXCAP) sc.idx[q++] = -1 - center;      // tagged: not a candidate
+                    for (int k = 0; k < cnt; ++k) if (sc.idx[k] < first) { sc.idx[q] = sc.idx[k]; sc.tag[q++] = 0; }
+                    if (!peak_exact) { sc.idx[q] = center; sc.tag[q++] = 1; }    // tagged: not a candidate
                     sc.cnt = q;
                 }
                 __syncthreads();
                 const int q = sc.cnt;
-                exact_eval_list(sc, q, [&](long long i) { return exact_ms(i < 0 ? -1 - i : i); });
+                exact_eval_list(ex, row, sc, q, esm);
                 double pk64 = peak;
-                for (int k = 0; k < q; ++k) if (sc.idx[k] < 0) pk64 = sc.val[k];
+                for (int k = 0; k < q; ++k) if (sc.tag[k]) pk64 = sc.val[k];
                 const double thr64 = 0.95 * pk64;
                 long long fx = first;
-                for (int k = 0; k < q; ++k) if (sc.idx[k] >= 0 && sc.val[k] <= thr64 && sc.idx[k] < fx) fx = sc.idx[k];
+                for (int k = 0; k < q; ++k) if (!sc.tag[k] && sc.val[k] <= thr64 && sc.idx[k] < fx) fx = sc.idx[k];
                 st |= OFS_ST_EXACT | (fx != first32 ? OFS_ST_CHANGED : 0);
                 first = fx;
                 __syncthreads();
@@ -770,7 +804,7 @@ __device__ void longest_run_block(const unsigned *mask, int64_t n, long long &bs
     bs = s_res[0]; be = s_res[1];
 }
 
-template <bool F64>
+template <bool F64, bool EXACT>
 __global__ void __launch_bounds__(F64 ? DNT : MNT, F64 ? 2 : 1) minn_peak_kernel(RowView r, int smooth_win, double gate_threshold,
                                                         int has_bounds, int64_t b_lo, int64_t b_hi, int64_t *peak,
                                                         int64_t *gate_span, void *Ms_out, const float *cm,
@@ -817,13 +851,13 @@ __global__ void __launch_bounds__(F64 ? DNT : MNT, F64 ? 2 : 1) minn_peak_kernel
 
     // exact mode (fused sync pipeline): the float64 value of the maximum always (it scales the gate level), every
     // float32 value within the band of a decision is re-evaluated from the samples (exact.cuh)
-    const bool exact_on = !F64 && ex.x != nullptr && wv <= 32;
-    auto exact_ms = [&](long long i) { return exact_trailing(ex, row, i, wv); };
+    const bool exact_on = EXACT && !F64 && ex.x != nullptr && wv <= 32;
+    const ExactSmooth esm{wv, wv - 1, true};
     if (exact_on) {
         const int cnt = collect_at_least(Ms, n, pr, best.v * (1.0 - ex.band), sc);
         if (cnt > EXCAP) st |= OFS_ST_UNRESOLVED;
         else {
-            exact_eval_list(sc, cnt, exact_ms);
+            exact_eval_list(ex, row, sc, cnt, esm);
             const ArgVal b = exact_list_argmax(sc, cnt);
             if (cnt > 1) st |= OFS_ST_EXACT | (b.i != best.i ? OFS_ST_CHANGED : 0);
             best = b;
@@ -866,16 +900,14 @@ __global__ void __launch_bounds__(F64 ? DNT : MNT, F64 ? 2 : 1) minn_peak_kernel
 #pragma unroll
                 for (int u = 0; u < KW; ++u)
                     if (u < cnt) {
-                        unsigned b8 = 0;
+                        unsigned b8 = 0, unc = 0;
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             const bool inrow = i0s[u] + k >= 0 && i0s[u] + k < n;
                             if (inrow && vk[u][k] >= level) b8 |= 1u << k;
-                            if (exact_on && inrow && vk[u][k] >= lvl_lo && vk[u][k] <= lvl_hi) {   // float64 decides this flag
-                                const int slot = atomicAdd(&sc.cnt, 1);
-                                if (slot < EXCAP) sc.idx[slot] = i0s[u] + k;
-                            }
+                            if (inrow && vk[u][k] >= lvl_lo && vk[u][k] <= lvl_hi) unc |= 1u << k;   // float64 decides this flag
                         }
+                        if (exact_on) push_hits(sc, i0s[u], unc);
                         unsigned wv32 = b8 << (8 * (lane & 3));
                         wv32 |= __shfl_xor_sync(0xffffffffu, wv32, 1);
                         wv32 |= __shfl_xor_sync(0xffffffffu, wv32, 2);
@@ -889,7 +921,7 @@ __global__ void __launch_bounds__(F64 ? DNT : MNT, F64 ? 2 : 1) minn_peak_kernel
         const int cnt = sc.cnt;
         if (cnt > EXCAP) st |= OFS_ST_UNRESOLVED;
         else if (cnt > 0) {
-            exact_eval_list(sc, cnt, exact_ms);
+            exact_eval_list(ex, row, sc, cnt, esm);
             if (tid < cnt) {
                 const long long t = sc.idx[tid] + toff;
                 const bool on = sc.val[tid] >= level, was = (mask[t >> 5] >> (t & 31)) & 1u;
@@ -926,7 +958,7 @@ __global__ void __launch_bounds__(F64 ? DNT : MNT, F64 ? 2 : 1) minn_peak_kernel
         const int cnt = collect_range_at_least(Ms, gs, ge, Ms.toff, pk.v * (1.0 - ex.band), sc);
         if (cnt > EXCAP) st |= OFS_ST_UNRESOLVED;
         else if (cnt > 1) {
-            exact_eval_list(sc, cnt, exact_ms);
+            exact_eval_list(ex, row, sc, cnt, esm);
             const ArgVal b = exact_list_argmax(sc, cnt);
             st |= OFS_ST_EXACT | (b.i != pk.i ? OFS_ST_CHANGED : 0);
             pk = b;
@@ -1481,7 +1513,8 @@ int launch_plateau(const ofs_rows *M, const float *chunk_max, int64_t cm_stride,
                                                                      cm_stride, chunk_max ? toff : 0, ex ? *ex : ExactSrc{}, status);
         return check_launch("plateau_kernel");
     };
-    return M->f64 ? go(plateau_kernel<true>) : go(plateau_kernel<false>);
+    if (M->f64) return go(plateau_kernel<true, false>);
+    return (ex && ex->x) ? go(plateau_kernel<false, true>) : go(plateau_kernel<false, false>);
 }
 
 }  // namespace ofs
@@ -1524,7 +1557,8 @@ int launch_minn_peak(const ofs_rows *M, const float *chunk_max, int64_t cm_strid
                                                                    status);
         return check_launch("minn_peak_kernel");
     };
-    return M->f64 ? go(minn_peak_kernel<true>) : go(minn_peak_kernel<false>);
+    if (M->f64) return go(minn_peak_kernel<true, false>);
+    return (ex && ex->x) ? go(minn_peak_kernel<false, true>) : go(minn_peak_kernel<false, false>);
 }
 }  // namespace ofs
 

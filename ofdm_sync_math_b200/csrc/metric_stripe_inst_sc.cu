@@ -1,0 +1,7 @@
+// Explicit instantiations of the stripe kernel (metric_stripe.cuh): sc.
+#define OFS_STRIPE_INSTANTIATE
+#include "metric_stripe.cuh"
+
+namespace ofs {
+OFS_STRIPE_FOR_KIND(OFS_STRIPE_DEFINE, OFS_SC)
+}  // namespace ofs

@@ -92,11 +92,12 @@ def metric(rx, kind: str, symbol_len: int, *, want_pr: bool = True, out_f64: boo
                      n_branches=B, n_frames=F, n_samples=n, x_frame_stride=B * n, x_branch_stride=n,
                      out_stride=0, store_mode=store_mode, reserved=1 if tma_mode == 1 else 0)
     lib = L.lib()
-    stripe_ok = not out_f64 and bool(lib.ofs_metric_stripe_ok(C.byref(d), _ptr(x), None))
+    stripe_ok = not out_f64 and bool(lib.ofs_metric_stripe_ok(C.byref(d), _ptr(x), None)) and not (B > 1 and want_pr)
     # auto keeps P / R requests on the precise kernels; path="stripe" serves them from the fast kernel (float32 windows)
     use_stripe = stripe_ok and (path == "stripe" or (path == "auto" and not want_pr))
     if path == "stripe" and not use_stripe:
-        raise L.OfsError("stripe path cannot serve this request (needs c64/iq16, 1 branch, lag in {256,512,1024}, float32 outputs)")
+        raise L.OfsError("stripe path cannot serve this request (needs c64/iq16, lag in {256,512,1024}, float32 outputs; several "
+                         "branches: kind sc / sc_both / minn, M only, frame and branch pitch multiples of 128 bytes)")
     if use_stripe:
         # causal-time rows: element d of a frame lives at column toff + d, so the kernel's 16-byte
         # vector / bulk stores (which work in t = d + toff) are aligned.

@@ -48,7 +48,7 @@ def test_rtl_gate_fsm_random_masks(style):
             valid = np.ones(n, bool)
             valid[: int(rng.integers(0, max(1, n // 4)))] = False
             cp = rng.integers(0, 50, n).astype(np.float64)          # many ties: the RTL rule keeps the LAST maximum
-            ev_o, seg_o = orc.detect_minn_rtl(dict(corr_positive=cp, above=above, metric_valid=valid), hysteresis=hyst, timing_offset=-3)
+            ev_o, seg_o = orc.detect_minn_rtl(dict(corr_positive=cp, above=above, metric_valid=valid), hysteresis=hyst, timing_offset=-3, max_ev=n + 2)
             ev_g = engine.minn_rtl_events(torch.as_tensor(cp), torch.as_tensor(valid), torch.as_tensor(above), hyst, -3)[0]
             seg_g = [(int(e["gate_start"]), int(e["gate_end"])) for e in ev_g]
             assert seg_g == [tuple(s) for s in seg_o.tolist()], (style, n, hyst)
@@ -70,7 +70,7 @@ def test_zc_gate_fsm_random_masks_batched(style):
             ev_g, gm = engine.zc_events(torch.as_tensor(mag), torch.as_tensor(valid), torch.as_tensor(above), 62, hyst)
             for r in range(rows):
                 st = orc.ZCState(mag[r], np.zeros(n), np.zeros(n), np.zeros(n), above[r], valid[r])
-                ev_o, vals_o, gm_o = orc.detect_zc_peaks(st, 62, hyst)
+                ev_o, vals_o, gm_o = orc.detect_zc_peaks(st, 62, hyst, max_ev=n + 2)
                 got = [(int(e["peak_index"]), int(e["gate_start"]), int(e["gate_end"]), int(e["aux"])) for e in ev_g[r]]
                 assert got == [tuple(int(v) for v in row) for row in ev_o.tolist()], (style, n, hyst, r)
                 assert np.array_equal(gm[r].cpu().numpy().astype(bool), gm_o), (style, n, hyst, r)
@@ -98,7 +98,7 @@ def test_gate_count_beyond_event_slots():
     mag = np.where(above, 1.0, 0.0)
     ev_z, _ = engine.zc_events(torch.as_tensor(mag), torch.as_tensor(valid), torch.as_tensor(above), 62, 2)
     st = orc.ZCState(mag, np.zeros(n), np.zeros(n), np.zeros(n), above, valid)
-    ev_zo, _, _ = orc.detect_zc_peaks(st, 62, 2)
+    ev_zo, _, _ = orc.detect_zc_peaks(st, 62, 2, max_ev=n + 2)
     assert len(ev_zo) > 64 and [int(e["peak_index"]) for e in ev_z[0]] == [int(r[0]) for r in ev_zo]
 
 
@@ -140,6 +140,6 @@ def test_zc_detect_bitmask_path_equals_three_step_path(n):
         for r in range(rows):
             assert ev2[r].tolist() == ev3[r].tolist(), (n, window, hyst, r)
             st = orc.zc_streaming_detection(mag[r].astype(np.float64), window, 64, 15, 0.3)
-            ev_o, vals_o, _ = orc.detect_zc_peaks(st, 62, hyst)
+            ev_o, vals_o, _ = orc.detect_zc_peaks(st, 62, hyst, max_ev=n + 2)
             got = [(int(e["peak_index"]), int(e["gate_start"]), int(e["gate_end"]), int(e["aux"])) for e in ev2[r]]
             assert got == [tuple(int(x) for x in row) for row in ev_o.tolist()], (n, window, hyst, r)

@@ -202,19 +202,19 @@ def test_fsm_random_flags_vs_oracle():
             st = orc.zc_streaming_detection(mag[r], W, 40, 15, 0.9)
             assert np.array_equal(above[r].cpu().numpy().astype(bool), st.above_threshold)
             assert np.allclose(ls[r].cpu().numpy(), st.local_sum, rtol=1e-12, atol=1e-9)
-            ev_o, val_o, gm_o = orc.detect_zc_peaks(st, 2048, hyst)
+            ev_o, val_o, gm_o = orc.detect_zc_peaks(st, 2048, hyst, max_ev=mag.shape[1] + 2)
             e = evs[r]
             got = np.stack([e["peak_index"], e["gate_start"], e["gate_end"], e["aux"]], axis=1) if len(e) else np.zeros((0, 4), np.int64)
-            assert np.array_equal(got, ev_o[:64]), (trial, r)
-            assert np.array_equal(gm[r].cpu().numpy().astype(bool), gm_o) or len(ev_o) > 64
+            assert np.array_equal(got, ev_o), (trial, r)
+            assert np.array_equal(gm[r].cpu().numpy().astype(bool), gm_o)
             # minn_rtl FSM (last max, `>=`) on the same flags
             d = dict(corr_positive=mag[r].copy(), above=st.above_threshold, metric_valid=st.metric_valid)
-            ev_r, seg_r = orc.detect_minn_rtl(d, hysteresis=hyst, timing_offset=-7)
+            ev_r, seg_r = orc.detect_minn_rtl(d, hysteresis=hyst, timing_offset=-7, max_ev=mag.shape[1] + 2)
             er = engine.minn_rtl_events(torch.as_tensor(mag[r]).cuda(), torch.as_tensor(st.metric_valid), torch.as_tensor(st.above_threshold), hyst, -7)[0]
             closed = er[er["closed"] == 1]
             assert np.array_equal(np.stack([closed["peak_index"], closed["aux"], closed["gate_start"], closed["gate_end"]], axis=1)
                                   if len(closed) else np.zeros((0, 4), np.int64), ev_r[:len(closed)]), (trial, r)
-            assert np.array_equal(np.stack([er["gate_start"], er["gate_end"]], axis=1) if len(er) else np.zeros((0, 2), np.int64), seg_r[:64])
+            assert np.array_equal(np.stack([er["gate_start"], er["gate_end"]], axis=1) if len(er) else np.zeros((0, 2), np.int64), seg_r)
 
 
 def test_sync_pipeline_device_and_host(golden):
@@ -307,3 +307,88 @@ def test_stripe_pr_outputs_vs_oracle(kind, N, dtype):
         _check_metric(M[f:f + 1], Mo[None])
         assert np.abs(P[f] - Po).max() <= 2e-5 * np.abs(Po).max()
         assert np.abs(R[f] - Ro).max() <= 2e-5 * Ro.max()
+
+
+def _oracle_metric_branches(xb, kind, N):
+    """Float64 metric of one frame with branches (B, L): P and R summed over the branches before the non-linear step
+    (sc.py:73-74, minn.py:106-107, combined_sc_min.py:159-160)."""
+    k = {"sc": 0, "sc_both": 1, "minn": 2}[kind]
+    P = 0; R = 0
+    for b in range(xb.shape[0]):
+        _, Pb, Rb = orc.metric_prefix_c64(xb[b], N, k, want_pr=True)
+        P = P + Pb; R = R + Rb
+    num = np.maximum(P.real, 0.0) ** 2 if kind == "minn" else np.abs(P) ** 2
+    return num / np.maximum(R, 1e-12) ** 2
+
+
+@pytest.mark.parametrize("kind,N", [("sc", 2048), ("sc_both", 2048), ("minn", 2048), ("minn", 4096), ("sc", 512)])
+@pytest.mark.parametrize("B", [2, 3, 4])
+@pytest.mark.parametrize("dtype", ["c64", "iq16"])
+def test_stripe_multibranch_vs_oracle(kind, N, B, dtype):
+    """Several branches per frame on the stripe path (MB kernel variant): branch sum before the scan, 1e-4 vs the float64 oracle;
+    path="auto" must pick it when the pitches allow the tiled TMA ring."""
+    from ofdm_sync_math_b200 import engine
+    n = 36864 + 3 * 1024                # multiple of 32: 128-byte branch pitch for both dtypes; several stripes
+    F = 3
+    x = _captures(F * B, n, "minn" if kind == "minn" else "sc", seed=31).reshape(F, B, n)
+    x[1, 1] *= 0.25                     # unequal branch powers
+    if dtype == "iq16":
+        q = np.round(np.stack((x.real, x.imag), axis=-1) * 300.0).clip(-2047, 2047).astype(np.int16)
+        xd = torch.as_tensor(q).cuda()
+        x = (q[..., 0].astype(np.float32) + 1j * q[..., 1].astype(np.float32)).astype(np.complex64)
+    else:
+        xd = torch.as_tensor(x).cuda()
+    r = engine.metric(xd, kind, N, want_pr=False, path="auto", want_chunk_max=True)
+    assert r.path == "stripe"
+    M = r.M.cpu().numpy()
+    for f in range(F):
+        _check_metric(M[f:f + 1], _oracle_metric_branches(x[f], kind, N)[None])
+    toff = N - 1
+    cm = r.chunk_max.cpu().numpy()
+    full = np.zeros((F, cm.shape[1] * 256), dtype=np.float32)
+    full[:, toff:toff + M.shape[1]] = M
+    assert np.array_equal(cm, full.reshape(F, -1, 256).max(axis=2))
+    # a pitch that is not a multiple of 128 bytes falls back to the precise kernel, same tolerance
+    r2 = engine.metric(xd[:, :, :n - 8].contiguous(), kind, N, want_pr=False, path="auto")
+    assert r2.path == "tile"
+
+
+def test_stripe_multibranch_golden_two_branch_fixtures(golden):
+    """The reference's own two-branch runs (minn.py:347-351 feeds both CIR channels; combined_sc_min.py likewise) through the
+    multi-branch stripe path: complex64 copies of the fixtures' rx, zero-padded to a 128-byte pitch, metric within 1e-4 of the
+    reference's float64 arrays."""
+    from ofdm_sync_math_b200 import engine
+    for name, kinds in (("minn_cir1", (("minn", "M"),)), ("combined_cir1", (("minn", "M"), ("sc_both", "M_sc")))):
+        g = golden(name)
+        rx = np.asarray(g["rx"])
+        assert rx.ndim == 2 and rx.shape[0] == 2
+        L = rx.shape[1]
+        Lp = (L + 15) // 16 * 16
+        x = np.zeros((1, 2, Lp), dtype=np.complex64)
+        x[0, :, :L] = rx.astype(np.complex64)
+        for kind, key in kinds:
+            if key not in g:
+                continue
+            r = engine.metric(torch.as_tensor(x).cuda(), kind, 2048, want_pr=False, path="auto")
+            assert r.path == "stripe"
+            Mref = np.asarray(g[key], dtype=np.float64)
+            M = r.M.cpu().numpy()[0, :Mref.size].astype(np.float64)
+            assert np.max(np.abs(M - Mref) / np.maximum(Mref, 1e-6)) <= 1e-4
+
+
+def test_sync_pipeline_two_branches_exact():
+    """ofs_sync on two-branch frames (stripe MB kernel + exact detector + branch-summed P / CFO record) vs the float64 oracle."""
+    from ofdm_sync_math_b200 import engine
+    F, B, n = 6, 2, 40960
+    x = _captures(F * B, n, "sc", seed=41).reshape(F, B, n)
+    plan = engine.SyncPlan(F, n, "sc", 2048, "c64", cp_len=512, smooth_win=16, sc_delta=16, n_branches=B)
+    xd = torch.as_tensor(x).cuda()
+    plan.run(xd)
+    plan.resolve(xd)
+    rec = plan.records_numpy()
+    for f in range(F):
+        Mo = _oracle_metric_branches(x[f], "sc", 2048)
+        assert int(rec["timing"][f]) == orc.find_plateau_end_from_metric(Mo, 512, 128, 16)
+        c = int(rec["coarse"][f])
+        P = sum(orc.metric_prefix_c64(x[f, b], 2048, 0, want_pr=True)[1][c] for b in range(B))
+        assert abs(rec["cfo"][f] + np.angle(P) / (2 * np.pi * 1024)) * 2 * np.pi <= 1e-5

@@ -69,14 +69,53 @@ class StdoutToStderr:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (recipe of B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region.  The region is K steps of ~2.4 ms -- far shorter than
+    nvidia-smi's 100 ms loop -- so a thread polls NVML directly every ~2 ms (nvmlDeviceGetClockInfo +
+    nvmlDeviceGetCurrentClocksEventReasons; the recipe's nvidia-smi query reads the same counters).  If the region is too short to
+    hold even one sample, one is taken right after its last kernel was queued (the GPU is still executing it).
+    Falls back to `nvidia-smi -lms` when pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index: int):
         self.rows, self.proc, self.index = [], None, index
+        self.nv, self.h, self.stop_flag, self.thread = None, None, False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in vis.split(",") if v.strip().isdigit()]
+            phys = int(ids[index]) if index < len(ids) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
+
+    def _sample(self):
+        nv = self.nv
+        try:
+            sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+            try:
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.rows.append((time.time(), float(sm), int(rs)))
+        except Exception:
+            pass
+
+    def _poll(self):
+        while not self.stop_flag:
+            self._sample()
+            time.sleep(0.002)
 
     def start(self):
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -88,7 +127,31 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
+    def mark_queued(self):
+        """Call right after the last kernel of the timed region was queued (before the synchronize): guarantees a sample
+        taken while the region is executing."""
+        if self.nv is not None:
+            self._sample()
+
     def stop(self, t0: float, t1: float) -> dict:
+        if self.nv is not None:
+            self.stop_flag = True
+            if self.thread is not None:
+                self.thread.join(timeout=1.0)
+            nv = self.nv
+            try:
+                mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            except Exception:
+                mx = None
+            inside = [(sm, rs) for ts, sm, rs in self.rows if t0 <= ts <= t1]
+            reasons = set()
+            for _, rs in inside:
+                for bit, nm in self.REASONS.items():
+                    if rs & bit:
+                        reasons.add(nm)
+            sm = [v for v, _ in inside]
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                    "samples": len(sm), "source": "nvml, polled every ~2 ms inside the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -106,7 +169,8 @@ class ClockSampler:
             for nm, val in zip(names, f[4:8]):
                 if val.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi -lms 100"}
 
 
 def cpu_port_rate(frames, n_threads: int, results: list | None = None) -> float:
@@ -153,12 +217,23 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": METRIC, "value": v, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * n_frames * args.samples / (v * 1e6), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "frames_per_gpu": args.frames, "samples_per_frame": args.samples},
+        "config": config_dict(args, args.gpus),
+        "reference_arm": {"frames_per_step": n_frames, "what": "bounded sample of the workload per step (the CPU needs ~2 s for 32 frames)"},
         "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference itself is pure Python (0.21 Msamples/s/core for sc_streaming_metric, BASELINE.md); "
                 "this arm is its C restatement, the fastest honest CPU form of the same algorithm",
     }))
+
+
+def config_dict(args, world: int) -> dict:
+    """The `config` object -- identical in both arms (ours / --impl reference) for the same command line."""
+    F, n = args.frames, args.samples
+    return {"workload": workload_name(args), "frames_per_gpu": F, "samples_per_frame": n, "n_fft": N_FFT, "cp_len": CP_LEN,
+            "smooth_win": SMOOTH, "sc_delta": SC_DELTA,
+            "l2": f"inputs larger than L2 ({F * n * 8 / 1e9:.2f} GB of samples per GPU, no flush needed)",
+            "e2e_frames_per_step": min(args.e2e_frames, F),
+            "parallelism": f"frames sharded over {world} GPU(s), no sample-path collective"}
 
 
 def workload_name(args) -> str:
@@ -178,6 +253,8 @@ def main() -> None:
     ap.add_argument("--store-mode", type=int, default=0)
     ap.add_argument("--tma-mode", type=int, default=2, help="2: tiled tensor-map copies with 128B swizzle, 1: 1-D bulk copies")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` object (the other BASELINE.json configs)")
+    ap.add_argument("--configs-scale", type=float, default=1.0, help="batch scale of the `configs` measurements")
     ap.add_argument("--no-exact", action="store_true", help="decide on the float32 metric only (no float64 re-evaluation of in-band decisions)")
     ap.add_argument("--exact-band", type=float, default=0.0, help="relative half-width of the float32 uncertainty band (0: library default)")
     args = ap.parse_args()
@@ -239,6 +316,7 @@ def main() -> None:
             if k == args.steps - 1:
                 gather.drain()                  # every gather finishes inside the timed region
         ev[k][2].record()
+    sampler.mark_queued()
     torch.cuda.synchronize()
     t_wall1 = time.time()
     if world > 1:
@@ -260,15 +338,21 @@ def main() -> None:
     alg_bytes = F * (8 * n + 4 * out_len)
     k_ms = float(statistics.mean(kern_ms))
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    traffic = None
+    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel, recorded per FRAME so that it
+    # scales with the launch it is printed next to (profiles/traffic.json names the frame count of the capture)
+    traffic, traffic_src = None, None
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists():
         try:
-            traffic = json.loads(tf.read_text()).get("metric_stripe_kernel_bytes_per_launch")
+            tj = json.loads(tf.read_text())
+            per_frame = float(tj["metric_stripe_kernel_bytes_per_launch"]) / float(tj.get("frames", 1024))
+            if int(tj.get("samples_per_frame", 262144)) == n:
+                traffic = per_frame * F
+                traffic_src = f"ncu capture at {int(tj.get('frames', 1024))} frames x {n} ({tj.get('source', '')}), scaled to {F} frames"
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "metric_stripe_kernel<4,SC,c64>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "peak_kind": peak_kind, "traffic": traffic, "kernel_ms": k_ms,
+                "frac": achieved / hbm_peak, "peak_kind": peak_kind, "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_share_of_step": k_ms / ms_per_step,
                 "frac_of_8TBs_spec": achieved / 8000.0}
 
@@ -298,7 +382,7 @@ def main() -> None:
     rec_d = plan.records_numpy()
     e2e_match = bool((rec_h["timing"] == rec_d["timing"][:Fe]).all())
     hs.close()
-    e2e = {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": Fe * n * 8, "d2h_bytes_per_step": Fe * (out_len * 4 + 32),
+    e2e = {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": Fe * n * 8, "d2h_bytes_per_step": Fe * (out_len * 4 + engine.REC_BYTES),
            "frames_per_step": Fe, "steps": e_steps, "records_match_device_path": e2e_match,
            "api": "ofs_sync_host (pinned host x -> M + records in host memory)"}
 
@@ -328,6 +412,17 @@ def main() -> None:
                                  "exact_moved_indices": int(((rec_d["status"] & 2) != 0).sum()),
                                  "unresolved_frames": int(((rec_d["status"] & 4) != 0).sum())}}
 
+    # ---- the other BASELINE.json configs (cfg 1, 3, 4, 5), a few timed launches each on this GPU (N = 1 only)
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        import bench_configs
+        del plan, x, xh, Mh
+        torch.cuda.empty_cache()
+        try:
+            configs = bench_configs.baseline_configs(args.configs_scale, local)
+        except Exception as e:           # the headline line must survive a failure here
+            configs = {"error": f"{type(e).__name__}: {e}"}
+
     if quiet is not None:
         quiet.stop()
     if rank == 0:
@@ -335,10 +430,11 @@ def main() -> None:
             "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(args), "frames_per_gpu": F, "samples_per_frame": n, "n_fft": N_FFT,
-                       "l2": f"inputs larger than L2 ({F * n * 8 / 1e9:.2f} GB of samples per GPU, no flush needed)",
-                       "store_mode": args.store_mode, "tma_mode": args.tma_mode, "parallelism": f"frames sharded over {world} GPU(s), no sample-path collective"},
+            "config": config_dict(args, world),
+            "kernel_options": {"store_mode": args.store_mode, "tma_mode": args.tma_mode, "exact": not args.no_exact,
+                               "exact_band": args.exact_band or 1e-5},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "configs": configs,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -37,27 +37,51 @@ def timeit(fn, steps=5, warmup=3):
     return e0.elapsed_time(e1) / steps
 
 
+class _Args:
+    def __init__(self, scale, cases):
+        self.scale, self.cases = scale, cases
+
+
+BASELINE_CASES = "rtl,minn,combined,park,zc,zcfreq,bank,aa64,mb"
+
+
+def baseline_configs(scale: float = 1.0, device_index: int = 0) -> dict:
+    """The BASELINE.json configs other than the headline, for bench.py's `configs` object: a few timed launches each on this
+    GPU, keyed cfg1 / cfg3_* / cfg4_* / cfg5 (entries that carry a `key`)."""
+    out = {}
+    run_cases(_Args(scale, BASELINE_CASES), lambda d: out.__setitem__(d["key"], {k: v for k, v in d.items() if k != "key"}) if "key" in d else None,
+              device_index)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
-    ap.add_argument("--cases", default="minn,iq16,chan,rx,combined,park,zc,zcfreq,bank,aa64,rtl,dropin,tile")
+    ap.add_argument("--cases", default="minn,iq16,chan,rx,combined,park,zc,zcfreq,bank,aa64,rtl,mb,dropin,tile")
     a = ap.parse_args()
+    run_cases(a, lambda d: print(json.dumps(d), flush=True))
+
+
+def run_cases(a, sink, device_index: int = 0):
     import numpy as np
     import torch
     from ofdm_sync_math_b200 import engine, synth
     from ofdm_sync_math_b200.zc import build_pss_symbol, generate_zadoff_chu
-    dev = torch.device("cuda", 0)
+    dev = torch.device("cuda", device_index)
     hbm = peaks()
     cases = a.cases.split(",")
 
-    def emit(name, ms, samples, alg_bytes=None, flops=None, note=""):
+    def emit(name, ms, samples, alg_bytes=None, flops=None, note="", key=None):
         d = {"case": name, "ms": ms, "Msamples_per_s": samples / (ms * 1e-3) / 1e6, "note": note}
+        if key:
+            d["key"] = key
         if alg_bytes is not None:
             d["roofline"] = {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                             "frac": alg_bytes / (ms * 1e-3) / 1e9 / hbm}
+                             "frac": alg_bytes / (ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": alg_bytes}
         if flops is not None:
-            d["flops"] = {"achieved_tflops": flops / (ms * 1e-3) / 1e12, "fp32_fma_peak_tflops_nominal": 80.0}
-        print(json.dumps(d), flush=True)
+            d["flops"] = {"achieved_tflops": flops / (ms * 1e-3) / 1e12, "fp32_fma_peak_tflops": 74.4,
+                          "frac": flops / (ms * 1e-3) / 1e12 / 74.4, "algorithmic_flops": flops}
+        sink(d)
 
     if "minn" in cases:
         # cfg 3: Minn metric + find_minn_peak + CFO, 1 M-sample captures x 1024 streams
@@ -67,8 +91,8 @@ def main():
         ms_k = timeit(lambda: plan.run_metric_only(x))
         ms = timeit(lambda: plan.run(x))
         emit("cfg3 minn metric kernel (stripe, D=512)", ms_k, F * n, alg_bytes=F * (8 * n + 4 * (n - 2047)))
-        emit("cfg3 minn metric + find_minn_peak + CFO", ms, F * n, alg_bytes=F * (8 * n + 4 * (n - 2047)),
-             note="roofline figure uses the metric kernel's algorithmic bytes over the whole step")
+        emit("cfg3 minn metric + find_minn_peak (exact mode) + CFO", ms, F * n, alg_bytes=F * (8 * n + 4 * (n - 2047)), key="cfg3_minn",
+             note=f"{F} streams x {n} c64; metric kernel alone {ms_k:.3f} ms; roofline figure = the metric kernel's algorithmic bytes over the whole step")
         del x, plan
     if "iq16" in cases:
         # cfg 2 with int16-IQ ingest (4 B/sample in, 4 B/sample out)
@@ -133,7 +157,8 @@ def main():
         ms = timeit(run_fused, steps=3, warmup=2)
         same = bool(torch.equal(run()[: F], run_fused()[0]))
         emit("cfg3 combined, fused detector (no gate array): Minn + S&C(both halves) metrics + ofs_combined_peak", ms, F * n,
-             alg_bytes=2 * F * (8 * n + 4 * (n - 2047)), note=f"peaks equal to the gate + gated-peak path: {same}")
+             alg_bytes=2 * F * (8 * n + 4 * (n - 2047)), key="cfg3_combined",
+             note=f"{F} streams x {n} c64; peaks equal to the gate + gated-peak path: {same}")
         del x
     if "park" in cases:
         F, n = max(int(64 * a.scale), 2), 1 << 18
@@ -141,7 +166,7 @@ def main():
         ms = timeit(lambda: engine.park_metric(x, 2048), steps=3, warmup=2)
         nout = n - 2048
         emit("cfg3 park metric (1024 complex MACs per output, 8x8 register tiles, de-interleaved smem)", ms, F * n, flops=F * nout * 1024 * 8,
-             note="FMA-bound (SURVEY 7.3-4); flops = 8 per complex MAC (the sliding energy is no longer recomputed per lag); fp32 peak 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s")
+             key="cfg3_park", note=f"{F} streams x {n} c64 (the O(h) direct form: 1024 streams x 1 M would be 8.8e15 flop); FMA-bound (SURVEY 7.3-4); flops = 8 per complex MAC (the sliding energy is no longer recomputed per lag); fp32 peak 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s")
         del x
     if "zc" in cases:
         # cfg 4 (single root): overlap-save matched filter + zc_v2 streaming detection + gate FSM
@@ -156,7 +181,7 @@ def main():
         ms_mf = timeit(lambda: engine.zc_matched_filter(x, ref, mode=1, out_f64=False), steps=3, warmup=2)
         ms = timeit(run, steps=3, warmup=2)
         emit("cfg4 zc matched filter (smem FFT overlap-save, fp32)", ms_mf, F * n, alg_bytes=F * (8 * n + 12 * (n + 2047)),
-             note="8 B in + 8 B corr + 4 B |corr| out per sample")
+             note="8 B in + 8 B corr + 4 B |corr| out per sample", key="cfg4_mf")
         emit("cfg4 zc_v2 pipeline: matched filter + running-sum threshold + gate FSM", ms, F * n)
 
         def run_fused():
@@ -166,7 +191,7 @@ def main():
         a3, a2 = run()[0], run_fused()
         same = all(u.tolist() == v.tolist() for u, v in zip(a3, a2))
         emit("cfg4 zc_v2 pipeline, threshold kernel and gate FSM exchanging a bitmask (ofs_zc_detect)", ms, F * n,
-             note=f"events equal to the three-call path: {same}")
+             note=f"events equal to the three-call path: {same}", key="cfg4_zc_v2_detect")
         del x
     if "zcfreq" in cases:
         F, n = max(int(256 * a.scale), 4), 65536
@@ -176,10 +201,12 @@ def main():
         tb = generate_zadoff_chu(25, 62)
         ms = timeit(lambda: engine.zc_freq_metric(x, bi, tb, 62.0, out_f64=False), steps=3, warmup=2)
         emit("cfg4 zc_freq metric (62-bin sliding DFT, float64 prefix)", ms, F * n, flops=F * (n - 2559) * 62 * 2 * 16,
-             note="flops ~ 62 bins x 2 (tile halo) x ~16 per modulated-prefix sample")
+             note=f"{F} captures x {n}; flops ~ 62 bins x 2 (tile halo) x ~16 per modulated-prefix sample (float64: the fp32 peak does not apply)",
+             key="cfg4_zcfreq_f64")
         ms = timeit(lambda: engine.zc_freq_metric(x, bi, tb, 62.0, out_f64=False, fast=True), steps=3, warmup=2)
         emit("cfg4 zc_freq metric, fast path (bank kernel: sliding-DFT recurrence + tcgen05, one template)", ms, F * n,
-             alg_bytes=F * (8 * n + 4 * (n - 2559)), note="8 B in + 4 B metric out per sample; FP16 operands, 5e-3 tolerance")
+             alg_bytes=F * (8 * n + 4 * (n - 2559)), note="8 B in + 4 B metric out per sample; FP16 operands, 5e-3 tolerance",
+             key="cfg4_zcfreq_fast")
         del x
     if "bank" in cases:
         # cfg 4 (bank): 64 ZC roots x 2048 captures x every offset; fused sliding-DFT producer + tcgen05 kind::f16 MMA
@@ -196,7 +223,8 @@ def main():
              "tensor": {"issued_tflops": F * noff * 2.0 * 128 * 128 / (ms * 1e-3) / 1e12,
                         "useful_tflops_8KR": F * noff * 8.0 * 62 * 64 / (ms * 1e-3) / 1e12,
                         "note": "issued = one 128x128x128 fp16 MMA group (fp32 accumulate) per 128 offsets; useful = 8*K*R, K=62 bins, R=64 roots (SURVEY 8d)"}}
-        print(json.dumps(d), flush=True)
+        d["key"] = "cfg4_bank"
+        sink(d)
         del x
     if "aa64" in cases:
         # cfg 5: 64-antenna [A][A] combining, 8 captures per GPU x 64 antennas x 262144 c64
@@ -211,7 +239,7 @@ def main():
         emit("cfg5 sync_aa 64-antenna metric, array kernel (TMA ring, antenna sum on chip; M,P,R out)", ms_k, F * A * n,
              alg_bytes=F * n * (8 * A + 16), note="8*A B in + M,P,R out per output sample")
         emit("cfg5 sync_aa 64-antenna fused detector: array kernel (M,P + bitmask) + gate FSM + CFO", ms, F * A * n,
-             alg_bytes=F * n * (8 * A + 12))
+             alg_bytes=F * n * (8 * A + 12), key="cfg5", note=f"{F} captures x {A} antennas x {n} c64 per GPU")
         del x, plan
         xi = torch.randint(-2047, 2048, (F, A, n, 2), dtype=torch.int16, device=dev)
         plan = engine.AADetectPlan(F, A, n, 512, 0.15, 128, 15.36e6, in_dtype="iq16")
@@ -227,8 +255,18 @@ def main():
             return engine.minn_rtl_events(d["corr_positive"], d["metric_valid"], d["above_threshold"], 2, 0)
         ms = timeit(run, steps=3, warmup=2)
         emit("cfg1 minn_rtl integer datapath + gate FSM (reference-order streams)", ms, F * A * n, alg_bytes=F * n * (4 * A + 4 * 8 + 2),
-             note="one thread per stream; int64 outputs dominate the traffic")
+             note=f"{F} streams x {A} antennas x {n} int16 IQ; int64 arrays out", key="cfg1_rtl_int")
         del iq
+    if "mb" in cases:
+        # two branches per frame (what minn.py:347-351 feeds): multi-branch stripe kernel vs the precise tile kernel
+        B, n = 2, 262144
+        F = max(int(1024 * a.scale), 8)
+        x = synth.make_batch_device(F * B, n, "sc", seed=15, device=dev, chunk=64).reshape(F, B, n)
+        for kind in ("sc", "minn"):
+            ms = timeit(lambda: engine.metric(x, kind, 2048, want_pr=False, path="auto", want_chunk_max=True), steps=5, warmup=3)
+            emit(f"{kind} metric, {B} branches summed on chip (multi-branch stripe kernel)", ms, F * B * n, alg_bytes=F * (8 * B * n + 4 * (n - 2047)),
+                 key=f"two_branch_{kind}", note=f"{F} frames x {B} branches x {n} c64")
+        del x
     if "agree" in cases:
         # how often does the float32 fast path pick a different timing index than a float64 metric on the same input?
         F, n = max(int(1024 * a.scale), 8), 262144
@@ -241,8 +279,8 @@ def main():
             t64 = engine.find_plateau_end(r.M, 512, 128, 16).cpu().numpy()
             d = np.abs(t64 - fast[f0:f0 + 128])
             diff += int((d != 0).sum()); big += int((d > 1).sum())
-        print(json.dumps({"case": "agreement of timing indices: float32 stripe path vs float64 tile path (same complex64 input)",
-                          "frames": F, "frames_with_different_index": diff, "of_which_differ_by_more_than_1": big}), flush=True)
+        sink({"case": "agreement of timing indices: float32 stripe path vs float64 tile path (same complex64 input)",
+              "frames": F, "frames_with_different_index": diff, "of_which_differ_by_more_than_1": big})
         del x, plan
     if "dropin" in cases:
         # the reference's own call signature: numpy complex128 in -> numpy float64 / complex128 out (H2D + kernel + D2H per call)
@@ -263,9 +301,9 @@ def main():
             torch.cuda.synchronize()
             dt = (time.perf_counter() - t0) / 3
             ns = rx.size if name.startswith(("sc.", "minn.")) else 1 << 18
-            print(json.dumps({"case": f"drop-in {name}: numpy complex128 in -> numpy out, one capture of {ns} samples", "ms": dt * 1e3,
-                              "Msamples_per_s": ns / dt / 1e6,
-                              "note": "wall clock incl. H2D, float64 kernel, D2H; the reference Python runs these at 0.21 / 0.04 / 0.12 Msamples/s (BASELINE.md)"}), flush=True)
+            sink({"case": f"drop-in {name}: numpy complex128 in -> numpy out, one capture of {ns} samples", "ms": dt * 1e3,
+                  "Msamples_per_s": ns / dt / 1e6,
+                  "note": "wall clock incl. H2D, float64 kernel, D2H; the reference Python runs these at 0.21 / 0.04 / 0.12 Msamples/s (BASELINE.md)"})
     if "tile" in cases:
         F, n = max(int(512 * a.scale), 8), 262144
         x = synth.make_batch_device(F, n, "sc", seed=13, device=dev, chunk=64)[:, None]

@@ -202,6 +202,15 @@ int ofs_zc_detect(const ofs_rows *corr_mag, int32_t window, int32_t thresh_value
                   int32_t reference_length, int32_t hysteresis, uint32_t *mask_ws, int64_t mask_stride, ofs_event *events,
                   int32_t *n_events, int32_t max_events, void *stream);
 
+/* zc_v2.detect_zc_preamble -- zc_v2.py:456-516 -- for a batch of complex64 / int16-IQ captures in three launches on the float32
+ * path: matched filter (8192-point overlap-save blocks when the capture is long enough) writing |corr| only (normalize != 0:
+ * per-branch normalisation, then branch sum, :488-495), running-sum threshold -> bitmask (:288-336), gate FSM (:360-450).
+ * mag_ws: float[n_frames][mag_stride >= n + nr - 1] (the corr_mag rows, kept for the caller); mask_ws as ofs_zc_detect. */
+int ofs_zc_v2_detect(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_branches, int64_t n, const void *ref_c128,
+                     int32_t nr, int32_t normalize, int32_t window, int32_t thresh_value, int32_t frac_bits,
+                     double min_corr_mag, int32_t hysteresis, float *mag_ws, int64_t mag_stride, uint32_t *mask_ws,
+                     int64_t mask_stride, ofs_event *events, int32_t *n_events, int32_t max_events, void *stream);
+
 /* minn_rtl.detect_minn_rtl -- minn_rtl.py:750-825 (== ref/minn_preamble_detector.sv:337-384).
  * corr_positive rows: float64, or int64 when is_int != 0 (integer RTL mode).  An unclosed tail gate
  * is returned as an event with closed == 0 (the reference reports it as a segment, not an event). */

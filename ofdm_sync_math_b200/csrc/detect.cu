@@ -1213,6 +1213,67 @@ __global__ void __launch_bounds__(DNT) zc_stream_kernel(RowView r, int W, double
     }
 }
 
+// Bitmask-only form of the threshold for float32 rows (the fused zc_v2 pipeline): zc_stream_kernel moves every sample through
+// shared memory seven times as a double (84 B per sample with its 50 % halo) and that, not HBM, bounds it.  Here a thread
+// owns 32 CONSECUTIVE samples: float32 samples cross shared memory once (coalesced load, padded so that the 32-sample
+// thread stride is conflict-free), the float64 inclusive prefix of the thread's samples lives in registers, only the prefix
+// goes back to shared memory (padded, conflict-free) and every window sum is (own register) - (one shared load at i - W).
+// The thread's 32 flags are one word of the bitmask.  Tile = TMZ outputs + a halo of >= W samples owned by extra warps.
+constexpr int TMZ = 8192;
+__global__ void __launch_bounds__(512) zc_thresh_mask_kernel(const float *mag, int64_t n, int64_t stride, int W, double thresh_value,
+                                                             double scale, double min_mag, unsigned *bitmask, int64_t bm_stride,
+                                                             int halo_threads)
+{
+    extern __shared__ __align__(16) unsigned char tsm[];
+    const int nthr = (int)blockDim.x, nel = nthr * 32;
+    double *P = reinterpret_cast<double *>(tsm);                              // inclusive prefix, padded: P[i + i / 32]
+    float *ms = reinterpret_cast<float *>(tsm);                               // samples, padded the same way; dead before P is written
+    __shared__ double wtot[16];
+    const int64_t row = blockIdx.y;
+    const int64_t i0 = (int64_t)blockIdx.x * TMZ;
+    const int64_t j0 = i0 - (int64_t)halo_threads * 32;                       // first sample of the tile (may be negative)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *mr = mag + row * stride;
+    for (int k = tid; k < nel; k += nthr) {
+        const int64_t j = j0 + k;
+        ms[k + (k >> 5)] = (j >= 0 && j < n) ? __ldg(mr + j) : 0.f;
+    }
+    __syncthreads();
+    double pre[32];
+    float mv[32];
+    double run = 0.0;
+    const int b = tid * 33;                                                   // padded index of this thread's first sample
+#pragma unroll
+    for (int e = 0; e < 32; ++e) { mv[e] = ms[b + e]; run += (double)mv[e]; pre[e] = run; }
+    double t = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double y = shfl_up_f64(t, o); if (lane >= o) t += y; }
+    if (lane == 31) wtot[warp] = t;
+    __syncthreads();
+    double off = t - run;
+    for (int w = 0; w < warp; ++w) off += wtot[w];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) { pre[e] += off; P[b + e] = pre[e]; }
+    __syncthreads();
+    if (tid < halo_threads) return;                                           // halo warps own no outputs
+    const int64_t ibase = j0 + (int64_t)tid * 32;                             // first output of this thread
+    if (ibase >= n) return;
+    unsigned word = 0u;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+        const int64_t i = ibase + e;
+        // local_sum[i] = prefix(i) - prefix(i - W) (inclusive prefixes; nothing to subtract while the window is still filling)
+        const int kl = tid * 32 + e - W;                                      // tile index of sample i - W (>= 0: the halo covers W)
+        const int64_t jl = i - W;
+        const double lo = jl >= 0 ? P[kl + (kl >> 5)] : 0.0;
+        const double sum = pre[e] - lo;
+        const double m = (double)mv[e];
+        const bool ab = i < n && i >= W && (m * scale >= sum * thresh_value) && (m >= min_mag);
+        word |= ab ? 1u << e : 0u;
+    }
+    bitmask[row * bm_stride + (ibase >> 5)] = word;
+}
+
 // ---- gate / hysteresis FSMs ------------------------------------------------------------------------
 enum { FSM_AA = 0, FSM_ZC = 1, FSM_RTL = 2 };
 
@@ -1736,16 +1797,52 @@ OFS_API int ofs_zc_detect(const ofs_rows *corr_mag, int32_t window, int32_t thre
     const int W = window > 1 ? window : 1;
     OFS_REQUIRE(W <= 16384, "ofs_zc_detect: window > 16384 unsupported");
     OFS_REQUIRE(corr_mag->n_rows < 65536, "ofs_zc_detect: too many rows");
-    dim3 grid((unsigned)((corr_mag->n + ZT - 1) / ZT), (unsigned)corr_mag->n_rows);
-    const size_t zsm = (size_t)(ZT + W + 2) * sizeof(double);
-    OFS_CUDA(cudaFuncSetAttribute(zc_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsm));
-    zc_stream_kernel<<<grid, DNT, zsm, (cudaStream_t)stream>>>(view(corr_mag), W, (double)thresh_value, (double)(1LL << frac_bits),
-                                                            min_corr_mag, nullptr, nullptr, nullptr, 0, mask_ws, mask_stride);
-    if (int rc = check_launch("zc_stream_kernel")) return rc;
+    if (!corr_mag->f64 && W <= 8192) {
+        // float32 rows: the register-prefix kernel (one mask word per thread)
+        const int halo_threads = ((W + 31) / 32 + 31) / 32 * 32;              // whole warps, >= W samples
+        const int nthr = TMZ / 32 + halo_threads;
+        const size_t tsm = (size_t)(nthr * 32 + nthr + 2) * sizeof(double);
+        dim3 grid2((unsigned)((corr_mag->n + TMZ - 1) / TMZ), (unsigned)corr_mag->n_rows);
+        static PerDeviceOnce once;
+        if (!once.done()) {
+            OFS_CUDA(cudaFuncSetAttribute(zc_thresh_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            once.mark();
+        }
+        zc_thresh_mask_kernel<<<grid2, nthr, tsm, (cudaStream_t)stream>>>(reinterpret_cast<const float *>(corr_mag->data), corr_mag->n,
+                                                                         corr_mag->stride, W, (double)thresh_value,
+                                                                         (double)(1LL << frac_bits), min_corr_mag, mask_ws, mask_stride,
+                                                                         halo_threads);
+        if (int rc = check_launch("zc_thresh_mask_kernel")) return rc;
+    } else {
+        dim3 grid((unsigned)((corr_mag->n + ZT - 1) / ZT), (unsigned)corr_mag->n_rows);
+        const size_t zsm = (size_t)(ZT + W + 2) * sizeof(double);
+        OFS_CUDA(cudaFuncSetAttribute(zc_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsm));
+        zc_stream_kernel<<<grid, DNT, zsm, (cudaStream_t)stream>>>(view(corr_mag), W, (double)thresh_value, (double)(1LL << frac_bits),
+                                                                min_corr_mag, nullptr, nullptr, nullptr, 0, mask_ws, mask_stride);
+        if (int rc = check_launch("zc_stream_kernel")) return rc;
+    }
     FsmParams p{};
     p.val = view(corr_mag); p.L = reference_length; p.heff = hysteresis > 1 ? hysteresis : 1; p.events = events; p.n_events = n_events;
     p.max_events = max_events; p.premask = mask_ws; p.premask_stride = mask_stride;
     return launch_fsm<FSM_ZC>(p, corr_mag->n_rows, (cudaStream_t)stream);
+}
+
+OFS_API int ofs_zc_v2_detect(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_branches, int64_t n, const void *ref_c128,
+                             int32_t nr, int32_t normalize, int32_t window, int32_t thresh_value, int32_t frac_bits,
+                             double min_corr_mag, int32_t hysteresis, float *mag_ws, int64_t mag_stride, uint32_t *mask_ws,
+                             int64_t mask_stride, ofs_event *events, int32_t *n_events, int32_t max_events, void *stream)
+{
+    OFS_REQUIRE(x && ref_c128 && mag_ws && mask_ws && events && n_events, "ofs_zc_v2_detect: null argument");
+    OFS_REQUIRE(in_dtype == OFS_C64 || in_dtype == OFS_IQ16, "ofs_zc_v2_detect: complex64 or int16 IQ captures (float32 pipeline)");
+    const int64_t n_out = n + nr - 1;
+    OFS_REQUIRE(mag_stride >= n_out && mask_stride >= (n_out + 31) / 32, "ofs_zc_v2_detect: workspace pitch too small");
+    // |corr| only (4 bytes per sample leave the filter), mode 1 = per-branch normalisation (zc_v2.py:488-495), mode 2 = raw
+    if (int rc = ofs_zc_matched_filter(x, in_dtype, n_frames, n_branches, n, ref_c128, nr, normalize ? 1 : 2, 0, nullptr, mag_ws, mag_stride,
+                                       stream))
+        return rc;
+    ofs_rows rows{mag_ws, 0, 0, n_frames, n_out, mag_stride};
+    return ofs_zc_detect(&rows, window, thresh_value, frac_bits, min_corr_mag, nr, hysteresis, mask_ws, mask_stride, events, n_events,
+                         max_events, stream);
 }
 
 OFS_API int ofs_minn_rtl_events(const void *corr_positive, int32_t is_int, const uint8_t *valid, const uint8_t *above,

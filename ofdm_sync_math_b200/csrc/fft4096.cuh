@@ -165,4 +165,64 @@ __device__ void ifft_dit(C2 *a, const double2 *tw)
     __syncthreads();
 }
 
+// ---- 8192-point FFT = one radix-2 stage + two 4096-point FFTs -----------------------------------------------------------
+// DIF: y0[n] = x[n] + x[n + 4096], y1[n] = (x[n] - x[n + 4096]) W8192^n, then X[2m] = FFT4096(y0)[m], X[2m + 1] = FFT4096(y1)[m].
+// The array is two padded 4096-blocks (ZFP elements each); output order = the 4096-point digit reversal inside each block.
+// The inverse runs the graph backwards (two unscaled inverse 4096-point transforms, then x[n], x[n + 4096] =
+// E[n] +- conj(W8192^n) O[n]; multiply by 1 / 8192 afterwards).  W8192^(t + 256 q) = W8192^t W32^q: one table entry per
+// thread (tw8: float2[256] / double2[256]) and compile-time constants.
+constexpr int ZF8 = 8192;
+constexpr int ZFP8 = 2 * ZFP;
+__device__ __forceinline__ int zpad8(int i) { return (i >> 12) * ZFP + zpad(i & (ZF - 1)); }
+
+template <typename C2>
+__device__ __forceinline__ C2 w32_const(int q)        // exp(-2 pi i q / 32), q < 16 (compile-time after unrolling)
+{
+    using T = decltype(C2{}.x);
+    constexpr double c[16] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708, 0.70710678118654752440,
+                              0.55557023301960222474, 0.38268343236508977173, 0.19509032201612826785, 0.0, -0.19509032201612826785,
+                              -0.38268343236508977173, -0.55557023301960222474, -0.70710678118654752440, -0.83146961230254523708,
+                              -0.92387953251128675613, -0.98078528040323044913};
+    constexpr double sn[16] = {0.0, 0.19509032201612826785, 0.38268343236508977173, 0.55557023301960222474, 0.70710678118654752440,
+                               0.83146961230254523708, 0.92387953251128675613, 0.98078528040323044913, 1.0, 0.98078528040323044913,
+                               0.92387953251128675613, 0.83146961230254523708, 0.70710678118654752440, 0.55557023301960222474,
+                               0.38268343236508977173, 0.19509032201612826785};
+    C2 w; w.x = (T)c[q]; w.y = (T)(-sn[q]);
+    return w;
+}
+
+template <typename C2>
+__device__ void fft8k_dif(C2 *a, const double2 *tw, C2 w0 /* exp(-2 pi i threadIdx.x / 8192) */)
+{
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int n = zpad(t + 256 * q);
+        const C2 u = a[n], v = a[ZFP + n];
+        a[n] = cadd(u, v);
+        const C2 d = csub(u, v);
+        a[ZFP + n] = q == 0 ? cmul(d, w0) : cmul(cmul(d, w0), w32_const<C2>(q));
+    }
+    __syncthreads();
+    fft_dif<C2>(a, tw);
+    fft_dif<C2>(a + ZFP, tw);
+}
+template <typename C2>
+__device__ void ifft8k_dit(C2 *a, const double2 *tw, C2 w0)
+{
+    ifft_dit<C2>(a, tw);
+    ifft_dit<C2>(a + ZFP, tw);
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int n = zpad(t + 256 * q);
+        const C2 u = a[n];
+        C2 v = cmulc(a[ZFP + n], w0);
+        if (q != 0) v = cmulc(v, w32_const<C2>(q));
+        a[n] = cadd(u, v);
+        a[ZFP + n] = csub(u, v);
+    }
+    __syncthreads();
+}
+
 }  // namespace ofs

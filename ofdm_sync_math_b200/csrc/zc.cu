@@ -11,6 +11,7 @@
 //                       instead of one 2048-point FFT per candidate offset.
 #include "common.cuh"
 #include "fft4096.cuh"
+#include <cstdlib>
 
 namespace ofs {
 
@@ -170,6 +171,123 @@ __global__ void __launch_bounds__(ZNT, (sizeof(T) == 4 ? 3 : 1)) zc_mf_kernel(co
             if (corr_out) reinterpret_cast<float2 *>(corr_out)[o] = make_float2((float)yr, (float)yi);
             if (mag_out) reinterpret_cast<float *>(mag_out)[o] = (float)hypot(yr, yi);
         }
+    }
+}
+
+// ---- K4b: the float32 single-branch matched filter on 8192-point blocks ------------------------------------------------
+// With the 2048-tap reference a 4096-point overlap-save block advances 2049 outputs (50 % useful), an 8192-point block 6145
+// (75 %) for 13/12 of the butterflies per point.  Same structure as zc_mf_kernel (load -> energy prefix -> forward FFT ->
+// pointwise product in transform order -> inverse FFT -> normalise), float32 throughout the epilogue (reciprocal square root
+// instead of float64 divisions and hypot), the filter spectrum as a float2 table, |corr| as the only mandatory output.
+__device__ __forceinline__ int spad(int i) { return i + (i >> 5); }     // energy prefix: 32-element thread stride -> 33
+
+__global__ void zc_twiddle8_kernel(float2 *tw8f, double2 *tw8d)
+{
+    const int i = threadIdx.x;              // 256 entries: exp(-2 pi i t / 8192)
+    double sn, c;
+    sincospi(-2.0 * (double)i / (double)ZF8, &sn, &c);
+    tw8d[i] = make_double2(c, sn);
+    tw8f[i] = make_float2((float)c, (float)sn);
+}
+
+// G8[p] = 8192-point DIF FFT of g[m] = conj(ref[nr-1-m]) zero-padded, in transform order (float2), plus ||ref||
+__global__ void __launch_bounds__(ZNT) zc_spectrum8k_kernel(const double2 *ref, int nr, const double2 *tw, const double2 *tw8d, float2 *G8,
+                                                            double *ref_norm)
+{
+    extern __shared__ __align__(16) unsigned char zsm[];
+    double2 *a = reinterpret_cast<double2 *>(zsm);
+    __shared__ double red[ZNT / 32];
+    double e = 0.0;
+    for (int m = threadIdx.x; m < ZF8; m += ZNT) {
+        double2 v = make_double2(0.0, 0.0);
+        if (m < nr) { const double2 r = ref[nr - 1 - m]; v = make_double2(r.x, -r.y); e += r.x * r.x + r.y * r.y; }
+        a[zpad8(m)] = v;
+    }
+    for (int o = 16; o > 0; o >>= 1) e += shfl_xor_f64(e, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
+    __syncthreads();
+    fft8k_dif<double2>(a, tw, tw8d[threadIdx.x]);
+    for (int m = threadIdx.x; m < ZF8; m += ZNT) { const double2 g = a[zpad8(m)]; G8[m] = make_float2((float)g.x, (float)g.y); }
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < ZNT / 32; ++w) t += red[w];
+        *ref_norm = sqrt(t);
+    }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(ZNT, 2) zc_mf8k_kernel(const void *x, int64_t n, int nr, const double2 *tw, const float2 *tw8,
+                                                        const float2 *G8, const double *ref_norm_p, int mode, float2 *corr_out,
+                                                        float *mag_out, int64_t out_stride, int blocks_per_frame)
+{
+    using In = typename InT<DT>::type;
+    extern __shared__ __align__(16) unsigned char zsm[];
+    float2 *a = reinterpret_cast<float2 *>(zsm);                              // ZFP8
+    float *se = reinterpret_cast<float *>(zsm + (size_t)ZFP8 * sizeof(float2)); // energy prefix, se[spad(k)] = sum of the first k
+    __shared__ double wtot[ZNT / 32];
+    const int V = ZF8 - nr + 1;                       // valid outputs per block
+    const int64_t frame = blockIdx.x / blocks_per_frame;
+    const int blk = blockIdx.x % blocks_per_frame;
+    const int64_t k0 = (int64_t)blk * V;              // first full-convolution output of this block
+    const int64_t jb = k0 - (nr - 1);                 // first input sample of this block
+    const int64_t out_len = n + nr - 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const In *xb = reinterpret_cast<const In *>(x) + frame * n;
+#pragma unroll 8
+    for (int q = 0; q < ZF8 / ZNT; ++q) {
+        const int m = tid + ZNT * q;
+        const int64_t j = jb + m;
+        float2 v = make_float2(0.f, 0.f);
+        if (j >= 0 && j < n) { const In s = xb[j]; v = make_float2((float)s.x, (float)s.y); }
+        a[zpad8(m)] = v;
+        se[spad(m + 1)] = fmaf(v.x, v.x, v.y * v.y);
+    }
+    if (tid == 0) se[0] = 0.f;
+    __syncthreads();
+    if (mode != 2) {
+        // inclusive prefix of the 8192 energies: 32 contiguous values per thread (stride 33 after padding: conflict-free),
+        // warp / CTA carries in float64
+        constexpr int IPT = ZF8 / ZNT;
+        const int s0 = tid * IPT + 1;
+        float run = 0.f;
+#pragma unroll
+        for (int m = 0; m < IPT; ++m) { run += se[spad(s0 + m)]; se[spad(s0 + m)] = run; }
+        double t = (double)run;
+        for (int o = 1; o < 32; o <<= 1) { const double y = shfl_up_f64(t, o); if (lane >= o) t += y; }
+        if (lane == 31) wtot[warp] = t;
+        __syncthreads();
+        double off = t - (double)run;
+        for (int w = 0; w < warp; ++w) off += wtot[w];
+#pragma unroll
+        for (int m = 0; m < IPT; ++m) se[spad(s0 + m)] = (float)((double)se[spad(s0 + m)] + off);
+        __syncthreads();
+    }
+    const float2 w0 = __ldg(tw8 + tid);
+    fft8k_dif<float2>(a, tw, w0);
+#pragma unroll 8
+    for (int q = 0; q < ZF8 / ZNT; ++q) {
+        const int p = tid + ZNT * q;
+        a[zpad8(p)] = cmul(a[zpad8(p)], __ldg(G8 + p));
+    }
+    __syncthreads();
+    ifft8k_dit<float2>(a, tw, w0);
+    const float inv = 1.0f / (float)ZF8, rn = (float)(1.0 / *ref_norm_p);
+#pragma unroll 4
+    for (int q = 0; q < ZF8 / ZNT; ++q) {
+        const int i = tid + ZNT * q;
+        const int64_t k = k0 + i;
+        if (i >= V || k >= out_len) break;
+        const float2 y = a[zpad8(nr - 1 + i)];        // output k0 + i is the window of local samples [i, i + nr - 1]
+        float sc = inv;
+        if (mode != 2) {
+            const float e = se[spad(i + nr)] - se[spad(i)];
+            sc *= rn * (mode == 1 ? rsqrtf(fmaxf(e, 1e-12f))              // zc_v2.py:257-271
+                                  : rsqrtf(fmaxf(e, 0.f) + 1e-12f));     // zc.py:125-126
+        }
+        const float yr = y.x * sc, yi = y.y * sc;
+        const int64_t o = frame * out_stride + k;
+        if (corr_out) corr_out[o] = make_float2(yr, yi);
+        if (mag_out) mag_out[o] = sqrtf(fmaf(yr, yr, yi * yi));
     }
 }
 
@@ -350,11 +468,43 @@ OFS_API int ofs_zc_matched_filter(const void *x, int32_t in_dtype, int64_t n_fra
     OFS_CUDA(cudaFuncSetAttribute(zc_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ZFP * sizeof(double2))));
     zc_spectrum_kernel<<<1, ZNT, ZFP * sizeof(double2), stream>>>((const double2 *)ref_c128, nr, tw, G, rn);
     if (int rc = check_launch("zc_spectrum_kernel")) return rc;
+    const bool dbl = in_dtype == OFS_C128 || out_f64;
+    // float32, one branch, captures of several blocks: the 8192-point kernel (75 % useful outputs per block instead of 50 %)
+    static const int mf_block = [] { const char *e = getenv("OFS_MF_BLOCK"); return e ? atoi(e) : 8192; }();
+    if (!dbl && n_branches == 1 && mf_block == 8192 && n + nr - 1 >= 2 * (ZF8 - nr + 1)) {
+        float2 *tw8f = nullptr, *G8 = nullptr;
+        double2 *tw8d = nullptr;
+        OFS_CUDA(cudaMallocAsync((void **)&tw8f, 256 * sizeof(float2), stream));
+        OFS_CUDA(cudaMallocAsync((void **)&tw8d, 256 * sizeof(double2), stream));
+        OFS_CUDA(cudaMallocAsync((void **)&G8, ZF8 * sizeof(float2), stream));
+        zc_twiddle8_kernel<<<1, 256, 0, stream>>>(tw8f, tw8d);
+        if (int rc = check_launch("zc_twiddle8_kernel")) return rc;
+        OFS_CUDA(cudaFuncSetAttribute(zc_spectrum8k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ZFP8 * sizeof(double2))));
+        zc_spectrum8k_kernel<<<1, ZNT, ZFP8 * sizeof(double2), stream>>>((const double2 *)ref_c128, nr, tw, tw8d, G8, rn);
+        if (int rc = check_launch("zc_spectrum8k_kernel")) return rc;
+        const int V8 = ZF8 - nr + 1;
+        const int bpf8 = (int)((n + nr - 1 + V8 - 1) / V8);
+        const int64_t grid8 = (int64_t)bpf8 * n_frames;
+        OFS_REQUIRE(grid8 < (1LL << 31), "ofs_zc_matched_filter: grid too large");
+        const size_t smem8 = (size_t)ZFP8 * sizeof(float2) + (size_t)(ZF8 + ZF8 / 32 + 8) * sizeof(float);
+        if (in_dtype == OFS_C64) {
+            OFS_CUDA(cudaFuncSetAttribute(zc_mf8k_kernel<OFS_C64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+            zc_mf8k_kernel<OFS_C64><<<(unsigned)grid8, ZNT, smem8, stream>>>(x, n, nr, tw, tw8f, G8, rn, mode, (float2 *)corr_out, (float *)mag_out,
+                                                                            out_stride, bpf8);
+        } else {
+            OFS_CUDA(cudaFuncSetAttribute(zc_mf8k_kernel<OFS_IQ16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+            zc_mf8k_kernel<OFS_IQ16><<<(unsigned)grid8, ZNT, smem8, stream>>>(x, n, nr, tw, tw8f, G8, rn, mode, (float2 *)corr_out, (float *)mag_out,
+                                                                             out_stride, bpf8);
+        }
+        if (int rc = check_launch("zc_mf8k_kernel")) return rc;
+        OFS_CUDA(cudaFreeAsync(tw8f, stream)); OFS_CUDA(cudaFreeAsync(tw8d, stream)); OFS_CUDA(cudaFreeAsync(G8, stream));
+        OFS_CUDA(cudaFreeAsync(tw, stream)); OFS_CUDA(cudaFreeAsync(G, stream)); OFS_CUDA(cudaFreeAsync(rn, stream));
+        return OFS_OK;
+    }
     const int V = ZF - nr + 1;
     const int bpf = (int)((n + nr - 1 + V - 1) / V);
     const int64_t grid = (int64_t)bpf * n_frames;
     OFS_REQUIRE(grid < (1LL << 31), "ofs_zc_matched_filter: grid too large");
-    const bool dbl = in_dtype == OFS_C128 || out_f64;
     // a + se (+ pw + acc when branches are summed)
     const size_t esz_t = dbl ? 8 : 4;
     const size_t smem = (size_t)ZFP * 2 * esz_t + (size_t)(ZFP + 8) * esz_t + (n_branches > 1 ? (size_t)ZF * esz_t + (size_t)ZF * 2 * esz_t : 0);

@@ -622,9 +622,9 @@ def minn_rtl_int(iq, quarter_len: int, smooth_shift: int, threshold_value: int, 
 
 
 # ------------------------------------------------------------------------------------------- Zadoff-Chu
-def zc_matched_filter(rx, ref, mode: int = 0, out_f64: bool | None = None):
+def zc_matched_filter(rx, ref, mode: int = 0, out_f64: bool | None = None, want_corr: bool = True):
     """FFT overlap-save matched filter (zc.py:115-126 mode 0, zc_v2.py:486-495 mode 1, raw sum mode 2)
-    -> (corr complex [F, n+nr-1], |corr|)."""
+    -> (corr complex [F, n+nr-1] or None with want_corr=False, |corr|)."""
     x, code, _ = to_device(rx)
     F, B, n = x.shape[0], x.shape[1], x.shape[2]
     if out_f64 is None:
@@ -634,11 +634,35 @@ def zc_matched_filter(rx, ref, mode: int = 0, out_f64: bool | None = None):
     n_out = n + nr - 1
     cdt = torch.complex128 if out_f64 else torch.complex64
     rdt = torch.float64 if out_f64 else torch.float32
-    corr = torch.empty((F, n_out), dtype=cdt, device=x.device)
+    corr = torch.empty((F, n_out), dtype=cdt, device=x.device) if want_corr else None
     mag = torch.empty((F, n_out), dtype=rdt, device=x.device)
     L.check(L.lib().ofs_zc_matched_filter(_ptr(x), code, C.c_int64(F), int(B), C.c_int64(n), _ptr(r), int(nr), int(mode),
                                           int(out_f64), _ptr(corr), _ptr(mag), C.c_int64(n_out), _stream()), "ofs_zc_matched_filter")
     return corr, mag
+
+
+def zc_v2_detect(rx, ref, *, normalize: bool = True, window: int = 2048, thresh_value: int = 64, frac_bits: int = 15,
+                 min_corr_mag: float = 0.3, hysteresis: int = 256, max_events: int | None = None):
+    """zc_v2.detect_zc_preamble (zc_v2.py:456-516) for a batch of complex64 / int16-IQ captures on the float32 path
+    (ofs_zc_v2_detect: matched filter writing |corr| only -> running-sum threshold bitmask -> gate FSM).
+    -> (events per capture, corr_mag float32 [F, n + nr - 1])."""
+    x, code, _ = to_device(rx)
+    if code == L.OFS_C128:
+        raise TypeError("zc_v2_detect is the float32 pipeline: pass complex64 or int16 IQ (the drop-in zc_v2 module serves complex128)")
+    F, B, n = x.shape[0], x.shape[1], x.shape[2]
+    r = torch.as_tensor(np.ascontiguousarray(np.asarray(ref, dtype=np.complex128))).to(x.device)
+    nr = r.numel()
+    n_out = n + nr - 1
+    mag = torch.empty((F, n_out), dtype=torch.float32, device=x.device)
+    mstride = (n_out + 31) // 32
+    mask = torch.empty((F, mstride), dtype=torch.int32, device=x.device)
+
+    def launch(ev, cnt, cap):
+        L.check(L.lib().ofs_zc_v2_detect(_ptr(x), code, C.c_int64(F), int(B), C.c_int64(n), _ptr(r), int(nr), int(bool(normalize)),
+                                         int(window), int(thresh_value), int(frac_bits), C.c_double(min_corr_mag), int(hysteresis),
+                                         _ptr(mag), C.c_int64(n_out), _ptr(mask), C.c_int64(mstride), _ptr(ev), _ptr(cnt), int(cap),
+                                         _stream()), "ofs_zc_v2_detect")
+    return _with_event_buffers(F, x.device, launch, max_events), mag
 
 
 def zc_normalize(corr, rx, reference):

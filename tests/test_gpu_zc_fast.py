@@ -1,0 +1,100 @@
+"""GPU parity: the float32 Zadoff-Chu fast path -- 8192-point overlap-save matched filter (zc.py:115-126, zc_v2.py:244-271,
+486-498), register-prefix threshold kernel (zc_v2.py:288-336) and the three-launch detect_zc_preamble pipeline
+(zc_v2.py:456-516) -- against the float64 oracle on the same complex64 / int16 captures."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _pss_capture(n, seed, snr_db=10.0, n_pss=3):
+    """Noise + a few PSS symbols (with CP) at random offsets, through a short random channel, complex64."""
+    from ofdm_sync_math_b200.zc import build_pss_symbol
+    rng = np.random.default_rng(seed)
+    pss = build_pss_symbol(include_cp=True)
+    x = np.zeros(n, complex)
+    for p in rng.integers(3000, n - 3000, size=n_pss):
+        x[p:p + pss.size] += pss * np.exp(1j * rng.uniform(0, 2 * np.pi))
+    h = (rng.standard_normal(8) + 1j * rng.standard_normal(8)) * np.exp(-np.arange(8) / 2.0)
+    x = np.convolve(x, h / np.linalg.norm(h))[:n]
+    std = np.sqrt(np.mean(np.abs(pss) ** 2) / 10 ** (snr_db / 10) / 2)
+    x += std * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    return x.astype(np.complex64)
+
+
+@pytest.mark.parametrize("n", [14000, 20000, 65536, 70001])
+@pytest.mark.parametrize("dtype", ["c64", "iq16"])
+def test_matched_filter_8k_blocks_vs_oracle(n, dtype):
+    from ofdm_sync_math_b200 import engine
+    from ofdm_sync_math_b200.zc import build_pss_symbol
+    ref = build_pss_symbol(include_cp=False)
+    x = np.stack([_pss_capture(n, 100 + s) for s in range(2)])
+    if dtype == "iq16":
+        q = np.round(np.stack((x.real, x.imag), axis=-1) * 400.0).clip(-2047, 2047).astype(np.int16)
+        xd = torch.as_tensor(q).cuda()[:, None]
+        x = (q[..., 0].astype(np.float32) + 1j * q[..., 1].astype(np.float32)).astype(np.complex64)
+    else:
+        xd = torch.as_tensor(x).cuda()[:, None]
+    ref_norm = np.sqrt(np.sum(np.abs(ref) ** 2))
+    for mode in (0, 1, 2):
+        corr, mag = engine.zc_matched_filter(xd, ref, mode=mode, out_f64=False)
+        _, mag_only = engine.zc_matched_filter(xd, ref, mode=mode, out_f64=False, want_corr=False)
+        assert torch.equal(mag, mag_only)
+        corr, mag = corr.cpu().numpy(), mag.cpu().numpy()
+        for f in range(x.shape[0]):
+            c, e = orc.matched_filter_correlation(x[f].astype(np.complex128), ref)
+            if mode == 0:
+                c = c / (ref_norm * np.sqrt(np.maximum(e, 0.0) + 1e-12))
+            elif mode == 1:
+                c = c / (ref_norm * np.sqrt(np.maximum(e, 1e-12)))
+            scale = np.abs(c).max()
+            assert np.abs(corr[f] - c).max() <= 1e-4 * scale, (mode, f, np.abs(corr[f] - c).max() / scale)
+            assert np.abs(mag[f] - np.abs(c)).max() <= 1e-4 * scale
+            assert int(np.argmax(mag[f])) == int(np.argmax(np.abs(c)))
+
+
+@pytest.mark.parametrize("n", [30000, 65536])
+def test_zc_v2_detect_pipeline_vs_oracle(n):
+    """ofs_zc_v2_detect: events equal to the oracle's detect_zc_preamble restatement run on the float64 |corr| of the same
+    complex64 capture, and to the oracle's FSM run on the GPU's own float32 |corr|."""
+    from ofdm_sync_math_b200 import engine
+    from ofdm_sync_math_b200.zc import build_pss_symbol
+    ref = build_pss_symbol(include_cp=False)
+    F = 3
+    x = np.stack([_pss_capture(n, 200 + s, snr_db=[5.0, 10.0, 20.0][s % 3]) for s in range(F)])
+    evs, mag = engine.zc_v2_detect(torch.as_tensor(x).cuda()[:, None], ref)
+    mag = mag.cpu().numpy()
+    for f in range(F):
+        got = [(int(e["peak_index"]), int(e["gate_start"]), int(e["gate_end"]), int(e["aux"])) for e in evs[f]]
+        st32 = orc.zc_streaming_detection(mag[f].astype(np.float64), 2048, 64, 15, 0.3)
+        ev32, _, _ = orc.detect_zc_peaks(st32, ref.size, 256, max_ev=4096)
+        assert got == [tuple(int(v) for v in r) for r in ev32.tolist()], f       # FSM + threshold kernel exact on the GPU's own |corr|
+        m64 = orc.zc_v2_corr_mag(x[f].astype(np.complex128), ref, True)
+        assert np.abs(mag[f] - m64).max() <= 1e-4 * m64.max()
+        st64 = orc.zc_streaming_detection(m64, 2048, 64, 15, 0.3)
+        ev64, _, _ = orc.detect_zc_peaks(st64, ref.size, 256, max_ev=4096)
+        assert len(got) >= 1 and got == [tuple(int(v) for v in r) for r in ev64.tolist()], f
+
+
+def test_zc_v2_detect_on_reference_fixture_repeated(golden):
+    """The reference's own zc_v2 capture (tests/golden/zc_v2_cir1.npz, 2 branches), tiled to cover several 8192-point blocks:
+    every repetition must reproduce the fixture's events (shifted), through the float32 pipeline."""
+    from ofdm_sync_math_b200 import engine
+    g = golden("zc_v2_cir1")
+    rx = np.asarray(g["rx"])
+    if rx.ndim == 1:
+        rx = rx[None]
+    reps = 3
+    x = np.tile(rx, (1, reps)).astype(np.complex64)
+    evs, mag = engine.zc_v2_detect(torch.as_tensor(x).cuda()[None], g["ref"])
+    m64 = orc.zc_v2_corr_mag(x.astype(np.complex128), g["ref"], True)
+    st64 = orc.zc_streaming_detection(m64, 2048, 64, 15, 0.3)
+    ev64, _, _ = orc.detect_zc_peaks(st64, g["ref"].size, 256, max_ev=4096)
+    got = [(int(e["peak_index"]), int(e["gate_start"]), int(e["gate_end"]), int(e["aux"])) for e in evs[0]]
+    assert got == [tuple(int(v) for v in r) for r in ev64.tolist()]
+    # first repetition = the fixture itself (the tail of the capture changes nothing before its own events)
+    n_first = int((g["events"][:, 2] < rx.shape[1]).sum())
+    assert [t[0] for t in got[:n_first]] == g["events"][:n_first, 0].tolist()

@@ -179,10 +179,22 @@ def run_cases(a, sink, device_index: int = 0):
             ls, v, ab = engine.zc_streaming_detection(mag, 2048, 64, 15, 0.3)
             return engine.zc_events(mag, v, ab, 2048, 256, want_gate_mask=False)
         ms_mf = timeit(lambda: engine.zc_matched_filter(x, ref, mode=1, out_f64=False), steps=3, warmup=2)
+        ms_mag = timeit(lambda: engine.zc_matched_filter(x, ref, mode=1, out_f64=False, want_corr=False), steps=5, warmup=2)
         ms = timeit(run, steps=3, warmup=2)
-        emit("cfg4 zc matched filter (smem FFT overlap-save, fp32)", ms_mf, F * n, alg_bytes=F * (8 * n + 12 * (n + 2047)),
-             note="8 B in + 8 B corr + 4 B |corr| out per sample", key="cfg4_mf")
-        emit("cfg4 zc_v2 pipeline: matched filter + running-sum threshold + gate FSM", ms, F * n)
+        emit("cfg4 zc matched filter, corr + |corr| out (8192-point overlap-save blocks, fp32)", ms_mf, F * n, alg_bytes=F * (8 * n + 12 * (n + 2047)),
+             note="8 B in + 8 B corr + 4 B |corr| out per sample")
+        emit("cfg4 zc matched filter, |corr| only (8192-point overlap-save blocks, fp32)", ms_mag, F * n, alg_bytes=F * (8 * n + 4 * (n + 2047)),
+             note=f"{F} captures x {n} c64, one root; 8 B in + 4 B |corr| out per sample (SURVEY 8d K4)", key="cfg4_mf")
+        emit("cfg4 zc_v2 pipeline, three separate calls with byte flags: matched filter + running-sum threshold + gate FSM", ms, F * n)
+        zplan = engine.ZCDetectPlan(F, 1, n, ref)
+        ms_p = timeit(lambda: zplan.run(x), steps=5, warmup=2)
+        import time as _time
+        torch.cuda.synchronize(); t0 = _time.perf_counter(); evl = zplan.events(); t_ev = (_time.perf_counter() - t0) * 1e3
+        emit("cfg4 zc_v2.detect_zc_preamble for the batch on the device (ofs_zc_v2_detect: filter -> |corr| -> bitmask -> gate FSM -> event slots)",
+             ms_p, F * n, alg_bytes=F * (8 * n + 4 * (n + 2047)), key="cfg4_zc_v2_pipeline",
+             note=f"{F} captures x {n} c64; reading the {sum(len(e) for e in evl)} events back into per-capture host lists: {t_ev:.2f} ms more")
+        ms_h = timeit(lambda: engine.zc_v2_detect(x, ref), steps=3, warmup=1)
+        emit("cfg4 zc_v2.detect_zc_preamble incl. buffer allocation and host event lists (engine.zc_v2_detect)", ms_h, F * n)
 
         def run_fused():
             corr, mag = engine.zc_matched_filter(x, ref, mode=1, out_f64=False)
@@ -191,7 +203,7 @@ def run_cases(a, sink, device_index: int = 0):
         a3, a2 = run()[0], run_fused()
         same = all(u.tolist() == v.tolist() for u, v in zip(a3, a2))
         emit("cfg4 zc_v2 pipeline, threshold kernel and gate FSM exchanging a bitmask (ofs_zc_detect)", ms, F * n,
-             note=f"events equal to the three-call path: {same}", key="cfg4_zc_v2_detect")
+             note=f"events equal to the three-call path: {same}")
         del x
     if "zcfreq" in cases:
         F, n = max(int(256 * a.scale), 4), 65536

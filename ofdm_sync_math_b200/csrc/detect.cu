@@ -1215,36 +1215,43 @@ __global__ void __launch_bounds__(DNT) zc_stream_kernel(RowView r, int W, double
 
 // Bitmask-only form of the threshold for float32 rows (the fused zc_v2 pipeline): zc_stream_kernel moves every sample through
 // shared memory seven times as a double (84 B per sample with its 50 % halo) and that, not HBM, bounds it.  Here a thread
-// owns 32 CONSECUTIVE samples: float32 samples cross shared memory once (coalesced load, padded so that the 32-sample
-// thread stride is conflict-free), the float64 inclusive prefix of the thread's samples lives in registers, only the prefix
-// goes back to shared memory (padded, conflict-free) and every window sum is (own register) - (one shared load at i - W).
-// The thread's 32 flags are one word of the bitmask.  Tile = TMZ outputs + a halo of >= W samples owned by extra warps.
+// owns 32 CONSECUTIVE samples and only the float32 samples live in shared memory (coalesced load, padded so that the
+// 32-sample thread stride is conflict-free): the thread's float64 total goes through a warp scan to an exclusive offset per
+// thread, and the window sum of sample i is
+//     (offset + running sum of the thread's own samples) - (offset + running sum of the samples of the thread W / 32 to the left)
+// both running sums re-accumulated in registers in one pass -- W is a multiple of 32, so sample i - W is element e of that
+// other thread.  The thread's 32 flags are one word of the bitmask.  Tile = TMZ outputs + a halo of W samples (extra warps).
 constexpr int TMZ = 8192;
-__global__ void __launch_bounds__(512) zc_thresh_mask_kernel(const float *mag, int64_t n, int64_t stride, int W, double thresh_value,
-                                                             double scale, double min_mag, unsigned *bitmask, int64_t bm_stride,
-                                                             int halo_threads)
+__global__ void __launch_bounds__(320, 3) zc_thresh_mask_kernel(const float *mag, int64_t n, int64_t stride, int W, double thresh_value,
+                                                                double scale, double min_mag, unsigned *bitmask, int64_t bm_stride,
+                                                                int halo_threads)
 {
     extern __shared__ __align__(16) unsigned char tsm[];
-    const int nthr = (int)blockDim.x, nel = nthr * 32;
-    double *P = reinterpret_cast<double *>(tsm);                              // inclusive prefix, padded: P[i + i / 32]
-    float *ms = reinterpret_cast<float *>(tsm);                               // samples, padded the same way; dead before P is written
-    __shared__ double wtot[16];
+    const int nthr = (int)blockDim.x;
+    float *ms = reinterpret_cast<float *>(tsm);                               // samples, padded: ms[k + k / 32]
+    __shared__ double offs[320];                                              // exclusive float64 offset of every thread's 32 samples
+    __shared__ double wtot[10];
     const int64_t row = blockIdx.y;
     const int64_t i0 = (int64_t)blockIdx.x * TMZ;
     const int64_t j0 = i0 - (int64_t)halo_threads * 32;                       // first sample of the tile (may be negative)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *mr = mag + row * stride;
-    for (int k = tid; k < nel; k += nthr) {
-        const int64_t j = j0 + k;
-        ms[k + (k >> 5)] = (j >= 0 && j < n) ? __ldg(mr + j) : 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                                             // two batches of 16 independent coalesced loads per thread
+        float ld[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int64_t j = j0 + tid + (16 * h + q) * nthr;
+            ld[q] = (j >= 0 && j < n) ? __ldg(mr + j) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) { const int k = tid + (16 * h + q) * nthr; ms[k + (k >> 5)] = ld[q]; }
     }
     __syncthreads();
-    double pre[32];
-    float mv[32];
+    const float *mine = ms + tid * 33;                                        // padded position of this thread's first sample
     double run = 0.0;
-    const int b = tid * 33;                                                   // padded index of this thread's first sample
 #pragma unroll
-    for (int e = 0; e < 32; ++e) { mv[e] = ms[b + e]; run += (double)mv[e]; pre[e] = run; }
+    for (int e = 0; e < 32; ++e) run += (double)mine[e];
     double t = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const double y = shfl_up_f64(t, o); if (lane >= o) t += y; }
@@ -1252,22 +1259,23 @@ __global__ void __launch_bounds__(512) zc_thresh_mask_kernel(const float *mag, i
     __syncthreads();
     double off = t - run;
     for (int w = 0; w < warp; ++w) off += wtot[w];
-#pragma unroll
-    for (int e = 0; e < 32; ++e) { pre[e] += off; P[b + e] = pre[e]; }
+    offs[tid] = off;
     __syncthreads();
     if (tid < halo_threads) return;                                           // halo warps own no outputs
     const int64_t ibase = j0 + (int64_t)tid * 32;                             // first output of this thread
     if (ibase >= n) return;
+    const int to = tid - W / 32;                                              // owner of the samples W to the left (>= 0: the halo covers W)
+    const float *other = ms + to * 33;
+    const double offo = offs[to];
     unsigned word = 0u;
-#pragma unroll
+    double own = 0.0, oth = 0.0;
+#pragma unroll 8
     for (int e = 0; e < 32; ++e) {
         const int64_t i = ibase + e;
-        // local_sum[i] = prefix(i) - prefix(i - W) (inclusive prefixes; nothing to subtract while the window is still filling)
-        const int kl = tid * 32 + e - W;                                      // tile index of sample i - W (>= 0: the halo covers W)
-        const int64_t jl = i - W;
-        const double lo = jl >= 0 ? P[kl + (kl >> 5)] : 0.0;
-        const double sum = pre[e] - lo;
-        const double m = (double)mv[e];
+        const double m = (double)mine[e];
+        own += m;                                                             // inclusive prefix up to sample i
+        oth += (double)other[e];                                              // inclusive prefix up to sample i - W (zeros below the row start)
+        const double sum = (own + off) - (oth + offo);                        // local_sum[i] (zc_v2.py:308-318)
         const bool ab = i < n && i >= W && (m * scale >= sum * thresh_value) && (m >= min_mag);
         word |= ab ? 1u << e : 0u;
     }
@@ -1797,11 +1805,11 @@ OFS_API int ofs_zc_detect(const ofs_rows *corr_mag, int32_t window, int32_t thre
     const int W = window > 1 ? window : 1;
     OFS_REQUIRE(W <= 16384, "ofs_zc_detect: window > 16384 unsupported");
     OFS_REQUIRE(corr_mag->n_rows < 65536, "ofs_zc_detect: too many rows");
-    if (!corr_mag->f64 && W <= 8192) {
-        // float32 rows: the register-prefix kernel (one mask word per thread)
-        const int halo_threads = ((W + 31) / 32 + 31) / 32 * 32;              // whole warps, >= W samples
+    if (!corr_mag->f64 && W <= 2048 && W % 32 == 0) {
+        // float32 rows: the register-prefix kernel (one mask word per thread; 256 + up to 64 halo threads)
+        const int halo_threads = (W / 32 + 31) / 32 * 32;                     // whole warps, >= W samples
         const int nthr = TMZ / 32 + halo_threads;
-        const size_t tsm = (size_t)(nthr * 32 + nthr + 2) * sizeof(double);
+        const size_t tsm = (size_t)(nthr * 32 + nthr + 2) * sizeof(float);
         dim3 grid2((unsigned)((corr_mag->n + TMZ - 1) / TMZ), (unsigned)corr_mag->n_rows);
         static PerDeviceOnce once;
         if (!once.done()) {

@@ -665,6 +665,37 @@ def zc_v2_detect(rx, ref, *, normalize: bool = True, window: int = 2048, thresh_
     return _with_event_buffers(F, x.device, launch, max_events), mag
 
 
+class ZCDetectPlan:
+    """zc_v2.detect_zc_preamble for repeated batches of captures [F, B, n] complex64 / int16 IQ (ofs_zc_v2_detect) with all
+    buffers allocated once: |corr| rows, threshold bitmask, event slots + counts.  run() only launches; events() reads back."""
+
+    def __init__(self, n_frames: int, n_branches: int, n: int, ref, *, normalize: bool = True, window: int = 2048,
+                 thresh_value: int = 64, frac_bits: int = 15, min_corr_mag: float = 0.3, hysteresis: int = 256,
+                 in_dtype: str = "c64", max_events: int = L.OFS_MAX_EVENTS):
+        dev = _device()
+        self.F, self.B, self.n = n_frames, n_branches, n
+        self.code = {"c64": L.OFS_C64, "iq16": L.OFS_IQ16}[in_dtype]
+        self.ref = torch.as_tensor(np.ascontiguousarray(np.asarray(ref, dtype=np.complex128))).to(dev)
+        self.nr = self.ref.numel()
+        self.n_out = n + self.nr - 1
+        self.args = (int(bool(normalize)), int(window), int(thresh_value), int(frac_bits), C.c_double(min_corr_mag), int(hysteresis))
+        self.mag = torch.empty((n_frames, self.n_out), dtype=torch.float32, device=dev)
+        self.mstride = (self.n_out + 31) // 32
+        self.mask = torch.empty((n_frames, self.mstride), dtype=torch.int32, device=dev)
+        self.cap = int(max_events)
+        self.ev, self.cnt, self.records = _event_buffers(n_frames, dev, want_flat=True, cap=self.cap)
+
+    def run(self, x: torch.Tensor) -> None:
+        assert x.is_cuda and x.is_contiguous() and x.shape[0] == self.F and x.shape[1] == self.B and x.shape[2] == self.n
+        L.check(L.lib().ofs_zc_v2_detect(_ptr(x), self.code, C.c_int64(self.F), int(self.B), C.c_int64(self.n), _ptr(self.ref),
+                                         int(self.nr), *self.args, _ptr(self.mag), C.c_int64(self.n_out), _ptr(self.mask),
+                                         C.c_int64(self.mstride), _ptr(self.ev), _ptr(self.cnt), int(self.cap), _stream()),
+                "ofs_zc_v2_detect")
+
+    def events(self, overflow: str = "raise") -> list[np.ndarray]:
+        return _events_to_numpy(self.ev, self.cnt, self.cap, overflow)
+
+
 def zc_normalize(corr, rx, reference):
     """zc_v2.normalize_correlation (zc_v2.py:257-271) of a caller-supplied correlation: corr (..., n + nr - 1) complex,
     rx (frames, n) or (n,) one branch -> corr / (||ref|| * sqrt(max(sliding energy, 1e-12))), same dtype as corr."""

@@ -11,6 +11,8 @@
 //                            ref/minn_antenna_path.sv:63-194, ref/minn_running_sum.sv:77-82
 //   rtl_combine_*            minn_rtl.py:695-733            ref/minn_preamble_detector.sv:247-325
 #include "common.cuh"
+#include <cstdlib>
+#include <cmath>
 #include <type_traits>
 
 namespace ofs {
@@ -409,7 +411,8 @@ constexpr int SMW = 4;     // warps (frames) per CTA
 template <typename T>
 __global__ void __launch_bounds__(SMW * 32) rtl_smooth_kernel(const T *corr_positive, const T *energy_total, const uint8_t *valid,
                                                               int64_t n_frames, int64_t n, int shift, T thr_value, int frac_bits,
-                                                              T *smooth, T *corr_scaled, T *energy_scaled, uint8_t *above)
+                                                              T *smooth, T *corr_scaled, T *energy_scaled, uint8_t *above,
+                                                              const int *only_if = nullptr)
 {
     __shared__ T sc[SMW][32];
     __shared__ T ss[SMW][32];
@@ -417,6 +420,7 @@ __global__ void __launch_bounds__(SMW * 32) rtl_smooth_kernel(const T *corr_posi
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t frame = (int64_t)blockIdx.x * SMW + w;
     if (frame >= n_frames) return;
+    if (only_if && only_if[frame] == 0) return;          // fallback pass behind the parallel smoother: flagged frames only
     T s = (T)0;
     const double inv_denom = 1.0 / (double)(1LL << (shift > 0 ? shift : 0));     // exact power of two
     const double cscale = (double)(1LL << frac_bits);
@@ -474,6 +478,94 @@ __global__ void __launch_bounds__(SMW * 32) rtl_smooth_kernel(const T *corr_posi
             above[o] = ab;
         }
         __syncwarp();
+    }
+}
+
+
+// ---- the integer smoother in parallel ---------------------------------------------------------------------------------
+// s <- s + floor((c - s) / 2^k) (minn_preamble_detector.sv:277-296) is a true recurrence, and one lane per frame walking
+// 32768 samples was 1.55 ms of the 3.9 ms integer path.  But the step is monotone in s and contracts: two states g apart are
+// at most g (1 - 2^-k) + 1 apart one step later, and less than 2^k apart they close by one whenever (c - s) mod 2^k allows
+// it.  So a chain that starts W samples EARLY from the two extreme states (0 and an upper bound of any reachable state) has
+// forgotten where it started by the time both trajectories coincide -- and from then on it is bit-exact whatever the history
+// was.  A thread runs one such chain: W warm-up samples (both trajectories), then its own PSS outputs.  Redundant work
+// (W + PSS) / PSS, but PSN chains per tile run at once.  A chain whose trajectories have NOT met when its segment starts
+// (probability ~1e-6 per chain on noisy data) leaves its segment to the nearest chain on its left, which simply keeps
+// going; only if that is the first chain of a tile is the frame handed to the serial kernel (dirty flag) -- the result is
+// bit-exact in every case.  The tile of corr_positive lives in shared memory and is overwritten in place by the state
+// (block-synchronous steps: a chain's own segment is written after every chain to its right has read it as warm-up).
+constexpr int PSN = 128, PSS = 64, PST = PSN * PSS;
+__device__ __forceinline__ int cpad(int k) { return k + (k >> 6); }      // a chain walks 64 consecutive values: thread stride 65 -> conflict-free
+__device__ __forceinline__ long long shift_iir_step(long long s, long long c, int shift)
+{
+    return s + ((c - s) >> shift);                   // arithmetic shift = floor; shift 0: s = c
+}
+__global__ void __launch_bounds__(PSN, 3) rtl_smooth_par_kernel(const long long *corr_positive, const long long *energy_total, int64_t n,
+                                                                int64_t first_valid, int shift, int W, long long hi0,
+                                                                long long thr_value, int frac_bits, long long *smooth,
+                                                                uint8_t *above, int *dirty)
+{
+    extern __shared__ long long cs[];                // cs[k]: corr_positive at position t0 - W + k, later the smoothed state
+    __shared__ unsigned char unres[PSN];
+    const int64_t frame = blockIdx.y, t0 = (int64_t)blockIdx.x * PST;
+    const int tid = threadIdx.x;
+    const long long *cp = corr_positive + frame * n;
+#pragma unroll 8
+    for (int k = tid; k < W + PST; k += PSN) {
+        const int64_t j = t0 - W + k;
+        cs[cpad(k)] = (j >= 0 && j < n) ? cp[j] : 0;
+    }
+    __syncthreads();
+    const int64_t seg = t0 + (int64_t)tid * PSS;     // first output of this chain
+    // before first_valid nothing updates the state: a chain that starts there knows it exactly (0)
+    long long lo = 0, hi = (seg - W <= first_valid) ? 0 : hi0;
+    const int nblk = W / PSS;
+    bool resolved = false;
+    for (int blk = 0; blk <= nblk; ++blk) {
+        const bool own = blk == nblk;
+        if (own) { resolved = lo == hi; unres[tid] = resolved ? 0 : 1; }
+        long long *c = cs + cpad(tid * PSS + blk * PSS);        // (a multiple of 64: the 64 values behind it are contiguous)
+        const int64_t pos0 = seg - W + (int64_t)blk * PSS;
+        if (!own) {
+#pragma unroll 8
+            for (int m = 0; m < PSS; ++m) {
+                const int64_t pos = pos0 + m;
+                if (pos >= first_valid && pos < n) { lo = shift_iir_step(lo, c[m], shift); hi = shift_iir_step(hi, c[m], shift); }
+            }
+        } else if (resolved) {
+#pragma unroll 8
+            for (int m = 0; m < PSS; ++m) {
+                const int64_t pos = pos0 + m;
+                if (pos >= first_valid && pos < n) lo = shift_iir_step(lo, c[m], shift);
+                c[m] = lo;
+            }
+        }
+        __syncthreads();
+    }
+    // segments whose chain did not converge in time: the nearest converged chain on the left keeps going through them
+    if (resolved) {
+        for (int nx = tid + 1; nx < PSN && unres[nx]; ++nx) {
+            long long *c = cs + cpad(nx * PSS + W);
+            const int64_t pos0 = t0 + (int64_t)nx * PSS;
+            for (int m = 0; m < PSS; ++m) {
+                const int64_t pos = pos0 + m;
+                if (pos >= first_valid && pos < n) lo = shift_iir_step(lo, c[m], shift);
+                c[m] = lo;
+            }
+        }
+    } else if (tid == 0 && seg < n) {
+        dirty[frame] = 1;                            // nobody on the left inside this tile: the serial kernel redoes the frame
+    }
+    __syncthreads();
+    const long long *en = energy_total + frame * n;
+#pragma unroll 4
+    for (int k = tid; k < PST; k += PSN) {
+        const int64_t i = t0 + k;
+        if (i >= n) break;
+        const long long sm = cs[cpad(W + k)];
+        const int64_t o = frame * n + i;
+        smooth[o] = sm;
+        above[o] = (i >= first_valid) && ((sm << frac_bits) >= en[i] * thr_value);
     }
 }
 
@@ -540,6 +632,49 @@ OFS_API int ofs_minn_rtl_metric(const void *x, int32_t in_dtype, int64_t n_frame
     return OFS_OK;
 }
 
+// Integer smoother + threshold: the parallel kernel when its warm-up fits (shift <= 4), then the serial kernel for the frames it
+// flagged (normally none); the serial kernel alone otherwise.  Bit-exact either way.
+static int launch_int_smoother(const long long *corr_positive, const long long *energy_total, const uint8_t *metric_valid,
+                               int64_t n_frames, int n_branches, int64_t n, int Q, int shift, int threshold_value, int frac_bits,
+                               long long *smooth, uint8_t *above, cudaStream_t stream)
+{
+    // upper bound of any state: the state never exceeds the largest corr_positive seen, and that is a sum of
+    // n_branches * 2Q products of two int16 pairs (|re re + im im| <= 2^31)
+    double bound = (double)n_branches * 2.0 * (double)Q * 2147483648.0;
+    int bits = 1;
+    while (bits < 62 && (double)(1LL << bits) <= bound) ++bits;
+    const long long hi0 = 1LL << bits;
+    const int K = 1 << (shift > 0 ? shift : 0);
+    // W: the geometric phase (gap 2^bits -> 2^shift, factor 1 - 2^-shift per step) plus 20 * 2^shift steps for the last units
+    int W = shift > 0 ? (int)((double)bits * 0.6931472 / -log1p(-1.0 / (double)K)) + 20 * K : PSS;
+    W = (W + PSS - 1) / PSS * PSS;
+    const char *force = getenv("OFS_RTL_SERIAL_SMOOTHER");
+    if (shift >= 0 && shift <= 4 && W <= 1024 && n_frames < 65536 && !(force && force[0] == '1')) {
+        int *dirty = nullptr;
+        keep_pool_cached();
+        OFS_CUDA(cudaMallocAsync((void **)&dirty, (size_t)n_frames * sizeof(int), stream));
+        OFS_CUDA(cudaMemsetAsync(dirty, 0, (size_t)n_frames * sizeof(int), stream));
+        const size_t sm = (size_t)(W + PST + (W + PST) / 64 + 2) * sizeof(long long);
+        static PerDeviceOnce once;
+        if (!once.done()) {
+            OFS_CUDA(cudaFuncSetAttribute(rtl_smooth_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1024 + PST + (1024 + PST) / 64 + 2) * sizeof(long long))));
+            once.mark();
+        }
+        rtl_smooth_par_kernel<<<dim3((unsigned)((n + PST - 1) / PST), (unsigned)n_frames), PSN, sm, stream>>>(
+            corr_positive, energy_total, n, 3 * (int64_t)Q - 1, shift, W, hi0, (long long)threshold_value, frac_bits, smooth, above, dirty);
+        if (int rc = check_launch("rtl_smooth_par_kernel")) return rc;
+        rtl_smooth_kernel<long long><<<(unsigned)((n_frames + SMW - 1) / SMW), SMW * 32, 0, stream>>>(
+            corr_positive, energy_total, metric_valid, n_frames, n, shift, (long long)threshold_value, frac_bits, smooth, nullptr, nullptr,
+            above, dirty);
+        if (int rc = check_launch("rtl_smooth_kernel")) return rc;
+        OFS_CUDA(cudaFreeAsync(dirty, stream));
+        return OFS_OK;
+    }
+    rtl_smooth_kernel<long long><<<(unsigned)((n_frames + SMW - 1) / SMW), SMW * 32, 0, stream>>>(
+        corr_positive, energy_total, metric_valid, n_frames, n, shift, (long long)threshold_value, frac_bits, smooth, nullptr, nullptr, above);
+    return check_launch("rtl_smooth_kernel");
+}
+
 OFS_API int ofs_minn_rtl_int(const int16_t *iq, int64_t n_frames, int32_t n_branches, int64_t n, int32_t quarter_len,
                              int32_t smooth_shift, int32_t threshold_value, int32_t frac_bits, int32_t lag_extra,
                              int64_t *corr_total, int64_t *corr_positive, int64_t *smooth_metric, int64_t *energy_total,
@@ -558,10 +693,8 @@ OFS_API int ofs_minn_rtl_int(const int16_t *iq, int64_t n_frames, int32_t n_bran
             reinterpret_cast<const short2 *>(iq), n_branches, n, quarter_len, quarter_len + lag_extra, (long long *)corr_total,
             (long long *)corr_positive, (long long *)energy_total, metric_valid);
         if (int rc = check_launch("rtl_int_fused_kernel")) return rc;
-        rtl_smooth_kernel<long long><<<(unsigned)((n_frames + SMW - 1) / SMW), SMW * 32, 0, stream>>>(
-            (const long long *)corr_positive, (const long long *)energy_total, metric_valid, n_frames, n, smooth_shift,
-            (long long)threshold_value, frac_bits, (long long *)smooth_metric, nullptr, nullptr, above);
-        return check_launch("rtl_smooth_kernel");
+        return launch_int_smoother((const long long *)corr_positive, (const long long *)energy_total, metric_valid, n_frames, n_branches, n,
+                                   quarter_len, smooth_shift, threshold_value, frac_bits, (long long *)smooth_metric, above, stream);
     }
     keep_pool_cached();
     const int64_t ns = n_frames * n_branches;
@@ -584,10 +717,9 @@ OFS_API int ofs_minn_rtl_int(const int16_t *iq, int64_t n_frames, int32_t n_bran
         C, E, n_frames, n_branches, n, quarter_len, (long long *)corr_total, (long long *)corr_positive,
         (long long *)energy_total, metric_valid);
     if (int rc = check_launch("rtl_combine_kernel")) return rc;
-    rtl_smooth_kernel<long long><<<(unsigned)((n_frames + SMW - 1) / SMW), SMW * 32, 0, stream>>>(
-        (const long long *)corr_positive, (const long long *)energy_total, metric_valid, n_frames, n, smooth_shift,
-        (long long)threshold_value, frac_bits, (long long *)smooth_metric, nullptr, nullptr, above);
-    if (int rc = check_launch("rtl_smooth_kernel")) return rc;
+    if (int rc = launch_int_smoother((const long long *)corr_positive, (const long long *)energy_total, metric_valid, n_frames, n_branches, n,
+                                     quarter_len, smooth_shift, threshold_value, frac_bits, (long long *)smooth_metric, above, stream))
+        return rc;
     OFS_CUDA(cudaFreeAsync(C, stream));
     OFS_CUDA(cudaFreeAsync(E, stream));
     return OFS_OK;

@@ -484,60 +484,101 @@ __global__ void __launch_bounds__(SMW * 32) rtl_smooth_kernel(const T *corr_posi
 
 // ---- the integer smoother in parallel ---------------------------------------------------------------------------------
 // s <- s + floor((c - s) / 2^k) (minn_preamble_detector.sv:277-296) is a true recurrence, and one lane per frame walking
-// 32768 samples was 1.55 ms of the 3.9 ms integer path.  But the step is monotone in s and contracts: two states g apart are
-// at most g (1 - 2^-k) + 1 apart one step later, and less than 2^k apart they close by one whenever (c - s) mod 2^k allows
-// it.  So a chain that starts W samples EARLY from the two extreme states (0 and an upper bound of any reachable state) has
-// forgotten where it started by the time both trajectories coincide -- and from then on it is bit-exact whatever the history
-// was.  A thread runs one such chain: W warm-up samples (both trajectories), then its own PSS outputs.  Redundant work
-// (W + PSS) / PSS, but PSN chains per tile run at once.  A chain whose trajectories have NOT met when its segment starts
-// (probability ~1e-6 per chain on noisy data) leaves its segment to the nearest chain on its left, which simply keeps
-// going; only if that is the first chain of a tile is the frame handed to the serial kernel (dirty flag) -- the result is
-// bit-exact in every case.  The tile of corr_positive lives in shared memory and is overwritten in place by the state
-// (block-synchronous steps: a chain's own segment is written after every chain to its right has read it as warm-up).
+// 32768 samples was 1.55 ms of the 3.9 ms integer path.  Two facts make it parallel and still bit-exact:
+//  (1) without the floor it is the LINEAR filter y <- y (1 - 2^-k) + c 2^-k, which a scan evaluates anywhere (float64: c < 2^53
+//      and both coefficients are exact, so y carries ~1e-3 absolute error), and the floor can only pull the integer state
+//      below it by less than 2^k:  y - (2^k - 1) <= s <= y  (induction on the step);
+//  (2) the step is monotone in s, so two trajectories started at floor(y) - 2^k - 1 and ceil(y) + 1 bracket the true state
+//      for ever, and the bracket closes by one whenever (c - s) mod 2^k allows it: once the two coincide they ARE the state.
+// A thread runs one chain: W warm-up samples with both trajectories (W = 64 for k <= 3: 99.8 % of the chains have met by
+// then), then its own PSS outputs.  A chain that has not met when its segment starts leaves the segment to the nearest chain
+// on its left, which simply keeps going; only if that is the first chain of a tile is the frame handed to the serial kernel
+// (dirty flag).  Bit-exact in every case.  The tile of corr_positive lives in shared memory and is overwritten in place by the
+// state (block-synchronous steps: a chain's segment is written after every chain to its right has read it as warm-up).
 constexpr int PSN = 128, PSS = 64, PST = PSN * PSS;
+constexpr int PS_MAXH = 1024;                                             // longest halo (linear scan history / warm-up)
 __device__ __forceinline__ int cpad(int k) { return k + (k >> 6); }      // a chain walks 64 consecutive values: thread stride 65 -> conflict-free
 __device__ __forceinline__ long long shift_iir_step(long long s, long long c, int shift)
 {
     return s + ((c - s) >> shift);                   // arithmetic shift = floor; shift 0: s = c
 }
 __global__ void __launch_bounds__(PSN, 3) rtl_smooth_par_kernel(const long long *corr_positive, const long long *energy_total, int64_t n,
-                                                                int64_t first_valid, int shift, int W, long long hi0,
-                                                                long long thr_value, int frac_bits, long long *smooth,
-                                                                uint8_t *above, int *dirty)
+                                                                int64_t first_valid, int shift, int H, int W, long long thr_value,
+                                                                int frac_bits, long long *smooth, uint8_t *above, int *dirty)
 {
-    extern __shared__ long long cs[];                // cs[k]: corr_positive at position t0 - W + k, later the smoothed state
+    extern __shared__ long long cs[];                // cs[cpad(k)]: corr_positive at position t0 - H + k, later the smoothed state
+    __shared__ double segA[PSN + PS_MAXH / PSS], segB[PSN + PS_MAXH / PSS], ystart[PSN + PS_MAXH / PSS + 1];
     __shared__ unsigned char unres[PSN];
     const int64_t frame = blockIdx.y, t0 = (int64_t)blockIdx.x * PST;
     const int tid = threadIdx.x;
     const long long *cp = corr_positive + frame * n;
 #pragma unroll 8
-    for (int k = tid; k < W + PST; k += PSN) {
-        const int64_t j = t0 - W + k;
+    for (int k = tid; k < H + PST; k += PSN) {
+        const int64_t j = t0 - H + k;
         cs[cpad(k)] = (j >= 0 && j < n) ? cp[j] : 0;
     }
     __syncthreads();
+    // (1) linear filter per 64-sample segment: y_end = A y_start + B (segments 0 .. hs-1 are the halo)
+    const int hs = H / PSS, nseg = hs + PSN;
+    const double b = 1.0 / (double)(1LL << shift), a = 1.0 - b;
+    for (int g = tid; g < nseg; g += PSN) {
+        const long long *c = cs + cpad(g * PSS);
+        const int64_t pos0 = t0 - H + (int64_t)g * PSS;
+        double A = 1.0, B = 0.0;
+#pragma unroll 8
+        for (int m = 0; m < PSS; ++m) {
+            const int64_t pos = pos0 + m;
+            if (pos >= first_valid && pos < n) { B = fma(B, a, (double)c[m] * b); A *= a; }
+        }
+        segA[g] = A; segB[g] = B;
+    }
+    __syncthreads();
+    if (tid == 0) {                                  // the state before the halo is forgotten by its end (H is chosen that way)
+        double y = 0.0;
+        for (int g = 0; g < nseg; ++g) { ystart[g] = y; y = fma(y, segA[g], segB[g]); }
+    }
+    __syncthreads();
+    // (2) the chain of segment hs + tid starts W samples (W / 64 segments) early, bracketing the state around the linear value
     const int64_t seg = t0 + (int64_t)tid * PSS;     // first output of this chain
-    // before first_valid nothing updates the state: a chain that starts there knows it exactly (0)
-    long long lo = 0, hi = (seg - W <= first_valid) ? 0 : hi0;
     const int nblk = W / PSS;
+    long long lo, hi;
+    if (seg - W <= first_valid) { lo = hi = 0; }     // nothing has updated the state yet: exactly 0
+    else {
+        const double y = ystart[hs + tid - nblk];
+        lo = (long long)floor(y) - (1LL << shift) - 1;
+        hi = (long long)ceil(y) + 1;
+    }
     bool resolved = false;
     for (int blk = 0; blk <= nblk; ++blk) {
         const bool own = blk == nblk;
         if (own) { resolved = lo == hi; unres[tid] = resolved ? 0 : 1; }
-        long long *c = cs + cpad(tid * PSS + blk * PSS);        // (a multiple of 64: the 64 values behind it are contiguous)
+        long long *c = cs + cpad(H - W + tid * PSS + blk * PSS);        // (a multiple of 64: the 64 values behind it are contiguous)
         const int64_t pos0 = seg - W + (int64_t)blk * PSS;
+        const bool all_valid = pos0 >= first_valid && pos0 + PSS <= n;
         if (!own) {
-#pragma unroll 8
-            for (int m = 0; m < PSS; ++m) {
-                const int64_t pos = pos0 + m;
-                if (pos >= first_valid && pos < n) { lo = shift_iir_step(lo, c[m], shift); hi = shift_iir_step(hi, c[m], shift); }
+            if (all_valid && lo != hi) {
+#pragma unroll 16
+                for (int m = 0; m < PSS; ++m) { lo = shift_iir_step(lo, c[m], shift); hi = shift_iir_step(hi, c[m], shift); }
+            } else if (all_valid) {
+#pragma unroll 16
+                for (int m = 0; m < PSS; ++m) lo = shift_iir_step(lo, c[m], shift);
+                hi = lo;
+            } else {
+                for (int m = 0; m < PSS; ++m) {
+                    const int64_t pos = pos0 + m;
+                    if (pos >= first_valid && pos < n) { lo = shift_iir_step(lo, c[m], shift); hi = shift_iir_step(hi, c[m], shift); }
+                }
             }
         } else if (resolved) {
-#pragma unroll 8
-            for (int m = 0; m < PSS; ++m) {
-                const int64_t pos = pos0 + m;
-                if (pos >= first_valid && pos < n) lo = shift_iir_step(lo, c[m], shift);
-                c[m] = lo;
+            if (all_valid) {
+#pragma unroll 16
+                for (int m = 0; m < PSS; ++m) { lo = shift_iir_step(lo, c[m], shift); c[m] = lo; }
+            } else {
+                for (int m = 0; m < PSS; ++m) {
+                    const int64_t pos = pos0 + m;
+                    if (pos >= first_valid && pos < n) lo = shift_iir_step(lo, c[m], shift);
+                    c[m] = lo;
+                }
             }
         }
         __syncthreads();
@@ -545,7 +586,7 @@ __global__ void __launch_bounds__(PSN, 3) rtl_smooth_par_kernel(const long long 
     // segments whose chain did not converge in time: the nearest converged chain on the left keeps going through them
     if (resolved) {
         for (int nx = tid + 1; nx < PSN && unres[nx]; ++nx) {
-            long long *c = cs + cpad(nx * PSS + W);
+            long long *c = cs + cpad(H + nx * PSS);
             const int64_t pos0 = t0 + (int64_t)nx * PSS;
             for (int m = 0; m < PSS; ++m) {
                 const int64_t pos = pos0 + m;
@@ -562,7 +603,7 @@ __global__ void __launch_bounds__(PSN, 3) rtl_smooth_par_kernel(const long long 
     for (int k = tid; k < PST; k += PSN) {
         const int64_t i = t0 + k;
         if (i >= n) break;
-        const long long sm = cs[cpad(W + k)];
+        const long long sm = cs[cpad(H + k)];
         const int64_t o = frame * n + i;
         smooth[o] = sm;
         above[o] = (i >= first_valid) && ((sm << frac_bits) >= en[i] * thr_value);
@@ -632,7 +673,7 @@ OFS_API int ofs_minn_rtl_metric(const void *x, int32_t in_dtype, int64_t n_frame
     return OFS_OK;
 }
 
-// Integer smoother + threshold: the parallel kernel when its warm-up fits (shift <= 4), then the serial kernel for the frames it
+// Integer smoother + threshold: the parallel kernel (shift <= 5), then the serial kernel for the frames it
 // flagged (normally none); the serial kernel alone otherwise.  Bit-exact either way.
 static int launch_int_smoother(const long long *corr_positive, const long long *energy_total, const uint8_t *metric_valid,
                                int64_t n_frames, int n_branches, int64_t n, int Q, int shift, int threshold_value, int frac_bits,
@@ -643,25 +684,28 @@ static int launch_int_smoother(const long long *corr_positive, const long long *
     double bound = (double)n_branches * 2.0 * (double)Q * 2147483648.0;
     int bits = 1;
     while (bits < 62 && (double)(1LL << bits) <= bound) ++bits;
-    const long long hi0 = 1LL << bits;
     const int K = 1 << (shift > 0 ? shift : 0);
-    // W: the geometric phase (gap 2^bits -> 2^shift, factor 1 - 2^-shift per step) plus 20 * 2^shift steps for the last units
-    int W = shift > 0 ? (int)((double)bits * 0.6931472 / -log1p(-1.0 / (double)K)) + 20 * K : PSS;
-    W = (W + PSS - 1) / PSS * PSS;
+    // H: history after which the linear filter has forgotten its start to 1/4 LSB: (1 - 1/K)^H 2^bits < 1/4
+    int H = shift > 0 ? (int)((double)(bits + 2) * 0.6931472 / -log1p(-1.0 / (double)K)) + 1 : 1;
+    H = (H + PSS - 1) / PSS * PSS;
+    // W: integer warm-up from a bracket of 2^k + 3 (simulated: < 0.5 % of the chains still apart, those hand over to their neighbour)
+    static const int wb[6] = {1, 1, 1, 1, 3, 5};
+    const int W = shift >= 0 && shift <= 5 ? wb[shift] * PSS : 0;
     const char *force = getenv("OFS_RTL_SERIAL_SMOOTHER");
-    if (shift >= 0 && shift <= 4 && W <= 1024 && n_frames < 65536 && !(force && force[0] == '1')) {
+    if (shift >= 0 && shift <= 5 && bits <= 50 && H <= PS_MAXH && W <= H && n_frames < 65536 && !(force && force[0] == '1')) {
         int *dirty = nullptr;
         keep_pool_cached();
         OFS_CUDA(cudaMallocAsync((void **)&dirty, (size_t)n_frames * sizeof(int), stream));
         OFS_CUDA(cudaMemsetAsync(dirty, 0, (size_t)n_frames * sizeof(int), stream));
-        const size_t sm = (size_t)(W + PST + (W + PST) / 64 + 2) * sizeof(long long);
+        const size_t sm = (size_t)(H + PST + (H + PST) / 64 + 2) * sizeof(long long);
         static PerDeviceOnce once;
         if (!once.done()) {
-            OFS_CUDA(cudaFuncSetAttribute(rtl_smooth_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1024 + PST + (1024 + PST) / 64 + 2) * sizeof(long long))));
+            OFS_CUDA(cudaFuncSetAttribute(rtl_smooth_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)((PS_MAXH + PST + (PS_MAXH + PST) / 64 + 2) * sizeof(long long))));
             once.mark();
         }
         rtl_smooth_par_kernel<<<dim3((unsigned)((n + PST - 1) / PST), (unsigned)n_frames), PSN, sm, stream>>>(
-            corr_positive, energy_total, n, 3 * (int64_t)Q - 1, shift, W, hi0, (long long)threshold_value, frac_bits, smooth, above, dirty);
+            corr_positive, energy_total, n, 3 * (int64_t)Q - 1, shift, H, W, (long long)threshold_value, frac_bits, smooth, above, dirty);
         if (int rc = check_launch("rtl_smooth_par_kernel")) return rc;
         rtl_smooth_kernel<long long><<<(unsigned)((n_frames + SMW - 1) / SMW), SMW * 32, 0, stream>>>(
             corr_positive, energy_total, metric_valid, n_frames, n, shift, (long long)threshold_value, frac_bits, smooth, nullptr, nullptr,

@@ -497,38 +497,59 @@ __global__ void __launch_bounds__(SMW * 32) rtl_smooth_kernel(const T *corr_posi
 // state (block-synchronous steps: a chain's segment is written after every chain to its right has read it as warm-up).
 constexpr int PSN = 128, PSS = 64, PST = PSN * PSS;
 constexpr int PS_MAXH = 1024;                                             // longest halo (linear scan history / warm-up)
-__device__ __forceinline__ int cpad(int k) { return k + (k >> 6); }      // a chain walks 64 consecutive values: thread stride 65 -> conflict-free
+__device__ __forceinline__ int cpad(int k) { return k + 2 * (k >> 6); }  // a chain walks 64 consecutive values: thread stride 66 keeps the
+                                                                         // segments 16-byte aligned for the bulk copies (2-way conflicts)
 __device__ __forceinline__ long long shift_iir_step(long long s, long long c, int shift)
 {
     return s + ((c - s) >> shift);                   // arithmetic shift = floor; shift 0: s = c
 }
-__global__ void __launch_bounds__(PSN, 3) rtl_smooth_par_kernel(const long long *corr_positive, const long long *energy_total, int64_t n,
-                                                                int64_t first_valid, int shift, int H, int W, long long thr_value,
-                                                                int frac_bits, long long *smooth, uint8_t *above, int *dirty)
+__global__ void __launch_bounds__(PSN, 3) rtl_smooth_par_kernel(const long long *corr_positive, int64_t n, int64_t first_valid, int shift,
+                                                                int H, int W, long long *smooth, int *dirty, int tiles_per_frame)
 {
-    extern __shared__ long long cs[];                // cs[cpad(k)]: corr_positive at position t0 - H + k, later the smoothed state
+    extern __shared__ __align__(16) long long cs[];  // cs[cpad(k)]: corr_positive at position t0 - H + k, later the smoothed state
     __shared__ double segA[PSN + PS_MAXH / PSS], segB[PSN + PS_MAXH / PSS], ystart[PSN + PS_MAXH / PSS + 1];
     __shared__ unsigned char unres[PSN];
+    __shared__ __align__(8) uint64_t bar;
     const int64_t frame = blockIdx.y, t0 = (int64_t)blockIdx.x * PST;
     const int tid = threadIdx.x;
     const long long *cp = corr_positive + frame * n;
-#pragma unroll 8
-    for (int k = tid; k < H + PST; k += PSN) {
-        const int64_t j = t0 - H + k;
-        cs[cpad(k)] = (j >= 0 && j < n) ? cp[j] : 0;
+    const int hs = H / PSS, nseg = hs + PSN;
+    // ---- the tile + halo arrive as one 512-byte bulk copy per 64-sample segment (cp.async.bulk on one mbarrier): every load of
+    //      the CTA is in flight at once; segments that stick out of the frame (or a frame that is not 16-byte aligned) take plain loads
+    const bool bulk_ok = ((reinterpret_cast<uintptr_t>(cp) & 15) == 0);
+    auto seg_full = [&](int g) { const int64_t p0 = t0 - H + (int64_t)g * PSS; return p0 >= 0 && p0 + PSS <= n; };
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        int full = 0;
+        if (bulk_ok) for (int g = 0; g < nseg; ++g) full += seg_full(g) ? 1 : 0;
+        mbar_expect_tx(&bar, (uint32_t)(full * PSS * 8));
     }
     __syncthreads();
+    for (int g = tid; g < nseg; g += PSN) {
+        const int64_t p0 = t0 - H + (int64_t)g * PSS;
+        long long *dst = cs + cpad(g * PSS);
+        if (bulk_ok && seg_full(g)) tma_load_1d(dst, cp + p0, PSS * 8, &bar);
+        else
+            for (int m = 0; m < PSS; ++m) { const int64_t j = p0 + m; dst[m] = (j >= 0 && j < n) ? cp[j] : 0; }
+    }
+    mbar_wait(&bar, 0);
+    __syncthreads();
     // (1) linear filter per 64-sample segment: y_end = A y_start + B (segments 0 .. hs-1 are the halo)
-    const int hs = H / PSS, nseg = hs + PSN;
     const double b = 1.0 / (double)(1LL << shift), a = 1.0 - b;
     for (int g = tid; g < nseg; g += PSN) {
         const long long *c = cs + cpad(g * PSS);
         const int64_t pos0 = t0 - H + (int64_t)g * PSS;
         double A = 1.0, B = 0.0;
-#pragma unroll 8
-        for (int m = 0; m < PSS; ++m) {
-            const int64_t pos = pos0 + m;
-            if (pos >= first_valid && pos < n) { B = fma(B, a, (double)c[m] * b); A *= a; }
+        if (pos0 >= first_valid && pos0 + PSS <= n) {
+#pragma unroll 16
+            for (int m = 0; m < PSS; ++m) B = fma(B, a, (double)c[m] * b);
+            A = pow(a, (double)PSS);
+        } else {
+            for (int m = 0; m < PSS; ++m) {
+                const int64_t pos = pos0 + m;
+                if (pos >= first_valid && pos < n) { B = fma(B, a, (double)c[m] * b); A *= a; }
+            }
         }
         segA[g] = A; segB[g] = B;
     }
@@ -583,7 +604,8 @@ __global__ void __launch_bounds__(PSN, 3) rtl_smooth_par_kernel(const long long 
         }
         __syncthreads();
     }
-    // segments whose chain did not converge in time: the nearest converged chain on the left keeps going through them
+    // segments whose chain did not converge in time: the nearest converged chain on the left keeps going through them; a run
+    // of them at the START of the tile has nobody on its left here -- its length goes to the fix-up kernel
     if (resolved) {
         for (int nx = tid + 1; nx < PSN && unres[nx]; ++nx) {
             long long *c = cs + cpad(H + nx * PSS);
@@ -594,19 +616,70 @@ __global__ void __launch_bounds__(PSN, 3) rtl_smooth_par_kernel(const long long 
                 c[m] = lo;
             }
         }
-    } else if (tid == 0 && seg < n) {
-        dirty[frame] = 1;                            // nobody on the left inside this tile: the serial kernel redoes the frame
+    } else if (tid == 0) {
+        int cnt = 0;
+        while (cnt < PSN && unres[cnt]) ++cnt;
+        dirty[frame * tiles_per_frame + blockIdx.x] = cnt;
     }
+    fence_proxy_async_smem();
     __syncthreads();
-    const long long *en = energy_total + frame * n;
-#pragma unroll 4
-    for (int k = tid; k < PST; k += PSN) {
-        const int64_t i = t0 + k;
-        if (i >= n) break;
-        const long long sm = cs[cpad(H + k)];
-        const int64_t o = frame * n + i;
-        smooth[o] = sm;
-        above[o] = (i >= first_valid) && ((sm << frac_bits) >= en[i] * thr_value);
+    // ---- results leave the same way: one bulk store per segment
+    long long *sr = smooth + frame * n;
+    const bool bulk_out = ((reinterpret_cast<uintptr_t>(sr) & 15) == 0);
+    if (seg < n) {
+        const long long *src = cs + cpad(H + tid * PSS);
+        if (bulk_out && seg + PSS <= n) {
+            tma_store_1d(sr + seg, src, PSS * 8);
+            tma_store_commit();
+            tma_store_wait_read<0>();
+        } else {
+            for (int m = 0; m < PSS && seg + m < n; ++m) sr[seg + m] = src[m];
+        }
+    }
+}
+
+// Leading segments of a tile whose chains had not converged (rtl_smooth_par_kernel's dirty counts): redone serially from the
+// last state of the previous tile, tiles in order, one warp per frame (the warp loads 32 samples at a time, every lane walks
+// the 32 steps and keeps its own).  Normally there is nothing to do.
+__global__ void __launch_bounds__(128) rtl_smooth_fixup_kernel(const long long *corr_positive, int64_t n_frames, int64_t n, int64_t first_valid,
+                                                              int shift, long long *smooth, const int *dirty, int tiles_per_frame)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t frame = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (frame >= n_frames) return;
+    for (int tile = 0; tile < tiles_per_frame; ++tile) {
+        const int cnt = dirty[frame * tiles_per_frame + tile];
+        if (cnt == 0) continue;
+        const int64_t t0 = (int64_t)tile * PST;
+        const int64_t t1 = t0 + (int64_t)cnt * PSS < n ? t0 + (int64_t)cnt * PSS : n;
+        long long s = t0 > 0 ? smooth[frame * n + t0 - 1] : 0;
+        for (int64_t i0 = t0; i0 < t1; i0 += 32) {
+            const int64_t i = i0 + lane;
+            const long long c = i < t1 ? corr_positive[frame * n + i] : 0;
+            long long mine = s;
+            for (int q = 0; q < 32; ++q) {
+                const long long cq = __shfl_sync(0xffffffffu, c, q);
+                if (i0 + q >= first_valid && i0 + q < t1) s = shift_iir_step(s, cq, shift);
+                if (q == lane) mine = s;
+            }
+            if (i < t1) smooth[frame * n + i] = mine;
+        }
+        __threadfence_block();
+    }
+}
+
+// above = valid && (smooth << frac_bits) >= energy_total * threshold  (minn_preamble_detector.sv:305-325), elementwise
+__global__ void __launch_bounds__(256) rtl_above_kernel(const long long *smooth, const long long *energy_total, int64_t n_frames, int64_t n,
+                                                        int64_t first_valid, long long thr_value, int frac_bits, uint8_t *above)
+{
+    const int64_t total = n_frames * n;
+    for (int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; idx < total; idx += (int64_t)gridDim.x * blockDim.x * 4) {
+        long long sm[4], en[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const int64_t k = idx + q < total ? idx + q : total - 1; sm[q] = smooth[k]; en[q] = energy_total[k]; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (idx + q < total) above[idx + q] = ((idx + q) % n >= first_valid) && ((sm[q] << frac_bits) >= en[q] * thr_value);
     }
 }
 
@@ -695,22 +768,30 @@ static int launch_int_smoother(const long long *corr_positive, const long long *
     if (shift >= 0 && shift <= 5 && bits <= 50 && H <= PS_MAXH && W <= H && n_frames < 65536 && !(force && force[0] == '1')) {
         int *dirty = nullptr;
         keep_pool_cached();
-        OFS_CUDA(cudaMallocAsync((void **)&dirty, (size_t)n_frames * sizeof(int), stream));
-        OFS_CUDA(cudaMemsetAsync(dirty, 0, (size_t)n_frames * sizeof(int), stream));
-        const size_t sm = (size_t)(H + PST + (H + PST) / 64 + 2) * sizeof(long long);
+        const int tiles = (int)((n + PST - 1) / PST);
+        OFS_CUDA(cudaMallocAsync((void **)&dirty, (size_t)n_frames * tiles * sizeof(int), stream));
+        OFS_CUDA(cudaMemsetAsync(dirty, 0, (size_t)n_frames * tiles * sizeof(int), stream));
+        const size_t sm = (size_t)(H + PST + 2 * ((H + PST) / 64) + 4) * sizeof(long long);
         static PerDeviceOnce once;
         if (!once.done()) {
             OFS_CUDA(cudaFuncSetAttribute(rtl_smooth_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)((PS_MAXH + PST + (PS_MAXH + PST) / 64 + 2) * sizeof(long long))));
+                                          (int)((PS_MAXH + PST + 2 * ((PS_MAXH + PST) / 64) + 4) * sizeof(long long))));
             once.mark();
         }
-        rtl_smooth_par_kernel<<<dim3((unsigned)((n + PST - 1) / PST), (unsigned)n_frames), PSN, sm, stream>>>(
-            corr_positive, energy_total, n, 3 * (int64_t)Q - 1, shift, H, W, (long long)threshold_value, frac_bits, smooth, above, dirty);
+        const int64_t first_valid = 3 * (int64_t)Q - 1;
+        rtl_smooth_par_kernel<<<dim3((unsigned)tiles, (unsigned)n_frames), PSN, sm, stream>>>(corr_positive, n, first_valid, shift, H, W, smooth,
+                                                                                           dirty, tiles);
         if (int rc = check_launch("rtl_smooth_par_kernel")) return rc;
-        rtl_smooth_kernel<long long><<<(unsigned)((n_frames + SMW - 1) / SMW), SMW * 32, 0, stream>>>(
-            corr_positive, energy_total, metric_valid, n_frames, n, shift, (long long)threshold_value, frac_bits, smooth, nullptr, nullptr,
-            above, dirty);
-        if (int rc = check_launch("rtl_smooth_kernel")) return rc;
+        rtl_smooth_fixup_kernel<<<(unsigned)((n_frames + 3) / 4), 128, 0, stream>>>(corr_positive, n_frames, n, first_valid, shift, smooth, dirty,
+                                                                                 tiles);
+        if (int rc = check_launch("rtl_smooth_fixup_kernel")) return rc;
+        const int64_t total = n_frames * n;
+        int64_t ab_grid = (total / 4 + 255) / 256;
+        if (ab_grid > (int64_t)sm_count() * 16) ab_grid = (int64_t)sm_count() * 16;
+        if (ab_grid < 1) ab_grid = 1;
+        rtl_above_kernel<<<(unsigned)ab_grid, 256, 0, stream>>>(smooth, energy_total, n_frames, n, first_valid, (long long)threshold_value,
+                                                               frac_bits, above);
+        if (int rc = check_launch("rtl_above_kernel")) return rc;
         OFS_CUDA(cudaFreeAsync(dirty, stream));
         return OFS_OK;
     }

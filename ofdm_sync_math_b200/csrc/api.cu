@@ -169,6 +169,7 @@ OFS_API int ofs_metric_array_ok(const ofs_metric_desc *d, const void *x)
 OFS_API int ofs_metric(const ofs_metric_desc *d, const void *x, void *M, void *P, void *R, float *chunk_max,
                        int64_t cm_stride, void *stream)
 {
+    OFS_TRACE();
     if (int rc = check_desc(d, "ofs_metric")) return rc;
     const int64_t out_len = ofs_metric_out_len(d);
     if (out_len == 0 || d->n_frames == 0) return OFS_OK;
@@ -206,6 +207,7 @@ OFS_API int ofs_sync_detect(const ofs_metric_desc *d, const void *x, const float
                             int64_t cm_stride, const ofs_sync_params *sp, ofs_sync_record *records, int64_t *scratch,
                             void *stream)
 {
+    OFS_TRACE();
     if (int rc = check_desc(d, "ofs_sync_detect")) return rc;
     if (int rc = check_sync_params(sp, "ofs_sync_detect")) return rc;
     OFS_REQUIRE(d->kind == OFS_SC || d->kind == OFS_SC_BOTH || d->kind == OFS_MINN, "ofs_sync: kind must be SC or MINN");
@@ -243,6 +245,7 @@ OFS_API int ofs_sync_detect(const ofs_metric_desc *d, const void *x, const float
 // flagged OFS_ST_UNRESOLVED is re-run through, and the yardstick of the exact mode in the tests.  Workspace from the stream's pool.
 OFS_API int ofs_sync_f64(const ofs_metric_desc *d, const void *x, const ofs_sync_params *sp, ofs_sync_record *records, void *stream_)
 {
+    OFS_TRACE();
     if (int rc = check_desc(d, "ofs_sync_f64")) return rc;
     if (int rc = check_sync_params(sp, "ofs_sync_f64")) return rc;
     OFS_REQUIRE(d->kind == OFS_SC || d->kind == OFS_SC_BOTH || d->kind == OFS_MINN, "ofs_sync_f64: kind must be SC or MINN");
@@ -282,6 +285,7 @@ OFS_API int ofs_sync_f64(const ofs_metric_desc *d, const void *x, const ofs_sync
 OFS_API int ofs_sync(const ofs_metric_desc *d, const void *x, float *M, float *chunk_max, int64_t cm_stride,
                      const ofs_sync_params *sp, ofs_sync_record *records, int64_t *scratch, void *stream)
 {
+    OFS_TRACE();
     if (int rc = check_desc(d, "ofs_sync")) return rc;
     OFS_REQUIRE(x && M && records && scratch, "ofs_sync: null argument");
     OFS_REQUIRE(d->out_f64 == 0, "ofs_sync: float32 metric only");
@@ -354,6 +358,7 @@ OFS_API void ofs_host_free(void *p) { if (p) cudaFreeHost(p); }
 OFS_API int ofs_sync_host(ofs_ctx *c, const ofs_metric_desc *d, const void *x_host, float *M_host, const ofs_sync_params *sp,
                           ofs_sync_record *records_host)
 {
+    OFS_TRACE();
     OFS_REQUIRE(c, "ofs_sync_host: null context");
     if (int rc = check_desc(d, "ofs_sync_host")) return rc;
     if (int rc = check_sync_params(sp, "ofs_sync_host")) return rc;

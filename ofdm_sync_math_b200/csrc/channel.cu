@@ -247,6 +247,7 @@ OFS_API int ofs_channel_apply(const void *tx, int32_t dtype, int64_t n_rows, int
                               const double *snr_db, const double *cfo_hz, double fs, const double *full_scale, int32_t bits,
                               void *out, int16_t *out_iq, int64_t out_stride, void *faded_ws, double *power_ws, void *stream_)
 {
+    OFS_TRACE();
     OFS_REQUIRE(tx && (out || out_iq) && faded_ws && power_ws, "ofs_channel_apply: null argument");
     OFS_REQUIRE(dtype == OFS_C64 || dtype == OFS_C128, "ofs_channel_apply: samples must be complex64 or complex128");
     OFS_REQUIRE(n_rows >= 0 && n_tx >= 1 && n_streams >= 0, "ofs_channel_apply: bad geometry");
@@ -292,6 +293,7 @@ OFS_API int ofs_cp_cfo(const void *x, int32_t in_dtype, int64_t n_frames, int32_
                        int64_t x_branch_stride, const int64_t *starts, int32_t n_fft, int32_t cp_len, int32_t span, int32_t win_len,
                        int32_t mode, double fs, double *cfo_hz, int64_t *best_d, void *P_c128, void *stream)
 {
+    OFS_TRACE();
     OFS_REQUIRE(x && starts && cfo_hz, "ofs_cp_cfo: null argument");
     OFS_REQUIRE(in_dtype >= OFS_C64 && in_dtype <= OFS_IQ16, "ofs_cp_cfo: unknown dtype");
     OFS_REQUIRE(n_frames >= 0 && n_branches >= 1 && n >= 1 && n_fft >= 1 && cp_len >= 1, "ofs_cp_cfo: bad geometry");
@@ -361,6 +363,7 @@ __global__ void __launch_bounds__(256) wire_unpack_kernel(const void *__restrict
 
 OFS_API int ofs_wire_pack(const int16_t *iq, int64_t n, int32_t format, void *words, void *stream)
 {
+    OFS_TRACE();
     OFS_REQUIRE(iq && words, "ofs_wire_pack: null argument");
     OFS_REQUIRE(format == OFS_WIRE_HEX24 || format == OFS_WIRE_AXIS48, "ofs_wire_pack: unknown format");
     OFS_REQUIRE(n >= 0, "ofs_wire_pack: bad length");
@@ -371,6 +374,7 @@ OFS_API int ofs_wire_pack(const int16_t *iq, int64_t n, int32_t format, void *wo
 
 OFS_API int ofs_wire_unpack(const void *words, int64_t n, int32_t format, int16_t *iq, void *stream)
 {
+    OFS_TRACE();
     OFS_REQUIRE(iq && words, "ofs_wire_unpack: null argument");
     OFS_REQUIRE(format == OFS_WIRE_HEX24 || format == OFS_WIRE_AXIS48, "ofs_wire_unpack: unknown format");
     OFS_REQUIRE(n >= 0, "ofs_wire_unpack: bad length");

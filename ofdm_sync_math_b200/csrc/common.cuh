@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/ofdmsync.h"
 
 #define OFS_API extern "C" __attribute__((visibility("default")))
@@ -42,6 +43,14 @@ inline int check_launch(const char *what)
     count_launch();
     return OFS_OK;
 }
+
+// NVTX range around every compute entry point of the C ABI (tracing hook).  Header-only NVTX3: a no-op function
+// pointer check unless a tool (nsys, ncu --nvtx) has injected itself.
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+#define OFS_TRACE() ofs::NvtxRange _ofs_trace_range(__func__)
 
 int sm_count();  // multiprocessor count of the CURRENT device (cached per device)
 int current_device();  // cudaGetDevice, clamped to [0, OFS_MAX_DEVICES)

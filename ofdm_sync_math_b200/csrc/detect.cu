@@ -1593,12 +1593,14 @@ OFS_API int ofs_find_plateau_end_pruned(const ofs_rows *M, const float *chunk_ma
                                         int32_t cp_len, int32_t lookahead, int32_t smooth_win, int64_t *plateau_end,
                                         void *stream)
 {
+    OFS_TRACE();
     return launch_plateau(M, chunk_max, cm_stride, toff, cp_len, lookahead, smooth_win, plateau_end, nullptr, nullptr, stream);
 }
 
 OFS_API int ofs_find_plateau_end(const ofs_rows *M, int32_t cp_len, int32_t lookahead, int32_t smooth_win,
                                  int64_t *plateau_end, void *stream)
 {
+    OFS_TRACE();
     return ofs_find_plateau_end_pruned(M, nullptr, 0, 0, cp_len, lookahead, smooth_win, plateau_end, stream);
 }
 
@@ -1635,6 +1637,7 @@ OFS_API int ofs_find_minn_peak_pruned(const ofs_rows *M, const float *chunk_max,
                                       int32_t smooth_win, double gate_threshold, int32_t has_bounds, int64_t bound_lo,
                                       int64_t bound_hi, int64_t *peak, int64_t *gate_span, void *Ms, void *stream)
 {
+    OFS_TRACE();
     return launch_minn_peak(M, chunk_max, cm_stride, toff, smooth_win, gate_threshold, has_bounds, bound_lo, bound_hi, peak, gate_span,
                             Ms, nullptr, nullptr, stream);
 }
@@ -1643,6 +1646,7 @@ OFS_API int ofs_find_minn_peak(const ofs_rows *M, int32_t smooth_win, double gat
                                int64_t bound_lo, int64_t bound_hi, int64_t *peak, int64_t *gate_span, void *Ms,
                                void *stream)
 {
+    OFS_TRACE();
     return ofs_find_minn_peak_pruned(M, nullptr, 0, 0, smooth_win, gate_threshold, has_bounds, bound_lo, bound_hi, peak,
                                      gate_span, Ms, stream);
 }
@@ -1650,6 +1654,7 @@ OFS_API int ofs_find_minn_peak(const ofs_rows *M, int32_t smooth_win, double gat
 OFS_API int ofs_sc_gate_pruned(const ofs_rows *Msc, const float *chunk_max, int64_t cm_stride, int32_t toff, double threshold,
                                uint8_t *gate, int64_t gate_stride, void *stream)
 {
+    OFS_TRACE();
     if (int rc = rows_ok(Msc, "ofs_sc_gate")) return rc;
     OFS_REQUIRE(gate && gate_stride >= Msc->n, "ofs_sc_gate: bad gate buffer");
     OFS_REQUIRE(!chunk_max || (toff >= 0 && cm_stride >= (Msc->n + toff + 255) / 256), "ofs_sc_gate: bad chunk_max geometry");
@@ -1667,12 +1672,14 @@ OFS_API int ofs_sc_gate_pruned(const ofs_rows *Msc, const float *chunk_max, int6
 
 OFS_API int ofs_sc_gate(const ofs_rows *Msc, double threshold, uint8_t *gate, int64_t gate_stride, void *stream)
 {
+    OFS_TRACE();
     return ofs_sc_gate_pruned(Msc, nullptr, 0, 0, threshold, gate, gate_stride, stream);
 }
 
 OFS_API int ofs_find_minn_peak_gated(const ofs_rows *M, int32_t smooth_win, const uint8_t *gate, int64_t gate_stride,
                                      int32_t has_bounds, int64_t bound_lo, int64_t bound_hi, int64_t *peak, void *stream)
 {
+    OFS_TRACE();
     if (int rc = rows_ok(M, "ofs_find_minn_peak_gated")) return rc;
     OFS_REQUIRE(peak && (gate || M->n == 0) && gate_stride >= M->n, "ofs_find_minn_peak_gated: bad arguments");
     if (M->n_rows == 0) return OFS_OK;
@@ -1689,6 +1696,7 @@ OFS_API int ofs_combined_peak(const ofs_rows *M_minn, const ofs_rows *M_sc, cons
                               double threshold, int32_t smooth_win, int32_t has_bounds, int64_t bound_lo, int64_t bound_hi,
                               int64_t *peak, int64_t *gate_span, void *stream)
 {
+    OFS_TRACE();
     if (int rc = rows_ok(M_minn, "ofs_combined_peak")) return rc;
     if (int rc = rows_ok(M_sc, "ofs_combined_peak")) return rc;
     OFS_REQUIRE(peak && chunk_max_sc, "ofs_combined_peak: null argument");
@@ -1705,6 +1713,7 @@ OFS_API int ofs_combined_peak(const ofs_rows *M_minn, const ofs_rows *M_sc, cons
 
 OFS_API int ofs_argmax(const ofs_rows *M, int64_t *index, void *stream)
 {
+    OFS_TRACE();
     if (int rc = rows_ok(M, "ofs_argmax")) return rc;
     OFS_REQUIRE(index, "ofs_argmax: null output");
     if (M->n_rows == 0) return OFS_OK;
@@ -1716,6 +1725,7 @@ OFS_API int ofs_zc_streaming_detection(const ofs_rows *corr_mag, int32_t window,
                                        double min_corr_mag, void *local_sum, uint8_t *valid, uint8_t *above,
                                        int64_t mask_stride, void *stream)
 {
+    OFS_TRACE();
     if (int rc = rows_ok(corr_mag, "ofs_zc_streaming_detection")) return rc;
     OFS_REQUIRE(local_sum && valid && above && mask_stride >= corr_mag->n, "ofs_zc_streaming_detection: bad outputs");
     OFS_REQUIRE(frac_bits >= 0 && frac_bits < 62, "ofs_zc_streaming_detection: bad frac_bits");
@@ -1754,6 +1764,7 @@ static int launch_fsm(FsmParams &p, int64_t n_rows, cudaStream_t stream)
 OFS_API int ofs_aa_events(const ofs_rows *M, const void *P, int32_t L, double threshold, int32_t hysteresis,
                           double sample_rate, ofs_event *events, int32_t *n_events, int32_t max_events, void *stream)
 {
+    OFS_TRACE();
     if (int rc = rows_ok(M, "ofs_aa_events")) return rc;
     OFS_REQUIRE(P && events && n_events && L > 0, "ofs_aa_events: bad arguments");
     FsmParams p{};
@@ -1767,6 +1778,7 @@ OFS_API int ofs_aa_detect(const void *x, int32_t in_dtype, int64_t n_frames, int
                           double sample_rate, float *M, void *P_c64, float *R, int64_t out_stride, uint32_t *mask_ws,
                           int64_t mask_stride, ofs_event *events, int32_t *n_events, int32_t max_events, void *stream)
 {
+    OFS_TRACE();
     OFS_REQUIRE(x && M && P_c64 && mask_ws && events && n_events && L > 0, "ofs_aa_detect: null argument");
     OFS_REQUIRE(n_frames >= 0 && n_antennas >= 1 && n >= 0 && n_frames < (1LL << 31), "ofs_aa_detect: bad geometry");
     if (n_frames == 0) return OFS_OK;
@@ -1784,6 +1796,7 @@ OFS_API int ofs_zc_events(const ofs_rows *corr_mag, const uint8_t *valid, const 
                           int32_t reference_length, int32_t hysteresis, ofs_event *events, int32_t *n_events,
                           int32_t max_events, uint8_t *gate_mask, void *stream)
 {
+    OFS_TRACE();
     if (int rc = rows_ok(corr_mag, "ofs_zc_events")) return rc;
     OFS_REQUIRE(valid && above && events && n_events && mask_stride >= corr_mag->n, "ofs_zc_events: bad arguments");
     if (gate_mask && corr_mag->n_rows > 0)
@@ -1798,6 +1811,7 @@ OFS_API int ofs_zc_detect(const ofs_rows *corr_mag, int32_t window, int32_t thre
                           int32_t reference_length, int32_t hysteresis, uint32_t *mask_ws, int64_t mask_stride, ofs_event *events,
                           int32_t *n_events, int32_t max_events, void *stream)
 {
+    OFS_TRACE();
     if (int rc = rows_ok(corr_mag, "ofs_zc_detect")) return rc;
     OFS_REQUIRE(mask_ws && events && n_events && mask_stride >= (corr_mag->n + 31) / 32, "ofs_zc_detect: bad arguments");
     OFS_REQUIRE(frac_bits >= 0 && frac_bits < 62, "ofs_zc_detect: bad frac_bits");
@@ -1840,6 +1854,7 @@ OFS_API int ofs_zc_v2_detect(const void *x, int32_t in_dtype, int64_t n_frames, 
                              double min_corr_mag, int32_t hysteresis, float *mag_ws, int64_t mag_stride, uint32_t *mask_ws,
                              int64_t mask_stride, ofs_event *events, int32_t *n_events, int32_t max_events, void *stream)
 {
+    OFS_TRACE();
     OFS_REQUIRE(x && ref_c128 && mag_ws && mask_ws && events && n_events, "ofs_zc_v2_detect: null argument");
     OFS_REQUIRE(in_dtype == OFS_C64 || in_dtype == OFS_IQ16, "ofs_zc_v2_detect: complex64 or int16 IQ captures (float32 pipeline)");
     const int64_t n_out = n + nr - 1;
@@ -1857,6 +1872,7 @@ OFS_API int ofs_minn_rtl_events(const void *corr_positive, int32_t is_int, const
                                 int64_t n_rows, int64_t n, int64_t stride, int32_t hysteresis, int32_t timing_offset,
                                 ofs_event *events, int32_t *n_events, int32_t max_events, void *stream)
 {
+    OFS_TRACE();
     OFS_REQUIRE(corr_positive && valid && above && events && n_events, "ofs_minn_rtl_events: null argument");
     OFS_REQUIRE(n_rows >= 0 && n >= 0 && stride >= n && n_rows < (1LL << 31), "ofs_minn_rtl_events: bad geometry");
     FsmParams p{};

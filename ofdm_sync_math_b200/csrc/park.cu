@@ -249,6 +249,7 @@ using namespace ofs;
 
 OFS_API int ofs_park_metric(const ofs_metric_desc *d, const void *x, void *M, void *P, void *E, void *stream)
 {
+    OFS_TRACE();
     OFS_REQUIRE(d && x, "ofs_park_metric: null argument");
     OFS_REQUIRE(d->symbol_len >= 2 && d->n_branches >= 1 && d->n_frames >= 0, "ofs_park_metric: bad descriptor");
     const int h = d->symbol_len / 2;

@@ -179,6 +179,7 @@ OFS_API int ofs_rx_chain(const void *x, int32_t in_dtype, int64_t n_frames, int3
                          const void *data_used_c128, int64_t data_stride, void *h_est_c128, void *xhat_c128, double *scalars,
                          void *stream_)
 {
+    OFS_TRACE();
     OFS_REQUIRE(x && pilot_cp_start && bins && k_index && pilot_used_c128 && data_used_c128 && h_est_c128 && xhat_c128 && scalars,
                 "ofs_rx_chain: null argument");
     OFS_REQUIRE(in_dtype >= OFS_C64 && in_dtype <= OFS_IQ16, "ofs_rx_chain: unknown dtype");

@@ -691,6 +691,7 @@ using namespace ofs;
 OFS_API int ofs_aa_metric_reference(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_antennas, int64_t n,
                                     int32_t L, void *P_c128, double *R, double *M, uint8_t *valid, void *stream)
 {
+    OFS_TRACE();
     OFS_REQUIRE(x && P_c128 && R && M && valid, "ofs_aa_metric_reference: null argument");
     OFS_REQUIRE(n_antennas >= 1 && n_antennas <= 64, "ofs_aa_metric_reference: 1..64 antennas");
     OFS_REQUIRE(L > 0 && n >= 0 && n_frames >= 0, "ofs_aa_metric_reference: bad geometry");
@@ -712,6 +713,7 @@ OFS_API int ofs_minn_rtl_metric(const void *x, int32_t in_dtype, int64_t n_frame
                                 double *corr_scaled, double *energy_scaled, uint8_t *metric_valid, uint8_t *above,
                                 void *stream_)
 {
+    OFS_TRACE();
     OFS_REQUIRE(x && corr_total && corr_positive && smooth_metric && energy_total && corr_scaled && energy_scaled &&
                     metric_valid && above, "ofs_minn_rtl_metric: null argument");
     OFS_REQUIRE(in_dtype == OFS_C64 || in_dtype == OFS_C128, "ofs_minn_rtl_metric: complex64/complex128 input");
@@ -805,6 +807,7 @@ OFS_API int ofs_minn_rtl_int(const int16_t *iq, int64_t n_frames, int32_t n_bran
                              int64_t *corr_total, int64_t *corr_positive, int64_t *smooth_metric, int64_t *energy_total,
                              uint8_t *metric_valid, uint8_t *above, void *stream_)
 {
+    OFS_TRACE();
     OFS_REQUIRE(iq && corr_total && corr_positive && smooth_metric && energy_total && metric_valid && above,
                 "ofs_minn_rtl_int: null argument");
     OFS_REQUIRE(quarter_len > 0 && (lag_extra == 0 || lag_extra == 1), "ofs_minn_rtl_int: bad quarter_len / lag_extra");

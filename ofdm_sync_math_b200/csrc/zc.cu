@@ -450,6 +450,7 @@ OFS_API int ofs_zc_matched_filter(const void *x, int32_t in_dtype, int64_t n_fra
                                   const void *ref_c128, int32_t nr, int32_t mode, int32_t out_f64, void *corr_out,
                                   void *mag_out, int64_t out_stride, void *stream_)
 {
+    OFS_TRACE();
     OFS_REQUIRE(x && ref_c128 && (corr_out || mag_out), "ofs_zc_matched_filter: null argument");
     OFS_REQUIRE(nr >= 1 && nr <= 2048, "ofs_zc_matched_filter: reference length must be 1..2048");
     OFS_REQUIRE(mode >= 0 && mode <= 2, "ofs_zc_matched_filter: mode must be 0, 1 or 2");
@@ -531,6 +532,7 @@ OFS_API int ofs_zc_matched_filter(const void *x, int32_t in_dtype, int64_t n_fra
 OFS_API int ofs_zc_normalize(const void *corr, const void *x, int32_t in_dtype, int64_t n_frames, int64_t n, int32_t nr,
                              double ref_norm, int32_t f64, void *out, int64_t stride, void *stream)
 {
+    OFS_TRACE();
     OFS_REQUIRE(corr && x && out, "ofs_zc_normalize: null argument");
     OFS_REQUIRE(in_dtype >= OFS_C64 && in_dtype <= OFS_IQ16, "ofs_zc_normalize: unknown dtype");
     OFS_REQUIRE(n >= 1 && nr >= 1 && n_frames >= 0 && n_frames < 65536 && stride >= n + nr - 1, "ofs_zc_normalize: bad geometry");
@@ -554,6 +556,7 @@ OFS_API int ofs_zc_freq_metric(const void *x, int32_t in_dtype, int64_t n_frames
                                int32_t n_fft, int32_t cp, const int32_t *bins, const void *templ_c128, int32_t nbins,
                                double templ_energy, int32_t out_f64, void *metric, int64_t out_stride, void *stream_)
 {
+    OFS_TRACE();
     OFS_REQUIRE(x && bins && templ_c128 && metric, "ofs_zc_freq_metric: null argument");
     OFS_REQUIRE(n_fft >= 2 && n_fft <= 2048 && cp >= 0 && nbins >= 1, "ofs_zc_freq_metric: n_fft must be 2..2048");
     const int64_t n_off = n - ((int64_t)n_fft + cp) + 1;

@@ -666,6 +666,7 @@ OFS_API int ofs_zc_bank(const void *x_c64, int64_t n_frames, int64_t n, int32_t 
                         const void *templ_c64, int32_t nbins, int32_t n_roots, float *best_metric, int32_t *best_offset,
                         void *stream)
 {
+    OFS_TRACE();
     OFS_REQUIRE(best_metric && best_offset, "ofs_zc_bank: null output");
     return bank_run(x_c64, n_frames, n, n_fft, cp, bins, templ_c64, nbins, n_roots, best_metric, best_offset, nullptr, 0, 1.0f, stream);
 }
@@ -674,6 +675,7 @@ OFS_API int ofs_zc_freq_metric_fast(const void *x_c64, int64_t n_frames, int64_t
                                     const void *templ_c64, int32_t nbins, double templ_energy, float *metric,
                                     int64_t out_stride, void *stream)
 {
+    OFS_TRACE();
     OFS_REQUIRE(metric && templ_energy > 0.0, "ofs_zc_freq_metric_fast: bad arguments");
     const int64_t n_off = n - ((int64_t)n_fft + cp) + 1;
     OFS_REQUIRE(n_off > 0, "Received stream is shorter than a single OFDM symbol.");   /* zc_freq.py:76-78 */

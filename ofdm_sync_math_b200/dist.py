@@ -8,6 +8,21 @@ import torch
 import torch.distributed as dist
 
 
+def init(backend: str | None = None, timeout_s: float = 120.0, device_id=None) -> None:
+    """init_process_group with a bounded collective timeout (a rank that died must not hang the others for
+    the default 10-30 minutes): the records all_gather is the only collective of the engine and moves < 1 MB, so two minutes
+    mean a lost peer, not a slow one.  RANK / WORLD_SIZE / MASTER_* come from the environment (torchrun)."""
+    from datetime import timedelta
+    if dist.is_initialized():
+        return
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    kw = {"timeout": timedelta(seconds=float(timeout_s))}
+    if device_id is not None and backend == "nccl":
+        kw["device_id"] = device_id
+    dist.init_process_group(backend, **kw)
+
+
 def shard_range(n_items: int, rank: int | None = None, world: int | None = None) -> tuple[int, int]:
     """Contiguous block [lo, hi) of the batch axis owned by `rank` (sizes differ by at most one)."""
     world = dist.get_world_size() if world is None else world
@@ -85,3 +100,24 @@ def gather_records(rec: torch.Tensor, n_total: int) -> np.ndarray | None:
     g = RecordGatherer(rec, max(sizes))
     parts = g.run()
     return np.concatenate([parts[r][: sizes[r]].cpu().numpy() for r in range(world)], axis=0)
+
+
+def gather_records_or_files(rec: torch.Tensor, n_total: int, fallback_dir=None):
+    """gather_records, but a failed collective (peer lost, NCCL timeout -- see init()) does not lose this rank's detections:
+    they are written to `<fallback_dir>/records_rank<r>_of<w>.npy` (global frame range in the file name) and None is returned,
+    so a post-mortem can still assemble the batch from the per-rank files."""
+    try:
+        return gather_records(rec, n_total)
+    except Exception as e:                         # DistBackendError / RuntimeError depending on the backend
+        if fallback_dir is None:
+            raise
+        from pathlib import Path
+        d = Path(fallback_dir)
+        d.mkdir(parents=True, exist_ok=True)
+        rank, world = dist.get_rank(), dist.get_world_size()
+        lo, hi = shard_range(n_total, rank, world)
+        path = d / f"records_rank{rank}_of{world}_frames{lo}-{hi}.npy"
+        np.save(path, rec.detach().cpu().numpy())
+        import sys
+        print(f"[ofdm_sync_math_b200.dist] records gather failed on rank {rank} ({type(e).__name__}: {e}); wrote {path}", file=sys.stderr)
+        return None

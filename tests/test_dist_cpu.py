@@ -105,3 +105,40 @@ def test_gloo_world2_gather_event_records():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, True), (1, True)]
+
+
+def _worker_fallback(rank, world, port, tmp, q):
+    """A failing collective: every rank keeps its records in a per-rank file instead of losing them."""
+    sys.path.insert(0, str(ROOT))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    os.environ["RANK"] = str(rank); os.environ["WORLD_SIZE"] = str(world)
+    from ofdm_sync_math_b200 import dist as odist
+    odist.init("gloo", timeout_s=30.0)
+    lo, hi = odist.shard_range(10)
+    rec = torch.full((hi - lo, 40), rank + 1, dtype=torch.uint8)
+    ok_path = odist.gather_records_or_files(rec, 10, tmp) is not None       # healthy group: the gather works
+    real = dist.all_gather
+    dist.all_gather = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("simulated NCCL timeout"))
+    try:
+        none = odist.gather_records_or_files(rec, 10, tmp)
+    finally:
+        dist.all_gather = real
+    q.put((rank, ok_path, none is None))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_gather_failure_writes_rank_files(tmp_path):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_fallback, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True, True), (1, True, True)]
+    files = sorted(f.name for f in tmp_path.iterdir())
+    assert files == ["records_rank0_of2_frames0-5.npy", "records_rank1_of2_frames5-10.npy"]
+    assert np.load(tmp_path / files[1]).shape == (5, 40) and int(np.load(tmp_path / files[1])[0, 0]) == 2

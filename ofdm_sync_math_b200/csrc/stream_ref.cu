@@ -568,6 +568,8 @@ __global__ void __launch_bounds__(PSN, 3) rtl_smooth_par_kernel(const long long 
         const double y = ystart[hs + tid - nblk];
         lo = (long long)floor(y) - (1LL << shift) - 1;
         hi = (long long)ceil(y) + 1;
+        if (lo < 0) lo = 0;                          // corr_positive >= 0 keeps the state >= 0; without this a bracket that starts
+                                                     // below zero sticks at -(2^k - 1) through a run of zeros (a fixed point) and never closes
     }
     bool resolved = false;
     for (int blk = 0; blk <= nblk; ++blk) {

@@ -215,6 +215,13 @@ def run_cases(a, sink, device_index: int = 0):
         emit("cfg4 zc_freq metric (62-bin sliding DFT, float64 prefix)", ms, F * n, flops=F * (n - 2559) * 62 * 2 * 16,
              note=f"{F} captures x {n}; flops ~ 62 bins x 2 (tile halo) x ~16 per modulated-prefix sample (float64: the fp32 peak does not apply)",
              key="cfg4_zcfreq_f64")
+        Ff = max(int(2048 * a.scale), 4)
+        xf = synth.make_batch_device(Ff, n, "sc", seed=11, device=dev, chunk=64)[:, None]
+        ms32 = timeit(lambda: engine.zc_freq_metric(xf, bi, tb, 62.0, out_f64=False, fast="f32"), steps=3, warmup=2)
+        emit("cfg4 zc_freq metric, float32 sliding-DFT kernel (packed fp32 recurrence, 1e-4 tolerance)", ms32, Ff * n,
+             flops=Ff * (n - 2559) * 62 * 24.0, key="cfg4_zcfreq_f32",
+             note=f"{Ff} captures x {n}; flops = 62 bins x 12 FMA-class operations per offset (rotation 4, energy 2, template product 4, feed 2)")
+        del xf
         ms = timeit(lambda: engine.zc_freq_metric(x, bi, tb, 62.0, out_f64=False, fast=True), steps=3, warmup=2)
         emit("cfg4 zc_freq metric, fast path (bank kernel: sliding-DFT recurrence + tcgen05, one template)", ms, F * n,
              alg_bytes=F * (8 * n + 4 * (n - 2559)), note="8 B in + 4 B metric out per sample; FP16 operands, 5e-3 tolerance",

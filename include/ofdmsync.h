@@ -276,6 +276,13 @@ int ofs_zc_freq_metric_fast(const void *x_c64, int64_t n_frames, int64_t n, int3
                             const void *templ_c64, int32_t nbins, double templ_energy, float *metric,
                             int64_t out_stride, void *stream);
 
+/* zc_freq.compute_frequency_metric at float32 accuracy (|d metric| <= 1e-4 * max(metric)) for complex64 single-branch captures:
+ * the sliding-DFT recurrence of the bank in packed fp32 with a float32 epilogue (no fp16 operands, no tensor cores) -- ~40x
+ * the float64-prefix kernel of ofs_zc_freq_metric.  bins int32[nbins], templ complex64[nbins] on the device, nbins <= 64. */
+int ofs_zc_freq_metric_f32(const void *x_c64, int64_t n_frames, int64_t n, int32_t n_fft, int32_t cp, const int32_t *bins,
+                           const void *templ_c64, int32_t nbins, double templ_energy, float *metric,
+                           int64_t out_stride, void *stream);
+
 /* Impairment chain = channel.apply_channel (channel.py:51-98) -> core.apply_cfo (core.py:123-138) ->
  * sync_aa.quantize_adc (sync_aa.py:263-291), batched on the device.
  *   tx: complex64 / complex128 [n_rows][n_tx]; taps (optional): complex128[n_taps] -> full convolution, n_out = n_tx+n_taps-1

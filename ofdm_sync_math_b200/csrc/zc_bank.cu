@@ -527,6 +527,142 @@ zc_bank_fused_kernel(const __grid_constant__ CUtensorMap mapT, const BankParams 
     if (warp == BK_PW) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------ K5b: float32 sliding DFT
+// zc_freq.compute_frequency_metric (zc_freq.py:62-99) for complex64 single-branch captures at float32 accuracy, SIMT only:
+// the producer recurrence of the bank above -- b(o+1) = w (b(o) + x[o+cp+N] - x[o+cp]), two bins per lane in packed fp32,
+// the rotation's systematic error divided out every 32 steps so that rounding only random-walks (~6e-8 sqrt(steps)) --
+// with a float32 epilogue instead of the fp16 tensor-core product: every step adds |b|^2 and conj(T) b of the lane's two
+// bins to 16-step partials, a transposed warp reduction (3 x 15 shuffles per 16 offsets) sums them over the 64 bins, and the
+// even lanes finish metric = |corr|^2 / max(E_T E, 1e-12).  One warp = one chain of offsets (N warm-up steps from an empty
+// window, then chain_len offsets).  Bound: fp32 FMA / issue -- 62 bins x ~12 FMA-class instructions per offset (the
+// reference's per-offset FFT is replaced by the recurrence, but the 62 bins are each 2 complex MACs per offset whatever one
+// does): 134 M offsets of cfg 4 are ~3 G warp instructions, 2.7 ms at full issue rate.
+constexpr int SD_WARPS = 8;
+struct SdftParams {
+    const float2 *x;
+    int64_t n, n_off, chain_len, n_chains, mstride;
+    int N, cp, chains_per_cap;
+    const float4 *wtab;        // [64] (w_re, w_im, kappa_re, kappa_im)
+    const float2 *ttab;        // [64] template bins (0 beyond nbins)
+    float templ_energy;
+    float *metric;
+};
+
+__global__ void zc_sdft_prep_kernel(const float2 *templ, int nbins, const int *bins, int N, float4 *wtab, float2 *ttab)
+{
+    const int k = threadIdx.x;          // 64 threads
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 t = make_float2(0.f, 0.f);
+    if (k < nbins) {
+        double sn, cs;
+        sincospi(2.0 * (double)bins[k] / (double)N, &sn, &cs);
+        const float hr = (float)cs, hi = (float)sn;
+        const double mag2 = (double)hr * hr + (double)hi * hi;
+        double qr = (cs * hr + sn * hi) / mag2, qi = (sn * hr - cs * hi) / mag2;      // w / w_float
+        double kr = 1.0, ki = 0.0;
+        for (int q = 0; q < 32; ++q) { const double u = kr * qr - ki * qi; ki = kr * qi + ki * qr; kr = u; }
+        w = make_float4(hr, hi, (float)kr, (float)ki);
+        t = templ[k];
+    }
+    wtab[k] = w; ttab[k] = t;
+}
+
+__global__ void __launch_bounds__(SD_WARPS * 32) zc_sdft_kernel(const SdftParams p)
+{
+    __shared__ float4 sC[SD_WARPS][2][32];        // comb samples of a 32-step block as (x, x, y, y), double-buffered per warp
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t chain = (int64_t)blockIdx.x * SD_WARPS + warp;
+    if (chain >= p.n_chains) return;
+    const int64_t cap = chain / p.chains_per_cap;
+    const int64_t o_lo = (chain % p.chains_per_cap) * p.chain_len;
+    const int64_t o_hi = o_lo + p.chain_len < p.n_off ? o_lo + p.chain_len : p.n_off;
+    if (o_lo >= o_hi) return;
+    const float2 *xc = p.x + cap * p.n;
+    float *mrow = p.metric + cap * p.mstride;
+    const int64_t s0 = o_lo + p.cp;                                   // first sample of the chain's first window
+    const float4 w0 = p.wtab[lane], w1 = p.wtab[32 + lane];
+    const float2 WX = make_float2(w0.x, w1.x), WY = make_float2(w0.y, w1.y), NWY = make_float2(-w0.y, -w1.y);
+    const float2 KX = make_float2(w0.z, w1.z), KY = make_float2(w0.w, w1.w), NKY = make_float2(-w0.w, -w1.w);
+    const float2 t0 = p.ttab[lane], t1 = p.ttab[32 + lane];
+    const float2 TR = make_float2(t0.x, t1.x), TI = make_float2(t0.y, t1.y), NTI = make_float2(-t0.y, -t1.y);
+    float4 *sc = &sC[warp][0][0];
+    auto ldx = [&](int64_t idx) { return idx < p.n ? __ldg(xc + idx) : make_float2(0.f, 0.f); };
+    const int n_warm = p.N / 32, n_real = (int)((o_hi - o_lo + 31) / 32), n_blocks = n_warm + n_real;
+    auto feed = [&](int u, float2 &a, float2 &b) {      // comb sample = a - b
+        if (u < n_warm) { a = ldx(s0 + 32 * (int64_t)u + lane); b = make_float2(0.f, 0.f); return; }
+        const int64_t s = s0 + 32 * (int64_t)(u - n_warm) + lane;
+        a = ldx(s + p.N); b = ldx(s);
+    };
+    float2 Bx = make_float2(0.f, 0.f), By = Bx;          // (bin lane, bin lane + 32): real parts, imaginary parts
+    {
+        float2 a, b;
+        feed(0, a, b);
+        sc[lane] = make_float4(a.x - b.x, a.x - b.x, a.y - b.y, a.y - b.y);
+    }
+    __syncwarp();
+    for (int u = 0; u < n_blocks; ++u) {
+        float2 na = make_float2(0.f, 0.f), nb = na;
+        if (u + 1 < n_blocks) feed(u + 1, na, nb);             // in flight during the 32 steps below
+        const float4 *cb4 = sc + (u & 1) * 32;
+        if (u < n_warm) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float4 c = cb4[i];
+                const float2 T = __fadd2_rn(Bx, make_float2(c.x, c.y)), U = __fadd2_rn(By, make_float2(c.z, c.w));
+                Bx = __ffma2_rn(T, WX, __fmul2_rn(U, NWY));
+                By = __ffma2_rn(T, WY, __fmul2_rn(U, WX));
+            }
+        } else {
+            const int64_t ob = o_lo + 32 * (int64_t)(u - n_warm);   // offset of step 0 of this block
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                float e[16], cr[16], ci[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float2 e2 = __ffma2_rn(Bx, Bx, __fmul2_rn(By, By));
+                    e[i] = e2.x + e2.y;
+                    // conj(T) b: re = Tr br + Ti bi, im = Tr bi - Ti br  (np.vdot, zc_freq.py:94)
+                    const float2 r2 = __ffma2_rn(TR, Bx, __fmul2_rn(TI, By)), i2 = __ffma2_rn(TR, By, __fmul2_rn(NTI, Bx));
+                    cr[i] = r2.x + r2.y; ci[i] = i2.x + i2.y;
+                    const float4 c = cb4[16 * hf + i];
+                    const float2 T = __fadd2_rn(Bx, make_float2(c.x, c.y)), U = __fadd2_rn(By, make_float2(c.z, c.w));
+                    Bx = __ffma2_rn(T, WX, __fmul2_rn(U, NWY));
+                    By = __ffma2_rn(T, WY, __fmul2_rn(U, WX));
+                }
+                // transposed reduction over the 32 lanes (= 64 bins): lanes 2r, 2r + 1 end with the totals of step r
+#pragma unroll
+                for (int s = 16; s >= 2; s >>= 1) {
+                    const bool hi = (lane & s) != 0;
+#pragma unroll
+                    for (int k = 0; k < s / 2; ++k) {
+                        const float se = hi ? e[k] : e[k + s / 2], ke = hi ? e[k + s / 2] : e[k];
+                        const float sr = hi ? cr[k] : cr[k + s / 2], kr = hi ? cr[k + s / 2] : cr[k];
+                        const float si = hi ? ci[k] : ci[k + s / 2], ki = hi ? ci[k + s / 2] : ci[k];
+                        e[k] = ke + __shfl_xor_sync(0xffffffffu, se, s);
+                        cr[k] = kr + __shfl_xor_sync(0xffffffffu, sr, s);
+                        ci[k] = ki + __shfl_xor_sync(0xffffffffu, si, s);
+                    }
+                }
+                e[0] += __shfl_xor_sync(0xffffffffu, e[0], 1);
+                cr[0] += __shfl_xor_sync(0xffffffffu, cr[0], 1);
+                ci[0] += __shfl_xor_sync(0xffffffffu, ci[0], 1);
+                const int64_t o = ob + 16 * hf + (lane >> 1);
+                if (!(lane & 1) && o < o_hi) {
+                    const float den = fmaxf(p.templ_energy * e[0], 1e-12f);       // zc_freq.py:96-97
+                    mrow[o] = fmaf(cr[0], cr[0], ci[0] * ci[0]) / den;
+                }
+            }
+        }
+        asm volatile("" : "+f"(na.x), "+f"(na.y), "+f"(nb.x), "+f"(nb.y));
+        sc[((u + 1) & 1) * 32 + lane] = make_float4(na.x - nb.x, na.x - nb.x, na.y - nb.y, na.y - nb.y);
+        {   // per-block correction of the float rotation: b *= kappa
+            const float2 nx = __ffma2_rn(Bx, KX, __fmul2_rn(By, NKY)), ny = __ffma2_rn(Bx, KY, __fmul2_rn(By, KX));
+            Bx = nx; By = ny;
+        }
+        __syncwarp();
+    }
+}
+
 typedef CUresult (*EncodeTiledFn2)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -682,4 +818,43 @@ OFS_API int ofs_zc_freq_metric_fast(const void *x_c64, int64_t n_frames, int64_t
     OFS_REQUIRE(out_stride >= n_off, "ofs_zc_freq_metric_fast: out_stride < number of offsets");
     return bank_run(x_c64, n_frames, n, n_fft, cp, bins, templ_c64, nbins, 1, nullptr, nullptr, metric, out_stride, (float)templ_energy,
                     stream);
+}
+
+OFS_API int ofs_zc_freq_metric_f32(const void *x_c64, int64_t n_frames, int64_t n, int32_t n_fft, int32_t cp, const int32_t *bins,
+                                   const void *templ_c64, int32_t nbins, double templ_energy, float *metric, int64_t out_stride,
+                                   void *stream_)
+{
+    OFS_TRACE();
+    OFS_REQUIRE(x_c64 && bins && templ_c64 && metric && templ_energy > 0.0, "ofs_zc_freq_metric_f32: bad arguments");
+    OFS_REQUIRE(n_fft >= 32 && n_fft <= 65536 && n_fft % 32 == 0 && cp >= 0, "ofs_zc_freq_metric_f32: n_fft must be a multiple of 32 in 32..65536");
+    OFS_REQUIRE(nbins >= 1 && nbins <= 64, "ofs_zc_freq_metric_f32: nbins <= 64");
+    const int64_t n_off = n - ((int64_t)n_fft + cp) + 1;
+    OFS_REQUIRE(n_off > 0, "Received stream is shorter than a single OFDM symbol.");   /* zc_freq.py:76-78 */
+    OFS_REQUIRE(out_stride >= n_off, "ofs_zc_freq_metric_f32: out_stride < number of offsets");
+    if (n_frames == 0) return OFS_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    keep_pool_cached();
+    float4 *wtab = nullptr;
+    float2 *ttab = nullptr;
+    OFS_CUDA(cudaMallocAsync((void **)&wtab, 64 * sizeof(float4), stream));
+    OFS_CUDA(cudaMallocAsync((void **)&ttab, 64 * sizeof(float2), stream));
+    zc_sdft_prep_kernel<<<1, 64, 0, stream>>>(reinterpret_cast<const float2 *>(templ_c64), nbins, bins, n_fft, wtab, ttab);
+    if (int rc = check_launch("zc_sdft_prep_kernel")) return rc;
+    // chains: each pays an n_fft-step warm-up, so they are >= 4 windows long; enough of them to fill the machine ~4 times
+    int64_t chain_len = 4LL * n_fft;
+    const int64_t want = 4LL * sm_count() * 16;                       // warps wanted
+    while (chain_len > n_fft && n_frames * ((n_off + chain_len - 1) / chain_len) < want) chain_len /= 2;
+    while (n_frames * ((n_off + chain_len - 1) / chain_len) > 8 * want && chain_len < n_off) chain_len *= 2;
+    chain_len = (chain_len + 31) / 32 * 32;
+    SdftParams p{};
+    p.x = reinterpret_cast<const float2 *>(x_c64); p.n = n; p.n_off = n_off; p.chain_len = chain_len;
+    p.chains_per_cap = (int)((n_off + chain_len - 1) / chain_len); p.n_chains = n_frames * p.chains_per_cap; p.mstride = out_stride;
+    p.N = n_fft; p.cp = cp; p.wtab = wtab; p.ttab = ttab; p.templ_energy = (float)templ_energy; p.metric = metric;
+    const int64_t grid = (p.n_chains + SD_WARPS - 1) / SD_WARPS;
+    OFS_REQUIRE(grid < (1LL << 31), "ofs_zc_freq_metric_f32: grid too large");
+    zc_sdft_kernel<<<(unsigned)grid, SD_WARPS * 32, 0, stream>>>(p);
+    if (int rc = check_launch("zc_sdft_kernel")) return rc;
+    OFS_CUDA(cudaFreeAsync(wtab, stream));
+    OFS_CUDA(cudaFreeAsync(ttab, stream));
+    return OFS_OK;
 }

@@ -98,3 +98,39 @@ def test_zc_v2_detect_on_reference_fixture_repeated(golden):
     # first repetition = the fixture itself (the tail of the capture changes nothing before its own events)
     n_first = int((g["events"][:, 2] < rx.shape[1]).sum())
     assert [t[0] for t in got[:n_first]] == g["events"][:n_first, 0].tolist()
+
+
+@pytest.mark.parametrize("n", [4000, 20000, 65536])
+def test_zc_freq_f32_sliding_dft_vs_oracle(n):
+    """compute_frequency_metric (zc_freq.py:62-99) on the packed-fp32 sliding-DFT kernel: float32 metric within 1e-4 of the
+    float64 oracle's maximum (north_star float tolerance) on noisy captures with PSS symbols, silence and a loud burst."""
+    from ofdm_sync_math_b200 import engine
+    from ofdm_sync_math_b200.zc import generate_zadoff_chu
+    half = 31
+    bi = np.concatenate((np.arange(-half, 0), np.arange(1, half + 1)))
+    tb = generate_zadoff_chu(25, 62)
+    x = np.stack([_pss_capture(n, 300 + s, snr_db=[0.0, 10.0, 25.0][s % 3], n_pss=2 if n > 8000 else 1) for s in range(3)]) \
+        if n > 8000 else np.stack([_pss_capture(8000, 300 + s)[:n] for s in range(3)])
+    x[1, n // 2:n // 2 + 300] *= 40.0            # a loud burst: the recurrence must forget it once it has left the window
+    x[2, : n // 4] = 0                           # exact silence
+    m = engine.zc_freq_metric(torch.as_tensor(x).cuda()[:, None], bi, tb, 62.0, fast="f32").cpu().numpy()
+    for f in range(x.shape[0]):
+        mo = orc.compute_frequency_metric(x[f].astype(np.complex128), bi, tb, 62.0)
+        assert m[f].shape == mo.shape
+        err = np.abs(m[f] - mo).max()
+        assert err <= 1e-4 * mo.max(), (f, err / mo.max())
+        assert int(np.argmax(m[f])) == int(np.argmax(mo))
+
+
+def test_zc_freq_f32_on_reference_fixture(golden):
+    from ofdm_sync_math_b200 import engine
+    for tag in ("cir1", "awgn"):
+        g = golden(f"zc_freq_{tag}")
+        rx = np.asarray(g["rx"])
+        rx = rx[0] if rx.ndim == 2 else rx          # the fast kernel takes one branch
+        x = rx.astype(np.complex64)
+        m = engine.zc_freq_metric(torch.as_tensor(x).cuda()[None, None], g["bin_indices"], g["template"], float(g["template_energy"]),
+                                  fast="f32").cpu().numpy()[0]
+        mo = orc.compute_frequency_metric(x.astype(np.complex128), g["bin_indices"], g["template"], float(g["template_energy"]))
+        assert np.abs(m - mo).max() <= 1e-4 * mo.max()
+        assert int(np.argmax(m)) == int(np.argmax(mo))

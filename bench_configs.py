@@ -272,9 +272,14 @@ def run_cases(a, sink, device_index: int = 0):
         def run():
             d = engine.minn_rtl_int(iq, 512, 3, 3276, 15)
             return engine.minn_rtl_events(d["corr_positive"], d["metric_valid"], d["above_threshold"], 2, 0)
-        ms = timeit(run, steps=3, warmup=2)
-        emit("cfg1 minn_rtl integer datapath + gate FSM (reference-order streams)", ms, F * A * n, alg_bytes=F * n * (4 * A + 4 * 8 + 2),
-             note=f"{F} streams x {A} antennas x {n} int16 IQ; int64 arrays out", key="cfg1_rtl_int")
+        ms_alloc = timeit(run, steps=3, warmup=2)
+        rplan = engine.RtlIntPlan(F, A, n, 512, 3, 3276, 15, hysteresis=2, timing_offset=0, max_events=2048)
+        ms = timeit(lambda: rplan.run(iq), steps=5, warmup=2)
+        emit("cfg1 minn_rtl integer datapath (window sums + combine, parallel floor-shift smoother, threshold) + gate FSM, on the device",
+             ms, F * A * n, alg_bytes=F * n * (4 * A + 4 * 8 + 2), key="cfg1_rtl_int",
+             note=f"{F} streams x {A} antennas x {n} int16 IQ; all six int64 / uint8 state arrays written (34 B per sample); with "
+                  f"allocation of the arrays and host event lists per call (engine.minn_rtl_int + minn_rtl_events): {ms_alloc:.2f} ms")
+        del rplan
         del iq
     if "mb" in cases:
         # two branches per frame (what minn.py:347-351 feeds): multi-branch stripe kernel vs the precise tile kernel

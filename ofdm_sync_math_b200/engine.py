@@ -621,6 +621,37 @@ def minn_rtl_int(iq, quarter_len: int, smooth_shift: int, threshold_value: int, 
     return d
 
 
+class RtlIntPlan:
+    """Integer RTL datapath + gate FSM (ofs_minn_rtl_int + ofs_minn_rtl_events) for repeated batches of int16-IQ streams
+    [F, B, n, 2] with every buffer allocated once: the six state arrays (int64 / uint8 [F, n]), event slots and counts.
+    run() only launches (window sums + antenna combining, parallel floor-shift smoother, threshold, gate FSM); events() reads back."""
+
+    def __init__(self, n_frames: int, n_branches: int, n: int, quarter_len: int = 512, smooth_shift: int = 3,
+                 threshold_value: int = 3276, frac_bits: int = 15, hysteresis: int = 2, timing_offset: int = 0,
+                 lag_extra: int = 0, max_events: int = L.OFS_MAX_EVENTS):
+        dev = _device()
+        self.F, self.B, self.n = n_frames, n_branches, n
+        self.args = (int(quarter_len), int(smooth_shift), int(threshold_value), int(frac_bits), int(lag_extra))
+        self.hyst, self.toff = int(hysteresis), int(timing_offset)
+        f = lambda: torch.empty((n_frames, n), dtype=torch.int64, device=dev)
+        u = lambda: torch.empty((n_frames, n), dtype=torch.uint8, device=dev)
+        self.state = dict(corr_total=f(), corr_positive=f(), smooth_metric=f(), energy_total=f(), metric_valid=u(), above_threshold=u())
+        self.cap = int(max_events)
+        self.ev, self.cnt, self.records = _event_buffers(n_frames, dev, want_flat=True, cap=self.cap)
+
+    def run(self, iq: torch.Tensor) -> None:
+        assert iq.is_cuda and iq.is_contiguous() and iq.dtype == torch.int16 and tuple(iq.shape) == (self.F, self.B, self.n, 2)
+        d = self.state
+        L.check(L.lib().ofs_minn_rtl_int(_ptr(iq), C.c_int64(self.F), int(self.B), C.c_int64(self.n), *self.args,
+                                         *[_ptr(d[k]) for k in d], _stream()), "ofs_minn_rtl_int")
+        L.check(L.lib().ofs_minn_rtl_events(_ptr(d["corr_positive"]), 1, _ptr(d["metric_valid"]), _ptr(d["above_threshold"]),
+                                            C.c_int64(self.F), C.c_int64(self.n), C.c_int64(self.n), self.hyst, self.toff,
+                                            _ptr(self.ev), _ptr(self.cnt), int(self.cap), _stream()), "ofs_minn_rtl_events")
+
+    def events(self, overflow: str = "raise") -> list[np.ndarray]:
+        return _events_to_numpy(self.ev, self.cnt, self.cap, overflow)
+
+
 # ------------------------------------------------------------------------------------------- Zadoff-Chu
 def zc_matched_filter(rx, ref, mode: int = 0, out_f64: bool | None = None, want_corr: bool = True):
     """FFT overlap-save matched filter (zc.py:115-126 mode 0, zc_v2.py:486-495 mode 1, raw sum mode 2)

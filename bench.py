@@ -378,12 +378,42 @@ def main() -> None:
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * Fe * n * e_steps / float(te.item()) / 1e6
+    # what the box can move at most: the same pinned buffers through plain copies, all ranks at once (H2D of x alone, and H2D of x
+    # with D2H of M on a second stream) -- the ceiling e2e is judged against (profiles/r2_e2e_ceiling_n{2,8}.json: the host side
+    # gives 55 GB/s to one GPU alone and 184 GB/s to eight at once)
+    xd_probe = x[:Fe]
+    s2 = torch.cuda.Stream()
+
+    def copies(bidir: bool) -> float:
+        def go():
+            xd_probe.copy_(xh, non_blocking=True)
+            if bidir:
+                with torch.cuda.stream(s2):
+                    Mh.copy_(plan.M[:Fe], non_blocking=True)
+                torch.cuda.current_stream().wait_stream(s2)
+        go(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0c = time.perf_counter()
+        for _ in range(2):
+            go()
+        torch.cuda.synchronize()
+        tc = torch.tensor([(time.perf_counter() - t0c) / 2], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        return float(tc.item())
+    t_h2d, t_bidir = copies(False), copies(True)          # (xh holds a copy of x[:Fe]: the device input is unchanged)
+    ceiling = {"h2d_GBps": world * Fe * n * 8 / t_h2d / 1e9, "h2d_plus_d2h_GBps": world * (Fe * n * 8 + Fe * out_len * 4) / t_bidir / 1e9,
+               "what": "plain pinned-memory copies of the same buffers, all ranks at once (x in alone; x in + M out on two streams)"}
+    e2e_gbps = world * (Fe * n * 8 + Fe * (out_len * 4 + engine.REC_BYTES)) * e_steps / float(te.item()) / 1e9
     # parity of the two paths on the same frames (indices must agree)
     rec_d = plan.records_numpy()
     e2e_match = bool((rec_h["timing"] == rec_d["timing"][:Fe]).all())
     hs.close()
     e2e = {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": Fe * n * 8, "d2h_bytes_per_step": Fe * (out_len * 4 + engine.REC_BYTES),
            "frames_per_step": Fe, "steps": e_steps, "records_match_device_path": e2e_match,
+           "GBps_both_directions": e2e_gbps, "host_link_ceiling": ceiling,
+           "fraction_of_bidirectional_ceiling": e2e_gbps / ceiling["h2d_plus_d2h_GBps"],
            "api": "ofs_sync_host (pinned host x -> M + records in host memory)"}
 
     # ---- CPU baseline: the oracle port on a bounded sample of the same workload (rank 0, N = 1 only)

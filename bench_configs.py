@@ -221,6 +221,11 @@ def run_cases(a, sink, device_index: int = 0):
         emit("cfg4 zc_freq metric, float32 sliding-DFT kernel (packed fp32 recurrence, 1e-4 tolerance)", ms32, Ff * n,
              flops=Ff * (n - 2559) * 62 * 24.0, key="cfg4_zcfreq_f32",
              note=f"{Ff} captures x {n}; flops = 62 bins x 12 FMA-class operations per offset (rotation 4, energy 2, template product 4, feed 2)")
+        msf = timeit(lambda: engine.zc_freq_metric(xf, bi, tb, 62.0, out_f64=False, fast="fft"), steps=3, warmup=2)
+        # 1 forward + 2 inverse 8192-point FFTs per 6145 offsets, 5 N log2 N flops each, + 2 pointwise products
+        emit("cfg4 zc_freq metric, FFT form (two overlap-save filters + energy recurrence, float32, 1e-4 tolerance)", msf, Ff * n,
+             alg_bytes=Ff * (8 * n + 4 * (n - 2559)), key="cfg4_zcfreq_fft",
+             note=f"{Ff} captures x {n}; 8 B in + 4 B metric out per sample; {Ff * ((n - 2559 + 6144) // 6145) * (3 * 5 * 8192 * 13 + 2 * 6 * 8192) / msf / 1e9:.1f} TFLOP/s of FFT arithmetic")
         del xf
         ms = timeit(lambda: engine.zc_freq_metric(x, bi, tb, 62.0, out_f64=False, fast=True), steps=3, warmup=2)
         emit("cfg4 zc_freq metric, fast path (bank kernel: sliding-DFT recurrence + tcgen05, one template)", ms, F * n,

@@ -283,6 +283,15 @@ int ofs_zc_freq_metric_f32(const void *x_c64, int64_t n_frames, int64_t n, int32
                            const void *templ_c64, int32_t nbins, double templ_energy, float *metric,
                            int64_t out_stride, void *stream);
 
+/* zc_freq.compute_frequency_metric (zc_freq.py:62-99) in FFT form, float32 (|d metric| <= 1e-4 * max(metric)), complex64
+ * single-branch captures, n_fft <= 2048, nbins <= 64: np.vdot(template, bins) (:94) and sum(bins) are two n_fft-tap matched
+ * filters of the capture (8192-point overlap-save blocks, one forward and two inverse FFTs per block), and the in-band energy
+ * sum|bins|^2 (:95) follows E(o+1) = E(o) + 2 Re(conj(sum bins(o)) d(o)) + nbins |d(o)|^2, d(o) = x[o+cp+n_fft] - x[o+cp],
+ * anchored by a direct DFT and carried in float64.  ~2.5x ofs_zc_freq_metric_f32.  Same arguments as ofs_zc_freq_metric_f32. */
+int ofs_zc_freq_metric_fft(const void *x_c64, int64_t n_frames, int64_t n, int32_t n_fft, int32_t cp, const int32_t *bins,
+                           const void *templ_c64, int32_t nbins, double templ_energy, float *metric,
+                           int64_t out_stride, void *stream);
+
 /* Impairment chain = channel.apply_channel (channel.py:51-98) -> core.apply_cfo (core.py:123-138) ->
  * sync_aa.quantize_adc (sync_aa.py:263-291), batched on the device.
  *   tx: complex64 / complex128 [n_rows][n_tx]; taps (optional): complex128[n_taps] -> full convolution, n_out = n_tx+n_taps-1

@@ -11,6 +11,7 @@
 //                       instead of one 2048-point FFT per candidate offset.
 #include "common.cuh"
 #include "fft4096.cuh"
+#include "conv8k.cuh"
 #include <cstdlib>
 
 namespace ofs {
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(ZNT, (sizeof(T) == 4 ? 3 : 1)) zc_mf_kernel(co
 // pointwise product in transform order -> inverse FFT -> normalise), float32 throughout the epilogue (reciprocal square root
 // instead of float64 divisions and hypot), the filter spectrum as a float2 table, |corr| as the only mandatory output.
 __device__ __forceinline__ int spad(int i) { return i + (i >> 5); }     // energy prefix: 32-element thread stride -> 33
+__device__ __forceinline__ float sqrt_approx(float v) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }   // MUFU.SQRT, <= 1 ulp off
 
 __global__ void zc_twiddle8_kernel(float2 *tw8f, double2 *tw8d)
 {
@@ -207,7 +209,12 @@ __global__ void __launch_bounds__(ZNT) zc_spectrum8k_kernel(const double2 *ref, 
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
     __syncthreads();
     fft8k_dif<double2>(a, tw, tw8d[threadIdx.x]);
-    for (int m = threadIdx.x; m < ZF8; m += ZNT) { const double2 g = a[zpad8(m)]; G8[m] = make_float2((float)g.x, (float)g.y); }
+    // stage-C order of conv8k.cuh, 1/8192 folded in
+    for (int m = threadIdx.x; m < ZF8; m += ZNT) {
+        const double2 g = a[zpad8(m)];
+        const int h = m >> 12, t = (m & (ZF - 1)) >> 4, q = m & 15;
+        G8[conv8k_gidx(h, t, q)] = make_float2((float)(g.x / ZF8), (float)(g.y / ZF8));
+    }
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int w = 0; w < ZNT / 32; ++w) t += red[w];
@@ -217,7 +224,7 @@ __global__ void __launch_bounds__(ZNT) zc_spectrum8k_kernel(const double2 *ref, 
 
 template <int DT>
 __global__ void __launch_bounds__(ZNT, 2) zc_mf8k_kernel(const void *x, int64_t n, int nr, const double2 *tw, const float2 *tw8,
-                                                        const float2 *G8, const double *ref_norm_p, int mode, float2 *corr_out,
+                                                        const float2 *Gp, const double *ref_norm_p, int mode, float2 *corr_out,
                                                         float *mag_out, int64_t out_stride, int blocks_per_frame)
 {
     using In = typename InT<DT>::type;
@@ -233,62 +240,291 @@ __global__ void __launch_bounds__(ZNT, 2) zc_mf8k_kernel(const void *x, int64_t 
     const int64_t out_len = n + nr - 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const In *xb = reinterpret_cast<const In *>(x) + frame * n;
-#pragma unroll 8
-    for (int q = 0; q < ZF8 / ZNT; ++q) {
-        const int m = tid + ZNT * q;
-        const int64_t j = jb + m;
-        float2 v = make_float2(0.f, 0.f);
-        if (j >= 0 && j < n) { const In s = xb[j]; v = make_float2((float)s.x, (float)s.y); }
-        a[zpad8(m)] = v;
-        se[spad(m + 1)] = fmaf(v.x, v.x, v.y * v.y);
-    }
+    const float2 w0 = __ldg(tw8 + tid);
+    const bool norm = mode != 2;
+    // local samples [m_lo, m_hi) of the block lie inside the capture (one unsigned compare per sample)
+    const int m_lo = jb < 0 ? (int)(-jb) : 0;
+    const int m_hi = n - jb < ZF8 ? (int)(n - jb) : ZF8;
+    const unsigned m_cnt = m_hi > m_lo ? (unsigned)(m_hi - m_lo) : 0u;
+    const In *xl = xb + jb;
+    conv8k_stage_a(a, tw, w0,
+                   [&](int m) {
+                       float2 v = make_float2(0.f, 0.f);
+                       if ((unsigned)(m - m_lo) < m_cnt) { const In s = xl[m]; v = make_float2((float)s.x, (float)s.y); }
+                       return v;
+                   },
+                   [&](int m, float e) { if (norm) se[spad(m + 1)] = e; });
     if (tid == 0) se[0] = 0.f;
     __syncthreads();
-    if (mode != 2) {
-        // inclusive prefix of the 8192 energies: 32 contiguous values per thread (stride 33 after padding: conflict-free),
-        // warp / CTA carries in float64
-        constexpr int IPT = ZF8 / ZNT;
-        const int s0 = tid * IPT + 1;
+    // inclusive prefix of the 8192 energies: 32 contiguous values per thread (stride 33 after padding: conflict-free),
+    // warp / CTA carries in float64; the CTA carry is added after the next barrier (the one stage B needs anyway)
+    constexpr int IPT = ZF8 / ZNT;
+    const int s0 = tid * IPT + 1;
+    double woff = 0.0;
+    if (norm) {
         float run = 0.f;
 #pragma unroll
         for (int m = 0; m < IPT; ++m) { run += se[spad(s0 + m)]; se[spad(s0 + m)] = run; }
         double t = (double)run;
         for (int o = 1; o < 32; o <<= 1) { const double y = shfl_up_f64(t, o); if (lane >= o) t += y; }
         if (lane == 31) wtot[warp] = t;
-        __syncthreads();
-        double off = t - (double)run;
-        for (int w = 0; w < warp; ++w) off += wtot[w];
-#pragma unroll
-        for (int m = 0; m < IPT; ++m) se[spad(s0 + m)] = (float)((double)se[spad(s0 + m)] + off);
-        __syncthreads();
+        woff = t - (double)run;
     }
-    const float2 w0 = __ldg(tw8 + tid);
-    fft8k_dif<float2>(a, tw, w0);
-#pragma unroll 8
-    for (int q = 0; q < ZF8 / ZNT; ++q) {
-        const int p = tid + ZNT * q;
-        a[zpad8(p)] = cmul(a[zpad8(p)], __ldg(G8 + p));
+    conv8k_stage_b(a, tw);
+    __syncthreads();
+    if (norm) {
+        for (int w = 0; w < warp; ++w) woff += wtot[w];
+#pragma unroll
+        for (int m = 0; m < IPT; ++m) se[spad(s0 + m)] = (float)((double)se[spad(s0 + m)] + woff);
+    }
+    conv8k_stage_c<false>(a, Gp, nullptr, nullptr);
+    __syncthreads();
+    conv8k_stage_d(a, tw);
+    __syncthreads();
+    const float rn = (float)(1.0 / *ref_norm_p);
+    // local outputs m in [nr - 1, o_hi) are this block's: output k0 + i, i = m - (nr - 1), is the window of local samples [i, i + nr - 1]
+    const int64_t left = out_len - k0;
+    const unsigned o_cnt = (unsigned)(left < V ? left : V);
+    float2 *co = corr_out ? corr_out + frame * out_stride + k0 - (nr - 1) : nullptr;
+    float *mo = mag_out ? mag_out + frame * out_stride + k0 - (nr - 1) : nullptr;
+    conv8k_stage_e(a, tw, w0, [&](int m, float2 y, int) {
+        const int i = m - (nr - 1);
+        if ((unsigned)i >= o_cnt) return;
+        float sc = 1.f;
+        if (norm) {
+            const float e = se[spad(i + nr)] - se[spad(i)];
+            sc = rn * (mode == 1 ? rsqrtf(fmaxf(e, 1e-12f))              // zc_v2.py:257-271
+                                 : rsqrtf(fmaxf(e, 0.f) + 1e-12f));     // zc.py:125-126
+        }
+        const float2 ys = __fmul2_rn(y, make_float2(sc, sc));
+        if (co) co[m] = ys;
+        if (mo) mo[m] = sqrt_approx(fmaf(ys.x, ys.x, ys.y * ys.y));
+    });
+}
+
+// ---- K5b: zc_freq.compute_frequency_metric (zc_freq.py:62-99) in FFT form, float32 -----------------------------------
+// With bins_j(o) = DFT bin k_j of x[o+cp : o+cp+N]:
+//   Y(o) = sum_j conj(T_j) bins_j(o) = sum_m x[o+cp+m] h_Y[m],  h_Y[m] = sum_j conj(T_j) e^{-2 pi i k_j m / N}   (np.vdot, :94)
+//   S(o) = sum_j bins_j(o)            = sum_m x[o+cp+m] h_S[m],  h_S[m] = sum_j e^{-2 pi i k_j m / N}
+// are two N-tap matched filters of the same signal, and the in-band energy E(o) = sum_j |bins_j(o)|^2 (:95) obeys
+//   bins_j(o+1) = w_j (bins_j(o) + d(o)),  d(o) = x[o+cp+N] - x[o+cp],  |w_j| = 1
+//   =>  E(o+1) = E(o) + 2 Re(conj(S(o)) d(o)) + J |d(o)|^2                                       (J = number of bins)
+// so the metric |Y|^2 / max(E_T E, eps) (:96-97) costs one forward FFT, two pointwise products and two inverse FFTs per
+// 8192-sample block (conv8k.cuh) plus a prefix sum -- instead of J sliding-DFT recurrences per offset (zc_sdft_kernel) or one
+// N-point FFT per offset (the reference).  One CTA walks consecutive blocks of one capture: E is anchored once per CTA by a
+// direct J-bin DFT of the first window and carried from block to block in float64; inside a block the prefix of the
+// increments is thread-serial float32 with float64 warp / CTA carries, rounded to float32 once.
+// Offsets whose E is below 1e-7 of the largest E seen so far in the CTA's range (this block included) give 0: there the
+// float32 FFT's rounding residue of |Y|^2 would be divided by a rounding residue of E (the reference's eps clamp gives 0
+// on exact silence).
+constexpr int ZQF_THREADS = ZNT;
+struct ZcFreqFftParams {
+    const float2 *x;
+    int64_t n, n_off, mstride;
+    int N, cp, nbins, blocks_per_cap, blocks_per_item, items_per_cap;
+    int64_t n_items;
+    const int *bins;
+    const double2 *tw;
+    const float2 *tw8, *GpY, *GpS;
+    float2 *stash;             // [gridDim.x][8192]
+    float templ_energy;
+    float *metric;
+};
+
+__device__ double zqf_anchor(const float2 *xl, int64_t avail, int N, const int *bins, int nbins, const double2 *tw, float2 *red, double *dred)
+{
+    const int tid = threadIdx.x, j = tid & 63, part = tid >> 6;
+    const int chunk = (N + 3) >> 2, m0 = part * chunk, m1 = m0 + chunk < N ? m0 + chunk : N;
+    float2 acc = make_float2(0.f, 0.f);
+    if (j < nbins) {
+        int k = bins[j] % N;
+        if (k < 0) k += N;
+        const bool tab = (ZF % N) == 0;
+        const int mulf = tab ? ZF / N : 0;
+        int ph = (int)(((long long)k * m0) % N);
+        for (int m = m0; m < m1; ++m) {
+            const float2 v = m < avail ? __ldg(xl + m) : make_float2(0.f, 0.f);
+            float2 w;
+            if (tab) w = tw4096<float2>(tw, ph * mulf);                       // e^{-2 pi i ph / N}
+            else { float sn, cs; sincospif(-2.0f * (float)ph / (float)N, &sn, &cs); w = make_float2(cs, sn); }
+            acc.x = fmaf(v.x, w.x, fmaf(-v.y, w.y, acc.x));
+            acc.y = fmaf(v.x, w.y, fmaf(v.y, w.x, acc.y));
+            ph += k;
+            if (ph >= N) ph -= N;
+        }
+    }
+    red[tid] = acc;
+    __syncthreads();
+    if (tid < 64) {
+        const float2 a0 = red[tid], a1 = red[tid + 64], a2 = red[tid + 128], a3 = red[tid + 192];
+        const double sx = (double)a0.x + a1.x + a2.x + a3.x, sy = (double)a0.y + a1.y + a2.y + a3.y;
+        double e = sx * sx + sy * sy;
+        for (int o = 16; o > 0; o >>= 1) e += shfl_xor_f64(e, o);
+        if ((tid & 31) == 0) dred[tid >> 5] = e;
     }
     __syncthreads();
-    ifft8k_dit<float2>(a, tw, w0);
-    const float inv = 1.0f / (float)ZF8, rn = (float)(1.0 / *ref_norm_p);
-#pragma unroll 4
-    for (int q = 0; q < ZF8 / ZNT; ++q) {
-        const int i = tid + ZNT * q;
-        const int64_t k = k0 + i;
-        if (i >= V || k >= out_len) break;
-        const float2 y = a[zpad8(nr - 1 + i)];        // output k0 + i is the window of local samples [i, i + nr - 1]
-        float sc = inv;
-        if (mode != 2) {
-            const float e = se[spad(i + nr)] - se[spad(i)];
-            sc *= rn * (mode == 1 ? rsqrtf(fmaxf(e, 1e-12f))              // zc_v2.py:257-271
-                                  : rsqrtf(fmaxf(e, 0.f) + 1e-12f));     // zc.py:125-126
-        }
-        const float yr = y.x * sc, yi = y.y * sc;
-        const int64_t o = frame * out_stride + k;
-        if (corr_out) corr_out[o] = make_float2(yr, yi);
-        if (mag_out) mag_out[o] = sqrtf(fmaf(yr, yr, yi * yi));
+    const double r = dred[0] + dred[1];
+    __syncthreads();
+    return r;
+}
+
+// one 8192-sample block: offsets o0 .. o0 + V - 1 of capture row xc; returns E at the first offset of the next block.
+// Kept out of line: the block loop's own state (item, capture, carries) then lives across ONE call instead of competing with
+// the 100+ registers each FFT stage wants.
+__device__ __noinline__ double zqf_block(const ZcFreqFftParams &p, float2 *a, float *se, double *wtot, float *wmax, double *dred,
+                                        const float2 *xc, float *mrow, int b, double Eb, float *emax_io)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = p.N, V = ZF8 - N + 1;
+    const float2 w0 = __ldg(p.tw8 + tid);
+    const int64_t o0 = (int64_t)b * V;                    // first offset of the block; local sample m = x[cp + o0 + m]
+    const float2 *xl = xc + p.cp + o0;
+    const int64_t availl = p.n - p.cp - o0;
+    const unsigned m_cnt = (unsigned)(availl < ZF8 ? availl : ZF8);
+    const int64_t left = p.n_off - o0;
+    const unsigned o_cnt = (unsigned)(left < V ? left : V);
+    constexpr int IPT = ZF8 / ZNT;
+    const int s0 = tid * IPT + 1;
+    auto ldx = [&](int m) { return (unsigned)m < m_cnt ? __ldg(xl + m) : make_float2(0.f, 0.f); };
+    conv8k_stage_a(a, p.tw, w0, ldx, [](int, float) {});
+    __syncthreads();
+    conv8k_stage_b(a, p.tw);
+    __syncthreads();
+    conv8k_stage_c<true>(a, p.GpS, p.GpY, p.stash + (size_t)blockIdx.x * ZF8);          // S back to shared memory, Y to the stash
+    __syncthreads();
+    conv8k_stage_d(a, p.tw);
+    __syncthreads();
+    // S(o) -> increment of E: se[spad(i + 1)] = E(o0 + i + 1) - E(o0 + i)
+    {
+        const float Jf = (float)p.nbins;
+        conv8k_stage_e(a, p.tw, w0, [&](int m, float2 S, int slot) {
+            if ((slot & 3) == 0) asm volatile("" ::: "memory");      // at most 8 sample loads in flight: 64 hoisted loads spill
+            const int i = m - (N - 1);
+            if ((unsigned)i >= (unsigned)V) return;
+            float dl = 0.f;
+            if ((unsigned)i < o_cnt) {
+                const float2 hi = (int64_t)(i + N) < availl ? __ldg(xl + i + N) : make_float2(0.f, 0.f), lo = ldx(i);   // i + N may be sample 8192: past the block, inside the capture
+                const float dx = hi.x - lo.x, dy = hi.y - lo.y;
+                dl = fmaf(2.f, fmaf(S.x, dx, S.y * dy), Jf * fmaf(dx, dx, dy * dy));
+            }
+            se[spad(i + 1)] = dl;
+        });
     }
+    __syncthreads();
+    // inclusive prefix: thread-serial float32 over 32 contiguous increments, float64 warp / CTA / block-to-block carries
+    float run = 0.f;
+#pragma unroll
+    for (int m = 0; m < IPT; ++m) { run += se[spad(s0 + m)]; se[spad(s0 + m)] = run; }
+    double t = (double)run;
+    for (int o = 1; o < 32; o <<= 1) { const double y = shfl_up_f64(t, o); if (lane >= o) t += y; }
+    if (lane == 31) wtot[warp] = t;
+    __syncthreads();
+    double off = Eb + (t - (double)run), tot = 0.0;
+    for (int w = 0; w < ZNT / 32; ++w) { if (w < warp) off += wtot[w]; tot += wtot[w]; }
+    // E itself into se (rounded to float32 once), and the block's largest / smallest E with the position of the largest
+    float mx = tid == 0 ? (float)Eb : -1.f, mn = tid == 0 ? (float)Eb : 3.0e38f;
+    int ix = 0;
+#pragma unroll
+    for (int m = 0; m < IPT; ++m) {
+        const float e = (float)((double)se[spad(s0 + m)] + off);
+        se[spad(s0 + m)] = s0 + m <= V ? e : 0.f;                  // the tail beyond the block's V offsets stays zero: it is summed again
+        if (s0 + m <= (int)o_cnt) {
+            if (e > mx) { mx = e; ix = s0 + m; }
+            mn = fminf(mn, e);
+        }
+    }
+    if (tid == 0) se[0] = (float)Eb;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float omx = __shfl_xor_sync(0xffffffffu, mx, o), omn = __shfl_xor_sync(0xffffffffu, mn, o);
+        const int oix = __shfl_xor_sync(0xffffffffu, ix, o);
+        if (omx > mx || (omx == mx && oix < ix)) { mx = omx; ix = oix; }
+        mn = fminf(mn, omn);
+    }
+    if (lane == 0) { wmax[warp] = mx; wmax[ZNT / 32 + warp] = mn; reinterpret_cast<int *>(wmax)[2 * (ZNT / 32) + warp] = ix; }
+    __syncthreads();
+    float emax = *emax_io;
+#pragma unroll
+    for (int w = 0; w < ZNT / 32; ++w) {
+        const float v = wmax[w];
+        const int vi = reinterpret_cast<const int *>(wmax)[2 * (ZNT / 32) + w];
+        if (w == 0 || v > mx || (v == mx && vi < ix)) { mx = v; ix = vi; }
+        mn = w == 0 ? wmax[ZNT / 32] : fminf(mn, wmax[ZNT / 32 + w]);
+    }
+    emax = fmaxf(emax, mx);
+    *emax_io = emax;
+    // A block whose E spans more than ~27 dB (a burst entering and leaving the window, or silence): the float32 FFT's error in
+    // S, multiplied by the burst-sized d, has accumulated ~3e-8 of the LARGEST E in the prefix -- too much for the small E
+    // that follows.  Anchor E at the block's end directly as well; the discrepancy D belongs to the offsets after the peak of
+    // E (it was gathered while the burst crossed the window, where E itself is huge), and the exact value is what the next
+    // block starts from.
+    double Enext = Eb + tot;
+    float Df = 0.f;
+    if (mn < 2e-3f * mx) {                                         // block-uniform
+        const double Ed = zqf_anchor(xl + o_cnt, availl - (int64_t)o_cnt, N, p.bins, p.nbins, p.tw, a, dred);
+        Df = (float)(Enext - Ed);
+        Enext = Ed;
+    }
+    conv8k_unstash(a, p.stash + (size_t)blockIdx.x * ZF8);
+    __syncthreads();
+    conv8k_stage_d(a, p.tw);
+    __syncthreads();
+    {
+        const float floor_e = 1e-7f * emax, te = p.templ_energy;
+        float *mo = mrow + o0 - (N - 1);
+        conv8k_stage_e(a, p.tw, w0, [&](int m, float2 Y, int) {
+            const int i = m - (N - 1);
+            if ((unsigned)i >= o_cnt) return;
+            const float e = se[spad(i)] - (i > ix ? Df : 0.f);
+            const float den = fmaxf(te * e, 1e-12f);                              // zc_freq.py:96
+            mo[m] = (e > floor_e && e > 0.f) ? __fdividef(fmaf(Y.x, Y.x, Y.y * Y.y), den) : 0.f;
+        });
+    }
+    __syncthreads();
+    return Enext;
+}
+
+__global__ void __launch_bounds__(ZQF_THREADS, 2) zc_freq_fft_kernel(const __grid_constant__ ZcFreqFftParams p)
+{
+    extern __shared__ __align__(16) unsigned char zsm[];
+    float2 *a = reinterpret_cast<float2 *>(zsm);                                   // ZFP8
+    float *se = reinterpret_cast<float *>(zsm + (size_t)ZFP8 * sizeof(float2));     // se[spad(i)] = E(first offset of the block + i)
+    __shared__ double wtot[ZNT / 32];
+    __shared__ float wmax[3 * (ZNT / 32)];            // per warp: max E, min E, position of the max
+    __shared__ double dred[2];
+    const int tid = threadIdx.x;
+    const int V = ZF8 - p.N + 1;
+    for (int i = tid; i < ZF8 + ZF8 / 32 + 8; i += ZNT) se[i] = 0.f;
+    for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int64_t cap = item / p.items_per_cap;
+        const int b0 = (int)(item % p.items_per_cap) * p.blocks_per_item;
+        const int b1 = b0 + p.blocks_per_item < p.blocks_per_cap ? b0 + p.blocks_per_item : p.blocks_per_cap;
+        const float2 *xc = p.x + cap * p.n;
+        __syncthreads();
+        // E at the item's first offset, directly (a is free here: its first 2 KB serve as the reduction buffer)
+        double Eb = zqf_anchor(xc + p.cp + (int64_t)b0 * V, p.n - p.cp - (int64_t)b0 * V, p.N, p.bins, p.nbins, p.tw, a, dred);
+        float emax = (float)Eb;
+        for (int b = b0; b < b1; ++b) Eb = zqf_block(p, a, se, wtot, wmax, dred, xc, p.metric + cap * p.mstride, b, Eb, &emax);
+    }
+}
+
+// ref[m] = sum_j T_j e^{+2 pi i k_j m / N} (T_j = 1 without a template): the time-domain sequence whose matched filter
+// (conj, reversed -- zc_spectrum8k_kernel) is h_Y / h_S above
+__global__ void zqf_ref_kernel(const int *bins, const float2 *templ, int nbins, int N, double2 *ref)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= N) return;
+    double sr = 0.0, si = 0.0;
+    for (int j = 0; j < nbins; ++j) {
+        int k = bins[j] % N;
+        if (k < 0) k += N;
+        double sn, cs;
+        sincospi(2.0 * (double)(((long long)k * m) % N) / (double)N, &sn, &cs);
+        const double tr = templ ? (double)templ[j].x : 1.0, ti = templ ? (double)templ[j].y : 0.0;
+        sr += tr * cs - ti * sn;
+        si += tr * sn + ti * cs;
+    }
+    ref[m] = make_double2(sr, si);
 }
 
 // ---- zc_v2.normalize_correlation (zc_v2.py:257-271) on a correlation the CALLER supplies ---------------------
@@ -585,4 +821,65 @@ OFS_API int ofs_zc_freq_metric(const void *x, int32_t in_dtype, int64_t n_frames
     else { set_error("ofs_zc_freq_metric: unknown dtype"); return OFS_EINVAL; }
 #undef OFS_ZQ_LAUNCH
     return check_launch("zc_freq_kernel");
+}
+
+OFS_API int ofs_zc_freq_metric_fft(const void *x_c64, int64_t n_frames, int64_t n, int32_t n_fft, int32_t cp, const int32_t *bins,
+                                   const void *templ_c64, int32_t nbins, double templ_energy, float *metric, int64_t out_stride,
+                                   void *stream_)
+{
+    OFS_TRACE();
+    OFS_REQUIRE(x_c64 && bins && templ_c64 && metric && templ_energy > 0.0, "ofs_zc_freq_metric_fft: bad arguments");
+    OFS_REQUIRE(n_fft >= 2 && n_fft <= 2048 && cp >= 0, "ofs_zc_freq_metric_fft: n_fft must be 2..2048");
+    OFS_REQUIRE(nbins >= 1 && nbins <= 64, "ofs_zc_freq_metric_fft: nbins <= 64");
+    const int64_t n_off = n - ((int64_t)n_fft + cp) + 1;
+    OFS_REQUIRE(n_off > 0, "Received stream is shorter than a single OFDM symbol.");   /* zc_freq.py:76-78 */
+    OFS_REQUIRE(out_stride >= n_off && n_frames >= 0, "ofs_zc_freq_metric_fft: out_stride < number of offsets");
+    if (n_frames == 0) return OFS_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    keep_pool_cached();
+    const int V = ZF8 - n_fft + 1;
+    ZcFreqFftParams p{};
+    p.blocks_per_cap = (int)((n_off + V - 1) / V);
+    // consecutive blocks of a capture share one CTA (one anchor, float64 carry of E); captures are split only when there are
+    // too few of them to fill the machine.  OFS_ZQF_BLOCKS_PER_ITEM overrides (tests exercise both the carry and the anchor).
+    const int slots = 2 * sm_count();
+    int64_t bpi = n_frames * p.blocks_per_cap / (4LL * slots);
+    if (const char *e = getenv("OFS_ZQF_BLOCKS_PER_ITEM")) bpi = atoll(e);
+    if (bpi < 1) bpi = 1;
+    if (bpi > p.blocks_per_cap) bpi = p.blocks_per_cap;
+    p.blocks_per_item = (int)bpi;
+    p.items_per_cap = (p.blocks_per_cap + p.blocks_per_item - 1) / p.blocks_per_item;
+    p.n_items = n_frames * p.items_per_cap;
+    const int grid = (int)(p.n_items < slots ? p.n_items : slots);
+    double2 *tw = nullptr, *tw8d = nullptr, *ref = nullptr;
+    float2 *tw8f = nullptr, *Gp = nullptr, *stash = nullptr;
+    double *rn = nullptr;
+    OFS_CUDA(cudaMallocAsync((void **)&tw, (ZF / 2) * (sizeof(double2) + sizeof(float2)), stream));
+    OFS_CUDA(cudaMallocAsync((void **)&tw8d, 256 * sizeof(double2), stream));
+    OFS_CUDA(cudaMallocAsync((void **)&tw8f, 256 * sizeof(float2), stream));
+    OFS_CUDA(cudaMallocAsync((void **)&ref, 2 * (size_t)n_fft * sizeof(double2), stream));
+    OFS_CUDA(cudaMallocAsync((void **)&Gp, 2 * ZF8 * sizeof(float2), stream));
+    OFS_CUDA(cudaMallocAsync((void **)&rn, 2 * sizeof(double), stream));
+    OFS_CUDA(cudaMallocAsync((void **)&stash, (size_t)grid * ZF8 * sizeof(float2), stream));
+    zc_twiddle_kernel<<<(ZF / 2 + 255) / 256, 256, 0, stream>>>(tw);
+    zc_twiddle8_kernel<<<1, 256, 0, stream>>>(tw8f, tw8d);
+    zqf_ref_kernel<<<(n_fft + 127) / 128, 128, 0, stream>>>(bins, reinterpret_cast<const float2 *>(templ_c64), nbins, n_fft, ref);
+    zqf_ref_kernel<<<(n_fft + 127) / 128, 128, 0, stream>>>(bins, nullptr, nbins, n_fft, ref + n_fft);
+    if (int rc = check_launch("zqf_ref_kernel")) return rc;
+    OFS_CUDA(cudaFuncSetAttribute(zc_spectrum8k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ZFP8 * sizeof(double2))));
+    zc_spectrum8k_kernel<<<1, ZNT, ZFP8 * sizeof(double2), stream>>>(ref, n_fft, tw, tw8d, Gp, rn);
+    zc_spectrum8k_kernel<<<1, ZNT, ZFP8 * sizeof(double2), stream>>>(ref + n_fft, n_fft, tw, tw8d, Gp + ZF8, rn + 1);
+    if (int rc = check_launch("zc_spectrum8k_kernel")) return rc;
+    count_launch(5);
+    p.x = reinterpret_cast<const float2 *>(x_c64); p.n = n; p.n_off = n_off; p.mstride = out_stride;
+    p.N = n_fft; p.cp = cp; p.nbins = nbins; p.bins = bins; p.tw = tw; p.tw8 = tw8f; p.GpY = Gp; p.GpS = Gp + ZF8; p.stash = stash;
+    p.templ_energy = (float)templ_energy; p.metric = metric;
+    const size_t smem = (size_t)ZFP8 * sizeof(float2) + (size_t)(ZF8 + ZF8 / 32 + 8) * sizeof(float);
+    OFS_CUDA(cudaFuncSetAttribute(zc_freq_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    zc_freq_fft_kernel<<<grid, ZQF_THREADS, smem, stream>>>(p);
+    if (int rc = check_launch("zc_freq_fft_kernel")) return rc;
+    OFS_CUDA(cudaFreeAsync(tw, stream)); OFS_CUDA(cudaFreeAsync(tw8d, stream)); OFS_CUDA(cudaFreeAsync(tw8f, stream));
+    OFS_CUDA(cudaFreeAsync(ref, stream)); OFS_CUDA(cudaFreeAsync(Gp, stream)); OFS_CUDA(cudaFreeAsync(rn, stream));
+    OFS_CUDA(cudaFreeAsync(stash, stream));
+    return OFS_OK;
 }

@@ -134,3 +134,71 @@ def test_zc_freq_f32_on_reference_fixture(golden):
         mo = orc.compute_frequency_metric(x.astype(np.complex128), g["bin_indices"], g["template"], float(g["template_energy"]))
         assert np.abs(m - mo).max() <= 1e-4 * mo.max()
         assert int(np.argmax(m)) == int(np.argmax(mo))
+
+
+@pytest.mark.parametrize("bpi", [None, "1", "64"])
+@pytest.mark.parametrize("n", [4000, 20000, 65536])
+def test_zc_freq_fft_form_vs_oracle(n, bpi, monkeypatch):
+    """compute_frequency_metric (zc_freq.py:62-99) in FFT form (ofs_zc_freq_metric_fft): float32 metric within 1e-4 of the float64
+    oracle's maximum on noisy captures with PSS symbols, exact silence and a loud burst -- with every block anchored on its own
+    (blocks per item = 1), with one anchor per capture and the float64 carry of E across all blocks (64), and the default split."""
+    from ofdm_sync_math_b200 import engine
+    from ofdm_sync_math_b200.zc import generate_zadoff_chu
+    if bpi is None:
+        monkeypatch.delenv("OFS_ZQF_BLOCKS_PER_ITEM", raising=False)
+    else:
+        monkeypatch.setenv("OFS_ZQF_BLOCKS_PER_ITEM", bpi)
+    half = 31
+    bi = np.concatenate((np.arange(-half, 0), np.arange(1, half + 1)))
+    tb = generate_zadoff_chu(25, 62)
+    x = np.stack([_pss_capture(n, 300 + s, snr_db=[0.0, 10.0, 25.0][s % 3], n_pss=2 if n > 8000 else 1) for s in range(3)]) \
+        if n > 8000 else np.stack([_pss_capture(8000, 300 + s)[:n] for s in range(3)])
+    x[1, n // 2:n // 2 + 300] *= 40.0            # a loud burst: E must come back down by cancellation
+    x[2, : n // 4] = 0                           # exact silence: E = 0, the FFT's rounding residue must not show
+    m = engine.zc_freq_metric(torch.as_tensor(x).cuda()[:, None], bi, tb, 62.0, fast="fft").cpu().numpy()
+    for f in range(x.shape[0]):
+        mo = orc.compute_frequency_metric(x[f].astype(np.complex128), bi, tb, 62.0)
+        assert m[f].shape == mo.shape
+        err = np.abs(m[f] - mo).max()
+        assert err <= 1e-4 * mo.max(), (f, err / mo.max(), int(np.argmax(np.abs(m[f] - mo))))
+        assert int(np.argmax(m[f])) == int(np.argmax(mo))
+
+
+def test_zc_freq_fft_form_on_reference_fixture(golden):
+    from ofdm_sync_math_b200 import engine
+    for tag in ("cir1", "awgn"):
+        g = golden(f"zc_freq_{tag}")
+        rx = np.asarray(g["rx"])
+        rx = rx[0] if rx.ndim == 2 else rx          # the fast kernels take one branch
+        x = rx.astype(np.complex64)
+        m = engine.zc_freq_metric(torch.as_tensor(x).cuda()[None, None], g["bin_indices"], g["template"], float(g["template_energy"]),
+                                  fast="fft").cpu().numpy()[0]
+        mo = orc.compute_frequency_metric(x.astype(np.complex128), g["bin_indices"], g["template"], float(g["template_energy"]))
+        assert np.abs(m - mo).max() <= 1e-4 * mo.max()
+        assert int(np.argmax(m)) == int(np.argmax(mo))
+
+
+@pytest.mark.parametrize("n_fft,cp,nb", [(2048, 512, 62), (1024, 72, 40), (512, 0, 12), (1536, 100, 62)])
+def test_zc_freq_fft_form_other_geometries(n_fft, cp, nb):
+    """Other FFT sizes (power of two: table twiddles in the anchor; 1536: sincospi), prefix lengths and bin counts."""
+    from ofdm_sync_math_b200 import engine
+    rng = np.random.default_rng(n_fft + nb)
+    n = 30000
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    bi = np.concatenate((np.arange(-(nb // 2), 0), np.arange(1, nb // 2 + 1)))
+    tb = np.exp(2j * np.pi * rng.random(nb))
+    # a preamble made of exactly these bins
+    spec = np.zeros(n_fft, complex); spec[bi % n_fft] = tb
+    x[7000:7000 + n_fft] += (8.0 * np.fft.ifft(spec) * np.sqrt(n_fft)).astype(np.complex64)
+    m = engine.zc_freq_metric(torch.as_tensor(x).cuda()[None, None], bi, tb, float(nb), n_fft=n_fft, cp=cp, fast="fft").cpu().numpy()[0]
+    # oracle for general geometry: direct sliding DFT in float64
+    n_off = n - (n_fft + cp) + 1
+    xd = x.astype(np.complex128)
+    k = bi % n_fft
+    W = np.exp(-2j * np.pi * np.outer(k, np.arange(n_fft)) / n_fft)
+    offs = np.unique(np.concatenate((np.arange(0, n_off, 97), np.arange(7000 - cp - 20, 7000 - cp + 20), [n_off - 1])))
+    for o in offs:
+        bins = W @ xd[o + cp:o + cp + n_fft]
+        ref = abs(np.vdot(tb, bins)) ** 2 / max(float(nb) * np.sum(np.abs(bins) ** 2), 1e-12)
+        assert abs(m[o] - ref) <= 1e-4, (o, m[o], ref)
+    assert int(np.argmax(m)) == 7000 - cp

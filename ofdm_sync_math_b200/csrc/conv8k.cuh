@@ -80,12 +80,21 @@ template <bool INV> __device__ __forceinline__ void dft16(float2 (&v)[16])
 // strides are the short ones, 30 L1 wavefronts per warp), the rest by one to three multiplications.  All 15 from the table is
 // the most accurate but costs 240 scattered wavefronts per pass (measured: matched filter 1.49 -> 1.88 ms); all from w1 by
 // squaring (depth 4) doubles the transform's rounding error, which the FFT-form zc_freq kernel multiplies by burst-sized samples.
-__device__ __forceinline__ void powers(const double2 *tw, int base, float2 (&w)[16])
+// The four table loads are a separate step so that a kernel can issue them BEFORE the barrier that precedes the stage: right
+// after a barrier every warp of the CTA would wait for them at once.
+struct Seeds { float2 w1, w2, w4, w8; };
+__device__ __forceinline__ Seeds seeds(const double2 *tw, int base)
 {
-    w[1] = tw4096<float2>(tw, base);
-    w[2] = tw4096<float2>(tw, 2 * base);
-    w[4] = tw4096<float2>(tw, 4 * base);
-    w[8] = tw4096<float2>(tw, 8 * base);
+    Seeds s;
+    s.w1 = tw4096<float2>(tw, base);
+    s.w2 = tw4096<float2>(tw, 2 * base);
+    s.w4 = tw4096<float2>(tw, 4 * base);
+    s.w8 = tw4096<float2>(tw, 8 * base);
+    return s;
+}
+__device__ __forceinline__ void powers(const Seeds &s, float2 (&w)[16])
+{
+    w[1] = s.w1; w[2] = s.w2; w[4] = s.w4; w[8] = s.w8;
     w[3] = mul(w[2], w[1]);
     w[5] = mul(w[4], w[1]); w[6] = mul(w[4], w[2]); w[7] = mul(w[4], w[3]);
 #pragma unroll
@@ -105,7 +114,7 @@ __device__ __forceinline__ float2 conv8k_w32(int q)      // exp(-2 pi i q / 32),
 // Stage A.  ld(m) returns local sample m of the block (0 <= m < 8192, zero outside the capture); en(m, |x|^2) receives
 // every sample's energy (for the sliding-energy normalisation) -- pass a no-op when it is not needed.
 template <class Load, class Energy>
-__device__ __forceinline__ void conv8k_stage_a(float2 *a, const double2 *tw, float2 w0, Load ld, Energy en)
+__device__ __forceinline__ void conv8k_stage_a(float2 *a, const pk::Seeds &sd, float2 w0, Load ld, Energy en)
 {
     const int t = threadIdx.x;
     float2 y0[16], y1[16];
@@ -121,7 +130,7 @@ __device__ __forceinline__ void conv8k_stage_a(float2 *a, const double2 *tw, flo
         y1[q] = d;
     }
     float2 w[16];
-    pk::powers(tw, t, w);
+    pk::powers(sd, w);
     pk::dft16<false>(y0);
 #pragma unroll
     for (int q = 0; q < 16; ++q) a[zpad(q * 256 + t)] = q ? pk::mul(y0[q], w[q]) : y0[0];
@@ -131,11 +140,11 @@ __device__ __forceinline__ void conv8k_stage_a(float2 *a, const double2 *tw, flo
 }
 
 // Stage B: second forward pass of both halves (inside each block of 256: stride 16, twiddle W256^(n0 k1))
-__device__ __forceinline__ void conv8k_stage_b(float2 *a, const double2 *tw)
+__device__ __forceinline__ void conv8k_stage_b(float2 *a, const pk::Seeds &sd)
 {
     const int t = threadIdx.x, k0 = t >> 4, n0 = t & 15;
     float2 w[16];
-    pk::powers(tw, 16 * n0, w);
+    pk::powers(sd, w);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         float2 *ah = a + h * ZFP + zpad(k0 * 256 + n0);         // + q * 17: zpad(k0 * 256 + q * 16 + n0), n0 < 16
@@ -191,22 +200,35 @@ __device__ __forceinline__ void conv8k_stage_c(float2 *a, const float2 *Gp, cons
         for (int q = 0; q < 16; ++q) ah[q] = v[q];
     }
 }
-// the stashed second product back into shared memory (same thread, same positions as stage C's own store)
-__device__ __forceinline__ void conv8k_unstash(float2 *a, const float2 *stash)
+// the stashed second product back into shared memory (same thread, same positions as stage C's own store), in two steps so
+// that the L2 round trip can hide behind other work: fetch into registers, ... , put into shared memory
+__device__ __forceinline__ void conv8k_unstash_fetch(const float2 *stash, float2 (&r)[32])
+{
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] = __ldcg(stash + i * 256 + t);
+}
+__device__ __forceinline__ void conv8k_unstash_put(float2 *a, const float2 (&r)[32])
 {
     const int t = threadIdx.x;
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int q = 0; q < 16; ++q) a[h * ZFP + t * 17 + q] = stash[(h * 16 + q) * 256 + t];
+        for (int q = 0; q < 16; ++q) a[h * ZFP + t * 17 + q] = r[h * 16 + q];
+}
+__device__ __forceinline__ void conv8k_unstash(float2 *a, const float2 *stash)
+{
+    float2 r[32];
+    conv8k_unstash_fetch(stash, r);
+    conv8k_unstash_put(a, r);
 }
 
 // Stage D: second inverse pass of both halves
-__device__ __forceinline__ void conv8k_stage_d(float2 *a, const double2 *tw)
+__device__ __forceinline__ void conv8k_stage_d(float2 *a, const pk::Seeds &sd)
 {
     const int t = threadIdx.x, k0 = t >> 4, n0 = t & 15;
     float2 w[16];
-    pk::powers(tw, 16 * n0, w);
+    pk::powers(sd, w);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         float2 *ah = a + h * ZFP + zpad(k0 * 256 + n0);
@@ -219,17 +241,28 @@ __device__ __forceinline__ void conv8k_stage_d(float2 *a, const double2 *tw)
     }
 }
 
-// Stage E: last inverse pass + inverse radix-2 stage; sink(m, y, slot) receives local output sample m (0 <= m < 8192) of the
+// seeds of stages A / E (base = thread index) and B / D (base = 16 (t & 15))
+__device__ __forceinline__ pk::Seeds conv8k_seeds_ae(const double2 *tw) { return pk::seeds(tw, threadIdx.x); }
+__device__ __forceinline__ pk::Seeds conv8k_seeds_bd(const double2 *tw) { return pk::seeds(tw, 16 * (threadIdx.x & 15)); }
+
+// Stage E: last inverse pass + inverse radix-2 stage; sink(m, y, pre_m) receives local output sample m (0 <= m < 8192) of the
 // circular convolution, already scaled (the 1/8192 sits in the spectrum).  Call order per thread: m = t + 256 q, then
-// m + 4096, q ascending -- consecutive threads hold consecutive m; slot = 0..31 is the compile-time call number.
-template <class Sink>
-__device__ __forceinline__ void conv8k_stage_e(const float2 *a, const double2 *tw, float2 w0, Sink sink)
+// m + 4096, q ascending -- consecutive threads hold consecutive m.  pre(m) is called 8 outputs ahead of sink(m, ., .) and its
+// result handed to that sink call: side data a sink needs from global memory (the FFT-form zc_freq kernel's samples) is in
+// flight while the previous outputs are processed.  conv8k_no_pre for sinks that need none.
+struct conv8k_no_pre { __device__ __forceinline__ int operator()(int) const { return 0; } };
+template <class Pre, class Sink>
+__device__ __forceinline__ void conv8k_stage_e(const float2 *a, const pk::Seeds &sd, float2 w0, Pre pre, Sink sink)
 {
     const int t = threadIdx.x;
+    auto m_of = [&](int slot) { return t + 256 * (slot >> 1) + (slot & 1) * ZF; };
+    decltype(pre(0)) ring[8];
+#pragma unroll
+    for (int sl = 0; sl < 8; ++sl) ring[sl] = pre(m_of(sl));
     float2 e[16], o[16];
     {
         float2 w[16];
-        pk::powers(tw, t, w);
+        pk::powers(sd, w);
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             e[q] = a[zpad(q * 256 + t)];
@@ -243,8 +276,12 @@ __device__ __forceinline__ void conv8k_stage_e(const float2 *a, const double2 *t
     for (int q = 0; q < 16; ++q) {
         float2 v = pk::mulc(o[q], w0);
         if (q != 0) { const float2 k = conv8k_w32(q); v = pk::mulk(v, k.x, -k.y); }
-        sink(t + 256 * q, pk::add(e[q], v), 2 * q);
-        sink(t + 256 * q + ZF, pk::sub(e[q], v), 2 * q + 1);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int slot = 2 * q + hf;
+            sink(m_of(slot), hf ? pk::sub(e[q], v) : pk::add(e[q], v), ring[slot & 7]);
+            if (slot + 8 < 32) ring[slot & 7] = pre(m_of(slot + 8));
+        }
     }
 }
 

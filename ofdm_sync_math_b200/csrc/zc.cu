@@ -247,13 +247,15 @@ __global__ void __launch_bounds__(ZNT, 2) zc_mf8k_kernel(const void *x, int64_t 
     const int m_hi = n - jb < ZF8 ? (int)(n - jb) : ZF8;
     const unsigned m_cnt = m_hi > m_lo ? (unsigned)(m_hi - m_lo) : 0u;
     const In *xl = xb + jb;
-    conv8k_stage_a(a, tw, w0,
+    const pk::Seeds s_ae = conv8k_seeds_ae(tw);
+    conv8k_stage_a(a, s_ae, w0,
                    [&](int m) {
                        float2 v = make_float2(0.f, 0.f);
                        if ((unsigned)(m - m_lo) < m_cnt) { const In s = xl[m]; v = make_float2((float)s.x, (float)s.y); }
                        return v;
                    },
                    [&](int m, float e) { if (norm) se[spad(m + 1)] = e; });
+    const pk::Seeds s_bd = conv8k_seeds_bd(tw);           // for stages B and D, fetched ahead of the barrier
     if (tid == 0) se[0] = 0.f;
     __syncthreads();
     // inclusive prefix of the 8192 energies: 32 contiguous values per thread (stride 33 after padding: conflict-free),
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(ZNT, 2) zc_mf8k_kernel(const void *x, int64_t 
         if (lane == 31) wtot[warp] = t;
         woff = t - (double)run;
     }
-    conv8k_stage_b(a, tw);
+    conv8k_stage_b(a, s_bd);
     __syncthreads();
     if (norm) {
         for (int w = 0; w < warp; ++w) woff += wtot[w];
@@ -279,7 +281,8 @@ __global__ void __launch_bounds__(ZNT, 2) zc_mf8k_kernel(const void *x, int64_t 
     }
     conv8k_stage_c<false>(a, Gp, nullptr, nullptr);
     __syncthreads();
-    conv8k_stage_d(a, tw);
+    conv8k_stage_d(a, s_bd);
+    const pk::Seeds s_e = conv8k_seeds_ae(tw);
     __syncthreads();
     const float rn = (float)(1.0 / *ref_norm_p);
     // local outputs m in [nr - 1, o_hi) are this block's: output k0 + i, i = m - (nr - 1), is the window of local samples [i, i + nr - 1]
@@ -287,7 +290,7 @@ __global__ void __launch_bounds__(ZNT, 2) zc_mf8k_kernel(const void *x, int64_t 
     const unsigned o_cnt = (unsigned)(left < V ? left : V);
     float2 *co = corr_out ? corr_out + frame * out_stride + k0 - (nr - 1) : nullptr;
     float *mo = mag_out ? mag_out + frame * out_stride + k0 - (nr - 1) : nullptr;
-    conv8k_stage_e(a, tw, w0, [&](int m, float2 y, int) {
+    conv8k_stage_e(a, s_e, w0, conv8k_no_pre(), [&](int m, float2 y, int) {
         const int i = m - (nr - 1);
         if ((unsigned)i >= o_cnt) return;
         float sc = 1.f;
@@ -331,6 +334,10 @@ struct ZcFreqFftParams {
     float *metric;
 };
 
+// the block function is out of line (see there); it reads the launch parameters from this shared copy (one LDS, no registers
+// held across the FFT stages) -- through a reference to the kernel's parameter block every access was a generic global load
+__shared__ ZcFreqFftParams g_zqf;
+
 __device__ double zqf_anchor(const float2 *xl, int64_t avail, int N, const int *bins, int nbins, const double2 *tw, float2 *red, double *dred)
 {
     const int tid = threadIdx.x, j = tid & 63, part = tid >> 6;
@@ -341,16 +348,38 @@ __device__ double zqf_anchor(const float2 *xl, int64_t avail, int N, const int *
         if (k < 0) k += N;
         const bool tab = (ZF % N) == 0;
         const int mulf = tab ? ZF / N : 0;
-        int ph = (int)(((long long)k * m0) % N);
-        for (int m = m0; m < m1; ++m) {
-            const float2 v = m < avail ? __ldg(xl + m) : make_float2(0.f, 0.f);
-            float2 w;
-            if (tab) w = tw4096<float2>(tw, ph * mulf);                       // e^{-2 pi i ph / N}
-            else { float sn, cs; sincospif(-2.0f * (float)ph / (float)N, &sn, &cs); w = make_float2(cs, sn); }
-            acc.x = fmaf(v.x, w.x, fmaf(-v.y, w.y, acc.x));
-            acc.y = fmaf(v.x, w.y, fmaf(v.y, w.x, acc.y));
-            ph += k;
-            if (ph >= N) ph -= N;
+        auto phasor = [&](int ph) {                                           // e^{-2 pi i ph / N}, 0 <= ph < N
+            if (tab) return tw4096<float2>(tw, ph * mulf);
+            float sn, cs;
+            sincospif(-2.0f * (float)ph / (float)N, &sn, &cs);
+            return make_float2(cs, sn);
+        };
+        const float2 ws = phasor(k);
+        // the phasor advances by rotation and is re-seeded exactly every 32 samples (a table load per sample made this loop
+        // latency-bound: 35 % of the kernel's stall samples)
+        for (int mb = m0; mb < m1; mb += 32) {
+            float2 w = phasor((int)(((long long)k * mb) % N));
+            if (mb + 32 <= m1 && mb + 32 <= avail) {                          // whole group inside the window and the capture
+#pragma unroll 8
+                for (int u = 0; u < 32; u += 2) {
+                    const float2 v0 = __ldg(xl + mb + u), v1 = __ldg(xl + mb + u + 1);
+                    const float4 v = make_float4(v0.x, v0.y, v1.x, v1.y);
+                    acc = __ffma2_rn(make_float2(v.x, v.x), w, acc);
+                    acc = __ffma2_rn(make_float2(v.y, v.y), make_float2(-w.y, w.x), acc);
+                    w = pk::mul(w, ws);
+                    acc = __ffma2_rn(make_float2(v.z, v.z), w, acc);
+                    acc = __ffma2_rn(make_float2(v.w, v.w), make_float2(-w.y, w.x), acc);
+                    w = pk::mul(w, ws);
+                }
+            } else {
+                for (int u = 0; u < 32 && mb + u < m1; ++u) {
+                    const int m = mb + u;
+                    const float2 v = m < avail ? __ldg(xl + m) : make_float2(0.f, 0.f);
+                    acc.x = fmaf(v.x, w.x, fmaf(-v.y, w.y, acc.x));
+                    acc.y = fmaf(v.x, w.y, fmaf(v.y, w.x, acc.y));
+                    w = pk::mul(w, ws);
+                }
+            }
         }
     }
     red[tid] = acc;
@@ -371,9 +400,10 @@ __device__ double zqf_anchor(const float2 *xl, int64_t avail, int N, const int *
 // one 8192-sample block: offsets o0 .. o0 + V - 1 of capture row xc; returns E at the first offset of the next block.
 // Kept out of line: the block loop's own state (item, capture, carries) then lives across ONE call instead of competing with
 // the 100+ registers each FFT stage wants.
-__device__ __noinline__ double zqf_block(const ZcFreqFftParams &p, float2 *a, float *se, double *wtot, float *wmax, double *dred,
+__device__ __noinline__ double zqf_block(float2 *a, float *se, float2 *red, double *wtot, float *wmax, double *dred,
                                         const float2 *xc, float *mrow, int b, double Eb, float *emax_io)
 {
+    const ZcFreqFftParams &p = g_zqf;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = p.N, V = ZF8 - N + 1;
     const float2 w0 = __ldg(p.tw8 + tid);
@@ -386,31 +416,45 @@ __device__ __noinline__ double zqf_block(const ZcFreqFftParams &p, float2 *a, fl
     constexpr int IPT = ZF8 / ZNT;
     const int s0 = tid * IPT + 1;
     auto ldx = [&](int m) { return (unsigned)m < m_cnt ? __ldg(xl + m) : make_float2(0.f, 0.f); };
-    conv8k_stage_a(a, p.tw, w0, ldx, [](int, float) {});
+    // twiddle seeds are fetched ahead of the barrier that precedes their stage
+    pk::Seeds sd = conv8k_seeds_ae(p.tw);
+    conv8k_stage_a(a, sd, w0, ldx, [](int, float) {});
+    sd = conv8k_seeds_bd(p.tw);
     __syncthreads();
-    conv8k_stage_b(a, p.tw);
+    conv8k_stage_b(a, sd);
     __syncthreads();
     conv8k_stage_c<true>(a, p.GpS, p.GpY, p.stash + (size_t)blockIdx.x * ZF8);          // S back to shared memory, Y to the stash
+    sd = conv8k_seeds_bd(p.tw);
     __syncthreads();
-    conv8k_stage_d(a, p.tw);
+    conv8k_stage_d(a, sd);
+    sd = conv8k_seeds_ae(p.tw);
     __syncthreads();
     // S(o) -> increment of E: se[spad(i + 1)] = E(o0 + i + 1) - E(o0 + i)
     {
         const float Jf = (float)p.nbins;
-        conv8k_stage_e(a, p.tw, w0, [&](int m, float2 S, int slot) {
-            if ((slot & 3) == 0) asm volatile("" ::: "memory");      // at most 8 sample loads in flight: 64 hoisted loads spill
-            const int i = m - (N - 1);
-            if ((unsigned)i >= (unsigned)V) return;
-            float dl = 0.f;
-            if ((unsigned)i < o_cnt) {
-                const float2 hi = (int64_t)(i + N) < availl ? __ldg(xl + i + N) : make_float2(0.f, 0.f), lo = ldx(i);   // i + N may be sample 8192: past the block, inside the capture
-                const float dx = hi.x - lo.x, dy = hi.y - lo.y;
-                dl = fmaf(2.f, fmaf(S.x, dx, S.y * dy), Jf * fmaf(dx, dx, dy * dy));
-            }
-            se[spad(i + 1)] = dl;
-        });
+        struct DPair { float2 hi, lo; };
+        conv8k_stage_e(a, sd, w0,
+                       [&](int m) {                                 // d(o) = x[o+cp+N] - x[o+cp], fetched 8 outputs ahead
+                           const int i = m - (N - 1);
+                           DPair d;
+                           d.hi = d.lo = make_float2(0.f, 0.f);
+                           if ((unsigned)i < o_cnt) {
+                               if ((int64_t)(i + N) < availl) d.hi = __ldg(xl + i + N);      // i + N may be sample 8192: past the block, inside the capture
+                               d.lo = ldx(i);
+                           }
+                           return d;
+                       },
+                       [&](int m, float2 S, const DPair &d) {
+                           const int i = m - (N - 1);
+                           if ((unsigned)i >= (unsigned)V) return;
+                           const float dx = d.hi.x - d.lo.x, dy = d.hi.y - d.lo.y;
+                           se[spad(i + 1)] = (unsigned)i < o_cnt ? fmaf(2.f, fmaf(S.x, dx, S.y * dy), Jf * fmaf(dx, dx, dy * dy)) : 0.f;
+                       });
     }
     __syncthreads();
+    // the Y product comes back from the stash while the prefix sum runs (an L2 round trip: 14 % of the kernel when exposed)
+    float2 yst[32];
+    conv8k_unstash_fetch(p.stash + (size_t)blockIdx.x * ZF8, yst);
     // inclusive prefix: thread-serial float32 over 32 contiguous increments, float64 warp / CTA / block-to-block carries
     float run = 0.f;
 #pragma unroll
@@ -461,18 +505,20 @@ __device__ __noinline__ double zqf_block(const ZcFreqFftParams &p, float2 *a, fl
     double Enext = Eb + tot;
     float Df = 0.f;
     if (mn < 2e-3f * mx) {                                         // block-uniform
-        const double Ed = zqf_anchor(xl + o_cnt, availl - (int64_t)o_cnt, N, p.bins, p.nbins, p.tw, a, dred);
+        const double Ed = zqf_anchor(xl + o_cnt, availl - (int64_t)o_cnt, N, p.bins, p.nbins, p.tw, red, dred);
         Df = (float)(Enext - Ed);
         Enext = Ed;
     }
-    conv8k_unstash(a, p.stash + (size_t)blockIdx.x * ZF8);
+    conv8k_unstash_put(a, yst);
+    sd = conv8k_seeds_bd(p.tw);
     __syncthreads();
-    conv8k_stage_d(a, p.tw);
+    conv8k_stage_d(a, sd);
+    sd = conv8k_seeds_ae(p.tw);
     __syncthreads();
     {
         const float floor_e = 1e-7f * emax, te = p.templ_energy;
         float *mo = mrow + o0 - (N - 1);
-        conv8k_stage_e(a, p.tw, w0, [&](int m, float2 Y, int) {
+        conv8k_stage_e(a, sd, w0, conv8k_no_pre(), [&](int m, float2 Y, int) {
             const int i = m - (N - 1);
             if ((unsigned)i >= o_cnt) return;
             const float e = se[spad(i)] - (i > ix ? Df : 0.f);
@@ -489,22 +535,24 @@ __global__ void __launch_bounds__(ZQF_THREADS, 2) zc_freq_fft_kernel(const __gri
     extern __shared__ __align__(16) unsigned char zsm[];
     float2 *a = reinterpret_cast<float2 *>(zsm);                                   // ZFP8
     float *se = reinterpret_cast<float *>(zsm + (size_t)ZFP8 * sizeof(float2));     // se[spad(i)] = E(first offset of the block + i)
+    __shared__ float2 red[ZNT];                        // the anchor's partial sums
     __shared__ double wtot[ZNT / 32];
     __shared__ float wmax[3 * (ZNT / 32)];            // per warp: max E, min E, position of the max
     __shared__ double dred[2];
     const int tid = threadIdx.x;
     const int V = ZF8 - p.N + 1;
     for (int i = tid; i < ZF8 + ZF8 / 32 + 8; i += ZNT) se[i] = 0.f;
+    if (tid == 0) g_zqf = p;
     for (int64_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int64_t cap = item / p.items_per_cap;
         const int b0 = (int)(item % p.items_per_cap) * p.blocks_per_item;
         const int b1 = b0 + p.blocks_per_item < p.blocks_per_cap ? b0 + p.blocks_per_item : p.blocks_per_cap;
         const float2 *xc = p.x + cap * p.n;
         __syncthreads();
-        // E at the item's first offset, directly (a is free here: its first 2 KB serve as the reduction buffer)
-        double Eb = zqf_anchor(xc + p.cp + (int64_t)b0 * V, p.n - p.cp - (int64_t)b0 * V, p.N, p.bins, p.nbins, p.tw, a, dred);
+        // E at the item's first offset, directly
+        double Eb = zqf_anchor(xc + p.cp + (int64_t)b0 * V, p.n - p.cp - (int64_t)b0 * V, p.N, p.bins, p.nbins, p.tw, red, dred);
         float emax = (float)Eb;
-        for (int b = b0; b < b1; ++b) Eb = zqf_block(p, a, se, wtot, wmax, dred, xc, p.metric + cap * p.mstride, b, Eb, &emax);
+        for (int b = b0; b < b1; ++b) Eb = zqf_block(a, se, red, wtot, wmax, dred, xc, p.metric + cap * p.mstride, b, Eb, &emax);
     }
 }
 

@@ -83,13 +83,13 @@ int main()
     std::vector<float> en(ZF8);
     auto all_threads = [&](auto fn) { for (int t = 0; t < 256; ++t) { threadIdx.x = t; fn(); } };
     all_threads([&] {
-        conv8k_stage_a(a.data(), tw, tw8f[threadIdx.x], [&](int m) { return make_float2((float)x[m].real(), (float)x[m].imag()); },
+        conv8k_stage_a(a.data(), conv8k_seeds_ae(tw), tw8f[threadIdx.x], [&](int m) { return make_float2((float)x[m].real(), (float)x[m].imag()); },
                        [&](int m, float e) { en[m] = e; });
     });
-    all_threads([&] { conv8k_stage_b(a.data(), tw); });
+    all_threads([&] { conv8k_stage_b(a.data(), conv8k_seeds_bd(tw)); });
     all_threads([&] { conv8k_stage_c<false>(a.data(), Gp.data(), nullptr, nullptr); });
-    all_threads([&] { conv8k_stage_d(a.data(), tw); });
-    all_threads([&] { conv8k_stage_e(a.data(), tw, tw8f[threadIdx.x], [&](int m, float2 y, int) { out[m] = y; }); });
+    all_threads([&] { conv8k_stage_d(a.data(), conv8k_seeds_bd(tw)); });
+    all_threads([&] { conv8k_stage_e(a.data(), conv8k_seeds_ae(tw), tw8f[threadIdx.x], conv8k_no_pre(), [&](int m, float2 y, int) { out[m] = y; }); });
 
     // ---- reference: circular convolution of x (as float) with g, float64
     double maxerr = 0, scale = 0;
@@ -110,8 +110,8 @@ int main()
     for (int m = 0; m < ZF8; ++m) ad[zpad8(m)] = make_double2(g2[m].real(), g2[m].imag());
     // spectrum of a delay: W^(5 k); use the pipeline itself to get transform order: forward stages on g2 in float are accurate enough
     std::vector<float2> a2(ZFP8), Gp2(ZF8), stash(ZF8), out2(ZF8);
-    all_threads([&] { conv8k_stage_a(a2.data(), tw, tw8f[threadIdx.x], [&](int m) { return make_float2((float)g2[m].real(), (float)g2[m].imag()); }, [](int, float) {}); });
-    all_threads([&] { conv8k_stage_b(a2.data(), tw); });
+    all_threads([&] { conv8k_stage_a(a2.data(), conv8k_seeds_ae(tw), tw8f[threadIdx.x], [&](int m) { return make_float2((float)g2[m].real(), (float)g2[m].imag()); }, [](int, float) {}); });
+    all_threads([&] { conv8k_stage_b(a2.data(), conv8k_seeds_bd(tw)); });
     for (int h = 0; h < 2; ++h)
         for (int t = 0; t < 256; ++t) {
             float2 v[16];
@@ -119,14 +119,14 @@ int main()
             pk::dft16<false>(v);
             for (int q = 0; q < 16; ++q) Gp2[conv8k_gidx(h, t, q)] = make_float2(v[q].x / ZF8, v[q].y / ZF8);
         }
-    all_threads([&] { conv8k_stage_a(a.data(), tw, tw8f[threadIdx.x], [&](int m) { return make_float2((float)x[m].real(), (float)x[m].imag()); }, [](int, float) {}); });
-    all_threads([&] { conv8k_stage_b(a.data(), tw); });
+    all_threads([&] { conv8k_stage_a(a.data(), conv8k_seeds_ae(tw), tw8f[threadIdx.x], [&](int m) { return make_float2((float)x[m].real(), (float)x[m].imag()); }, [](int, float) {}); });
+    all_threads([&] { conv8k_stage_b(a.data(), conv8k_seeds_bd(tw)); });
     all_threads([&] { conv8k_stage_c<true>(a.data(), Gp.data(), Gp2.data(), stash.data()); });
-    all_threads([&] { conv8k_stage_d(a.data(), tw); });
-    all_threads([&] { conv8k_stage_e(a.data(), tw, tw8f[threadIdx.x], [&](int m, float2 y, int) { out[m] = y; }); });
+    all_threads([&] { conv8k_stage_d(a.data(), conv8k_seeds_bd(tw)); });
+    all_threads([&] { conv8k_stage_e(a.data(), conv8k_seeds_ae(tw), tw8f[threadIdx.x], conv8k_no_pre(), [&](int m, float2 y, int) { out[m] = y; }); });
     all_threads([&] { conv8k_unstash(a.data(), stash.data()); });
-    all_threads([&] { conv8k_stage_d(a.data(), tw); });
-    all_threads([&] { conv8k_stage_e(a.data(), tw, tw8f[threadIdx.x], [&](int m, float2 y, int) { out2[m] = y; }); });
+    all_threads([&] { conv8k_stage_d(a.data(), conv8k_seeds_bd(tw)); });
+    all_threads([&] { conv8k_stage_e(a.data(), conv8k_seeds_ae(tw), tw8f[threadIdx.x], conv8k_no_pre(), [&](int m, float2 y, int) { out2[m] = y; }); });
     double e1 = 0, e2 = 0;
     for (int k = 0; k < ZF8; k += 37) {
         cd s(0, 0);

@@ -16,6 +16,7 @@ inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z,
 static struct { int x; } threadIdx;
 inline void __syncthreads() {}
 template <typename T> inline T __ldg(const T *p) { return *p; }
+template <typename T> inline T __ldcg(const T *p) { return *p; }
 inline float2 __fadd2_rn(float2 a, float2 b) { return {a.x + b.x, a.y + b.y}; }
 inline float2 __fmul2_rn(float2 a, float2 b) { return {a.x * b.x, a.y * b.y}; }
 inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return {fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }

@@ -4,6 +4,7 @@
   two changes no rounding) -- a wrong halo, a lost carry or a cross-frame leak anywhere in the batch breaks the equality;
 * batch independence: a frame's outputs and detection record do not depend on which other frames share its launch
   (whole batch vs. two halves: identical bits), which also pins the persistent-CTA work distribution at full grid size;
+* sampled frames of the full batch (8 of cfg 2's 4096, 4 of cfg 3's 1024) against the float64 oracle: metric and timing index;
 * the small-size oracle parity (tests/test_gpu_stripe.py, test_gpu_array.py, test_gpu_bank.py) then carries over."""
 import numpy as np
 import pytest
@@ -34,6 +35,21 @@ def test_cfg2_cfg3_full_size_properties(kind, F, n):
     M1 = out.M.clone()
     # (sc.py normalises by the second-half energy only and minn.py by three quarters: M is not bounded by 1)
     assert bool(torch.isfinite(M1).all()) and float(M1.min()) >= 0.0 and float(M1.max()) < 100.0
+    # (0) sampled frames of the FULL batch against the float64 oracle: metric within 1e-4, timing index and coarse index equal,
+    #     CFO within 1e-5 rad/sample (the oracle takes ~0.1 s per 262 144-sample frame; 8 random frames out of the batch)
+    from oracle import oracle as orc
+    rng = np.random.default_rng(2025)
+    for f in sorted(rng.choice(F, size=8 if n <= 300000 else 4, replace=False).tolist()):
+        xf = x[f].cpu().numpy().astype(np.complex128)
+        Mg = M1[f].cpu().numpy()
+        if kind == "sc":
+            Mo, Po, _ = orc.sc_streaming_metric(xf)
+            t_ref = orc.find_plateau_end_from_metric(Mo, 512, 128, 16)
+        else:
+            Mo, Po, _ = orc.minn_streaming_metric(xf)
+            t_ref = orc.find_minn_peak(Mo, 16)[0]
+        assert np.max(np.abs(Mg - Mo) / np.maximum(Mo, 1e-6)) <= 1e-4, f
+        assert int(rec["timing"][f]) == int(t_ref), (f, rec["timing"][f], t_ref)
     # (1) scale invariance, bit for bit, over the whole batch
     x.mul_(2.0)
     out2 = plan.run(x)

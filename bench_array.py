@@ -68,7 +68,9 @@ def main() -> None:
         caps.append(torch.roll(base, shifts=sh, dims=1))
     x = torch.stack(caps).contiguous()
     del caps, base
-    plan = engine.AADetectPlan(F, A, n, HALF_LEN, THRESH, HYST, FS, in_dtype=args.dtype)
+    # 64 preambles per capture; a circular shift can cut one in two (65 gates), and the drop-ins no longer cut event lists at
+    # the slot count (EventOverflow): 128 slots per capture
+    plan = engine.AADetectPlan(F, A, n, HALF_LEN, THRESH, HYST, FS, in_dtype=args.dtype, max_events=128)
     gather = None                                                                      # event slots + counts, one buffer
     if world > 1:
         gather = (odist.RecordGatherer if args.sync_gather else odist.PipelinedGatherer)(plan.records.view(1, -1))

@@ -226,7 +226,11 @@ def run_cases(a, sink, device_index: int = 0):
         emit("cfg4 zc_freq metric, FFT form (two overlap-save filters + energy recurrence, float32, 1e-4 tolerance)", msf, Ff * n,
              alg_bytes=Ff * (8 * n + 4 * (n - 2559)), key="cfg4_zcfreq_fft",
              note=f"{Ff} captures x {n}; 8 B in + 4 B metric out per sample; {Ff * ((n - 2559 + 6144) // 6145) * (3 * 5 * 8192 * 13 + 2 * 6 * 8192) / msf / 1e9:.1f} TFLOP/s of FFT arithmetic")
-        del xf
+        x2 = xf.reshape(Ff // 2, 2, n)
+        ms2 = timeit(lambda: engine.zc_freq_metric(x2, bi, tb, 62.0, out_f64=False, fast="fft"), steps=3, warmup=2)
+        emit("cfg4 zc_freq metric, FFT form, 2 receive branches summed (what zc_freq.py's own run feeds)", ms2, Ff * n,
+             alg_bytes=Ff // 2 * (16 * n + 4 * (n - 2559)), key="cfg4_zcfreq_fft_2br", note=f"{Ff // 2} captures x 2 branches x {n}")
+        del xf, x2
         ms = timeit(lambda: engine.zc_freq_metric(x, bi, tb, 62.0, out_f64=False, fast=True), steps=3, warmup=2)
         emit("cfg4 zc_freq metric, fast path (bank kernel: sliding-DFT recurrence + tcgen05, one template)", ms, F * n,
              alg_bytes=F * (8 * n + 4 * (n - 2559)), note="8 B in + 4 B metric out per sample; FP16 operands, 5e-3 tolerance",

@@ -159,9 +159,10 @@ __device__ __forceinline__ void conv8k_stage_b(float2 *a, const pk::Seeds &sd)
 
 // Stage C: last forward pass, product with the filter spectrum, first inverse pass.  With a second spectrum Gp2 the same
 // forward result is filtered twice: the first product goes back to shared memory, the second to `stash` (global scratch in
-// the thread's own order: element (h, q) of thread t at stash[(h * 16 + q) * 256 + t], coalesced) for conv8k_unstash.
+// the thread's own order: element (h, q) of thread t at stash[(h * 16 + q) * 256 + t], coalesced) for conv8k_unstash;
+// stash_add: add to what the stash holds (the inverse transform is linear: products of several inputs are summed there).
 template <bool TWO>
-__device__ __forceinline__ void conv8k_stage_c(float2 *a, const float2 *Gp, const float2 *Gp2, float2 *stash)
+__device__ __forceinline__ void conv8k_stage_c(float2 *a, const float2 *Gp, const float2 *Gp2, float2 *stash, bool stash_add = false)
 {
     const int t = threadIdx.x;
 #pragma unroll
@@ -183,6 +184,10 @@ __device__ __forceinline__ void conv8k_stage_c(float2 *a, const float2 *Gp, cons
                 v[q + 1] = pk::mul(v[q + 1], make_float2(g.z, g.w));
             }
             pk::dft16<true>(v);
+            if (stash_add) {                                   // several branches: their second products add up (linearity)
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v[q] = pk::add(v[q], __ldcg(stash + (h * 16 + q) * 256 + t));
+            }
 #pragma unroll
             for (int q = 0; q < 16; ++q) stash[(h * 16 + q) * 256 + t] = v[q];
             asm volatile("" ::: "memory");                     // the reload below is a real shared-memory read

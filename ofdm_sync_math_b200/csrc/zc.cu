@@ -324,7 +324,7 @@ constexpr int ZQF_THREADS = ZNT;
 struct ZcFreqFftParams {
     const float2 *x;
     int64_t n, n_off, mstride;
-    int N, cp, nbins, blocks_per_cap, blocks_per_item, items_per_cap;
+    int N, cp, nbins, nb, blocks_per_cap, blocks_per_item, items_per_cap;     // nb: receive branches, [frames][nb][n]
     int64_t n_items;
     const int *bins;
     const double2 *tw;
@@ -400,22 +400,17 @@ __device__ double zqf_anchor(const float2 *xl, int64_t avail, int N, const int *
 // one 8192-sample block: offsets o0 .. o0 + V - 1 of capture row xc; returns E at the first offset of the next block.
 // Kept out of line: the block loop's own state (item, capture, carries) then lives across ONE call instead of competing with
 // the 100+ registers each FFT stage wants.
-__device__ __noinline__ double zqf_block(float2 *a, float *se, float2 *red, double *wtot, float *wmax, double *dred,
-                                        const float2 *xc, float *mrow, int b, double Eb, float *emax_io)
+// S path of one branch of one block: forward transform, both products (S back to shared memory, Y into / onto the stash),
+// inverse transform of S, increments of E into se (added to the previous branches' when `add`).  Out of line for the same
+// reason as zqf_block: called once per branch, its 100+ registers per stage do not compete with the caller's state.
+__device__ __noinline__ void zqf_spath(float2 *a, float *se, const float2 *xb, int64_t availl, unsigned o_cnt, bool add)
 {
     const ZcFreqFftParams &p = g_zqf;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int N = p.N, V = ZF8 - N + 1;
     const float2 w0 = __ldg(p.tw8 + tid);
-    const int64_t o0 = (int64_t)b * V;                    // first offset of the block; local sample m = x[cp + o0 + m]
-    const float2 *xl = xc + p.cp + o0;
-    const int64_t availl = p.n - p.cp - o0;
     const unsigned m_cnt = (unsigned)(availl < ZF8 ? availl : ZF8);
-    const int64_t left = p.n_off - o0;
-    const unsigned o_cnt = (unsigned)(left < V ? left : V);
-    constexpr int IPT = ZF8 / ZNT;
-    const int s0 = tid * IPT + 1;
-    auto ldx = [&](int m) { return (unsigned)m < m_cnt ? __ldg(xl + m) : make_float2(0.f, 0.f); };
+    auto ldx = [&](int m) { return (unsigned)m < m_cnt ? __ldg(xb + m) : make_float2(0.f, 0.f); };
     // twiddle seeds are fetched ahead of the barrier that precedes their stage
     pk::Seeds sd = conv8k_seeds_ae(p.tw);
     conv8k_stage_a(a, sd, w0, ldx, [](int, float) {});
@@ -423,35 +418,56 @@ __device__ __noinline__ double zqf_block(float2 *a, float *se, float2 *red, doub
     __syncthreads();
     conv8k_stage_b(a, sd);
     __syncthreads();
-    conv8k_stage_c<true>(a, p.GpS, p.GpY, p.stash + (size_t)blockIdx.x * ZF8);          // S back to shared memory, Y to the stash
+    conv8k_stage_c<true>(a, p.GpS, p.GpY, p.stash + (size_t)blockIdx.x * ZF8, add);      // S back to shared memory, Y to the stash
     sd = conv8k_seeds_bd(p.tw);
     __syncthreads();
     conv8k_stage_d(a, sd);
     sd = conv8k_seeds_ae(p.tw);
     __syncthreads();
     // S(o) -> increment of E: se[spad(i + 1)] = E(o0 + i + 1) - E(o0 + i)
-    {
-        const float Jf = (float)p.nbins;
-        struct DPair { float2 hi, lo; };
-        conv8k_stage_e(a, sd, w0,
-                       [&](int m) {                                 // d(o) = x[o+cp+N] - x[o+cp], fetched 8 outputs ahead
-                           const int i = m - (N - 1);
-                           DPair d;
-                           d.hi = d.lo = make_float2(0.f, 0.f);
-                           if ((unsigned)i < o_cnt) {
-                               if ((int64_t)(i + N) < availl) d.hi = __ldg(xl + i + N);      // i + N may be sample 8192: past the block, inside the capture
-                               d.lo = ldx(i);
-                           }
-                           return d;
-                       },
-                       [&](int m, float2 S, const DPair &d) {
-                           const int i = m - (N - 1);
-                           if ((unsigned)i >= (unsigned)V) return;
-                           const float dx = d.hi.x - d.lo.x, dy = d.hi.y - d.lo.y;
-                           se[spad(i + 1)] = (unsigned)i < o_cnt ? fmaf(2.f, fmaf(S.x, dx, S.y * dy), Jf * fmaf(dx, dx, dy * dy)) : 0.f;
-                       });
-    }
+    const float Jf = (float)p.nbins;
+    struct DPair { float2 hi, lo; };
+    conv8k_stage_e(a, sd, w0,
+                   [&](int m) {                                 // d(o) = x[o+cp+N] - x[o+cp], fetched 8 outputs ahead
+                       const int i = m - (N - 1);
+                       DPair d;
+                       d.hi = d.lo = make_float2(0.f, 0.f);
+                       if ((unsigned)i < o_cnt) {
+                           if ((int64_t)(i + N) < availl) d.hi = __ldg(xb + i + N);      // i + N may be sample 8192: past the block, inside the capture
+                           d.lo = ldx(i);
+                       }
+                       return d;
+                   },
+                   [&](int m, float2 S, const DPair &d) {
+                       const int i = m - (N - 1);
+                       if ((unsigned)i >= (unsigned)V) return;
+                       const float dx = d.hi.x - d.lo.x, dy = d.hi.y - d.lo.y;
+                       const float dl = (unsigned)i < o_cnt ? fmaf(2.f, fmaf(S.x, dx, S.y * dy), Jf * fmaf(dx, dx, dy * dy)) : 0.f;
+                       se[spad(i + 1)] = add ? se[spad(i + 1)] + dl : dl;       // the same thread wrote it for the previous branch
+                   });
     __syncthreads();
+}
+
+// one 8192-sample block: offsets o0 .. o0 + V - 1 of capture row xc; returns E at the first offset of the next block.
+// Kept out of line: the block loop's own state (item, capture, carries) then lives across ONE call instead of competing with
+// the 100+ registers each FFT stage wants.  Branches (zc_freq.py:88-97): Y is linear in the samples, so the branches' Y
+// products are summed in the stash (one inverse transform for all of them); E is not, so every branch runs its own S path
+// and the increments add up in se.
+__device__ __noinline__ double zqf_block(float2 *a, float *se, float2 *red, double *wtot, float *wmax, double *dred,
+                                        const float2 *xc, float *mrow, int b, double Eb, float *emax_io)
+{
+    const ZcFreqFftParams &p = g_zqf;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = p.N, V = ZF8 - N + 1;
+    const int64_t o0 = (int64_t)b * V;                    // first offset of the block; local sample m = x[cp + o0 + m]
+    const float2 *xl = xc + p.cp + o0;
+    const int64_t availl = p.n - p.cp - o0;
+    const int64_t left = p.n_off - o0;
+    const unsigned o_cnt = (unsigned)(left < V ? left : V);
+    constexpr int IPT = ZF8 / ZNT;
+    const int s0 = tid * IPT + 1;
+    const int n_br = p.nb;
+    for (int br = 0; br < n_br; ++br) zqf_spath(a, se, xl + (int64_t)br * p.n, availl, o_cnt, br > 0);
     // the Y product comes back from the stash while the prefix sum runs (an L2 round trip: 14 % of the kernel when exposed)
     float2 yst[32];
     conv8k_unstash_fetch(p.stash + (size_t)blockIdx.x * ZF8, yst);
@@ -505,12 +521,15 @@ __device__ __noinline__ double zqf_block(float2 *a, float *se, float2 *red, doub
     double Enext = Eb + tot;
     float Df = 0.f;
     if (mn < 2e-3f * mx) {                                         // block-uniform
-        const double Ed = zqf_anchor(xl + o_cnt, availl - (int64_t)o_cnt, N, p.bins, p.nbins, p.tw, red, dred);
+        double Ed = 0.0;
+        for (int br = 0; br < n_br; ++br)
+            Ed += zqf_anchor(xl + (int64_t)br * p.n + o_cnt, availl - (int64_t)o_cnt, N, p.bins, p.nbins, p.tw, red, dred);
         Df = (float)(Enext - Ed);
         Enext = Ed;
     }
     conv8k_unstash_put(a, yst);
-    sd = conv8k_seeds_bd(p.tw);
+    const float2 w0 = __ldg(p.tw8 + tid);
+    pk::Seeds sd = conv8k_seeds_bd(p.tw);
     __syncthreads();
     conv8k_stage_d(a, sd);
     sd = conv8k_seeds_ae(p.tw);
@@ -547,10 +566,12 @@ __global__ void __launch_bounds__(ZQF_THREADS, 2) zc_freq_fft_kernel(const __gri
         const int64_t cap = item / p.items_per_cap;
         const int b0 = (int)(item % p.items_per_cap) * p.blocks_per_item;
         const int b1 = b0 + p.blocks_per_item < p.blocks_per_cap ? b0 + p.blocks_per_item : p.blocks_per_cap;
-        const float2 *xc = p.x + cap * p.n;
+        const float2 *xc = p.x + cap * p.nb * p.n;
         __syncthreads();
-        // E at the item's first offset, directly
-        double Eb = zqf_anchor(xc + p.cp + (int64_t)b0 * V, p.n - p.cp - (int64_t)b0 * V, p.N, p.bins, p.nbins, p.tw, red, dred);
+        // E at the item's first offset, directly (summed over the branches)
+        double Eb = 0.0;
+        for (int br = 0; br < p.nb; ++br)
+            Eb += zqf_anchor(xc + (int64_t)br * p.n + p.cp + (int64_t)b0 * V, p.n - p.cp - (int64_t)b0 * V, p.N, p.bins, p.nbins, p.tw, red, dred);
         float emax = (float)Eb;
         for (int b = b0; b < b1; ++b) Eb = zqf_block(a, se, red, wtot, wmax, dred, xc, p.metric + cap * p.mstride, b, Eb, &emax);
     }
@@ -871,7 +892,7 @@ OFS_API int ofs_zc_freq_metric(const void *x, int32_t in_dtype, int64_t n_frames
     return check_launch("zc_freq_kernel");
 }
 
-OFS_API int ofs_zc_freq_metric_fft(const void *x_c64, int64_t n_frames, int64_t n, int32_t n_fft, int32_t cp, const int32_t *bins,
+OFS_API int ofs_zc_freq_metric_fft(const void *x_c64, int64_t n_frames, int32_t n_branches, int64_t n, int32_t n_fft, int32_t cp, const int32_t *bins,
                                    const void *templ_c64, int32_t nbins, double templ_energy, float *metric, int64_t out_stride,
                                    void *stream_)
 {
@@ -879,6 +900,7 @@ OFS_API int ofs_zc_freq_metric_fft(const void *x_c64, int64_t n_frames, int64_t 
     OFS_REQUIRE(x_c64 && bins && templ_c64 && metric && templ_energy > 0.0, "ofs_zc_freq_metric_fft: bad arguments");
     OFS_REQUIRE(n_fft >= 2 && n_fft <= 2048 && cp >= 0, "ofs_zc_freq_metric_fft: n_fft must be 2..2048");
     OFS_REQUIRE(nbins >= 1 && nbins <= 64, "ofs_zc_freq_metric_fft: nbins <= 64");
+    OFS_REQUIRE(n_branches >= 1 && n_branches <= 64, "ofs_zc_freq_metric_fft: 1..64 branches");
     const int64_t n_off = n - ((int64_t)n_fft + cp) + 1;
     OFS_REQUIRE(n_off > 0, "Received stream is shorter than a single OFDM symbol.");   /* zc_freq.py:76-78 */
     OFS_REQUIRE(out_stride >= n_off && n_frames >= 0, "ofs_zc_freq_metric_fft: out_stride < number of offsets");
@@ -920,7 +942,7 @@ OFS_API int ofs_zc_freq_metric_fft(const void *x_c64, int64_t n_frames, int64_t 
     if (int rc = check_launch("zc_spectrum8k_kernel")) return rc;
     count_launch(5);
     p.x = reinterpret_cast<const float2 *>(x_c64); p.n = n; p.n_off = n_off; p.mstride = out_stride;
-    p.N = n_fft; p.cp = cp; p.nbins = nbins; p.bins = bins; p.tw = tw; p.tw8 = tw8f; p.GpY = Gp; p.GpS = Gp + ZF8; p.stash = stash;
+    p.N = n_fft; p.cp = cp; p.nbins = nbins; p.nb = n_branches; p.bins = bins; p.tw = tw; p.tw8 = tw8f; p.GpY = Gp; p.GpS = Gp + ZF8; p.stash = stash;
     p.templ_energy = (float)templ_energy; p.metric = metric;
     const size_t smem = (size_t)ZFP8 * sizeof(float2) + (size_t)(ZF8 + ZF8 / 32 + 8) * sizeof(float);
     OFS_CUDA(cudaFuncSetAttribute(zc_freq_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

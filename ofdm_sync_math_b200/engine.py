@@ -752,8 +752,8 @@ def zc_normalize(corr, rx, reference):
 def zc_freq_metric(rx, bin_indices, template_bins, template_energy: float, n_fft: int = 2048, cp: int = 512,
                    out_f64: bool | None = None, fast: bool | str = False) -> torch.Tensor:
     """zc_freq.py:62-99 -> metric [F, n - (n_fft+cp) + 1].  Default: the float64-prefix kernel (1e-11).  For complex64
-    single-branch captures: fast="fft" the FFT form (ofs_zc_freq_metric_fft: two overlap-save filters + the energy recurrence,
-    float32 metric within 1e-4 of its maximum, n_fft <= 2048); fast="f32" the packed-fp32 sliding-DFT kernel
+    captures: fast="fft" the FFT form (ofs_zc_freq_metric_fft: two overlap-save filters + the energy recurrence,
+    float32 metric within 1e-4 of its maximum, n_fft <= 2048, any number of branches); single-branch only: fast="f32" the packed-fp32 sliding-DFT kernel
     (ofs_zc_freq_metric_f32, same tolerance, any n_fft multiple of 32); fast=True / "tc" the tensor-core kernel of the
     correlator bank (fp16 operands, 5e-3)."""
     x, code, _ = to_device(rx)
@@ -764,14 +764,18 @@ def zc_freq_metric(rx, bin_indices, template_bins, template_energy: float, n_fft
     if n_off <= 0:
         raise ValueError("Received stream is shorter than a single OFDM symbol.")     # zc_freq.py:76-78
     if fast:
-        if code != L.OFS_C64 or B != 1 or out_f64:
-            raise L.OfsError("zc_freq_metric(fast=...) takes complex64 single-branch captures and returns float32")
+        if code != L.OFS_C64 or out_f64 or (B != 1 and fast != "fft"):
+            raise L.OfsError("zc_freq_metric(fast=...) takes complex64 captures (one branch; any number with fast='fft') and returns float32")
         k = np.mod(np.asarray(bin_indices, dtype=np.int64), n_fft).astype(np.int32)
         bins = torch.as_tensor(k).to(x.device)
         t = torch.as_tensor(np.ascontiguousarray(np.asarray(template_bins, dtype=np.complex64))).to(x.device)
         out = torch.empty((F, n_off), dtype=torch.float32, device=x.device)
+        if fast == "fft":
+            L.check(L.lib().ofs_zc_freq_metric_fft(_ptr(x), C.c_int64(F), int(B), C.c_int64(n), int(n_fft), int(cp), _ptr(bins), _ptr(t),
+                                                   int(k.size), C.c_double(float(template_energy)), _ptr(out), C.c_int64(n_off),
+                                                   _stream()), "ofs_zc_freq_metric_fft")
+            return out
         fn, name = (L.lib().ofs_zc_freq_metric_f32, "ofs_zc_freq_metric_f32") if fast == "f32" else \
-                   (L.lib().ofs_zc_freq_metric_fft, "ofs_zc_freq_metric_fft") if fast == "fft" else \
                    (L.lib().ofs_zc_freq_metric_fast, "ofs_zc_freq_metric_fast")
         L.check(fn(_ptr(x), C.c_int64(F), C.c_int64(n), int(n_fft), int(cp), _ptr(bins), _ptr(t), int(k.size),
                    C.c_double(float(template_energy)), _ptr(out), C.c_int64(n_off), _stream()), name)

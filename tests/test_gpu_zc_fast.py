@@ -165,17 +165,38 @@ def test_zc_freq_fft_form_vs_oracle(n, bpi, monkeypatch):
 
 
 def test_zc_freq_fft_form_on_reference_fixture(golden):
+    """The reference script's own input, ALL of its receive branches (zc_freq.py:88-97 sums them), as complex64."""
     from ofdm_sync_math_b200 import engine
     for tag in ("cir1", "awgn"):
         g = golden(f"zc_freq_{tag}")
-        rx = np.asarray(g["rx"])
-        rx = rx[0] if rx.ndim == 2 else rx          # the fast kernels take one branch
+        rx = np.atleast_2d(np.asarray(g["rx"]))
         x = rx.astype(np.complex64)
-        m = engine.zc_freq_metric(torch.as_tensor(x).cuda()[None, None], g["bin_indices"], g["template"], float(g["template_energy"]),
+        m = engine.zc_freq_metric(torch.as_tensor(x).cuda()[None], g["bin_indices"], g["template"], float(g["template_energy"]),
                                   fast="fft").cpu().numpy()[0]
         mo = orc.compute_frequency_metric(x.astype(np.complex128), g["bin_indices"], g["template"], float(g["template_energy"]))
-        assert np.abs(m - mo).max() <= 1e-4 * mo.max()
+        assert m.shape == mo.shape
+        assert np.abs(m - mo).max() <= 1e-4 * mo.max(), (tag, rx.shape, np.abs(m - mo).max() / mo.max())
         assert int(np.argmax(m)) == int(np.argmax(mo))
+
+
+@pytest.mark.parametrize("nb", [2, 3])
+def test_zc_freq_fft_form_branches_summed(nb, monkeypatch):
+    """Several receive branches per capture: correlations and in-band energies summed over the branches before the ratio
+    (zc_freq.py:88-97) -- float32 metric within 1e-4 of the float64 oracle's maximum, carry across blocks forced."""
+    from ofdm_sync_math_b200 import engine
+    from ofdm_sync_math_b200.zc import generate_zadoff_chu
+    monkeypatch.setenv("OFS_ZQF_BLOCKS_PER_ITEM", "64")
+    n = 30000
+    bi = np.concatenate((np.arange(-31, 0), np.arange(1, 32)))
+    tb = generate_zadoff_chu(25, 62)
+    x = np.stack([np.stack([_pss_capture(n, 500 + 10 * f + b, snr_db=[0.0, 10.0][f % 2], n_pss=2) for b in range(nb)]) for f in range(2)])
+    x[1, 0, n // 2:n // 2 + 300] *= 40.0          # a burst on one branch only
+    m = engine.zc_freq_metric(torch.as_tensor(x).cuda(), bi, tb, 62.0, fast="fft").cpu().numpy()
+    for f in range(2):
+        mo = orc.compute_frequency_metric(x[f].astype(np.complex128), bi, tb, 62.0)
+        err = np.abs(m[f] - mo).max()
+        assert err <= 1e-4 * mo.max(), (f, err / mo.max(), int(np.argmax(np.abs(m[f] - mo))))
+        assert int(np.argmax(m[f])) == int(np.argmax(mo))
 
 
 @pytest.mark.parametrize("n_fft,cp,nb", [(2048, 512, 62), (1024, 72, 40), (512, 0, 12), (1536, 100, 62)])

@@ -122,21 +122,6 @@ struct Prune {
 // slack / n_near (exact mode): chunks are kept while their bound reaches v* (1 - slack), and *n_near receives how many values
 // reach that level -- 1 means the maximum has no contender inside the band and needs no float64 re-evaluation; -1 = unknown
 // (no chunk maxima to derive v* from).
-// L2 prefetch of the row elements [lo, hi) (element size esz): the chunk sweeps below test 32 chunk bounds at a time and then
-// evaluate the survivors one after the other -- each evaluation a dependent DRAM round trip, which is what a detector CTA on a
-// long row spends its time on (minn_peak_kernel on 1 M-sample rows: ~60 of them per warp, ~100 us per row).  Every lane whose
-// chunk survives the bound test asks for its chunk's lines right away, so the evaluations that follow find them in L2.
-__device__ __forceinline__ void prefetch_l2_range(const void *base, int64_t lo, int64_t hi, int64_t n, int esz)
-{
-    if (lo < 0) lo = 0;
-    if (hi > n) hi = n;
-    if (lo >= hi) return;
-    const char *p = reinterpret_cast<const char *>(base) + lo * esz;
-    const char *e = reinterpret_cast<const char *>(base) + hi * esz;
-    for (const char *q = reinterpret_cast<const char *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)127); q < e; q += 128)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-}
-
 template <int K = 1, typename F>
 __device__ ArgVal pruned_argmax(const F &fn, int64_t n_out, const Prune &pr, ArgVal *sh_av, double slack = 0.0, int *n_near = nullptr)
 {
@@ -173,7 +158,6 @@ __device__ ArgVal pruned_argmax(const F &fn, int64_t n_out, const Prune &pr, Arg
     for (int c0 = warp * 32; c0 < nchi; c0 += (int)blockDim.x) {
         const int cl = c0 + lane;
         const bool pass = cl < nchi && (!have || (double)pr.bound(cl) >= near_lvl);
-        if (pass && have) fn.prefetch((int64_t)cl * 256 - pr.toff, 256);
         unsigned m = __ballot_sync(0xffffffffu, pass);
         while (m) {                              // K surviving chunks per round, in ascending order (first maximum wins)
             int64_t i0s[K];
@@ -290,10 +274,6 @@ struct SmoothSame {   // np.convolve(M, ones(w)/w, "same")[i], sc.py:100
         const double v = pd ? pd[jc] : (double)pf[jc];
         return ok ? v * h : 0.0;
     }
-    __device__ __forceinline__ void prefetch(int64_t i0, int cnt) const        // the elements outputs i0 .. i0 + cnt - 1 read
-    {
-        prefetch_l2_range(pd ? (const void *)pd : (const void *)pf, i0 + off - w, i0 + off + cnt, n, pd ? 8 : 4);
-    }
     // compile-time window: the W+7 values are fetched by independent (predicated) loads first, then slid.  The window is held
     // in the row's own type (float rows: half the registers of a double window; the conversion at use is exact).
     template <int W, typename T>
@@ -379,7 +359,6 @@ __device__ int collect_at_least(const F &fn, int64_t n_out, const Prune &pr, dou
     for (int c0 = warp * 32; c0 < nchi; c0 += (int)blockDim.x) {
         const int cl = c0 + lane;
         const bool pass = cl < nchi && (pr.cm == nullptr || (double)pr.bound(cl) >= lvl);
-        if (pass && pr.cm) fn.prefetch((int64_t)cl * 256 - pr.toff, 256);
         unsigned m = __ballot_sync(0xffffffffu, pass);
         while (m) {
             const int c = c0 + __ffs(m) - 1;
@@ -625,10 +604,6 @@ struct Trailing {   // minn._trailing_average(max(M,0), w)[i], minn.py:115-128
         return (ok && v > 0.0) ? v : 0.0;
     }
     __device__ __forceinline__ double denom(int64_t i) const { return (double)(i >= w - 1 ? w : (i >= 0 ? i + 1 : 1)); }
-    __device__ __forceinline__ void prefetch(int64_t i0, int cnt) const        // the elements outputs i0 .. i0 + cnt - 1 read
-    {
-        prefetch_l2_range(pd ? (const void *)pd : (const void *)pf, i0 - w, i0 + cnt, n, pd ? 8 : 4);
-    }
     template <int W, typename T>
     __device__ __forceinline__ void load_win(const T *p, int64_t i0, T (&y)[W + 7]) const
     {
@@ -902,7 +877,6 @@ __global__ void __launch_bounds__(F64 ? DNT : MNT, F64 ? 2 : 1) minn_peak_kernel
             const int cl = c0 + lane;
             const bool inr = cl < nchi;
             const bool pass = inr && (!pr.cm || (double)pr.bound(cl) >= lvl_lo);
-            if (pass && pr.cm) Ms.prefetch((int64_t)cl * 256 - toff, 256);
             if (inr && !pass) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) mask[cl * 8 + q] = 0u;

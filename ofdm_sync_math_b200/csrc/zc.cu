@@ -222,11 +222,14 @@ __global__ void __launch_bounds__(ZNT) zc_spectrum8k_kernel(const double2 *ref, 
     }
 }
 
-template <int DT>
+// MODE (0: zc.py:125-126, 1: zc_v2.py:257-271, 2: raw) and the presence of the complex output are compile-time: the epilogue
+// is a third of the kernel's instructions and every run-time choice in it is paid 32 times per thread
+template <int DT, int MODE, bool CORR>
 __global__ void __launch_bounds__(ZNT, 2) zc_mf8k_kernel(const void *x, int64_t n, int nr, const double2 *tw, const float2 *tw8,
-                                                        const float2 *Gp, const double *ref_norm_p, int mode, float2 *corr_out,
+                                                        const float2 *Gp, const double *ref_norm_p, float2 *corr_out,
                                                         float *mag_out, int64_t out_stride, int blocks_per_frame)
 {
+    constexpr int mode = MODE;
     using In = typename InT<DT>::type;
     extern __shared__ __align__(16) unsigned char zsm[];
     float2 *a = reinterpret_cast<float2 *>(zsm);                              // ZFP8
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(ZNT, 2) zc_mf8k_kernel(const void *x, int64_t 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const In *xb = reinterpret_cast<const In *>(x) + frame * n;
     const float2 w0 = __ldg(tw8 + tid);
-    const bool norm = mode != 2;
+    constexpr bool norm = MODE != 2;
     // local samples [m_lo, m_hi) of the block lie inside the capture (one unsigned compare per sample)
     const int m_lo = jb < 0 ? (int)(-jb) : 0;
     const int m_hi = n - jb < ZF8 ? (int)(n - jb) : ZF8;
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(ZNT, 2) zc_mf8k_kernel(const void *x, int64_t 
     // local outputs m in [nr - 1, o_hi) are this block's: output k0 + i, i = m - (nr - 1), is the window of local samples [i, i + nr - 1]
     const int64_t left = out_len - k0;
     const unsigned o_cnt = (unsigned)(left < V ? left : V);
-    float2 *co = corr_out ? corr_out + frame * out_stride + k0 - (nr - 1) : nullptr;
+    float2 *co = CORR ? corr_out + frame * out_stride + k0 - (nr - 1) : nullptr;
     float *mo = mag_out ? mag_out + frame * out_stride + k0 - (nr - 1) : nullptr;
     conv8k_stage_e(a, s_e, w0, conv8k_no_pre(), [&](int m, float2 y, int) {
         const int i = m - (nr - 1);
@@ -300,8 +303,8 @@ __global__ void __launch_bounds__(ZNT, 2) zc_mf8k_kernel(const void *x, int64_t 
                                  : rsqrtf(fmaxf(e, 0.f) + 1e-12f));     // zc.py:125-126
         }
         const float2 ys = __fmul2_rn(y, make_float2(sc, sc));
-        if (co) co[m] = ys;
-        if (mo) mo[m] = sqrt_approx(fmaf(ys.x, ys.x, ys.y * ys.y));
+        if (CORR) co[m] = ys;
+        if (!CORR || mo) mo[m] = sqrt_approx(fmaf(ys.x, ys.x, ys.y * ys.y));
     });
 }
 
@@ -793,15 +796,22 @@ OFS_API int ofs_zc_matched_filter(const void *x, int32_t in_dtype, int64_t n_fra
         const int64_t grid8 = (int64_t)bpf8 * n_frames;
         OFS_REQUIRE(grid8 < (1LL << 31), "ofs_zc_matched_filter: grid too large");
         const size_t smem8 = (size_t)ZFP8 * sizeof(float2) + (size_t)(ZF8 + ZF8 / 32 + 8) * sizeof(float);
-        if (in_dtype == OFS_C64) {
-            OFS_CUDA(cudaFuncSetAttribute(zc_mf8k_kernel<OFS_C64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-            zc_mf8k_kernel<OFS_C64><<<(unsigned)grid8, ZNT, smem8, stream>>>(x, n, nr, tw, tw8f, G8, rn, mode, (float2 *)corr_out, (float *)mag_out,
-                                                                            out_stride, bpf8);
-        } else {
-            OFS_CUDA(cudaFuncSetAttribute(zc_mf8k_kernel<OFS_IQ16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-            zc_mf8k_kernel<OFS_IQ16><<<(unsigned)grid8, ZNT, smem8, stream>>>(x, n, nr, tw, tw8f, G8, rn, mode, (float2 *)corr_out, (float *)mag_out,
-                                                                             out_stride, bpf8);
-        }
+#define OFS_MF8_LAUNCH(DT, MODE, CORR)                                                                              \
+    do {                                                                                                           \
+        auto kern = zc_mf8k_kernel<DT, MODE, CORR>;                                                                \
+        OFS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));             \
+        kern<<<(unsigned)grid8, ZNT, smem8, stream>>>(x, n, nr, tw, tw8f, G8, rn, (float2 *)corr_out, (float *)mag_out, out_stride, bpf8); \
+    } while (0)
+#define OFS_MF8_MODE(DT, CORR)                                                                                     \
+    do {                                                                                                           \
+        if (mode == 0) OFS_MF8_LAUNCH(DT, 0, CORR);                                                                \
+        else if (mode == 1) OFS_MF8_LAUNCH(DT, 1, CORR);                                                           \
+        else OFS_MF8_LAUNCH(DT, 2, CORR);                                                                          \
+    } while (0)
+        if (in_dtype == OFS_C64) { if (corr_out) OFS_MF8_MODE(OFS_C64, true); else OFS_MF8_MODE(OFS_C64, false); }
+        else { if (corr_out) OFS_MF8_MODE(OFS_IQ16, true); else OFS_MF8_MODE(OFS_IQ16, false); }
+#undef OFS_MF8_MODE
+#undef OFS_MF8_LAUNCH
         if (int rc = check_launch("zc_mf8k_kernel")) return rc;
         OFS_CUDA(cudaFreeAsync(tw8f, stream)); OFS_CUDA(cudaFreeAsync(tw8d, stream)); OFS_CUDA(cudaFreeAsync(G8, stream));
         OFS_CUDA(cudaFreeAsync(tw, stream)); OFS_CUDA(cudaFreeAsync(G, stream)); OFS_CUDA(cudaFreeAsync(rn, stream));
@@ -917,8 +927,8 @@ OFS_API int ofs_zc_freq_metric_fft(const void *x_c64, int64_t n_frames, int32_t 
     if (const char *e = getenv("OFS_ZQF_BLOCKS_PER_ITEM")) bpi = atoll(e);
     if (bpi < 1) bpi = 1;
     if (bpi > p.blocks_per_cap) bpi = p.blocks_per_cap;
-    p.blocks_per_item = (int)bpi;
-    p.items_per_cap = (p.blocks_per_cap + p.blocks_per_item - 1) / p.blocks_per_item;
+    p.items_per_cap = (int)((p.blocks_per_cap + bpi - 1) / bpi);
+    p.blocks_per_item = (p.blocks_per_cap + p.items_per_cap - 1) / p.items_per_cap;      // equal parts: 11 blocks in 2 items are 6 + 5, not 9 + 2
     p.n_items = n_frames * p.items_per_cap;
     const int grid = (int)(p.n_items < slots ? p.n_items : slots);
     double2 *tw = nullptr, *tw8d = nullptr, *ref = nullptr;

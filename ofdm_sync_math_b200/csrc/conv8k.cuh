@@ -205,6 +205,41 @@ __device__ __forceinline__ void conv8k_stage_c(float2 *a, const float2 *Gp, cons
         for (int q = 0; q < 16; ++q) ah[q] = v[q];
     }
 }
+// Halves of stage C on their own.  Stage B followed by conv8k_stage_c_fwd is a 256-point forward FFT of EVERY aligned
+// 256-element block of the array (the last two passes of the 4096-point transforms work inside such blocks), each spectrum in
+// the same (digit-reversed) order; conv8k_stage_c_inv followed by stage D is the inverse (unscaled: x 256), natural order
+// out.  The block-FFT Park kernel (park.cu) uses the array as 32 independent 256-point transforms.
+__device__ __forceinline__ void conv8k_stage_c_fwd(float2 *a)
+{
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float2 *ah = a + h * ZFP + t * 17;
+        float2 v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = ah[q];
+        pk::dft16<false>(v);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) ah[q] = v[q];
+    }
+}
+__device__ __forceinline__ void conv8k_stage_c_inv(float2 *a)
+{
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float2 *ah = a + h * ZFP + t * 17;
+        float2 v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = ah[q];
+        pk::dft16<true>(v);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) ah[q] = v[q];
+    }
+}
+// element e (0..255) of 256-block s (0..31) of the array
+__device__ __forceinline__ int conv8k_blk(int s, int e) { return (s >> 4) * ZFP + zpad((s & 15) * 256 + e); }
+
 // the stashed second product back into shared memory (same thread, same positions as stage C's own store), in two steps so
 // that the L2 round trip can hide behind other work: fetch into registers, ... , put into shared memory
 __device__ __forceinline__ void conv8k_unstash_fetch(const float2 *stash, float2 (&r)[32])

@@ -7,6 +7,8 @@
 // (14 smem loads per 16 complex MACs).  Accumulation: T (float for c64/iq16 input with float64
 // flushes every 128 lags, double for c128).
 #include "common.cuh"
+#include "conv8k.cuh"
+#include <cstdlib>
 
 namespace ofs {
 
@@ -213,10 +215,190 @@ __global__ void __launch_bounds__(QNT2) park_kernel_v2(const void *x, int nb, in
     }
 }
 
+// ---- K3b: the Park metric by block FFTs (float32; h a multiple of 128, h <= 1024) ---------------------------------------
+// P(d) = sum_{k<h} x[d-k] x[d+k] is half of a BAND-LIMITED self-convolution: with C(2d) = sum_{i+j=2d, |j-i|<2h} x[i] x[j]
+// (ordered pairs), C(2d) = 2 P(d) - x[d]^2.  i + j even means i and j have the same parity, so with the half-rate sequences
+// xe[p] = x[2p], xo[p] = x[2p+1]:  C(2d) = Cb_e(d) + Cb_o(d-1),  Cb_y(n) = sum_{p+q=n, |q-p|<h} y[p] y[q]  (no parity waste).
+// Cut y into blocks of B = 128 and let m = h / B.  A block pair (I, J) lies entirely inside the band when |J - I| <= m - 1 and
+// contributes the plain linear convolution y_I * y_J to the outputs n in [(I+J) B, (I+J+2) B); pairs with |J - I| = m are cut
+// by the band edge to the strict triangle q' < p' (local indices), pairs further apart contribute nothing.  Hence, per
+// anti-diagonal S = I + J:   Z_S = sum_{I+J=S, |J-I|<m} X_I X_J   (X = 256-point FFT of the zero-padded block: the products are
+// summed in the FREQUENCY domain and ONE inverse transform per anti-diagonal brings them back), plus the edge triangle of the
+// one pair with |J - I| = m directly.  ~700 flops per output instead of 8192.
+// One CTA = 1536 consecutive outputs of one frame.  The 8192-element array of conv8k.cuh serves as 32 independent 256-point
+// transforms (stage B + half of stage C): 16 blocks of samples and 14 anti-diagonals per parity pass.  Checked against the
+// float64 oracle and against the direct kernel (tests/test_gpu_park.py); OFS_PARK_DIRECT=1 forces the direct kernel.
+constexpr int PF_B = 128, PF_T = 12, PF_OUT = PF_T * PF_B, PF_NZ = PF_T + 2, PF_NBLK = 16, PF_R = PF_OUT / ZNT;
+
+__global__ void park_twiddle_kernel(double2 *tw)         // the table layout of fft4096.cuh: double2[2048] then float2[2048]
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ZF / 2) {
+        double sn, c;
+        sincospi(-2.0 * (double)i / (double)ZF, &sn, &c);
+        tw[i] = make_double2(c, sn);
+        reinterpret_cast<float2 *>(tw + ZF / 2)[i] = make_float2((float)c, (float)sn);
+    }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(ZNT, 2) park_fft_kernel(const void *x, int nb, int64_t L, int64_t xfs, int64_t xbs, int h, int64_t n_out,
+                                                         int64_t out_stride, float *M, float2 *P, float *E, int tiles_per_frame,
+                                                         const double2 *tw)
+{
+    using In = typename InT<DT>::type;
+    extern __shared__ __align__(16) unsigned char psm[];
+    float2 *a = reinterpret_cast<float2 *>(psm);              // 32 blocks of 256 (padded): 16 sample blocks, 14 anti-diagonals
+    float2 *yc = a + ZFP8;                                    // [16][128] the loaded blocks in the time domain (edge triangles)
+    __shared__ double wsum[ZNT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t frame = blockIdx.x / tiles_per_frame;
+    const int tile = blockIdx.x % tiles_per_frame;
+    const int m = h / PF_B;
+    const int S0 = tile * PF_T;                               // first anti-diagonal block of the tile (even)
+    const int64_t D0 = (int64_t)S0 * PF_B;                    // first centre d of the tile (d = h + output index)
+    const int I_lo = (S0 - 2 - m) >> 1;                       // first sample block loaded (floor; blocks before the frame are zero)
+    float2 accP[PF_R];
+#pragma unroll
+    for (int r = 0; r < PF_R; ++r) accP[r] = make_float2(0.f, 0.f);
+
+    for (int b = 0; b < nb; ++b) {
+        const In *xb = reinterpret_cast<const In *>(x) + frame * xfs + (int64_t)b * xbs;
+        for (int par = 0; par < 2; ++par) {
+            __syncthreads();
+            for (int idx = tid; idx < PF_NBLK * PF_B; idx += ZNT) {
+                const int s = idx >> 7, pp = idx & (PF_B - 1);
+                const int64_t p = (int64_t)(I_lo + s) * PF_B + pp, j = 2 * p + par;
+                float2 v = make_float2(0.f, 0.f);
+                if (p >= 0 && j < L) { const In t = xb[j]; v = make_float2((float)t.x, (float)t.y); }
+                a[conv8k_blk(s, pp)] = v;
+                a[conv8k_blk(s, PF_B + pp)] = make_float2(0.f, 0.f);
+                yc[idx] = v;
+            }
+            const pk::Seeds sbd = conv8k_seeds_bd(tw);
+            __syncthreads();
+            conv8k_stage_b(a, sbd);
+            __syncthreads();
+            conv8k_stage_c_fwd(a);
+            __syncthreads();
+            // anti-diagonal sums in the frequency domain: thread = one of the 256 spectrum positions
+            for (int zs = 0; zs < PF_NZ; ++zs) {
+                const int S = S0 - 2 + zs;
+                const int Ia = (S - m + 2) >> 1, Ib = S >> 1;                  // I <= J = S - I, J - I <= m - 1
+                float2 acc = make_float2(0.f, 0.f);
+                for (int I = Ia; I <= Ib; ++I) {
+                    const int J = S - I;
+                    const float2 pr = pk::mul(a[conv8k_blk(I - I_lo, tid)], a[conv8k_blk(J - I_lo, tid)]);
+                    const float w = I == J ? 1.0f / 256.0f : 2.0f / 256.0f;  // the mirrored pair (J, I); 1/256 of the inverse transform
+                    acc = __ffma2_rn(pr, make_float2(w, w), acc);
+                }
+                a[conv8k_blk(PF_NBLK + zs, tid)] = acc;
+            }
+            __syncthreads();
+            conv8k_stage_c_inv(a);
+            __syncthreads();
+            conv8k_stage_d(a, sbd);
+            __syncthreads();
+            // overlap-add of the two anti-diagonals that cover an output, plus the edge triangle of the one pair with J - I = m
+#pragma unroll
+            for (int r = 0; r < PF_R; ++r) {
+                const int64_t n = D0 + tid + ZNT * r - par;                  // index into Cb_y
+                if (n < 0) continue;
+                const int S1 = (int)(n / PF_B), u1 = (int)(n - (int64_t)S1 * PF_B);
+                const float2 z1 = a[conv8k_blk(PF_NBLK + S1 - S0 + 2, u1)], z0 = a[conv8k_blk(PF_NBLK + S1 - S0 + 1, u1 + PF_B)];
+                const int Se = ((S1 - m) & 1) ? S1 - 1 : S1;
+                const int u = (int)(n - (int64_t)Se * PF_B);                   // 0 .. 255
+                const int I = (Se - m) >> 1;
+                const float2 *yi = yc + (I - I_lo) * PF_B, *yj = yc + (I + m - I_lo) * PF_B;
+                const int q_lo = u > PF_B - 1 ? u - (PF_B - 1) : 0, q_hi = (u + 1) >> 1;   // q' < p' = u - q' < B
+                float2 e = make_float2(0.f, 0.f);
+                for (int q = q_lo; q < q_hi; ++q) e = pk::add(e, pk::mul(yi[u - q], yj[q]));
+                accP[r] = pk::add(accP[r], pk::add(pk::add(z1, z0), pk::add(e, e)));
+            }
+        }
+    }
+    // ---- energies E(d) = sum_{k<h} |x[d+k]|^2 over the branches: float64 prefix of the tile's |x|^2 in shared memory ----------
+    __syncthreads();
+    double *pre = reinterpret_cast<double *>(psm);             // pre[k] = sum of |x[D0 + j]|^2, j < k
+    const int cnt = PF_OUT + h;
+    const int per = (cnt + ZNT - 1) / ZNT;
+    {
+        const int k0 = tid * per, k1 = k0 + per < cnt ? k0 + per : cnt;
+        double run = 0.0;
+        for (int k = k0; k < k1; ++k) {
+            const int64_t j = D0 + k;
+            double en = 0.0;
+            if (j < L)
+                for (int b = 0; b < nb; ++b) {
+                    const In t = (reinterpret_cast<const In *>(x) + frame * xfs + (int64_t)b * xbs)[j];
+                    en += (double)t.x * (double)t.x + (double)t.y * (double)t.y;
+                }
+            run += en;
+            pre[k + 1] = run;
+        }
+        double t = run;
+        for (int o = 1; o < 32; o <<= 1) { const double y = shfl_up_f64(t, o); if (lane >= o) t += y; }
+        if (lane == 31) wsum[warp] = t;
+        __syncthreads();
+        double off = t - run;
+        for (int w = 0; w < warp; ++w) off += wsum[w];
+        for (int k = k0; k < k1; ++k) pre[k + 1] += off;
+        if (tid == 0) pre[0] = 0.0;
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < PF_R; ++r) {
+        const int kd = tid + ZNT * r;                          // d - D0
+        const int64_t d = D0 + kd, i = d - h;
+        if (i < 0 || i >= n_out) continue;
+        float2 xs = make_float2(0.f, 0.f);                     // sum over branches of x[d]^2
+        for (int b = 0; b < nb; ++b) {
+            const In t = (reinterpret_cast<const In *>(x) + frame * xfs + (int64_t)b * xbs)[d];
+            const float2 v = make_float2((float)t.x, (float)t.y);
+            xs = pk::add(xs, pk::mul(v, v));
+        }
+        const float pr = 0.5f * (accP[r].x + xs.x), pi = 0.5f * (accP[r].y + xs.y);
+        const double en = pre[kd + h] - pre[kd];
+        const double ee = en > 1e-12 ? en : 1e-12;
+        const int64_t oi = frame * out_stride + i;
+        if (M) M[oi] = (float)(((double)pr * pr + (double)pi * pi) / (ee * ee));
+        if (P) P[oi] = make_float2(pr, pi);
+        if (E) E[oi] = (float)en;
+    }
+}
+
+template <int DT>
+static int launch_park_fft(const ofs_metric_desc *d, const void *x, void *M, void *P, void *E, int64_t n_out, cudaStream_t st)
+{
+    const int h = d->symbol_len / 2;
+    const int tiles = (int)((h + n_out + PF_OUT - 1) / PF_OUT);
+    const int64_t grid = (int64_t)tiles * d->n_frames;
+    OFS_REQUIRE(grid < (1LL << 31), "ofs_park_metric: grid too large");
+    double2 *tw = nullptr;
+    OFS_CUDA(cudaMallocAsync((void **)&tw, (ZF / 2) * (sizeof(double2) + sizeof(float2)), st));
+    park_twiddle_kernel<<<(ZF / 2 + 255) / 256, 256, 0, st>>>(tw);
+    if (int rc = check_launch("park_twiddle_kernel")) return rc;
+    const size_t smem = (size_t)ZFP8 * sizeof(float2) + (size_t)PF_NBLK * PF_B * sizeof(float2);
+    auto kern = park_fft_kernel<DT>;
+    OFS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, ZNT, smem, st>>>(x, d->n_branches, d->n_samples, d->x_frame_stride, d->x_branch_stride, h, n_out, d->out_stride,
+                                           (float *)M, (float2 *)P, (float *)E, tiles, tw);
+    if (int rc = check_launch("park_fft_kernel")) return rc;
+    OFS_CUDA(cudaFreeAsync(tw, st));
+    return OFS_OK;
+}
+
 template <typename T, int DT>
 static int launch_park(const ofs_metric_desc *d, const void *x, void *M, void *P, void *E, int64_t n_out, cudaStream_t st)
 {
     const int h = d->symbol_len / 2;
+    if constexpr (sizeof(T) == 4) {
+        // float32 outputs, h a multiple of 128 up to 1024 (the scripts' N_FFT = 2048): block FFTs; OFS_PARK_DIRECT=1: direct form
+        const char *env = getenv("OFS_PARK_DIRECT");
+        const bool force_direct = env && atoi(env) != 0;
+        if (!d->out_f64 && !force_direct && h % PF_B == 0 && h / PF_B >= 1 && h / PF_B <= 8)
+            return launch_park_fft<DT>(d, x, M, P, E, n_out, st);
+    }
     if (h % 8 == 0 && h >= 8) {
         const int tiles2 = (int)((n_out + QTILE - 1) / QTILE);
         const size_t smem2 = (size_t)(QTILE + 2 * h + 16) * sizeof(Cx<T>);

@@ -135,7 +135,32 @@ int main()
         e2 = std::max(e2, std::abs(xf[(k - 5 + ZF8) % ZF8] - cd(out2[k].x, out2[k].y)));
     }
     printf("conv8k two filters: first rel err %.3e, delayed copy abs err %.3e\n", e1 / scale, e2);
-    const bool ok = maxerr / scale < 2e-6 && een < 1e-5 && e1 / scale < 2e-6 && e2 < 2e-5;
+    // ---- the array as 32 independent 256-point transforms (block-FFT Park kernel): stage B + stage C (forward half) on every
+    //      256-block, position-wise product of two spectra, stage C (inverse half) + stage D: linear convolution of two 128-blocks
+    std::vector<float2> ab(ZFP8, make_float2(0.f, 0.f));
+    std::vector<cd> u0(128), u1(128);
+    for (auto &v : u0) v = cd(nd(rng), nd(rng));
+    for (auto &v : u1) v = cd(nd(rng), nd(rng));
+    for (int e = 0; e < 128; ++e) {
+        ab[conv8k_blk(3, e)] = make_float2((float)u0[e].real(), (float)u0[e].imag());      // slots 3 and 21: both halves of the array
+        ab[conv8k_blk(21, e)] = make_float2((float)u1[e].real(), (float)u1[e].imag());
+    }
+    all_threads([&] { conv8k_stage_b(ab.data(), conv8k_seeds_bd(tw)); });
+    all_threads([&] { conv8k_stage_c_fwd(ab.data()); });
+    for (int f = 0; f < 256; ++f) ab[conv8k_blk(30, f)] = pk::mul(ab[conv8k_blk(3, f)], ab[conv8k_blk(21, f)]);
+    all_threads([&] { conv8k_stage_c_inv(ab.data()); });
+    all_threads([&] { conv8k_stage_d(ab.data(), conv8k_seeds_bd(tw)); });
+    double e3 = 0, sc3 = 0;
+    for (int k = 0; k < 255; ++k) {
+        cd s(0, 0);
+        for (int m = 0; m < 128; ++m)
+            if (k - m >= 0 && k - m < 128) s += cd((float)u0[m].real(), (float)u0[m].imag()) * cd((float)u1[k - m].real(), (float)u1[k - m].imag());
+        const float2 g = ab[conv8k_blk(30, k)];
+        e3 = std::max(e3, std::abs(s - cd(g.x / 256.0, g.y / 256.0)));
+        sc3 = std::max(sc3, std::abs(s));
+    }
+    printf("256-point blocks: linear convolution rel err %.3e\n", e3 / sc3);
+    const bool ok = maxerr / scale < 2e-6 && een < 1e-5 && e1 / scale < 2e-6 && e2 < 2e-5 && e3 / sc3 < 2e-6;
     printf(ok ? "PASS\n" : "FAIL\n");
     return ok ? 0 : 1;
 }

@@ -163,10 +163,20 @@ def run_cases(a, sink, device_index: int = 0):
     if "park" in cases:
         F, n = max(int(64 * a.scale), 2), 1 << 18
         x = synth.make_batch_device(F, n, "sc", seed=9, device=dev, chunk=16)[:, None]
+        import os
+        os.environ["OFS_PARK_DIRECT"] = "0"
         ms = timeit(lambda: engine.park_metric(x, 2048), steps=3, warmup=2)
         nout = n - 2048
-        emit("cfg3 park metric (1024 complex MACs per output, 8x8 register tiles, de-interleaved smem)", ms, F * n, flops=F * nout * 1024 * 8,
-             key="cfg3_park", note=f"{F} streams x {n} c64 (the O(h) direct form: 1024 streams x 1 M would be 8.8e15 flop); FMA-bound (SURVEY 7.3-4); flops = 8 per complex MAC (the sliding energy is no longer recomputed per lag); fp32 peak 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s")
+        emit("cfg3 park metric, block-FFT kernel (band-limited self-convolution: 256-point block transforms summed per anti-diagonal, edge triangles direct)",
+             ms, F * n, key="cfg3_park",
+             note=f"{F} streams x {n} c64, M + P + E out; ~700 flops per output instead of the direct form's 8192 (1024 complex MACs): "
+                  f"{F * nout * 1024 * 8 / (ms * 1e-3) / 1e12:.1f} TFLOP/s direct-form equivalent")
+        os.environ["OFS_PARK_DIRECT"] = "1"
+        msd = timeit(lambda: engine.park_metric(x, 2048), steps=3, warmup=2)
+        os.environ["OFS_PARK_DIRECT"] = "0"
+        emit("cfg3 park metric, direct O(h) kernel (1024 complex MACs per output, 8x8 register tiles, de-interleaved smem; OFS_PARK_DIRECT=1)", msd, F * n,
+             flops=F * nout * 1024 * 8, key="cfg3_park_direct",
+             note=f"{F} streams x {n} c64; FMA-bound (SURVEY 7.3-4); flops = 8 per complex MAC; fp32 peak 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s")
         del x
     if "zc" in cases:
         # cfg 4 (single root): overlap-save matched filter + zc_v2 streaming detection + gate FSM

@@ -229,6 +229,24 @@ __global__ void __launch_bounds__(QNT2) park_kernel_v2(const void *x, int nb, in
 // transforms (stage B + half of stage C): 16 blocks of samples and 14 anti-diagonals per parity pass.  Checked against the
 // float64 oracle and against the direct kernel (tests/test_gpu_park.py); OFS_PARK_DIRECT=1 forces the direct kernel.
 constexpr int PF_B = 128, PF_T = 12, PF_OUT = PF_T * PF_B, PF_NZ = PF_T + 2, PF_NBLK = 16, PF_R = PF_OUT / ZNT;
+constexpr int PF_BS = 272;                 // a 256-block and its padding (one element per 16) in the array of conv8k.cuh
+// Complex multiply-accumulate split over two packed accumulators, two FFMA2 per term and nothing else:
+//   sum a w = A + (-1, 1) (.) B,   A += a (.) (w.x, w.x),   B += (a.y, a.x) (.) (w.y, w.y)
+// (the broadcasts and the swizzle are operand modifiers; the sign pattern is applied once, after the loop)
+struct ParkAcc {
+    float2 A, B;
+    __device__ __forceinline__ void zero() { A = B = make_float2(0.f, 0.f); }
+    __device__ __forceinline__ void mac(float2 a, float2 w)
+    {
+        A = __ffma2_rn(a, make_float2(w.x, w.x), A);
+        B = __ffma2_rn(make_float2(a.y, a.x), make_float2(w.y, w.y), B);
+    }
+    __device__ __forceinline__ float2 value() const { return __ffma2_rn(B, make_float2(-1.f, 1.f), A); }
+};
+// Output r of thread t inside the tile (d - D0).  The edge triangle of an output at offset u inside its anti-diagonal has
+// min(u, 255 - u) / 2 terms, and a plain t + 256 r ownership would give a thread the same u six times (warps around u = 128
+// doing eight times the work of those around 0): rotate the assignment by 43 from one group of 256 outputs to the next.
+__device__ __forceinline__ int park_fft_own(int t, int r) { return ((t + 43 * r) & (ZNT - 1)) + ZNT * r; }
 
 __global__ void park_twiddle_kernel(double2 *tw)         // the table layout of fft4096.cuh: double2[2048] then float2[2048]
 {
@@ -266,14 +284,23 @@ __global__ void __launch_bounds__(ZNT, 2) park_fft_kernel(const void *x, int nb,
         const In *xb = reinterpret_cast<const In *>(x) + frame * xfs + (int64_t)b * xbs;
         for (int par = 0; par < 2; ++par) {
             __syncthreads();
-            for (int idx = tid; idx < PF_NBLK * PF_B; idx += ZNT) {
-                const int s = idx >> 7, pp = idx & (PF_B - 1);
-                const int64_t p = (int64_t)(I_lo + s) * PF_B + pp, j = 2 * p + par;
-                float2 v = make_float2(0.f, 0.f);
-                if (p >= 0 && j < L) { const In t = xb[j]; v = make_float2((float)t.x, (float)t.y); }
-                a[conv8k_blk(s, pp)] = v;
-                a[conv8k_blk(s, PF_B + pp)] = make_float2(0.f, 0.f);
-                yc[idx] = v;
+            {
+                // thread = sample pp (+128) of blocks s0, s0 + 2, ...: 8 independent loads in flight, then the stores
+                const int pp = tid & (PF_B - 1), s0 = tid >> 7;
+                float2 v[PF_NBLK / 2];
+#pragma unroll
+                for (int k = 0; k < PF_NBLK / 2; ++k) {
+                    const int64_t p = (int64_t)(I_lo + s0 + 2 * k) * PF_B + pp, j = 2 * p + par;
+                    v[k] = make_float2(0.f, 0.f);
+                    if (p >= 0 && j < L) { const In t = xb[j]; v[k] = make_float2((float)t.x, (float)t.y); }
+                }
+#pragma unroll
+                for (int k = 0; k < PF_NBLK / 2; ++k) {
+                    const int sl = s0 + 2 * k;
+                    a[sl * PF_BS + pp + (pp >> 4)] = v[k];
+                    a[sl * PF_BS + PF_B + pp + ((PF_B + pp) >> 4)] = make_float2(0.f, 0.f);
+                    yc[sl * PF_B + pp] = v[k];
+                }
             }
             const pk::Seeds sbd = conv8k_seeds_bd(tw);
             __syncthreads();
@@ -282,17 +309,26 @@ __global__ void __launch_bounds__(ZNT, 2) park_fft_kernel(const void *x, int nb,
             conv8k_stage_c_fwd(a);
             __syncthreads();
             // anti-diagonal sums in the frequency domain: thread = one of the 256 spectrum positions
-            for (int zs = 0; zs < PF_NZ; ++zs) {
-                const int S = S0 - 2 + zs;
-                const int Ia = (S - m + 2) >> 1, Ib = S >> 1;                  // I <= J = S - I, J - I <= m - 1
-                float2 acc = make_float2(0.f, 0.f);
-                for (int I = Ia; I <= Ib; ++I) {
-                    const int J = S - I;
-                    const float2 pr = pk::mul(a[conv8k_blk(I - I_lo, tid)], a[conv8k_blk(J - I_lo, tid)]);
-                    const float w = I == J ? 1.0f / 256.0f : 2.0f / 256.0f;  // the mirrored pair (J, I); 1/256 of the inverse transform
-                    acc = __ffma2_rn(pr, make_float2(w, w), acc);
+            {
+                // block s of the first half starts at s * 272 (256 + its padding); the anti-diagonals live in the second half
+                const float2 *xs0 = a + tid + (tid >> 4);
+                float2 *zs0 = a + ZFP + tid + (tid >> 4);
+                for (int zs = 0; zs < PF_NZ; ++zs) {
+                    // pairs (c_lo - k, c_hi + k), k = 0 .. kmax: J - I = 2 k + (S & 1) <= m - 1; every pair but the diagonal one
+                    // (k = 0 of an even S) also stands for its mirror image (J, I):  Z = 2 sum - [S even] X_c^2
+                    const int S = S0 - 2 + zs;
+                    const int c_lo = S >> 1, kmax = (m - 1 - (S & 1)) >> 1;
+                    const float2 *pi = xs0 + (c_lo - I_lo) * PF_BS, *pj = xs0 + (S - c_lo - I_lo) * PF_BS;
+                    const float2 xc = *pi;
+                    ParkAcc pa;
+                    pa.zero();
+#pragma unroll 4
+                    for (int k = 0; k <= kmax; ++k, pi -= PF_BS, pj += PF_BS) pa.mac(*pi, *pj);
+                    float2 acc = pa.value();
+                    acc = pk::add(acc, acc);
+                    if (!(S & 1) && kmax >= 0) acc = pk::sub(acc, pk::mul(xc, xc));
+                    zs0[zs * PF_BS] = __fmul2_rn(acc, make_float2(1.0f / 256.0f, 1.0f / 256.0f));   // 1/256 of the inverse transform
                 }
-                a[conv8k_blk(PF_NBLK + zs, tid)] = acc;
             }
             __syncthreads();
             conv8k_stage_c_inv(a);
@@ -302,17 +338,27 @@ __global__ void __launch_bounds__(ZNT, 2) park_fft_kernel(const void *x, int nb,
             // overlap-add of the two anti-diagonals that cover an output, plus the edge triangle of the one pair with J - I = m
 #pragma unroll
             for (int r = 0; r < PF_R; ++r) {
-                const int64_t n = D0 + tid + ZNT * r - par;                  // index into Cb_y
+                const int64_t n = D0 + park_fft_own(tid, r) - par;          // index into Cb_y
                 if (n < 0) continue;
-                const int S1 = (int)(n / PF_B), u1 = (int)(n - (int64_t)S1 * PF_B);
-                const float2 z1 = a[conv8k_blk(PF_NBLK + S1 - S0 + 2, u1)], z0 = a[conv8k_blk(PF_NBLK + S1 - S0 + 1, u1 + PF_B)];
+                const int S1 = (int)((uint64_t)n >> 7), u1 = (int)(n & (PF_B - 1));       // n >= 0; PF_B = 128
+                const float2 *zb = a + ZFP + (S1 - S0 + 1) * PF_BS;        // anti-diagonal S1 - 1; S1 is the next block
+                const float2 z0 = zb[u1 + PF_B + ((u1 + PF_B) >> 4)], z1 = zb[PF_BS + u1 + (u1 >> 4)];
                 const int Se = ((S1 - m) & 1) ? S1 - 1 : S1;
                 const int u = (int)(n - (int64_t)Se * PF_B);                   // 0 .. 255
                 const int I = (Se - m) >> 1;
-                const float2 *yi = yc + (I - I_lo) * PF_B, *yj = yc + (I + m - I_lo) * PF_B;
+                const float2 *yi = yc + (I - I_lo) * PF_B + u, *yj = yc + (I + m - I_lo) * PF_B;
                 const int q_lo = u > PF_B - 1 ? u - (PF_B - 1) : 0, q_hi = (u + 1) >> 1;   // q' < p' = u - q' < B
-                float2 e = make_float2(0.f, 0.f);
-                for (int q = q_lo; q < q_hi; ++q) e = pk::add(e, pk::mul(yi[u - q], yj[q]));
+                ParkAcc e0, e1;                                               // two independent chains
+                e0.zero(); e1.zero();
+                int q = q_lo;
+                for (; q + 4 <= q_hi; q += 4) {
+                    e0.mac(yi[-q], yj[q]);
+                    e1.mac(yi[-(q + 1)], yj[q + 1]);
+                    e0.mac(yi[-(q + 2)], yj[q + 2]);
+                    e1.mac(yi[-(q + 3)], yj[q + 3]);
+                }
+                for (; q < q_hi; ++q) e0.mac(yi[-q], yj[q]);
+                const float2 e = pk::add(e0.value(), e1.value());
                 accP[r] = pk::add(accP[r], pk::add(pk::add(z1, z0), pk::add(e, e)));
             }
         }
@@ -324,18 +370,21 @@ __global__ void __launch_bounds__(ZNT, 2) park_fft_kernel(const void *x, int nb,
     const int per = (cnt + ZNT - 1) / ZNT;
     {
         const int k0 = tid * per, k1 = k0 + per < cnt ? k0 + per : cnt;
-        double run = 0.0;
-        for (int k = k0; k < k1; ++k) {
-            const int64_t j = D0 + k;
-            double en = 0.0;
-            if (j < L)
+        double en[10];                                         // per <= (1536 + 1024) / 256 = 10
+#pragma unroll
+        for (int q = 0; q < 10; ++q) {
+            en[q] = 0.0;
+            const int64_t j = D0 + k0 + q;
+            if (k0 + q < k1 && j < L)
                 for (int b = 0; b < nb; ++b) {
                     const In t = (reinterpret_cast<const In *>(x) + frame * xfs + (int64_t)b * xbs)[j];
-                    en += (double)t.x * (double)t.x + (double)t.y * (double)t.y;
+                    en[q] += (double)t.x * (double)t.x + (double)t.y * (double)t.y;
                 }
-            run += en;
-            pre[k + 1] = run;
         }
+        double run = 0.0;
+#pragma unroll
+        for (int q = 0; q < 10; ++q)
+            if (k0 + q < k1) { run += en[q]; pre[k0 + q + 1] = run; }
         double t = run;
         for (int o = 1; o < 32; o <<= 1) { const double y = shfl_up_f64(t, o); if (lane >= o) t += y; }
         if (lane == 31) wsum[warp] = t;
@@ -348,7 +397,7 @@ __global__ void __launch_bounds__(ZNT, 2) park_fft_kernel(const void *x, int nb,
     }
 #pragma unroll
     for (int r = 0; r < PF_R; ++r) {
-        const int kd = tid + ZNT * r;                          // d - D0
+        const int kd = park_fft_own(tid, r);                   // d - D0
         const int64_t d = D0 + kd, i = d - h;
         if (i < 0 || i >= n_out) continue;
         float2 xs = make_float2(0.f, 0.f);                     // sum over branches of x[d]^2

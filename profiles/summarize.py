@@ -34,6 +34,11 @@ def raw(rep):
 
 def main():
     tag, cmd = "stripe", "python bench.py ..."
+    frames = samples = 0
+    if "--frames" in sys.argv:
+        i = sys.argv.index("--frames"); frames = int(sys.argv[i + 1]); del sys.argv[i:i + 2]
+    if "--samples" in sys.argv:
+        i = sys.argv.index("--samples"); samples = int(sys.argv[i + 1]); del sys.argv[i:i + 2]
     if "--tag" in sys.argv:
         i = sys.argv.index("--tag"); tag = sys.argv[i + 1]; del sys.argv[i:i + 2]
     if "--cmd" in sys.argv:
@@ -106,6 +111,10 @@ def main():
         lines.append("")
     (HERE / f"r{rnd}_{tag}_ncu.md").write_text("\n".join(lines))
     if traffic:
+        # the capture's geometry (bench.py scales the figure to its own frame count): --frames / --samples, else what the file held
+        old = json.loads((HERE / "traffic.json").read_text()) if (HERE / "traffic.json").exists() else {}
+        traffic["frames"] = frames or old.get("frames", 1024)
+        traffic["samples_per_frame"] = samples or old.get("samples_per_frame", 262144)
         (HERE / "traffic.json").write_text(json.dumps(traffic, indent=1))
     if len(sys.argv) > 3:
         rows = [r for r in csv.reader(open(sys.argv[3])) if r]

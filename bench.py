@@ -378,6 +378,23 @@ def main() -> None:
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * Fe * n * e_steps / float(te.item()) / 1e6
+    # the same call without the metric rows going back (M_host = None: records only -- what a caller that only wants timing and
+    # CFO does); reported next to the headline figure, which keeps reading M back
+    timing_with_m = rec_h["timing"].copy()               # rec_h views the pinned record buffer the next calls overwrite
+    rh.zero_()
+    hs.run(xh, None, rh, **kw)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        rec_ro = hs.run(xh, None, rh, **kw)
+    torch.cuda.synchronize()
+    tro = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tro, op=dist.ReduceOp.MAX)
+    e2e_records_only = world * Fe * n * e_steps / float(tro.item()) / 1e6
+    ro_match = bool((rec_ro["timing"] == timing_with_m).all())
     # what the box can move at most: the same pinned buffers through plain copies, all ranks at once (H2D of x alone, and H2D of x
     # with D2H of M on a second stream) -- the ceiling e2e is judged against (profiles/r2_e2e_ceiling_n{2,8}.json: the host side
     # gives 55 GB/s to one GPU alone and 184 GB/s to eight at once)
@@ -414,6 +431,8 @@ def main() -> None:
            "frames_per_step": Fe, "steps": e_steps, "records_match_device_path": e2e_match,
            "GBps_both_directions": e2e_gbps, "host_link_ceiling": ceiling,
            "fraction_of_bidirectional_ceiling": e2e_gbps / ceiling["h2d_plus_d2h_GBps"],
+           "records_only": {"value": e2e_records_only, "unit": "Msamples/s", "d2h_bytes_per_step": Fe * engine.REC_BYTES,
+                            "records_equal": ro_match, "what": "same call with M_host = NULL: only the 32-byte records come back"},
            "api": "ofs_sync_host (pinned host x -> M + records in host memory)"}
 
     # ---- CPU baseline: the oracle port on a bounded sample of the same workload (rank 0, N = 1 only)

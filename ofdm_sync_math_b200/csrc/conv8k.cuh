@@ -140,6 +140,9 @@ __device__ __forceinline__ void conv8k_stage_a(float2 *a, const pk::Seeds &sd, f
 }
 
 // Stage B: second forward pass of both halves (inside each block of 256: stride 16, twiddle W256^(n0 k1))
+// (H0 / H1: which halves of the array to process -- the Park kernel transforms its sample blocks, which live in the first half,
+// forward only and its anti-diagonals, in the second half, backward only)
+template <bool H0 = true, bool H1 = true>
 __device__ __forceinline__ void conv8k_stage_b(float2 *a, const pk::Seeds &sd)
 {
     const int t = threadIdx.x, k0 = t >> 4, n0 = t & 15;
@@ -147,6 +150,7 @@ __device__ __forceinline__ void conv8k_stage_b(float2 *a, const pk::Seeds &sd)
     pk::powers(sd, w);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
+        if ((h == 0 && !H0) || (h == 1 && !H1)) continue;
         float2 *ah = a + h * ZFP + zpad(k0 * 256 + n0);         // + q * 17: zpad(k0 * 256 + q * 16 + n0), n0 < 16
         float2 v[16];
 #pragma unroll
@@ -209,11 +213,13 @@ __device__ __forceinline__ void conv8k_stage_c(float2 *a, const float2 *Gp, cons
 // 256-element block of the array (the last two passes of the 4096-point transforms work inside such blocks), each spectrum in
 // the same (digit-reversed) order; conv8k_stage_c_inv followed by stage D is the inverse (unscaled: x 256), natural order
 // out.  The block-FFT Park kernel (park.cu) uses the array as 32 independent 256-point transforms.
+template <bool H0 = true, bool H1 = true>
 __device__ __forceinline__ void conv8k_stage_c_fwd(float2 *a)
 {
     const int t = threadIdx.x;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
+        if ((h == 0 && !H0) || (h == 1 && !H1)) continue;
         float2 *ah = a + h * ZFP + t * 17;
         float2 v[16];
 #pragma unroll
@@ -223,11 +229,13 @@ __device__ __forceinline__ void conv8k_stage_c_fwd(float2 *a)
         for (int q = 0; q < 16; ++q) ah[q] = v[q];
     }
 }
+template <bool H0 = true, bool H1 = true>
 __device__ __forceinline__ void conv8k_stage_c_inv(float2 *a)
 {
     const int t = threadIdx.x;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
+        if ((h == 0 && !H0) || (h == 1 && !H1)) continue;
         float2 *ah = a + h * ZFP + t * 17;
         float2 v[16];
 #pragma unroll
@@ -264,6 +272,7 @@ __device__ __forceinline__ void conv8k_unstash(float2 *a, const float2 *stash)
 }
 
 // Stage D: second inverse pass of both halves
+template <bool H0 = true, bool H1 = true>
 __device__ __forceinline__ void conv8k_stage_d(float2 *a, const pk::Seeds &sd)
 {
     const int t = threadIdx.x, k0 = t >> 4, n0 = t & 15;
@@ -271,6 +280,7 @@ __device__ __forceinline__ void conv8k_stage_d(float2 *a, const pk::Seeds &sd)
     pk::powers(sd, w);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
+        if ((h == 0 && !H0) || (h == 1 && !H1)) continue;
         float2 *ah = a + h * ZFP + zpad(k0 * 256 + n0);
         float2 v[16];
 #pragma unroll

@@ -304,9 +304,9 @@ __global__ void __launch_bounds__(ZNT, 2) park_fft_kernel(const void *x, int nb,
             }
             const pk::Seeds sbd = conv8k_seeds_bd(tw);
             __syncthreads();
-            conv8k_stage_b(a, sbd);
+            conv8k_stage_b<true, false>(a, sbd);                        // the sample blocks (first half of the array) forward
             __syncthreads();
-            conv8k_stage_c_fwd(a);
+            conv8k_stage_c_fwd<true, false>(a);
             __syncthreads();
             // anti-diagonal sums in the frequency domain: thread = one of the 256 spectrum positions
             {
@@ -331,9 +331,9 @@ __global__ void __launch_bounds__(ZNT, 2) park_fft_kernel(const void *x, int nb,
                 }
             }
             __syncthreads();
-            conv8k_stage_c_inv(a);
+            conv8k_stage_c_inv<false, true>(a);                         // the anti-diagonals (second half) back
             __syncthreads();
-            conv8k_stage_d(a, sbd);
+            conv8k_stage_d<false, true>(a, sbd);
             __syncthreads();
             // overlap-add of the two anti-diagonals that cover an output, plus the edge triangle of the one pair with J - I = m
 #pragma unroll

@@ -92,7 +92,11 @@ int ofs_metric(const ofs_metric_desc *d, const void *x, void *M, void *P, void *
                float *chunk_max, int64_t cm_stride, void *stream);
 
 /* Park metric -- park.py:64-114.  n = L - 2*(N/2) outputs per frame (0 if L < N+1): M, P, E
- * (ds = h + arange(n) is implicit).  in/out dtypes as in ofs_metric_desc (kind ignored). */
+ * (ds = h + arange(n) is implicit).  in/out dtypes as in ofs_metric_desc (kind ignored).
+ * complex64 / int16-IQ input with float32 outputs and h = N/2 a multiple of 128 up to 1024 runs the block-FFT kernel
+ * (band-limited self-convolution by 256-point block transforms, |d M| <= 1e-4 max M against float64); everything else, and
+ * everything when the environment variable OFS_PARK_DIRECT is set to a non-zero value, the direct O(h) kernel
+ * (float64 accumulation for complex128 input: the drop-in path, 1e-11). */
 int ofs_park_metric(const ofs_metric_desc *d, const void *x, void *M, void *P, void *E, void *stream);
 
 /* Detectors on metric arrays (one row per frame; float32 or float64 rows) ----------------------- */
@@ -289,7 +293,9 @@ int ofs_zc_freq_metric_f32(const void *x_c64, int64_t n_frames, int64_t n, int32
  * filters of the capture (8192-point overlap-save blocks, one forward and two inverse FFTs per block), and the in-band energy
  * sum|bins|^2 (:95) follows E(o+1) = E(o) + 2 Re(conj(sum bins(o)) d(o)) + nbins |d(o)|^2, d(o) = x[o+cp+n_fft] - x[o+cp],
  * anchored by a direct DFT and carried in float64.  ~2.5x ofs_zc_freq_metric_f32.  Arguments as ofs_zc_freq_metric_f32 plus
- * the branch count. */
+ * the branch count.  Consecutive 8192-sample blocks of a capture share one CTA and one anchor unless there are too few
+ * captures to fill the GPU; the environment variable OFS_ZQF_BLOCKS_PER_ITEM overrides the split (tests use it to force
+ * both the per-block anchor and the whole-capture carry). */
 int ofs_zc_freq_metric_fft(const void *x_c64, int64_t n_frames, int32_t n_branches, int64_t n, int32_t n_fft, int32_t cp, const int32_t *bins,
                            const void *templ_c64, int32_t nbins, double templ_energy, float *metric,
                            int64_t out_stride, void *stream);

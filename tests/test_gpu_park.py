@@ -79,3 +79,24 @@ def test_park_fft_equals_direct_kernel_on_a_batch(monkeypatch):
     assert float((Mf - Md).abs().max()) <= 2e-5 * float(Md.max())
     assert torch.equal(Mf.argmax(dim=1), Md.argmax(dim=1))
     assert float((Ef - Ed).abs().max()) <= 2e-6 * float(Ed.max())
+
+
+def test_park_fft_degenerate_inputs(monkeypatch):
+    """All-zero frames (M = 0, no NaN), frames shorter than one tile, the shortest frame with an output (L = N + 1), and exact
+    invariance of M under scaling by a power of two."""
+    from ofdm_sync_math_b200 import engine
+    monkeypatch.setenv("OFS_PARK_DIRECT", "0")
+    z = torch.zeros((2, 1, 5000), dtype=torch.complex64, device="cuda")
+    M, P, E = engine.park_metric(z, 2048)
+    assert bool(torch.isfinite(M).all()) and float(M.abs().max()) == 0.0 and float(E.abs().max()) == 0.0
+    for n in (2049, 2050, 2100, 3583, 3584, 3585):
+        x = _capture(max(n, 5200), n)[:, :n]
+        M, P, E = engine.park_metric(torch.as_tensor(x).cuda()[None], 2048)
+        assert M.shape[-1] == n - 2048
+        ds, Mo, Po, Eo = orc.park_streaming_metric(x.astype(np.complex128), 2048)
+        assert np.abs(M[0].cpu().numpy() - Mo).max() <= 1e-4 * max(Mo.max(), 1e-6)
+        assert np.abs(E[0].cpu().numpy() - Eo).max() <= 2e-6 * Eo.max()
+    x = torch.as_tensor(_capture(30000, 5)).cuda()[None]
+    M1, _, _ = engine.park_metric(x, 2048)
+    M2, _, _ = engine.park_metric(x * 32.0, 2048)
+    assert torch.equal(M1, M2)

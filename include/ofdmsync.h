@@ -288,15 +288,15 @@ int ofs_zc_freq_metric_f32(const void *x_c64, int64_t n_frames, int64_t n, int32
                            int64_t out_stride, void *stream);
 
 /* zc_freq.compute_frequency_metric (zc_freq.py:62-99) in FFT form, float32 (|d metric| <= 1e-4 * max(metric)), complex64
- * captures [frames][branches][n] (branches summed as at :88-97: one inverse transform for the sum of their correlations, one
+ * or int16-IQ captures [frames][branches][n] (branches summed as at :88-97: one inverse transform for the sum of their correlations, one
  * energy path each), n_fft <= 2048, nbins <= 64: np.vdot(template, bins) (:94) and sum(bins) are two n_fft-tap matched
  * filters of the capture (8192-point overlap-save blocks, one forward and two inverse FFTs per block), and the in-band energy
  * sum|bins|^2 (:95) follows E(o+1) = E(o) + 2 Re(conj(sum bins(o)) d(o)) + nbins |d(o)|^2, d(o) = x[o+cp+n_fft] - x[o+cp],
  * anchored by a direct DFT and carried in float64.  ~2.5x ofs_zc_freq_metric_f32.  Arguments as ofs_zc_freq_metric_f32 plus
- * the branch count.  Consecutive 8192-sample blocks of a capture share one CTA and one anchor unless there are too few
+ * the input dtype (OFS_C64 / OFS_IQ16) and the branch count.  Consecutive 8192-sample blocks of a capture share one CTA and one anchor unless there are too few
  * captures to fill the GPU; the environment variable OFS_ZQF_BLOCKS_PER_ITEM overrides the split (tests use it to force
  * both the per-block anchor and the whole-capture carry). */
-int ofs_zc_freq_metric_fft(const void *x_c64, int64_t n_frames, int32_t n_branches, int64_t n, int32_t n_fft, int32_t cp, const int32_t *bins,
+int ofs_zc_freq_metric_fft(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_branches, int64_t n, int32_t n_fft, int32_t cp, const int32_t *bins,
                            const void *templ_c64, int32_t nbins, double templ_energy, float *metric,
                            int64_t out_stride, void *stream);
 

@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(ZNT, 2) zc_mf8k_kernel(const void *x, int64_t 
 // on exact silence).
 constexpr int ZQF_THREADS = ZNT;
 struct ZcFreqFftParams {
-    const float2 *x;
+    const void *x;             // complex64 or int16 IQ, [frames][nb][n]
     int64_t n, n_off, mstride;
     int N, cp, nbins, nb, blocks_per_cap, blocks_per_item, items_per_cap;     // nb: receive branches, [frames][nb][n]
     int64_t n_items;
@@ -340,8 +340,15 @@ struct ZcFreqFftParams {
 // the block function is out of line (see there); it reads the launch parameters from this shared copy (one LDS, no registers
 // held across the FFT stages) -- through a reference to the kernel's parameter block every access was a generic global load
 __shared__ ZcFreqFftParams g_zqf;
+// sample as float2 from complex64 or int16-IQ rows
+template <typename In> __device__ __forceinline__ float2 zq_ld(const In *p)
+{
+    const In s = __ldg(p);
+    return make_float2((float)s.x, (float)s.y);
+}
 
-__device__ double zqf_anchor(const float2 *xl, int64_t avail, int N, const int *bins, int nbins, const double2 *tw, float2 *red, double *dred)
+template <typename In>
+__device__ double zqf_anchor(const In *xl, int64_t avail, int N, const int *bins, int nbins, const double2 *tw, float2 *red, double *dred)
 {
     const int tid = threadIdx.x, j = tid & 63, part = tid >> 6;
     const int chunk = (N + 3) >> 2, m0 = part * chunk, m1 = m0 + chunk < N ? m0 + chunk : N;
@@ -365,7 +372,7 @@ __device__ double zqf_anchor(const float2 *xl, int64_t avail, int N, const int *
             if (mb + 32 <= m1 && mb + 32 <= avail) {                          // whole group inside the window and the capture
 #pragma unroll 8
                 for (int u = 0; u < 32; u += 2) {
-                    const float2 v0 = __ldg(xl + mb + u), v1 = __ldg(xl + mb + u + 1);
+                    const float2 v0 = zq_ld(xl + mb + u), v1 = zq_ld(xl + mb + u + 1);
                     const float4 v = make_float4(v0.x, v0.y, v1.x, v1.y);
                     acc = __ffma2_rn(make_float2(v.x, v.x), w, acc);
                     acc = __ffma2_rn(make_float2(v.y, v.y), make_float2(-w.y, w.x), acc);
@@ -377,7 +384,7 @@ __device__ double zqf_anchor(const float2 *xl, int64_t avail, int N, const int *
             } else {
                 for (int u = 0; u < 32 && mb + u < m1; ++u) {
                     const int m = mb + u;
-                    const float2 v = m < avail ? __ldg(xl + m) : make_float2(0.f, 0.f);
+                    const float2 v = m < avail ? zq_ld(xl + m) : make_float2(0.f, 0.f);
                     acc.x = fmaf(v.x, w.x, fmaf(-v.y, w.y, acc.x));
                     acc.y = fmaf(v.x, w.y, fmaf(v.y, w.x, acc.y));
                     w = pk::mul(w, ws);
@@ -406,14 +413,15 @@ __device__ double zqf_anchor(const float2 *xl, int64_t avail, int N, const int *
 // S path of one branch of one block: forward transform, both products (S back to shared memory, Y into / onto the stash),
 // inverse transform of S, increments of E into se (added to the previous branches' when `add`).  Out of line for the same
 // reason as zqf_block: called once per branch, its 100+ registers per stage do not compete with the caller's state.
-__device__ __noinline__ void zqf_spath(float2 *a, float *se, const float2 *xb, int64_t availl, unsigned o_cnt, bool add)
+template <typename In>
+__device__ __noinline__ void zqf_spath(float2 *a, float *se, const In *xb, int64_t availl, unsigned o_cnt, bool add)
 {
     const ZcFreqFftParams &p = g_zqf;
     const int tid = threadIdx.x;
     const int N = p.N, V = ZF8 - N + 1;
     const float2 w0 = __ldg(p.tw8 + tid);
     const unsigned m_cnt = (unsigned)(availl < ZF8 ? availl : ZF8);
-    auto ldx = [&](int m) { return (unsigned)m < m_cnt ? __ldg(xb + m) : make_float2(0.f, 0.f); };
+    auto ldx = [&](int m) { return (unsigned)m < m_cnt ? zq_ld(xb + m) : make_float2(0.f, 0.f); };
     // twiddle seeds are fetched ahead of the barrier that precedes their stage
     pk::Seeds sd = conv8k_seeds_ae(p.tw);
     conv8k_stage_a(a, sd, w0, ldx, [](int, float) {});
@@ -436,7 +444,7 @@ __device__ __noinline__ void zqf_spath(float2 *a, float *se, const float2 *xb, i
                        DPair d;
                        d.hi = d.lo = make_float2(0.f, 0.f);
                        if ((unsigned)i < o_cnt) {
-                           if ((int64_t)(i + N) < availl) d.hi = __ldg(xb + i + N);      // i + N may be sample 8192: past the block, inside the capture
+                           if ((int64_t)(i + N) < availl) d.hi = zq_ld(xb + i + N);      // i + N may be sample 8192: past the block, inside the capture
                            d.lo = ldx(i);
                        }
                        return d;
@@ -456,14 +464,15 @@ __device__ __noinline__ void zqf_spath(float2 *a, float *se, const float2 *xb, i
 // the 100+ registers each FFT stage wants.  Branches (zc_freq.py:88-97): Y is linear in the samples, so the branches' Y
 // products are summed in the stash (one inverse transform for all of them); E is not, so every branch runs its own S path
 // and the increments add up in se.
+template <typename In>
 __device__ __noinline__ double zqf_block(float2 *a, float *se, float2 *red, double *wtot, float *wmax, double *dred,
-                                        const float2 *xc, float *mrow, int b, double Eb, float *emax_io)
+                                        const In *xc, float *mrow, int b, double Eb, float *emax_io)
 {
     const ZcFreqFftParams &p = g_zqf;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = p.N, V = ZF8 - N + 1;
     const int64_t o0 = (int64_t)b * V;                    // first offset of the block; local sample m = x[cp + o0 + m]
-    const float2 *xl = xc + p.cp + o0;
+    const In *xl = xc + p.cp + o0;
     const int64_t availl = p.n - p.cp - o0;
     const int64_t left = p.n_off - o0;
     const unsigned o_cnt = (unsigned)(left < V ? left : V);
@@ -552,8 +561,10 @@ __device__ __noinline__ double zqf_block(float2 *a, float *se, float2 *red, doub
     return Enext;
 }
 
+template <int DT>
 __global__ void __launch_bounds__(ZQF_THREADS, 2) zc_freq_fft_kernel(const __grid_constant__ ZcFreqFftParams p)
 {
+    using In = typename InT<DT>::type;
     extern __shared__ __align__(16) unsigned char zsm[];
     float2 *a = reinterpret_cast<float2 *>(zsm);                                   // ZFP8
     float *se = reinterpret_cast<float *>(zsm + (size_t)ZFP8 * sizeof(float2));     // se[spad(i)] = E(first offset of the block + i)
@@ -569,7 +580,7 @@ __global__ void __launch_bounds__(ZQF_THREADS, 2) zc_freq_fft_kernel(const __gri
         const int64_t cap = item / p.items_per_cap;
         const int b0 = (int)(item % p.items_per_cap) * p.blocks_per_item;
         const int b1 = b0 + p.blocks_per_item < p.blocks_per_cap ? b0 + p.blocks_per_item : p.blocks_per_cap;
-        const float2 *xc = p.x + cap * p.nb * p.n;
+        const In *xc = reinterpret_cast<const In *>(p.x) + cap * p.nb * p.n;
         __syncthreads();
         // E at the item's first offset, directly (summed over the branches)
         double Eb = 0.0;
@@ -902,12 +913,13 @@ OFS_API int ofs_zc_freq_metric(const void *x, int32_t in_dtype, int64_t n_frames
     return check_launch("zc_freq_kernel");
 }
 
-OFS_API int ofs_zc_freq_metric_fft(const void *x_c64, int64_t n_frames, int32_t n_branches, int64_t n, int32_t n_fft, int32_t cp, const int32_t *bins,
+OFS_API int ofs_zc_freq_metric_fft(const void *x, int32_t in_dtype, int64_t n_frames, int32_t n_branches, int64_t n, int32_t n_fft, int32_t cp, const int32_t *bins,
                                    const void *templ_c64, int32_t nbins, double templ_energy, float *metric, int64_t out_stride,
                                    void *stream_)
 {
     OFS_TRACE();
-    OFS_REQUIRE(x_c64 && bins && templ_c64 && metric && templ_energy > 0.0, "ofs_zc_freq_metric_fft: bad arguments");
+    OFS_REQUIRE(x && bins && templ_c64 && metric && templ_energy > 0.0, "ofs_zc_freq_metric_fft: bad arguments");
+    OFS_REQUIRE(in_dtype == OFS_C64 || in_dtype == OFS_IQ16, "ofs_zc_freq_metric_fft: complex64 or int16-IQ captures");
     OFS_REQUIRE(n_fft >= 2 && n_fft <= 2048 && cp >= 0, "ofs_zc_freq_metric_fft: n_fft must be 2..2048");
     OFS_REQUIRE(nbins >= 1 && nbins <= 64, "ofs_zc_freq_metric_fft: nbins <= 64");
     OFS_REQUIRE(n_branches >= 1 && n_branches <= 64, "ofs_zc_freq_metric_fft: 1..64 branches");
@@ -951,12 +963,13 @@ OFS_API int ofs_zc_freq_metric_fft(const void *x_c64, int64_t n_frames, int32_t 
     zc_spectrum8k_kernel<<<1, ZNT, ZFP8 * sizeof(double2), stream>>>(ref + n_fft, n_fft, tw, tw8d, Gp + ZF8, rn + 1);
     if (int rc = check_launch("zc_spectrum8k_kernel")) return rc;
     count_launch(5);
-    p.x = reinterpret_cast<const float2 *>(x_c64); p.n = n; p.n_off = n_off; p.mstride = out_stride;
+    p.x = x; p.n = n; p.n_off = n_off; p.mstride = out_stride;
     p.N = n_fft; p.cp = cp; p.nbins = nbins; p.nb = n_branches; p.bins = bins; p.tw = tw; p.tw8 = tw8f; p.GpY = Gp; p.GpS = Gp + ZF8; p.stash = stash;
     p.templ_energy = (float)templ_energy; p.metric = metric;
     const size_t smem = (size_t)ZFP8 * sizeof(float2) + (size_t)(ZF8 + ZF8 / 32 + 8) * sizeof(float);
-    OFS_CUDA(cudaFuncSetAttribute(zc_freq_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    zc_freq_fft_kernel<<<grid, ZQF_THREADS, smem, stream>>>(p);
+    auto kern = in_dtype == OFS_C64 ? zc_freq_fft_kernel<OFS_C64> : zc_freq_fft_kernel<OFS_IQ16>;
+    OFS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, ZQF_THREADS, smem, stream>>>(p);
     if (int rc = check_launch("zc_freq_fft_kernel")) return rc;
     OFS_CUDA(cudaFreeAsync(tw, stream)); OFS_CUDA(cudaFreeAsync(tw8d, stream)); OFS_CUDA(cudaFreeAsync(tw8f, stream));
     OFS_CUDA(cudaFreeAsync(ref, stream)); OFS_CUDA(cudaFreeAsync(Gp, stream)); OFS_CUDA(cudaFreeAsync(rn, stream));

@@ -764,14 +764,17 @@ def zc_freq_metric(rx, bin_indices, template_bins, template_energy: float, n_fft
     if n_off <= 0:
         raise ValueError("Received stream is shorter than a single OFDM symbol.")     # zc_freq.py:76-78
     if fast:
-        if code != L.OFS_C64 or out_f64 or (B != 1 and fast != "fft"):
-            raise L.OfsError("zc_freq_metric(fast=...) takes complex64 captures (one branch; any number with fast='fft') and returns float32")
+        if fast == "fft":
+            if code == L.OFS_C128 or out_f64:
+                raise L.OfsError("zc_freq_metric(fast='fft') takes complex64 or int16-IQ captures and returns float32")
+        elif code != L.OFS_C64 or out_f64 or B != 1:
+            raise L.OfsError("zc_freq_metric(fast=...) takes complex64 single-branch captures (fast='fft': any branch count, int16 IQ too) and returns float32")
         k = np.mod(np.asarray(bin_indices, dtype=np.int64), n_fft).astype(np.int32)
         bins = torch.as_tensor(k).to(x.device)
         t = torch.as_tensor(np.ascontiguousarray(np.asarray(template_bins, dtype=np.complex64))).to(x.device)
         out = torch.empty((F, n_off), dtype=torch.float32, device=x.device)
         if fast == "fft":
-            L.check(L.lib().ofs_zc_freq_metric_fft(_ptr(x), C.c_int64(F), int(B), C.c_int64(n), int(n_fft), int(cp), _ptr(bins), _ptr(t),
+            L.check(L.lib().ofs_zc_freq_metric_fft(_ptr(x), code, C.c_int64(F), int(B), C.c_int64(n), int(n_fft), int(cp), _ptr(bins), _ptr(t),
                                                    int(k.size), C.c_double(float(template_energy)), _ptr(out), C.c_int64(n_off),
                                                    _stream()), "ofs_zc_freq_metric_fft")
             return out

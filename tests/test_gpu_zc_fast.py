@@ -273,3 +273,21 @@ def test_zc_freq_fft_form_degenerate_inputs():
     ok = E >= 0.01 * np.median(E)
     assert np.abs(m3 - ref)[ok].max() <= 1e-4 * ref.max()
     assert np.abs(m3 - ref).max() <= 1e-2 * ref.max()
+
+
+def test_zc_freq_fft_form_int16_iq_two_branches():
+    """int16-IQ captures [F, B, n, 2] (the 12-bit ADC format) through the FFT form: same metric as the oracle on the same integers."""
+    from ofdm_sync_math_b200 import engine
+    from ofdm_sync_math_b200.zc import generate_zadoff_chu
+    bi = np.concatenate((np.arange(-31, 0), np.arange(1, 32)))
+    tb = generate_zadoff_chu(25, 62)
+    n = 20000
+    x = np.stack([_pss_capture(n, 800 + b, snr_db=10.0, n_pss=2) for b in range(2)])
+    q = np.round(x / np.abs(x).max() * 2000.0)                      # integer-valued I / Q within 12 bits
+    q = (q.real + 1j * q.imag)
+    iq = np.stack([q.real, q.imag], axis=-1).astype(np.int16)       # [2, n, 2]
+    m = engine.zc_freq_metric(torch.as_tensor(iq).cuda()[None], bi, tb, 62.0, fast="fft").cpu().numpy()[0]
+    mo = orc.compute_frequency_metric(q.astype(np.complex128), bi, tb, 62.0)
+    assert m.shape == mo.shape
+    assert np.abs(m - mo).max() <= 1e-4 * mo.max()
+    assert int(np.argmax(m)) == int(np.argmax(mo))

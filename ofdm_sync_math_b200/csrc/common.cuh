@@ -52,6 +52,19 @@ struct NvtxRange {
 };
 #define OFS_TRACE() ofs::NvtxRange _ofs_trace_range(__func__)
 
+// Stream-ordered scratch allocation that is returned on every exit path (an early `return rc` after a failed launch used to
+// leak the buffers allocated before it).
+struct AsyncBuf {
+    void *p = nullptr;
+    cudaStream_t st = nullptr;
+    AsyncBuf() = default;
+    AsyncBuf(const AsyncBuf &) = delete;
+    AsyncBuf &operator=(const AsyncBuf &) = delete;
+    cudaError_t alloc(size_t bytes, cudaStream_t s) { st = s; return cudaMallocAsync(&p, bytes, s); }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+    ~AsyncBuf() { if (p) cudaFreeAsync(p, st); }
+};
+
 int sm_count();  // multiprocessor count of the CURRENT device (cached per device)
 int current_device();  // cudaGetDevice, clamped to [0, OFS_MAX_DEVICES)
 constexpr int OFS_MAX_DEVICES = 64;

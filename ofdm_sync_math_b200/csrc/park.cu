@@ -423,8 +423,9 @@ static int launch_park_fft(const ofs_metric_desc *d, const void *x, void *M, voi
     const int tiles = (int)((h + n_out + PF_OUT - 1) / PF_OUT);
     const int64_t grid = (int64_t)tiles * d->n_frames;
     OFS_REQUIRE(grid < (1LL << 31), "ofs_park_metric: grid too large");
-    double2 *tw = nullptr;
-    OFS_CUDA(cudaMallocAsync((void **)&tw, (ZF / 2) * (sizeof(double2) + sizeof(float2)), st));
+    AsyncBuf b_tw;                                                        // returned to the pool on every exit path
+    OFS_CUDA(b_tw.alloc((ZF / 2) * (sizeof(double2) + sizeof(float2)), st));
+    double2 *tw = b_tw.as<double2>();
     park_twiddle_kernel<<<(ZF / 2 + 255) / 256, 256, 0, st>>>(tw);
     if (int rc = check_launch("park_twiddle_kernel")) return rc;
     const size_t smem = (size_t)ZFP8 * sizeof(float2) + (size_t)PF_NBLK * PF_B * sizeof(float2);
@@ -432,9 +433,7 @@ static int launch_park_fft(const ofs_metric_desc *d, const void *x, void *M, voi
     OFS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)grid, ZNT, smem, st>>>(x, d->n_branches, d->n_samples, d->x_frame_stride, d->x_branch_stride, h, n_out, d->out_stride,
                                            (float *)M, (float2 *)P, (float *)E, tiles, tw);
-    if (int rc = check_launch("park_fft_kernel")) return rc;
-    OFS_CUDA(cudaFreeAsync(tw, st));
-    return OFS_OK;
+    return check_launch("park_fft_kernel");
 }
 
 template <typename T, int DT>

@@ -778,11 +778,12 @@ OFS_API int ofs_zc_matched_filter(const void *x, int32_t in_dtype, int64_t n_fra
     if (n_frames == 0) return OFS_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     keep_pool_cached();
-    double2 *tw = nullptr, *G = nullptr;
-    double *rn = nullptr;
-    OFS_CUDA(cudaMallocAsync((void **)&tw, (ZF / 2) * (sizeof(double2) + sizeof(float2)), stream));
-    OFS_CUDA(cudaMallocAsync((void **)&G, ZF * sizeof(double2), stream));
-    OFS_CUDA(cudaMallocAsync((void **)&rn, sizeof(double), stream));
+    AsyncBuf b_tw, b_G, b_rn, b_tw8f, b_tw8d, b_G8;                     // returned to the pool on every exit path
+    OFS_CUDA(b_tw.alloc((ZF / 2) * (sizeof(double2) + sizeof(float2)), stream));
+    OFS_CUDA(b_G.alloc(ZF * sizeof(double2), stream));
+    OFS_CUDA(b_rn.alloc(sizeof(double), stream));
+    double2 *tw = b_tw.as<double2>(), *G = b_G.as<double2>();
+    double *rn = b_rn.as<double>();
     zc_twiddle_kernel<<<(ZF / 2 + 255) / 256, 256, 0, stream>>>(tw);
     if (int rc = check_launch("zc_twiddle_kernel")) return rc;
     OFS_CUDA(cudaFuncSetAttribute(zc_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ZFP * sizeof(double2))));
@@ -792,11 +793,11 @@ OFS_API int ofs_zc_matched_filter(const void *x, int32_t in_dtype, int64_t n_fra
     // float32, one branch, captures of several blocks: the 8192-point kernel (75 % useful outputs per block instead of 50 %)
     static const int mf_block = [] { const char *e = getenv("OFS_MF_BLOCK"); return e ? atoi(e) : 8192; }();
     if (!dbl && n_branches == 1 && mf_block == 8192 && n + nr - 1 >= 2 * (ZF8 - nr + 1)) {
-        float2 *tw8f = nullptr, *G8 = nullptr;
-        double2 *tw8d = nullptr;
-        OFS_CUDA(cudaMallocAsync((void **)&tw8f, 256 * sizeof(float2), stream));
-        OFS_CUDA(cudaMallocAsync((void **)&tw8d, 256 * sizeof(double2), stream));
-        OFS_CUDA(cudaMallocAsync((void **)&G8, ZF8 * sizeof(float2), stream));
+        OFS_CUDA(b_tw8f.alloc(256 * sizeof(float2), stream));
+        OFS_CUDA(b_tw8d.alloc(256 * sizeof(double2), stream));
+        OFS_CUDA(b_G8.alloc(ZF8 * sizeof(float2), stream));
+        float2 *tw8f = b_tw8f.as<float2>(), *G8 = b_G8.as<float2>();
+        double2 *tw8d = b_tw8d.as<double2>();
         zc_twiddle8_kernel<<<1, 256, 0, stream>>>(tw8f, tw8d);
         if (int rc = check_launch("zc_twiddle8_kernel")) return rc;
         OFS_CUDA(cudaFuncSetAttribute(zc_spectrum8k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ZFP8 * sizeof(double2))));
@@ -823,10 +824,7 @@ OFS_API int ofs_zc_matched_filter(const void *x, int32_t in_dtype, int64_t n_fra
         else { if (corr_out) OFS_MF8_MODE(OFS_IQ16, true); else OFS_MF8_MODE(OFS_IQ16, false); }
 #undef OFS_MF8_MODE
 #undef OFS_MF8_LAUNCH
-        if (int rc = check_launch("zc_mf8k_kernel")) return rc;
-        OFS_CUDA(cudaFreeAsync(tw8f, stream)); OFS_CUDA(cudaFreeAsync(tw8d, stream)); OFS_CUDA(cudaFreeAsync(G8, stream));
-        OFS_CUDA(cudaFreeAsync(tw, stream)); OFS_CUDA(cudaFreeAsync(G, stream)); OFS_CUDA(cudaFreeAsync(rn, stream));
-        return OFS_OK;
+        return check_launch("zc_mf8k_kernel");
     }
     const int V = ZF - nr + 1;
     const int bpf = (int)((n + nr - 1 + V - 1) / V);
@@ -848,11 +846,7 @@ OFS_API int ofs_zc_matched_filter(const void *x, int32_t in_dtype, int64_t n_fra
     else if (in_dtype == OFS_IQ16) OFS_MF_LAUNCH(float, OFS_IQ16);
     else { set_error("ofs_zc_matched_filter: unknown dtype"); return OFS_EINVAL; }
 #undef OFS_MF_LAUNCH
-    if (int rc = check_launch("zc_mf_kernel")) return rc;
-    OFS_CUDA(cudaFreeAsync(tw, stream));
-    OFS_CUDA(cudaFreeAsync(G, stream));
-    OFS_CUDA(cudaFreeAsync(rn, stream));
-    return OFS_OK;
+    return check_launch("zc_mf_kernel");
 }
 
 OFS_API int ofs_zc_normalize(const void *corr, const void *x, int32_t in_dtype, int64_t n_frames, int64_t n, int32_t nr,
@@ -943,16 +937,17 @@ OFS_API int ofs_zc_freq_metric_fft(const void *x, int32_t in_dtype, int64_t n_fr
     p.blocks_per_item = (p.blocks_per_cap + p.items_per_cap - 1) / p.items_per_cap;      // equal parts: 11 blocks in 2 items are 6 + 5, not 9 + 2
     p.n_items = n_frames * p.items_per_cap;
     const int grid = (int)(p.n_items < slots ? p.n_items : slots);
-    double2 *tw = nullptr, *tw8d = nullptr, *ref = nullptr;
-    float2 *tw8f = nullptr, *Gp = nullptr, *stash = nullptr;
-    double *rn = nullptr;
-    OFS_CUDA(cudaMallocAsync((void **)&tw, (ZF / 2) * (sizeof(double2) + sizeof(float2)), stream));
-    OFS_CUDA(cudaMallocAsync((void **)&tw8d, 256 * sizeof(double2), stream));
-    OFS_CUDA(cudaMallocAsync((void **)&tw8f, 256 * sizeof(float2), stream));
-    OFS_CUDA(cudaMallocAsync((void **)&ref, 2 * (size_t)n_fft * sizeof(double2), stream));
-    OFS_CUDA(cudaMallocAsync((void **)&Gp, 2 * ZF8 * sizeof(float2), stream));
-    OFS_CUDA(cudaMallocAsync((void **)&rn, 2 * sizeof(double), stream));
-    OFS_CUDA(cudaMallocAsync((void **)&stash, (size_t)grid * ZF8 * sizeof(float2), stream));
+    AsyncBuf b_tw, b_tw8d, b_tw8f, b_ref, b_gp, b_rn, b_stash;          // returned to the pool on every exit path
+    OFS_CUDA(b_tw.alloc((ZF / 2) * (sizeof(double2) + sizeof(float2)), stream));
+    OFS_CUDA(b_tw8d.alloc(256 * sizeof(double2), stream));
+    OFS_CUDA(b_tw8f.alloc(256 * sizeof(float2), stream));
+    OFS_CUDA(b_ref.alloc(2 * (size_t)n_fft * sizeof(double2), stream));
+    OFS_CUDA(b_gp.alloc(2 * ZF8 * sizeof(float2), stream));
+    OFS_CUDA(b_rn.alloc(2 * sizeof(double), stream));
+    OFS_CUDA(b_stash.alloc((size_t)grid * ZF8 * sizeof(float2), stream));
+    double2 *tw = b_tw.as<double2>(), *tw8d = b_tw8d.as<double2>(), *ref = b_ref.as<double2>();
+    float2 *tw8f = b_tw8f.as<float2>(), *Gp = b_gp.as<float2>(), *stash = b_stash.as<float2>();
+    double *rn = b_rn.as<double>();
     zc_twiddle_kernel<<<(ZF / 2 + 255) / 256, 256, 0, stream>>>(tw);
     zc_twiddle8_kernel<<<1, 256, 0, stream>>>(tw8f, tw8d);
     zqf_ref_kernel<<<(n_fft + 127) / 128, 128, 0, stream>>>(bins, reinterpret_cast<const float2 *>(templ_c64), nbins, n_fft, ref);
@@ -970,9 +965,5 @@ OFS_API int ofs_zc_freq_metric_fft(const void *x, int32_t in_dtype, int64_t n_fr
     auto kern = in_dtype == OFS_C64 ? zc_freq_fft_kernel<OFS_C64> : zc_freq_fft_kernel<OFS_IQ16>;
     OFS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, ZQF_THREADS, smem, stream>>>(p);
-    if (int rc = check_launch("zc_freq_fft_kernel")) return rc;
-    OFS_CUDA(cudaFreeAsync(tw, stream)); OFS_CUDA(cudaFreeAsync(tw8d, stream)); OFS_CUDA(cudaFreeAsync(tw8f, stream));
-    OFS_CUDA(cudaFreeAsync(ref, stream)); OFS_CUDA(cudaFreeAsync(Gp, stream)); OFS_CUDA(cudaFreeAsync(rn, stream));
-    OFS_CUDA(cudaFreeAsync(stash, stream));
-    return OFS_OK;
+    return check_launch("zc_freq_fft_kernel");
 }

@@ -1,5 +1,7 @@
 // Fused 8192-point overlap-save convolution pipeline (float32) for the Zadoff-Chu matched filter (zc.py:115-126,
-// zc_v2.py:244-271) and the FFT form of zc_freq.compute_frequency_metric (zc_freq.py:62-99).
+// zc_v2.py:244-271), the FFT form of zc_freq.compute_frequency_metric (zc_freq.py:62-99) and -- as 32 independent 256-point
+// transforms -- the block-FFT Park metric (park.py:64-114, park.cu).  Header-only, no barriers inside: the kernels place
+// their own __syncthreads between the stages, so tests/host/conv8k_host_test.cpp can run the same code on the CPU.
 //
 // Same flow graph as fft8k_dif / ifft8k_dit of fft4096.cuh (radix-2 split, then two 4096-point transforms of three radix-16
 // passes), but

@@ -259,7 +259,9 @@ __global__ void park_twiddle_kernel(double2 *tw)         // the table layout of 
     }
 }
 
-template <int DT>
+// MC: h / 128 as a compile-time constant (8 for the scripts' N_FFT = 2048; 0: run-time) -- with it every block index of the
+// frequency-domain products is a constant and the 16 spectra of a position are read into registers once
+template <int DT, int MC>
 __global__ void __launch_bounds__(ZNT, 2) park_fft_kernel(const void *x, int nb, int64_t L, int64_t xfs, int64_t xbs, int h, int64_t n_out,
                                                          int64_t out_stride, float *M, float2 *P, float *E, int tiles_per_frame,
                                                          const double2 *tw)
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(ZNT, 2) park_fft_kernel(const void *x, int nb,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t frame = blockIdx.x / tiles_per_frame;
     const int tile = blockIdx.x % tiles_per_frame;
-    const int m = h / PF_B;
+    const int m = MC ? MC : h / PF_B;
     const int S0 = tile * PF_T;                               // first anti-diagonal block of the tile (even)
     const int64_t D0 = (int64_t)S0 * PF_B;                    // first centre d of the tile (d = h + output index)
     const int I_lo = (S0 - 2 - m) >> 1;                       // first sample block loaded (floor; blocks before the frame are zero)
@@ -313,6 +315,24 @@ __global__ void __launch_bounds__(ZNT, 2) park_fft_kernel(const void *x, int nb,
                 // block s of the first half starts at s * 272 (256 + its padding); the anti-diagonals live in the second half
                 const float2 *xs0 = a + tid + (tid >> 4);
                 float2 *zs0 = a + ZFP + tid + (tid >> 4);
+                if constexpr (MC == 8) {
+                    // S0 is even and I_lo = S0 / 2 - 5: anti-diagonal zs pairs the blocks 4 + zs / 2 - k and 4 + (zs + 1) / 2 + k,
+                    // k = 0 .. 3 -- all compile-time, so the 16 spectra of this position are loaded once (16 LDS instead of 112)
+                    float2 X[PF_NBLK];
+#pragma unroll
+                    for (int sl = 0; sl < PF_NBLK; ++sl) X[sl] = xs0[sl * PF_BS];
+#pragma unroll
+                    for (int zs = 0; zs < PF_NZ; ++zs) {
+                        ParkAcc pa;
+                        pa.zero();
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) pa.mac(X[4 + zs / 2 - k], X[4 + (zs + 1) / 2 + k]);
+                        float2 acc = pa.value();
+                        acc = pk::add(acc, acc);
+                        if (!(zs & 1)) acc = pk::sub(acc, pk::mul(X[4 + zs / 2], X[4 + zs / 2]));
+                        zs0[zs * PF_BS] = __fmul2_rn(acc, make_float2(1.0f / 256.0f, 1.0f / 256.0f));
+                    }
+                } else
                 for (int zs = 0; zs < PF_NZ; ++zs) {
                     // pairs (c_lo - k, c_hi + k), k = 0 .. kmax: J - I = 2 k + (S & 1) <= m - 1; every pair but the diagonal one
                     // (k = 0 of an even S) also stands for its mirror image (J, I):  Z = 2 sum - [S even] X_c^2
@@ -429,7 +449,7 @@ static int launch_park_fft(const ofs_metric_desc *d, const void *x, void *M, voi
     park_twiddle_kernel<<<(ZF / 2 + 255) / 256, 256, 0, st>>>(tw);
     if (int rc = check_launch("park_twiddle_kernel")) return rc;
     const size_t smem = (size_t)ZFP8 * sizeof(float2) + (size_t)PF_NBLK * PF_B * sizeof(float2);
-    auto kern = park_fft_kernel<DT>;
+    auto kern = h == 8 * PF_B ? park_fft_kernel<DT, 8> : park_fft_kernel<DT, 0>;
     OFS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)grid, ZNT, smem, st>>>(x, d->n_branches, d->n_samples, d->x_frame_stride, d->x_branch_stride, h, n_out, d->out_stride,
                                            (float *)M, (float2 *)P, (float *)E, tiles, tw);

@@ -786,9 +786,6 @@ OFS_API int ofs_zc_matched_filter(const void *x, int32_t in_dtype, int64_t n_fra
     double *rn = b_rn.as<double>();
     zc_twiddle_kernel<<<(ZF / 2 + 255) / 256, 256, 0, stream>>>(tw);
     if (int rc = check_launch("zc_twiddle_kernel")) return rc;
-    OFS_CUDA(cudaFuncSetAttribute(zc_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ZFP * sizeof(double2))));
-    zc_spectrum_kernel<<<1, ZNT, ZFP * sizeof(double2), stream>>>((const double2 *)ref_c128, nr, tw, G, rn);
-    if (int rc = check_launch("zc_spectrum_kernel")) return rc;
     const bool dbl = in_dtype == OFS_C128 || out_f64;
     // float32, one branch, captures of several blocks: the 8192-point kernel (75 % useful outputs per block instead of 50 %)
     static const int mf_block = [] { const char *e = getenv("OFS_MF_BLOCK"); return e ? atoi(e) : 8192; }();
@@ -826,6 +823,10 @@ OFS_API int ofs_zc_matched_filter(const void *x, int32_t in_dtype, int64_t n_fra
 #undef OFS_MF8_LAUNCH
         return check_launch("zc_mf8k_kernel");
     }
+    // the 4096-point filter spectrum (only this path needs it: the 8192-point path above has its own)
+    OFS_CUDA(cudaFuncSetAttribute(zc_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ZFP * sizeof(double2))));
+    zc_spectrum_kernel<<<1, ZNT, ZFP * sizeof(double2), stream>>>((const double2 *)ref_c128, nr, tw, G, rn);
+    if (int rc = check_launch("zc_spectrum_kernel")) return rc;
     const int V = ZF - nr + 1;
     const int bpf = (int)((n + nr - 1 + V - 1) / V);
     const int64_t grid = (int64_t)bpf * n_frames;

@@ -390,21 +390,23 @@ __global__ void __launch_bounds__(ZNT, 2) park_fft_kernel(const void *x, int nb,
     const int per = (cnt + ZNT - 1) / ZNT;
     {
         const int k0 = tid * per, k1 = k0 + per < cnt ? k0 + per : cnt;
-        double en[10];                                         // per <= (1536 + 1024) / 256 = 10
+        float en[10];                                          // per <= (1536 + 1024) / 256 = 10; |x|^2 in float32 (exact for int16
+#pragma unroll                                                 // IQ, 6e-8 relative for complex64), summed in float64
+        for (int q = 0; q < 10; ++q) en[q] = 0.f;
+        for (int b = 0; b < nb; ++b) {
+            const In *xr = reinterpret_cast<const In *>(x) + frame * xfs + (int64_t)b * xbs + D0 + k0;
 #pragma unroll
-        for (int q = 0; q < 10; ++q) {
-            en[q] = 0.0;
-            const int64_t j = D0 + k0 + q;
-            if (k0 + q < k1 && j < L)
-                for (int b = 0; b < nb; ++b) {
-                    const In t = (reinterpret_cast<const In *>(x) + frame * xfs + (int64_t)b * xbs)[j];
-                    en[q] += (double)t.x * (double)t.x + (double)t.y * (double)t.y;
+            for (int q = 0; q < 10; ++q)
+                if (k0 + q < k1 && D0 + k0 + q < L) {
+                    const In t = xr[q];
+                    const float tx = (float)t.x, ty = (float)t.y;
+                    en[q] += fmaf(tx, tx, ty * ty);
                 }
         }
         double run = 0.0;
 #pragma unroll
         for (int q = 0; q < 10; ++q)
-            if (k0 + q < k1) { run += en[q]; pre[k0 + q + 1] = run; }
+            if (k0 + q < k1) { run += (double)en[q]; pre[k0 + q + 1] = run; }
         double t = run;
         for (int o = 1; o < 32; o <<= 1) { const double y = shfl_up_f64(t, o); if (lane >= o) t += y; }
         if (lane == 31) wsum[warp] = t;
@@ -427,12 +429,13 @@ __global__ void __launch_bounds__(ZNT, 2) park_fft_kernel(const void *x, int nb,
             xs = pk::add(xs, pk::mul(v, v));
         }
         const float pr = 0.5f * (accP[r].x + xs.x), pi = 0.5f * (accP[r].y + xs.y);
-        const double en = pre[kd + h] - pre[kd];
-        const double ee = en > 1e-12 ? en : 1e-12;
+        const float en = (float)(pre[kd + h] - pre[kd]);
+        const float ee = fmaxf(en, 1e-12f);                    // park.py:111
         const int64_t oi = frame * out_stride + i;
-        if (M) M[oi] = (float)(((double)pr * pr + (double)pi * pi) / (ee * ee));
+        const float re = 1.0f / ee, qr = pr * re, qi = pi * re;  // |P / E|^2: no intermediate leaves the float32 range
+        if (M) M[oi] = fmaf(qr, qr, qi * qi);
         if (P) P[oi] = make_float2(pr, pi);
-        if (E) E[oi] = (float)en;
+        if (E) E[oi] = en;
     }
 }
 

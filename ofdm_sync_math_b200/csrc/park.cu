@@ -147,6 +147,12 @@ __global__ void __launch_bounds__(QNT2) park_kernel_v2(const void *x, int nb, in
         T pr[QO], pi[QO];
 #pragma unroll
         for (int o = 0; o < QO; ++o) pr[o] = pi[o] = (T)0;
+        // float32: the complex multiply-accumulate as two packed FFMA2 on two accumulator pairs per output (ParkAcc below: the
+        // broadcasts and the swizzle are operand modifiers, so no register moves -- the packed loop tried in round 1 built its
+        // operand pairs with moves and was slower); float64 keeps the scalar form
+        float2 pA[QO], pB[QO];
+#pragma unroll
+        for (int o = 0; o < QO; ++o) pA[o] = pB[o] = make_float2(0.f, 0.f);
         for (int k0 = 0; k0 < h; k0 += QK) {
             // a[q] = x[d_0 - k0 - 7 + q], q = 0..14: logical c - k0 - 7 + q = 8 (cslot - k0/8 - 1) + (q + 1)
             // bb[q] = x[d_0 + k0 + q],    q = 0..14: logical c + k0 + q     = 8 (cslot + k0/8) + q
@@ -162,17 +168,29 @@ __global__ void __launch_bounds__(QNT2) park_kernel_v2(const void *x, int nb, in
 #pragma unroll
                 for (int kk = 0; kk < QK; ++kk) {
                     const Cx<T> u = a[o - kk + QK - 1], v = bb[o + kk];
-                    pr[o] = fma(u.x, v.x, pr[o]); pr[o] = fma(-u.y, v.y, pr[o]);
-                    pi[o] = fma(u.x, v.y, pi[o]); pi[o] = fma(u.y, v.x, pi[o]);
+                    if constexpr (sizeof(T) == 4) {
+                        // sum u v = A + (-1, 1) (.) B,  A += u (.) (v.x, v.x),  B += (u.y, u.x) (.) (v.y, v.y)
+                        pA[o] = __ffma2_rn(make_float2(u.x, u.y), make_float2(v.x, v.x), pA[o]);
+                        pB[o] = __ffma2_rn(make_float2(u.y, u.x), make_float2(v.y, v.y), pB[o]);
+                    } else {
+                        pr[o] = fma(u.x, v.x, pr[o]); pr[o] = fma(-u.y, v.y, pr[o]);
+                        pi[o] = fma(u.x, v.y, pi[o]); pi[o] = fma(u.y, v.x, pi[o]);
+                    }
                 }
             }
             if (sizeof(T) == 4 && ((k0 + QK) % 128 == 0)) {   // bounded fp32 error: flush partial sums
 #pragma unroll
-                for (int o = 0; o < QO; ++o) { accr[o] += (double)pr[o]; acci[o] += (double)pi[o]; pr[o] = pi[o] = (T)0; }
+                for (int o = 0; o < QO; ++o) {
+                    accr[o] += (double)(pA[o].x - pB[o].x); acci[o] += (double)(pA[o].y + pB[o].y);
+                    pA[o] = pB[o] = make_float2(0.f, 0.f);
+                }
             }
         }
 #pragma unroll
-        for (int o = 0; o < QO; ++o) { accr[o] += (double)pr[o]; acci[o] += (double)pi[o]; }
+        for (int o = 0; o < QO; ++o) {
+            accr[o] += (double)pr[o] + (double)(pA[o].x - pB[o].x);
+            acci[o] += (double)pi[o] + (double)(pA[o].y + pB[o].y);
+        }
         // E(d) = sum_{k<h} |x[d+k]|^2: direct for the thread's first output (float partials flushed every 128 terms), then slid
         {
             double e0 = 0.0;
